@@ -1,0 +1,11 @@
+"""Public names of the package."""
+from . import _lib
+from ._lib import FlatlandB200Error
+from .batch import BatchedRailEnv
+from .rail_env import AgentView, RailEnv, TrainState, TreeObsForRailEnv
+from .worlds import (draw_schedule, draw_schedule_fast, load_worlds_npz, save_worlds_npz, unique_target_slots,
+                     world_from_reference_env)
+
+__all__ = ["BatchedRailEnv", "RailEnv", "TreeObsForRailEnv", "TrainState", "AgentView", "FlatlandB200Error",
+           "world_from_reference_env", "draw_schedule", "draw_schedule_fast", "load_worlds_npz", "save_worlds_npz",
+           "unique_target_slots", "_lib"]

@@ -1,0 +1,164 @@
+/* flatland_b200.h — C ABI of the B200-native batched Flatland-3 hot path.
+ *
+ * Drop-in boundary.  The reference (RoboEden/flatland-marl) exposes this path through two
+ * duck-typed Python interfaces, `RailEnv.reset/step` (pure Python) and the pybind11 class
+ * `flatland_cutils.TreeObsForRailEnv` (flatland_cutils/src/main.cpp:17-22); neither is a C ABI, so
+ * this header defines the C ABI that sits UNDER Python classes keeping those signatures
+ * (flatland-marl_b200/rail_env.py, tree_obs.py).  Every entry point cites the reference interface
+ * it replaces; citations are relative to the reference repository root.
+ *
+ * Conventions: plain pointers and sizes only (no torch / pybind types); every pointer inside
+ * `FlBatch` and every `d_` argument is a DEVICE pointer owned by the caller; `h_` arguments are
+ * HOST pointers (pinned for async copies); `stream` is a `cudaStream_t` passed as `void*`; the
+ * library never allocates or frees device memory and keeps no global state; return value is 0 or
+ * an `FlStatus` / CUDA error code (see fl_error_string); no exceptions cross the boundary.
+ * Calls on one FlBatch must be serialised by the caller (one stream); different batches are
+ * independent.
+ */
+#ifndef FLATLAND_B200_H
+#define FLATLAND_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FL_ABI_VERSION 1
+
+/* fixed by the reference (solution/impl_config.py:4-21, flatland_cutils/src/tool.h:67-93) */
+#define FL_MAX_NODES 31     /* num_tree_obs_nodes = 1 + 3*10 */
+#define FL_NODE_F 12        /* floats per tree node (treeobs.cpp:562-573) */
+#define FL_ATTR_F 83        /* floats per agent attribute vector (feature_parser.cpp:19-94) */
+#define FL_PRED_DEPTH 500   /* tree_pred_path_depth */
+#define FL_ACTION_ABSENT 255 /* agent key not present in action_dict (rail_env.py:527) */
+#define FL_NO_AGENT 0xFFFFu
+#define FL_DIST_INF 0xFFFFu /* unreachable in the uint16 distance map (np.inf in distance_map.py:66) */
+#define FL_MAX_AGENTS 1024
+
+enum FlStatus {
+    FL_OK = 0,
+    FL_ERR_BAD_ARG = -1,
+    FL_ERR_TOO_MANY_AGENTS = -2,
+    FL_ERR_SMEM = -3
+};
+
+/* per-environment status bits written by fl_step into FlBatch.status */
+#define FL_ST_STEP_AFTER_DONE 1u /* step() on a finished episode: reference raises (rail_env.py:508-509) */
+#define FL_ST_AUTO_RESET 2u      /* the env was reset in place by this call (FL_FLAG_AUTO_RESET) */
+#define FL_ST_BAD_CELL 4u        /* tree walk met a cell with 0 transitions (treeobs.cpp:527-535 throws) */
+
+/* fl_step flags */
+#define FL_FLAG_AUTO_RESET 1u /* a finished env is reset in place (reset(False, False)) instead of stepped */
+
+/* Device-resident state of E lock-step environments of one configuration (same N, H, W).
+ * Struct of arrays; E is the slowest index everywhere.  "rc" arrays hold (row, col) int16 pairs.
+ * Layout rationale: DESIGN.md §3. */
+typedef struct FlBatch {
+    int64_t E, N, H, W;
+    int64_t n_slots;   /* unique-target slots allocated per env (max over envs) */
+    int64_t S;         /* malfunction-schedule rows per env */
+    int64_t ent_cap;   /* capacity of `entries` per env, >= N * (FL_PRED_DEPTH + 1) */
+    int64_t reserved0;
+
+    /* ---- world, static after upload (RailEnv.reset generators stay reference Python) ---- */
+    const uint16_t *grid;      /* [E][H*W] transition bitmask per cell (core/transition_map.py:144) */
+    const int16_t *slot_rc;    /* [E][n_slots][2] target cell of each unique-target slot, (-1,-1) unused */
+    uint16_t *dist;            /* [E][n_slots][H*W][4] distance map, written by fl_distance_map */
+    const int32_t *max_steps;  /* [E] _max_episode_steps */
+    const int16_t *init_rc;    /* [E][N][2] */
+    const int16_t *tgt_rc;     /* [E][N][2] */
+    const uint8_t *init_dir;   /* [E][N] */
+    const uint8_t *max_count;  /* [E][N] int(1/speed)-1 (speed_counter.py:40-42) */
+    const uint16_t *slot;      /* [E][N] index into the env's distance-map slots */
+    const double *speed;       /* [E][N] */
+    const int32_t *earliest;   /* [E][N] earliest_departure */
+    const int32_t *latest;     /* [E][N] latest_arrival */
+    const uint8_t *sched;      /* [E][S][N] pre-drawn malfunction durations (0 = none); row sched_pos % S */
+
+    /* ---- agent state (agent_utils.py:58-105 and step_utils/*) ---- */
+    int16_t *rc;          /* [E][N][2] position, (-1,-1) = None */
+    int16_t *old_rc;      /* [E][N][2] */
+    uint8_t *dir;         /* [E][N] */
+    uint8_t *old_dir;     /* [E][N] 255 = None */
+    uint8_t *state;       /* [E][N] TrainState */
+    uint8_t *ctr;         /* [E][N] speed counter */
+    uint8_t *mal;         /* [E][N] malfunction_down_counter */
+    uint8_t *saved;       /* [E][N] saved action, 0 = None */
+    uint8_t *sig_mal;     /* [E][N] st_signals.in_malfunction of the last step */
+    uint8_t *deadlocked;  /* [E][N] sticky deadlock flag (deadlock_checker.cpp) */
+    uint8_t *done;        /* [E][N] dones[i] */
+    uint16_t *nmal;       /* [E][N] num_malfunctions */
+    int32_t *arrival;     /* [E][N] arrival_time, -1 = None */
+
+    /* ---- environment state ---- */
+    int32_t *elapsed;     /* [E] _elapsed_steps */
+    int32_t *sched_pos;   /* [E] schedule rows consumed so far */
+    uint8_t *done_all;    /* [E] dones["__all__"] */
+    uint32_t *status;     /* [E] FL_ST_* bits, sticky until cleared by the caller */
+    uint32_t *cellinfo;   /* [E][H*W] low 16 bits: agent standing on the cell (FL_NO_AGENT = none);
+                                       high 16 bits: number of off-map agents whose initial cell this is */
+
+    /* ---- per-step observation workspace (rebuilt by every fl_observe) ---- */
+    uint32_t *key_start;  /* [E][W*W + H + 1] CSR offsets of predicted-occupancy entries per cell id c*W+r */
+    uint64_t *entries;    /* [E][ent_cap] predicted-occupancy intervals sorted by cell id */
+} FlBatch;
+
+int fl_abi_version(void);
+size_t fl_batch_sizeof(void);
+const char *fl_error_string(int code);
+
+/* Replaces DistanceMap._compute/_distance_map_walker (flatland/envs/distance_map.py:57-160): one BFS
+ * over (cell, orientation) per unique target slot, writing FlBatch.dist.  Reset-time only. */
+int fl_distance_map(const FlBatch *b, void *stream);
+
+/* Replaces the tail of RailEnv.reset (flatland/envs/rail_env.py:335-347: reset_agents, elapsed=0,
+ * dones cleared) and TreeObsForRailEnv::reset (flatland_cutils/src/treeobs.cpp:22-28: a fresh
+ * DeadlockChecker).  d_env_mask: [E] bytes, non-zero = reset this env; NULL = all. */
+int fl_reset(const FlBatch *b, const uint8_t *d_env_mask, void *stream);
+
+/* Replaces RailEnv.step(action_dict) up to but excluding the observation
+ * (flatland/envs/rail_env.py:501-632, step_utils/*, agent_chains.py MotionCheck).
+ * d_actions [E][N] uint8 (FL_ACTION_ABSENT = key missing); d_rewards [E][N] int32;
+ * d_dones [E][N+1] uint8, last column = "__all__". */
+int fl_step(const FlBatch *b, const uint8_t *d_actions, int32_t *d_rewards, uint8_t *d_dones,
+            uint32_t flags, void *stream);
+
+/* Replaces TreeObsForRailEnv::get_many + get_properties (flatland_cutils/src/treeobs.cpp:30-108,
+ * 612-640; loader.cpp:221-327; predictions.cpp; deadlock_checker.cpp; feature_parser.cpp), output in
+ * the policy's input layout (solution/plfActor.py:48-74):
+ *   d_agent_attr [E][N][83] f32, d_forest [E][N][31][12] f32, d_adjacency [E][N][30][3] i32,
+ *   d_node_order [E][N][31] i32, d_edge_order [E][N][30] i32, d_valid_actions [E][N][5] u8,
+ *   d_dist_target [E][N] f32 (inf = unreachable).  `deadlocked` is read from FlBatch.deadlocked. */
+int fl_observe(const FlBatch *b, float *d_agent_attr, float *d_forest, int32_t *d_adjacency,
+               int32_t *d_node_order, int32_t *d_edge_order, uint8_t *d_valid_actions,
+               float *d_dist_target, void *stream);
+
+/* One env.step as the reference's caller sees it (solution/eval_env.py:108-114) with HOST buffers:
+ * copies h_actions to d_actions, runs fl_step + fl_observe, copies rewards, dones and every
+ * observation tensor back to the h_ buffers (any h_ output may be NULL to leave it on the device).
+ * All work is enqueued on `stream`; the caller synchronises. */
+typedef struct FlObsBuffers {
+    float *agent_attr;
+    float *forest;
+    int32_t *adjacency;
+    int32_t *node_order;
+    int32_t *edge_order;
+    uint8_t *valid_actions;
+    float *dist_target;
+    int32_t *rewards;
+    uint8_t *dones;
+} FlObsBuffers;
+
+int fl_step_observe_host(const FlBatch *b, const uint8_t *h_actions, uint8_t *d_actions,
+                         const FlObsBuffers *d_out, const FlObsBuffers *h_out, uint32_t flags,
+                         void *stream);
+
+/* Number of kernel launches issued by this library since load (bench.py reports it as gpu_launches). */
+uint64_t fl_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

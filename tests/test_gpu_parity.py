@@ -1,0 +1,189 @@
+"""GPU parity tests proper: the CUDA path (through the C ABI, via BatchedRailEnv) against the C oracle
+and the golden vectors of the unmodified reference, on identical worlds, actions and malfunction
+schedules.  Integer fields (positions, directions, states, counters, rewards, dones, adjacency,
+orders, valid actions, deadlocks, distance maps) must match bit-exactly; float features to
+rtol 1e-6 (BASELINE.json north_star), and in practice bit-exactly as well.
+"""
+import numpy as np
+import pytest
+
+from conftest import golden_names
+
+pytestmark = pytest.mark.gpu
+
+STATE_KEYS = ["pos", "dir", "state", "ctr", "mal", "nmal", "saved", "arrival", "old_pos", "old_dir", "sig_mal"]
+INT_OBS = ["adjacency", "node_order", "edge_order", "valid_actions"]
+FLOAT_OBS = ["attr", "forest", "dist_target"]
+RTOL = 1e-6
+
+
+def _first_bad(a, b):
+    bad = np.argwhere(np.asarray(a) != np.asarray(b))
+    return None if len(bad) == 0 else tuple(int(x) for x in bad[0])
+
+
+def assert_same(got, want, what):
+    got, want = np.asarray(got), np.asarray(want)
+    assert got.shape == want.shape, "%s: shape %s vs %s" % (what, got.shape, want.shape)
+    if got.dtype.kind == "f":
+        ok = np.isclose(got, want, rtol=RTOL, atol=0, equal_nan=True) | (got == want)
+        if not ok.all():
+            idx = tuple(int(x) for x in np.argwhere(~ok)[0])
+            raise AssertionError("%s: first float mismatch at %s: got %r want %r (%d bad)" %
+                                 (what, idx, got[idx], want[idx], int((~ok).sum())))
+    else:
+        idx = _first_bad(got, want)
+        if idx is not None:
+            raise AssertionError("%s: first mismatch at %s: got %r want %r (%d bad)" %
+                                 (what, idx, got[idx], want[idx], int((got != want).sum())))
+
+
+def cuda_obs_numpy(batch, e):
+    o = {k: v[e].cpu().numpy() for k, v in batch.obs.items()}
+    o["attr"] = o.pop("agent_attr")
+    o["deadlocked"] = batch.t["deadlocked"][e].cpu().numpy()
+    return o
+
+
+def compare_obs(batch, e, oracle_obs, what):
+    o = cuda_obs_numpy(batch, e)
+    for k in INT_OBS + ["deadlocked"]:
+        assert_same(o[k], oracle_obs[k], "%s %s" % (what, k))
+    for k in FLOAT_OBS:
+        assert_same(o[k], oracle_obs[k], "%s %s" % (what, k))
+
+
+def compare_state(batch, e, oracle_state, what):
+    s = batch.state_numpy(e)
+    for k in STATE_KEYS:
+        assert_same(s[k], oracle_state[k], "%s %s" % (what, k))
+
+
+def run_against_oracle(worlds, actions, scheds, n_steps, check_every=1):
+    """Steps E envs on the GPU and E oracle envs in lock-step; compares everything."""
+    import torch
+    import flatland_marl_b200 as fb
+    from oracle import oracle as orc
+    ws = []
+    for w, s in zip(worlds, scheds):
+        w = dict(w)
+        w["sched"] = s
+        ws.append(w)
+    batch = fb.BatchedRailEnv(ws, sched_rows=max(len(s) for s in scheds))
+    envs = [orc.OracleEnv(w) for w in ws]
+    batch.reset()
+    for e, env in enumerate(envs):
+        env.reset()
+        assert_same(batch.dist_numpy(e)[: env.dist_u16().shape[0]], env.dist_u16(), "env %d distance map" % e)
+        compare_state(batch, e, env.state(), "env %d reset" % e)
+        compare_obs(batch, e, env.obs(), "env %d reset obs" % e)
+    alive = [True] * len(envs)
+    for t in range(n_steps):
+        act = np.stack([a[t] if t < len(a) else np.zeros_like(a[0]) for a in actions])
+        _, rew, don = batch.step(torch.from_numpy(act).to(batch.device))
+        rew, don = rew.cpu().numpy(), don.cpu().numpy()
+        for e, env in enumerate(envs):
+            if not alive[e]:
+                continue
+            orew, odon = env.step(act[e], scheds[e][t % len(scheds[e])])
+            what = "env %d step %d" % (e, t + 1)
+            assert_same(rew[e], orew, what + " rewards")
+            assert_same(don[e], odon, what + " dones")
+            if t % check_every == 0 or odon[-1]:
+                compare_state(batch, e, env.state(), what)
+                compare_obs(batch, e, env.obs(), what + " obs")
+            if odon[-1]:
+                alive[e] = False
+        if not any(alive):
+            break
+    return batch
+
+
+@pytest.mark.parametrize("name", golden_names())
+def test_cuda_matches_golden_and_oracle(golden, name):
+    """Same world, actions and schedule as the reference run that produced the fixture."""
+    g = golden(name)
+    n_steps = int(g["n_steps"])
+    # env 0 replays the golden action stream; env 1 a different stream on the same world
+    rng = np.random.RandomState(123)
+    other = rng.randint(0, 5, size=g["actions"].shape).astype(np.uint8)
+    batch = run_against_oracle([g, g], [g["actions"], other], [g["sched"], g["sched"]], n_steps,
+                               check_every=1 if int(g["N"]) <= 80 else 4)
+    # and directly against what the reference recorded at the final step
+    final = {k: g["tr_" + k][n_steps] for k in STATE_KEYS}
+    s = batch.state_numpy(0)
+    for k in STATE_KEYS:
+        assert_same(s[k], final[k], "%s final reference %s" % (name, k))
+    assert_same(batch.dist_numpy(0)[: g["dist"].shape[0]], g["dist"], name + " reference distance map")
+
+
+def test_step_after_done_and_auto_reset(golden):
+    import torch
+    import flatland_marl_b200 as fb
+    g = golden("t00_l1_greedy")
+    w = dict(g)
+    n_steps = int(g["n_steps"])
+    batch = fb.BatchedRailEnv([w], sched_rows=n_steps)
+    batch.reset()
+    for t in range(n_steps):
+        batch.step(torch.from_numpy(g["actions"][t][None]).to(batch.device))
+    assert int(batch.t["done_all"][0]) == 1
+    batch.step_only(torch.from_numpy(g["actions"][0][None]).to(batch.device))
+    assert int(batch.t["status"][0]) & fb._lib.ST_STEP_AFTER_DONE
+    # reference-API facade raises like rail_env.py:508-509
+    env = fb.RailEnv.from_world(w)
+    env.reset()
+    for t in range(n_steps):
+        acts = {i: int(a) for i, a in enumerate(g["actions"][t]) if a != 255}
+        obs, rew, done, info = env.step(acts)
+    assert done["__all__"]
+    assert [rew[i] for i in range(int(g["N"]))] == list(g["rewards"][n_steps - 1])
+    with pytest.raises(Exception):
+        env.step({})
+    # auto reset: the finished env starts a new episode in place
+    batch2 = fb.BatchedRailEnv([w], sched_rows=n_steps, auto_reset=True)
+    batch2.reset()
+    for t in range(n_steps + 1):
+        batch2.step(torch.from_numpy(g["actions"][t % n_steps][None]).to(batch2.device))
+    assert int(batch2.t["elapsed"][0]) == 0 and int(batch2.t["done_all"][0]) == 0
+    assert int(batch2.t["status"][0]) & fb._lib.ST_AUTO_RESET
+    assert (batch2.t["state"][0].cpu().numpy() == 0).all()
+
+
+def test_facade_matches_reference_api_shapes(golden):
+    """The reference-API facade returns what flatland_cutils returns: nested lists with the shapes
+    (N,83) (N,31,12) (N,30,3) (N,31) (N,30) and the get_properties triple (treeobs.cpp:612-640)."""
+    import flatland_marl_b200 as fb
+    g = golden("t00_l0_random")
+    env = fb.RailEnv.from_world(dict(g))
+    (attr, (forest, adj, norder, eorder)), info = env.reset()
+    n = int(g["N"])
+    assert np.array(attr).shape == (n, 83) and np.array(forest).shape == (n, 31, 12)
+    assert np.array(adj).shape == (n, 30, 3) and np.array(norder).shape == (n, 31) and np.array(eorder).shape == (n, 30)
+    np.testing.assert_array_equal(np.array(attr, dtype=np.float32), g["obs0_attr"])
+    np.testing.assert_array_equal(np.array(forest, dtype=np.float32), g["obs0_forest"])
+    np.testing.assert_array_equal(np.array(adj), g["obs0_adjacency"])
+    cfg, props, valid = env.obs_builder.get_properties()
+    assert cfg == {"curr_step": 0, "n_agents": n, "max_timesteps": int(g["T"]), "height": int(g["H"]), "width": int(g["W"])}
+    assert set(props) == {"dist_target", "deadlocked", "ready_not_depart", "earliest_departure", "latest_arrival", "speed"}
+    np.testing.assert_array_equal(np.array(valid, dtype=np.uint8), g["obs0_valid_actions"])
+    assert set(info) == {"action_required", "malfunction", "speed", "state"}
+    assert not any(env.action_required(a) for a in env.agents)  # everyone is WAITING at reset
+
+
+def test_host_buffer_step_matches_device_step(golden):
+    """fl_step_observe_host (pinned host in/out) gives the same bytes as the device-resident path."""
+    import torch
+    import flatland_marl_b200 as fb
+    g = golden("t02_l1_greedy")
+    a = fb.BatchedRailEnv([dict(g)] * 3, sched_rows=int(g["n_steps"]))
+    b = fb.BatchedRailEnv([dict(g)] * 3, sched_rows=int(g["n_steps"]))
+    a.reset(); b.reset()
+    for t in range(40):
+        act = np.repeat(g["actions"][t][None], 3, 0)
+        a.step(torch.from_numpy(act).to(a.device))
+        h = b.step_host(act)
+        for k in a.obs:
+            np.testing.assert_array_equal(h[k].numpy(), a.obs[k].cpu().numpy(), err_msg="%s step %d" % (k, t))
+        np.testing.assert_array_equal(h["rewards"].numpy(), a.rewards.cpu().numpy())
+        np.testing.assert_array_equal(h["dones"].numpy(), a.dones.cpu().numpy())
