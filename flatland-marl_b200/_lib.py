@@ -16,7 +16,7 @@ _PTR = ["grid", "slot_rc", "dist", "max_steps", "init_rc", "tgt_rc", "init_dir",
         "earliest", "latest", "sched",
         "rc", "old_rc", "dir", "old_dir", "state", "ctr", "mal", "saved", "sig_mal", "deadlocked", "done", "nmal",
         "arrival",
-        "elapsed", "sched_pos", "done_all", "status", "cellinfo",
+        "elapsed", "sched_pos", "done_all", "status", "cellinfo", "occ_cell",
         "key_start", "entries"]
 
 

@@ -84,10 +84,9 @@ DEVI int fsm(int s, bool in_mal, bool mal_done, bool edr, bool stop, bool valid_
 // EnvAgent.reset for every agent of env e + cleared maps (agent_utils.py:90-105, rail_env.py:335-344,
 // treeobs.cpp:22-28).  Called by all threads of a CTA.
 DEVI void reset_env(const FlBatch &b, int e, bool rewind_schedule) {
-    const int N = (int)b.N, HW = (int)(b.H * b.W), W = (int)b.W;
+    const int N = (int)b.N, HW = (int)(b.H * b.W);
     uint32_t *ci = b.cellinfo + (size_t)e * HW;
-    for (int k = threadIdx.x; k < HW; k += blockDim.x) ci[k] = FL_NO_AGENT;
-    __syncthreads();
+    for (int k = threadIdx.x; k < HW; k += blockDim.x) ci[k] = 0;
     for (int i = threadIdx.x; i < N; i += blockDim.x) {
         const size_t ea = (size_t)e * N + i;
         b.rc[2 * ea] = -1; b.rc[2 * ea + 1] = -1;
@@ -95,7 +94,7 @@ DEVI void reset_env(const FlBatch &b, int e, bool rewind_schedule) {
         b.dir[ea] = b.init_dir[ea]; b.old_dir[ea] = 255;
         b.state[ea] = WAITING; b.ctr[ea] = 0; b.mal[ea] = 0; b.saved[ea] = 0; b.sig_mal[ea] = 0;
         b.deadlocked[ea] = 0; b.done[ea] = 0; b.nmal[ea] = 0; b.arrival[ea] = -1;
-        atomicAdd(&ci[b.init_rc[2 * ea] * W + b.init_rc[2 * ea + 1]], 0x10000u);
+        b.occ_cell[ea] = -1;
     }
     if (threadIdx.x == 0) {
         b.elapsed[e] = 0; b.done_all[e] = 0;
@@ -119,10 +118,9 @@ k_step(FlBatch b, const uint8_t *__restrict__ actions, int32_t *__restrict__ rew
     const int i = threadIdx.x;
     const bool act = i < N;
     extern __shared__ int sm[];
-    int *s_cur = sm, *s_nxt = sm + N, *s_occn = sm + 2 * N, *s_seed = sm + 3 * N;
+    int *s_cur = sm, *s_nxt = sm + N, *s_rep = sm + 2 * N, *s_blk = sm + 3 * N;
     const size_t ea = (size_t)e * N + (act ? i : 0);
     const uint16_t *__restrict__ g = b.grid + (size_t)e * HW;
-    uint32_t *ci = b.cellinfo + (size_t)e * HW;
 
     const bool was_done = b.done_all[e] != 0;
     const int elapsed = b.elapsed[e] + 1;
@@ -177,38 +175,44 @@ k_step(FlBatch b, const uint8_t *__restrict__ actions, int32_t *__restrict__ rew
         } else { nr = r; nc = c; nd = d; }
         cur_id = r < 0 ? -1 - i : r * W + c;       // agent_chains.py:28-33: off-map = private node
         nxt_id = nr < 0 ? -1 - i : nr * W + nc;
-        s_cur[i] = cur_id; s_nxt[i] = nxt_id;
+        s_cur[i] = cur_id; s_nxt[i] = nxt_id; s_blk[i] = 0;
     }
     __syncthreads();
 
-    // ---- MotionCheck (agent_chains.py:151-236) as the least fixpoint of
-    //      blocked = stop | swap | loser | blocked[occupant(next)]    -----------
-    bool seed = true;
-    int occn = -1;
+    // ---- MotionCheck (agent_chains.py:151-236) as a least fixpoint over CELL NODES:
+    //        blocked(X) = some train on X stays | swaps | loses a contended cell | heads for a blocked node
+    //      Several trains can share a cell (MALFUNCTION_OFF_MAP + STOP enters the map unchecked,
+    //      state_machine.py:41-42); a node's verdict is shared by all of them and its "agent" attribute is
+    //      the last one added, i.e. the highest handle (agent_chains.py:33) — its representative here.
+    int rep_cur = i, rep_nxt = -1;
+    bool sw = false;
     if (act) {
-        const bool stop = nxt_id == cur_id;
-        bool loser = false;
         for (int k = 0; k < N; k++) {              // shared-memory broadcasts, no bank conflicts
             const int ck = s_cur[k], nk = s_nxt[k];
-            if (ck == nxt_id) occn = k;
-            if (k < i && nk == nxt_id && nk != ck) loser = true;
+            if (ck == cur_id) rep_cur = max(rep_cur, k);
+            if (ck == nxt_id) { rep_nxt = max(rep_nxt, k); if (nk == cur_id && nxt_id != cur_id) sw = true; }
         }
-        const bool swap = !stop && occn >= 0 && occn != i && s_nxt[occn] == cur_id;
-        seed = stop || swap || loser;
-        s_seed[i] = seed; s_occn[i] = occn;
+        s_rep[i] = rep_cur;
     }
     __syncthreads();
-    bool blocked = seed;
-    if (act && !seed) {                            // follow the chain of occupants until a seed / a free cell
-        int k = occn, hops = 0;
-        while (k >= 0 && hops < N) {
-            if (s_seed[k]) { blocked = true; break; }
-            k = s_occn[k]; hops++;
-        }
+    if (act) {
+        bool loser = false;                        // another node wants my target and its agent index is lower
+        if (nxt_id != cur_id)
+            for (int k = 0; k < N; k++) {
+                const int ck = s_cur[k];
+                if (s_nxt[k] == nxt_id && ck != cur_id && ck != nxt_id && s_rep[k] < rep_cur) loser = true;
+            }
+        if (nxt_id == cur_id || sw || loser) s_blk[rep_cur] = 1;
     }
+    __syncthreads();
+    while (true) {                                 // propagate along chains until nothing changes
+        int changed = 0;
+        if (act && nxt_id != cur_id && rep_nxt >= 0 && !s_blk[rep_cur] && s_blk[rep_nxt]) { s_blk[rep_cur] = 1; changed = 1; }
+        if (!__syncthreads_or(changed)) break;
+    }
+    const bool blocked = act ? s_blk[rep_cur] != 0 : true;
 
     // ---- loop B (rail_env.py:574-627) --------------------------------------------------------
-    bool entered = false;
     if (act) {
         const bool exit_ = ctr == maxc;
         bool allowed = (mal > 0 ? false : !blocked) || (st == STOPPED && !exit_);
@@ -220,7 +224,7 @@ k_step(FlBatch b, const uint8_t *__restrict__ actions, int32_t *__restrict__ rew
         st = fsm(prev, in_mal, mal_done, edr, stop_given, vm, reached, conflict);
         allowed = allowed && st != DONE;
         if (on_map(st)) {
-            if (off_map(prev)) { r = ir; c = ic; d = idir; entered = true; }
+            if (off_map(prev)) { r = ir; c = ic; d = idir; }
             else if (allowed && exit_) {
                 r = nr; c = nc; d = nd;
                 if (r == tr && c == tc) st = DONE;                              // update_if_reached
@@ -233,15 +237,6 @@ k_step(FlBatch b, const uint8_t *__restrict__ actions, int32_t *__restrict__ rew
         if (ctr == 0 && r >= 0) saved = 0;                                      // rail_env.py:626-627
     }
     const int all_done = __syncthreads_and(!act || st == DONE);
-    // occupancy map: every departure first, then every arrival
-    const bool moved = act && (r != old_r || c != old_c);
-    if (moved && old_r >= 0) atomicOr(&ci[old_r * W + old_c], (uint32_t)FL_NO_AGENT);
-    __syncthreads();
-    if (moved && r >= 0) {
-        atomicAnd(&ci[r * W + c], 0xFFFF0000u | (uint32_t)i);
-        if (entered) atomicSub(&ci[r * W + c], 0x10000u);
-    }
-
     // ---- end of episode (rail_env.py:476-491, 397-423; agent_utils.py:129-147) ---------------
     const bool ended = all_done || elapsed >= b.max_steps[e];
     if (act) {
@@ -392,8 +387,7 @@ DEVI void update_deadlocks(const DeadlockScratch &x, const uint32_t *ci, int N, 
                     const int rr = hr + d_row(dd), cc = hc + d_col(dd);
                     opp = -1;
                     if (rr >= 0 && cc >= 0 && rr < H && cc < W) {
-                        const unsigned o = ci[rr * W + cc] & 0xFFFFu;
-                        if (o != FL_NO_AGENT) opp = (int)o;
+                        opp = (int)(ci[rr * W + cc] >> 21) - 1;
                     }
                     if (opp < 0) { x.checked[h] = 2; popped = true; break; }           // road is free
                     if (x.dl[opp]) { x.stk_d[f]++; continue; }                          // road is blocked
@@ -450,11 +444,13 @@ k_prep(FlBatch b, uint8_t *__restrict__ valid_actions, float *__restrict__ dist_
     uint8_t *s_checked = reinterpret_cast<uint8_t *>(s_stk_opp + N);   // [N] x6
     uint8_t *s_ndep = s_checked + N, *s_dl = s_ndep + N, *s_ct = s_dl + N, *s_stk_d = s_ct + N,
             *s_stk_phase = s_stk_d + N;
+    int *s_initcell = reinterpret_cast<int *>(s_stk_phase + N + ((4 - (6 * N) % 4) % 4));  // [N]
     const uint16_t *__restrict__ g = b.grid + (size_t)e * HW;
-    const uint32_t *ci = b.cellinfo + (size_t)e * HW;
+    uint32_t *ci = b.cellinfo + (size_t)e * HW;
     const size_t ea = (size_t)e * N + (act ? i : 0);
 
     for (int k = i; k <= K; k += nt) s_cnt[k] = 0;
+    if (act) { const int oc = b.occ_cell[ea]; if (oc >= 0) ci[oc] = 0; }   // forget the previous step's occupancy
     int r = -1, c = -1, d = 0, st = DONE, vr = 0, vc = 0, tr = 0, tc = 0, tpc = 1;
     const uint16_t *dm = nullptr;
     if (act) {
@@ -467,6 +463,7 @@ k_prep(FlBatch b, uint8_t *__restrict__ valid_actions, float *__restrict__ dist_
         dm = b.dist + ((size_t)e * b.n_slots + b.slot[ea]) * HW * 4;
         tpc = (int)(1.0f / (float)b.speed[ea]);                        // predictions.cpp:184
         s_cellid[i] = on_map(st) ? r * W + c : -1;
+        s_initcell[i] = off_map(st) ? ip.x * W + ip.y : -1;
         s_ct[i] = on_map(st) ? (uint8_t)nibble(__ldg(g + r * W + c), d) : 0;
         s_dl[i] = b.deadlocked[ea]; s_checked[i] = 0; s_ndep[i] = 0;
         uint8_t va[5];
@@ -480,6 +477,20 @@ k_prep(FlBatch b, uint8_t *__restrict__ valid_actions, float *__restrict__ dist_
             dt = dv == FL_DIST_INF ? INFINITY : (float)dv;
         }
         dist_target[ea] = dt;
+    }
+    __syncthreads();
+    // occupancy map (treeobs.cpp:67-92, deadlock_checker.cpp:15-20): per cell the HIGHEST handle standing on
+    // it (std::map assignment in handle order = last writer), its direction and malfunction flag, and the
+    // number of off-map trains whose initial cell it is.  handle+1 sits in the top bits so atomicMax picks it.
+    if (act) {
+        int cellid = s_cellid[i];
+        if (cellid >= 0) {
+            int cnt = 0;
+            for (int k = 0; k < N; k++) cnt += s_initcell[k] == cellid;
+            atomicMax(&ci[cellid], ((uint32_t)(i + 1) << 21) | ((uint32_t)cnt << 11) | ((uint32_t)d << 9) |
+                                       ((uint32_t)(b.mal[ea] != 0) << 8));
+        }
+        b.occ_cell[ea] = cellid;
     }
     __syncthreads();
     if (i == N) {                                  // the spare thread (block has at least N+1 threads)
@@ -634,15 +645,15 @@ k_tree(FlBatch b, const uint8_t *__restrict__ valid_actions, const float *__rest
             const int cell = r * W + c;
             const uint32_t cinfo = ci[cell];
             const unsigned gc = __ldg(g + cell);
-            const unsigned occ = cinfo & 0xFFFFu;
-            if (occ != FL_NO_AGENT) {              // treeobs.cpp:322-360 (the observer itself counts too)
-                const size_t oa = (size_t)e * N + occ;
+            if (cinfo) {                           // treeobs.cpp:322-360 (the observer itself counts too)
                 if (tot < other_agent) other_agent = tot;
-                malf = max(malf, (int)(b.mal[oa] != 0));
-                const int cnt = (int)(cinfo >> 16);
+                malf = max(malf, (int)((cinfo >> 8) & 1u));
+                const int cnt = (int)((cinfo >> 11) & 1023u);
                 rtdn += cnt ? cnt - 1 : 0;
-                if ((int)b.dir[oa] == d) { same++; min_speed = fminf(min_speed, (float)b.speed[oa]); }
-                else opp++;
+                if ((int)((cinfo >> 9) & 3u) == d) {
+                    same++;
+                    min_speed = fminf(min_speed, (float)b.speed[(size_t)e * N + (cinfo >> 21) - 1]);
+                } else opp++;
             }
             const int nb = nibble(gc, d);
             int total = __popc(gc);
@@ -888,7 +899,7 @@ int check_batch(const FlBatch *b) {
 
 size_t prep_smem_bytes(const FlBatch *b, int nt) {
     const size_t K = (size_t)(b->W * b->W + b->H), N = (size_t)b->N;
-    return (K + 1) * 4 + (size_t)nt * 4 + N * 4 + 4 * N * 2 + 2 * N * 2 + 6 * N + 16;
+    return (K + 1) * 4 + (size_t)nt * 4 + N * 4 + 4 * N * 2 + 2 * N * 2 + 6 * N + 4 + N * 4 + 16;
 }
 
 int finish(cudaError_t launch_err) { return launch_err == cudaSuccess ? FL_OK : (int)launch_err; }

@@ -10,7 +10,7 @@
  * Conventions: plain pointers and sizes only (no torch / pybind types); every pointer inside
  * `FlBatch` and every `d_` argument is a DEVICE pointer owned by the caller; `h_` arguments are
  * HOST pointers (pinned for async copies); `stream` is a `cudaStream_t` passed as `void*`; the
- * library never allocates or frees device memory and keeps no global state; return value is 0 or
+ * library never allocates or frees device memory and keeps no global state except a launch counter; return value is 0 or
  * an `FlStatus` / CUDA error code (see fl_error_string); no exceptions cross the boundary.
  * Calls on one FlBatch must be serialised by the caller (one stream); different batches are
  * independent.
@@ -97,8 +97,10 @@ typedef struct FlBatch {
     int32_t *sched_pos;   /* [E] schedule rows consumed so far */
     uint8_t *done_all;    /* [E] dones["__all__"] */
     uint32_t *status;     /* [E] FL_ST_* bits, sticky until cleared by the caller */
-    uint32_t *cellinfo;   /* [E][H*W] low 16 bits: agent standing on the cell (FL_NO_AGENT = none);
-                                       high 16 bits: number of off-map agents whose initial cell this is */
+    uint32_t *cellinfo;   /* [E][H*W] occupancy map rebuilt by fl_observe, 0 = empty cell, else
+                                       bits 31..21 highest handle on the cell + 1, 20..11 number of off-map
+                                       agents whose initial cell this is, 10..9 direction, 8 malfunctioning */
+    int32_t *occ_cell;    /* [E][N] cell each agent was entered under in cellinfo, -1 = none */
 
     /* ---- per-step observation workspace (rebuilt by every fl_observe) ---- */
     uint32_t *key_start;  /* [E][W*W + H + 1] CSR offsets of predicted-occupancy entries per cell id c*W+r */

@@ -220,20 +220,29 @@ static int preprocess_action(const FoEnv *e, int i, int raw) {
 /* ------------------------------------------------------------------------------------------- */
 enum { COL_NONE = 0, COL_RED = 1, COL_PURPLE = 2, COL_OTHER = 3 };
 
+/* The motion graph: nodes are cells in insertion order; every agent contributes one edge
+ * cur -> next.  Several agents can stand on one cell (the reference puts a train on the map without
+ * asking MotionCheck when MALFUNCTION_OFF_MAP meets a STOP action, state_machine.py:41-42), so a node
+ * can have several out-edges; its "agent" attribute is the last agent added (agent_chains.py:33). */
 typedef struct {
     int n_nodes, n_agents;
     int *nr, *nc;      /* node key (row, col) in insertion order */
     int *agent;        /* agent attribute of a node, -1 if none */
-    int *succ;         /* each source node has exactly one out-edge (latest add_edge wins is n/a) */
+    int *first_succ;   /* first out-edge added to the node (what G.successors(n).__next__() yields) */
     int *color;
-    int *cur_node, *nxt_node;
+    int *cur_node, *nxt_node; /* per agent */
 } MGraph;
 
 static int mg_node(MGraph *g, int r, int c) {
     for (int i = 0; i < g->n_nodes; i++) if (g->nr[i] == r && g->nc[i] == c) return i;
     int i = g->n_nodes++;
-    g->nr[i] = r; g->nc[i] = c; g->agent[i] = -1; g->succ[i] = -1; g->color[i] = COL_NONE;
+    g->nr[i] = r; g->nc[i] = c; g->agent[i] = -1; g->first_succ[i] = -1; g->color[i] = COL_NONE;
     return i;
+}
+
+static int mg_edge(const MGraph *g, int u, int v) {
+    for (int k = 0; k < g->n_agents; k++) if (g->cur_node[k] == u && g->nxt_node[k] == v) return 1;
+    return 0;
 }
 
 /* marks every node from which `v` is reachable (v included): dfs over the reversed graph */
@@ -244,8 +253,10 @@ static void mg_reverse_closure(const MGraph *g, int v, uint8_t *mark) {
     while (sp) {
         int u = stack[--sp];
         mark[u] = 1;
-        for (int w = 0; w < g->n_nodes; w++)
-            if (g->succ[w] == u && !seen[w]) { seen[w] = 1; stack[sp++] = w; }
+        for (int k = 0; k < g->n_agents; k++) {
+            int w = g->cur_node[k];
+            if (g->nxt_node[k] == u && !seen[w]) { seen[w] = 1; stack[sp++] = w; }
+        }
     }
     free(stack); free(seen);
 }
@@ -261,28 +272,29 @@ void fo_motion_check(int n, const int16_t *cur, const int16_t *nxt, uint8_t *can
     MGraph g;
     int cap = 2 * n + 2;
     g.n_nodes = 0; g.n_agents = n;
-    g.nr = IALLOC(cap); g.nc = IALLOC(cap); g.agent = IALLOC(cap); g.succ = IALLOC(cap); g.color = IALLOC(cap);
+    g.nr = IALLOC(cap); g.nc = IALLOC(cap); g.agent = IALLOC(cap); g.first_succ = IALLOC(cap); g.color = IALLOC(cap);
     g.cur_node = IALLOC(n); g.nxt_node = IALLOC(n);
+    for (int i = 0; i < n; i++) { g.cur_node[i] = g.nxt_node[i] = -1; }
     for (int i = 0; i < n; i++) {                       /* addAgent, agent_chains.py:19-37 */
         int u = mg_node(&g, cur[2 * i], cur[2 * i + 1]);
         g.agent[u] = i;
         int v = mg_node(&g, nxt[2 * i], nxt[2 * i + 1]);
-        g.succ[u] = v;
+        if (g.first_succ[u] < 0) g.first_succ[u] = v;
         g.cur_node[i] = u; g.nxt_node[i] = v;
     }
     int nn = g.n_nodes;
     uint8_t *stops = calloc(nn, 1), *swaps = calloc(nn, 1), *blocked = calloc(nn, 1);
-    for (int u = 0; u < nn; u++) if (g.succ[u] == u) stops[u] = 1;           /* find_stops2 */
-    for (int u = 0; u < nn; u++) {                                             /* find_swaps */
-        int v = g.succ[u];
-        if (v >= 0 && v != u && g.succ[v] == u) swaps[u] = 1;
+    for (int u = 0; u < nn; u++) if (mg_edge(&g, u, u)) stops[u] = 1;          /* find_stops2 */
+    for (int k = 0; k < n; k++) {                                               /* find_swaps: 2-cycles */
+        int u = g.cur_node[k], v = g.nxt_node[k];
+        if (u != v && mg_edge(&g, v, u)) { swaps[u] = 1; swaps[v] = 1; }
     }
     for (int u = 0; u < nn; u++) if (swaps[u]) mg_block_preds(&g, u, COL_PURPLE);
     for (int u = 0; u < nn; u++) if (stops[u]) mg_reverse_closure(&g, u, blocked); /* find_stop_preds */
-    int *preds = IALLOC(nn);
+    int *preds = IALLOC(nn + 1);
     for (int v = 0; v < nn; v++) {                      /* G.pred.items() in node insertion order */
         int np = 0;
-        for (int w = 0; w < nn; w++) if (g.succ[w] == v) preds[np++] = w;
+        for (int w = 0; w < nn; w++) if (mg_edge(&g, w, v)) preds[np++] = w;
         if (blocked[v]) {
             g.color[v] = COL_RED;
         } else if (np > 1) {
@@ -296,10 +308,10 @@ void fo_motion_check(int n, const int16_t *cur, const int16_t *nxt, uint8_t *can
     for (int i = 0; i < n; i++) {                       /* check_motion, agent_chains.py:204-236 */
         int u = g.cur_node[i];
         if (g.color[u] == COL_RED || g.color[u] == COL_PURPLE) can_move[i] = 0;
-        else can_move[i] = (g.succ[u] != u);
+        else can_move[i] = (g.first_succ[u] != u);
     }
     free(preds); free(stops); free(swaps); free(blocked);
-    free(g.nr); free(g.nc); free(g.agent); free(g.succ); free(g.color); free(g.cur_node); free(g.nxt_node);
+    free(g.nr); free(g.nc); free(g.agent); free(g.first_succ); free(g.color); free(g.cur_node); free(g.nxt_node);
 }
 
 /* ------------------------------------------------------------------------------------------- */

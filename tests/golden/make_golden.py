@@ -171,6 +171,7 @@ def run_episode(env, policy, seed, max_steps=None, n_samples=6, absent_p=0.1, in
 
     record(0, obs)
     n_done = 0
+    n_stacked = 0
     for t in range(steps):
         act = {}
         for i in range(n):
@@ -193,6 +194,8 @@ def run_episode(env, policy, seed, max_steps=None, n_samples=6, absent_p=0.1, in
         dones[t, :n] = [done[i] for i in range(n)]
         dones[t, n] = done["__all__"]
         record(t + 1, obs)
+        onmap = [a.position for a in env.agents if a.position is not None]
+        n_stacked += len(onmap) != len(set(onmap))
         n_done = t + 1
         if done["__all__"]:
             break
@@ -202,6 +205,7 @@ def run_episode(env, policy, seed, max_steps=None, n_samples=6, absent_p=0.1, in
     out["rewards"] = rewards[:n_done]
     out["dones"] = dones[:n_done]
     out["n_steps"] = np.int32(n_done)
+    out["n_stacked_steps"] = np.int32(n_stacked)
     out["sample_steps"] = np.array([k for k in sample_at if k <= n_done], np.int32)
     for key in rec:
         out["tr_" + key] = np.stack(rec[key])
@@ -228,7 +232,7 @@ def simple_rail_env(n_agents, seed, mal_interval):
     return env
 
 
-def motion_cases(n_cases, seed):
+def motion_cases(n_cases, seed, stack_p=0.0):
     """Random MotionCheck scenarios (agent_chains.py:19-37,151-236): dense little grids with
     off-map entrants, stoppers, swaps, chains and cycles; records the reference's verdict."""
     ref = rh.load()
@@ -248,6 +252,8 @@ def motion_cases(n_cases, seed):
         pos = []
         for i in range(n):
             p = None if rng.rand() < 0.2 else cells[i]
+            if p is not None and i > 0 and rng.rand() < stack_p:
+                p = cells[rng.randint(i)]  # several trains on one cell (MALFUNCTION_OFF_MAP + STOP placement)
             if p is None:
                 q = None if rng.rand() < 0.3 else cells[rng.randint(len(cells))]
             elif rng.rand() < 0.3:
@@ -270,7 +276,8 @@ def motion_cases(n_cases, seed):
 def save(name, d):
     path = os.path.join(OUT, name + ".npz")
     np.savez_compressed(path, **d)
-    print("%-28s %8.1f KB  steps=%s" % (name, os.path.getsize(path) / 1024, d.get("n_steps")))
+    print("%-28s %8.1f KB  steps=%s stacked_steps=%s" % (name, os.path.getsize(path) / 1024, d.get("n_steps"),
+                                                          d.get("n_stacked_steps")))
 
 
 def main():
@@ -285,6 +292,9 @@ def main():
         ("t03_l1_greedy", "Test_03", (3, 1), "greedy", 7, 450, None),
         ("t08_l0_greedy", "Test_08", (8, 0), "greedy", 8, 720, 400),
         ("t14_l0_forward", "Test_14", (14, 0), "forward", 9, 3600, 40),
+        # heavy malfunctions + uniform random actions: MALFUNCTION_OFF_MAP + STOP puts trains on occupied cells
+        ("t02_l2_stacking", "Test_02", (2, 2), "random", 10, 25, None),
+        ("t03_l2_stacking", "Test_03", (3, 2), "random", 11, 40, 300),
     ]
     only = sys.argv[1:]
     for name, cfg, (test, level), policy, aseed, mal, max_steps in jobs:
@@ -299,7 +309,9 @@ def main():
         env = simple_rail_env(n_agents, seed, 30)
         save(name, run_episode(env, "greedy" if n_agents < 4 else "random", 20 + n_agents))
     if not only or "motion_cases" in only:
-        save("motion_cases", motion_cases(3000, 99))
+        d = motion_cases(3000, 99)
+        d2 = motion_cases(3000, 100, stack_p=0.35)
+        save("motion_cases", {k: np.concatenate([d[k], d2[k]]) for k in d})
 
 
 if __name__ == "__main__":
