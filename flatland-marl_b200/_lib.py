@@ -16,7 +16,7 @@ _PTR = ["grid", "slot_rc", "dist", "max_steps", "init_rc", "tgt_rc", "init_dir",
         "earliest", "latest", "sched",
         "rc", "old_rc", "dir", "old_dir", "state", "ctr", "mal", "saved", "sig_mal", "deadlocked", "done", "nmal",
         "arrival",
-        "elapsed", "sched_pos", "done_all", "status", "cellinfo", "occ_cell",
+        "elapsed", "sched_pos", "done_all", "status", "cellinfo", "occ_cell", "stats",
         "key_start", "entries"]
 
 
@@ -31,7 +31,8 @@ class FlObsBuffers(C.Structure):
 
 
 EXPORTS = ["fl_abi_version", "fl_batch_sizeof", "fl_error_string", "fl_distance_map", "fl_reset", "fl_step",
-           "fl_observe", "fl_step_observe_host", "fl_launch_count"]
+           "fl_observe", "fl_step_observe_host", "fl_launch_count", "fl_profile_num_kernels", "fl_profile_kernel_name",
+           "fl_profile_enable", "fl_profile_collect"]
 
 _lib = None
 
@@ -61,6 +62,13 @@ def lib():
     L.fl_observe.argtypes = [C.POINTER(FlBatch)] + [P] * 8
     L.fl_step_observe_host.argtypes = [C.POINTER(FlBatch), P, P, C.POINTER(FlObsBuffers), C.POINTER(FlObsBuffers),
                                        C.c_uint32, P]
+    L.fl_profile_num_kernels.restype = C.c_int
+    L.fl_profile_kernel_name.restype = C.c_char_p
+    L.fl_profile_kernel_name.argtypes = [C.c_int]
+    L.fl_profile_enable.argtypes = [C.c_int]
+    L.fl_profile_enable.restype = None
+    L.fl_profile_collect.argtypes = [P, P, C.c_int]
+    L.fl_profile_collect.restype = C.c_int
     for f in ("fl_distance_map", "fl_reset", "fl_step", "fl_observe", "fl_step_observe_host"):
         getattr(L, f).restype = C.c_int
     if L.fl_batch_sizeof() != C.sizeof(FlBatch):

@@ -21,6 +21,8 @@
 #include <cuda_runtime.h>
 
 #include <atomic>
+#include <mutex>
+#include <vector>
 
 #define DEVI __device__ __forceinline__
 
@@ -32,6 +34,38 @@ constexpr int NPRED = FL_PRED_DEPTH + 1;  // prediction rows 0..500 (treeobs.cpp
 constexpr int TREE_WARPS = 8;
 
 std::atomic<uint64_t> g_launches{0};
+
+// Optional per-kernel timing (fl_profile_*): every launch is bracketed by CUDA events recorded on the
+// launching stream; fl_profile_collect turns them into per-kernel totals.  Off by default.
+enum KernelId : int { K_BFS = 0, K_RESET, K_STEP, K_PREP, K_TREE, K_COUNT };
+const char *const kKernelNames[K_COUNT] = {"k_bfs", "k_reset", "k_step", "k_prep", "k_tree"};
+struct ProfRec { int id; cudaEvent_t a, b; };
+std::mutex g_prof_mu;
+bool g_prof_on = false;
+std::vector<ProfRec> g_prof_pending;
+std::vector<cudaEvent_t> g_prof_free;
+double g_prof_ms[K_COUNT];
+uint64_t g_prof_n[K_COUNT];
+
+struct LaunchScope {  // RAII: counts the launch and, when profiling, records the event pair around it
+    int id; cudaStream_t st; cudaEvent_t a = nullptr, b = nullptr; bool on;
+    static cudaEvent_t get() {
+        if (!g_prof_free.empty()) { cudaEvent_t e = g_prof_free.back(); g_prof_free.pop_back(); return e; }
+        cudaEvent_t e; cudaEventCreate(&e); return e;
+    }
+    LaunchScope(int id_, cudaStream_t st_) : id(id_), st(st_) {
+        g_launches++;
+        std::lock_guard<std::mutex> lk(g_prof_mu);
+        on = g_prof_on;
+        if (on) { a = get(); b = get(); cudaEventRecord(a, st); }
+    }
+    ~LaunchScope() {
+        if (!on) return;
+        cudaEventRecord(b, st);
+        std::lock_guard<std::mutex> lk(g_prof_mu);
+        g_prof_pending.push_back({id, a, b});
+    }
+};
 
 DEVI bool on_map(int s) { return s >= MOVING && s <= MALFUNCTION; }
 DEVI bool off_map(int s) { return s <= MAL_OFF; }
@@ -252,6 +286,10 @@ k_step(FlBatch b, const uint8_t *__restrict__ actions, int32_t *__restrict__ rew
                 rew = off_map(st) ? -tt : (b.latest[ea] - elapsed) - tt;
             }
             b.done[ea] = 1;
+            // episode statistics (eval_env.py:81-94 final_metric): arrivals and total reward
+            unsigned long long *stt = reinterpret_cast<unsigned long long *>(b.stats + (size_t)e * 4);
+            if (st == DONE) atomicAdd(stt + 1, 1ull);
+            if (rew) atomicAdd(stt + 2, (unsigned long long)(long long)rew);
         }
         rewards[ea] = rew;
         dones[(size_t)e * (N + 1) + i] = ended ? 1 : b.done[ea];
@@ -263,7 +301,8 @@ k_step(FlBatch b, const uint8_t *__restrict__ actions, int32_t *__restrict__ rew
     if (i == 0) {
         b.elapsed[e] = elapsed;
         b.sched_pos[e] = b.sched_pos[e] + 1;
-        if (ended) b.done_all[e] = 1;
+        if (ended) { b.done_all[e] = 1; atomicAdd(reinterpret_cast<unsigned long long *>(b.stats + (size_t)e * 4), 1ull); }
+        atomicAdd(reinterpret_cast<unsigned long long *>(b.stats + (size_t)e * 4 + 3), (unsigned long long)N);
         dones[(size_t)e * (N + 1) + N] = ended ? 1 : 0;
     }
 }
@@ -912,6 +951,34 @@ int fl_abi_version(void) { return FL_ABI_VERSION; }
 size_t fl_batch_sizeof(void) { return sizeof(FlBatch); }
 uint64_t fl_launch_count(void) { return g_launches.load(); }
 
+int fl_profile_num_kernels(void) { return K_COUNT; }
+const char *fl_profile_kernel_name(int k) { return k >= 0 && k < K_COUNT ? kKernelNames[k] : ""; }
+
+void fl_profile_enable(int on) {
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    g_prof_on = on != 0;
+}
+
+int fl_profile_collect(double *ms_out, uint64_t *launches_out, int reset) {
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    for (const ProfRec &r : g_prof_pending) {
+        cudaError_t err = cudaEventSynchronize(r.b);
+        if (err != cudaSuccess) return (int)err;
+        float ms = 0.0f;
+        err = cudaEventElapsedTime(&ms, r.a, r.b);
+        if (err != cudaSuccess) return (int)err;
+        g_prof_ms[r.id] += ms; g_prof_n[r.id] += 1;
+        g_prof_free.push_back(r.a); g_prof_free.push_back(r.b);
+    }
+    g_prof_pending.clear();
+    for (int k = 0; k < K_COUNT; k++) {
+        if (ms_out) ms_out[k] = g_prof_ms[k];
+        if (launches_out) launches_out[k] = g_prof_n[k];
+        if (reset) { g_prof_ms[k] = 0.0; g_prof_n[k] = 0; }
+    }
+    return FL_OK;
+}
+
 const char *fl_error_string(int code) {
     switch (code) {
     case FL_OK: return "ok";
@@ -934,18 +1001,21 @@ int fl_distance_map(const FlBatch *b, void *stream) {
             cudaError_t err = cudaFuncSetAttribute(k_bfs<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             if (err != cudaSuccess) return (int)err;
         }
+        LaunchScope ls(K_BFS, st);
         k_bfs<true><<<grid, nt, smem, st>>>(*b);
     } else {
+        LaunchScope ls(K_BFS, st);
         k_bfs<false><<<grid, nt, 0, st>>>(*b);
     }
-    g_launches++;
     return finish(cudaGetLastError());
 }
 
 int fl_reset(const FlBatch *b, const uint8_t *d_env_mask, void *stream) {
     if (int rc = check_batch(b)) return rc;
-    k_reset<<<(unsigned)b->E, 128, 0, (cudaStream_t)stream>>>(*b, d_env_mask);
-    g_launches++;
+    {
+        LaunchScope ls(K_RESET, (cudaStream_t)stream);
+        k_reset<<<(unsigned)b->E, 128, 0, (cudaStream_t)stream>>>(*b, d_env_mask);
+    }
     return finish(cudaGetLastError());
 }
 
@@ -954,8 +1024,10 @@ int fl_step(const FlBatch *b, const uint8_t *d_actions, int32_t *d_rewards, uint
     if (int rc = check_batch(b)) return rc;
     if (!d_actions || !d_rewards || !d_dones) return FL_ERR_BAD_ARG;
     const int nt = round_up((int)b->N, 32);
-    k_step<<<(unsigned)b->E, nt, 4 * b->N * sizeof(int), (cudaStream_t)stream>>>(*b, d_actions, d_rewards, d_dones, flags);
-    g_launches++;
+    {
+        LaunchScope ls(K_STEP, (cudaStream_t)stream);
+        k_step<<<(unsigned)b->E, nt, 4 * b->N * sizeof(int), (cudaStream_t)stream>>>(*b, d_actions, d_rewards, d_dones, flags);
+    }
     return finish(cudaGetLastError());
 }
 
@@ -973,8 +1045,10 @@ int fl_observe(const FlBatch *b, float *d_agent_attr, float *d_forest, int32_t *
             cudaError_t err = cudaFuncSetAttribute(k_prep, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             if (err != cudaSuccess) return (int)err;
         }
-        k_prep<<<(unsigned)b->E, nt, smem, st>>>(*b, d_valid_actions, d_dist_target);
-        g_launches++;
+        {
+            LaunchScope ls(K_PREP, st);
+            k_prep<<<(unsigned)b->E, nt, smem, st>>>(*b, d_valid_actions, d_dist_target);
+        }
         if (cudaError_t err = cudaGetLastError()) return (int)err;
     }
     {
@@ -987,9 +1061,9 @@ int fl_observe(const FlBatch *b, float *d_agent_attr, float *d_forest, int32_t *
         }
         const long long agents = b->E * b->N;
         const unsigned grid = (unsigned)((agents + TREE_WARPS - 1) / TREE_WARPS);
+        LaunchScope ls(K_TREE, st);
         k_tree<<<grid, TREE_WARPS * 32, smem, st>>>(*b, d_valid_actions, d_dist_target, d_agent_attr, d_forest,
                                                      d_adjacency, d_node_order, d_edge_order, words);
-        g_launches++;
     }
     return finish(cudaGetLastError());
 }

@@ -10,7 +10,8 @@
  * Conventions: plain pointers and sizes only (no torch / pybind types); every pointer inside
  * `FlBatch` and every `d_` argument is a DEVICE pointer owned by the caller; `h_` arguments are
  * HOST pointers (pinned for async copies); `stream` is a `cudaStream_t` passed as `void*`; the
- * library never allocates or frees device memory and keeps no global state except a launch counter; return value is 0 or
+ * library never allocates or frees device memory and keeps no global state except a launch counter
+ * and the optional fl_profile_* event log; return value is 0 or
  * an `FlStatus` / CUDA error code (see fl_error_string); no exceptions cross the boundary.
  * Calls on one FlBatch must be serialised by the caller (one stream); different batches are
  * independent.
@@ -101,6 +102,8 @@ typedef struct FlBatch {
                                        bits 31..21 highest handle on the cell + 1, 20..11 number of off-map
                                        agents whose initial cell this is, 10..9 direction, 8 malfunctioning */
     int32_t *occ_cell;    /* [E][N] cell each agent was entered under in cellinfo, -1 = none */
+    int64_t *stats;       /* [E][4] running totals since upload: episodes finished, agents arrived at episode
+                                    end, sum of end-of-episode rewards, agent-steps (eval_env.py:81-94 final_metric) */
 
     /* ---- per-step observation workspace (rebuilt by every fl_observe) ---- */
     uint32_t *key_start;  /* [E][W*W + H + 1] CSR offsets of predicted-occupancy entries per cell id c*W+r */
@@ -159,6 +162,16 @@ int fl_step_observe_host(const FlBatch *b, const uint8_t *h_actions, uint8_t *d_
 
 /* Number of kernel launches issued by this library since load (bench.py reports it as gpu_launches). */
 uint64_t fl_launch_count(void);
+
+/* Measurement hooks (no reference counterpart; BASELINE.json asks for per-kernel numbers).  While
+ * enabled, every kernel launch of this library is bracketed by two CUDA events recorded on the
+ * launching stream.  fl_profile_collect waits for the pending events and writes the accumulated
+ * device time in ms and the launch count per kernel into ms_out / launches_out
+ * (fl_profile_num_kernels() entries each; either may be NULL); reset != 0 zeroes the totals. */
+int fl_profile_num_kernels(void);
+const char *fl_profile_kernel_name(int k);
+void fl_profile_enable(int on);
+int fl_profile_collect(double *ms_out, uint64_t *launches_out, int reset);
 
 #ifdef __cplusplus
 }
