@@ -11,7 +11,7 @@ ACTION_ABSENT = 255
 ST_STEP_AFTER_DONE, ST_AUTO_RESET, ST_BAD_CELL = 1, 2, 4
 FLAG_AUTO_RESET = 1
 
-_I64 = ["E", "N", "H", "W", "n_slots", "S", "ent_cap", "reserved0"]
+_I64 = ["E", "N", "H", "W", "n_slots", "S", "ent_cap", "grid_stride", "dist_stride", "reserved0"]
 _PTR = ["grid", "slot_rc", "dist", "max_steps", "init_rc", "tgt_rc", "init_dir", "max_count", "slot", "speed",
         "earliest", "latest", "sched",
         "rc", "old_rc", "dir", "old_dir", "state", "ctr", "mal", "saved", "sig_mal", "deadlocked", "done", "nmal",

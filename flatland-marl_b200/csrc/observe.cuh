@@ -1,0 +1,809 @@
+// observe.cuh — k_observe: TreeObsForRailEnv::get_many + get_properties (treeobs.cpp:30-108, 612-640) for
+// one environment per CTA, the whole per-environment working set staged in shared memory.
+//
+// Phases of one CTA (= one environment):
+//   0  stage the rail grid and the distance maps into shared memory with two 1-D TMA bulk copies
+//      (cp.async.bulk + mbarrier) while phase 1 reads the agents.
+//   1  loader view per agent (loader.cpp:8-179, 221-327): virtual position, valid actions, distance to
+//      target, the per-cell occupancy word (treeobs.cpp:67-92) built with shared-memory atomics.
+//   2  the serial, sticky DeadlockChecker (deadlock_checker.cpp:11-110) on lane 0 of the last warp, running
+//      concurrently with phases 3 and 4 (its result is only needed by the attribute vector).
+//   3  greedy shortest-path predictions (predictions.cpp:13-235) as occupancy intervals, counting-sorted by
+//      the reference's cell id c*W+r into a CSR inverse index  cell id -> intervals  (two walks: count,
+//      scatter).
+//   4  the 31-node branch trees (treeobs.cpp:154-610).  One LANE per branch walk: walks are work items in a
+//      shared-memory queue; a lane that finishes a walk creates its node's three children in place (their
+//      BFS indices follow from the bit mask of real nodes of the level) and the lane that finishes the
+//      last walk of an agent's level releases the next level into the queue.  No CTA barrier inside the
+//      phase; lanes of a warp advance different walks one cell per iteration.  Node features go straight
+//      to the policy's forest tensor as three 16-byte stores per node.
+//   5  evaluation orders (tool.h:468-524), adjacency and the 83-float attribute vector
+//      (feature_parser.cpp:3-98), written with coalesced stores.
+// Arrays that do not fit in shared memory for a configuration (large grids) stay in global memory behind
+// the same generic pointers (ObsLayout offsets < 0).
+#pragma once
+#include "common.cuh"
+
+namespace {
+
+constexpr int OBS_MAX_TILE = 64;        // agents whose trees are built together (bounds the node table)
+constexpr int OBS_Q_EMPTY = 0xFFFF;
+constexpr int OBS_WALK_CAP = 1024;      // branch walks longer than this are checked for a rail cycle (Brent)
+constexpr int I_INF = 0x7fffffff;
+
+struct ObsLayout {   // byte offsets into dynamic shared memory (host: make_obs_layout); < 0 = lives in global memory
+    int grid, ci, dist, ks, ent, ent_cap, part, ag, dl, tree, bar, total, tile;
+};
+
+// ---- mbarrier + 1-D TMA bulk copy (global -> shared), sm_90+ ------------------------------------
+DEVI uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+DEVI void mbar_init(uint64_t *bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+DEVI void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+DEVI void tma_load_1d(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+DEVI void mbar_wait(uint64_t *bar, uint32_t parity) {
+    uint32_t ok;
+    do {
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, p;\n"
+            "}\n"
+            : "=r"(ok)
+            : "r"(smem_u32(bar)), "r"(parity)
+            : "memory");
+    } while (!ok);
+}
+DEVI void named_bar_sync(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
+
+DEVI uint32_t ld_vol_u32(const uint32_t *p) { return *reinterpret_cast<const volatile uint32_t *>(p); }
+DEVI int ld_vol_i32(const int *p) { return *reinterpret_cast<const volatile int *>(p); }
+DEVI unsigned ld_vol_u16(const uint16_t *p) { return *reinterpret_cast<const volatile uint16_t *>(p); }
+
+// get_valid_move_actions_ (predictions.cpp:13-76), result in std::set order L,F,R
+DEVI int greedy_moves(unsigned cell, int d, int out_d[3]) {
+    const int nb = nibble(cell, d);
+    int k = 0;
+    if (__popc(cell) == 1) {                      // dead end: only way is back
+        const int ex = (d + 2) & 3;
+        if (tbit(nb, ex)) out_d[k++] = ex;
+        return k;
+    }
+#pragma unroll
+    for (int t = -1; t <= 1; t++) {
+        const int nd = (d + t) & 3;
+        if (tbit(nb, nd)) out_d[k++] = nd;
+    }
+    return k;
+}
+
+// Predicted occupancy of one agent as intervals per path element (predictions.cpp:78-235 + the
+// transpose in treeobs.cpp:50-65).  Path element k >= 1 is occupied for prediction rows
+// [1+(k-1)*tpc, k*tpc], the last element until row 500, element 0 for row 0 only (or all rows when
+// the path has a single element).  The reference stops advancing once the cell equals the target.
+// Emit(key, t0, t1, dir_here, dir_prev, dir_next) is called once per occupied element.
+template <class Emit>
+DEVI void walk_prediction(const uint16_t *g, const uint16_t *dm, int W, int vr, int vc, int dir, int tr, int tc,
+                          int tpc, Emit emit) {
+    int r = vr, c = vc, d = dir, k = 0;
+    unsigned best_dist = FL_DIST_INF;
+    int pr = r, pc = c, pd = d, ppd = d;          // pending (previous) element and the one before it
+    bool have_prev = false;
+    while (true) {
+        // element k = (r, c, d) is known here; emit element k-1 now that its successor is known
+        if (have_prev) {
+            const int kk = k - 1;
+            const int t0 = kk == 0 ? 0 : 1 + (kk - 1) * tpc;
+            const int t1 = kk == 0 ? 0 : kk * tpc;
+            if (t0 < NPRED) emit(pc * W + pr, t0, min(t1, NPRED - 1), pd, ppd, d);
+            else return;
+        }
+        bool last = (r == tr && c == tc) || k >= FL_PRED_DEPTH;   // at target, or 500 greedy steps done
+        int nr = r, nc = c, ndir = d;
+        if (!last) {
+            int md[3];
+            const int n = greedy_moves(g[r * W + c], d, md);
+            int best = -1;
+            for (int j = 0; j < n; j++) {
+                const int rr = r + d_row(md[j]), cc = c + d_col(md[j]);
+                const unsigned v = dm[((size_t)(rr * W + cc)) * 4 + md[j]];
+                if (v < best_dist) { best = j; best_dist = v; nr = rr; nc = cc; ndir = md[j]; }
+            }
+            if (best < 0) last = true;             // rail disconnected: path ends here
+        }
+        if (last) {
+            const int t0 = k == 0 ? 0 : 1 + (k - 1) * tpc;
+            if (t0 < NPRED) emit(c * W + r, t0, NPRED - 1, d, pd, d);
+            return;
+        }
+        ppd = pd; pr = r; pc = c; pd = d; have_prev = true;
+        r = nr; c = nc; d = ndir; k++;
+    }
+}
+
+DEVI uint64_t pack_entry(int agent, int t0, int t1, int dh, int dp, int dn, int done) {
+    return (uint64_t)agent | ((uint64_t)t0 << 10) | ((uint64_t)t1 << 19) | ((uint64_t)dh << 28) |
+           ((uint64_t)dp << 30) | ((uint64_t)dn << 32) | ((uint64_t)done << 34);
+}
+
+// loader.cpp:273-312: valid-action mask, bit a = action a allowed
+DEVI int valid_actions_of(const uint16_t *g, int W, int st, int ctr, int r, int c, int d) {
+    int va = 0;
+    if (st == MOVING || st == STOPPED) {
+        if (ctr == 0) {
+            const unsigned cell = g[r * W + c];
+            const int nb = nibble(cell, d);
+            int cnt = 0;
+            bool branch_next = false;
+            for (int a = A_LEFT; a <= A_RIGHT; a++) {
+                const int nd = (d + a - 2) & 3;
+                if (tbit(nb, nd)) {
+                    va |= 1 << a;
+                    cnt++;
+                    if (__popc(g[(r + d_row(nd)) * W + c + d_col(nd)]) > 2) branch_next = true;
+                }
+            }
+            if (__popc(cell) > 2 || (cnt == 1 && branch_next)) va |= 1 << A_STOP;
+        } else va = 1 << A_NOTHING;
+    } else if (st == READY) va = (1 << A_FORWARD) | (1 << A_STOP);
+    else va = 1 << A_NOTHING;
+    return va;
+}
+
+// Serial, order-dependent and sticky: an exact restatement of DeadlockChecker::update_deadlocks /
+// _check_blocked / _fix_deps (deadlock_checker.cpp:11-110) with the recursion turned into an explicit
+// stack.  Runs on one lane per environment while the other warps walk predictions and trees.
+struct DeadlockScratch {
+    uint8_t *checked, *ndep, *dl, *ct, *stk_d, *stk_phase;
+    uint16_t *dep, *stk_h, *stk_opp;
+    const int *cellid;
+};
+
+DEVI void update_deadlocks(const DeadlockScratch &x, const uint32_t *ci, int N, int H, int W) {
+    for (int a0 = 0; a0 < N; a0++) {
+        if (x.cellid[a0] < 0 || x.dl[a0] || x.checked[a0]) continue;
+        int sp = 0;
+        x.stk_h[0] = a0; x.stk_d[0] = 0; x.stk_phase[0] = 0; x.checked[a0] = 1; sp = 1;
+        while (sp > 0) {
+            const int f = sp - 1, h = x.stk_h[f];
+            const int hr = x.cellid[h] / W, hc = x.cellid[h] % W;
+            bool popped = false, pushed = false;
+            while (x.stk_d[f] < 4) {
+                const int dd = x.stk_d[f];
+                int opp;
+                if (x.stk_phase[f] == 1) { opp = x.stk_opp[f]; x.stk_phase[f] = 0; }
+                else {
+                    if (!tbit(x.ct[h], dd)) { x.stk_d[f]++; continue; }
+                    const int rr = hr + d_row(dd), cc = hc + d_col(dd);
+                    opp = -1;
+                    if (rr >= 0 && cc >= 0 && rr < H && cc < W) opp = (int)(ci[rr * W + cc] >> 21) - 1;
+                    if (opp < 0) { x.checked[h] = 2; popped = true; break; }           // road is free
+                    if (x.dl[opp]) { x.stk_d[f]++; continue; }                          // road is blocked
+                    if (x.checked[opp] == 0) {                                          // recurse
+                        x.stk_phase[f] = 1; x.stk_opp[f] = (uint16_t)opp;
+                        x.stk_h[sp] = (uint16_t)opp; x.stk_d[sp] = 0; x.stk_phase[sp] = 0; x.checked[opp] = 1; sp++;
+                        pushed = true;
+                        break;
+                    }
+                }
+                if (x.checked[opp] == 2 && !x.dl[opp]) { x.checked[h] = 2; popped = true; break; }  // may become free
+                x.dep[h * 4 + x.ndep[h]] = (uint16_t)opp; x.ndep[h]++;
+                x.stk_d[f]++;
+            }
+            if (pushed) continue;
+            if (!popped && x.ndep[h] == 0) {
+                x.checked[h] = 2;
+                if (x.ct[h] != 0) x.dl[h] = 1;
+            }
+            sp--;
+        }
+    }
+    bool any = true;                                                                    // _fix_deps
+    while (any) {
+        any = false;
+        for (int h = 0; h < N; h++) {
+            if (x.checked[h] != 1) continue;
+            int cnt = 0;
+            for (int k = 0; k < x.ndep[h]; k++) {
+                const int o = x.dep[h * 4 + k];
+                if (x.checked[o] == 2) {
+                    if (x.dl[o]) cnt++;
+                    else { x.checked[h] = 2; any = true; }
+                }
+            }
+            if (cnt == x.ndep[h]) { x.checked[h] = 2; x.dl[h] = 1; any = true; }
+        }
+    }
+    for (int h = 0; h < N; h++) if (x.checked[h] == 1) { x.dl[h] = 1; x.checked[h] = 2; }
+}
+
+// rotate_transition (tool.h:300-335): rotate the 4 bits inside every orientation block right by k,
+// then rotate the four blocks right by k
+DEVI int rotate_transition(int t, int k) {
+    int v = 0;
+#pragma unroll
+    for (int o = 0; o < 4; o++) {
+        int bl = (t >> ((3 - o) * 4)) & 0xF;
+        bl = ((bl >> k) | (bl << (4 - k))) & 0xF;
+        v |= bl << ((3 - o) * 4);
+    }
+    return (((v & ((1 << (k * 4)) - 1)) << ((4 - k) * 4)) | (v >> (k * 4))) & 0xFFFF;
+}
+
+__constant__ int c_road_types[11] = {0x0000, 0x8020, 0x9220, 0x8421, 0x9621, 0xCC33,
+                                     0x5202, 0x2000, 0x4002, 0x1200, 0xC022};  // loader.cpp:123-134
+
+DEVI int road_type_of(int trans) {  // loader.cpp:122-161: first rotation that is in the table
+    for (int q = 0; q < 4; q++) {
+        const int rot = q == 0 ? trans : rotate_transition(trans, q);
+        for (int k = 0; k < 11; k++) if (c_road_types[k] == rot) return k;
+    }
+    return 0;
+}
+
+DEVI float scale_i(int v, float T) { return v != I_INF ? (float)v / T : -1.0f; }  // treeobs.cpp:111-152
+
+// static successor of a branch-walk state (treeobs.cpp:476-539 without the dynamic features); false = the walk ends here
+DEVI bool walk_succ(const uint16_t *g, int W, int tr, int tc, int &r, int &c, int &d) {
+    if (r == tr && c == tc) return false;
+    const unsigned gc = g[r * W + c];
+    const int nb = nibble(gc, d);
+    if (__popc(nb) != 1) return false;
+    if (__popc(gc) == 1) return false;              // dead end (a diamond crossing has 4 bits)
+    d = first_dir(nb); r += d_row(d); c += d_col(d);
+    return true;
+}
+
+// Brent's cycle detection on walk_succ: index of the first revisited state (mu + lambda) when the walk
+// from (r0,c0,d0) runs into a cycle of plain rail, -1 when it ends at a switch / dead end / target.
+DEVI int walk_cycle_index(const uint16_t *g, int W, int tr, int tc, int r0, int c0, int d0) {
+    int tr_ = r0, tc_ = c0, td = d0, hr = r0, hc = c0, hd = d0;
+    int power = 1, lam = 1;
+    if (!walk_succ(g, W, tr, tc, hr, hc, hd)) return -1;
+    while (tr_ != hr || tc_ != hc || td != hd) {
+        if (power == lam) { tr_ = hr; tc_ = hc; td = hd; power *= 2; lam = 0; }
+        if (!walk_succ(g, W, tr, tc, hr, hc, hd)) return -1;
+        lam++;
+    }
+    tr_ = hr = r0; tc_ = hc = c0; td = hd = d0;
+    for (int k = 0; k < lam; k++) walk_succ(g, W, tr, tc, hr, hc, hd);
+    int mu = 0;
+    while (tr_ != hr || tc_ != hc || td != hd) {
+        walk_succ(g, W, tr, tc, tr_, tc_, td);
+        walk_succ(g, W, tr, tc, hr, hc, hd);
+        mu++;
+    }
+    return mu + lam;
+}
+
+DEVI void store_node(float *forest_node, float4 a, float4 b, float4 c) {
+    float4 *p = reinterpret_cast<float4 *>(forest_node);
+    p[0] = a; p[1] = b; p[2] = c;
+}
+DEVI void store_null_node(float *forest_node) {
+    const float4 m = make_float4(-1.0f, -1.0f, -1.0f, -1.0f);
+    store_node(forest_node, m, m, m);
+}
+
+// per-agent shared-memory record (struct of arrays, N entries each)
+struct ObsAgents {
+    uint32_t *vrc;      // virtual position r | c << 16 (loader.cpp:87-101)
+    uint32_t *tgt;      // target r | c << 16
+    uint32_t *info;     // dir | st << 2 | done << 5 | slot << 8 | tpc << 24
+    float *speed;       // (float)speed
+    float *dt;          // dist_target, INFINITY = unreachable
+    int *cellid;        // on-map cell index, -1 otherwise
+    int *initcell;      // initial cell index while off map, -1 otherwise
+    uint32_t *rec_a;    // st | road << 3 | idir << 7 | od << 9 | ctr << 11 | maxc << 19 | va << 27
+    uint32_t *rec_b;    // trans | nmal01 << 16 | mal01 << 17 | sig_mal << 18
+    float *f_earliest, *f_latest, *f_arrival, *f_dist, *f_idist;
+};
+
+struct ObsTile {
+    uint32_t *n_rc, *n_meta, *n_tot;        // [OBS_TILE][31] node table: start cell, dir|ad|null|parent, distance so far
+    uint32_t *t_mask, *t_next;              // [OBS_TILE] real-node bit mask of the level being walked / being created
+    int *t_pend;                            // [OBS_TILE] walks of the current level still running
+    uint32_t *t_lsle;                       // [OBS_TILE] level start | level end << 8
+    int *t_count;                           // [OBS_TILE] nodes created (rows >= count are padding)
+    int8_t *norder;                         // [OBS_TILE][32]
+    uint16_t *q;                            // [OBS_TILE * 30] work queue: local agent << 5 | node
+    int *q_head, *q_tail, *n_done;
+};
+
+template <int NT>
+__global__ void __launch_bounds__(NT)
+k_observe(FlBatch b, ObsLayout lay, float *__restrict__ out_attr, float *__restrict__ out_forest,
+          int32_t *__restrict__ out_adj, int32_t *__restrict__ out_norder, int32_t *__restrict__ out_eorder,
+          uint8_t *__restrict__ out_valid, float *__restrict__ out_dist_target) {
+    const int e = blockIdx.x, N = (int)b.N, H = (int)b.H, W = (int)b.W, HW = H * W;
+    const int K = W * W + H;                       // key space of the reference's cell id c*W + r
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    extern __shared__ __align__(128) unsigned char obs_smem[];
+    unsigned char *const smraw = obs_smem;
+
+    // ---- pointers: shared-memory copy when the layout has room, global memory otherwise ---------
+    const uint16_t *g_grid = b.grid + (size_t)e * b.grid_stride;
+    const uint16_t *g_dist = b.dist + (size_t)e * b.dist_stride;
+    const uint16_t *grid = lay.grid >= 0 ? reinterpret_cast<const uint16_t *>(smraw + lay.grid) : g_grid;
+    const uint16_t *dist = lay.dist >= 0 ? reinterpret_cast<const uint16_t *>(smraw + lay.dist) : g_dist;
+    uint32_t *ci = lay.ci >= 0 ? reinterpret_cast<uint32_t *>(smraw + lay.ci) : b.cellinfo + (size_t)e * HW;
+    uint32_t *ks = lay.ks >= 0 ? reinterpret_cast<uint32_t *>(smraw + lay.ks) : b.key_start + (size_t)e * (K + 1);
+    uint32_t *s_part = reinterpret_cast<uint32_t *>(smraw + lay.part);
+    uint64_t *bar = reinterpret_cast<uint64_t *>(smraw + lay.bar);
+    int *s_misc = reinterpret_cast<int *>(smraw + lay.bar + 16);     // [0] entries total
+
+    ObsAgents A;
+    {
+        uint32_t *p = reinterpret_cast<uint32_t *>(smraw + lay.ag);
+        A.vrc = p; p += N; A.tgt = p; p += N; A.info = p; p += N;
+        A.speed = reinterpret_cast<float *>(p); p += N; A.dt = reinterpret_cast<float *>(p); p += N;
+        A.cellid = reinterpret_cast<int *>(p); p += N; A.initcell = reinterpret_cast<int *>(p); p += N;
+        A.rec_a = p; p += N; A.rec_b = p; p += N;
+        A.f_earliest = reinterpret_cast<float *>(p); p += N; A.f_latest = reinterpret_cast<float *>(p); p += N;
+        A.f_arrival = reinterpret_cast<float *>(p); p += N; A.f_dist = reinterpret_cast<float *>(p); p += N;
+        A.f_idist = reinterpret_cast<float *>(p); p += N;
+    }
+    DeadlockScratch D;
+    {
+        uint16_t *p = reinterpret_cast<uint16_t *>(smraw + lay.dl);
+        D.dep = p; p += 4 * N; D.stk_h = p; p += N; D.stk_opp = p; p += N;
+        uint8_t *q = reinterpret_cast<uint8_t *>(p);
+        D.checked = q; q += N; D.ndep = q; q += N; D.dl = q; q += N; D.ct = q; q += N; D.stk_d = q; q += N; D.stk_phase = q;
+        D.cellid = A.cellid;
+    }
+    const int OBS_TILE = lay.tile;
+    ObsTile Tt;
+    {
+        uint32_t *p = reinterpret_cast<uint32_t *>(smraw + lay.tree);
+        Tt.n_rc = p; p += OBS_TILE * 31; Tt.n_meta = p; p += OBS_TILE * 31; Tt.n_tot = p; p += OBS_TILE * 31;
+        Tt.t_mask = p; p += OBS_TILE; Tt.t_next = p; p += OBS_TILE;
+        Tt.t_pend = reinterpret_cast<int *>(p); p += OBS_TILE; Tt.t_lsle = p; p += OBS_TILE;
+        Tt.t_count = reinterpret_cast<int *>(p); p += OBS_TILE;
+        Tt.q_head = reinterpret_cast<int *>(p); Tt.q_tail = Tt.q_head + 1; Tt.n_done = Tt.q_head + 2; p += 4;
+        Tt.norder = reinterpret_cast<int8_t *>(p); p += OBS_TILE * 8;
+        Tt.q = reinterpret_cast<uint16_t *>(p);
+    }
+
+    // ---- phase 0: TMA bulk copies of the static world ---------------------------------------------
+    const bool use_tma = lay.grid >= 0 || lay.dist >= 0;
+    if (use_tma && tid == 0) {
+        mbar_init(bar, 1);
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        const uint32_t gb = lay.grid >= 0 ? (uint32_t)(b.grid_stride * 2) : 0u;
+        const uint32_t db = lay.dist >= 0 ? (uint32_t)(b.dist_stride * 2) : 0u;
+        mbar_expect_tx(bar, gb + db);
+        if (gb) tma_load_1d(smraw + lay.grid, g_grid, gb, bar);
+        if (db) tma_load_1d(smraw + lay.dist, g_dist, db, bar);
+    }
+    // zero the key counters; forget the previous occupancy
+    for (int k = tid; k <= K; k += NT) ks[k] = 0;
+    if (lay.ci >= 0) { for (int k = tid; k < HW; k += NT) ci[k] = 0; }
+    else { for (int i = tid; i < N; i += NT) { const int oc = b.occ_cell[(size_t)e * N + i]; if (oc >= 0) ci[oc] = 0; } }
+    const float T = (float)b.max_steps[e], Nf = (float)N;
+    const int elapsed = b.elapsed[e];
+    __syncthreads();                               // mbarrier initialised, counters zeroed
+    if (use_tma) mbar_wait(bar, 0);
+
+    // ---- phase 1: loader view (loader.cpp:8-179, 221-327) -----------------------------------------
+    for (int i = tid; i < N; i += NT) {
+        const size_t ea = (size_t)e * N + i;
+        const short2 p = reinterpret_cast<const short2 *>(b.rc)[ea];
+        const short2 ip = reinterpret_cast<const short2 *>(b.init_rc)[ea];
+        const short2 tp = reinterpret_cast<const short2 *>(b.tgt_rc)[ea];
+        const int r = p.x, c = p.y, d = b.dir[ea], st = b.state[ea], idir = b.init_dir[ea];
+        const int slot = b.slot[ea], ctr = b.ctr[ea], maxc = b.max_count[ea];
+        const double speed_d = b.speed[ea];
+        const float speed = (float)speed_d;
+        int vr, vc;
+        if (off_map(st)) { vr = ip.x; vc = ip.y; } else if (on_map(st)) { vr = r; vc = c; } else { vr = tp.x; vc = tp.y; }
+        const int tpc = (int)(1.0f / speed);                             // predictions.cpp:184
+        const uint16_t *dm = dist + (size_t)slot * HW * 4;
+        A.vrc[i] = (uint32_t)(vr & 0xFFFF) | ((uint32_t)vc << 16);
+        A.tgt[i] = (uint32_t)(tp.x & 0xFFFF) | ((uint32_t)tp.y << 16);
+        A.info[i] = (uint32_t)d | ((uint32_t)st << 2) | ((uint32_t)(st == DONE) << 5) | ((uint32_t)slot << 8) |
+                    ((uint32_t)min(tpc, 255) << 24);
+        A.speed[i] = speed;
+        A.cellid[i] = on_map(st) ? r * W + c : -1;
+        A.initcell[i] = off_map(st) ? ip.x * W + ip.y : -1;
+        const int trans = on_map(st) ? (int)grid[r * W + c] : 0;
+        D.ct[i] = on_map(st) ? (uint8_t)nibble(trans, d) : 0;
+        D.dl[i] = b.deadlocked[ea]; D.checked[i] = 0; D.ndep[i] = 0;
+        const int va = valid_actions_of(grid, W, st, ctr, r, c, d);
+        for (int k = 0; k < 5; k++) out_valid[ea * 5 + k] = (va >> k) & 1;
+        float dt;                                                        // loader.cpp:163-179
+        if (st == DONE) dt = 0.0f;
+        else {
+            const unsigned dv = off_map(st) ? dm[((size_t)(ip.x * W + ip.y)) * 4 + idir] : dm[((size_t)(r * W + c)) * 4 + d];
+            dt = dv == FL_DIST_INF ? INFINITY : (float)dv;
+        }
+        out_dist_target[ea] = dt;
+        A.dt[i] = dt;
+        // attribute record (feature_parser.cpp:19-94)
+        const int od_raw = b.old_dir[ea], od = od_raw == 255 ? d : od_raw;
+        const int road = r >= 0 ? road_type_of((int)grid[r * W + c]) : 0;
+        const int trans_attr = r >= 0 ? (int)grid[r * W + c] : 0;
+        A.rec_a[i] = (uint32_t)st | ((uint32_t)road << 3) | ((uint32_t)idir << 7) | ((uint32_t)od << 9) |
+                     ((uint32_t)ctr << 11) | ((uint32_t)maxc << 19) | ((uint32_t)va << 27);
+        A.rec_b[i] = (uint32_t)trans_attr | ((uint32_t)(b.nmal[ea] != 0) << 16) | ((uint32_t)(b.mal[ea] != 0) << 17) |
+                     ((uint32_t)(b.sig_mal[ea] != 0) << 18);
+        const float max_dist = (float)((H + W) * 8);
+        A.f_earliest[i] = (float)b.earliest[ea] / T;
+        A.f_latest[i] = (float)b.latest[ea] / T;
+        A.f_arrival[i] = (float)b.arrival[ea] / T;
+        A.f_dist[i] = dt == INFINITY ? 8.0f : dt / max_dist;
+        const unsigned idv = dm[((size_t)(ip.x * W + ip.y)) * 4 + idir];
+        A.f_idist[i] = idv == FL_DIST_INF ? 8.0f : (float)idv / max_dist;
+    }
+    __syncthreads();
+    // occupancy word per cell (treeobs.cpp:67-92, deadlock_checker.cpp:15-20): the HIGHEST handle standing on the
+    // cell (std::map assignment in handle order = last writer) in the top bits so atomicMax picks it, its
+    // direction and malfunction flag; then the number of off-map trains whose initial cell it is.
+    for (int i = tid; i < N; i += NT) {
+        const int cellid = A.cellid[i];
+        if (cellid >= 0)
+            atomicMax(&ci[cellid], ((uint32_t)(i + 1) << 21) | ((A.info[i] & 3u) << 9) | (((A.rec_b[i] >> 17) & 1u) << 8));
+        if (lay.ci < 0) b.occ_cell[(size_t)e * N + i] = cellid;
+    }
+    __syncthreads();
+    for (int i = tid; i < N; i += NT) {
+        const int ic = A.initcell[i];
+        if (ic >= 0 && ld_vol_u32(&ci[ic]) != 0) atomicAdd(&ci[ic], 1u << 11);
+    }
+    __syncthreads();
+
+    // ---- phase 2 (last warp, lane 0) || phase 3 (all other warps, named barrier 1): deadlocks, predictions ----
+    const bool dl_warp = warp == NT / 32 - 1;
+    constexpr int NW = NT - 32;                    // threads walking predictions
+    uint64_t *ent = reinterpret_cast<uint64_t *>(smraw + lay.ent);
+    if (dl_warp) {
+        if (lane == 0) update_deadlocks(D, ci, N, H, W);
+        __syncwarp();
+    } else {
+        for (int i = tid; i < N; i += NW) {        // pass 1: count entries per cell id
+            const uint32_t info = A.info[i];
+            const int vr = (int)(short)(A.vrc[i] & 0xFFFF), vc = (int)(A.vrc[i] >> 16);
+            const int tr = (int)(short)(A.tgt[i] & 0xFFFF), tc = (int)(A.tgt[i] >> 16);
+            walk_prediction(grid, dist + (size_t)((info >> 8) & 0xFFFF) * HW * 4, W, vr, vc, (int)(info & 3), tr, tc,
+                            (int)(info >> 24), [&](int key, int, int, int, int, int) { atomicAdd(&ks[key], 1u); });
+        }
+        named_bar_sync(1, NW);
+        // exclusive scan of ks[0..K] (K+1 values; the last becomes the total)
+        const int per = (K + 1 + NW - 1) / NW, lo = min(tid * per, K + 1), hi = min(lo + per, K + 1);
+        uint32_t sum = 0;
+        for (int k = lo; k < hi; k++) sum += ks[k];
+        s_part[tid] = sum;
+        named_bar_sync(1, NW);
+        for (int off = 1; off < NW; off <<= 1) {   // Hillis-Steele inclusive scan of the partials
+            const uint32_t v = tid >= off ? s_part[tid - off] : 0;
+            named_bar_sync(1, NW);
+            s_part[tid] += v;
+            named_bar_sync(1, NW);
+        }
+        uint32_t run = s_part[tid] - sum;
+        for (int k = lo; k < hi; k++) { const uint32_t v = ks[k]; ks[k] = run; run += v; }
+        named_bar_sync(1, NW);
+        const int n_ent = (int)s_part[NW - 1];
+        if (n_ent > lay.ent_cap) ent = b.entries + (size_t)e * b.ent_cap;
+        if (tid == 0) s_misc[0] = n_ent;
+        // pass 2: scatter.  ks[key] is advanced to the END of its bucket; bucket k is [k ? ks[k-1] : 0, ks[k]) afterwards.
+        for (int i = tid; i < N; i += NW) {
+            const uint32_t info = A.info[i];
+            const int vr = (int)(short)(A.vrc[i] & 0xFFFF), vc = (int)(A.vrc[i] >> 16);
+            const int tr = (int)(short)(A.tgt[i] & 0xFFFF), tc = (int)(A.tgt[i] >> 16);
+            const int done_flag = (info >> 5) & 1;
+            walk_prediction(grid, dist + (size_t)((info >> 8) & 0xFFFF) * HW * 4, W, vr, vc, (int)(info & 3), tr, tc,
+                            (int)(info >> 24), [&](int key, int t0, int t1, int dh, int dp, int dn) {
+                                const uint32_t pos = atomicAdd(&ks[key], 1u);
+                                ent[pos] = pack_entry(i, t0, t1, dh, dp, dn, done_flag);
+                            });
+        }
+    }
+    __syncthreads();
+    if (dl_warp && s_misc[0] > lay.ent_cap) ent = b.entries + (size_t)e * b.ent_cap;
+    for (int i = tid; i < N; i += NT) b.deadlocked[(size_t)e * N + i] = D.dl[i];
+
+    // ---- phase 4: branch trees, OBS_TILE agents at a time -----------------------------------------
+    for (int a0 = 0; a0 < N; a0 += OBS_TILE) {
+        const int na = min(OBS_TILE, N - a0);
+        const int qcap = OBS_TILE * 30;
+        for (int k = tid; k < qcap; k += NT) Tt.q[k] = OBS_Q_EMPTY;
+        if (tid == 0) { *Tt.q_head = 0; *Tt.q_tail = 0; *Tt.n_done = 0; }
+        __syncthreads();
+        // roots (treeobs.cpp:171-221)
+        for (int la = tid; la < na; la += NT) {
+            const int i = a0 + la;
+            const size_t ea = (size_t)e * N + i;
+            float *forest = out_forest + ea * (FL_MAX_NODES * FL_NODE_F);
+            const uint32_t info = A.info[i];
+            const int vr = (int)(short)(A.vrc[i] & 0xFFFF), vc = (int)(A.vrc[i] >> 16), dir = (int)(info & 3);
+            const float dtv = A.dt[i];
+            store_node(forest, make_float4(0.f, 0.f, 0.f, 0.f),
+                       make_float4(0.f, 0.f, dtv != INFINITY ? dtv / T : -1.0f, 0.f),
+                       make_float4(0.f, (float)((A.rec_b[i] >> 16) & 1u) / Nf, A.speed[i], 0.f));
+            const int nb = nibble(grid[vr * W + vc], dir);
+            int orientation = dir;
+            if (__popc(nb) == 1) orientation = first_dir(nb);
+            uint32_t mask = 0;
+            for (int ad = -1; ad <= 1; ad++) {
+                const int bd = (orientation + ad) & 3, idx = 2 + ad;
+                const bool real = tbit(nb, bd);
+                Tt.n_rc[la * 31 + idx] = real ? (uint32_t)((vr + d_row(bd)) & 0xFFFF) | ((uint32_t)(vc + d_col(bd)) << 16) : 0xFFFFFFFFu;
+                Tt.n_meta[la * 31 + idx] = (uint32_t)bd | ((uint32_t)(ad + 1) << 2) | ((real ? 0u : 1u) << 4);
+                Tt.n_tot[la * 31 + idx] = 1;
+                if (real) mask |= 1u << (idx - 1);
+                else store_null_node(forest + idx * FL_NODE_F);
+            }
+            Tt.n_meta[la * 31] = 0;
+            Tt.t_mask[la] = mask; Tt.t_next[la] = 0; Tt.t_lsle[la] = 1u | (4u << 8); Tt.t_pend[la] = __popc(mask);
+            if (mask == 0) {
+                Tt.t_count[la] = 4;
+                for (int n = 4; n < FL_MAX_NODES; n++) store_null_node(forest + n * FL_NODE_F);
+                atomicAdd(Tt.n_done, 1);
+            } else {
+                int slot = atomicAdd(Tt.q_tail, __popc(mask));
+                for (uint32_t m = mask; m; m &= m - 1) Tt.q[slot++] = (uint16_t)((la << 5) | (1 + __ffs(m) - 1));
+            }
+        }
+        __syncthreads();
+
+        // persistent lanes: one branch walk (treeobs.cpp:258-610) per lane, one cell per iteration
+        {
+            bool active = false;
+            int claim = -1;
+            int la = 0, n = 0, r = 0, c = 0, d = 0, tot = 0, steps = 0, stop_at = -1;
+            int r_start = 0, c_start = 0, d_start = 0, tot_start = 0;
+            bool cycle_checked = false;
+            int own = I_INF, other_agent = I_INF, conflict = I_INF, unusable = I_INF;
+            int same = 0, opp = 0, malf = 0, rtdn = 0;
+            float min_speed = 1.0f, tpc_f = 1.0f;
+            int h = 0, tr = 0, tc = 0;
+            const uint16_t *dm = dist;
+            while (true) {
+                if (!active) {
+                    if (claim < 0) claim = atomicAdd(Tt.q_head, 1);
+                    const unsigned it = claim < qcap ? ld_vol_u16(&Tt.q[claim]) : (unsigned)OBS_Q_EMPTY;
+                    if (it != (unsigned)OBS_Q_EMPTY) {
+                        __threadfence_block();
+                        claim = -1; active = true;
+                        la = (int)(it >> 5); n = (int)(it & 31);
+                        h = a0 + la;
+                        const uint32_t rc0 = Tt.n_rc[la * 31 + n], meta = Tt.n_meta[la * 31 + n];
+                        r = (int)(short)(rc0 & 0xFFFF); c = (int)(rc0 >> 16); d = (int)(meta & 3);
+                        tot = (int)Tt.n_tot[la * 31 + n];
+                        r_start = r; c_start = c; d_start = d; tot_start = tot;
+                        steps = 0; stop_at = -1; cycle_checked = false;
+                        own = other_agent = conflict = unusable = I_INF;
+                        same = opp = malf = rtdn = 0; min_speed = 1.0f;
+                        tr = (int)(short)(A.tgt[h] & 0xFFFF); tc = (int)(A.tgt[h] >> 16);
+                        tpc_f = (float)(1.0 / (double)A.speed[h]);                       // treeobs.cpp:304
+                        dm = dist + (size_t)((A.info[h] >> 8) & 0xFFFF) * HW * 4;
+                    }
+                }
+                if (active) {
+                    int kind = 0;                  // 1 switch, 2 dead end, 3 terminal (cycle), 4 target
+                    const int cell = r * W + c;
+                    const uint32_t cinfo = ci[cell];
+                    const unsigned gc = grid[cell];
+                    if (cinfo) {                   // treeobs.cpp:322-360 (the observer itself counts too)
+                        other_agent = min(other_agent, tot);
+                        malf = max(malf, (int)((cinfo >> 8) & 1u));
+                        const int cnt = (int)((cinfo >> 11) & 1023u);
+                        rtdn += cnt ? cnt - 1 : 0;
+                        if ((int)((cinfo >> 9) & 3u) == d) { same++; min_speed = fminf(min_speed, A.speed[(cinfo >> 21) - 1]); }
+                        else opp++;
+                    }
+                    const int nb = nibble(gc, d);
+                    int total = __popc(gc);
+                    const int pt = (int)__fmul_rn((float)tot, tpc_f);                   // treeobs.cpp:378
+                    if (pt < NPRED && tot < NPRED) {                                     // treeobs.cpp:379-465
+                        const int key = c * W + r;
+                        const uint32_t s0 = key ? ks[key - 1] : 0u, s1 = ks[key];
+                        const int pre = max(0, pt - 1), post = min(NPRED - 1, pt + 1);
+                        unsigned acc = 0;
+                        for (uint32_t idx = s0; idx < s1; idx++) {
+                            const uint64_t en = ent[idx];
+                            const int ag = (int)(en & 1023), t0 = (int)((en >> 10) & 511), t1 = (int)((en >> 19) & 511);
+                            if (t1 < pre || t0 > post) continue;
+                            const int dh = (int)((en >> 28) & 3), dp = (int)((en >> 30) & 3), dn = (int)((en >> 32) & 3);
+                            const bool done = (en >> 34) & 1;
+                            const bool in_cur = t0 <= pt && pt <= t1, in_pre = t0 <= pre && pre <= t1,
+                                       in_post = t0 <= post && post <= t1;
+                            const int pdir = pt < t0 ? dp : (pt > t1 ? dn : dh);  // always the direction at row pt
+                            const bool cf = (d != pdir && tbit(nb, (pdir + 2) & 3)) || done;
+                            const bool other = ag != h;
+                            acc |= (in_cur && other ? 1u : 0u) | (in_pre && other ? 2u : 0u) | (in_post && other ? 4u : 0u) |
+                                   (in_cur && cf ? 8u : 0u) | (in_pre && cf ? 16u : 0u) | (in_post && cf ? 32u : 0u);
+                        }
+                        const bool cf = (acc & 1u) ? (acc & 8u) : (acc & 2u) ? (acc & 16u) : (acc & 4u) ? (acc & 32u) : false;
+                        if (cf) conflict = min(conflict, tot);
+                    }
+                    const bool is_target = r == tr && c == tc;
+                    if (is_target) own = min(own, tot);
+                    if (steps == stop_at) kind = 3;                                     // revisited (cell, dir): treeobs.cpp:476-481
+                    else if (is_target) kind = 4;
+                    else {
+                        if (gc == 0x8421u) total = 2;                                   // diamond crossing
+                        const int num = __popc(nb);
+                        if (total > 2 && num < 2) unusable = min(unusable, tot);
+                        if (num == 1) {
+                            if (total == 1) kind = 2;
+                            else {
+                                d = first_dir(nb); r += d_row(d); c += d_col(d); tot += 1; steps++;
+                                if (steps >= OBS_WALK_CAP && !cycle_checked) {          // suspiciously long: is this a rail cycle?
+                                    cycle_checked = true;
+                                    stop_at = walk_cycle_index(grid, W, tr, tc, r_start, c_start, d_start);
+                                    if (stop_at >= 0) {                                 // yes: redo the walk, ending at the first revisit
+                                        r = r_start; c = c_start; d = d_start; tot = tot_start; steps = 0;
+                                        own = other_agent = conflict = unusable = I_INF;
+                                        same = opp = malf = rtdn = 0; min_speed = 1.0f;
+                                    }
+                                }
+                            }
+                        } else if (num > 1) kind = 1;
+                        else {                     // treeobs.cpp:527-535 throws; report and stop here
+                            atomicOr(&b.status[e], FL_ST_BAD_CELL);
+                            kind = 3;
+                        }
+                    }
+                    if (kind) {
+                        active = false;
+                        const size_t ea = (size_t)e * N + h;
+                        float *forest = out_forest + ea * (FL_MAX_NODES * FL_NODE_F);
+                        int dnb, dmin;
+                        if (kind == 4) { dnb = tot; dmin = 0; }
+                        else {
+                            const unsigned dv = dm[((size_t)(r * W + c)) * 4 + d];
+                            dmin = dv == FL_DIST_INF ? I_INF : (int)dv;
+                            dnb = kind == 3 ? I_INF : tot;
+                        }
+                        store_node(forest + n * FL_NODE_F,                              // scale_node (treeobs.cpp:111-152)
+                                   make_float4(scale_i(own, T), -1.0f, scale_i(other_agent, T), scale_i(conflict, T)),
+                                   make_float4(scale_i(unusable, T), scale_i(dnb, T), scale_i(dmin, T), (float)same / Nf),
+                                   make_float4((float)opp / Nf, (float)malf / Nf, min_speed, (float)rtdn / Nf));
+                        // children in order L, F, R (treeobs.cpp:583-608); their BFS indices follow from the level's mask
+                        const uint32_t lsle = Tt.t_lsle[la], lmask = Tt.t_mask[la];
+                        const int ls = (int)(lsle & 0xFF), le = (int)(lsle >> 8);
+                        const int base = le + 3 * __popc(lmask & ((1u << (n - ls)) - 1u));
+                        const int nb2 = nibble(grid[r * W + c], d);
+                        uint32_t bits = 0;
+                        for (int a2 = -1; a2 <= 1; a2++) {
+                            const int idx = base + a2 + 1;
+                            if (idx >= FL_MAX_NODES) break;
+                            const int bd = (d + a2) & 3, rb = (bd + 2) & 3;
+                            int cd = bd;
+                            bool real = false;
+                            if (kind == 2 && tbit(nb2, rb)) { cd = rb; real = true; }
+                            else if (kind == 1 && tbit(nb2, bd)) { cd = bd; real = true; }
+                            Tt.n_rc[la * 31 + idx] = real ? (uint32_t)((r + d_row(cd)) & 0xFFFF) | ((uint32_t)(c + d_col(cd)) << 16) : 0xFFFFFFFFu;
+                            Tt.n_meta[la * 31 + idx] = (uint32_t)cd | ((uint32_t)(a2 + 1) << 2) | ((real ? 0u : 1u) << 4) | ((uint32_t)n << 8);
+                            Tt.n_tot[la * 31 + idx] = (uint32_t)(tot + 1);
+                            if (real) bits |= 1u << (idx - le);
+                            else store_null_node(forest + idx * FL_NODE_F);
+                        }
+                        if (bits) atomicOr(&Tt.t_next[la], bits);
+                        __threadfence_block();
+                        if (atomicSub(&Tt.t_pend[la], 1) == 1) {                        // last walk of this agent's level: release the next one
+                            __threadfence_block();
+                            const uint32_t nmask = atomicExch(&Tt.t_next[la], 0u);
+                            const int nls = le, nle = min(FL_MAX_NODES, le + 3 * __popc(lmask));
+                            if (nmask == 0) {                                           // no real node left: the rest is padding
+                                Tt.t_count[la] = nle;
+                                for (int k = nle; k < FL_MAX_NODES; k++) store_null_node(forest + k * FL_NODE_F);
+                                __threadfence_block();
+                                atomicAdd(Tt.n_done, 1);
+                            } else {
+                                Tt.t_mask[la] = nmask; Tt.t_lsle[la] = (uint32_t)nls | ((uint32_t)nle << 8);
+                                Tt.t_pend[la] = __popc(nmask);
+                                __threadfence_block();
+                                int slot = atomicAdd(Tt.q_tail, __popc(nmask));
+                                for (uint32_t m = nmask; m; m &= m - 1)
+                                    *reinterpret_cast<volatile uint16_t *>(&Tt.q[slot++]) = (uint16_t)((la << 5) | (nls + __ffs(m) - 1));
+                            }
+                        }
+                    }
+                }
+                const bool finished = !active && ld_vol_i32(Tt.n_done) >= na;
+                if (__all_sync(0xFFFFFFFFu, finished)) break;
+            }
+        }
+        __syncthreads();
+
+        // ---- phase 5a: evaluation orders (tool.h:468-524): node_order = height above the leaves ------
+        for (int la = tid; la < na; la += NT) {
+            const int count = Tt.t_count[la];
+            int8_t *no = Tt.norder + la * 32;
+            for (int k = 0; k < 32; k++) no[k] = k < count ? 0 : -2;
+            for (int k = count - 1; k >= 1; k--) {
+                const int pa = (int)((Tt.n_meta[la * 31 + k] >> 8) & 31);
+                no[pa] = (int8_t)max((int)no[pa], (int)no[k] + 1);
+            }
+        }
+        __syncthreads();
+        // ---- phase 5b: adjacency / node_order / edge_order, coalesced over the tile -------------------
+        {
+            const size_t base_a = (size_t)e * N + a0;
+            int32_t *adj = out_adj + base_a * ((FL_MAX_NODES - 1) * 3);
+            for (int k = tid; k < na * 90; k += NT) {
+                const int la = k / 90, j = (k % 90) / 3, comp = k % 3, node = j + 1;
+                int v = -2;
+                if (node < Tt.t_count[la]) {
+                    const uint32_t meta = Tt.n_meta[la * 31 + node];
+                    v = comp == 0 ? (int)((meta >> 8) & 31) : comp == 1 ? node : (int)((meta >> 2) & 3) - 1;
+                }
+                adj[k] = v;
+            }
+            int32_t *no = out_norder + base_a * FL_MAX_NODES;
+            for (int k = tid; k < na * FL_MAX_NODES; k += NT) no[k] = Tt.norder[(k / FL_MAX_NODES) * 32 + k % FL_MAX_NODES];
+            int32_t *eo = out_eorder + base_a * (FL_MAX_NODES - 1);
+            for (int k = tid; k < na * 30; k += NT) {
+                const int la = k / 30, node = k % 30 + 1;
+                eo[k] = node < Tt.t_count[la] ? (int)Tt.norder[la * 32 + ((Tt.n_meta[la * 31 + node] >> 8) & 31)] : -2;
+            }
+        }
+        __syncthreads();
+    }
+
+    // ---- phase 5c: agent attributes (feature_parser.cpp:3-98), coalesced over the environment ---------
+    {
+        float *dst = out_attr + (size_t)e * N * FL_ATTR_F;
+        const float curr_step = (float)elapsed / T;
+        for (int idx = tid; idx < N * FL_ATTR_F; idx += NT) {
+            const int i = idx / FL_ATTR_F, k = idx - i * FL_ATTR_F;
+            const uint32_t ra = A.rec_a[i], rb = A.rec_b[i];
+            const int st = ra & 7, road = (ra >> 3) & 15, idir = (ra >> 7) & 3, od = (ra >> 9) & 3, ctr = (ra >> 11) & 255,
+                      maxc = (ra >> 19) & 255, va = (ra >> 27) & 31, dir = A.info[i] & 3;
+            const int trans = rb & 0xFFFF, nmal01 = (rb >> 16) & 1, mal01 = (rb >> 17) & 1, sig_mal = (rb >> 18) & 1;
+            float v;
+            if (k < 7) v = k == st;
+            else if (k < 18) v = (k - 7) == road;
+            else if (k < 28) v = (k - 18) == nmal01;
+            else if (k < 32) v = (k - 28) == idir;
+            else if (k < 36) v = (k - 32) == dir;
+            else if (k < 40) v = (k - 36) == od;
+            else if (k < 49) {
+                switch (k - 40) {
+                case 0: v = st == MOVING; break;
+                case 1: v = D.dl[i] != 0; break;
+                case 2: v = sig_mal; break;
+                case 3: v = !mal01; break;
+                case 4: v = ctr == 0; break;
+                case 5: v = ctr == maxc; break;
+                case 6: v = st == MALFUNCTION || st == MAL_OFF; break;
+                case 7: v = off_map(st); break;
+                default: v = on_map(st); break;
+                }
+            } else if (k < 65) v = (trans >> (15 - (k - 49))) & 1;
+            else if (k < 70) v = (va >> (k - 65)) & 1;
+            else {
+                const float latest = A.f_latest[i], before_late = __fsub_rn(latest, curr_step), dist_f = A.f_dist[i];
+                switch (k - 70) {
+                case 0: v = (float)i / Nf; break;
+                case 1: v = curr_step; break;
+                case 2: v = A.f_earliest[i]; break;
+                case 3: v = latest; break;
+                case 4: v = A.f_arrival[i]; break;
+                case 5: v = before_late; break;
+                case 6: v = dist_f; break;
+                case 7: v = before_late < dist_f ? before_late : dist_f; break;
+                case 8: v = (float)maxc / 10.0f; break;
+                case 9: v = A.speed[i] / 1.0f; break;
+                case 10: v = (float)ctr / 10.0f; break;
+                case 11: v = (float)mal01 / 10.0f; break;
+                default: v = A.f_idist[i]; break;
+                }
+            }
+            dst[idx] = v;
+        }
+    }
+}
+
+}  // namespace

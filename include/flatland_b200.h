@@ -61,12 +61,15 @@ typedef struct FlBatch {
     int64_t n_slots;   /* unique-target slots allocated per env (max over envs) */
     int64_t S;         /* malfunction-schedule rows per env */
     int64_t ent_cap;   /* capacity of `entries` per env, >= N * (FL_PRED_DEPTH + 1) */
+    int64_t grid_stride; /* uint16 elements between the grids of consecutive envs, >= H*W, multiple of 8 */
+    int64_t dist_stride; /* uint16 elements between the distance maps of consecutive envs,
+                            >= n_slots*H*W*4, multiple of 8 (16-byte aligned blocks: moved by TMA bulk copies) */
     int64_t reserved0;
 
     /* ---- world, static after upload (RailEnv.reset generators stay reference Python) ---- */
-    const uint16_t *grid;      /* [E][H*W] transition bitmask per cell (core/transition_map.py:144) */
+    const uint16_t *grid;      /* [E][grid_stride] transition bitmask per cell (core/transition_map.py:144) */
     const int16_t *slot_rc;    /* [E][n_slots][2] target cell of each unique-target slot, (-1,-1) unused */
-    uint16_t *dist;            /* [E][n_slots][H*W][4] distance map, written by fl_distance_map */
+    uint16_t *dist;            /* [E][dist_stride] = per env [n_slots][H*W][4] distance map, written by fl_distance_map */
     const int32_t *max_steps;  /* [E] _max_episode_steps */
     const int16_t *init_rc;    /* [E][N][2] */
     const int16_t *tgt_rc;     /* [E][N][2] */
@@ -100,14 +103,16 @@ typedef struct FlBatch {
     uint32_t *status;     /* [E] FL_ST_* bits, sticky until cleared by the caller */
     uint32_t *cellinfo;   /* [E][H*W] occupancy map rebuilt by fl_observe, 0 = empty cell, else
                                        bits 31..21 highest handle on the cell + 1, 20..11 number of off-map
-                                       agents whose initial cell this is, 10..9 direction, 8 malfunctioning */
-    int32_t *occ_cell;    /* [E][N] cell each agent was entered under in cellinfo, -1 = none */
+                                       agents whose initial cell this is, 10..9 direction, 8 malfunctioning.
+                                       Only touched when the map does not fit in shared memory (large grids). */
+    int32_t *occ_cell;    /* [E][N] cell each agent was entered under in cellinfo, -1 = none (same) */
     int64_t *stats;       /* [E][4] running totals since upload: episodes finished, agents arrived at episode
                                     end, sum of end-of-episode rewards, agent-steps (eval_env.py:81-94 final_metric) */
 
     /* ---- per-step observation workspace (rebuilt by every fl_observe) ---- */
-    uint32_t *key_start;  /* [E][W*W + H + 1] CSR offsets of predicted-occupancy entries per cell id c*W+r */
-    uint64_t *entries;    /* [E][ent_cap] predicted-occupancy intervals sorted by cell id */
+    uint32_t *key_start;  /* [E][W*W + H + 1] CSR end offsets of predicted-occupancy entries per cell id c*W+r
+                                       (spill space: used only when the index does not fit in shared memory) */
+    uint64_t *entries;    /* [E][ent_cap] predicted-occupancy intervals sorted by cell id (spill space) */
 } FlBatch;
 
 int fl_abi_version(void);
