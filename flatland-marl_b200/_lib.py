@@ -11,7 +11,7 @@ ACTION_ABSENT = 255
 ST_STEP_AFTER_DONE, ST_AUTO_RESET, ST_BAD_CELL = 1, 2, 4
 FLAG_AUTO_RESET = 1
 
-_I64 = ["E", "N", "H", "W", "n_slots", "S", "ent_cap", "grid_stride", "dist_stride", "reserved0"]
+_I64 = ["E", "N", "H", "W", "n_slots", "S", "ent_cap", "grid_stride", "dist_stride", "debug_clocks"]
 _PTR = ["grid", "slot_rc", "dist", "max_steps", "init_rc", "tgt_rc", "init_dir", "max_count", "slot", "speed",
         "earliest", "latest", "sched",
         "rc", "old_rc", "dir", "old_dir", "state", "ctr", "mal", "saved", "sig_mal", "deadlocked", "done", "nmal",
@@ -31,7 +31,7 @@ class FlObsBuffers(C.Structure):
 
 
 EXPORTS = ["fl_abi_version", "fl_batch_sizeof", "fl_error_string", "fl_distance_map", "fl_reset", "fl_step",
-           "fl_observe", "fl_step_observe_host", "fl_launch_count", "fl_profile_num_kernels", "fl_profile_kernel_name",
+           "fl_observe", "fl_batch_slice", "fl_step_observe_host", "fl_launch_count", "fl_profile_num_kernels", "fl_profile_kernel_name",
            "fl_profile_enable", "fl_profile_collect"]
 
 _lib = None
@@ -61,7 +61,8 @@ def lib():
     L.fl_step.argtypes = [C.POINTER(FlBatch), P, P, P, C.c_uint32, P]
     L.fl_observe.argtypes = [C.POINTER(FlBatch)] + [P] * 8
     L.fl_step_observe_host.argtypes = [C.POINTER(FlBatch), P, P, C.POINTER(FlObsBuffers), C.POINTER(FlObsBuffers),
-                                       C.c_uint32, P]
+                                       C.c_uint32, C.c_int, P, P]
+    L.fl_batch_slice.argtypes = [C.POINTER(FlBatch), C.c_int64, C.c_int64, C.POINTER(FlBatch)]
     L.fl_profile_num_kernels.restype = C.c_int
     L.fl_profile_kernel_name.restype = C.c_char_p
     L.fl_profile_kernel_name.argtypes = [C.c_int]
@@ -69,7 +70,7 @@ def lib():
     L.fl_profile_enable.restype = None
     L.fl_profile_collect.argtypes = [P, P, C.c_int]
     L.fl_profile_collect.restype = C.c_int
-    for f in ("fl_distance_map", "fl_reset", "fl_step", "fl_observe", "fl_step_observe_host"):
+    for f in ("fl_distance_map", "fl_reset", "fl_step", "fl_observe", "fl_step_observe_host", "fl_batch_slice"):
         getattr(L, f).restype = C.c_int
     if L.fl_batch_sizeof() != C.sizeof(FlBatch):
         raise FlatlandB200Error("FlBatch layout mismatch: library %d bytes, binding %d bytes"

@@ -21,6 +21,7 @@
 #include <cuda_runtime.h>
 
 #include <atomic>
+#include <cstdlib>
 #include <mutex>
 #include <vector>
 
@@ -83,45 +84,52 @@ constexpr int SMEM_MAX = 227 * 1024;
 int align_up(int v, int a) { return (v + a - 1) / a * a; }
 
 // Shared-memory plan of k_observe for one configuration.  Mandatory: barrier + scalars, scan partials, the
-// per-agent records, the deadlock scratch and the tree tile.  Optional, in this order while they fit: rail
-// grid, occupancy words, key counters, distance maps; predicted-occupancy entries take the rest.  The budget
-// per CTA is chosen so that as many CTAs as possible share an SM when everything fits.
+// per-agent records, the deadlock scratch and the tree tile (which doubles as the unsorted-entry buffer).
+// Optional, in this order while they fit: rail grid, occupancy words, key counters, the sorted predicted-
+// occupancy entries, and last the distance maps.  The budget per CTA is the largest that still lets
+// `ctas` CTAs share an SM; ctas is the largest count (<= 6) for which grid, occupancy, counters and a
+// typical entry array fit.  FL_OBS_CTAS / FL_OBS_NT override the choice (tuning only).
 ObsLayout make_obs_layout(const FlBatch *b, int nt) {
     const int N = (int)b->N, HW = (int)(b->H * b->W), K = (int)(b->W * b->W + b->H);
     ObsLayout L;
     L.tile = N < OBS_MAX_TILE ? N : OBS_MAX_TILE;
     int off = 0;
-    auto take = [&](int bytes) { const int o = off; off = align_up(off + bytes, 128); return o; };
+    auto take = [&](long long bytes) { const int o = off; off = align_up(off + (int)bytes, 128); return o; };
     L.bar = take(32);
     L.part = take(nt * 4);
     L.ag = take(14 * N * 4);
     L.dl = take(18 * N);
-    L.tree = take((3 * L.tile * 31 + 5 * L.tile + 4 + L.tile * 8) * 4 + L.tile * 30 * 2);
-    const int grid_b = (int)b->grid_stride * 2, ci_b = HW * 4, ks_b = (K + 1) * 4;
-    const long long dist_b = (long long)b->dist_stride * 2;
-    const long long ent_typ = (long long)N * 96 * 8;   // typical upper bound of predicted path cells per agent
-    const long long want = (long long)off + align_up(grid_b, 128) + align_up(ci_b, 128) + align_up(ks_b, 128) +
-                           align_up((int)(dist_b < SMEM_MAX ? dist_b : SMEM_MAX), 128) + ent_typ;
-    int budget = SMEM_MAX / 2 - 1024;
-    if (want <= SMEM_MAX - 1024) {
-        int ctas = (int)((SMEM_MAX) / (want + 1024));
-        if (ctas < 1) ctas = 1;
-        if (ctas > 8) ctas = 8;
-        budget = SMEM_MAX / ctas - 1024;
-    }
-    auto opt = [&](long long bytes) { if ((long long)off + bytes > budget) return -1; return take((int)bytes); };
+    const int tree_b = (3 * L.tile * 31 + 5 * L.tile + 4 + L.tile * 8) * 4 + L.tile * 30 * 2;
+    L.tree = take(tree_b);
+    L.tmp_cap = tree_b / 6;
+    const long long grid_b = b->grid_stride * 2, ci_b = (long long)HW * 4, ks_b = (long long)(K + 1) * 4;
+    const long long dist_b = b->dist_stride * 2, ent_typ = (long long)N * 48 * 4;
+    int ctas = 1;
+    if (const char *s = getenv("FL_OBS_CTAS")) ctas = atoi(s) > 0 ? atoi(s) : 1;
+    else
+        for (int c = 6; c >= 1; c--)
+            if (off + grid_b + ci_b + ks_b + ent_typ + 4 * 128 <= SMEM_MAX / c - 1024) { ctas = c; break; }
+    const int budget = SMEM_MAX / ctas - 1024;
+    auto opt = [&](long long bytes) { if ((long long)off + bytes + 128 > budget) return -1; return take(bytes); };
     L.grid = opt(grid_b);
     L.ci = opt(ci_b);
-    L.ks = opt(ks_b);
-    L.dist = opt(dist_b);
-    L.ent = off;
-    long long cap = ((long long)budget - off) / 8;
-    if (cap < 0) cap = 0;
-    if (cap > (long long)N * NPRED) cap = (long long)N * NPRED;
-    L.ent_cap = (int)cap;
-    off += (int)cap * 8;
+    L.ks = K <= 0xFFFF ? opt(ks_b) : -1;
+    // entries: at least the typical size, the rest of the budget when the distance maps do not fit anyway
+    long long ent_b = (long long)budget - off - 128;
+    const bool dist_fits = ent_b - ent_typ >= dist_b + 128;
+    if (dist_fits) ent_b -= dist_b + 128;
+    if (ent_b > (long long)N * NPRED * 4) ent_b = (long long)N * NPRED * 4;
+    if (ent_b < 0) ent_b = 0;
+    L.ent = take(ent_b);
+    L.ent_cap = (int)(ent_b / 4);
+    L.dist = dist_fits ? opt(dist_b) : -1;
     L.total = off;
     return L;
+}
+
+int obs_threads(const FlBatch *b) {
+    if (const char *s = getenv("FL_OBS_NT")) { const int v = atoi(s); if (v == 64 || v == 128 || v == 256) return v; }
+    return b->N <= 24 ? 64 : 128;
 }
 
 int finish(cudaError_t launch_err) { return launch_err == cudaSuccess ? FL_OK : (int)launch_err; }
@@ -220,10 +228,10 @@ int fl_observe(const FlBatch *b, float *d_agent_attr, float *d_forest, int32_t *
     if (!d_agent_attr || !d_forest || !d_adjacency || !d_node_order || !d_edge_order || !d_valid_actions || !d_dist_target)
         return FL_ERR_BAD_ARG;
     cudaStream_t st = (cudaStream_t)stream;
-    const int nt = b->N <= 24 ? 128 : 256;
+    const int nt = obs_threads(b);
     const ObsLayout lay = make_obs_layout(b, nt);
     if (lay.total > SMEM_MAX) return FL_ERR_SMEM;
-    auto kern = nt == 128 ? k_observe<128> : k_observe<256>;
+    auto kern = nt == 64 ? k_observe<64> : nt == 128 ? k_observe<128> : k_observe<256>;
     if (lay.total > 48 * 1024) {
         cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, lay.total);
         if (err != cudaSuccess) return (int)err;
@@ -234,33 +242,88 @@ int fl_observe(const FlBatch *b, float *d_agent_attr, float *d_forest, int32_t *
     return finish(cudaGetLastError());
 }
 
+int fl_batch_slice(const FlBatch *b, int64_t e0, int64_t n, FlBatch *out) {
+    if (!b || !out || e0 < 0 || n <= 0 || e0 + n > b->E) return FL_ERR_BAD_ARG;
+    *out = *b;
+    out->E = n;
+    const int64_t N = b->N, HW = b->H * b->W, K1 = b->W * b->W + b->H + 1;
+#define FL_ADV(field, per_env) out->field = b->field ? b->field + (size_t)e0 * (size_t)(per_env) : b->field;
+    FL_ADV(grid, b->grid_stride) FL_ADV(slot_rc, b->n_slots * 2) FL_ADV(dist, b->dist_stride) FL_ADV(max_steps, 1)
+    FL_ADV(init_rc, N * 2) FL_ADV(tgt_rc, N * 2) FL_ADV(init_dir, N) FL_ADV(max_count, N) FL_ADV(slot, N) FL_ADV(speed, N)
+    FL_ADV(earliest, N) FL_ADV(latest, N) FL_ADV(sched, b->S * N)
+    FL_ADV(rc, N * 2) FL_ADV(old_rc, N * 2) FL_ADV(dir, N) FL_ADV(old_dir, N) FL_ADV(state, N) FL_ADV(ctr, N) FL_ADV(mal, N)
+    FL_ADV(saved, N) FL_ADV(sig_mal, N) FL_ADV(deadlocked, N) FL_ADV(done, N) FL_ADV(nmal, N) FL_ADV(arrival, N)
+    FL_ADV(elapsed, 1) FL_ADV(sched_pos, 1) FL_ADV(done_all, 1) FL_ADV(status, 1) FL_ADV(cellinfo, HW) FL_ADV(occ_cell, N)
+    FL_ADV(stats, 4) FL_ADV(key_start, K1) FL_ADV(entries, b->ent_cap) FL_ADV(debug_clocks, 16)
+#undef FL_ADV
+    return FL_OK;
+}
+
+namespace {
+// events that order the copy stream behind the compute stream, one per chunk and device, created on first use
+cudaEvent_t chunk_event(int k) {
+    static std::mutex mu;
+    static std::vector<std::vector<cudaEvent_t>> pool;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    std::lock_guard<std::mutex> lk(mu);
+    if ((int)pool.size() <= dev) pool.resize(dev + 1);
+    while ((int)pool[dev].size() <= k) {
+        cudaEvent_t e;
+        cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
+        pool[dev].push_back(e);
+    }
+    return pool[dev][k];
+}
+}  // namespace
+
 int fl_step_observe_host(const FlBatch *b, const uint8_t *h_actions, uint8_t *d_actions, const FlObsBuffers *d_out,
-                         const FlObsBuffers *h_out, uint32_t flags, void *stream) {
+                         const FlObsBuffers *h_out, uint32_t flags, int n_chunks, void *stream, void *copy_stream) {
     if (int rc = check_batch(b)) return rc;
     if (!h_actions || !d_actions || !d_out || !h_out) return FL_ERR_BAD_ARG;
-    cudaStream_t st = (cudaStream_t)stream;
-    const size_t EN = (size_t)(b->E * b->N);
-    cudaError_t err = cudaMemcpyAsync(d_actions, h_actions, EN, cudaMemcpyHostToDevice, st);
+    cudaStream_t st = (cudaStream_t)stream, cs = copy_stream ? (cudaStream_t)copy_stream : st;
+    if (n_chunks < 1 || !copy_stream) n_chunks = 1;
+    if (n_chunks > b->E) n_chunks = (int)b->E;
+    const size_t N = (size_t)b->N;
+    cudaError_t err = cudaMemcpyAsync(d_actions, h_actions, (size_t)b->E * N, cudaMemcpyHostToDevice, st);
     if (err != cudaSuccess) return (int)err;
-    if (int rc = fl_step(b, d_actions, d_out->rewards, d_out->dones, flags, stream)) return rc;
-    if (int rc = fl_observe(b, d_out->agent_attr, d_out->forest, d_out->adjacency, d_out->node_order, d_out->edge_order,
-                            d_out->valid_actions, d_out->dist_target, stream))
-        return rc;
-#define FL_D2H(field, bytes)                                                                              \
-    if (h_out->field) {                                                                                   \
-        err = cudaMemcpyAsync(h_out->field, d_out->field, (bytes), cudaMemcpyDeviceToHost, st);           \
-        if (err != cudaSuccess) return (int)err;                                                          \
+    for (int c = 0; c < n_chunks; c++) {
+        const int64_t e0 = b->E * c / n_chunks, e1 = b->E * (c + 1) / n_chunks, n = e1 - e0;
+        const size_t a0 = (size_t)e0 * N, an = (size_t)n * N;       // first agent / agents of the chunk
+        FlBatch sub;
+        if (int rc = fl_batch_slice(b, e0, n, &sub)) return rc;
+        if (int rc = fl_step(&sub, d_actions + a0, d_out->rewards + a0, d_out->dones + (size_t)e0 * (N + 1), flags, stream)) return rc;
+        if (int rc = fl_observe(&sub, d_out->agent_attr + a0 * FL_ATTR_F, d_out->forest + a0 * FL_MAX_NODES * FL_NODE_F,
+                                d_out->adjacency + a0 * (FL_MAX_NODES - 1) * 3, d_out->node_order + a0 * FL_MAX_NODES,
+                                d_out->edge_order + a0 * (FL_MAX_NODES - 1), d_out->valid_actions + a0 * 5,
+                                d_out->dist_target + a0, stream))
+            return rc;
+        if (cs != st) {                                             // the chunk's copies wait for its kernels only
+            cudaEvent_t ev = chunk_event(c);
+            if ((err = cudaEventRecord(ev, st)) != cudaSuccess) return (int)err;
+            if ((err = cudaStreamWaitEvent(cs, ev, 0)) != cudaSuccess) return (int)err;
+        }
+#define FL_D2H(field, first, count, elem)                                                                              \
+    if (h_out->field) {                                                                                                \
+        err = cudaMemcpyAsync(h_out->field + (first), d_out->field + (first), (size_t)(count) * (elem), cudaMemcpyDeviceToHost, cs); \
+        if (err != cudaSuccess) return (int)err;                                                                       \
     }
-    FL_D2H(rewards, EN * 4)
-    FL_D2H(dones, (size_t)b->E * (b->N + 1))
-    FL_D2H(agent_attr, EN * FL_ATTR_F * 4)
-    FL_D2H(forest, EN * FL_MAX_NODES * FL_NODE_F * 4)
-    FL_D2H(adjacency, EN * (FL_MAX_NODES - 1) * 3 * 4)
-    FL_D2H(node_order, EN * FL_MAX_NODES * 4)
-    FL_D2H(edge_order, EN * (FL_MAX_NODES - 1) * 4)
-    FL_D2H(valid_actions, EN * 5)
-    FL_D2H(dist_target, EN * 4)
+        FL_D2H(rewards, a0, an, 4)
+        FL_D2H(dones, (size_t)e0 * (N + 1), (size_t)n * (N + 1), 1)
+        FL_D2H(agent_attr, a0 * FL_ATTR_F, an * FL_ATTR_F, 4)
+        FL_D2H(forest, a0 * FL_MAX_NODES * FL_NODE_F, an * FL_MAX_NODES * FL_NODE_F, 4)
+        FL_D2H(adjacency, a0 * (FL_MAX_NODES - 1) * 3, an * (FL_MAX_NODES - 1) * 3, 4)
+        FL_D2H(node_order, a0 * FL_MAX_NODES, an * FL_MAX_NODES, 4)
+        FL_D2H(edge_order, a0 * (FL_MAX_NODES - 1), an * (FL_MAX_NODES - 1), 4)
+        FL_D2H(valid_actions, a0 * 5, an * 5, 1)
+        FL_D2H(dist_target, a0, an, 4)
 #undef FL_D2H
+    }
+    if (cs != st) {                                                 // `stream` completes when the last copy has landed
+        cudaEvent_t ev = chunk_event(n_chunks);
+        if ((err = cudaEventRecord(ev, cs)) != cudaSuccess) return (int)err;
+        if ((err = cudaStreamWaitEvent(st, ev, 0)) != cudaSuccess) return (int)err;
+    }
     return FL_OK;
 }
 

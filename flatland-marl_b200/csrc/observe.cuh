@@ -7,10 +7,10 @@
 //   1  loader view per agent (loader.cpp:8-179, 221-327): virtual position, valid actions, distance to
 //      target, the per-cell occupancy word (treeobs.cpp:67-92) built with shared-memory atomics.
 //   2  the serial, sticky DeadlockChecker (deadlock_checker.cpp:11-110) on lane 0 of the last warp, running
-//      concurrently with phases 3 and 4 (its result is only needed by the attribute vector).
+//      concurrently with phase 3 (its result is only needed by the attribute vector).
 //   3  greedy shortest-path predictions (predictions.cpp:13-235) as occupancy intervals, counting-sorted by
-//      the reference's cell id c*W+r into a CSR inverse index  cell id -> intervals  (two walks: count,
-//      scatter).
+//      the reference's cell id c*W+r into a CSR inverse index  cell id -> intervals, every bucket ordered by
+//      start time so that the tree walk only scans the entries of a three-step time window.
 //   4  the 31-node branch trees (treeobs.cpp:154-610).  One LANE per branch walk: walks are work items in a
 //      shared-memory queue; a lane that finishes a walk creates its node's three children in place (their
 //      BFS indices follow from the bit mask of real nodes of the level) and the lane that finishes the
@@ -32,7 +32,7 @@ constexpr int OBS_WALK_CAP = 1024;      // branch walks longer than this are che
 constexpr int I_INF = 0x7fffffff;
 
 struct ObsLayout {   // byte offsets into dynamic shared memory (host: make_obs_layout); < 0 = lives in global memory
-    int grid, ci, dist, ks, ent, ent_cap, part, ag, dl, tree, bar, total, tile;
+    int grid, ci, dist, ks, ent, ent_cap, tmp_cap, part, ag, dl, tree, bar, total, tile;
 };
 
 // ---- mbarrier + 1-D TMA bulk copy (global -> shared), sm_90+ ------------------------------------
@@ -130,10 +130,13 @@ DEVI void walk_prediction(const uint16_t *g, const uint16_t *dm, int W, int vr, 
     }
 }
 
-DEVI uint64_t pack_entry(int agent, int t0, int t1, int dh, int dp, int dn, int done) {
-    return (uint64_t)agent | ((uint64_t)t0 << 10) | ((uint64_t)t1 << 19) | ((uint64_t)dh << 28) |
-           ((uint64_t)dp << 30) | ((uint64_t)dn << 32) | ((uint64_t)done << 34);
+// Predicted-occupancy entry, 4 bytes: agent | t0 << 10 | last << 19 | dir_here << 20 | dir_prev << 22 | dir_next << 24.
+// The interval end is implied: 500 for the last element of a path ("last"), 0 for element 0, t0 + tpc - 1 otherwise.
+DEVI uint32_t pack_entry(int agent, int t0, int t1, int dh, int dp, int dn) {
+    return (uint32_t)agent | ((uint32_t)t0 << 10) | ((uint32_t)(t1 == NPRED - 1) << 19) | ((uint32_t)dh << 20) |
+           ((uint32_t)dp << 22) | ((uint32_t)dn << 24);
 }
+DEVI uint32_t entry_sort_key(uint32_t en) { return (((en >> 19) & 1u) ? 0u : 512u) + ((en >> 10) & 511u); }  // long-lived first, then by t0
 
 // loader.cpp:273-312: valid-action mask, bit a = action a allowed
 DEVI int valid_actions_of(const uint16_t *g, int W, int st, int ctr, int r, int c, int d) {
@@ -339,7 +342,7 @@ k_observe(FlBatch b, ObsLayout lay, float *__restrict__ out_attr, float *__restr
     uint32_t *ks = lay.ks >= 0 ? reinterpret_cast<uint32_t *>(smraw + lay.ks) : b.key_start + (size_t)e * (K + 1);
     uint32_t *s_part = reinterpret_cast<uint32_t *>(smraw + lay.part);
     uint64_t *bar = reinterpret_cast<uint64_t *>(smraw + lay.bar);
-    int *s_misc = reinterpret_cast<int *>(smraw + lay.bar + 16);     // [0] entries total
+    int *s_misc = reinterpret_cast<int *>(smraw + lay.bar + 16);
 
     ObsAgents A;
     {
@@ -373,6 +376,10 @@ k_observe(FlBatch b, ObsLayout lay, float *__restrict__ out_attr, float *__restr
         Tt.q = reinterpret_cast<uint16_t *>(p);
     }
 
+    // optional phase timestamps (tuning only): FlBatch.debug_clocks [E][16] int64, NULL = off
+    int64_t *dbg = b.debug_clocks ? b.debug_clocks + (size_t)e * 16 : nullptr;
+#define OBS_TICK(k) do { if (dbg && tid == 0) dbg[k] = clock64(); } while (0)
+    if (dbg && tid == 0) dbg[15] = clock64();
     // ---- phase 0: TMA bulk copies of the static world ---------------------------------------------
     const bool use_tma = lay.grid >= 0 || lay.dist >= 0;
     if (use_tma && tid == 0) {
@@ -390,7 +397,9 @@ k_observe(FlBatch b, ObsLayout lay, float *__restrict__ out_attr, float *__restr
     else { for (int i = tid; i < N; i += NT) { const int oc = b.occ_cell[(size_t)e * N + i]; if (oc >= 0) ci[oc] = 0; } }
     const float T = (float)b.max_steps[e], Nf = (float)N;
     const int elapsed = b.elapsed[e];
+    if (tid < 4) s_misc[tid] = 0;                  // [0] entries, [1] unsorted entries written, [2] max time per cell
     __syncthreads();                               // mbarrier initialised, counters zeroed
+    OBS_TICK(0);
     if (use_tma) mbar_wait(bar, 0);
 
     // ---- phase 1: loader view (loader.cpp:8-179, 221-327) -----------------------------------------
@@ -412,6 +421,7 @@ k_observe(FlBatch b, ObsLayout lay, float *__restrict__ out_attr, float *__restr
         A.info[i] = (uint32_t)d | ((uint32_t)st << 2) | ((uint32_t)(st == DONE) << 5) | ((uint32_t)slot << 8) |
                     ((uint32_t)min(tpc, 255) << 24);
         A.speed[i] = speed;
+        atomicMax(&s_misc[2], min(tpc, 255));
         A.cellid[i] = on_map(st) ? r * W + c : -1;
         A.initcell[i] = off_map(st) ? ip.x * W + ip.y : -1;
         const int trans = on_map(st) ? (int)grid[r * W + c] : 0;
@@ -459,23 +469,31 @@ k_observe(FlBatch b, ObsLayout lay, float *__restrict__ out_attr, float *__restr
         if (ic >= 0 && ld_vol_u32(&ci[ic]) != 0) atomicAdd(&ci[ic], 1u << 11);
     }
     __syncthreads();
+    OBS_TICK(1);
 
     // ---- phase 2 (last warp, lane 0) || phase 3 (all other warps, named barrier 1): deadlocks, predictions ----
     const bool dl_warp = warp == NT / 32 - 1;
     constexpr int NW = NT - 32;                    // threads walking predictions
-    uint64_t *ent = reinterpret_cast<uint64_t *>(smraw + lay.ent);
+    uint32_t *ent = reinterpret_cast<uint32_t *>(smraw + lay.ent);
+    uint32_t *tmp_pay = reinterpret_cast<uint32_t *>(smraw + lay.tree);          // unsorted entries, aliasing the tree tile
+    uint16_t *tmp_key = reinterpret_cast<uint16_t *>(tmp_pay + lay.tmp_cap);
     if (dl_warp) {
-        if (lane == 0) update_deadlocks(D, ci, N, H, W);
+        if (lane == 0) { update_deadlocks(D, ci, N, H, W); if (dbg) dbg[8] = clock64(); }
         __syncwarp();
     } else {
-        for (int i = tid; i < N; i += NW) {        // pass 1: count entries per cell id
+        for (int i = tid; i < N; i += NW) {        // one greedy walk per agent: count per cell id, keep the entries unsorted
             const uint32_t info = A.info[i];
             const int vr = (int)(short)(A.vrc[i] & 0xFFFF), vc = (int)(A.vrc[i] >> 16);
             const int tr = (int)(short)(A.tgt[i] & 0xFFFF), tc = (int)(A.tgt[i] >> 16);
             walk_prediction(grid, dist + (size_t)((info >> 8) & 0xFFFF) * HW * 4, W, vr, vc, (int)(info & 3), tr, tc,
-                            (int)(info >> 24), [&](int key, int, int, int, int, int) { atomicAdd(&ks[key], 1u); });
+                            (int)(info >> 24), [&](int key, int t0, int t1, int dh, int dp, int dn) {
+                                atomicAdd(&ks[key], 1u);
+                                const int pos = atomicAdd(&s_misc[1], 1);
+                                if (pos < lay.tmp_cap) { tmp_pay[pos] = pack_entry(i, t0, t1, dh, dp, dn); tmp_key[pos] = (uint16_t)key; }
+                            });
         }
         named_bar_sync(1, NW);
+        OBS_TICK(2);
         // exclusive scan of ks[0..K] (K+1 values; the last becomes the total)
         const int per = (K + 1 + NW - 1) / NW, lo = min(tid * per, K + 1), hi = min(lo + per, K + 1);
         uint32_t sum = 0;
@@ -492,23 +510,39 @@ k_observe(FlBatch b, ObsLayout lay, float *__restrict__ out_attr, float *__restr
         for (int k = lo; k < hi; k++) { const uint32_t v = ks[k]; ks[k] = run; run += v; }
         named_bar_sync(1, NW);
         const int n_ent = (int)s_part[NW - 1];
-        if (n_ent > lay.ent_cap) ent = b.entries + (size_t)e * b.ent_cap;
         if (tid == 0) s_misc[0] = n_ent;
-        // pass 2: scatter.  ks[key] is advanced to the END of its bucket; bucket k is [k ? ks[k-1] : 0, ks[k]) afterwards.
-        for (int i = tid; i < N; i += NW) {
-            const uint32_t info = A.info[i];
-            const int vr = (int)(short)(A.vrc[i] & 0xFFFF), vc = (int)(A.vrc[i] >> 16);
-            const int tr = (int)(short)(A.tgt[i] & 0xFFFF), tc = (int)(A.tgt[i] >> 16);
-            const int done_flag = (info >> 5) & 1;
-            walk_prediction(grid, dist + (size_t)((info >> 8) & 0xFFFF) * HW * 4, W, vr, vc, (int)(info & 3), tr, tc,
-                            (int)(info >> 24), [&](int key, int t0, int t1, int dh, int dp, int dn) {
-                                const uint32_t pos = atomicAdd(&ks[key], 1u);
-                                ent[pos] = pack_entry(i, t0, t1, dh, dp, dn, done_flag);
-                            });
+        // scatter.  ks[key] is advanced to the END of its bucket; bucket k is [k ? ks[k-1] : 0, ks[k]) afterwards.
+        if (n_ent <= lay.tmp_cap && n_ent <= lay.ent_cap && K <= 0xFFFF) {
+            for (int j = tid; j < n_ent; j += NW) ent[atomicAdd(&ks[tmp_key[j]], 1u)] = tmp_pay[j];
+        } else {                                    // does not fit in shared memory: walk again, scatter into the global spill space
+            ent = reinterpret_cast<uint32_t *>(b.entries + (size_t)e * b.ent_cap);
+            for (int i = tid; i < N; i += NW) {
+                const uint32_t info = A.info[i];
+                const int vr = (int)(short)(A.vrc[i] & 0xFFFF), vc = (int)(A.vrc[i] >> 16);
+                const int tr = (int)(short)(A.tgt[i] & 0xFFFF), tc = (int)(A.tgt[i] >> 16);
+                walk_prediction(grid, dist + (size_t)((info >> 8) & 0xFFFF) * HW * 4, W, vr, vc, (int)(info & 3), tr, tc,
+                                (int)(info >> 24), [&](int key, int t0, int t1, int dh, int dp, int dn) {
+                                    ent[atomicAdd(&ks[key], 1u)] = pack_entry(i, t0, t1, dh, dp, dn);
+                                });
+            }
+        }
+        named_bar_sync(1, NW);
+        // order every bucket: long-lived entries first, then by t0, so that the tree walk scans a time window only
+        for (int key = tid; key < K; key += NW) {
+            const int s0 = key ? (int)ks[key - 1] : 0, s1 = (int)ks[key];
+            for (int x = s0 + 1; x < s1; x++) {
+                const uint32_t v = ent[x], kv = entry_sort_key(v);
+                int y = x - 1;
+                while (y >= s0 && entry_sort_key(ent[y]) > kv) { ent[y + 1] = ent[y]; y--; }
+                ent[y + 1] = v;
+            }
         }
     }
     __syncthreads();
-    if (dl_warp && s_misc[0] > lay.ent_cap) ent = b.entries + (size_t)e * b.ent_cap;
+    OBS_TICK(3);
+    if (dl_warp && !(s_misc[0] <= lay.tmp_cap && s_misc[0] <= lay.ent_cap && K <= 0xFFFF))
+        ent = reinterpret_cast<uint32_t *>(b.entries + (size_t)e * b.ent_cap);
+    const int tpc_max = s_misc[2];
     for (int i = tid; i < N; i += NT) b.deadlocked[(size_t)e * N + i] = D.dl[i];
 
     // ---- phase 4: branch trees, OBS_TILE agents at a time -----------------------------------------
@@ -554,6 +588,7 @@ k_observe(FlBatch b, ObsLayout lay, float *__restrict__ out_attr, float *__restr
             }
         }
         __syncthreads();
+    OBS_TICK(4);
 
         // persistent lanes: one branch walk (treeobs.cpp:258-610) per lane, one cell per iteration
         {
@@ -567,7 +602,9 @@ k_observe(FlBatch b, ObsLayout lay, float *__restrict__ out_attr, float *__restr
             float min_speed = 1.0f, tpc_f = 1.0f;
             int h = 0, tr = 0, tc = 0;
             const uint16_t *dm = dist;
+            int iters = 0;
             while (true) {
+                iters++;
                 if (!active) {
                     if (claim < 0) claim = atomicAdd(Tt.q_head, 1);
                     const unsigned it = claim < qcap ? ld_vol_u16(&Tt.q[claim]) : (unsigned)OBS_Q_EMPTY;
@@ -610,11 +647,19 @@ k_observe(FlBatch b, ObsLayout lay, float *__restrict__ out_attr, float *__restr
                         const int pre = max(0, pt - 1), post = min(NPRED - 1, pt + 1);
                         unsigned acc = 0;
                         for (uint32_t idx = s0; idx < s1; idx++) {
-                            const uint64_t en = ent[idx];
-                            const int ag = (int)(en & 1023), t0 = (int)((en >> 10) & 511), t1 = (int)((en >> 19) & 511);
-                            if (t1 < pre || t0 > post) continue;
-                            const int dh = (int)((en >> 28) & 3), dp = (int)((en >> 30) & 3), dn = (int)((en >> 32) & 3);
-                            const bool done = (en >> 34) & 1;
+                            const uint32_t en = ent[idx];
+                            const int t0 = (int)((en >> 10) & 511);
+                            if ((en >> 19) & 1u) { if (t0 > post) continue; }           // long-lived entries come first
+                            else {                                                       // then regular ones ordered by t0
+                                if (t0 > post) break;
+                                if (t0 + tpc_max <= pre) continue;
+                            }
+                            const int ag = (int)(en & 1023);
+                            const uint32_t ainfo = A.info[ag];
+                            const int t1 = ((en >> 19) & 1u) ? NPRED - 1 : (t0 ? t0 + (int)(ainfo >> 24) - 1 : 0);
+                            if (t1 < pre) continue;
+                            const int dh = (int)((en >> 20) & 3), dp = (int)((en >> 22) & 3), dn = (int)((en >> 24) & 3);
+                            const bool done = (ainfo >> 5) & 1;
                             const bool in_cur = t0 <= pt && pt <= t1, in_pre = t0 <= pre && pre <= t1,
                                        in_post = t0 <= post && post <= t1;
                             const int pdir = pt < t0 ? dp : (pt > t1 ? dn : dh);  // always the direction at row pt
@@ -714,8 +759,10 @@ k_observe(FlBatch b, ObsLayout lay, float *__restrict__ out_attr, float *__restr
                 const bool finished = !active && ld_vol_i32(Tt.n_done) >= na;
                 if (__all_sync(0xFFFFFFFFu, finished)) break;
             }
+            if (dbg && tid == 0) { dbg[9] = iters; dbg[10] = s_misc[0]; }
         }
         __syncthreads();
+    OBS_TICK(5);
 
         // ---- phase 5a: evaluation orders (tool.h:468-524): node_order = height above the leaves ------
         for (int la = tid; la < na; la += NT) {
@@ -750,6 +797,7 @@ k_observe(FlBatch b, ObsLayout lay, float *__restrict__ out_attr, float *__restr
             }
         }
         __syncthreads();
+    OBS_TICK(6);
     }
 
     // ---- phase 5c: agent attributes (feature_parser.cpp:3-98), coalesced over the environment ---------
@@ -804,6 +852,9 @@ k_observe(FlBatch b, ObsLayout lay, float *__restrict__ out_attr, float *__restr
             dst[idx] = v;
         }
     }
+    __syncthreads();
+    OBS_TICK(7);
+#undef OBS_TICK
 }
 
 }  // namespace

@@ -64,7 +64,7 @@ typedef struct FlBatch {
     int64_t grid_stride; /* uint16 elements between the grids of consecutive envs, >= H*W, multiple of 8 */
     int64_t dist_stride; /* uint16 elements between the distance maps of consecutive envs,
                             >= n_slots*H*W*4, multiple of 8 (16-byte aligned blocks: moved by TMA bulk copies) */
-    int64_t reserved0;
+    int64_t *debug_clocks; /* tuning only: [E][16] SM-clock timestamps of k_observe's phases, NULL = off */
 
     /* ---- world, static after upload (RailEnv.reset generators stay reference Python) ---- */
     const uint16_t *grid;      /* [E][grid_stride] transition bitmask per cell (core/transition_map.py:144) */
@@ -145,10 +145,16 @@ int fl_observe(const FlBatch *b, float *d_agent_attr, float *d_forest, int32_t *
                int32_t *d_node_order, int32_t *d_edge_order, uint8_t *d_valid_actions,
                float *d_dist_target, void *stream);
 
+/* A view of environments [e0, e0+n) of a batch: every pointer advanced by e0 environments, E = n.  The view
+ * aliases the parent's memory; stepping disjoint views on different streams is allowed. */
+int fl_batch_slice(const FlBatch *b, int64_t e0, int64_t n, FlBatch *out);
+
 /* One env.step as the reference's caller sees it (solution/eval_env.py:108-114) with HOST buffers:
  * copies h_actions to d_actions, runs fl_step + fl_observe, copies rewards, dones and every
  * observation tensor back to the h_ buffers (any h_ output may be NULL to leave it on the device).
- * All work is enqueued on `stream`; the caller synchronises. */
+ * With n_chunks > 1 and a copy_stream the batch is cut into n_chunks environment ranges and the
+ * device-to-host copies of one range (on copy_stream) overlap the kernels of the next (on stream).
+ * All work is ordered before the end of `stream`; the caller synchronises `stream`. */
 typedef struct FlObsBuffers {
     float *agent_attr;
     float *forest;
@@ -163,7 +169,7 @@ typedef struct FlObsBuffers {
 
 int fl_step_observe_host(const FlBatch *b, const uint8_t *h_actions, uint8_t *d_actions,
                          const FlObsBuffers *d_out, const FlObsBuffers *h_out, uint32_t flags,
-                         void *stream);
+                         int n_chunks, void *stream, void *copy_stream);
 
 /* Number of kernel launches issued by this library since load (bench.py reports it as gpu_launches). */
 uint64_t fl_launch_count(void);

@@ -1,0 +1,91 @@
+"""Parity at BASELINE.json's full batch sizes.  The oracle cannot step thousands of environments in
+seconds, so each full-size batch is checked three ways: (1) a sample of its environments is stepped by
+the oracle with the same worlds, actions and schedules and compared bit-exactly every few steps;
+(2) size-independent properties: an environment's results do not depend on which batch, slice or chunk it
+is computed in (same bytes from the full batch, from a batch holding only that environment, and from the
+chunked host-buffer entry point), and the agent-step counter equals E*N*steps; (3) the sticky status
+word stays clean (no bad cell, no step-after-done)."""
+import os
+
+import numpy as np
+import pytest
+
+from test_gpu_parity import assert_same, compare_obs, compare_state
+
+pytestmark = pytest.mark.gpu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+CASES = [  # config, envs, steps, sampled envs, oracle check every
+    ("Test_03", 1024, 60, (0, 517, 1023), 5),
+    ("Test_08", 512, 40, (3, 511), 8),
+    ("Test_14", 64, 24, (63,), 8),
+    ("Test_02", 8192, 50, (1, 4097, 8191), 5),
+]
+
+
+def _load(config, n):
+    import bench
+    return bench.load_worlds(config, n)
+
+
+@pytest.mark.parametrize("config,n_envs,n_steps,sample,every", CASES)
+def test_full_batch_matches_oracle_on_sampled_envs(config, n_envs, n_steps, sample, every):
+    import torch
+    import flatland_marl_b200 as fb
+    from oracle import oracle as orc
+    worlds = _load(config, n_envs)
+    N = int(worlds[0]["N"])
+    batch = fb.BatchedRailEnv(worlds)
+    solo = fb.BatchedRailEnv([worlds[e] for e in sample])           # the same environments in a batch of their own
+    envs = {e: orc.OracleEnv(worlds[e]) for e in sample}
+    batch.reset(); solo.reset()
+    for e, env in envs.items():
+        env.reset()
+        assert_same(batch.dist_numpy(e)[: env.dist_u16().shape[0]], env.dist_u16(), "%s env %d distance map" % (config, e))
+        compare_obs(batch, e, env.obs(), "%s env %d reset obs" % (config, e))
+    rng = np.random.RandomState(7)
+    idx = torch.tensor(sample, device=batch.device)
+    for t in range(n_steps):
+        # mostly forward so that trains leave the stations and meet each other
+        act = np.where(rng.rand(n_envs, N) < 0.7, 2, rng.randint(0, 5, (n_envs, N))).astype(np.uint8)
+        a = torch.from_numpy(act).to(batch.device)
+        _, rew, don = batch.step(a)
+        solo.step(a[idx].contiguous())
+        for j, e in enumerate(sample):
+            orew, odon = envs[e].step(act[e], worlds[e]["sched"][t])
+            what = "%s env %d step %d" % (config, e, t + 1)
+            assert_same(rew[e].cpu().numpy(), orew, what + " rewards")
+            assert_same(don[e].cpu().numpy(), odon, what + " dones")
+            if t % every == 0 or t == n_steps - 1:
+                compare_state(batch, e, envs[e].state(), what)
+                compare_obs(batch, e, envs[e].obs(), what + " obs")
+                for k in batch.obs:                                   # batch-composition independence, byte for byte
+                    assert torch.equal(batch.obs[k][e], solo.obs[k][j]), what + " " + k + " differs between batch sizes"
+    stats = batch.episode_stats().cpu().numpy()
+    assert int(stats[3]) == n_envs * N * n_steps
+    assert int(batch.t["status"].max()) == 0
+
+
+def test_chunked_host_step_equals_device_step():
+    """fl_step_observe_host with 1, 3 and 8 chunks (copies overlapped on a second stream) returns the same
+    bytes as the device-resident path on the full Test_03 batch."""
+    import torch
+    import flatland_marl_b200 as fb
+    worlds = _load("Test_03", 256)
+    N = int(worlds[0]["N"])
+    ref = fb.BatchedRailEnv(worlds)
+    others = {c: fb.BatchedRailEnv(worlds) for c in (1, 3, 8)}
+    ref.reset()
+    for b in others.values():
+        b.reset()
+    rng = np.random.RandomState(11)
+    for t in range(25):
+        act = np.where(rng.rand(256, N) < 0.7, 2, rng.randint(0, 5, (256, N))).astype(np.uint8)
+        ref.step(torch.from_numpy(act).to(ref.device))
+        for c, b in others.items():
+            h = b.step_host(act, n_chunks=c)
+            for k in ref.obs:
+                np.testing.assert_array_equal(h[k].numpy(), ref.obs[k].cpu().numpy(), err_msg="%s chunks=%d step %d" % (k, c, t))
+            np.testing.assert_array_equal(h["rewards"].numpy(), ref.rewards.cpu().numpy())
+            np.testing.assert_array_equal(h["dones"].numpy(), ref.dones.cpu().numpy())

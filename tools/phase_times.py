@@ -1,0 +1,40 @@
+"""Tuning aid: per-phase SM-clock cycles of k_observe (FlBatch.debug_clocks), averaged over environments.
+usage: python tools/phase_times.py [config] [envs] [steps]"""
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import bench  # noqa: E402
+import flatland_marl_b200 as fb  # noqa: E402
+
+cfg = sys.argv[1] if len(sys.argv) > 1 else "Test_03"
+E = int(sys.argv[2]) if len(sys.argv) > 2 else bench.CONFIGS[cfg]["envs"]
+steps = int(sys.argv[3]) if len(sys.argv) > 3 else 150
+worlds = bench.load_worlds(cfg, E)
+batch = fb.BatchedRailEnv(worlds, auto_reset=True, debug_clocks=True)
+N = batch.N
+batch.reset()
+gen = torch.Generator(device=batch.device); gen.manual_seed(1)
+acc = []
+for t in range(steps):
+    a = torch.randint(0, 5, (E, N), dtype=torch.uint8, device=batch.device, generator=gen)
+    batch.step(a)
+    if t >= steps - 20:
+        acc.append(batch.debug_clocks.cpu().numpy().copy())
+d = np.stack(acc).astype(np.float64)          # [20, E, 16]
+t0 = d[..., 15]
+names = [("setup+zero", 15, 0), ("tma wait+loader+occupancy", 0, 1), ("prediction walks", 1, 2), ("scan+scatter+sort (+deadlock join)", 2, 3),
+         ("tile init/roots", 3, 4), ("tree walks", 4, 5), ("orders+adjacency", 5, 6), ("attributes", 6, 7)]
+tot = d[..., 7] - t0
+print("%s E=%d N=%d: mean cycles per env %.0f (p50 %.0f, p99 %.0f, max %.0f)" % (cfg, E, N, tot.mean(), np.median(tot), np.percentile(tot, 99), tot.max()))
+for nm, a, b in names:
+    x = d[..., b] - d[..., a]
+    print("  %-40s mean %9.0f  p99 %9.0f  (%.1f%%)" % (nm, x.mean(), np.percentile(x, 99), 100 * x.mean() / tot.mean()))
+dl = d[..., 8] - d[..., 1]
+print("  %-40s mean %9.0f  p99 %9.0f" % ("deadlock lane (from occupancy done)", dl.mean(), np.percentile(dl, 99)))
+print("  tree-loop iterations of warp 0: mean %.0f p99 %.0f max %.0f; entries per env: mean %.0f max %.0f" %
+      (d[..., 9].mean(), np.percentile(d[..., 9], 99), d[..., 9].max(), d[..., 10].mean(), d[..., 10].max()))
