@@ -11,9 +11,12 @@ ACTION_ABSENT = 255
 ST_STEP_AFTER_DONE, ST_AUTO_RESET, ST_BAD_CELL = 1, 2, 4
 FLAG_AUTO_RESET = 1
 
-_I64 = ["E", "N", "H", "W", "n_slots", "S", "ent_cap", "grid_stride", "dist_stride", "debug_clocks"]
+# field order of struct FlBatch (include/flatland_b200.h)
+_FIELDS = [("E", "i"), ("N", "i"), ("H", "i"), ("W", "i"), ("n_slots", "i"), ("S", "i"), ("ent_cap", "i"), ("grid_stride", "i"),
+           ("dist_stride", "i"), ("debug_clocks", "p"), ("ridx_stride", "i"), ("state_stride", "i"), ("wlist_stride", "i"),
+           ("reserved1", "i")]
 _PTR = ["grid", "slot_rc", "dist", "max_steps", "init_rc", "tgt_rc", "init_dir", "max_count", "slot", "speed",
-        "earliest", "latest", "sched",
+        "earliest", "latest", "sched", "ridx", "srec", "wstart", "wlenk", "wlist", "walk_total",
         "rc", "old_rc", "dir", "old_dir", "state", "ctr", "mal", "saved", "sig_mal", "deadlocked", "done", "nmal",
         "arrival",
         "elapsed", "sched_pos", "done_all", "status", "cellinfo", "occ_cell", "stats",
@@ -22,7 +25,7 @@ _PTR = ["grid", "slot_rc", "dist", "max_steps", "init_rc", "tgt_rc", "init_dir",
 
 class FlBatch(C.Structure):
     """Mirror of `struct FlBatch` (include/flatland_b200.h); the size is checked against the library."""
-    _fields_ = [(n, C.c_int64) for n in _I64] + [(n, C.c_void_p) for n in _PTR]
+    _fields_ = [(n, C.c_int64 if k == "i" else C.c_void_p) for n, k in _FIELDS] + [(n, C.c_void_p) for n in _PTR]
 
 
 class FlObsBuffers(C.Structure):
@@ -30,7 +33,7 @@ class FlObsBuffers(C.Structure):
                                           "valid_actions", "dist_target", "rewards", "dones")]
 
 
-EXPORTS = ["fl_abi_version", "fl_batch_sizeof", "fl_error_string", "fl_distance_map", "fl_reset", "fl_step",
+EXPORTS = ["fl_abi_version", "fl_batch_sizeof", "fl_error_string", "fl_distance_map", "fl_walk_tables", "fl_reset", "fl_step",
            "fl_observe", "fl_batch_slice", "fl_step_observe_host", "fl_launch_count", "fl_profile_num_kernels", "fl_profile_kernel_name",
            "fl_profile_enable", "fl_profile_collect"]
 
@@ -58,6 +61,7 @@ def lib():
     L.fl_launch_count.restype = C.c_uint64
     L.fl_distance_map.argtypes = [C.POINTER(FlBatch), P]
     L.fl_reset.argtypes = [C.POINTER(FlBatch), P, P]
+    L.fl_walk_tables.argtypes = [C.POINTER(FlBatch), C.c_int, P]
     L.fl_step.argtypes = [C.POINTER(FlBatch), P, P, P, C.c_uint32, P]
     L.fl_observe.argtypes = [C.POINTER(FlBatch)] + [P] * 8
     L.fl_step_observe_host.argtypes = [C.POINTER(FlBatch), P, P, C.POINTER(FlObsBuffers), C.POINTER(FlObsBuffers),
@@ -70,7 +74,7 @@ def lib():
     L.fl_profile_enable.restype = None
     L.fl_profile_collect.argtypes = [P, P, C.c_int]
     L.fl_profile_collect.restype = C.c_int
-    for f in ("fl_distance_map", "fl_reset", "fl_step", "fl_observe", "fl_step_observe_host", "fl_batch_slice"):
+    for f in ("fl_distance_map", "fl_walk_tables", "fl_reset", "fl_step", "fl_observe", "fl_step_observe_host", "fl_batch_slice"):
         getattr(L, f).restype = C.c_int
     if L.fl_batch_sizeof() != C.sizeof(FlBatch):
         raise FlatlandB200Error("FlBatch layout mismatch: library %d bytes, binding %d bytes"

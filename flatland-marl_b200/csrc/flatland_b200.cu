@@ -36,8 +36,8 @@ std::atomic<uint64_t> g_launches{0};
 
 // Optional per-kernel timing (fl_profile_*): every launch is bracketed by CUDA events recorded on the
 // launching stream; fl_profile_collect turns them into per-kernel totals.  Off by default.
-enum KernelId : int { K_BFS = 0, K_RESET, K_STEP, K_OBSERVE, K_COUNT };
-const char *const kKernelNames[K_COUNT] = {"k_bfs", "k_reset", "k_step", "k_observe"};
+enum KernelId : int { K_BFS = 0, K_RESET, K_STEP, K_OBSERVE, K_WALKS, K_COUNT };
+const char *const kKernelNames[K_COUNT] = {"k_bfs", "k_reset", "k_step", "k_observe", "k_walks"};
 struct ProfRec { int id; cudaEvent_t a, b; };
 std::mutex g_prof_mu;
 bool g_prof_on = false;
@@ -73,6 +73,7 @@ int check_batch(const FlBatch *b) {
     if (b->N >= FL_MAX_AGENTS) return FL_ERR_TOO_MANY_AGENTS;
     if (b->ent_cap < b->N * (int64_t)NPRED) return FL_ERR_BAD_ARG;
     if (b->H >= 32768 || b->W >= 32768 || b->H * b->W > (1 << 20)) return FL_ERR_BAD_ARG;
+    if (b->ridx_stride < b->H * b->W || b->ridx_stride % 8 || b->state_stride % 4 || b->wlist_stride % 8) return FL_ERR_BAD_ARG;
     // per-environment blocks are 16-byte aligned so that they can be moved with TMA bulk copies
     if (b->grid_stride < b->H * b->W || b->grid_stride % 8 || b->dist_stride < b->n_slots * b->H * b->W * 4 || b->dist_stride % 8)
         return FL_ERR_BAD_ARG;
@@ -86,9 +87,9 @@ int align_up(int v, int a) { return (v + a - 1) / a * a; }
 // Shared-memory plan of k_observe for one configuration.  Mandatory: barrier + scalars, scan partials, the
 // per-agent records, the deadlock scratch and the tree tile (which doubles as the unsorted-entry buffer).
 // Optional, in this order while they fit: rail grid, occupancy words, key counters, the sorted predicted-
-// occupancy entries, and last the distance maps.  The budget per CTA is the largest that still lets
-// `ctas` CTAs share an SM; ctas is the largest count (<= 6) for which grid, occupancy, counters and a
-// typical entry array fit.  FL_OBS_CTAS / FL_OBS_NT override the choice (tuning only).
+// occupancy entries ("core"), the static walk tables, and last the distance maps.  The budget per CTA is the
+// largest that still lets `ctas` CTAs share an SM: the largest ctas >= 3 for which core + walk tables fit, else
+// the largest ctas for which the core fits.  FL_OBS_CTAS / FL_OBS_TABLES / FL_OBS_NT override (tuning only).
 ObsLayout make_obs_layout(const FlBatch *b, int nt) {
     const int N = (int)b->N, HW = (int)(b->H * b->W), K = (int)(b->W * b->W + b->H);
     ObsLayout L;
@@ -104,16 +105,26 @@ ObsLayout make_obs_layout(const FlBatch *b, int nt) {
     L.tmp_cap = tree_b / 6;
     const long long grid_b = b->grid_stride * 2, ci_b = (long long)HW * 4, ks_b = (long long)(K + 1) * 4;
     const long long dist_b = b->dist_stride * 2, ent_typ = (long long)N * 48 * 4;
-    int ctas = 1;
+    const long long ridx_b = b->ridx_stride * 2, st_b = b->state_stride * 4, wl_b = b->wlist_stride * 2;
+    const long long core = off + grid_b + ci_b + ks_b + ent_typ + 5 * 128, tables = ridx_b + 3 * st_b + wl_b + 5 * 128;
+    bool want_tables = true;
+    if (const char *s = getenv("FL_OBS_TABLES")) want_tables = atoi(s) != 0;
+    int ctas = 0;
     if (const char *s = getenv("FL_OBS_CTAS")) ctas = atoi(s) > 0 ? atoi(s) : 1;
-    else
+    if (!ctas && want_tables)
+        for (int c = 6; c >= 3; c--)
+            if (core + tables <= SMEM_MAX / c - 1024) { ctas = c; break; }
+    if (!ctas)
         for (int c = 6; c >= 1; c--)
-            if (off + grid_b + ci_b + ks_b + ent_typ + 4 * 128 <= SMEM_MAX / c - 1024) { ctas = c; break; }
+            if (core <= SMEM_MAX / c - 1024 || c == 1) { ctas = c; break; }
     const int budget = SMEM_MAX / ctas - 1024;
     auto opt = [&](long long bytes) { if ((long long)off + bytes + 128 > budget) return -1; return take(bytes); };
     L.grid = opt(grid_b);
     L.ci = opt(ci_b);
     L.ks = K <= 0xFFFF ? opt(ks_b) : -1;
+    const bool tables_fit = want_tables && (long long)off + ent_typ + tables + 128 <= budget;
+    L.ridx = L.srec = L.wstart = L.wlenk = L.wlist = -1;
+    if (tables_fit) { L.ridx = take(ridx_b); L.srec = take(st_b); L.wstart = take(st_b); L.wlenk = take(st_b); L.wlist = take(wl_b); }
     // entries: at least the typical size, the rest of the budget when the distance maps do not fit anyway
     long long ent_b = (long long)budget - off - 128;
     const bool dist_fits = ent_b - ent_typ >= dist_b + 128;
@@ -201,6 +212,17 @@ int fl_distance_map(const FlBatch *b, void *stream) {
     return finish(cudaGetLastError());
 }
 
+int fl_walk_tables(const FlBatch *b, int fill, void *stream) {
+    if (int rc = check_batch(b)) return rc;
+    if (!b->ridx || !b->walk_total) return FL_ERR_BAD_ARG;
+    if (fill && (!b->srec || !b->wstart || !b->wlenk || !b->wlist || b->state_stride <= 0 || b->wlist_stride <= 0)) return FL_ERR_BAD_ARG;
+    cudaStream_t st = (cudaStream_t)stream;
+    LaunchScope ls(K_WALKS, st);
+    if (fill) k_walks<true, 256><<<(unsigned)b->E, 256, 0, st>>>(*b);
+    else k_walks<false, 256><<<(unsigned)b->E, 256, 0, st>>>(*b);
+    return finish(cudaGetLastError());
+}
+
 int fl_reset(const FlBatch *b, const uint8_t *d_env_mask, void *stream) {
     if (int rc = check_batch(b)) return rc;
     {
@@ -227,6 +249,7 @@ int fl_observe(const FlBatch *b, float *d_agent_attr, float *d_forest, int32_t *
     if (int rc = check_batch(b)) return rc;
     if (!d_agent_attr || !d_forest || !d_adjacency || !d_node_order || !d_edge_order || !d_valid_actions || !d_dist_target)
         return FL_ERR_BAD_ARG;
+    if (!b->srec || !b->wstart || !b->wlenk || !b->wlist || !b->ridx) return FL_ERR_BAD_ARG;   // fl_walk_tables first
     cudaStream_t st = (cudaStream_t)stream;
     const int nt = obs_threads(b);
     const ObsLayout lay = make_obs_layout(b, nt);
@@ -251,6 +274,8 @@ int fl_batch_slice(const FlBatch *b, int64_t e0, int64_t n, FlBatch *out) {
     FL_ADV(grid, b->grid_stride) FL_ADV(slot_rc, b->n_slots * 2) FL_ADV(dist, b->dist_stride) FL_ADV(max_steps, 1)
     FL_ADV(init_rc, N * 2) FL_ADV(tgt_rc, N * 2) FL_ADV(init_dir, N) FL_ADV(max_count, N) FL_ADV(slot, N) FL_ADV(speed, N)
     FL_ADV(earliest, N) FL_ADV(latest, N) FL_ADV(sched, b->S * N)
+    FL_ADV(ridx, b->ridx_stride) FL_ADV(srec, b->state_stride) FL_ADV(wstart, b->state_stride) FL_ADV(wlenk, b->state_stride)
+    FL_ADV(wlist, b->wlist_stride) FL_ADV(walk_total, 4)
     FL_ADV(rc, N * 2) FL_ADV(old_rc, N * 2) FL_ADV(dir, N) FL_ADV(old_dir, N) FL_ADV(state, N) FL_ADV(ctr, N) FL_ADV(mal, N)
     FL_ADV(saved, N) FL_ADV(sig_mal, N) FL_ADV(deadlocked, N) FL_ADV(done, N) FL_ADV(nmal, N) FL_ADV(arrival, N)
     FL_ADV(elapsed, 1) FL_ADV(sched_pos, 1) FL_ADV(done_all, 1) FL_ADV(status, 1) FL_ADV(cellinfo, HW) FL_ADV(occ_cell, N)

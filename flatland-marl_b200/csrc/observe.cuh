@@ -23,16 +23,18 @@
 // the same generic pointers (ObsLayout offsets < 0).
 #pragma once
 #include "common.cuh"
+#include "walks.cuh"
 
 namespace {
 
 constexpr int OBS_MAX_TILE = 64;        // agents whose trees are built together (bounds the node table)
 constexpr int OBS_Q_EMPTY = 0xFFFF;
-constexpr int OBS_WALK_CAP = 1024;      // branch walks longer than this are checked for a rail cycle (Brent)
+constexpr int OBS_G = 8;                // lanes that share one branch walk
 constexpr int I_INF = 0x7fffffff;
 
 struct ObsLayout {   // byte offsets into dynamic shared memory (host: make_obs_layout); < 0 = lives in global memory
     int grid, ci, dist, ks, ent, ent_cap, tmp_cap, part, ag, dl, tree, bar, total, tile;
+    int ridx, srec, wstart, wlenk, wlist;   // static walk tables (walks.cuh)
 };
 
 // ---- mbarrier + 1-D TMA bulk copy (global -> shared), sm_90+ ------------------------------------
@@ -255,37 +257,12 @@ DEVI int road_type_of(int trans) {  // loader.cpp:122-161: first rotation that i
 
 DEVI float scale_i(int v, float T) { return v != I_INF ? (float)v / T : -1.0f; }  // treeobs.cpp:111-152
 
-// static successor of a branch-walk state (treeobs.cpp:476-539 without the dynamic features); false = the walk ends here
-DEVI bool walk_succ(const uint16_t *g, int W, int tr, int tc, int &r, int &c, int &d) {
-    if (r == tr && c == tc) return false;
-    const unsigned gc = g[r * W + c];
-    const int nb = nibble(gc, d);
-    if (__popc(nb) != 1) return false;
-    if (__popc(gc) == 1) return false;              // dead end (a diamond crossing has 4 bits)
-    d = first_dir(nb); r += d_row(d); c += d_col(d);
-    return true;
-}
-
-// Brent's cycle detection on walk_succ: index of the first revisited state (mu + lambda) when the walk
-// from (r0,c0,d0) runs into a cycle of plain rail, -1 when it ends at a switch / dead end / target.
-DEVI int walk_cycle_index(const uint16_t *g, int W, int tr, int tc, int r0, int c0, int d0) {
-    int tr_ = r0, tc_ = c0, td = d0, hr = r0, hc = c0, hd = d0;
-    int power = 1, lam = 1;
-    if (!walk_succ(g, W, tr, tc, hr, hc, hd)) return -1;
-    while (tr_ != hr || tc_ != hc || td != hd) {
-        if (power == lam) { tr_ = hr; tc_ = hc; td = hd; power *= 2; lam = 0; }
-        if (!walk_succ(g, W, tr, tc, hr, hc, hd)) return -1;
-        lam++;
-    }
-    tr_ = hr = r0; tc_ = hc = c0; td = hd = d0;
-    for (int k = 0; k < lam; k++) walk_succ(g, W, tr, tc, hr, hc, hd);
-    int mu = 0;
-    while (tr_ != hr || tc_ != hc || td != hd) {
-        walk_succ(g, W, tr, tc, tr_, tc_, td);
-        walk_succ(g, W, tr, tc, hr, hc, hd);
-        mu++;
-    }
-    return mu + lam;
+// state id of the cell entered from (r, c) in direction cd; 0xFFFFFFFF when the rail leads nowhere (invalid grid)
+DEVI uint32_t child_state(const uint16_t *ridx, int H, int W, int r, int c, int cd) {
+    const int rr = r + d_row(cd), cc = c + d_col(cd);
+    if (rr < 0 || cc < 0 || rr >= H || cc >= W) return 0xFFFFFFFFu;
+    const unsigned ri = ridx[rr * W + cc];
+    return ri == 0xFFFFu ? 0xFFFFFFFFu : ri * 4u + (uint32_t)cd;
 }
 
 DEVI void store_node(float *forest_node, float4 a, float4 b, float4 c) {
@@ -312,7 +289,7 @@ struct ObsAgents {
 };
 
 struct ObsTile {
-    uint32_t *n_rc, *n_meta, *n_tot;        // [OBS_TILE][31] node table: start cell, dir|ad|null|parent, distance so far
+    uint32_t *n_rc, *n_meta, *n_tot;        // [OBS_TILE][31] node table: start state id, dir|ad|null|parent, distance so far
     uint32_t *t_mask, *t_next;              // [OBS_TILE] real-node bit mask of the level being walked / being created
     int *t_pend;                            // [OBS_TILE] walks of the current level still running
     uint32_t *t_lsle;                       // [OBS_TILE] level start | level end << 8
@@ -340,6 +317,15 @@ k_observe(FlBatch b, ObsLayout lay, float *__restrict__ out_attr, float *__restr
     const uint16_t *dist = lay.dist >= 0 ? reinterpret_cast<const uint16_t *>(smraw + lay.dist) : g_dist;
     uint32_t *ci = lay.ci >= 0 ? reinterpret_cast<uint32_t *>(smraw + lay.ci) : b.cellinfo + (size_t)e * HW;
     uint32_t *ks = lay.ks >= 0 ? reinterpret_cast<uint32_t *>(smraw + lay.ks) : b.key_start + (size_t)e * (K + 1);
+    const uint16_t *g_ridx = b.ridx + (size_t)e * b.ridx_stride;
+    const uint32_t *g_srec = b.srec + (size_t)e * b.state_stride, *g_wstart = b.wstart + (size_t)e * b.state_stride,
+                   *g_wlenk = b.wlenk + (size_t)e * b.state_stride;
+    const uint16_t *g_wlist = b.wlist + (size_t)e * b.wlist_stride;
+    const uint16_t *ridx = lay.ridx >= 0 ? reinterpret_cast<const uint16_t *>(smraw + lay.ridx) : g_ridx;
+    const uint32_t *srec = lay.srec >= 0 ? reinterpret_cast<const uint32_t *>(smraw + lay.srec) : g_srec;
+    const uint32_t *wstart = lay.wstart >= 0 ? reinterpret_cast<const uint32_t *>(smraw + lay.wstart) : g_wstart;
+    const uint32_t *wlenk = lay.wlenk >= 0 ? reinterpret_cast<const uint32_t *>(smraw + lay.wlenk) : g_wlenk;
+    const uint16_t *wlist = lay.wlist >= 0 ? reinterpret_cast<const uint16_t *>(smraw + lay.wlist) : g_wlist;
     uint32_t *s_part = reinterpret_cast<uint32_t *>(smraw + lay.part);
     uint64_t *bar = reinterpret_cast<uint64_t *>(smraw + lay.bar);
     int *s_misc = reinterpret_cast<int *>(smraw + lay.bar + 16);
@@ -381,14 +367,23 @@ k_observe(FlBatch b, ObsLayout lay, float *__restrict__ out_attr, float *__restr
 #define OBS_TICK(k) do { if (dbg && tid == 0) dbg[k] = clock64(); } while (0)
     if (dbg && tid == 0) dbg[15] = clock64();
     // ---- phase 0: TMA bulk copies of the static world ---------------------------------------------
-    const bool use_tma = lay.grid >= 0 || lay.dist >= 0;
+    const bool use_tma = lay.grid >= 0 || lay.dist >= 0 || lay.ridx >= 0 || lay.srec >= 0 || lay.wstart >= 0 || lay.wlenk >= 0 ||
+                         lay.wlist >= 0;
     if (use_tma && tid == 0) {
         mbar_init(bar, 1);
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         const uint32_t gb = lay.grid >= 0 ? (uint32_t)(b.grid_stride * 2) : 0u;
         const uint32_t db = lay.dist >= 0 ? (uint32_t)(b.dist_stride * 2) : 0u;
-        mbar_expect_tx(bar, gb + db);
+        const uint32_t rb = lay.ridx >= 0 ? (uint32_t)(b.ridx_stride * 2) : 0u;
+        const uint32_t sb = (uint32_t)(b.state_stride * 4);
+        const uint32_t lb = lay.wlist >= 0 ? (uint32_t)(b.wlist_stride * 2) : 0u;
+        mbar_expect_tx(bar, gb + db + rb + lb + (lay.srec >= 0 ? sb : 0u) + (lay.wstart >= 0 ? sb : 0u) + (lay.wlenk >= 0 ? sb : 0u));
         if (gb) tma_load_1d(smraw + lay.grid, g_grid, gb, bar);
+        if (rb) tma_load_1d(smraw + lay.ridx, g_ridx, rb, bar);
+        if (lay.srec >= 0) tma_load_1d(smraw + lay.srec, g_srec, sb, bar);
+        if (lay.wstart >= 0) tma_load_1d(smraw + lay.wstart, g_wstart, sb, bar);
+        if (lay.wlenk >= 0) tma_load_1d(smraw + lay.wlenk, g_wlenk, sb, bar);
+        if (lb) tma_load_1d(smraw + lay.wlist, g_wlist, lb, bar);
         if (db) tma_load_1d(smraw + lay.dist, g_dist, db, bar);
     }
     // zero the key counters; forget the previous occupancy
@@ -569,8 +564,9 @@ k_observe(FlBatch b, ObsLayout lay, float *__restrict__ out_attr, float *__restr
             uint32_t mask = 0;
             for (int ad = -1; ad <= 1; ad++) {
                 const int bd = (orientation + ad) & 3, idx = 2 + ad;
-                const bool real = tbit(nb, bd);
-                Tt.n_rc[la * 31 + idx] = real ? (uint32_t)((vr + d_row(bd)) & 0xFFFF) | ((uint32_t)(vc + d_col(bd)) << 16) : 0xFFFFFFFFu;
+                const uint32_t csid = tbit(nb, bd) ? child_state(ridx, H, W, vr, vc, bd) : 0xFFFFFFFFu;
+                const bool real = csid != 0xFFFFFFFFu;
+                Tt.n_rc[la * 31 + idx] = csid;
                 Tt.n_meta[la * 31 + idx] = (uint32_t)bd | ((uint32_t)(ad + 1) << 2) | ((real ? 0u : 1u) << 4);
                 Tt.n_tot[la * 31 + idx] = 1;
                 if (real) mask |= 1u << (idx - 1);
@@ -584,174 +580,187 @@ k_observe(FlBatch b, ObsLayout lay, float *__restrict__ out_attr, float *__restr
                 atomicAdd(Tt.n_done, 1);
             } else {
                 int slot = atomicAdd(Tt.q_tail, __popc(mask));
-                for (uint32_t m = mask; m; m &= m - 1) Tt.q[slot++] = (uint16_t)((la << 5) | (1 + __ffs(m) - 1));
+                for (uint32_t m = mask; m; m &= m - 1) Tt.q[slot++] = (uint16_t)((la << 5) | __ffs(m));
             }
         }
         __syncthreads();
     OBS_TICK(4);
 
-        // persistent lanes: one branch walk (treeobs.cpp:258-610) per lane, one cell per iteration
+        // Branch walks (treeobs.cpp:258-610).  A group of OBS_G lanes takes one walk from the queue; the states
+        // the walk visits come from the static list of its start state (walks.cuh), OBS_G of them per iteration,
+        // one per lane; the per-cell findings are reduced over the group when the walk ends.
         {
+            const int gl = lane & (OBS_G - 1), gbase = lane & ~(OBS_G - 1);
+            const unsigned gmask = (OBS_G == 32 ? 0xFFFFFFFFu : ((1u << OBS_G) - 1u)) << gbase;
             bool active = false;
             int claim = -1;
-            int la = 0, n = 0, r = 0, c = 0, d = 0, tot = 0, steps = 0, stop_at = -1;
-            int r_start = 0, c_start = 0, d_start = 0, tot_start = 0;
-            bool cycle_checked = false;
+            int la = 0, n = 0, h = 0, tot0 = 0, k0 = 0, L = 0, skind = 0, tcell = -1;
+            uint32_t wbase = 0;
             int own = I_INF, other_agent = I_INF, conflict = I_INF, unusable = I_INF;
             int same = 0, opp = 0, malf = 0, rtdn = 0;
             float min_speed = 1.0f, tpc_f = 1.0f;
-            int h = 0, tr = 0, tc = 0;
             const uint16_t *dm = dist;
             int iters = 0;
             while (true) {
                 iters++;
                 if (!active) {
-                    if (claim < 0) claim = atomicAdd(Tt.q_head, 1);
-                    const unsigned it = claim < qcap ? ld_vol_u16(&Tt.q[claim]) : (unsigned)OBS_Q_EMPTY;
+                    unsigned it = (unsigned)OBS_Q_EMPTY;
+                    if (gl == 0) {
+                        if (claim < 0) claim = atomicAdd(Tt.q_head, 1);
+                        it = claim < qcap ? ld_vol_u16(&Tt.q[claim]) : (unsigned)OBS_Q_EMPTY;
+                        if (it != (unsigned)OBS_Q_EMPTY) { __threadfence_block(); claim = -1; }
+                    }
+                    it = __shfl_sync(gmask, it, gbase);
                     if (it != (unsigned)OBS_Q_EMPTY) {
-                        __threadfence_block();
-                        claim = -1; active = true;
+                        active = true;
                         la = (int)(it >> 5); n = (int)(it & 31);
                         h = a0 + la;
-                        const uint32_t rc0 = Tt.n_rc[la * 31 + n], meta = Tt.n_meta[la * 31 + n];
-                        r = (int)(short)(rc0 & 0xFFFF); c = (int)(rc0 >> 16); d = (int)(meta & 3);
-                        tot = (int)Tt.n_tot[la * 31 + n];
-                        r_start = r; c_start = c; d_start = d; tot_start = tot;
-                        steps = 0; stop_at = -1; cycle_checked = false;
+                        const uint32_t sid0 = Tt.n_rc[la * 31 + n];
+                        tot0 = (int)Tt.n_tot[la * 31 + n];
+                        wbase = wstart[sid0];
+                        const uint32_t lk = wlenk[sid0];
+                        L = (int)(lk & 0x0FFFFFFFu); skind = (int)(lk >> 28);
+                        k0 = 0;
                         own = other_agent = conflict = unusable = I_INF;
                         same = opp = malf = rtdn = 0; min_speed = 1.0f;
-                        tr = (int)(short)(A.tgt[h] & 0xFFFF); tc = (int)(A.tgt[h] >> 16);
+                        const uint32_t tg = A.tgt[h];
+                        tcell = (int)(short)(tg & 0xFFFF) * W + (int)(tg >> 16);
                         tpc_f = (float)(1.0 / (double)A.speed[h]);                       // treeobs.cpp:304
                         dm = dist + (size_t)((A.info[h] >> 8) & 0xFFFF) * HW * 4;
                     }
                 }
                 if (active) {
-                    int kind = 0;                  // 1 switch, 2 dead end, 3 terminal (cycle), 4 target
-                    const int cell = r * W + c;
-                    const uint32_t cinfo = ci[cell];
-                    const unsigned gc = grid[cell];
-                    if (cinfo) {                   // treeobs.cpp:322-360 (the observer itself counts too)
-                        other_agent = min(other_agent, tot);
-                        malf = max(malf, (int)((cinfo >> 8) & 1u));
-                        const int cnt = (int)((cinfo >> 11) & 1023u);
-                        rtdn += cnt ? cnt - 1 : 0;
-                        if ((int)((cinfo >> 9) & 3u) == d) { same++; min_speed = fminf(min_speed, A.speed[(cinfo >> 21) - 1]); }
-                        else opp++;
-                    }
-                    const int nb = nibble(gc, d);
-                    int total = __popc(gc);
-                    const int pt = (int)__fmul_rn((float)tot, tpc_f);                   // treeobs.cpp:378
-                    if (pt < NPRED && tot < NPRED) {                                     // treeobs.cpp:379-465
-                        const int key = c * W + r;
-                        const uint32_t s0 = key ? ks[key - 1] : 0u, s1 = ks[key];
-                        const int pre = max(0, pt - 1), post = min(NPRED - 1, pt + 1);
-                        unsigned acc = 0;
-                        for (uint32_t idx = s0; idx < s1; idx++) {
-                            const uint32_t en = ent[idx];
-                            const int t0 = (int)((en >> 10) & 511);
-                            if ((en >> 19) & 1u) { if (t0 > post) continue; }           // long-lived entries come first
-                            else {                                                       // then regular ones ordered by t0
-                                if (t0 > post) break;
-                                if (t0 + tpc_max <= pre) continue;
-                            }
-                            const int ag = (int)(en & 1023);
-                            const uint32_t ainfo = A.info[ag];
-                            const int t1 = ((en >> 19) & 1u) ? NPRED - 1 : (t0 ? t0 + (int)(ainfo >> 24) - 1 : 0);
-                            if (t1 < pre) continue;
-                            const int dh = (int)((en >> 20) & 3), dp = (int)((en >> 22) & 3), dn = (int)((en >> 24) & 3);
-                            const bool done = (ainfo >> 5) & 1;
-                            const bool in_cur = t0 <= pt && pt <= t1, in_pre = t0 <= pre && pre <= t1,
-                                       in_post = t0 <= post && post <= t1;
-                            const int pdir = pt < t0 ? dp : (pt > t1 ? dn : dh);  // always the direction at row pt
-                            const bool cf = (d != pdir && tbit(nb, (pdir + 2) & 3)) || done;
-                            const bool other = ag != h;
-                            acc |= (in_cur && other ? 1u : 0u) | (in_pre && other ? 2u : 0u) | (in_post && other ? 4u : 0u) |
-                                   (in_cur && cf ? 8u : 0u) | (in_pre && cf ? 16u : 0u) | (in_post && cf ? 32u : 0u);
+                    const int k = k0 + gl;
+                    const bool valid = k <= L;
+                    uint32_t rec = 0;
+                    if (valid) rec = srec[wlist[wbase + k]];
+                    const int cell = (int)(rec & 0xFFFFF), d = (int)((rec >> 20) & 3), nb = (int)((rec >> 22) & 15);
+                    // the walk stops on the observer's own target (treeobs.cpp:467-475, 483-489): cells behind it do not count
+                    const unsigned tb = (__ballot_sync(gmask, valid && cell == tcell) >> gbase) & (OBS_G == 32 ? 0xFFFFFFFFu : ((1u << OBS_G) - 1u));
+                    const int kt = tb ? __ffs(tb) - 1 : OBS_G;
+                    const bool ends = tb != 0 || k0 + OBS_G > L;                         // this chunk holds the last cell
+                    const int k_end = tb ? k0 + kt : L;
+                    if (valid && gl <= kt) {
+                        const int tot = tot0 + k;
+                        const uint32_t cinfo = ci[cell];
+                        if (cinfo) {                   // treeobs.cpp:322-360 (the observer itself counts too)
+                            other_agent = min(other_agent, tot);
+                            malf = max(malf, (int)((cinfo >> 8) & 1u));
+                            const int cnt = (int)((cinfo >> 11) & 1023u);
+                            rtdn += cnt ? cnt - 1 : 0;
+                            if ((int)((cinfo >> 9) & 3u) == d) { same++; min_speed = fminf(min_speed, A.speed[(cinfo >> 21) - 1]); }
+                            else opp++;
                         }
-                        const bool cf = (acc & 1u) ? (acc & 8u) : (acc & 2u) ? (acc & 16u) : (acc & 4u) ? (acc & 32u) : false;
-                        if (cf) conflict = min(conflict, tot);
-                    }
-                    const bool is_target = r == tr && c == tc;
-                    if (is_target) own = min(own, tot);
-                    if (steps == stop_at) kind = 3;                                     // revisited (cell, dir): treeobs.cpp:476-481
-                    else if (is_target) kind = 4;
-                    else {
-                        if (gc == 0x8421u) total = 2;                                   // diamond crossing
-                        const int num = __popc(nb);
-                        if (total > 2 && num < 2) unusable = min(unusable, tot);
-                        if (num == 1) {
-                            if (total == 1) kind = 2;
-                            else {
-                                d = first_dir(nb); r += d_row(d); c += d_col(d); tot += 1; steps++;
-                                if (steps >= OBS_WALK_CAP && !cycle_checked) {          // suspiciously long: is this a rail cycle?
-                                    cycle_checked = true;
-                                    stop_at = walk_cycle_index(grid, W, tr, tc, r_start, c_start, d_start);
-                                    if (stop_at >= 0) {                                 // yes: redo the walk, ending at the first revisit
-                                        r = r_start; c = c_start; d = d_start; tot = tot_start; steps = 0;
-                                        own = other_agent = conflict = unusable = I_INF;
-                                        same = opp = malf = rtdn = 0; min_speed = 1.0f;
-                                    }
+                        const int pt = (int)__fmul_rn((float)tot, tpc_f);               // treeobs.cpp:378
+                        if (pt < NPRED && tot < NPRED) {                                 // treeobs.cpp:379-465
+                            const int r = cell / W, c = cell - r * W;
+                            const int key = c * W + r;
+                            const uint32_t s0 = key ? ks[key - 1] : 0u, s1 = ks[key];
+                            const int pre = max(0, pt - 1), post = min(NPRED - 1, pt + 1);
+                            unsigned acc = 0;
+                            for (uint32_t idx = s0; idx < s1; idx++) {
+                                const uint32_t en = ent[idx];
+                                const int t0 = (int)((en >> 10) & 511);
+                                if ((en >> 19) & 1u) { if (t0 > post) continue; }       // long-lived entries come first
+                                else {                                                   // then regular ones ordered by t0
+                                    if (t0 > post) break;
+                                    if (t0 + tpc_max <= pre) continue;
                                 }
+                                const int ag = (int)(en & 1023);
+                                const uint32_t ainfo = A.info[ag];
+                                const int t1 = ((en >> 19) & 1u) ? NPRED - 1 : (t0 ? t0 + (int)(ainfo >> 24) - 1 : 0);
+                                if (t1 < pre) continue;
+                                const int dh = (int)((en >> 20) & 3), dp = (int)((en >> 22) & 3), dn = (int)((en >> 24) & 3);
+                                const bool done = (ainfo >> 5) & 1;
+                                const bool in_cur = t0 <= pt && pt <= t1, in_pre = t0 <= pre && pre <= t1,
+                                           in_post = t0 <= post && post <= t1;
+                                const int pdir = pt < t0 ? dp : (pt > t1 ? dn : dh);  // always the direction at row pt
+                                const bool cf = (d != pdir && tbit(nb, (pdir + 2) & 3)) || done;
+                                const bool other = ag != h;
+                                acc |= (in_cur && other ? 1u : 0u) | (in_pre && other ? 2u : 0u) | (in_post && other ? 4u : 0u) |
+                                       (in_cur && cf ? 8u : 0u) | (in_pre && cf ? 16u : 0u) | (in_post && cf ? 32u : 0u);
                             }
-                        } else if (num > 1) kind = 1;
-                        else {                     // treeobs.cpp:527-535 throws; report and stop here
-                            atomicOr(&b.status[e], FL_ST_BAD_CELL);
-                            kind = 3;
+                            const bool cf = (acc & 1u) ? (acc & 8u) : (acc & 2u) ? (acc & 16u) : (acc & 4u) ? (acc & 32u) : false;
+                            if (cf) conflict = min(conflict, tot);
                         }
+                        if (cell == tcell) own = min(own, tot);
+                        if (k < k_end && ((rec >> 26) & 1u)) unusable = min(unusable, tot);   // never on the cell the walk ends on
                     }
-                    if (kind) {
+                    if (!ends) k0 += OBS_G;
+                    else {
+                        // ---- the walk is over: reduce the findings over the group -------------------------
+#pragma unroll
+                        for (int o = OBS_G / 2; o > 0; o >>= 1) {
+                            own = min(own, __shfl_xor_sync(gmask, own, o));
+                            other_agent = min(other_agent, __shfl_xor_sync(gmask, other_agent, o));
+                            conflict = min(conflict, __shfl_xor_sync(gmask, conflict, o));
+                            unusable = min(unusable, __shfl_xor_sync(gmask, unusable, o));
+                            same += __shfl_xor_sync(gmask, same, o);
+                            opp += __shfl_xor_sync(gmask, opp, o);
+                            malf = max(malf, __shfl_xor_sync(gmask, malf, o));
+                            rtdn += __shfl_xor_sync(gmask, rtdn, o);
+                            min_speed = fminf(min_speed, __shfl_xor_sync(gmask, min_speed, o));
+                        }
                         active = false;
-                        const size_t ea = (size_t)e * N + h;
-                        float *forest = out_forest + ea * (FL_MAX_NODES * FL_NODE_F);
-                        int dnb, dmin;
-                        if (kind == 4) { dnb = tot; dmin = 0; }
-                        else {
-                            const unsigned dv = dm[((size_t)(r * W + c)) * 4 + d];
-                            dmin = dv == FL_DIST_INF ? I_INF : (int)dv;
-                            dnb = kind == 3 ? I_INF : tot;
-                        }
-                        store_node(forest + n * FL_NODE_F,                              // scale_node (treeobs.cpp:111-152)
-                                   make_float4(scale_i(own, T), -1.0f, scale_i(other_agent, T), scale_i(conflict, T)),
-                                   make_float4(scale_i(unusable, T), scale_i(dnb, T), scale_i(dmin, T), (float)same / Nf),
-                                   make_float4((float)opp / Nf, (float)malf / Nf, min_speed, (float)rtdn / Nf));
-                        // children in order L, F, R (treeobs.cpp:583-608); their BFS indices follow from the level's mask
-                        const uint32_t lsle = Tt.t_lsle[la], lmask = Tt.t_mask[la];
-                        const int ls = (int)(lsle & 0xFF), le = (int)(lsle >> 8);
-                        const int base = le + 3 * __popc(lmask & ((1u << (n - ls)) - 1u));
-                        const int nb2 = nibble(grid[r * W + c], d);
-                        uint32_t bits = 0;
-                        for (int a2 = -1; a2 <= 1; a2++) {
-                            const int idx = base + a2 + 1;
-                            if (idx >= FL_MAX_NODES) break;
-                            const int bd = (d + a2) & 3, rb = (bd + 2) & 3;
-                            int cd = bd;
-                            bool real = false;
-                            if (kind == 2 && tbit(nb2, rb)) { cd = rb; real = true; }
-                            else if (kind == 1 && tbit(nb2, bd)) { cd = bd; real = true; }
-                            Tt.n_rc[la * 31 + idx] = real ? (uint32_t)((r + d_row(cd)) & 0xFFFF) | ((uint32_t)(c + d_col(cd)) << 16) : 0xFFFFFFFFu;
-                            Tt.n_meta[la * 31 + idx] = (uint32_t)cd | ((uint32_t)(a2 + 1) << 2) | ((real ? 0u : 1u) << 4) | ((uint32_t)n << 8);
-                            Tt.n_tot[la * 31 + idx] = (uint32_t)(tot + 1);
-                            if (real) bits |= 1u << (idx - le);
-                            else store_null_node(forest + idx * FL_NODE_F);
-                        }
-                        if (bits) atomicOr(&Tt.t_next[la], bits);
-                        __threadfence_block();
-                        if (atomicSub(&Tt.t_pend[la], 1) == 1) {                        // last walk of this agent's level: release the next one
+                        const int kind = tb ? 4 : (skind == WK_BAD ? 3 : skind);         // 1 switch, 2 dead end, 3 cycle, 4 target
+                        if (gl == 0) {
+                            if (!tb && skind == WK_BAD) atomicOr(&b.status[e], FL_ST_BAD_CELL);   // treeobs.cpp:527-535 throws
+                            const uint32_t erec = srec[wlist[wbase + k_end]];            // the state the walk ended on
+                            const int ecell = (int)(erec & 0xFFFFF), ed = (int)((erec >> 20) & 3), enb = (int)((erec >> 22) & 15);
+                            const int er = ecell / W, ec = ecell - er * W, tot = tot0 + k_end;
+                            const size_t ea = (size_t)e * N + h;
+                            float *forest = out_forest + ea * (FL_MAX_NODES * FL_NODE_F);
+                            int dnb, dmin;
+                            if (kind == 4) { dnb = tot; dmin = 0; }
+                            else {
+                                const unsigned dv = dm[((size_t)ecell) * 4 + ed];
+                                dmin = dv == FL_DIST_INF ? I_INF : (int)dv;
+                                dnb = kind == 3 ? I_INF : tot;
+                            }
+                            store_node(forest + n * FL_NODE_F,                          // scale_node (treeobs.cpp:111-152)
+                                       make_float4(scale_i(own, T), -1.0f, scale_i(other_agent, T), scale_i(conflict, T)),
+                                       make_float4(scale_i(unusable, T), scale_i(dnb, T), scale_i(dmin, T), (float)same / Nf),
+                                       make_float4((float)opp / Nf, (float)malf / Nf, min_speed, (float)rtdn / Nf));
+                            // children in order L, F, R (treeobs.cpp:583-608); their BFS indices follow from the level's mask
+                            const uint32_t lsle = Tt.t_lsle[la], lmask = Tt.t_mask[la];
+                            const int ls = (int)(lsle & 0xFF), le = (int)(lsle >> 8);
+                            const int base = le + 3 * __popc(lmask & ((1u << (n - ls)) - 1u));
+                            uint32_t bits = 0;
+                            for (int a2 = -1; a2 <= 1; a2++) {
+                                const int idx = base + a2 + 1;
+                                if (idx >= FL_MAX_NODES) break;
+                                const int bd = (ed + a2) & 3, rb = (bd + 2) & 3;
+                                int cd = bd;
+                                bool real = false;
+                                if (kind == 2 && tbit(enb, rb)) { cd = rb; real = true; }
+                                else if (kind == 1 && tbit(enb, bd)) { cd = bd; real = true; }
+                                const uint32_t csid = real ? child_state(ridx, H, W, er, ec, cd) : 0xFFFFFFFFu;
+                                real = csid != 0xFFFFFFFFu;
+                                Tt.n_rc[la * 31 + idx] = csid;
+                                Tt.n_meta[la * 31 + idx] = (uint32_t)cd | ((uint32_t)(a2 + 1) << 2) | ((real ? 0u : 1u) << 4) | ((uint32_t)n << 8);
+                                Tt.n_tot[la * 31 + idx] = (uint32_t)(tot + 1);
+                                if (real) bits |= 1u << (idx - le);
+                                else store_null_node(forest + idx * FL_NODE_F);
+                            }
+                            if (bits) atomicOr(&Tt.t_next[la], bits);
                             __threadfence_block();
-                            const uint32_t nmask = atomicExch(&Tt.t_next[la], 0u);
-                            const int nls = le, nle = min(FL_MAX_NODES, le + 3 * __popc(lmask));
-                            if (nmask == 0) {                                           // no real node left: the rest is padding
-                                Tt.t_count[la] = nle;
-                                for (int k = nle; k < FL_MAX_NODES; k++) store_null_node(forest + k * FL_NODE_F);
+                            if (atomicSub(&Tt.t_pend[la], 1) == 1) {                    // last walk of this agent's level: release the next one
                                 __threadfence_block();
-                                atomicAdd(Tt.n_done, 1);
-                            } else {
-                                Tt.t_mask[la] = nmask; Tt.t_lsle[la] = (uint32_t)nls | ((uint32_t)nle << 8);
-                                Tt.t_pend[la] = __popc(nmask);
-                                __threadfence_block();
-                                int slot = atomicAdd(Tt.q_tail, __popc(nmask));
-                                for (uint32_t m = nmask; m; m &= m - 1)
-                                    *reinterpret_cast<volatile uint16_t *>(&Tt.q[slot++]) = (uint16_t)((la << 5) | (nls + __ffs(m) - 1));
+                                const uint32_t nmask = atomicExch(&Tt.t_next[la], 0u);
+                                const int nls = le, nle = min(FL_MAX_NODES, le + 3 * __popc(lmask));
+                                if (nmask == 0) {                                       // no real node left: the rest is padding
+                                    Tt.t_count[la] = nle;
+                                    for (int q = nle; q < FL_MAX_NODES; q++) store_null_node(forest + q * FL_NODE_F);
+                                    __threadfence_block();
+                                    atomicAdd(Tt.n_done, 1);
+                                } else {
+                                    Tt.t_mask[la] = nmask; Tt.t_lsle[la] = (uint32_t)nls | ((uint32_t)nle << 8);
+                                    Tt.t_pend[la] = __popc(nmask);
+                                    __threadfence_block();
+                                    int slot = atomicAdd(Tt.q_tail, __popc(nmask));
+                                    for (uint32_t m = nmask; m; m &= m - 1)
+                                        *reinterpret_cast<volatile uint16_t *>(&Tt.q[slot++]) = (uint16_t)((la << 5) | (nls + __ffs(m) - 1));
+                                }
                             }
                         }
                     }

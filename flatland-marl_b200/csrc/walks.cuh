@@ -1,0 +1,162 @@
+// walks.cuh — k_walks: static branch-walk tables, built once per world at reset.
+//
+// The tree observation explores the rail from a (cell, direction) state to the next switch, dead end or
+// revisited state (treeobs.cpp:258-610, _explore_branch).  Which cells such a walk passes is a property of
+// the rail alone — only what it meets on them (trains, predicted conflicts, the observer's own target) is
+// dynamic.  k_walks therefore lists, for every rail state, the states its walk visits, so that k_observe can
+// spread the cells of one walk over the lanes of a lane group instead of chasing them one by one:
+//   ridx[cell]     rail index of a cell (0xFFFF = no rail); state id sid = 4 * ridx[cell] + direction
+//   srec[sid]      cell | dir << 20 | transitions nibble of (cell, dir) << 22 | "unusable switch here" << 26
+//   wstart[sid]    offset of the walk from sid in wlist
+//   wlenk[sid]     steps of the walk (it visits steps + 1 states) | kind << 28:
+//                  1 = ends on a switch, 2 = dead end, 3 = the last state revisits an earlier one (rail cycle,
+//                  treeobs.cpp:476-481), 0 = ends on a cell without transitions (treeobs.cpp:527-535 throws)
+//   wlist[...]     the visited state ids, walk after walk
+// FILL = false only measures (states, list length) so that the host can size wlist.
+#pragma once
+#include "common.cuh"
+
+namespace {
+
+constexpr int WK_SWITCH = 1, WK_DEADEND = 2, WK_CYCLE = 3, WK_BAD = 0;
+
+// one step of a branch walk ignoring everything dynamic (treeobs.cpp:476-539); returns false when the walk
+// ends on this state and sets kind
+DEVI bool static_succ(const uint16_t *__restrict__ g, int H, int W, int &r, int &c, int &d, int &kind) {
+    const unsigned gc = g[r * W + c];
+    const int nb = nibble(gc, d), num = __popc(nb);
+    int total = __popc(gc);
+    if (gc == 0x8421u) total = 2;                    // diamond crossing
+    if (num == 1) {
+        if (total == 1) { kind = WK_DEADEND; return false; }
+        const int nd = first_dir(nb), rr = r + d_row(nd), cc = c + d_col(nd);
+        if (rr < 0 || cc < 0 || rr >= H || cc >= W || !g[rr * W + cc]) { kind = WK_BAD; return false; }  // rail into nothing
+        d = nd; r = rr; c = cc;
+        return true;
+    }
+    kind = num > 1 ? WK_SWITCH : WK_BAD;
+    return false;
+}
+
+// steps and kind of the walk from (r, c, d); bound = number of states of the world (a longer walk must cycle)
+DEVI int static_walk_len(const uint16_t *__restrict__ g, int H, int W, int r, int c, int d, int bound, int &kind) {
+    const int r0 = r, c0 = c, d0 = d;
+    int steps = 0;
+    while (static_succ(g, H, W, r, c, d, kind)) {
+        if (++steps > bound) {                       // rail cycle: Brent for the index of the first revisit
+            int tr_ = r0, tc_ = c0, td = d0, hr = r0, hc = c0, hd = d0, power = 1, lam = 1, k2;
+            static_succ(g, H, W, hr, hc, hd, k2);
+            while (tr_ != hr || tc_ != hc || td != hd) {
+                if (power == lam) { tr_ = hr; tc_ = hc; td = hd; power *= 2; lam = 0; }
+                static_succ(g, H, W, hr, hc, hd, k2);
+                lam++;
+            }
+            tr_ = hr = r0; tc_ = hc = c0; td = hd = d0;
+            for (int k = 0; k < lam; k++) static_succ(g, H, W, hr, hc, hd, k2);
+            int mu = 0;
+            while (tr_ != hr || tc_ != hc || td != hd) {
+                static_succ(g, H, W, tr_, tc_, td, k2);
+                static_succ(g, H, W, hr, hc, hd, k2);
+                mu++;
+            }
+            kind = WK_CYCLE;
+            return mu + lam;
+        }
+    }
+    return steps;
+}
+
+template <int NT>
+DEVI uint32_t block_exclusive_scan(uint32_t v, uint32_t *s_part, uint32_t &total) {
+    const int tid = threadIdx.x;
+    s_part[tid] = v;
+    __syncthreads();
+    for (int off = 1; off < NT; off <<= 1) {
+        const uint32_t x = tid >= off ? s_part[tid - off] : 0;
+        __syncthreads();
+        s_part[tid] += x;
+        __syncthreads();
+    }
+    total = s_part[NT - 1];
+    const uint32_t ex = s_part[tid] - v;
+    __syncthreads();
+    return ex;
+}
+
+template <bool FILL, int NT>
+__global__ void __launch_bounds__(NT) k_walks(FlBatch b) {
+    const int e = blockIdx.x, H = (int)b.H, W = (int)b.W, HW = H * W, tid = threadIdx.x;
+    __shared__ uint32_t s_part[NT];
+    const uint16_t *__restrict__ g = b.grid + (size_t)e * b.grid_stride;
+    uint16_t *ridx = b.ridx + (size_t)e * b.ridx_stride;
+    int32_t *tot = b.walk_total + (size_t)e * 4;
+
+    // rail indices in cell order
+    const int per = (HW + NT - 1) / NT, lo = min(tid * per, HW), hi = min(lo + per, HW);
+    uint32_t cnt = 0;
+    for (int k = lo; k < hi; k++) cnt += g[k] != 0;
+    uint32_t n_rail;
+    uint32_t run = block_exclusive_scan<NT>(cnt, s_part, n_rail);
+    const int S = (int)n_rail * 4;
+    if (!FILL) {
+        // list length = sum over states of (steps + 1)
+        uint32_t len = 0;
+        for (int cs = tid; cs < HW * 4; cs += NT) {
+            const int cell = cs >> 2, d = cs & 3;
+            if (!g[cell]) continue;
+            int kind;
+            len += (uint32_t)static_walk_len(g, H, W, cell / W, cell % W, d, S, kind) + 1u;
+        }
+        uint32_t total;
+        block_exclusive_scan<NT>(len, s_part, total);
+        if (tid == 0) { tot[0] = S; tot[1] = (int)total; }
+        return;
+    }
+    uint32_t *srec = b.srec + (size_t)e * b.state_stride;
+    uint32_t *wstart = b.wstart + (size_t)e * b.state_stride;
+    uint32_t *wlenk = b.wlenk + (size_t)e * b.state_stride;
+    uint16_t *wlist = b.wlist + (size_t)e * b.wlist_stride;
+    for (int k = lo; k < hi; k++) {
+        const unsigned gc = g[k];
+        if (!gc) { ridx[k] = 0xFFFF; continue; }
+        ridx[k] = (uint16_t)run;
+        int total = __popc(gc);
+        if (gc == 0x8421u) total = 2;
+        for (int d = 0; d < 4; d++) {
+            const int nb = nibble(gc, d);
+            srec[run * 4 + d] = (uint32_t)k | ((uint32_t)d << 20) | ((uint32_t)nb << 22) |
+                                ((uint32_t)(total > 2 && __popc(nb) < 2) << 26);
+        }
+        run++;
+    }
+    for (int k = HW + tid; k < (int)b.ridx_stride; k += NT) ridx[k] = 0xFFFF;
+    __syncthreads();
+    // walk lengths, offsets, lists: thread t owns the contiguous states [slo, shi)
+    const int sper = (S + NT - 1) / NT, slo = min(tid * sper, S), shi = min(slo + sper, S);
+    uint32_t len = 0;
+    for (int sid = slo; sid < shi; sid++) {
+        const uint32_t rec = srec[sid];
+        const int cell = (int)(rec & 0xFFFFF), d = (int)((rec >> 20) & 3);
+        int kind = WK_BAD;
+        const int steps = static_walk_len(g, H, W, cell / W, cell % W, d, S, kind);
+        wlenk[sid] = (uint32_t)steps | ((uint32_t)kind << 28);
+        len += (uint32_t)steps + 1u;
+    }
+    uint32_t total;
+    uint32_t off = block_exclusive_scan<NT>(len, s_part, total);
+    for (int sid = slo; sid < shi; sid++) {
+        const uint32_t rec = srec[sid];
+        int r = (int)(rec & 0xFFFFF) / W, c = (int)(rec & 0xFFFFF) % W, d = (int)((rec >> 20) & 3), kind;
+        const int steps = (int)(wlenk[sid] & 0x0FFFFFFFu);
+        wstart[sid] = off;
+        for (int k = 0; k <= steps; k++) {
+            if (off < (uint32_t)b.wlist_stride) wlist[off] = (uint16_t)(ridx[r * W + c] * 4 + d);
+            off++;
+            if (k < steps) static_succ(g, H, W, r, c, d, kind);
+        }
+    }
+    for (int sid = S + tid; sid < (int)b.state_stride; sid += NT) { srec[sid] = 0; wstart[sid] = 0; wlenk[sid] = 0; }
+    if (tid == 0) { tot[0] = S; tot[1] = (int)total; }
+}
+
+}  // namespace

@@ -65,6 +65,10 @@ typedef struct FlBatch {
     int64_t dist_stride; /* uint16 elements between the distance maps of consecutive envs,
                             >= n_slots*H*W*4, multiple of 8 (16-byte aligned blocks: moved by TMA bulk copies) */
     int64_t *debug_clocks; /* tuning only: [E][16] SM-clock timestamps of k_observe's phases, NULL = off */
+    int64_t ridx_stride;   /* uint16 elements per env of ridx, >= H*W, multiple of 8 */
+    int64_t state_stride;  /* elements per env of srec / wstart / wlenk, >= 4 * rail cells, multiple of 4 */
+    int64_t wlist_stride;  /* uint16 elements per env of wlist, multiple of 8 */
+    int64_t reserved1;
 
     /* ---- world, static after upload (RailEnv.reset generators stay reference Python) ---- */
     const uint16_t *grid;      /* [E][grid_stride] transition bitmask per cell (core/transition_map.py:144) */
@@ -80,6 +84,14 @@ typedef struct FlBatch {
     const int32_t *earliest;   /* [E][N] earliest_departure */
     const int32_t *latest;     /* [E][N] latest_arrival */
     const uint8_t *sched;      /* [E][S][N] pre-drawn malfunction durations (0 = none); row sched_pos % S */
+    /* static branch-walk tables written by fl_walk_tables (csrc/walks.cuh): which states the tree observation's
+     * walk from a (cell, direction) state visits (treeobs.cpp:258-610 _explore_branch, rail-only part) */
+    uint16_t *ridx;            /* [E][ridx_stride] rail index per cell, 0xFFFF = no rail; state id = 4*ridx + dir */
+    uint32_t *srec;            /* [E][state_stride] cell | dir<<20 | transitions nibble<<22 | unusable switch<<26 */
+    uint32_t *wstart;          /* [E][state_stride] offset of the state's walk in wlist */
+    uint32_t *wlenk;           /* [E][state_stride] steps of the walk | kind<<28 (1 switch, 2 dead end, 3 cycle, 0 bad cell) */
+    uint16_t *wlist;           /* [E][wlist_stride] visited state ids, walk after walk */
+    int32_t *walk_total;       /* [E][4] written by fl_walk_tables: states, wlist elements needed, 0, 0 */
 
     /* ---- agent state (agent_utils.py:58-105 and step_utils/*) ---- */
     int16_t *rc;          /* [E][N][2] position, (-1,-1) = None */
@@ -122,6 +134,12 @@ const char *fl_error_string(int code);
 /* Replaces DistanceMap._compute/_distance_map_walker (flatland/envs/distance_map.py:57-160): one BFS
  * over (cell, orientation) per unique target slot, writing FlBatch.dist.  Reset-time only. */
 int fl_distance_map(const FlBatch *b, void *stream);
+
+/* Builds the static branch-walk tables of every environment (reset time, after the grid upload).  Two
+ * passes: fill == 0 only writes walk_total (ridx and walk_total must be allocated) so that the caller can
+ * size srec / wstart / wlenk / wlist; fill != 0 writes all tables.  No reference counterpart: the reference
+ * re-walks the rail cell by cell in every _explore_branch call (treeobs.cpp:258-610). */
+int fl_walk_tables(const FlBatch *b, int fill, void *stream);
 
 /* Replaces the tail of RailEnv.reset (flatland/envs/rail_env.py:335-347: reset_agents, elapsed=0,
  * dones cleared) and TreeObsForRailEnv::reset (flatland_cutils/src/treeobs.cpp:22-28: a fresh

@@ -187,3 +187,16 @@ def test_host_buffer_step_matches_device_step(golden):
             np.testing.assert_array_equal(h[k].numpy(), a.obs[k].cpu().numpy(), err_msg="%s step %d" % (k, t))
         np.testing.assert_array_equal(h["rewards"].numpy(), a.rewards.cpu().numpy())
         np.testing.assert_array_equal(h["dones"].numpy(), a.dones.cpu().numpy())
+
+
+@pytest.mark.parametrize("n_agents", [1, 4, 6])
+def test_rail_cycle_world_matches_oracle(n_agents):
+    """Switch-free rail cycle + dead-end spur (tests/handmade_worlds.py): the walk that comes back to its own
+    first state must end as a terminal node exactly where the reference's visited set stops it."""
+    from handmade_worlds import loop_world
+    w = loop_world(n_agents)
+    rng = np.random.RandomState(5 + n_agents)
+    acts = [np.where(rng.rand(w["T"], n_agents) < 0.8, 2, rng.randint(0, 5, (w["T"], n_agents))).astype(np.uint8) for _ in range(3)]
+    sched = np.zeros((w["T"], n_agents), np.uint8)
+    sched[7, 0] = 5                                   # one malfunction for good measure
+    run_against_oracle([w, w, w], acts, [sched, sched, sched], w["T"])

@@ -53,3 +53,24 @@ def test_oracle_motion_check_matches_reference(golden):
     for k in range(len(n)):
         got = orc.motion_check(cur[k, : n[k]], nxt[k, : n[k]])
         np.testing.assert_array_equal(got, ok[k, : n[k]], err_msg="case %d" % k)
+
+
+def test_oracle_runs_rail_cycle_world():
+    """The hand-made loop world (tests/handmade_worlds.py) exercises the `visited` branch of
+    _explore_branch; the oracle must produce terminal nodes (dist_to_next_branch = inf -> -1) there."""
+    from handmade_worlds import loop_world
+    w = loop_world(4)
+    env = orc.OracleEnv(w)
+    env.reset()
+    rng = np.random.RandomState(3)
+    saw_cycle_node = False
+    for t in range(50):
+        act = np.where(rng.rand(4) < 0.8, 2, rng.randint(0, 5, 4)).astype(np.uint8)
+        _, dones = env.step(act, np.zeros(4, np.uint8))
+        f = env.obs()["forest"]
+        # a real node (some feature != -1) whose dist_to_next_branch (feature 5) is -1 ended on a revisited state
+        real = (f != -1).any(axis=2)
+        saw_cycle_node |= bool((real[:, 1:] & (f[:, 1:, 5] == -1)).any())
+        if dones[-1]:
+            break
+    assert saw_cycle_node
