@@ -34,7 +34,7 @@ class FlObsBuffers(C.Structure):
 
 
 EXPORTS = ["fl_abi_version", "fl_batch_sizeof", "fl_error_string", "fl_distance_map", "fl_walk_tables", "fl_reset", "fl_step",
-           "fl_observe", "fl_batch_slice", "fl_step_observe_host", "fl_launch_count", "fl_profile_num_kernels", "fl_profile_kernel_name",
+           "fl_observe", "fl_observe_plan", "fl_batch_slice", "fl_step_observe_host", "fl_launch_count", "fl_profile_num_kernels", "fl_profile_kernel_name",
            "fl_profile_enable", "fl_profile_collect"]
 
 _lib = None
@@ -66,6 +66,8 @@ def lib():
     L.fl_observe.argtypes = [C.POINTER(FlBatch)] + [P] * 8
     L.fl_step_observe_host.argtypes = [C.POINTER(FlBatch), P, P, C.POINTER(FlObsBuffers), C.POINTER(FlObsBuffers),
                                        C.c_uint32, C.c_int, P, P]
+    L.fl_observe_plan.argtypes = [C.POINTER(FlBatch), P, C.c_int]
+    L.fl_observe_plan.restype = C.c_int
     L.fl_batch_slice.argtypes = [C.POINTER(FlBatch), C.c_int64, C.c_int64, C.POINTER(FlBatch)]
     L.fl_profile_num_kernels.restype = C.c_int
     L.fl_profile_kernel_name.restype = C.c_char_p

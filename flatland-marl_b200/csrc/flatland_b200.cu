@@ -100,7 +100,7 @@ ObsLayout make_obs_layout(const FlBatch *b, int nt) {
     L.part = take(nt * 4);
     L.ag = take(14 * N * 4);
     L.dl = take(18 * N);
-    const int tree_b = (3 * L.tile * 31 + 5 * L.tile + 4 + L.tile * 8) * 4 + L.tile * 30 * 2;
+    const int tree_b = (2 * L.tile * 31 + (L.tile & 1) + 5 * L.tile + 4 + L.tile * 8) * 4 + L.tile * 30 * 2;
     L.tree = take(tree_b);
     L.tmp_cap = tree_b / 6;
     const long long grid_b = b->grid_stride * 2, ci_b = (long long)HW * 4, ks_b = (long long)(K + 1) * 4;
@@ -136,6 +136,11 @@ ObsLayout make_obs_layout(const FlBatch *b, int nt) {
     L.dist = dist_fits ? opt(dist_b) : -1;
     L.total = off;
     return L;
+}
+
+int obs_group(const FlBatch *) {
+    if (const char *s = getenv("FL_OBS_G")) { const int v = atoi(s); if (v == 4 || v == 8 || v == 16 || v == 32) return v; }
+    return 8;
 }
 
 int obs_threads(const FlBatch *b) {
@@ -254,7 +259,12 @@ int fl_observe(const FlBatch *b, float *d_agent_attr, float *d_forest, int32_t *
     const int nt = obs_threads(b);
     const ObsLayout lay = make_obs_layout(b, nt);
     if (lay.total > SMEM_MAX) return FL_ERR_SMEM;
-    auto kern = nt == 64 ? k_observe<64> : nt == 128 ? k_observe<128> : k_observe<256>;
+    const int g = obs_group(b);
+    using Kern = void (*)(FlBatch, ObsLayout, float *, float *, int32_t *, int32_t *, int32_t *, uint8_t *, float *);
+    static const Kern table[3][4] = {{k_observe<64, 4>, k_observe<64, 8>, k_observe<64, 16>, k_observe<64, 32>},
+                                     {k_observe<128, 4>, k_observe<128, 8>, k_observe<128, 16>, k_observe<128, 32>},
+                                     {k_observe<256, 4>, k_observe<256, 8>, k_observe<256, 16>, k_observe<256, 32>}};
+    Kern kern = table[nt == 64 ? 0 : nt == 128 ? 1 : 2][g == 4 ? 0 : g == 8 ? 1 : g == 16 ? 2 : 3];
     if (lay.total > 48 * 1024) {
         cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, lay.total);
         if (err != cudaSuccess) return (int)err;
@@ -301,6 +311,17 @@ cudaEvent_t chunk_event(int k) {
     return pool[dev][k];
 }
 }  // namespace
+
+int fl_observe_plan(const FlBatch *b, int32_t *out, int n_out) {
+    if (int rc = check_batch(b)) return rc;
+    if (!out || n_out < 20) return FL_ERR_BAD_ARG;
+    const int nt = obs_threads(b);
+    const ObsLayout L = make_obs_layout(b, nt);
+    const int v[20] = {nt, L.total, L.tile, L.ent_cap, L.tmp_cap, L.grid, L.ci, L.ks, L.ent, L.dist,
+                       L.ridx, L.srec, L.wstart, L.wlenk, L.wlist, L.ag, L.dl, L.tree, SMEM_MAX / (L.total + 1024), obs_group(b)};
+    for (int k = 0; k < 20; k++) out[k] = v[k];
+    return FL_OK;
+}
 
 int fl_step_observe_host(const FlBatch *b, const uint8_t *h_actions, uint8_t *d_actions, const FlObsBuffers *d_out,
                          const FlObsBuffers *h_out, uint32_t flags, int n_chunks, void *stream, void *copy_stream) {

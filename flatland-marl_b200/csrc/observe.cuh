@@ -29,7 +29,6 @@ namespace {
 
 constexpr int OBS_MAX_TILE = 64;        // agents whose trees are built together (bounds the node table)
 constexpr int OBS_Q_EMPTY = 0xFFFF;
-constexpr int OBS_G = 8;                // lanes that share one branch walk
 constexpr int I_INF = 0x7fffffff;
 
 struct ObsLayout {   // byte offsets into dynamic shared memory (host: make_obs_layout); < 0 = lives in global memory
@@ -289,7 +288,8 @@ struct ObsAgents {
 };
 
 struct ObsTile {
-    uint32_t *n_rc, *n_meta, *n_tot;        // [OBS_TILE][31] node table: start state id, dir|ad|null|parent, distance so far
+    uint16_t *n_sid, *n_meta;               // [OBS_TILE][31] node table: start state id (0xFFFF = null), dir|ad|null|parent
+    uint32_t *n_tot;                        //                distance walked before the node's branch starts
     uint32_t *t_mask, *t_next;              // [OBS_TILE] real-node bit mask of the level being walked / being created
     int *t_pend;                            // [OBS_TILE] walks of the current level still running
     uint32_t *t_lsle;                       // [OBS_TILE] level start | level end << 8
@@ -299,8 +299,9 @@ struct ObsTile {
     int *q_head, *q_tail, *n_done;
 };
 
-template <int NT>
-__global__ void __launch_bounds__(NT)
+// NT threads per CTA; OBS_G lanes share one branch walk
+template <int NT, int OBS_G>
+__global__ void __launch_bounds__(NT, NT == 256 ? 4 : (NT == 128 ? 6 : 8))
 k_observe(FlBatch b, ObsLayout lay, float *__restrict__ out_attr, float *__restrict__ out_forest,
           int32_t *__restrict__ out_adj, int32_t *__restrict__ out_norder, int32_t *__restrict__ out_eorder,
           uint8_t *__restrict__ out_valid, float *__restrict__ out_dist_target) {
@@ -353,7 +354,8 @@ k_observe(FlBatch b, ObsLayout lay, float *__restrict__ out_attr, float *__restr
     ObsTile Tt;
     {
         uint32_t *p = reinterpret_cast<uint32_t *>(smraw + lay.tree);
-        Tt.n_rc = p; p += OBS_TILE * 31; Tt.n_meta = p; p += OBS_TILE * 31; Tt.n_tot = p; p += OBS_TILE * 31;
+        Tt.n_tot = p; p += OBS_TILE * 31;
+        Tt.n_sid = reinterpret_cast<uint16_t *>(p); Tt.n_meta = Tt.n_sid + OBS_TILE * 31 + (OBS_TILE & 1); p += OBS_TILE * 31 + (OBS_TILE & 1);
         Tt.t_mask = p; p += OBS_TILE; Tt.t_next = p; p += OBS_TILE;
         Tt.t_pend = reinterpret_cast<int *>(p); p += OBS_TILE; Tt.t_lsle = p; p += OBS_TILE;
         Tt.t_count = reinterpret_cast<int *>(p); p += OBS_TILE;
@@ -566,8 +568,8 @@ k_observe(FlBatch b, ObsLayout lay, float *__restrict__ out_attr, float *__restr
                 const int bd = (orientation + ad) & 3, idx = 2 + ad;
                 const uint32_t csid = tbit(nb, bd) ? child_state(ridx, H, W, vr, vc, bd) : 0xFFFFFFFFu;
                 const bool real = csid != 0xFFFFFFFFu;
-                Tt.n_rc[la * 31 + idx] = csid;
-                Tt.n_meta[la * 31 + idx] = (uint32_t)bd | ((uint32_t)(ad + 1) << 2) | ((real ? 0u : 1u) << 4);
+                Tt.n_sid[la * 31 + idx] = (uint16_t)csid;
+                Tt.n_meta[la * 31 + idx] = (uint16_t)(bd | ((ad + 1) << 2) | ((real ? 0 : 1) << 4));
                 Tt.n_tot[la * 31 + idx] = 1;
                 if (real) mask |= 1u << (idx - 1);
                 else store_null_node(forest + idx * FL_NODE_F);
@@ -588,17 +590,18 @@ k_observe(FlBatch b, ObsLayout lay, float *__restrict__ out_attr, float *__restr
 
         // Branch walks (treeobs.cpp:258-610).  A group of OBS_G lanes takes one walk from the queue; the states
         // the walk visits come from the static list of its start state (walks.cuh), OBS_G of them per iteration,
-        // one per lane; the per-cell findings are reduced over the group when the walk ends.
+        // one per lane; what the lanes find is combined with warp ballots and redux instructions.
         {
             const int gl = lane & (OBS_G - 1), gbase = lane & ~(OBS_G - 1);
-            const unsigned gmask = (OBS_G == 32 ? 0xFFFFFFFFu : ((1u << OBS_G) - 1u)) << gbase;
+            constexpr unsigned GM = OBS_G == 32 ? 0xFFFFFFFFu : ((1u << OBS_G) - 1u);
+            const unsigned gmask = GM << gbase;
             bool active = false;
             int claim = -1;
             int la = 0, n = 0, h = 0, tot0 = 0, k0 = 0, L = 0, skind = 0, tcell = -1;
             uint32_t wbase = 0;
-            int own = I_INF, other_agent = I_INF, conflict = I_INF, unusable = I_INF;
-            int same = 0, opp = 0, malf = 0, rtdn = 0;
-            float min_speed = 1.0f, tpc_f = 1.0f;
+            // group-uniform findings: first walk index (k) of each event, counts, flags
+            int k_other = I_INF, k_conf = I_INF, k_unus = I_INF, same = 0, opp = 0, malf = 0, rtdn = 0, spd_bits = 0x3F800000;
+            float tpc_f = 1.0f;
             const uint16_t *dm = dist;
             int iters = 0;
             while (true) {
@@ -615,14 +618,14 @@ k_observe(FlBatch b, ObsLayout lay, float *__restrict__ out_attr, float *__restr
                         active = true;
                         la = (int)(it >> 5); n = (int)(it & 31);
                         h = a0 + la;
-                        const uint32_t sid0 = Tt.n_rc[la * 31 + n];
+                        const uint32_t sid0 = Tt.n_sid[la * 31 + n];
                         tot0 = (int)Tt.n_tot[la * 31 + n];
                         wbase = wstart[sid0];
                         const uint32_t lk = wlenk[sid0];
                         L = (int)(lk & 0x0FFFFFFFu); skind = (int)(lk >> 28);
                         k0 = 0;
-                        own = other_agent = conflict = unusable = I_INF;
-                        same = opp = malf = rtdn = 0; min_speed = 1.0f;
+                        k_other = k_conf = k_unus = I_INF;
+                        same = opp = malf = rtdn = 0; spd_bits = 0x3F800000;             // min speed starts at 1.0f
                         const uint32_t tg = A.tgt[h];
                         tcell = (int)(short)(tg & 0xFFFF) * W + (int)(tg >> 16);
                         tpc_f = (float)(1.0 / (double)A.speed[h]);                       // treeobs.cpp:304
@@ -636,20 +639,23 @@ k_observe(FlBatch b, ObsLayout lay, float *__restrict__ out_attr, float *__restr
                     if (valid) rec = srec[wlist[wbase + k]];
                     const int cell = (int)(rec & 0xFFFFF), d = (int)((rec >> 20) & 3), nb = (int)((rec >> 22) & 15);
                     // the walk stops on the observer's own target (treeobs.cpp:467-475, 483-489): cells behind it do not count
-                    const unsigned tb = (__ballot_sync(gmask, valid && cell == tcell) >> gbase) & (OBS_G == 32 ? 0xFFFFFFFFu : ((1u << OBS_G) - 1u));
+                    const unsigned tb = (__ballot_sync(gmask, valid && cell == tcell) >> gbase) & GM;
                     const int kt = tb ? __ffs(tb) - 1 : OBS_G;
                     const bool ends = tb != 0 || k0 + OBS_G > L;                         // this chunk holds the last cell
                     const int k_end = tb ? k0 + kt : L;
-                    if (valid && gl <= kt) {
+                    const bool counts = valid && gl <= kt;
+                    bool f_agent = false, f_same = false, f_malf = false, f_conf = false;
+                    int my_rtd = 0, my_spd = 0x3F800000;
+                    if (counts) {
                         const int tot = tot0 + k;
                         const uint32_t cinfo = ci[cell];
                         if (cinfo) {                   // treeobs.cpp:322-360 (the observer itself counts too)
-                            other_agent = min(other_agent, tot);
-                            malf = max(malf, (int)((cinfo >> 8) & 1u));
+                            f_agent = true;
+                            f_malf = (cinfo >> 8) & 1u;
                             const int cnt = (int)((cinfo >> 11) & 1023u);
-                            rtdn += cnt ? cnt - 1 : 0;
-                            if ((int)((cinfo >> 9) & 3u) == d) { same++; min_speed = fminf(min_speed, A.speed[(cinfo >> 21) - 1]); }
-                            else opp++;
+                            my_rtd = cnt ? cnt - 1 : 0;
+                            f_same = (int)((cinfo >> 9) & 3u) == d;
+                            if (f_same) my_spd = __float_as_int(A.speed[(cinfo >> 21) - 1]);
                         }
                         const int pt = (int)__fmul_rn((float)tot, tpc_f);               // treeobs.cpp:378
                         if (pt < NPRED && tot < NPRED) {                                 // treeobs.cpp:379-465
@@ -658,18 +664,11 @@ k_observe(FlBatch b, ObsLayout lay, float *__restrict__ out_attr, float *__restr
                             const uint32_t s0 = key ? ks[key - 1] : 0u, s1 = ks[key];
                             const int pre = max(0, pt - 1), post = min(NPRED - 1, pt + 1);
                             unsigned acc = 0;
-                            for (uint32_t idx = s0; idx < s1; idx++) {
-                                const uint32_t en = ent[idx];
-                                const int t0 = (int)((en >> 10) & 511);
-                                if ((en >> 19) & 1u) { if (t0 > post) continue; }       // long-lived entries come first
-                                else {                                                   // then regular ones ordered by t0
-                                    if (t0 > post) break;
-                                    if (t0 + tpc_max <= pre) continue;
-                                }
+                            auto candidate = [&](uint32_t en, int t0) {
                                 const int ag = (int)(en & 1023);
                                 const uint32_t ainfo = A.info[ag];
                                 const int t1 = ((en >> 19) & 1u) ? NPRED - 1 : (t0 ? t0 + (int)(ainfo >> 24) - 1 : 0);
-                                if (t1 < pre) continue;
+                                if (t1 < pre) return;
                                 const int dh = (int)((en >> 20) & 3), dp = (int)((en >> 22) & 3), dn = (int)((en >> 24) & 3);
                                 const bool done = (ainfo >> 5) & 1;
                                 const bool in_cur = t0 <= pt && pt <= t1, in_pre = t0 <= pre && pre <= t1,
@@ -679,56 +678,79 @@ k_observe(FlBatch b, ObsLayout lay, float *__restrict__ out_attr, float *__restr
                                 const bool other = ag != h;
                                 acc |= (in_cur && other ? 1u : 0u) | (in_pre && other ? 2u : 0u) | (in_post && other ? 4u : 0u) |
                                        (in_cur && cf ? 8u : 0u) | (in_pre && cf ? 16u : 0u) | (in_post && cf ? 32u : 0u);
+                            };
+                            uint32_t idx = s0;
+                            for (; idx < s1; idx++) {                                    // long-lived entries come first
+                                const uint32_t en = ent[idx];
+                                if (!((en >> 19) & 1u)) break;
+                                const int t0 = (int)((en >> 10) & 511);
+                                if (t0 <= post) candidate(en, t0);
                             }
-                            const bool cf = (acc & 1u) ? (acc & 8u) : (acc & 2u) ? (acc & 16u) : (acc & 4u) ? (acc & 32u) : false;
-                            if (cf) conflict = min(conflict, tot);
+                            // regular entries are ordered by t0: only those with pre - tpc_max < t0 <= post can matter
+                            const int t_lo = pre - tpc_max + 1;
+                            uint32_t lo = idx, hi = s1;
+                            while (lo < hi) {
+                                const uint32_t mid = (lo + hi) >> 1;
+                                if ((int)((ent[mid] >> 10) & 511) < t_lo) lo = mid + 1; else hi = mid;
+                            }
+                            for (idx = lo; idx < s1; idx++) {
+                                const uint32_t en = ent[idx];
+                                const int t0 = (int)((en >> 10) & 511);
+                                if (t0 > post) break;
+                                candidate(en, t0);
+                            }
+                            f_conf = (acc & 1u) ? (acc & 8u) : (acc & 2u) ? (acc & 16u) : (acc & 4u) ? (acc & 32u) : false;
                         }
-                        if (cell == tcell) own = min(own, tot);
-                        if (k < k_end && ((rec >> 26) & 1u)) unusable = min(unusable, tot);   // never on the cell the walk ends on
                     }
+                    // combine over the group: the first lane of an event gives its walk index, counts are popcounts
+                    const unsigned b_agent = (__ballot_sync(gmask, f_agent) >> gbase) & GM;
+                    if (b_agent) {                                                       // group-uniform
+                        const unsigned b_same = (__ballot_sync(gmask, f_same) >> gbase) & GM;
+                        k_other = min(k_other, k0 + __ffs(b_agent) - 1);
+                        same += __popc(b_same); opp += __popc(b_agent & ~b_same);
+                        malf |= __any_sync(gmask, f_malf);
+                        rtdn += __reduce_add_sync(gmask, my_rtd);
+                        spd_bits = min(spd_bits, __reduce_min_sync(gmask, my_spd));     // positive floats order like their bits
+                    }
+                    const unsigned b_conf = (__ballot_sync(gmask, f_conf) >> gbase) & GM;
+                    if (b_conf) k_conf = min(k_conf, k0 + __ffs(b_conf) - 1);
+                    const unsigned b_unus = (__ballot_sync(gmask, counts && k < k_end && ((rec >> 26) & 1u)) >> gbase) & GM;
+                    if (b_unus) k_unus = min(k_unus, k0 + __ffs(b_unus) - 1);            // never on the cell the walk ends on
                     if (!ends) k0 += OBS_G;
                     else {
-                        // ---- the walk is over: reduce the findings over the group -------------------------
-#pragma unroll
-                        for (int o = OBS_G / 2; o > 0; o >>= 1) {
-                            own = min(own, __shfl_xor_sync(gmask, own, o));
-                            other_agent = min(other_agent, __shfl_xor_sync(gmask, other_agent, o));
-                            conflict = min(conflict, __shfl_xor_sync(gmask, conflict, o));
-                            unusable = min(unusable, __shfl_xor_sync(gmask, unusable, o));
-                            same += __shfl_xor_sync(gmask, same, o);
-                            opp += __shfl_xor_sync(gmask, opp, o);
-                            malf = max(malf, __shfl_xor_sync(gmask, malf, o));
-                            rtdn += __shfl_xor_sync(gmask, rtdn, o);
-                            min_speed = fminf(min_speed, __shfl_xor_sync(gmask, min_speed, o));
-                        }
+                        // ---- the walk is over: lanes 0..2 write one float4 of the node and create one child each ----
                         active = false;
                         const int kind = tb ? 4 : (skind == WK_BAD ? 3 : skind);         // 1 switch, 2 dead end, 3 cycle, 4 target
-                        if (gl == 0) {
-                            if (!tb && skind == WK_BAD) atomicOr(&b.status[e], FL_ST_BAD_CELL);   // treeobs.cpp:527-535 throws
-                            const uint32_t erec = srec[wlist[wbase + k_end]];            // the state the walk ended on
-                            const int ecell = (int)(erec & 0xFFFFF), ed = (int)((erec >> 20) & 3), enb = (int)((erec >> 22) & 15);
-                            const int er = ecell / W, ec = ecell - er * W, tot = tot0 + k_end;
-                            const size_t ea = (size_t)e * N + h;
-                            float *forest = out_forest + ea * (FL_MAX_NODES * FL_NODE_F);
-                            int dnb, dmin;
-                            if (kind == 4) { dnb = tot; dmin = 0; }
-                            else {
-                                const unsigned dv = dm[((size_t)ecell) * 4 + ed];
-                                dmin = dv == FL_DIST_INF ? I_INF : (int)dv;
-                                dnb = kind == 3 ? I_INF : tot;
+                        const uint32_t erec = srec[wlist[wbase + k_end]];                // the state the walk ended on
+                        const int ecell = (int)(erec & 0xFFFFF), ed = (int)((erec >> 20) & 3), enb = (int)((erec >> 22) & 15);
+                        const int er = ecell / W, ec = ecell - er * W, tot = tot0 + k_end;
+                        const size_t ea = (size_t)e * N + h;
+                        float *forest = out_forest + ea * (FL_MAX_NODES * FL_NODE_F);
+                        const uint32_t lsle = Tt.t_lsle[la], lmask = Tt.t_mask[la];
+                        const int ls = (int)(lsle & 0xFF), le = (int)(lsle >> 8);
+                        const int base = le + 3 * __popc(lmask & ((1u << (n - ls)) - 1u));
+                        bool child_real = false;
+                        if (gl < 3) {
+                            float4 v;
+                            if (gl == 0) {                                               // scale_node (treeobs.cpp:111-152)
+                                v = make_float4(tb ? (float)tot / T : -1.0f, -1.0f, k_other != I_INF ? (float)(tot0 + k_other) / T : -1.0f,
+                                                k_conf != I_INF ? (float)(tot0 + k_conf) / T : -1.0f);
+                            } else if (gl == 1) {
+                                int dnb, dmin;
+                                if (kind == 4) { dnb = tot; dmin = 0; }
+                                else {
+                                    const unsigned dv = dm[((size_t)ecell) * 4 + ed];
+                                    dmin = dv == FL_DIST_INF ? I_INF : (int)dv;
+                                    dnb = kind == 3 ? I_INF : tot;
+                                }
+                                v = make_float4(k_unus != I_INF ? (float)(tot0 + k_unus) / T : -1.0f, scale_i(dnb, T), scale_i(dmin, T), (float)same / Nf);
+                            } else {
+                                v = make_float4((float)opp / Nf, (float)malf / Nf, __int_as_float(spd_bits), (float)rtdn / Nf);
                             }
-                            store_node(forest + n * FL_NODE_F,                          // scale_node (treeobs.cpp:111-152)
-                                       make_float4(scale_i(own, T), -1.0f, scale_i(other_agent, T), scale_i(conflict, T)),
-                                       make_float4(scale_i(unusable, T), scale_i(dnb, T), scale_i(dmin, T), (float)same / Nf),
-                                       make_float4((float)opp / Nf, (float)malf / Nf, min_speed, (float)rtdn / Nf));
-                            // children in order L, F, R (treeobs.cpp:583-608); their BFS indices follow from the level's mask
-                            const uint32_t lsle = Tt.t_lsle[la], lmask = Tt.t_mask[la];
-                            const int ls = (int)(lsle & 0xFF), le = (int)(lsle >> 8);
-                            const int base = le + 3 * __popc(lmask & ((1u << (n - ls)) - 1u));
-                            uint32_t bits = 0;
-                            for (int a2 = -1; a2 <= 1; a2++) {
-                                const int idx = base + a2 + 1;
-                                if (idx >= FL_MAX_NODES) break;
+                            reinterpret_cast<float4 *>(forest + n * FL_NODE_F)[gl] = v;
+                            // child gl - 1 in order L, F, R (treeobs.cpp:583-608); its BFS index follows from the level's mask
+                            const int a2 = gl - 1, idx = base + gl;
+                            if (idx < FL_MAX_NODES) {
                                 const int bd = (ed + a2) & 3, rb = (bd + 2) & 3;
                                 int cd = bd;
                                 bool real = false;
@@ -736,13 +758,18 @@ k_observe(FlBatch b, ObsLayout lay, float *__restrict__ out_attr, float *__restr
                                 else if (kind == 1 && tbit(enb, bd)) { cd = bd; real = true; }
                                 const uint32_t csid = real ? child_state(ridx, H, W, er, ec, cd) : 0xFFFFFFFFu;
                                 real = csid != 0xFFFFFFFFu;
-                                Tt.n_rc[la * 31 + idx] = csid;
-                                Tt.n_meta[la * 31 + idx] = (uint32_t)cd | ((uint32_t)(a2 + 1) << 2) | ((real ? 0u : 1u) << 4) | ((uint32_t)n << 8);
+                                Tt.n_sid[la * 31 + idx] = (uint16_t)csid;
+                                Tt.n_meta[la * 31 + idx] = (uint16_t)(cd | ((a2 + 1) << 2) | ((real ? 0 : 1) << 4) | (n << 8));
                                 Tt.n_tot[la * 31 + idx] = (uint32_t)(tot + 1);
-                                if (real) bits |= 1u << (idx - le);
-                                else store_null_node(forest + idx * FL_NODE_F);
+                                child_real = real;
+                                if (!real) store_null_node(forest + idx * FL_NODE_F);
                             }
-                            if (bits) atomicOr(&Tt.t_next[la], bits);
+                        }
+                        __syncwarp(gmask);                                               // the children are in the node table
+                        const unsigned cb = (__ballot_sync(gmask, child_real) >> gbase) & 7u;  // bit j = child j is real
+                        if (gl == 0) {
+                            if (!tb && skind == WK_BAD) atomicOr(&b.status[e], FL_ST_BAD_CELL);   // treeobs.cpp:527-535 throws
+                            if (cb) atomicOr(&Tt.t_next[la], cb << (base - le));
                             __threadfence_block();
                             if (atomicSub(&Tt.t_pend[la], 1) == 1) {                    // last walk of this agent's level: release the next one
                                 __threadfence_block();

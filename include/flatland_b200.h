@@ -163,6 +163,12 @@ int fl_observe(const FlBatch *b, float *d_agent_attr, float *d_forest, int32_t *
                int32_t *d_node_order, int32_t *d_edge_order, uint8_t *d_valid_actions,
                float *d_dist_target, void *stream);
 
+/* Diagnostics: the shared-memory plan fl_observe uses for this batch.  out[0..19] = threads per CTA, dynamic
+ * shared bytes, tree tile (agents), entry capacity, unsorted-entry capacity, byte offsets of grid, occupancy,
+ * key counters, entries, distance maps, ridx, srec, wstart, wlenk, wlist (-1 = stays in global memory),
+ * agents, deadlock scratch, tree tile, CTAs per SM that fit, lanes per walk group. */
+int fl_observe_plan(const FlBatch *b, int32_t *out, int n_out);
+
 /* A view of environments [e0, e0+n) of a batch: every pointer advanced by e0 environments, E = n.  The view
  * aliases the parent's memory; stepping disjoint views on different streams is allowed. */
 int fl_batch_slice(const FlBatch *b, int64_t e0, int64_t n, FlBatch *out);

@@ -9,9 +9,9 @@ if ! grep -q "pytest rc=0" gpurun_out/pytest_gpu.log; then
 fi
 : > gpurun_out/sweep.txt
 for cfg in ${CONFIGS:-Test_03}; do
-for nt in ${NTS:-64 128 256}; do for c in ${CTAS:-2 3 4 5 6}; do
-  FL_OBS_NT=$nt FL_OBS_CTAS=$c timeout 300 python bench.py --config $cfg --steps 60 --warmup 5 --no-cpu --e2e-steps 3 --profile-steps 20 > gpurun_out/sw.json 2> gpurun_out/sw.err
-  python - "$cfg" "$nt" "$c" >> gpurun_out/sweep.txt <<'PY'
+for g in ${GS:-8}; do for nt in ${NTS:-64 128 256}; do for c in ${CTAS:-2 3 4 5 6}; do
+  FL_OBS_G=$g FL_OBS_NT=$nt FL_OBS_CTAS=$c timeout 300 python bench.py --config $cfg --steps 60 --warmup 5 --no-cpu --e2e-steps 3 --profile-steps 20 > gpurun_out/sw.json 2> gpurun_out/sw.err
+  python - "$cfg" "g$g-nt$nt" "$c" >> gpurun_out/sweep.txt <<'PY'
 import json,sys
 try:
     d=json.load(open('gpurun_out/sw.json'))
@@ -19,5 +19,5 @@ try:
 except Exception as e:
     print(sys.argv[1:], 'FAILED', e, open('gpurun_out/sw.err').read()[-300:])
 PY
-done; done; done
+done; done; done; done
 cat gpurun_out/sweep.txt

@@ -18,6 +18,7 @@ worlds = bench.load_worlds(cfg, E)
 batch = fb.BatchedRailEnv(worlds, auto_reset=True, debug_clocks=True)
 N = batch.N
 batch.reset()
+print('plan', batch.observe_plan())
 gen = torch.Generator(device=batch.device); gen.manual_seed(1)
 acc = []
 for t in range(steps):
