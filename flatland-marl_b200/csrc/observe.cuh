@@ -729,9 +729,12 @@ k_observe(FlBatch b, ObsLayout lay, float *__restrict__ out_attr, float *__restr
                         const uint32_t lsle = Tt.t_lsle[la], lmask = Tt.t_mask[la];
                         const int ls = (int)(lsle & 0xFF), le = (int)(lsle >> 8);
                         const int base = le + 3 * __popc(lmask & ((1u << (n - ls)) - 1u));
-                        bool child_real = false;
+                        // Shared-memory bookkeeping first, global stores last: a CTA-scope fence waits for the thread's
+                        // outstanding global stores too, and nothing in this kernel reads the forest back.
+                        bool child_real = false, child_null = false;
+                        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                        const int cidx = base + gl;
                         if (gl < 3) {
-                            float4 v;
                             if (gl == 0) {                                               // scale_node (treeobs.cpp:111-152)
                                 v = make_float4(tb ? (float)tot / T : -1.0f, -1.0f, k_other != I_INF ? (float)(tot0 + k_other) / T : -1.0f,
                                                 k_conf != I_INF ? (float)(tot0 + k_conf) / T : -1.0f);
@@ -747,10 +750,9 @@ k_observe(FlBatch b, ObsLayout lay, float *__restrict__ out_attr, float *__restr
                             } else {
                                 v = make_float4((float)opp / Nf, (float)malf / Nf, __int_as_float(spd_bits), (float)rtdn / Nf);
                             }
-                            reinterpret_cast<float4 *>(forest + n * FL_NODE_F)[gl] = v;
                             // child gl - 1 in order L, F, R (treeobs.cpp:583-608); its BFS index follows from the level's mask
-                            const int a2 = gl - 1, idx = base + gl;
-                            if (idx < FL_MAX_NODES) {
+                            const int a2 = gl - 1;
+                            if (cidx < FL_MAX_NODES) {
                                 const int bd = (ed + a2) & 3, rb = (bd + 2) & 3;
                                 int cd = bd;
                                 bool real = false;
@@ -758,15 +760,15 @@ k_observe(FlBatch b, ObsLayout lay, float *__restrict__ out_attr, float *__restr
                                 else if (kind == 1 && tbit(enb, bd)) { cd = bd; real = true; }
                                 const uint32_t csid = real ? child_state(ridx, H, W, er, ec, cd) : 0xFFFFFFFFu;
                                 real = csid != 0xFFFFFFFFu;
-                                Tt.n_sid[la * 31 + idx] = (uint16_t)csid;
-                                Tt.n_meta[la * 31 + idx] = (uint16_t)(cd | ((a2 + 1) << 2) | ((real ? 0 : 1) << 4) | (n << 8));
-                                Tt.n_tot[la * 31 + idx] = (uint32_t)(tot + 1);
-                                child_real = real;
-                                if (!real) store_null_node(forest + idx * FL_NODE_F);
+                                Tt.n_sid[la * 31 + cidx] = (uint16_t)csid;
+                                Tt.n_meta[la * 31 + cidx] = (uint16_t)(cd | ((a2 + 1) << 2) | ((real ? 0 : 1) << 4) | (n << 8));
+                                Tt.n_tot[la * 31 + cidx] = (uint32_t)(tot + 1);
+                                child_real = real; child_null = !real;
                             }
                         }
                         __syncwarp(gmask);                                               // the children are in the node table
                         const unsigned cb = (__ballot_sync(gmask, child_real) >> gbase) & 7u;  // bit j = child j is real
+                        int pad_from = FL_MAX_NODES;
                         if (gl == 0) {
                             if (!tb && skind == WK_BAD) atomicOr(&b.status[e], FL_ST_BAD_CELL);   // treeobs.cpp:527-535 throws
                             if (cb) atomicOr(&Tt.t_next[la], cb << (base - le));
@@ -777,7 +779,7 @@ k_observe(FlBatch b, ObsLayout lay, float *__restrict__ out_attr, float *__restr
                                 const int nls = le, nle = min(FL_MAX_NODES, le + 3 * __popc(lmask));
                                 if (nmask == 0) {                                       // no real node left: the rest is padding
                                     Tt.t_count[la] = nle;
-                                    for (int q = nle; q < FL_MAX_NODES; q++) store_null_node(forest + q * FL_NODE_F);
+                                    pad_from = nle;
                                     __threadfence_block();
                                     atomicAdd(Tt.n_done, 1);
                                 } else {
@@ -790,6 +792,11 @@ k_observe(FlBatch b, ObsLayout lay, float *__restrict__ out_attr, float *__restr
                                 }
                             }
                         }
+                        if (gl < 3) {
+                            reinterpret_cast<float4 *>(forest + n * FL_NODE_F)[gl] = v;
+                            if (child_null) store_null_node(forest + cidx * FL_NODE_F);
+                        }
+                        for (int q = pad_from; q < FL_MAX_NODES; q++) store_null_node(forest + q * FL_NODE_F);
                     }
                 }
                 const bool finished = !active && ld_vol_i32(Tt.n_done) >= na;
