@@ -254,7 +254,18 @@ DEVI int road_type_of(int trans) {  // loader.cpp:122-161: first rotation that i
     return 0;
 }
 
-DEVI float scale_i(int v, float T) { return v != I_INF ? (float)v / T : -1.0f; }  // treeobs.cpp:111-152
+// a / b correctly rounded (identical to IEEE division for the integer-valued operands of this kernel) from the
+// correctly rounded reciprocal rb = __frcp_rn(b): q0 = RN(a*rb), r = a - b*q0 (exact in an FMA), q = RN(q0 + r*rb).
+// The only inputs for which this sequence can misround have an all-ones significand in b; b is a step or agent
+// count here.  Replaces the ~20-instruction division sequence on the per-node path.
+DEVI float div_rn(float a, float b, float rb) {
+    const float q0 = a * rb;
+    const float r = fmaf(-q0, b, a);
+    return fmaf(r, rb, q0);
+}
+struct Scale { float T, rT, N, rN; };
+DEVI float scale_i(int v, const Scale &sc) { return v != I_INF ? div_rn((float)v, sc.T, sc.rT) : -1.0f; }  // treeobs.cpp:111-152
+DEVI float scale_n(int v, const Scale &sc) { return div_rn((float)v, sc.N, sc.rN); }
 
 // state id of the cell entered from (r, c) in direction cd; 0xFFFFFFFF when the rail leads nowhere (invalid grid)
 DEVI uint32_t child_state(const uint16_t *ridx, int H, int W, int r, int c, int cd) {
@@ -393,6 +404,7 @@ k_observe(FlBatch b, ObsLayout lay, float *__restrict__ out_attr, float *__restr
     if (lay.ci >= 0) { for (int k = tid; k < HW; k += NT) ci[k] = 0; }
     else { for (int i = tid; i < N; i += NT) { const int oc = b.occ_cell[(size_t)e * N + i]; if (oc >= 0) ci[oc] = 0; } }
     const float T = (float)b.max_steps[e], Nf = (float)N;
+    const Scale sc{T, __frcp_rn(T), Nf, __frcp_rn(Nf)};
     const int elapsed = b.elapsed[e];
     if (tid < 4) s_misc[tid] = 0;                  // [0] entries, [1] unsorted entries written, [2] max time per cell
     __syncthreads();                               // mbarrier initialised, counters zeroed
@@ -607,13 +619,12 @@ k_observe(FlBatch b, ObsLayout lay, float *__restrict__ out_attr, float *__restr
             while (true) {
                 iters++;
                 if (!active) {
-                    unsigned it = (unsigned)OBS_Q_EMPTY;
-                    if (gl == 0) {
-                        if (claim < 0) claim = atomicAdd(Tt.q_head, 1);
-                        it = claim < qcap ? ld_vol_u16(&Tt.q[claim]) : (unsigned)OBS_Q_EMPTY;
-                        if (it != (unsigned)OBS_Q_EMPTY) { __threadfence_block(); claim = -1; }
+                    if (claim < 0) {                                                     // group-uniform: take the next queue index
+                        if (gl == 0) claim = atomicAdd(Tt.q_head, 1);
+                        claim = __shfl_sync(gmask, claim, gbase);
                     }
-                    it = __shfl_sync(gmask, it, gbase);
+                    const unsigned it = claim < qcap ? ld_vol_u16(&Tt.q[claim]) : (unsigned)OBS_Q_EMPTY;   // broadcast read
+                    if (it != (unsigned)OBS_Q_EMPTY) { __threadfence_block(); claim = -1; }
                     if (it != (unsigned)OBS_Q_EMPTY) {
                         active = true;
                         la = (int)(it >> 5); n = (int)(it & 31);
@@ -736,8 +747,8 @@ k_observe(FlBatch b, ObsLayout lay, float *__restrict__ out_attr, float *__restr
                         const int cidx = base + gl;
                         if (gl < 3) {
                             if (gl == 0) {                                               // scale_node (treeobs.cpp:111-152)
-                                v = make_float4(tb ? (float)tot / T : -1.0f, -1.0f, k_other != I_INF ? (float)(tot0 + k_other) / T : -1.0f,
-                                                k_conf != I_INF ? (float)(tot0 + k_conf) / T : -1.0f);
+                                v = make_float4(tb ? scale_i(tot, sc) : -1.0f, -1.0f, k_other != I_INF ? scale_i(tot0 + k_other, sc) : -1.0f,
+                                                k_conf != I_INF ? scale_i(tot0 + k_conf, sc) : -1.0f);
                             } else if (gl == 1) {
                                 int dnb, dmin;
                                 if (kind == 4) { dnb = tot; dmin = 0; }
@@ -746,9 +757,9 @@ k_observe(FlBatch b, ObsLayout lay, float *__restrict__ out_attr, float *__restr
                                     dmin = dv == FL_DIST_INF ? I_INF : (int)dv;
                                     dnb = kind == 3 ? I_INF : tot;
                                 }
-                                v = make_float4(k_unus != I_INF ? (float)(tot0 + k_unus) / T : -1.0f, scale_i(dnb, T), scale_i(dmin, T), (float)same / Nf);
+                                v = make_float4(k_unus != I_INF ? scale_i(tot0 + k_unus, sc) : -1.0f, scale_i(dnb, sc), scale_i(dmin, sc), scale_n(same, sc));
                             } else {
-                                v = make_float4((float)opp / Nf, (float)malf / Nf, __int_as_float(spd_bits), (float)rtdn / Nf);
+                                v = make_float4(scale_n(opp, sc), scale_n(malf, sc), __int_as_float(spd_bits), scale_n(rtdn, sc));
                             }
                             // child gl - 1 in order L, F, R (treeobs.cpp:583-608); its BFS index follows from the level's mask
                             const int a2 = gl - 1;
@@ -801,6 +812,7 @@ k_observe(FlBatch b, ObsLayout lay, float *__restrict__ out_attr, float *__restr
                 }
                 const bool finished = !active && ld_vol_i32(Tt.n_done) >= na;
                 if (__all_sync(0xFFFFFFFFu, finished)) break;
+                if (!__any_sync(0xFFFFFFFFu, active)) __nanosleep(100);                 // nothing to do in this warp: leave the issue slots to the others
             }
             if (dbg && tid == 0) { dbg[9] = iters; dbg[10] = s_misc[0]; }
         }
@@ -811,32 +823,38 @@ k_observe(FlBatch b, ObsLayout lay, float *__restrict__ out_attr, float *__restr
         for (int la = tid; la < na; la += NT) {
             const int count = Tt.t_count[la];
             int8_t *no = Tt.norder + la * 32;
-            for (int k = 0; k < 32; k++) no[k] = k < count ? 0 : -2;
+            uint32_t *no4 = reinterpret_cast<uint32_t *>(no);
+            for (int k = 0; k < 8; k++) {
+                const int lo = 4 * k;
+                no4[k] = (lo < count ? 0u : 0xFEu) | (lo + 1 < count ? 0u : 0xFE00u) | (lo + 2 < count ? 0u : 0xFE0000u) |
+                         (lo + 3 < count ? 0u : 0xFE000000u);
+            }
             for (int k = count - 1; k >= 1; k--) {
                 const int pa = (int)((Tt.n_meta[la * 31 + k] >> 8) & 31);
                 no[pa] = (int8_t)max((int)no[pa], (int)no[k] + 1);
             }
         }
         __syncthreads();
-        // ---- phase 5b: adjacency / node_order / edge_order, coalesced over the tile -------------------
-        {
-            const size_t base_a = (size_t)e * N + a0;
-            int32_t *adj = out_adj + base_a * ((FL_MAX_NODES - 1) * 3);
-            for (int k = tid; k < na * 90; k += NT) {
-                const int la = k / 90, j = (k % 90) / 3, comp = k % 3, node = j + 1;
+        // ---- phase 5b: adjacency / node_order / edge_order: one warp per agent, lanes over the row -------
+        for (int la = warp; la < na; la += NT / 32) {
+            const size_t ea = (size_t)e * N + a0 + la;
+            const int count = Tt.t_count[la];
+            const int8_t *no = Tt.norder + la * 32;
+            const uint16_t *meta = Tt.n_meta + la * 31;
+            int32_t *adj = out_adj + ea * ((FL_MAX_NODES - 1) * 3);
+            for (int j = lane; j < 90; j += 32) {
+                const int edge = j / 3, comp = j - edge * 3, node = edge + 1;
                 int v = -2;
-                if (node < Tt.t_count[la]) {
-                    const uint32_t meta = Tt.n_meta[la * 31 + node];
-                    v = comp == 0 ? (int)((meta >> 8) & 31) : comp == 1 ? node : (int)((meta >> 2) & 3) - 1;
+                if (node < count) {
+                    const unsigned m = meta[node];
+                    v = comp == 0 ? (int)((m >> 8) & 31) : comp == 1 ? node : (int)((m >> 2) & 3) - 1;
                 }
-                adj[k] = v;
+                adj[j] = v;
             }
-            int32_t *no = out_norder + base_a * FL_MAX_NODES;
-            for (int k = tid; k < na * FL_MAX_NODES; k += NT) no[k] = Tt.norder[(k / FL_MAX_NODES) * 32 + k % FL_MAX_NODES];
-            int32_t *eo = out_eorder + base_a * (FL_MAX_NODES - 1);
-            for (int k = tid; k < na * 30; k += NT) {
-                const int la = k / 30, node = k % 30 + 1;
-                eo[k] = node < Tt.t_count[la] ? (int)Tt.norder[la * 32 + ((Tt.n_meta[la * 31 + node] >> 8) & 31)] : -2;
+            if (lane < FL_MAX_NODES) out_norder[ea * FL_MAX_NODES + lane] = no[lane];
+            if (lane < FL_MAX_NODES - 1) {
+                const int node = lane + 1;
+                out_eorder[ea * (FL_MAX_NODES - 1) + lane] = node < count ? (int)no[(meta[node] >> 8) & 31] : -2;
             }
         }
         __syncthreads();
