@@ -72,7 +72,7 @@ int check_batch(const FlBatch *b) {
     if (!b || b->E <= 0 || b->N <= 0 || b->H <= 0 || b->W <= 0 || b->n_slots <= 0 || b->S <= 0) return FL_ERR_BAD_ARG;
     if (b->N >= FL_MAX_AGENTS) return FL_ERR_TOO_MANY_AGENTS;
     if (b->ent_cap < b->N * (int64_t)NPRED) return FL_ERR_BAD_ARG;
-    if (b->H >= 32768 || b->W >= 32768 || b->H * b->W > (1 << 20)) return FL_ERR_BAD_ARG;
+    if (b->H >= 1024 || b->W >= 1024) return FL_ERR_BAD_ARG;   // srec packs row and column in 10 bits each
     if (b->ridx_stride < b->H * b->W || b->ridx_stride % 8 || b->state_stride % 4 || b->wlist_stride % 8) return FL_ERR_BAD_ARG;
     // per-environment blocks are 16-byte aligned so that they can be moved with TMA bulk copies
     if (b->grid_stride < b->H * b->W || b->grid_stride % 8 || b->dist_stride < b->n_slots * b->H * b->W * 4 || b->dist_stride % 8)
@@ -106,7 +106,7 @@ ObsLayout make_obs_layout(const FlBatch *b, int nt) {
     const long long grid_b = b->grid_stride * 2, ci_b = (long long)HW * 4, ks_b = (long long)(K + 1) * 4;
     const long long dist_b = b->dist_stride * 2, ent_typ = (long long)N * 48 * 4;
     const long long ridx_b = b->ridx_stride * 2, st_b = b->state_stride * 4, wl_b = b->wlist_stride * 2;
-    const long long core = off + grid_b + ci_b + ks_b + ent_typ + 5 * 128, tables = ridx_b + 3 * st_b + wl_b + 5 * 128;
+    const long long core = off + grid_b + ci_b + ks_b + ent_typ + 5 * 128, tables = ridx_b + 5 * st_b + wl_b + 6 * 128;
     bool want_tables = true;
     if (const char *s = getenv("FL_OBS_TABLES")) want_tables = atoi(s) != 0;
     int ctas = 0;
@@ -123,8 +123,11 @@ ObsLayout make_obs_layout(const FlBatch *b, int nt) {
     L.ci = opt(ci_b);
     L.ks = K <= 0xFFFF ? opt(ks_b) : -1;
     const bool tables_fit = want_tables && (long long)off + ent_typ + tables + 128 <= budget;
-    L.ridx = L.srec = L.wstart = L.wlenk = L.wlist = -1;
-    if (tables_fit) { L.ridx = take(ridx_b); L.srec = take(st_b); L.wstart = take(st_b); L.wlenk = take(st_b); L.wlist = take(wl_b); }
+    L.ridx = L.srec = L.wstart = L.wlenk = L.wlist = L.wchild = -1;
+    if (tables_fit) {
+        L.ridx = take(ridx_b); L.srec = take(st_b); L.wstart = take(st_b); L.wlenk = take(st_b); L.wlist = take(wl_b);
+        L.wchild = take(2 * st_b);
+    }
     // entries: at least the typical size, the rest of the budget when the distance maps do not fit anyway
     long long ent_b = (long long)budget - off - 128;
     const bool dist_fits = ent_b - ent_typ >= dist_b + 128;
@@ -220,7 +223,7 @@ int fl_distance_map(const FlBatch *b, void *stream) {
 int fl_walk_tables(const FlBatch *b, int fill, void *stream) {
     if (int rc = check_batch(b)) return rc;
     if (!b->ridx || !b->walk_total) return FL_ERR_BAD_ARG;
-    if (fill && (!b->srec || !b->wstart || !b->wlenk || !b->wlist || b->state_stride <= 0 || b->wlist_stride <= 0)) return FL_ERR_BAD_ARG;
+    if (fill && (!b->srec || !b->wstart || !b->wlenk || !b->wlist || !b->wchild || b->state_stride <= 0 || b->wlist_stride <= 0)) return FL_ERR_BAD_ARG;
     cudaStream_t st = (cudaStream_t)stream;
     LaunchScope ls(K_WALKS, st);
     if (fill) k_walks<true, 256><<<(unsigned)b->E, 256, 0, st>>>(*b);
@@ -254,7 +257,7 @@ int fl_observe(const FlBatch *b, float *d_agent_attr, float *d_forest, int32_t *
     if (int rc = check_batch(b)) return rc;
     if (!d_agent_attr || !d_forest || !d_adjacency || !d_node_order || !d_edge_order || !d_valid_actions || !d_dist_target)
         return FL_ERR_BAD_ARG;
-    if (!b->srec || !b->wstart || !b->wlenk || !b->wlist || !b->ridx) return FL_ERR_BAD_ARG;   // fl_walk_tables first
+    if (!b->srec || !b->wstart || !b->wlenk || !b->wlist || !b->wchild || !b->ridx) return FL_ERR_BAD_ARG;   // fl_walk_tables first
     cudaStream_t st = (cudaStream_t)stream;
     const int nt = obs_threads(b);
     const ObsLayout lay = make_obs_layout(b, nt);
@@ -285,7 +288,7 @@ int fl_batch_slice(const FlBatch *b, int64_t e0, int64_t n, FlBatch *out) {
     FL_ADV(init_rc, N * 2) FL_ADV(tgt_rc, N * 2) FL_ADV(init_dir, N) FL_ADV(max_count, N) FL_ADV(slot, N) FL_ADV(speed, N)
     FL_ADV(earliest, N) FL_ADV(latest, N) FL_ADV(sched, b->S * N)
     FL_ADV(ridx, b->ridx_stride) FL_ADV(srec, b->state_stride) FL_ADV(wstart, b->state_stride) FL_ADV(wlenk, b->state_stride)
-    FL_ADV(wlist, b->wlist_stride) FL_ADV(walk_total, 4)
+    FL_ADV(wlist, b->wlist_stride) FL_ADV(wchild, b->state_stride * 4) FL_ADV(walk_total, 4)
     FL_ADV(rc, N * 2) FL_ADV(old_rc, N * 2) FL_ADV(dir, N) FL_ADV(old_dir, N) FL_ADV(state, N) FL_ADV(ctr, N) FL_ADV(mal, N)
     FL_ADV(saved, N) FL_ADV(sig_mal, N) FL_ADV(deadlocked, N) FL_ADV(done, N) FL_ADV(nmal, N) FL_ADV(arrival, N)
     FL_ADV(elapsed, 1) FL_ADV(sched_pos, 1) FL_ADV(done_all, 1) FL_ADV(status, 1) FL_ADV(cellinfo, HW) FL_ADV(occ_cell, N)

@@ -33,7 +33,7 @@ constexpr int I_INF = 0x7fffffff;
 
 struct ObsLayout {   // byte offsets into dynamic shared memory (host: make_obs_layout); < 0 = lives in global memory
     int grid, ci, dist, ks, ent, ent_cap, tmp_cap, part, ag, dl, tree, bar, total, tile;
-    int ridx, srec, wstart, wlenk, wlist;   // static walk tables (walks.cuh)
+    int ridx, srec, wstart, wlenk, wlist, wchild;   // static walk tables (walks.cuh)
 };
 
 // ---- mbarrier + 1-D TMA bulk copy (global -> shared), sm_90+ ------------------------------------
@@ -332,12 +332,13 @@ k_observe(FlBatch b, ObsLayout lay, float *__restrict__ out_attr, float *__restr
     const uint16_t *g_ridx = b.ridx + (size_t)e * b.ridx_stride;
     const uint32_t *g_srec = b.srec + (size_t)e * b.state_stride, *g_wstart = b.wstart + (size_t)e * b.state_stride,
                    *g_wlenk = b.wlenk + (size_t)e * b.state_stride;
-    const uint16_t *g_wlist = b.wlist + (size_t)e * b.wlist_stride;
+    const uint16_t *g_wlist = b.wlist + (size_t)e * b.wlist_stride, *g_wchild = b.wchild + (size_t)e * b.state_stride * 4;
     const uint16_t *ridx = lay.ridx >= 0 ? reinterpret_cast<const uint16_t *>(smraw + lay.ridx) : g_ridx;
     const uint32_t *srec = lay.srec >= 0 ? reinterpret_cast<const uint32_t *>(smraw + lay.srec) : g_srec;
     const uint32_t *wstart = lay.wstart >= 0 ? reinterpret_cast<const uint32_t *>(smraw + lay.wstart) : g_wstart;
     const uint32_t *wlenk = lay.wlenk >= 0 ? reinterpret_cast<const uint32_t *>(smraw + lay.wlenk) : g_wlenk;
     const uint16_t *wlist = lay.wlist >= 0 ? reinterpret_cast<const uint16_t *>(smraw + lay.wlist) : g_wlist;
+    const uint16_t *wchild = lay.wchild >= 0 ? reinterpret_cast<const uint16_t *>(smraw + lay.wchild) : g_wchild;
     uint32_t *s_part = reinterpret_cast<uint32_t *>(smraw + lay.part);
     uint64_t *bar = reinterpret_cast<uint64_t *>(smraw + lay.bar);
     int *s_misc = reinterpret_cast<int *>(smraw + lay.bar + 16);
@@ -381,7 +382,7 @@ k_observe(FlBatch b, ObsLayout lay, float *__restrict__ out_attr, float *__restr
     if (dbg && tid == 0) dbg[15] = clock64();
     // ---- phase 0: TMA bulk copies of the static world ---------------------------------------------
     const bool use_tma = lay.grid >= 0 || lay.dist >= 0 || lay.ridx >= 0 || lay.srec >= 0 || lay.wstart >= 0 || lay.wlenk >= 0 ||
-                         lay.wlist >= 0;
+                         lay.wlist >= 0 || lay.wchild >= 0;
     if (use_tma && tid == 0) {
         mbar_init(bar, 1);
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -390,13 +391,15 @@ k_observe(FlBatch b, ObsLayout lay, float *__restrict__ out_attr, float *__restr
         const uint32_t rb = lay.ridx >= 0 ? (uint32_t)(b.ridx_stride * 2) : 0u;
         const uint32_t sb = (uint32_t)(b.state_stride * 4);
         const uint32_t lb = lay.wlist >= 0 ? (uint32_t)(b.wlist_stride * 2) : 0u;
-        mbar_expect_tx(bar, gb + db + rb + lb + (lay.srec >= 0 ? sb : 0u) + (lay.wstart >= 0 ? sb : 0u) + (lay.wlenk >= 0 ? sb : 0u));
+        mbar_expect_tx(bar, gb + db + rb + lb + (lay.srec >= 0 ? sb : 0u) + (lay.wstart >= 0 ? sb : 0u) + (lay.wlenk >= 0 ? sb : 0u) +
+                                (lay.wchild >= 0 ? 2 * sb : 0u));
         if (gb) tma_load_1d(smraw + lay.grid, g_grid, gb, bar);
         if (rb) tma_load_1d(smraw + lay.ridx, g_ridx, rb, bar);
         if (lay.srec >= 0) tma_load_1d(smraw + lay.srec, g_srec, sb, bar);
         if (lay.wstart >= 0) tma_load_1d(smraw + lay.wstart, g_wstart, sb, bar);
         if (lay.wlenk >= 0) tma_load_1d(smraw + lay.wlenk, g_wlenk, sb, bar);
         if (lb) tma_load_1d(smraw + lay.wlist, g_wlist, lb, bar);
+        if (lay.wchild >= 0) tma_load_1d(smraw + lay.wchild, g_wchild, 2 * sb, bar);
         if (db) tma_load_1d(smraw + lay.dist, g_dist, db, bar);
     }
     // zero the key counters; forget the previous occupancy
@@ -610,7 +613,7 @@ k_observe(FlBatch b, ObsLayout lay, float *__restrict__ out_attr, float *__restr
             bool active = false;
             int claim = -1;
             int la = 0, n = 0, h = 0, tot0 = 0, k0 = 0, L = 0, skind = 0, tcell = -1;
-            uint32_t wbase = 0;
+            uint32_t wbase = 0, sid0 = 0;
             // group-uniform findings: first walk index (k) of each event, counts, flags
             int k_other = I_INF, k_conf = I_INF, k_unus = I_INF, same = 0, opp = 0, malf = 0, rtdn = 0, spd_bits = 0x3F800000;
             float tpc_f = 1.0f;
@@ -629,7 +632,7 @@ k_observe(FlBatch b, ObsLayout lay, float *__restrict__ out_attr, float *__restr
                         active = true;
                         la = (int)(it >> 5); n = (int)(it & 31);
                         h = a0 + la;
-                        const uint32_t sid0 = Tt.n_sid[la * 31 + n];
+                        sid0 = Tt.n_sid[la * 31 + n];
                         tot0 = (int)Tt.n_tot[la * 31 + n];
                         wbase = wstart[sid0];
                         const uint32_t lk = wlenk[sid0];
@@ -648,7 +651,8 @@ k_observe(FlBatch b, ObsLayout lay, float *__restrict__ out_attr, float *__restr
                     const bool valid = k <= L;
                     uint32_t rec = 0;
                     if (valid) rec = srec[wlist[wbase + k]];
-                    const int cell = (int)(rec & 0xFFFFF), d = (int)((rec >> 20) & 3), nb = (int)((rec >> 22) & 15);
+                    const int cr = (int)(rec & 1023), cc_ = (int)((rec >> 10) & 1023), cell = cr * W + cc_;
+                    const int d = (int)((rec >> 20) & 3), nb = (int)((rec >> 22) & 15);
                     // the walk stops on the observer's own target (treeobs.cpp:467-475, 483-489): cells behind it do not count
                     const unsigned tb = (__ballot_sync(gmask, valid && cell == tcell) >> gbase) & GM;
                     const int kt = tb ? __ffs(tb) - 1 : OBS_G;
@@ -670,8 +674,7 @@ k_observe(FlBatch b, ObsLayout lay, float *__restrict__ out_attr, float *__restr
                         }
                         const int pt = (int)__fmul_rn((float)tot, tpc_f);               // treeobs.cpp:378
                         if (pt < NPRED && tot < NPRED) {                                 // treeobs.cpp:379-465
-                            const int r = cell / W, c = cell - r * W;
-                            const int key = c * W + r;
+                            const int key = cc_ * W + cr;
                             const uint32_t s0 = key ? ks[key - 1] : 0u, s1 = ks[key];
                             const int pre = max(0, pt - 1), post = min(NPRED - 1, pt + 1);
                             unsigned acc = 0;
@@ -733,8 +736,8 @@ k_observe(FlBatch b, ObsLayout lay, float *__restrict__ out_attr, float *__restr
                         active = false;
                         const int kind = tb ? 4 : (skind == WK_BAD ? 3 : skind);         // 1 switch, 2 dead end, 3 cycle, 4 target
                         const uint32_t erec = srec[wlist[wbase + k_end]];                // the state the walk ended on
-                        const int ecell = (int)(erec & 0xFFFFF), ed = (int)((erec >> 20) & 3), enb = (int)((erec >> 22) & 15);
-                        const int er = ecell / W, ec = ecell - er * W, tot = tot0 + k_end;
+                        const int ecell = (int)(erec & 1023) * W + (int)((erec >> 10) & 1023), ed = (int)((erec >> 20) & 3);
+                        const int tot = tot0 + k_end;
                         const size_t ea = (size_t)e * N + h;
                         float *forest = out_forest + ea * (FL_MAX_NODES * FL_NODE_F);
                         const uint32_t lsle = Tt.t_lsle[la], lmask = Tt.t_mask[la];
@@ -764,15 +767,10 @@ k_observe(FlBatch b, ObsLayout lay, float *__restrict__ out_attr, float *__restr
                             // child gl - 1 in order L, F, R (treeobs.cpp:583-608); its BFS index follows from the level's mask
                             const int a2 = gl - 1;
                             if (cidx < FL_MAX_NODES) {
-                                const int bd = (ed + a2) & 3, rb = (bd + 2) & 3;
-                                int cd = bd;
-                                bool real = false;
-                                if (kind == 2 && tbit(enb, rb)) { cd = rb; real = true; }
-                                else if (kind == 1 && tbit(enb, bd)) { cd = bd; real = true; }
-                                const uint32_t csid = real ? child_state(ridx, H, W, er, ec, cd) : 0xFFFFFFFFu;
-                                real = csid != 0xFFFFFFFFu;
+                                const unsigned csid = kind <= 2 ? wchild[sid0 * 4 + gl] : 0xFFFFu;   // static: walks.cuh
+                                const bool real = csid != 0xFFFFu;
                                 Tt.n_sid[la * 31 + cidx] = (uint16_t)csid;
-                                Tt.n_meta[la * 31 + cidx] = (uint16_t)(cd | ((a2 + 1) << 2) | ((real ? 0 : 1) << 4) | (n << 8));
+                                Tt.n_meta[la * 31 + cidx] = (uint16_t)(((a2 + 1) << 2) | ((real ? 0 : 1) << 4) | (n << 8));
                                 Tt.n_tot[la * 31 + cidx] = (uint32_t)(tot + 1);
                                 child_real = real; child_null = !real;
                             }
@@ -823,12 +821,7 @@ k_observe(FlBatch b, ObsLayout lay, float *__restrict__ out_attr, float *__restr
         for (int la = tid; la < na; la += NT) {
             const int count = Tt.t_count[la];
             int8_t *no = Tt.norder + la * 32;
-            uint32_t *no4 = reinterpret_cast<uint32_t *>(no);
-            for (int k = 0; k < 8; k++) {
-                const int lo = 4 * k;
-                no4[k] = (lo < count ? 0u : 0xFEu) | (lo + 1 < count ? 0u : 0xFE00u) | (lo + 2 < count ? 0u : 0xFE0000u) |
-                         (lo + 3 < count ? 0u : 0xFE000000u);
-            }
+            for (int k = 0; k < 32; k++) no[k] = k < count ? 0 : -2;
             for (int k = count - 1; k >= 1; k--) {
                 const int pa = (int)((Tt.n_meta[la * 31 + k] >> 8) & 31);
                 no[pa] = (int8_t)max((int)no[pa], (int)no[k] + 1);

@@ -6,12 +6,14 @@
 // dynamic.  k_walks therefore lists, for every rail state, the states its walk visits, so that k_observe can
 // spread the cells of one walk over the lanes of a lane group instead of chasing them one by one:
 //   ridx[cell]     rail index of a cell (0xFFFF = no rail); state id sid = 4 * ridx[cell] + direction
-//   srec[sid]      cell | dir << 20 | transitions nibble of (cell, dir) << 22 | "unusable switch here" << 26
+//   srec[sid]      row | col << 10 | dir << 20 | transitions nibble of (cell, dir) << 22 | "unusable switch here" << 26
 //   wstart[sid]    offset of the walk from sid in wlist
 //   wlenk[sid]     steps of the walk (it visits steps + 1 states) | kind << 28:
 //                  1 = ends on a switch, 2 = dead end, 3 = the last state revisits an earlier one (rail cycle,
 //                  treeobs.cpp:476-481), 0 = ends on a cell without transitions (treeobs.cpp:527-535 throws)
 //   wlist[...]     the visited state ids, walk after walk
+//   wchild[4*sid+j] state id the j-th child (left, forward, right; treeobs.cpp:583-608) of the node ending this walk
+//                  starts from, 0xFFFF = null child (also for walks ending in a cycle or a bad cell)
 // FILL = false only measures (states, list length) so that the host can size wlist.
 #pragma once
 #include "common.cuh"
@@ -116,6 +118,7 @@ __global__ void __launch_bounds__(NT) k_walks(FlBatch b) {
     uint32_t *wstart = b.wstart + (size_t)e * b.state_stride;
     uint32_t *wlenk = b.wlenk + (size_t)e * b.state_stride;
     uint16_t *wlist = b.wlist + (size_t)e * b.wlist_stride;
+    uint16_t *wchild = b.wchild + (size_t)e * b.state_stride * 4;
     for (int k = lo; k < hi; k++) {
         const unsigned gc = g[k];
         if (!gc) { ridx[k] = 0xFFFF; continue; }
@@ -124,7 +127,7 @@ __global__ void __launch_bounds__(NT) k_walks(FlBatch b) {
         if (gc == 0x8421u) total = 2;
         for (int d = 0; d < 4; d++) {
             const int nb = nibble(gc, d);
-            srec[run * 4 + d] = (uint32_t)k | ((uint32_t)d << 20) | ((uint32_t)nb << 22) |
+            srec[run * 4 + d] = (uint32_t)(k / W) | ((uint32_t)(k % W) << 10) | ((uint32_t)d << 20) | ((uint32_t)nb << 22) |
                                 ((uint32_t)(total > 2 && __popc(nb) < 2) << 26);
         }
         run++;
@@ -136,9 +139,9 @@ __global__ void __launch_bounds__(NT) k_walks(FlBatch b) {
     uint32_t len = 0;
     for (int sid = slo; sid < shi; sid++) {
         const uint32_t rec = srec[sid];
-        const int cell = (int)(rec & 0xFFFFF), d = (int)((rec >> 20) & 3);
+        const int d = (int)((rec >> 20) & 3);
         int kind = WK_BAD;
-        const int steps = static_walk_len(g, H, W, cell / W, cell % W, d, S, kind);
+        const int steps = static_walk_len(g, H, W, (int)(rec & 1023), (int)((rec >> 10) & 1023), d, S, kind);
         wlenk[sid] = (uint32_t)steps | ((uint32_t)kind << 28);
         len += (uint32_t)steps + 1u;
     }
@@ -146,7 +149,7 @@ __global__ void __launch_bounds__(NT) k_walks(FlBatch b) {
     uint32_t off = block_exclusive_scan<NT>(len, s_part, total);
     for (int sid = slo; sid < shi; sid++) {
         const uint32_t rec = srec[sid];
-        int r = (int)(rec & 0xFFFFF) / W, c = (int)(rec & 0xFFFFF) % W, d = (int)((rec >> 20) & 3), kind;
+        int r = (int)(rec & 1023), c = (int)((rec >> 10) & 1023), d = (int)((rec >> 20) & 3), kind;
         const int steps = (int)(wlenk[sid] & 0x0FFFFFFFu);
         wstart[sid] = off;
         for (int k = 0; k <= steps; k++) {
@@ -154,8 +157,26 @@ __global__ void __launch_bounds__(NT) k_walks(FlBatch b) {
             off++;
             if (k < steps) static_succ(g, H, W, r, c, d, kind);
         }
+        // children of the node this walk ends in, from its last state (r, c, d)
+        const int wk = (int)(wlenk[sid] >> 28), enb = nibble(g[r * W + c], d);
+        for (int a2 = -1; a2 <= 1; a2++) {
+            const int bd = (d + a2) & 3, rb = (bd + 2) & 3;
+            int cd = -1;
+            if (wk == WK_DEADEND && tbit(enb, rb)) cd = rb;
+            else if (wk == WK_SWITCH && tbit(enb, bd)) cd = bd;
+            unsigned cs = 0xFFFF;
+            if (cd >= 0) {
+                const int rr = r + d_row(cd), cc = c + d_col(cd);
+                if (rr >= 0 && cc >= 0 && rr < H && cc < W && ridx[rr * W + cc] != 0xFFFF) cs = ridx[rr * W + cc] * 4u + (unsigned)cd;
+            }
+            wchild[sid * 4 + a2 + 1] = (uint16_t)cs;
+        }
+        wchild[sid * 4 + 3] = 0xFFFF;
     }
-    for (int sid = S + tid; sid < (int)b.state_stride; sid += NT) { srec[sid] = 0; wstart[sid] = 0; wlenk[sid] = 0; }
+    for (int sid = S + tid; sid < (int)b.state_stride; sid += NT) {
+        srec[sid] = 0; wstart[sid] = 0; wlenk[sid] = 0;
+        for (int j = 0; j < 4; j++) wchild[sid * 4 + j] = 0xFFFF;
+    }
     if (tid == 0) { tot[0] = S; tot[1] = (int)total; }
 }
 

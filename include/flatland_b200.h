@@ -87,10 +87,11 @@ typedef struct FlBatch {
     /* static branch-walk tables written by fl_walk_tables (csrc/walks.cuh): which states the tree observation's
      * walk from a (cell, direction) state visits (treeobs.cpp:258-610 _explore_branch, rail-only part) */
     uint16_t *ridx;            /* [E][ridx_stride] rail index per cell, 0xFFFF = no rail; state id = 4*ridx + dir */
-    uint32_t *srec;            /* [E][state_stride] cell | dir<<20 | transitions nibble<<22 | unusable switch<<26 */
+    uint32_t *srec;            /* [E][state_stride] row | col<<10 | dir<<20 | transitions nibble<<22 | unusable switch<<26 */
     uint32_t *wstart;          /* [E][state_stride] offset of the state's walk in wlist */
     uint32_t *wlenk;           /* [E][state_stride] steps of the walk | kind<<28 (1 switch, 2 dead end, 3 cycle, 0 bad cell) */
     uint16_t *wlist;           /* [E][wlist_stride] visited state ids, walk after walk */
+    uint16_t *wchild;          /* [E][state_stride][4] start states of the three children of the node a walk ends in, 0xFFFF = null */
     int32_t *walk_total;       /* [E][4] written by fl_walk_tables: states, wlist elements needed, 0, 0 */
 
     /* ---- agent state (agent_utils.py:58-105 and step_utils/*) ---- */
