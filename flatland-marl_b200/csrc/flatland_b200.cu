@@ -9,9 +9,10 @@
 //            copies of grid + distance maps): loader view + valid actions (loader.cpp:221-327), the
 //            serial sticky deadlock checker on a spare lane (deadlock_checker.cpp), greedy shortest-path
 //            predictions (predictions.cpp) as a CSR inverse index  cell id -> occupancy intervals, the
-//            31-node branch trees (treeobs.cpp:154-610) with one LANE per branch walk fed from a
-//            shared-memory work queue, evaluation orders (tool.h:468-524) and the 83-float agent
-//            attributes (feature_parser.cpp), written in the policy's input layout (observe.cuh).
+//            31-node branch trees (treeobs.cpp:154-610): structure per agent from the static walk tables, then
+//            one warp per agent over the flat list of the cells of all its walks, evaluation orders
+//            (tool.h:468-524) and the 83-float agent attributes (feature_parser.cpp), written in the policy's
+//            input layout (observe.cuh).
 //   k_bfs    one CTA per (environment, unique target): DistanceMap (distance_map.py:57-160) as a
 //            level-synchronous pull BFS with the whole map in shared memory.  Reset-time only.
 // Reference citations are relative to the reference repository root.  No fast-math: every float
@@ -73,7 +74,9 @@ int check_batch(const FlBatch *b) {
     if (b->N >= FL_MAX_AGENTS) return FL_ERR_TOO_MANY_AGENTS;
     if (b->ent_cap < b->N * (int64_t)NPRED) return FL_ERR_BAD_ARG;
     if (b->H >= 1024 || b->W >= 1024) return FL_ERR_BAD_ARG;   // srec packs row and column in 10 bits each
-    if (b->ridx_stride < b->H * b->W || b->ridx_stride % 8 || b->state_stride % 4 || b->wlist_stride % 8) return FL_ERR_BAD_ARG;
+    if (b->ridx_stride < b->H * b->W || b->ridx_stride % 8 || b->state_stride % 8 || b->wlist_stride % 8 || b->whits_stride % 4)
+        return FL_ERR_BAD_ARG;
+    if (b->state_stride > 0xFFFF) return FL_ERR_BAD_ARG;       // state ids are 16 bit
     // per-environment blocks are 16-byte aligned so that they can be moved with TMA bulk copies
     if (b->grid_stride < b->H * b->W || b->grid_stride % 8 || b->dist_stride < b->n_slots * b->H * b->W * 4 || b->dist_stride % 8)
         return FL_ERR_BAD_ARG;
@@ -85,13 +88,14 @@ constexpr int SMEM_MAX = 227 * 1024;
 int align_up(int v, int a) { return (v + a - 1) / a * a; }
 
 // Shared-memory plan of k_observe for one configuration.  Mandatory: barrier + scalars, scan partials, the
-// per-agent records, the deadlock scratch and the tree tile (which doubles as the unsorted-entry buffer).
-// Optional, in this order while they fit: rail grid, occupancy words, key counters, the sorted predicted-
-// occupancy entries ("core"), the static walk tables, and last the distance maps.  The budget per CTA is the
-// largest that still lets `ctas` CTAs share an SM: the largest ctas >= 3 for which core + walk tables fit, else
-// the largest ctas for which the core fits.  FL_OBS_CTAS / FL_OBS_TABLES / FL_OBS_NT override (tuning only).
-ObsLayout make_obs_layout(const FlBatch *b, int nt) {
-    const int N = (int)b->N, HW = (int)(b->H * b->W), K = (int)(b->W * b->W + b->H);
+// per-agent records, the deadlock scratch, the node table of a tile of agents (which doubles as the unsorted-entry
+// buffer), the occupancy word and the bucket offsets per rail cell.  Optional, in this order while they fit: rail
+// grid, rail index, the sorted predicted-occupancy entries ("core"), the static walk tables, and last the distance
+// maps.  The budget per CTA is the largest that still lets `ctas` CTAs share an SM: the largest ctas >= min_ctas
+// for which core + walk tables fit, else the largest ctas for which the core fits.  FL_OBS_CTAS / FL_OBS_TABLES /
+// FL_OBS_NT override (tuning only).
+ObsLayout make_obs_layout(const FlBatch *b, int nt, int *ctas_out = nullptr) {
+    const int N = (int)b->N, Rmax = (int)(b->state_stride / 4);
     ObsLayout L;
     L.tile = N < OBS_MAX_TILE ? N : OBS_MAX_TILE;
     int off = 0;
@@ -100,50 +104,51 @@ ObsLayout make_obs_layout(const FlBatch *b, int nt) {
     L.part = take(nt * 4);
     L.ag = take(14 * N * 4);
     L.dl = take(18 * N);
-    const int tree_b = (2 * L.tile * 31 + (L.tile & 1) + 5 * L.tile + 4 + L.tile * 8) * 4 + L.tile * 30 * 2;
-    L.tree = take(tree_b);
-    L.tmp_cap = tree_b / 6;
-    const long long grid_b = b->grid_stride * 2, ci_b = (long long)HW * 4, ks_b = (long long)(K + 1) * 4;
-    const long long dist_b = b->dist_stride * 2, ent_typ = (long long)N * 48 * 4;
-    const long long ridx_b = b->ridx_stride * 2, st_b = b->state_stride * 4, wl_b = b->wlist_stride * 2;
-    const long long core = off + grid_b + ci_b + ks_b + ent_typ + 5 * 128, tables = ridx_b + 5 * st_b + wl_b + 6 * 128;
+    const long long ent_typ = (long long)N * 56 * 4;
+    long long nodes_b = (long long)L.tile * OBS_NODE_BYTES;
+    if (nodes_b < ent_typ / 4 * 6) nodes_b = ent_typ / 4 * 6;        // also holds the unsorted entries (6 bytes each)
+    L.nodes = take(nodes_b);
+    L.nodes_bytes = (int)nodes_b;
+    L.tmp_cap = (int)(nodes_b / 6);
+    L.ci = take((long long)Rmax * 4);
+    L.ks = take((long long)(Rmax + 2) * 4);
+    L.kcls = b->H > b->W ? take(b->state_stride * 2) : -1;      // key classes of the reference's c*W + r (walks.cuh)
+    const long long grid_b = b->grid_stride * 2, ridx_b = b->ridx_stride * 2, dist_b = b->dist_stride * 2;
+    const long long st_b = b->state_stride * 4, wl_b = b->wlist_stride * 2, wh_b = b->whits_stride * 4;
+    const long long core = off + grid_b + ridx_b + ent_typ + 4 * 128, tables = 6 * st_b + wl_b + wh_b + 6 * 128;
     bool want_tables = true;
     if (const char *s = getenv("FL_OBS_TABLES")) want_tables = atoi(s) != 0;
+    const int max_ctas = nt == 256 ? 4 : nt == 128 ? 8 : 12, min_ctas = nt == 256 ? 2 : 3;
     int ctas = 0;
     if (const char *s = getenv("FL_OBS_CTAS")) ctas = atoi(s) > 0 ? atoi(s) : 1;
     if (!ctas && want_tables)
-        for (int c = 6; c >= 3; c--)
+        for (int c = max_ctas; c >= min_ctas; c--)
             if (core + tables <= SMEM_MAX / c - 1024) { ctas = c; break; }
     if (!ctas)
-        for (int c = 6; c >= 1; c--)
+        for (int c = max_ctas; c >= 1; c--)
             if (core <= SMEM_MAX / c - 1024 || c == 1) { ctas = c; break; }
+    if (ctas_out) *ctas_out = ctas;
     const int budget = SMEM_MAX / ctas - 1024;
     auto opt = [&](long long bytes) { if ((long long)off + bytes + 128 > budget) return -1; return take(bytes); };
     L.grid = opt(grid_b);
-    L.ci = opt(ci_b);
-    L.ks = K <= 0xFFFF ? opt(ks_b) : -1;
+    L.ridx = opt(ridx_b);
     const bool tables_fit = want_tables && (long long)off + ent_typ + tables + 128 <= budget;
-    L.ridx = L.srec = L.wstart = L.wlenk = L.wlist = L.wchild = -1;
+    L.srec = L.wrec = L.whoff = L.whits = L.wlist = -1;
     if (tables_fit) {
-        L.ridx = take(ridx_b); L.srec = take(st_b); L.wstart = take(st_b); L.wlenk = take(st_b); L.wlist = take(wl_b);
-        L.wchild = take(2 * st_b);
+        L.wrec = take(4 * st_b); L.srec = take(st_b); L.whoff = take(st_b); L.whits = take(wh_b); L.wlist = take(wl_b);
     }
     // entries: at least the typical size, the rest of the budget when the distance maps do not fit anyway
     long long ent_b = (long long)budget - off - 128;
     const bool dist_fits = ent_b - ent_typ >= dist_b + 128;
     if (dist_fits) ent_b -= dist_b + 128;
     if (ent_b > (long long)N * NPRED * 4) ent_b = (long long)N * NPRED * 4;
+    if (ent_b > 2 * ent_typ && !dist_fits) ent_b = 2 * ent_typ;      // more than ever needed: leave the rest to the L1 cache
     if (ent_b < 0) ent_b = 0;
     L.ent = take(ent_b);
     L.ent_cap = (int)(ent_b / 4);
     L.dist = dist_fits ? opt(dist_b) : -1;
     L.total = off;
     return L;
-}
-
-int obs_group(const FlBatch *) {
-    if (const char *s = getenv("FL_OBS_G")) { const int v = atoi(s); if (v == 4 || v == 8 || v == 16 || v == 32) return v; }
-    return 8;
 }
 
 int obs_threads(const FlBatch *b) {
@@ -223,11 +228,20 @@ int fl_distance_map(const FlBatch *b, void *stream) {
 int fl_walk_tables(const FlBatch *b, int fill, void *stream) {
     if (int rc = check_batch(b)) return rc;
     if (!b->ridx || !b->walk_total) return FL_ERR_BAD_ARG;
-    if (fill && (!b->srec || !b->wstart || !b->wlenk || !b->wlist || !b->wchild || b->state_stride <= 0 || b->wlist_stride <= 0)) return FL_ERR_BAD_ARG;
+    if (fill && (!b->srec || !b->wrec || !b->whoff || !b->wlist || !b->whits || !b->kcls || b->state_stride <= 0 || b->wlist_stride <= 0 ||
+                 b->whits_stride <= 0))
+        return FL_ERR_BAD_ARG;
     cudaStream_t st = (cudaStream_t)stream;
+    const size_t smem = (size_t)((b->H * b->W + 31) / 32) * 4;   // one bit per cell: a slot's target stands here
+    if (smem > 200 * 1024) return FL_ERR_SMEM;
+    if (smem > 40 * 1024) {
+        cudaError_t err = cudaFuncSetAttribute(k_walks<true, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (err == cudaSuccess) err = cudaFuncSetAttribute(k_walks<false, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (err != cudaSuccess) return (int)err;
+    }
     LaunchScope ls(K_WALKS, st);
-    if (fill) k_walks<true, 256><<<(unsigned)b->E, 256, 0, st>>>(*b);
-    else k_walks<false, 256><<<(unsigned)b->E, 256, 0, st>>>(*b);
+    if (fill) k_walks<true, 256><<<(unsigned)b->E, 256, smem, st>>>(*b);
+    else k_walks<false, 256><<<(unsigned)b->E, 256, smem, st>>>(*b);
     return finish(cudaGetLastError());
 }
 
@@ -257,17 +271,18 @@ int fl_observe(const FlBatch *b, float *d_agent_attr, float *d_forest, int32_t *
     if (int rc = check_batch(b)) return rc;
     if (!d_agent_attr || !d_forest || !d_adjacency || !d_node_order || !d_edge_order || !d_valid_actions || !d_dist_target)
         return FL_ERR_BAD_ARG;
-    if (!b->srec || !b->wstart || !b->wlenk || !b->wlist || !b->wchild || !b->ridx) return FL_ERR_BAD_ARG;   // fl_walk_tables first
+    if (!b->srec || !b->wrec || !b->whoff || !b->wlist || !b->whits || !b->kcls || !b->ridx || !b->walk_total) return FL_ERR_BAD_ARG;   // fl_walk_tables first
     cudaStream_t st = (cudaStream_t)stream;
     const int nt = obs_threads(b);
-    const ObsLayout lay = make_obs_layout(b, nt);
+    int ctas = 1;
+    const ObsLayout lay = make_obs_layout(b, nt, &ctas);
     if (lay.total > SMEM_MAX) return FL_ERR_SMEM;
-    const int g = obs_group(b);
     using Kern = void (*)(FlBatch, ObsLayout, float *, float *, int32_t *, int32_t *, int32_t *, uint8_t *, float *);
-    static const Kern table[3][4] = {{k_observe<64, 4>, k_observe<64, 8>, k_observe<64, 16>, k_observe<64, 32>},
-                                     {k_observe<128, 4>, k_observe<128, 8>, k_observe<128, 16>, k_observe<128, 32>},
-                                     {k_observe<256, 4>, k_observe<256, 8>, k_observe<256, 16>, k_observe<256, 32>}};
-    Kern kern = table[nt == 64 ? 0 : nt == 128 ? 1 : 2][g == 4 ? 0 : g == 8 ? 1 : g == 16 ? 2 : 3];
+    // the register budget follows the number of CTAs the shared-memory plan lets share an SM
+    Kern kern;
+    if (nt == 64) kern = ctas > 8 ? k_observe<64, 12> : k_observe<64, 8>;
+    else if (nt == 128) kern = ctas > 6 ? k_observe<128, 8> : ctas > 4 ? k_observe<128, 6> : k_observe<128, 4>;
+    else kern = ctas > 3 ? k_observe<256, 4> : ctas > 2 ? k_observe<256, 3> : k_observe<256, 2>;
     if (lay.total > 48 * 1024) {
         cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, lay.total);
         if (err != cudaSuccess) return (int)err;
@@ -282,17 +297,17 @@ int fl_batch_slice(const FlBatch *b, int64_t e0, int64_t n, FlBatch *out) {
     if (!b || !out || e0 < 0 || n <= 0 || e0 + n > b->E) return FL_ERR_BAD_ARG;
     *out = *b;
     out->E = n;
-    const int64_t N = b->N, HW = b->H * b->W, K1 = b->W * b->W + b->H + 1;
+    const int64_t N = b->N;
 #define FL_ADV(field, per_env) out->field = b->field ? b->field + (size_t)e0 * (size_t)(per_env) : b->field;
     FL_ADV(grid, b->grid_stride) FL_ADV(slot_rc, b->n_slots * 2) FL_ADV(dist, b->dist_stride) FL_ADV(max_steps, 1)
     FL_ADV(init_rc, N * 2) FL_ADV(tgt_rc, N * 2) FL_ADV(init_dir, N) FL_ADV(max_count, N) FL_ADV(slot, N) FL_ADV(speed, N)
     FL_ADV(earliest, N) FL_ADV(latest, N) FL_ADV(sched, b->S * N)
-    FL_ADV(ridx, b->ridx_stride) FL_ADV(srec, b->state_stride) FL_ADV(wstart, b->state_stride) FL_ADV(wlenk, b->state_stride)
-    FL_ADV(wlist, b->wlist_stride) FL_ADV(wchild, b->state_stride * 4) FL_ADV(walk_total, 4)
+    FL_ADV(ridx, b->ridx_stride) FL_ADV(srec, b->state_stride) FL_ADV(wrec, b->state_stride * 4) FL_ADV(whoff, b->state_stride)
+    FL_ADV(wlist, b->wlist_stride) FL_ADV(whits, b->whits_stride) FL_ADV(kcls, b->state_stride) FL_ADV(walk_total, 4)
     FL_ADV(rc, N * 2) FL_ADV(old_rc, N * 2) FL_ADV(dir, N) FL_ADV(old_dir, N) FL_ADV(state, N) FL_ADV(ctr, N) FL_ADV(mal, N)
     FL_ADV(saved, N) FL_ADV(sig_mal, N) FL_ADV(deadlocked, N) FL_ADV(done, N) FL_ADV(nmal, N) FL_ADV(arrival, N)
-    FL_ADV(elapsed, 1) FL_ADV(sched_pos, 1) FL_ADV(done_all, 1) FL_ADV(status, 1) FL_ADV(cellinfo, HW) FL_ADV(occ_cell, N)
-    FL_ADV(stats, 4) FL_ADV(key_start, K1) FL_ADV(entries, b->ent_cap) FL_ADV(debug_clocks, 16)
+    FL_ADV(elapsed, 1) FL_ADV(sched_pos, 1) FL_ADV(done_all, 1) FL_ADV(status, 1)
+    FL_ADV(stats, 4) FL_ADV(entries, b->ent_cap) FL_ADV(debug_clocks, 16)
 #undef FL_ADV
     return FL_OK;
 }
@@ -319,9 +334,10 @@ int fl_observe_plan(const FlBatch *b, int32_t *out, int n_out) {
     if (int rc = check_batch(b)) return rc;
     if (!out || n_out < 20) return FL_ERR_BAD_ARG;
     const int nt = obs_threads(b);
-    const ObsLayout L = make_obs_layout(b, nt);
+    int ctas = 1;
+    const ObsLayout L = make_obs_layout(b, nt, &ctas);
     const int v[20] = {nt, L.total, L.tile, L.ent_cap, L.tmp_cap, L.grid, L.ci, L.ks, L.ent, L.dist,
-                       L.ridx, L.srec, L.wstart, L.wlenk, L.wlist, L.ag, L.dl, L.tree, SMEM_MAX / (L.total + 1024), obs_group(b)};
+                       L.ridx, L.srec, L.wrec, L.whoff, L.wlist, L.ag, L.dl, L.nodes, SMEM_MAX / (L.total + 1024), L.whits};
     for (int k = 0; k < 20; k++) out[k] = v[k];
     return FL_OK;
 }

@@ -1,24 +1,30 @@
 // observe.cuh — k_observe: TreeObsForRailEnv::get_many + get_properties (treeobs.cpp:30-108, 612-640) for
-// one environment per CTA, the whole per-environment working set staged in shared memory.
+// one environment per CTA, the per-environment working set staged in shared memory.
 //
 // Phases of one CTA (= one environment):
-//   0  stage the rail grid and the distance maps into shared memory with two 1-D TMA bulk copies
-//      (cp.async.bulk + mbarrier) while phase 1 reads the agents.
+//   0  stage the rail grid, the rail index and (as far as they fit) the static walk tables and distance maps into
+//      shared memory with 1-D TMA bulk copies (cp.async.bulk + mbarrier) while phase 1 reads the agents.
 //   1  loader view per agent (loader.cpp:8-179, 221-327): virtual position, valid actions, distance to
-//      target, the per-cell occupancy word (treeobs.cpp:67-92) built with shared-memory atomics.
+//      target, the occupancy word per RAIL CELL (treeobs.cpp:67-92) built with shared-memory atomics.
 //   2  the serial, sticky DeadlockChecker (deadlock_checker.cpp:11-110) on lane 0 of the last warp, running
 //      concurrently with phase 3 (its result is only needed by the attribute vector).
 //   3  greedy shortest-path predictions (predictions.cpp:13-235) as occupancy intervals, counting-sorted by
-//      the reference's cell id c*W+r into a CSR inverse index  cell id -> intervals, every bucket ordered by
-//      start time so that the tree walk only scans the entries of a three-step time window.
-//   4  the 31-node branch trees (treeobs.cpp:154-610).  One LANE per branch walk: walks are work items in a
-//      shared-memory queue; a lane that finishes a walk creates its node's three children in place (their
-//      BFS indices follow from the bit mask of real nodes of the level) and the lane that finishes the
-//      last walk of an agent's level releases the next level into the queue.  No CTA barrier inside the
-//      phase; lanes of a warp advance different walks one cell per iteration.  Node features go straight
-//      to the policy's forest tensor as three 16-byte stores per node.
-//   5  evaluation orders (tool.h:468-524), adjacency and the 83-float attribute vector
-//      (feature_parser.cpp:3-98), written with coalesced stores.
+//      rail cell into a CSR inverse index  rail cell -> intervals, every bucket ordered by start time so that
+//      the tree walk only scans the entries of a three-step time window.  (The reference keys positions by
+//      c * W + r, which makes distinct cells of a grid with H > W share predictions; kcls of walks.cuh maps a
+//      rail cell to its key class so that these false conflicts are reproduced.)
+//   4  the 31-node branch trees (treeobs.cpp:154-610), in two steps:
+//      A  STRUCTURE, one lane per agent: which walk every node stands for, where it ends and what its children
+//         are follows from the static walk tables alone (walks.cuh: steps, kind, children, the steps at which the
+//         walk crosses the target of a slot), so the lane runs the reference's FIFO over <= 31 nodes without
+//         touching a rail cell, and finishes with the evaluation orders (tool.h:468-524).
+//      B  FEATURES, one warp per agent: the cells of all walks of the agent form one flat list (about 130 cells);
+//         the warp takes it 32 cells at a time, one cell per lane — no idle lanes, no queue, no atomics.  The
+//         owner node of a cell follows from a ballot + a bit mask of segment starts; what the lanes find
+//         (trains, predicted conflicts) returns to the lane that owns the node as ballots masked by the node's
+//         segment.  Lane n then writes node n of the forest (three 16-byte stores) and the warp writes the
+//         agent's adjacency / order rows.
+//   5  the 83-float attribute vector (feature_parser.cpp:3-98), written with coalesced stores.
 // Arrays that do not fit in shared memory for a configuration (large grids) stay in global memory behind
 // the same generic pointers (ObsLayout offsets < 0).
 #pragma once
@@ -28,12 +34,11 @@
 namespace {
 
 constexpr int OBS_MAX_TILE = 64;        // agents whose trees are built together (bounds the node table)
-constexpr int OBS_Q_EMPTY = 0xFFFF;
 constexpr int I_INF = 0x7fffffff;
 
 struct ObsLayout {   // byte offsets into dynamic shared memory (host: make_obs_layout); < 0 = lives in global memory
-    int grid, ci, dist, ks, ent, ent_cap, tmp_cap, part, ag, dl, tree, bar, total, tile;
-    int ridx, srec, wstart, wlenk, wlist, wchild;   // static walk tables (walks.cuh)
+    int bar, part, ag, dl, nodes, nodes_bytes, ci, ks, grid, ridx, ent, ent_cap, tmp_cap, dist, total, tile;
+    int srec, wrec, whoff, whits, wlist, kcls;   // static walk tables (walks.cuh)
 };
 
 // ---- mbarrier + 1-D TMA bulk copy (global -> shared), sm_90+ ------------------------------------
@@ -91,7 +96,7 @@ DEVI int greedy_moves(unsigned cell, int d, int out_d[3]) {
 // transpose in treeobs.cpp:50-65).  Path element k >= 1 is occupied for prediction rows
 // [1+(k-1)*tpc, k*tpc], the last element until row 500, element 0 for row 0 only (or all rows when
 // the path has a single element).  The reference stops advancing once the cell equals the target.
-// Emit(key, t0, t1, dir_here, dir_prev, dir_next) is called once per occupied element.
+// Emit(cell, t0, t1, dir_here, dir_prev, dir_next) is called once per occupied element (cell = r * W + c).
 template <class Emit>
 DEVI void walk_prediction(const uint16_t *g, const uint16_t *dm, int W, int vr, int vc, int dir, int tr, int tc,
                           int tpc, Emit emit) {
@@ -105,7 +110,7 @@ DEVI void walk_prediction(const uint16_t *g, const uint16_t *dm, int W, int vr, 
             const int kk = k - 1;
             const int t0 = kk == 0 ? 0 : 1 + (kk - 1) * tpc;
             const int t1 = kk == 0 ? 0 : kk * tpc;
-            if (t0 < NPRED) emit(pc * W + pr, t0, min(t1, NPRED - 1), pd, ppd, d);
+            if (t0 < NPRED) emit(pr * W + pc, t0, min(t1, NPRED - 1), pd, ppd, d);
             else return;
         }
         bool last = (r == tr && c == tc) || k >= FL_PRED_DEPTH;   // at target, or 500 greedy steps done
@@ -123,7 +128,7 @@ DEVI void walk_prediction(const uint16_t *g, const uint16_t *dm, int W, int vr, 
         }
         if (last) {
             const int t0 = k == 0 ? 0 : 1 + (k - 1) * tpc;
-            if (t0 < NPRED) emit(c * W + r, t0, NPRED - 1, d, pd, d);
+            if (t0 < NPRED) emit(r * W + c, t0, NPRED - 1, d, pd, d);
             return;
         }
         ppd = pd; pr = r; pc = c; pd = d; have_prev = true;
@@ -172,7 +177,7 @@ struct DeadlockScratch {
     const int *cellid;
 };
 
-DEVI void update_deadlocks(const DeadlockScratch &x, const uint32_t *ci, int N, int H, int W) {
+DEVI void update_deadlocks(const DeadlockScratch &x, const uint32_t *ci, const uint16_t *ridx, int N, int H, int W) {
     for (int a0 = 0; a0 < N; a0++) {
         if (x.cellid[a0] < 0 || x.dl[a0] || x.checked[a0]) continue;
         int sp = 0;
@@ -189,7 +194,10 @@ DEVI void update_deadlocks(const DeadlockScratch &x, const uint32_t *ci, int N, 
                     if (!tbit(x.ct[h], dd)) { x.stk_d[f]++; continue; }
                     const int rr = hr + d_row(dd), cc = hc + d_col(dd);
                     opp = -1;
-                    if (rr >= 0 && cc >= 0 && rr < H && cc < W) opp = (int)(ci[rr * W + cc] >> 21) - 1;
+                    if (rr >= 0 && cc >= 0 && rr < H && cc < W) {
+                        const unsigned ri = ridx[rr * W + cc];
+                        if (ri != 0xFFFFu) opp = (int)(ci[ri] >> 21) - 1;
+                    }
                     if (opp < 0) { x.checked[h] = 2; popped = true; break; }           // road is free
                     if (x.dl[opp]) { x.stk_d[f]++; continue; }                          // road is blocked
                     if (x.checked[opp] == 0) {                                          // recurse
@@ -298,47 +306,58 @@ struct ObsAgents {
     float *f_earliest, *f_latest, *f_arrival, *f_dist, *f_idist;
 };
 
-struct ObsTile {
-    uint16_t *n_sid, *n_meta;               // [OBS_TILE][31] node table: start state id (0xFFFF = null), dir|ad|null|parent
-    uint32_t *n_tot;                        //                distance walked before the node's branch starts
-    uint32_t *t_mask, *t_next;              // [OBS_TILE] real-node bit mask of the level being walked / being created
-    int *t_pend;                            // [OBS_TILE] walks of the current level still running
-    uint32_t *t_lsle;                       // [OBS_TILE] level start | level end << 8
-    int *t_count;                           // [OBS_TILE] nodes created (rows >= count are padding)
-    int8_t *norder;                         // [OBS_TILE][32]
-    uint16_t *q;                            // [OBS_TILE * 30] work queue: local agent << 5 | node
-    int *q_head, *q_tail, *n_done;
+// node table of a tile of agents, written by phase 4A (one lane per agent), read by phase 4B (one warp per agent)
+struct ObsNodes {
+    uint32_t *n_a;      // [tile][31] tot0 (distance walked before the node's branch starts) | kind << 20 | parent << 23 |
+                        //            (action direction + 1) << 28 | null << 30; kind 1 switch, 2 dead end, 3 cycle / bad cell, 4 target
+    uint32_t *n_sk;     // [tile][31] start state id of the node's walk (0xFFFF = null) | step the walk ends on << 16
+    int8_t *norder;     // [tile][32] node_order (tool.h:468-524), -2 = padding row
+    int *count;         // [tile] nodes created (rows >= count are padding)
 };
+constexpr int OBS_NODE_BYTES = 31 * 8 + 32 + 4;   // per agent of a tile
 
-// NT threads per CTA; OBS_G lanes share one branch walk
-template <int NT, int OBS_G>
-__global__ void __launch_bounds__(NT, NT == 256 ? 4 : (NT == 128 ? 6 : 8))
+DEVI unsigned warp_excl_scan(unsigned v, int lane, unsigned &total) {
+    unsigned x = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const unsigned y = __shfl_up_sync(0xFFFFFFFFu, x, o);
+        if (lane >= o) x += y;
+    }
+    total = __shfl_sync(0xFFFFFFFFu, x, 31);
+    return x - v;
+}
+
+// NT threads per CTA, RES CTAs per SM the register budget is cut for
+template <int NT, int RES>
+__global__ void __launch_bounds__(NT, RES)
 k_observe(FlBatch b, ObsLayout lay, float *__restrict__ out_attr, float *__restrict__ out_forest,
           int32_t *__restrict__ out_adj, int32_t *__restrict__ out_norder, int32_t *__restrict__ out_eorder,
           uint8_t *__restrict__ out_valid, float *__restrict__ out_dist_target) {
     const int e = blockIdx.x, N = (int)b.N, H = (int)b.H, W = (int)b.W, HW = H * W;
-    const int K = W * W + H;                       // key space of the reference's cell id c*W + r
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     extern __shared__ __align__(128) unsigned char obs_smem[];
     unsigned char *const smraw = obs_smem;
+    const int R = b.walk_total[(size_t)e * 4] >> 2;         // rail cells of this environment
 
     // ---- pointers: shared-memory copy when the layout has room, global memory otherwise ---------
     const uint16_t *g_grid = b.grid + (size_t)e * b.grid_stride;
     const uint16_t *g_dist = b.dist + (size_t)e * b.dist_stride;
+    const uint16_t *g_ridx = b.ridx + (size_t)e * b.ridx_stride;
+    const uint32_t *g_srec = b.srec + (size_t)e * b.state_stride, *g_whoff = b.whoff + (size_t)e * b.state_stride;
+    const uint4 *g_wrec = reinterpret_cast<const uint4 *>(b.wrec) + (size_t)e * b.state_stride;
+    const uint16_t *g_wlist = b.wlist + (size_t)e * b.wlist_stride;
+    const uint32_t *g_whits = b.whits + (size_t)e * b.whits_stride;
     const uint16_t *grid = lay.grid >= 0 ? reinterpret_cast<const uint16_t *>(smraw + lay.grid) : g_grid;
     const uint16_t *dist = lay.dist >= 0 ? reinterpret_cast<const uint16_t *>(smraw + lay.dist) : g_dist;
-    uint32_t *ci = lay.ci >= 0 ? reinterpret_cast<uint32_t *>(smraw + lay.ci) : b.cellinfo + (size_t)e * HW;
-    uint32_t *ks = lay.ks >= 0 ? reinterpret_cast<uint32_t *>(smraw + lay.ks) : b.key_start + (size_t)e * (K + 1);
-    const uint16_t *g_ridx = b.ridx + (size_t)e * b.ridx_stride;
-    const uint32_t *g_srec = b.srec + (size_t)e * b.state_stride, *g_wstart = b.wstart + (size_t)e * b.state_stride,
-                   *g_wlenk = b.wlenk + (size_t)e * b.state_stride;
-    const uint16_t *g_wlist = b.wlist + (size_t)e * b.wlist_stride, *g_wchild = b.wchild + (size_t)e * b.state_stride * 4;
     const uint16_t *ridx = lay.ridx >= 0 ? reinterpret_cast<const uint16_t *>(smraw + lay.ridx) : g_ridx;
     const uint32_t *srec = lay.srec >= 0 ? reinterpret_cast<const uint32_t *>(smraw + lay.srec) : g_srec;
-    const uint32_t *wstart = lay.wstart >= 0 ? reinterpret_cast<const uint32_t *>(smraw + lay.wstart) : g_wstart;
-    const uint32_t *wlenk = lay.wlenk >= 0 ? reinterpret_cast<const uint32_t *>(smraw + lay.wlenk) : g_wlenk;
+    const uint4 *wrec = lay.wrec >= 0 ? reinterpret_cast<const uint4 *>(smraw + lay.wrec) : g_wrec;
+    const uint32_t *whoff = lay.whoff >= 0 ? reinterpret_cast<const uint32_t *>(smraw + lay.whoff) : g_whoff;
+    const uint32_t *whits = lay.whits >= 0 ? reinterpret_cast<const uint32_t *>(smraw + lay.whits) : g_whits;
     const uint16_t *wlist = lay.wlist >= 0 ? reinterpret_cast<const uint16_t *>(smraw + lay.wlist) : g_wlist;
-    const uint16_t *wchild = lay.wchild >= 0 ? reinterpret_cast<const uint16_t *>(smraw + lay.wchild) : g_wchild;
+    const uint16_t *kcls = lay.kcls >= 0 ? reinterpret_cast<const uint16_t *>(smraw + lay.kcls) : nullptr;   // only when H > W
+    uint32_t *ci = reinterpret_cast<uint32_t *>(smraw + lay.ci);             // [R] occupancy word per rail cell
+    uint32_t *ks = reinterpret_cast<uint32_t *>(smraw + lay.ks) + 1;         // ks[-1..R]: bucket r = [ks[r-1], ks[r])
     uint32_t *s_part = reinterpret_cast<uint32_t *>(smraw + lay.part);
     uint64_t *bar = reinterpret_cast<uint64_t *>(smraw + lay.bar);
     int *s_misc = reinterpret_cast<int *>(smraw + lay.bar + 16);
@@ -363,17 +382,12 @@ k_observe(FlBatch b, ObsLayout lay, float *__restrict__ out_attr, float *__restr
         D.cellid = A.cellid;
     }
     const int OBS_TILE = lay.tile;
-    ObsTile Tt;
+    ObsNodes T;
     {
-        uint32_t *p = reinterpret_cast<uint32_t *>(smraw + lay.tree);
-        Tt.n_tot = p; p += OBS_TILE * 31;
-        Tt.n_sid = reinterpret_cast<uint16_t *>(p); Tt.n_meta = Tt.n_sid + OBS_TILE * 31 + (OBS_TILE & 1); p += OBS_TILE * 31 + (OBS_TILE & 1);
-        Tt.t_mask = p; p += OBS_TILE; Tt.t_next = p; p += OBS_TILE;
-        Tt.t_pend = reinterpret_cast<int *>(p); p += OBS_TILE; Tt.t_lsle = p; p += OBS_TILE;
-        Tt.t_count = reinterpret_cast<int *>(p); p += OBS_TILE;
-        Tt.q_head = reinterpret_cast<int *>(p); Tt.q_tail = Tt.q_head + 1; Tt.n_done = Tt.q_head + 2; p += 4;
-        Tt.norder = reinterpret_cast<int8_t *>(p); p += OBS_TILE * 8;
-        Tt.q = reinterpret_cast<uint16_t *>(p);
+        uint32_t *p = reinterpret_cast<uint32_t *>(smraw + lay.nodes);
+        T.n_a = p; p += OBS_TILE * 31; T.n_sk = p; p += OBS_TILE * 31;
+        T.count = reinterpret_cast<int *>(p); p += OBS_TILE;
+        T.norder = reinterpret_cast<int8_t *>(p);
     }
 
     // optional phase timestamps (tuning only): FlBatch.debug_clocks [E][16] int64, NULL = off
@@ -381,8 +395,8 @@ k_observe(FlBatch b, ObsLayout lay, float *__restrict__ out_attr, float *__restr
 #define OBS_TICK(k) do { if (dbg && tid == 0) dbg[k] = clock64(); } while (0)
     if (dbg && tid == 0) dbg[15] = clock64();
     // ---- phase 0: TMA bulk copies of the static world ---------------------------------------------
-    const bool use_tma = lay.grid >= 0 || lay.dist >= 0 || lay.ridx >= 0 || lay.srec >= 0 || lay.wstart >= 0 || lay.wlenk >= 0 ||
-                         lay.wlist >= 0 || lay.wchild >= 0;
+    const bool use_tma = lay.grid >= 0 || lay.dist >= 0 || lay.ridx >= 0 || lay.srec >= 0 || lay.wrec >= 0 || lay.whoff >= 0 ||
+                         lay.whits >= 0 || lay.wlist >= 0 || lay.kcls >= 0;
     if (use_tma && tid == 0) {
         mbar_init(bar, 1);
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -391,25 +405,26 @@ k_observe(FlBatch b, ObsLayout lay, float *__restrict__ out_attr, float *__restr
         const uint32_t rb = lay.ridx >= 0 ? (uint32_t)(b.ridx_stride * 2) : 0u;
         const uint32_t sb = (uint32_t)(b.state_stride * 4);
         const uint32_t lb = lay.wlist >= 0 ? (uint32_t)(b.wlist_stride * 2) : 0u;
-        mbar_expect_tx(bar, gb + db + rb + lb + (lay.srec >= 0 ? sb : 0u) + (lay.wstart >= 0 ? sb : 0u) + (lay.wlenk >= 0 ? sb : 0u) +
-                                (lay.wchild >= 0 ? 2 * sb : 0u));
+        const uint32_t hb = lay.whits >= 0 ? (uint32_t)(b.whits_stride * 4) : 0u;
+        const uint32_t kb = lay.kcls >= 0 ? (uint32_t)(b.state_stride * 2) : 0u;
+        mbar_expect_tx(bar, gb + db + rb + lb + hb + kb + (lay.srec >= 0 ? sb : 0u) + (lay.wrec >= 0 ? 4 * sb : 0u) + (lay.whoff >= 0 ? sb : 0u));
         if (gb) tma_load_1d(smraw + lay.grid, g_grid, gb, bar);
         if (rb) tma_load_1d(smraw + lay.ridx, g_ridx, rb, bar);
         if (lay.srec >= 0) tma_load_1d(smraw + lay.srec, g_srec, sb, bar);
-        if (lay.wstart >= 0) tma_load_1d(smraw + lay.wstart, g_wstart, sb, bar);
-        if (lay.wlenk >= 0) tma_load_1d(smraw + lay.wlenk, g_wlenk, sb, bar);
+        if (lay.wrec >= 0) tma_load_1d(smraw + lay.wrec, g_wrec, 4 * sb, bar);
+        if (lay.whoff >= 0) tma_load_1d(smraw + lay.whoff, g_whoff, sb, bar);
+        if (hb) tma_load_1d(smraw + lay.whits, g_whits, hb, bar);
+        if (kb) tma_load_1d(smraw + lay.kcls, b.kcls + (size_t)e * b.state_stride, kb, bar);
         if (lb) tma_load_1d(smraw + lay.wlist, g_wlist, lb, bar);
-        if (lay.wchild >= 0) tma_load_1d(smraw + lay.wchild, g_wchild, 2 * sb, bar);
         if (db) tma_load_1d(smraw + lay.dist, g_dist, db, bar);
     }
-    // zero the key counters; forget the previous occupancy
-    for (int k = tid; k <= K; k += NT) ks[k] = 0;
-    if (lay.ci >= 0) { for (int k = tid; k < HW; k += NT) ci[k] = 0; }
-    else { for (int i = tid; i < N; i += NT) { const int oc = b.occ_cell[(size_t)e * N + i]; if (oc >= 0) ci[oc] = 0; } }
-    const float T = (float)b.max_steps[e], Nf = (float)N;
-    const Scale sc{T, __frcp_rn(T), Nf, __frcp_rn(Nf)};
+    // zero the bucket counters and the occupancy words
+    for (int k = tid; k <= R + 1; k += NT) ks[k - 1] = 0;
+    for (int k = tid; k < R; k += NT) ci[k] = 0;
+    const float T_ = (float)b.max_steps[e], Nf = (float)N;
+    const Scale sc{T_, __frcp_rn(T_), Nf, __frcp_rn(Nf)};
     const int elapsed = b.elapsed[e];
-    if (tid < 4) s_misc[tid] = 0;                  // [0] entries, [1] unsorted entries written, [2] max time per cell
+    if (tid < 4) s_misc[tid] = 0;                  // [0] entries, [1] unsorted entries written, [2] max time per cell, [3] bad cell met
     __syncthreads();                               // mbarrier initialised, counters zeroed
     OBS_TICK(0);
     if (use_tma) mbar_wait(bar, 0);
@@ -458,27 +473,32 @@ k_observe(FlBatch b, ObsLayout lay, float *__restrict__ out_attr, float *__restr
         A.rec_b[i] = (uint32_t)trans_attr | ((uint32_t)(b.nmal[ea] != 0) << 16) | ((uint32_t)(b.mal[ea] != 0) << 17) |
                      ((uint32_t)(b.sig_mal[ea] != 0) << 18);
         const float max_dist = (float)((H + W) * 8);
-        A.f_earliest[i] = (float)b.earliest[ea] / T;
-        A.f_latest[i] = (float)b.latest[ea] / T;
-        A.f_arrival[i] = (float)b.arrival[ea] / T;
+        A.f_earliest[i] = (float)b.earliest[ea] / T_;
+        A.f_latest[i] = (float)b.latest[ea] / T_;
+        A.f_arrival[i] = (float)b.arrival[ea] / T_;
         A.f_dist[i] = dt == INFINITY ? 8.0f : dt / max_dist;
         const unsigned idv = dm[((size_t)(ip.x * W + ip.y)) * 4 + idir];
         A.f_idist[i] = idv == FL_DIST_INF ? 8.0f : (float)idv / max_dist;
     }
     __syncthreads();
-    // occupancy word per cell (treeobs.cpp:67-92, deadlock_checker.cpp:15-20): the HIGHEST handle standing on the
+    // occupancy word per rail cell (treeobs.cpp:67-92, deadlock_checker.cpp:15-20): the HIGHEST handle standing on the
     // cell (std::map assignment in handle order = last writer) in the top bits so atomicMax picks it, its
     // direction and malfunction flag; then the number of off-map trains whose initial cell it is.
     for (int i = tid; i < N; i += NT) {
         const int cellid = A.cellid[i];
-        if (cellid >= 0)
-            atomicMax(&ci[cellid], ((uint32_t)(i + 1) << 21) | ((A.info[i] & 3u) << 9) | (((A.rec_b[i] >> 17) & 1u) << 8));
-        if (lay.ci < 0) b.occ_cell[(size_t)e * N + i] = cellid;
+        if (cellid >= 0) {
+            const unsigned ri = ridx[cellid];
+            if (ri != 0xFFFFu)
+                atomicMax(&ci[ri], ((uint32_t)(i + 1) << 21) | ((A.info[i] & 3u) << 9) | (((A.rec_b[i] >> 17) & 1u) << 8));
+        }
     }
     __syncthreads();
     for (int i = tid; i < N; i += NT) {
         const int ic = A.initcell[i];
-        if (ic >= 0 && ld_vol_u32(&ci[ic]) != 0) atomicAdd(&ci[ic], 1u << 11);
+        if (ic >= 0) {
+            const unsigned ri = ridx[ic];
+            if (ri != 0xFFFFu && ld_vol_u32(&ci[ri]) != 0) atomicAdd(&ci[ri], 1u << 11);
+        }
     }
     __syncthreads();
     OBS_TICK(1);
@@ -487,18 +507,21 @@ k_observe(FlBatch b, ObsLayout lay, float *__restrict__ out_attr, float *__restr
     const bool dl_warp = warp == NT / 32 - 1;
     constexpr int NW = NT - 32;                    // threads walking predictions
     uint32_t *ent = reinterpret_cast<uint32_t *>(smraw + lay.ent);
-    uint32_t *tmp_pay = reinterpret_cast<uint32_t *>(smraw + lay.tree);          // unsorted entries, aliasing the tree tile
+    uint32_t *tmp_pay = reinterpret_cast<uint32_t *>(smraw + lay.nodes);         // unsorted entries, aliasing the node table
     uint16_t *tmp_key = reinterpret_cast<uint16_t *>(tmp_pay + lay.tmp_cap);
     if (dl_warp) {
-        if (lane == 0) { update_deadlocks(D, ci, N, H, W); if (dbg) dbg[8] = clock64(); }
+        if (lane == 0) { update_deadlocks(D, ci, ridx, N, H, W); if (dbg) dbg[8] = clock64(); }
         __syncwarp();
     } else {
-        for (int i = tid; i < N; i += NW) {        // one greedy walk per agent: count per cell id, keep the entries unsorted
+        for (int i = tid; i < N; i += NW) {        // one greedy walk per agent: count per rail cell, keep the entries unsorted
             const uint32_t info = A.info[i];
             const int vr = (int)(short)(A.vrc[i] & 0xFFFF), vc = (int)(A.vrc[i] >> 16);
             const int tr = (int)(short)(A.tgt[i] & 0xFFFF), tc = (int)(A.tgt[i] >> 16);
             walk_prediction(grid, dist + (size_t)((info >> 8) & 0xFFFF) * HW * 4, W, vr, vc, (int)(info & 3), tr, tc,
-                            (int)(info >> 24), [&](int key, int t0, int t1, int dh, int dp, int dn) {
+                            (int)(info >> 24), [&](int cell, int t0, int t1, int dh, int dp, int dn) {
+                                unsigned key = ridx[cell];
+                                if (key == 0xFFFFu) return;
+                                if (kcls) key = kcls[key];
                                 atomicAdd(&ks[key], 1u);
                                 const int pos = atomicAdd(&s_misc[1], 1);
                                 if (pos < lay.tmp_cap) { tmp_pay[pos] = pack_entry(i, t0, t1, dh, dp, dn); tmp_key[pos] = (uint16_t)key; }
@@ -506,8 +529,8 @@ k_observe(FlBatch b, ObsLayout lay, float *__restrict__ out_attr, float *__restr
         }
         named_bar_sync(1, NW);
         OBS_TICK(2);
-        // exclusive scan of ks[0..K] (K+1 values; the last becomes the total)
-        const int per = (K + 1 + NW - 1) / NW, lo = min(tid * per, K + 1), hi = min(lo + per, K + 1);
+        // exclusive scan of ks[0..R] (R+1 values; the last becomes the total)
+        const int per = (R + 1 + NW - 1) / NW, lo = min(tid * per, R + 1), hi = min(lo + per, R + 1);
         uint32_t sum = 0;
         for (int k = lo; k < hi; k++) sum += ks[k];
         s_part[tid] = sum;
@@ -523,25 +546,28 @@ k_observe(FlBatch b, ObsLayout lay, float *__restrict__ out_attr, float *__restr
         named_bar_sync(1, NW);
         const int n_ent = (int)s_part[NW - 1];
         if (tid == 0) s_misc[0] = n_ent;
-        // scatter.  ks[key] is advanced to the END of its bucket; bucket k is [k ? ks[k-1] : 0, ks[k]) afterwards.
-        if (n_ent <= lay.tmp_cap && n_ent <= lay.ent_cap && K <= 0xFFFF) {
+        // scatter.  ks[key] is advanced to the END of its bucket; bucket r is [ks[r-1], ks[r]) afterwards (ks[-1] = 0).
+        if (n_ent <= lay.tmp_cap && n_ent <= lay.ent_cap) {
             for (int j = tid; j < n_ent; j += NW) ent[atomicAdd(&ks[tmp_key[j]], 1u)] = tmp_pay[j];
         } else {                                    // does not fit in shared memory: walk again, scatter into the global spill space
-            ent = reinterpret_cast<uint32_t *>(b.entries + (size_t)e * b.ent_cap);
+            ent = b.entries + (size_t)e * b.ent_cap;
             for (int i = tid; i < N; i += NW) {
                 const uint32_t info = A.info[i];
                 const int vr = (int)(short)(A.vrc[i] & 0xFFFF), vc = (int)(A.vrc[i] >> 16);
                 const int tr = (int)(short)(A.tgt[i] & 0xFFFF), tc = (int)(A.tgt[i] >> 16);
                 walk_prediction(grid, dist + (size_t)((info >> 8) & 0xFFFF) * HW * 4, W, vr, vc, (int)(info & 3), tr, tc,
-                                (int)(info >> 24), [&](int key, int t0, int t1, int dh, int dp, int dn) {
+                                (int)(info >> 24), [&](int cell, int t0, int t1, int dh, int dp, int dn) {
+                                    unsigned key = ridx[cell];
+                                    if (key == 0xFFFFu) return;
+                                    if (kcls) key = kcls[key];
                                     ent[atomicAdd(&ks[key], 1u)] = pack_entry(i, t0, t1, dh, dp, dn);
                                 });
             }
         }
         named_bar_sync(1, NW);
         // order every bucket: long-lived entries first, then by t0, so that the tree walk scans a time window only
-        for (int key = tid; key < K; key += NW) {
-            const int s0 = key ? (int)ks[key - 1] : 0, s1 = (int)ks[key];
+        for (int key = tid; key < R; key += NW) {
+            const int s0 = (int)ks[key - 1], s1 = (int)ks[key];
             for (int x = s0 + 1; x < s1; x++) {
                 const uint32_t v = ent[x], kv = entry_sort_key(v);
                 int y = x - 1;
@@ -552,139 +578,155 @@ k_observe(FlBatch b, ObsLayout lay, float *__restrict__ out_attr, float *__restr
     }
     __syncthreads();
     OBS_TICK(3);
-    if (dl_warp && !(s_misc[0] <= lay.tmp_cap && s_misc[0] <= lay.ent_cap && K <= 0xFFFF))
-        ent = reinterpret_cast<uint32_t *>(b.entries + (size_t)e * b.ent_cap);
+    if (dbg && tid == 0) dbg[10] = s_misc[0];
+    if (dl_warp && !(s_misc[0] <= lay.tmp_cap && s_misc[0] <= lay.ent_cap)) ent = b.entries + (size_t)e * b.ent_cap;
     const int tpc_max = s_misc[2];
     for (int i = tid; i < N; i += NT) b.deadlocked[(size_t)e * N + i] = D.dl[i];
 
     // ---- phase 4: branch trees, OBS_TILE agents at a time -----------------------------------------
     for (int a0 = 0; a0 < N; a0 += OBS_TILE) {
         const int na = min(OBS_TILE, N - a0);
-        const int qcap = OBS_TILE * 30;
-        for (int k = tid; k < qcap; k += NT) Tt.q[k] = OBS_Q_EMPTY;
-        if (tid == 0) { *Tt.q_head = 0; *Tt.q_tail = 0; *Tt.n_done = 0; }
-        __syncthreads();
-        // roots (treeobs.cpp:171-221)
+        // ---- 4A: tree structure, one lane per agent (treeobs.cpp:171-256 FIFO, 583-608 children) ----
         for (int la = tid; la < na; la += NT) {
             const int i = a0 + la;
-            const size_t ea = (size_t)e * N + i;
-            float *forest = out_forest + ea * (FL_MAX_NODES * FL_NODE_F);
+            uint32_t *n_a = T.n_a + la * 31, *n_sk = T.n_sk + la * 31;
             const uint32_t info = A.info[i];
             const int vr = (int)(short)(A.vrc[i] & 0xFFFF), vc = (int)(A.vrc[i] >> 16), dir = (int)(info & 3);
-            const float dtv = A.dt[i];
-            store_node(forest, make_float4(0.f, 0.f, 0.f, 0.f),
-                       make_float4(0.f, 0.f, dtv != INFINITY ? dtv / T : -1.0f, 0.f),
-                       make_float4(0.f, (float)((A.rec_b[i] >> 16) & 1u) / Nf, A.speed[i], 0.f));
+            const unsigned slot = (info >> 8) & 0xFFFFu;
             const int nb = nibble(grid[vr * W + vc], dir);
             int orientation = dir;
             if (__popc(nb) == 1) orientation = first_dir(nb);
-            uint32_t mask = 0;
-            for (int ad = -1; ad <= 1; ad++) {
+            n_a[0] = 0; n_sk[0] = 0xFFFFu;
+            for (int ad = -1; ad <= 1; ad++) {                               // roots (treeobs.cpp:171-221)
                 const int bd = (orientation + ad) & 3, idx = 2 + ad;
                 const uint32_t csid = tbit(nb, bd) ? child_state(ridx, H, W, vr, vc, bd) : 0xFFFFFFFFu;
                 const bool real = csid != 0xFFFFFFFFu;
-                Tt.n_sid[la * 31 + idx] = (uint16_t)csid;
-                Tt.n_meta[la * 31 + idx] = (uint16_t)(bd | ((ad + 1) << 2) | ((real ? 0 : 1) << 4));
-                Tt.n_tot[la * 31 + idx] = 1;
-                if (real) mask |= 1u << (idx - 1);
-                else store_null_node(forest + idx * FL_NODE_F);
+                n_a[idx] = 1u | ((uint32_t)(ad + 1) << 28) | ((real ? 0u : 1u) << 30);
+                n_sk[idx] = csid & 0xFFFFu;
             }
-            Tt.n_meta[la * 31] = 0;
-            Tt.t_mask[la] = mask; Tt.t_next[la] = 0; Tt.t_lsle[la] = 1u | (4u << 8); Tt.t_pend[la] = __popc(mask);
-            if (mask == 0) {
-                Tt.t_count[la] = 4;
-                for (int n = 4; n < FL_MAX_NODES; n++) store_null_node(forest + n * FL_NODE_F);
-                atomicAdd(Tt.n_done, 1);
-            } else {
-                int slot = atomicAdd(Tt.q_tail, __popc(mask));
-                for (uint32_t m = mask; m; m &= m - 1) Tt.q[slot++] = (uint16_t)((la << 5) | __ffs(m));
+            int count = 4;
+            bool bad = false;
+            for (int n = 1; n < count; n++) {
+                const uint32_t a = n_a[n];
+                if ((a >> 30) & 1u) continue;
+                const unsigned sid = n_sk[n] & 0xFFFFu;
+                const uint4 w = wrec[sid];
+                const int L = (int)(w.y & 0xFFFFu), skind = (int)((w.y >> 16) & 15u), nh = (int)((w.y >> 20) & 255u);
+                int kend = L;
+                bool hit = false;
+                if (nh) {                                                    // the observer's own target ends the walk early
+                    const uint32_t ho = whoff[sid];
+                    for (int q = 0; q < nh; q++) {
+                        const uint32_t hv = whits[ho + q];
+                        if ((hv >> 16) == slot) { kend = (int)(hv & 0xFFFFu); hit = true; break; }
+                    }
+                }
+                const int kind = hit ? 4 : (skind == WK_BAD ? 3 : skind);
+                if (!hit && skind == WK_BAD) bad = true;                     // treeobs.cpp:527-535 throws
+                n_a[n] = a | ((uint32_t)kind << 20);
+                n_sk[n] = sid | ((uint32_t)kend << 16);
+                if (count < FL_MAX_NODES) {
+                    const uint32_t tot1 = (a & 0xFFFFFu) + (uint32_t)kend + 1u;
+                    const unsigned ch[3] = {w.z & 0xFFFFu, w.z >> 16, w.w & 0xFFFFu};
+#pragma unroll
+                    for (int j = 0; j < 3; j++) {
+                        const int cidx = count + j;
+                        if (cidx < FL_MAX_NODES) {
+                            const unsigned cs = kind <= 2 ? ch[j] : 0xFFFFu;
+                            n_a[cidx] = min(tot1, 0xFFFFFu) | ((uint32_t)n << 23) | ((uint32_t)j << 28) | ((cs == 0xFFFFu ? 1u : 0u) << 30);
+                            n_sk[cidx] = cs;
+                        }
+                    }
+                    count = min(FL_MAX_NODES, count + 3);
+                }
+            }
+            if (bad) s_misc[3] = 1;
+            T.count[la] = count;
+            // evaluation orders (tool.h:468-524): node_order = height above the leaves
+            int8_t *no = T.norder + la * 32;
+            for (int k = 0; k < 32; k++) no[k] = k < count ? 0 : -2;
+            for (int k = count - 1; k >= 1; k--) {
+                const int pa = (int)((n_a[k] >> 23) & 31u);
+                no[pa] = (int8_t)max((int)no[pa], (int)no[k] + 1);
             }
         }
         __syncthreads();
-    OBS_TICK(4);
+        OBS_TICK(4);
 
-        // Branch walks (treeobs.cpp:258-610).  A group of OBS_G lanes takes one walk from the queue; the states
-        // the walk visits come from the static list of its start state (walks.cuh), OBS_G of them per iteration,
-        // one per lane; what the lanes find is combined with warp ballots and redux instructions.
-        {
-            const int gl = lane & (OBS_G - 1), gbase = lane & ~(OBS_G - 1);
-            constexpr unsigned GM = OBS_G == 32 ? 0xFFFFFFFFu : ((1u << OBS_G) - 1u);
-            const unsigned gmask = GM << gbase;
-            bool active = false;
-            int claim = -1;
-            int la = 0, n = 0, h = 0, tot0 = 0, k0 = 0, L = 0, skind = 0, tcell = -1;
-            uint32_t wbase = 0, sid0 = 0;
-            // group-uniform findings: first walk index (k) of each event, counts, flags
-            int k_other = I_INF, k_conf = I_INF, k_unus = I_INF, same = 0, opp = 0, malf = 0, rtdn = 0, spd_bits = 0x3F800000;
-            float tpc_f = 1.0f;
-            const uint16_t *dm = dist;
-            int iters = 0;
-            while (true) {
-                iters++;
-                if (!active) {
-                    if (claim < 0) {                                                     // group-uniform: take the next queue index
-                        if (gl == 0) claim = atomicAdd(Tt.q_head, 1);
-                        claim = __shfl_sync(gmask, claim, gbase);
+        // ---- 4B: node features, one warp per agent over the flat list of the cells of all its walks ----
+        for (int la = warp; la < na; la += NT / 32) {
+            const int h = a0 + la;
+            const size_t ea = (size_t)e * N + h;
+            const int count = T.count[la];
+            const int n = lane;
+            const uint32_t a = n < FL_MAX_NODES ? T.n_a[la * 31 + n] : (1u << 30);
+            const uint32_t sk = n < FL_MAX_NODES ? T.n_sk[la * 31 + n] : 0xFFFFu;
+            const bool real = n >= 1 && n < count && !((a >> 30) & 1u);
+            const int kind = (int)((a >> 20) & 7u), tot0 = (int)(a & 0xFFFFFu), kend = (int)(sk >> 16);
+            const unsigned sid0 = sk & 0xFFFFu;
+            uint4 w = make_uint4(0u, 0u, 0u, 0u);
+            if (real) w = wrec[sid0];
+            const unsigned wbase = w.x, kunus = w.w >> 16;
+            const uint32_t ainfo = A.info[h];
+            const uint16_t *dm = dist + (size_t)((ainfo >> 8) & 0xFFFF) * HW * 4;
+            const float tpc_f = (float)(1.0 / (double)A.speed[h]);                          // treeobs.cpp:304
+            // the state the walk ends on and its distance to the target: loaded now, used when the node is written
+            unsigned dv_end = 0;
+            if (real && kind != 4) {
+                const uint32_t erec = srec[wlist[wbase + kend]];
+                dv_end = dm[((size_t)((int)(erec & 1023) * W + (int)((erec >> 10) & 1023))) * 4 + ((erec >> 20) & 3)];
+            }
+            const unsigned len = real ? (unsigned)kend + 1u : 0u;
+            unsigned total;
+            const unsigned off = warp_excl_scan(len, lane, total);
+            const unsigned real_mask = __ballot_sync(0xFFFFFFFFu, real);
+            const int nreal = __popc(real_mask);
+            // lane q holds the q-th real node's (offset, list base, tot0): the owner of a cell is found by rank
+            const unsigned src = __fns(real_mask, 0, lane + 1) & 31u;
+            const unsigned c_off = __shfl_sync(0xFFFFFFFFu, off, src), c_wb = __shfl_sync(0xFFFFFFFFu, wbase, src);
+            const int c_t0 = __shfl_sync(0xFFFFFFFFu, tot0, src);
+            const bool c_valid = lane < nreal;
+            int k_other = I_INF, k_conf = I_INF, same = 0, opp = 0, malf = 0, rtdn = 0, spd_bits = 0x3F800000;  // min speed starts at 1.0f
+            for (unsigned base = 0; base < total; base += 32) {
+                const unsigned j = base + lane;
+                const int cnt0 = __popc(__ballot_sync(0xFFFFFFFFu, c_valid && c_off <= base));
+                const unsigned starts = __reduce_or_sync(0xFFFFFFFFu, (c_valid && c_off > base && c_off < base + 32) ? 1u << (c_off - base) : 0u);
+                const int rank = cnt0 - 1 + __popc(starts & (0xFFFFFFFFu >> (31 - lane)));
+                const unsigned o_off = __shfl_sync(0xFFFFFFFFu, c_off, rank), o_wb = __shfl_sync(0xFFFFFFFFu, c_wb, rank);
+                const int o_t0 = __shfl_sync(0xFFFFFFFFu, c_t0, rank);
+                const bool valid = j < total;
+                bool f_agent = false, f_same = false, f_malf = false, f_conf = false;
+                int my_rtd = 0, my_spd = 0x3F800000;
+                if (valid) {
+                    const int k = (int)(j - o_off);
+                    const unsigned sidc = wlist[o_wb + k];
+                    const unsigned rail = sidc >> 2;
+                    const int d = (int)(sidc & 3u);
+                    const int tot = o_t0 + k;
+                    const uint32_t cinfo = ci[rail];
+                    if (cinfo) {                   // treeobs.cpp:322-360 (the observer itself counts too)
+                        f_agent = true;
+                        f_malf = (cinfo >> 8) & 1u;
+                        const int cnt = (int)((cinfo >> 11) & 1023u);
+                        my_rtd = cnt ? cnt - 1 : 0;
+                        f_same = (int)((cinfo >> 9) & 3u) == d;
+                        if (f_same) my_spd = __float_as_int(A.speed[(cinfo >> 21) - 1]);
                     }
-                    const unsigned it = claim < qcap ? ld_vol_u16(&Tt.q[claim]) : (unsigned)OBS_Q_EMPTY;   // broadcast read
-                    if (it != (unsigned)OBS_Q_EMPTY) { __threadfence_block(); claim = -1; }
-                    if (it != (unsigned)OBS_Q_EMPTY) {
-                        active = true;
-                        la = (int)(it >> 5); n = (int)(it & 31);
-                        h = a0 + la;
-                        sid0 = Tt.n_sid[la * 31 + n];
-                        tot0 = (int)Tt.n_tot[la * 31 + n];
-                        wbase = wstart[sid0];
-                        const uint32_t lk = wlenk[sid0];
-                        L = (int)(lk & 0x0FFFFFFFu); skind = (int)(lk >> 28);
-                        k0 = 0;
-                        k_other = k_conf = k_unus = I_INF;
-                        same = opp = malf = rtdn = 0; spd_bits = 0x3F800000;             // min speed starts at 1.0f
-                        const uint32_t tg = A.tgt[h];
-                        tcell = (int)(short)(tg & 0xFFFF) * W + (int)(tg >> 16);
-                        tpc_f = (float)(1.0 / (double)A.speed[h]);                       // treeobs.cpp:304
-                        dm = dist + (size_t)((A.info[h] >> 8) & 0xFFFF) * HW * 4;
-                    }
-                }
-                if (active) {
-                    const int k = k0 + gl;
-                    const bool valid = k <= L;
-                    uint32_t rec = 0;
-                    if (valid) rec = srec[wlist[wbase + k]];
-                    const int cr = (int)(rec & 1023), cc_ = (int)((rec >> 10) & 1023), cell = cr * W + cc_;
-                    const int d = (int)((rec >> 20) & 3), nb = (int)((rec >> 22) & 15);
-                    // the walk stops on the observer's own target (treeobs.cpp:467-475, 483-489): cells behind it do not count
-                    const unsigned tb = (__ballot_sync(gmask, valid && cell == tcell) >> gbase) & GM;
-                    const int kt = tb ? __ffs(tb) - 1 : OBS_G;
-                    const bool ends = tb != 0 || k0 + OBS_G > L;                         // this chunk holds the last cell
-                    const int k_end = tb ? k0 + kt : L;
-                    const bool counts = valid && gl <= kt;
-                    bool f_agent = false, f_same = false, f_malf = false, f_conf = false;
-                    int my_rtd = 0, my_spd = 0x3F800000;
-                    if (counts) {
-                        const int tot = tot0 + k;
-                        const uint32_t cinfo = ci[cell];
-                        if (cinfo) {                   // treeobs.cpp:322-360 (the observer itself counts too)
-                            f_agent = true;
-                            f_malf = (cinfo >> 8) & 1u;
-                            const int cnt = (int)((cinfo >> 11) & 1023u);
-                            my_rtd = cnt ? cnt - 1 : 0;
-                            f_same = (int)((cinfo >> 9) & 3u) == d;
-                            if (f_same) my_spd = __float_as_int(A.speed[(cinfo >> 21) - 1]);
-                        }
-                        const int pt = (int)__fmul_rn((float)tot, tpc_f);               // treeobs.cpp:378
-                        if (pt < NPRED && tot < NPRED) {                                 // treeobs.cpp:379-465
-                            const int key = cc_ * W + cr;
-                            const uint32_t s0 = key ? ks[key - 1] : 0u, s1 = ks[key];
+                    const int pt = (int)__fmul_rn((float)tot, tpc_f);               // treeobs.cpp:378
+                    if (pt < NPRED && tot < NPRED) {                                 // treeobs.cpp:379-465
+                        const unsigned bk = kcls ? kcls[rail] : rail;                 // the reference's position key c*W + r
+                        const uint32_t s0 = ks[(int)bk - 1], s1 = ks[bk];
+                        if (s0 < s1) {
                             const int pre = max(0, pt - 1), post = min(NPRED - 1, pt + 1);
+                            const int nb = (int)((srec[sidc] >> 22) & 15u);
                             unsigned acc = 0;
                             auto candidate = [&](uint32_t en, int t0) {
                                 const int ag = (int)(en & 1023);
-                                const uint32_t ainfo = A.info[ag];
-                                const int t1 = ((en >> 19) & 1u) ? NPRED - 1 : (t0 ? t0 + (int)(ainfo >> 24) - 1 : 0);
+                                const uint32_t oinfo = A.info[ag];
+                                const int t1 = ((en >> 19) & 1u) ? NPRED - 1 : (t0 ? t0 + (int)(oinfo >> 24) - 1 : 0);
                                 if (t1 < pre) return;
                                 const int dh = (int)((en >> 20) & 3), dp = (int)((en >> 22) & 3), dn = (int)((en >> 24) & 3);
-                                const bool done = (ainfo >> 5) & 1;
+                                const bool done = (oinfo >> 5) & 1;
                                 const bool in_cur = t0 <= pt && pt <= t1, in_pre = t0 <= pre && pre <= t1,
                                            in_post = t0 <= post && post <= t1;
                                 const int pdir = pt < t0 ? dp : (pt > t1 ? dn : dh);  // always the direction at row pt
@@ -716,148 +758,86 @@ k_observe(FlBatch b, ObsLayout lay, float *__restrict__ out_attr, float *__restr
                             f_conf = (acc & 1u) ? (acc & 8u) : (acc & 2u) ? (acc & 16u) : (acc & 4u) ? (acc & 32u) : false;
                         }
                     }
-                    // combine over the group: the first lane of an event gives its walk index, counts are popcounts
-                    const unsigned b_agent = (__ballot_sync(gmask, f_agent) >> gbase) & GM;
-                    if (b_agent) {                                                       // group-uniform
-                        const unsigned b_same = (__ballot_sync(gmask, f_same) >> gbase) & GM;
-                        k_other = min(k_other, k0 + __ffs(b_agent) - 1);
-                        same += __popc(b_same); opp += __popc(b_agent & ~b_same);
-                        malf |= __any_sync(gmask, f_malf);
-                        rtdn += __reduce_add_sync(gmask, my_rtd);
-                        spd_bits = min(spd_bits, __reduce_min_sync(gmask, my_spd));     // positive floats order like their bits
+                }
+                // what the lanes found returns to the lane owning the node: ballots masked by the node's segment of this window
+                const unsigned b_agent = __ballot_sync(0xFFFFFFFFu, f_agent);
+                const unsigned b_conf = __ballot_sync(0xFFFFFFFFu, f_conf);
+                const int lo_ = max((int)off - (int)base, 0), hi_ = min((int)(off + len) - (int)base, 32);
+                const unsigned seg = (real && lo_ < hi_) ? ((hi_ == 32 ? 0xFFFFFFFFu : ((1u << hi_) - 1u)) & ~((1u << lo_) - 1u)) : 0u;
+                if (b_agent) {                                                       // warp-uniform
+                    const unsigned b_same = __ballot_sync(0xFFFFFFFFu, f_same), b_malf = __ballot_sync(0xFFFFFFFFu, f_malf);
+                    const unsigned m = b_agent & seg;
+                    if (m) {
+                        k_other = min(k_other, (int)base + __ffs(m) - 1 - (int)off);
+                        same += __popc(b_same & seg); opp += __popc(m & ~b_same);
+                        malf |= (b_malf & seg) != 0u;
                     }
-                    const unsigned b_conf = (__ballot_sync(gmask, f_conf) >> gbase) & GM;
-                    if (b_conf) k_conf = min(k_conf, k0 + __ffs(b_conf) - 1);
-                    const unsigned b_unus = (__ballot_sync(gmask, counts && k < k_end && ((rec >> 26) & 1u)) >> gbase) & GM;
-                    if (b_unus) k_unus = min(k_unus, k0 + __ffs(b_unus) - 1);            // never on the cell the walk ends on
-                    if (!ends) k0 += OBS_G;
-                    else {
-                        // ---- the walk is over: lanes 0..2 write one float4 of the node and create one child each ----
-                        active = false;
-                        const int kind = tb ? 4 : (skind == WK_BAD ? 3 : skind);         // 1 switch, 2 dead end, 3 cycle, 4 target
-                        const uint32_t erec = srec[wlist[wbase + k_end]];                // the state the walk ended on
-                        const int ecell = (int)(erec & 1023) * W + (int)((erec >> 10) & 1023), ed = (int)((erec >> 20) & 3);
-                        const int tot = tot0 + k_end;
-                        const size_t ea = (size_t)e * N + h;
-                        float *forest = out_forest + ea * (FL_MAX_NODES * FL_NODE_F);
-                        const uint32_t lsle = Tt.t_lsle[la], lmask = Tt.t_mask[la];
-                        const int ls = (int)(lsle & 0xFF), le = (int)(lsle >> 8);
-                        const int base = le + 3 * __popc(lmask & ((1u << (n - ls)) - 1u));
-                        // Shared-memory bookkeeping first, global stores last: a CTA-scope fence waits for the thread's
-                        // outstanding global stores too, and nothing in this kernel reads the forest back.
-                        bool child_real = false, child_null = false;
-                        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-                        const int cidx = base + gl;
-                        if (gl < 3) {
-                            if (gl == 0) {                                               // scale_node (treeobs.cpp:111-152)
-                                v = make_float4(tb ? scale_i(tot, sc) : -1.0f, -1.0f, k_other != I_INF ? scale_i(tot0 + k_other, sc) : -1.0f,
-                                                k_conf != I_INF ? scale_i(tot0 + k_conf, sc) : -1.0f);
-                            } else if (gl == 1) {
-                                int dnb, dmin;
-                                if (kind == 4) { dnb = tot; dmin = 0; }
-                                else {
-                                    const unsigned dv = dm[((size_t)ecell) * 4 + ed];
-                                    dmin = dv == FL_DIST_INF ? I_INF : (int)dv;
-                                    dnb = kind == 3 ? I_INF : tot;
-                                }
-                                v = make_float4(k_unus != I_INF ? scale_i(tot0 + k_unus, sc) : -1.0f, scale_i(dnb, sc), scale_i(dmin, sc), scale_n(same, sc));
-                            } else {
-                                v = make_float4(scale_n(opp, sc), scale_n(malf, sc), __int_as_float(spd_bits), scale_n(rtdn, sc));
-                            }
-                            // child gl - 1 in order L, F, R (treeobs.cpp:583-608); its BFS index follows from the level's mask
-                            const int a2 = gl - 1;
-                            if (cidx < FL_MAX_NODES) {
-                                const unsigned csid = kind <= 2 ? wchild[sid0 * 4 + gl] : 0xFFFFu;   // static: walks.cuh
-                                const bool real = csid != 0xFFFFu;
-                                Tt.n_sid[la * 31 + cidx] = (uint16_t)csid;
-                                Tt.n_meta[la * 31 + cidx] = (uint16_t)(((a2 + 1) << 2) | ((real ? 0 : 1) << 4) | (n << 8));
-                                Tt.n_tot[la * 31 + cidx] = (uint32_t)(tot + 1);
-                                child_real = real; child_null = !real;
-                            }
-                        }
-                        __syncwarp(gmask);                                               // the children are in the node table
-                        const unsigned cb = (__ballot_sync(gmask, child_real) >> gbase) & 7u;  // bit j = child j is real
-                        int pad_from = FL_MAX_NODES;
-                        if (gl == 0) {
-                            if (!tb && skind == WK_BAD) atomicOr(&b.status[e], FL_ST_BAD_CELL);   // treeobs.cpp:527-535 throws
-                            if (cb) atomicOr(&Tt.t_next[la], cb << (base - le));
-                            __threadfence_block();
-                            if (atomicSub(&Tt.t_pend[la], 1) == 1) {                    // last walk of this agent's level: release the next one
-                                __threadfence_block();
-                                const uint32_t nmask = atomicExch(&Tt.t_next[la], 0u);
-                                const int nls = le, nle = min(FL_MAX_NODES, le + 3 * __popc(lmask));
-                                if (nmask == 0) {                                       // no real node left: the rest is padding
-                                    Tt.t_count[la] = nle;
-                                    pad_from = nle;
-                                    __threadfence_block();
-                                    atomicAdd(Tt.n_done, 1);
-                                } else {
-                                    Tt.t_mask[la] = nmask; Tt.t_lsle[la] = (uint32_t)nls | ((uint32_t)nle << 8);
-                                    Tt.t_pend[la] = __popc(nmask);
-                                    __threadfence_block();
-                                    int slot = atomicAdd(Tt.q_tail, __popc(nmask));
-                                    for (uint32_t m = nmask; m; m &= m - 1)
-                                        *reinterpret_cast<volatile uint16_t *>(&Tt.q[slot++]) = (uint16_t)((la << 5) | (nls + __ffs(m) - 1));
-                                }
-                            }
-                        }
-                        if (gl < 3) {
-                            reinterpret_cast<float4 *>(forest + n * FL_NODE_F)[gl] = v;
-                            if (child_null) store_null_node(forest + cidx * FL_NODE_F);
-                        }
-                        for (int q = pad_from; q < FL_MAX_NODES; q++) store_null_node(forest + q * FL_NODE_F);
+                    for (unsigned mm = b_agent; mm; mm &= mm - 1) {                  // few trains per window: values by shuffle
+                        const int s = __ffs(mm) - 1;
+                        const int r_ = __shfl_sync(0xFFFFFFFFu, my_rtd, s), sp = __shfl_sync(0xFFFFFFFFu, my_spd, s);
+                        if ((seg >> s) & 1u) { rtdn += r_; spd_bits = min(spd_bits, sp); }   // positive floats order like their bits
                     }
                 }
-                const bool finished = !active && ld_vol_i32(Tt.n_done) >= na;
-                if (__all_sync(0xFFFFFFFFu, finished)) break;
-                if (!__any_sync(0xFFFFFFFFu, active)) __nanosleep(100);                 // nothing to do in this warp: leave the issue slots to the others
+                const unsigned mc = b_conf & seg;
+                if (mc) k_conf = min(k_conf, (int)base + __ffs(mc) - 1 - (int)off);
             }
-            if (dbg && tid == 0) { dbg[9] = iters; dbg[10] = s_misc[0]; }
-        }
-        __syncthreads();
-    OBS_TICK(5);
-
-        // ---- phase 5a: evaluation orders (tool.h:468-524): node_order = height above the leaves ------
-        for (int la = tid; la < na; la += NT) {
-            const int count = Tt.t_count[la];
-            int8_t *no = Tt.norder + la * 32;
-            for (int k = 0; k < 32; k++) no[k] = k < count ? 0 : -2;
-            for (int k = count - 1; k >= 1; k--) {
-                const int pa = (int)((Tt.n_meta[la * 31 + k] >> 8) & 31);
-                no[pa] = (int8_t)max((int)no[pa], (int)no[k] + 1);
+            // ---- lane n writes node n (scale_node, treeobs.cpp:111-152) ----
+            float *forest = out_forest + ea * (FL_MAX_NODES * FL_NODE_F);
+            if (n < FL_MAX_NODES) {
+                float4 v0, v1, v2;
+                if (n == 0) {
+                    const float dtv = A.dt[h];
+                    v0 = make_float4(0.f, 0.f, 0.f, 0.f);
+                    v1 = make_float4(0.f, 0.f, dtv != INFINITY ? dtv / T_ : -1.0f, 0.f);
+                    v2 = make_float4(0.f, (float)((A.rec_b[h] >> 16) & 1u) / Nf, A.speed[h], 0.f);
+                } else if (real) {
+                    const int tot = tot0 + kend;
+                    const bool tb = kind == 4;
+                    int dnb, dmin;
+                    if (tb) { dnb = tot; dmin = 0; }
+                    else {
+                        dmin = dv_end == FL_DIST_INF ? I_INF : (int)dv_end;
+                        dnb = kind == 3 ? I_INF : tot;
+                    }
+                    const bool unus = kunus != 0xFFFFu && (int)kunus < kend;
+                    v0 = make_float4(tb ? scale_i(tot, sc) : -1.0f, -1.0f, k_other != I_INF ? scale_i(tot0 + k_other, sc) : -1.0f,
+                                     k_conf != I_INF ? scale_i(tot0 + k_conf, sc) : -1.0f);
+                    v1 = make_float4(unus ? scale_i(tot0 + (int)kunus, sc) : -1.0f, scale_i(dnb, sc), scale_i(dmin, sc), scale_n(same, sc));
+                    v2 = make_float4(scale_n(opp, sc), scale_n(malf, sc), __int_as_float(spd_bits), scale_n(rtdn, sc));
+                } else {
+                    v0 = v1 = v2 = make_float4(-1.0f, -1.0f, -1.0f, -1.0f);
+                }
+                store_node(forest + n * FL_NODE_F, v0, v1, v2);
             }
-        }
-        __syncthreads();
-        // ---- phase 5b: adjacency / node_order / edge_order: one warp per agent, lanes over the row -------
-        for (int la = warp; la < na; la += NT / 32) {
-            const size_t ea = (size_t)e * N + a0 + la;
-            const int count = Tt.t_count[la];
-            const int8_t *no = Tt.norder + la * 32;
-            const uint16_t *meta = Tt.n_meta + la * 31;
+            // ---- adjacency / node_order / edge_order rows of the agent, lanes over the row ----
+            const int8_t *no = T.norder + la * 32;
+            const uint32_t *meta = T.n_a + la * 31;
             int32_t *adj = out_adj + ea * ((FL_MAX_NODES - 1) * 3);
-            for (int j = lane; j < 90; j += 32) {
-                const int edge = j / 3, comp = j - edge * 3, node = edge + 1;
+            for (int jj = lane; jj < 90; jj += 32) {
+                const int edge = jj / 3, comp = jj - edge * 3, node = edge + 1;
                 int v = -2;
                 if (node < count) {
-                    const unsigned m = meta[node];
-                    v = comp == 0 ? (int)((m >> 8) & 31) : comp == 1 ? node : (int)((m >> 2) & 3) - 1;
+                    const uint32_t m = meta[node];
+                    v = comp == 0 ? (int)((m >> 23) & 31u) : comp == 1 ? node : (int)((m >> 28) & 3u) - 1;
                 }
-                adj[j] = v;
+                adj[jj] = v;
             }
             if (lane < FL_MAX_NODES) out_norder[ea * FL_MAX_NODES + lane] = no[lane];
             if (lane < FL_MAX_NODES - 1) {
                 const int node = lane + 1;
-                out_eorder[ea * (FL_MAX_NODES - 1) + lane] = node < count ? (int)no[(meta[node] >> 8) & 31] : -2;
+                out_eorder[ea * (FL_MAX_NODES - 1) + lane] = node < count ? (int)no[(meta[node] >> 23) & 31u] : -2;
             }
         }
         __syncthreads();
-    OBS_TICK(6);
+        OBS_TICK(5);
     }
+    if (tid == 0 && s_misc[3]) atomicOr(&b.status[e], FL_ST_BAD_CELL);
+    OBS_TICK(6);
 
-    // ---- phase 5c: agent attributes (feature_parser.cpp:3-98), coalesced over the environment ---------
+    // ---- phase 5: agent attributes (feature_parser.cpp:3-98), coalesced over the environment ---------
     {
         float *dst = out_attr + (size_t)e * N * FL_ATTR_F;
-        const float curr_step = (float)elapsed / T;
+        const float curr_step = (float)elapsed / T_;
         for (int idx = tid; idx < N * FL_ATTR_F; idx += NT) {
             const int i = idx / FL_ATTR_F, k = idx - i * FL_ATTR_F;
             const uint32_t ra = A.rec_a[i], rb = A.rec_b[i];

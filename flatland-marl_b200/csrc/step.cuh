@@ -46,9 +46,7 @@ DEVI int fsm(int s, bool in_mal, bool mal_done, bool edr, bool stop, bool valid_
 // EnvAgent.reset for every agent of env e + cleared maps (agent_utils.py:90-105, rail_env.py:335-344,
 // treeobs.cpp:22-28).  Called by all threads of a CTA.
 DEVI void reset_env(const FlBatch &b, int e, bool rewind_schedule) {
-    const int N = (int)b.N, HW = (int)(b.H * b.W);
-    uint32_t *ci = b.cellinfo + (size_t)e * HW;
-    for (int k = threadIdx.x; k < HW; k += blockDim.x) ci[k] = 0;
+    const int N = (int)b.N;
     for (int i = threadIdx.x; i < N; i += blockDim.x) {
         const size_t ea = (size_t)e * N + i;
         b.rc[2 * ea] = -1; b.rc[2 * ea + 1] = -1;
@@ -56,7 +54,6 @@ DEVI void reset_env(const FlBatch &b, int e, bool rewind_schedule) {
         b.dir[ea] = b.init_dir[ea]; b.old_dir[ea] = 255;
         b.state[ea] = WAITING; b.ctr[ea] = 0; b.mal[ea] = 0; b.saved[ea] = 0; b.sig_mal[ea] = 0;
         b.deadlocked[ea] = 0; b.done[ea] = 0; b.nmal[ea] = 0; b.arrival[ea] = -1;
-        b.occ_cell[ea] = -1;
     }
     if (threadIdx.x == 0) {
         b.elapsed[e] = 0; b.done_all[e] = 0;

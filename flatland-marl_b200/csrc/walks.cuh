@@ -7,14 +7,23 @@
 // spread the cells of one walk over the lanes of a lane group instead of chasing them one by one:
 //   ridx[cell]     rail index of a cell (0xFFFF = no rail); state id sid = 4 * ridx[cell] + direction
 //   srec[sid]      row | col << 10 | dir << 20 | transitions nibble of (cell, dir) << 22 | "unusable switch here" << 26
-//   wstart[sid]    offset of the walk from sid in wlist
-//   wlenk[sid]     steps of the walk (it visits steps + 1 states) | kind << 28:
-//                  1 = ends on a switch, 2 = dead end, 3 = the last state revisits an earlier one (rail cycle,
-//                  treeobs.cpp:476-481), 0 = ends on a cell without transitions (treeobs.cpp:527-535 throws)
+//   wrec[sid]      16-byte record of the walk from sid:
+//                  x  offset of the walk in wlist
+//                  y  steps (the walk visits steps + 1 states) | kind << 16 | number of target hits << 20; kind:
+//                     1 = ends on a switch, 2 = dead end, 3 = the last state revisits an earlier one (rail cycle,
+//                     treeobs.cpp:476-481), 0 = ends on a cell without transitions (treeobs.cpp:527-535 throws)
+//                  z  child 0 | child 1 << 16      state ids the children (left, forward, right; treeobs.cpp:583-608) of the
+//                  w  child 2 | k_unusable << 16   node ending this walk start from, 0xFFFF = null child (always for walks
+//                                                  ending in a cycle or a bad cell); k_unusable = first step < steps that
+//                                                  stands on an unusable switch (treeobs.cpp:497-513), 0xFFFF = none
+//   whoff[sid]     offset of the walk's target hits in whits (valid when the record counts any)
+//   whits[...]     step | slot << 16 for every state of the walk standing on the target cell of a unique-target slot, in
+//                  walk order: the observer's own target ends its walk early (treeobs.cpp:467-475, 483-489)
 //   wlist[...]     the visited state ids, walk after walk
-//   wchild[4*sid+j] state id the j-th child (left, forward, right; treeobs.cpp:583-608) of the node ending this walk
-//                  starts from, 0xFFFF = null child (also for walks ending in a cycle or a bad cell)
-// FILL = false only measures (states, list length) so that the host can size wlist.
+//   kcls[rail]     the reference keys predicted positions by c * W + r (treeobs.cpp:50-65, 379-465), which is not unique when
+//                  H > W: cells (r, c) and (r + W, c - 1) share a key and conflict with each other's predictions.  kcls maps
+//                  a rail cell to the lowest rail index of its key class (itself when H <= W)
+// FILL = false only measures (states, list length, hits) so that the host can size wlist and whits.
 #pragma once
 #include "common.cuh"
 
@@ -85,14 +94,30 @@ DEVI uint32_t block_exclusive_scan(uint32_t v, uint32_t *s_part, uint32_t &total
     return ex;
 }
 
+// slot of the target standing on `cell`, -1 = none.  tbits: one bit per cell, set when some slot's target is there.
+DEVI int target_slot_at(const FlBatch &b, int e, const uint32_t *tbits, int cell, int W) {
+    if (!((tbits[cell >> 5] >> (cell & 31)) & 1u)) return -1;
+    const int16_t *rc = b.slot_rc + (size_t)e * b.n_slots * 2;
+    const int r = cell / W, c = cell - r * W;
+    for (int s = 0; s < (int)b.n_slots; s++) if (rc[2 * s] == r && rc[2 * s + 1] == c) return s;
+    return -1;
+}
+
 template <bool FILL, int NT>
 __global__ void __launch_bounds__(NT) k_walks(FlBatch b) {
     const int e = blockIdx.x, H = (int)b.H, W = (int)b.W, HW = H * W, tid = threadIdx.x;
     __shared__ uint32_t s_part[NT];
+    extern __shared__ uint32_t s_tbits[];            // (HW + 31) / 32 words: cells holding the target of a slot
     const uint16_t *__restrict__ g = b.grid + (size_t)e * b.grid_stride;
     uint16_t *ridx = b.ridx + (size_t)e * b.ridx_stride;
     int32_t *tot = b.walk_total + (size_t)e * 4;
 
+    for (int k = tid; k < (HW + 31) / 32; k += NT) s_tbits[k] = 0;
+    __syncthreads();
+    for (int s = tid; s < (int)b.n_slots; s += NT) {
+        const int r = b.slot_rc[((size_t)e * b.n_slots + s) * 2], c = b.slot_rc[((size_t)e * b.n_slots + s) * 2 + 1];
+        if (r >= 0 && c >= 0 && r < H && c < W) atomicOr(&s_tbits[(r * W + c) >> 5], 1u << ((r * W + c) & 31));
+    }
     // rail indices in cell order
     const int per = (HW + NT - 1) / NT, lo = min(tid * per, HW), hi = min(lo + per, HW);
     uint32_t cnt = 0;
@@ -101,24 +126,30 @@ __global__ void __launch_bounds__(NT) k_walks(FlBatch b) {
     uint32_t run = block_exclusive_scan<NT>(cnt, s_part, n_rail);
     const int S = (int)n_rail * 4;
     if (!FILL) {
-        // list length = sum over states of (steps + 1)
-        uint32_t len = 0;
+        // list length = sum over states of (steps + 1); hits = states of all walks standing on a slot's target
+        uint32_t len = 0, nh = 0;
         for (int cs = tid; cs < HW * 4; cs += NT) {
-            const int cell = cs >> 2, d = cs & 3;
+            const int cell = cs >> 2, d0 = cs & 3;
             if (!g[cell]) continue;
-            int kind;
-            len += (uint32_t)static_walk_len(g, H, W, cell / W, cell % W, d, S, kind) + 1u;
+            int kind, r = cell / W, c = cell % W, d = d0;
+            const int steps = static_walk_len(g, H, W, r, c, d, S, kind);
+            len += (uint32_t)steps + 1u;
+            for (int k = 0; k <= steps; k++) {
+                nh += (s_tbits[(r * W + c) >> 5] >> ((r * W + c) & 31)) & 1u;
+                if (k < steps) static_succ(g, H, W, r, c, d, kind);
+            }
         }
-        uint32_t total;
+        uint32_t total, total_h;
         block_exclusive_scan<NT>(len, s_part, total);
-        if (tid == 0) { tot[0] = S; tot[1] = (int)total; }
+        block_exclusive_scan<NT>(nh, s_part, total_h);
+        if (tid == 0) { tot[0] = S; tot[1] = (int)total; tot[2] = (int)total_h; tot[3] = 0; }
         return;
     }
     uint32_t *srec = b.srec + (size_t)e * b.state_stride;
-    uint32_t *wstart = b.wstart + (size_t)e * b.state_stride;
-    uint32_t *wlenk = b.wlenk + (size_t)e * b.state_stride;
+    uint4 *wrec = reinterpret_cast<uint4 *>(b.wrec) + (size_t)e * b.state_stride;
+    uint32_t *whoff = b.whoff + (size_t)e * b.state_stride;
     uint16_t *wlist = b.wlist + (size_t)e * b.wlist_stride;
-    uint16_t *wchild = b.wchild + (size_t)e * b.state_stride * 4;
+    uint32_t *whits = b.whits + (size_t)e * b.whits_stride;
     for (int k = lo; k < hi; k++) {
         const unsigned gc = g[k];
         if (!gc) { ridx[k] = 0xFFFF; continue; }
@@ -134,31 +165,60 @@ __global__ void __launch_bounds__(NT) k_walks(FlBatch b) {
     }
     for (int k = HW + tid; k < (int)b.ridx_stride; k += NT) ridx[k] = 0xFFFF;
     __syncthreads();
+    uint16_t *kcls = b.kcls + (size_t)e * b.state_stride;
+    for (int k = lo; k < hi; k++) {
+        const unsigned ri = ridx[k];
+        if (ri == 0xFFFF) continue;
+        const int r = k / W, c = k - r * W;
+        unsigned cls = ri;
+        for (int m = -(r / W); m < 0; m++) {             // aliases in front of this cell in cell order: (r + m W, c - m)
+            const int rr = r + m * W, cc = c - m;
+            if (cc < W && ridx[rr * W + cc] != 0xFFFF) { cls = ridx[rr * W + cc]; break; }
+        }
+        kcls[ri] = (uint16_t)cls;
+    }
+    for (int k = (int)n_rail + tid; k < (int)b.state_stride; k += NT) kcls[k] = 0xFFFF;
     // walk lengths, offsets, lists: thread t owns the contiguous states [slo, shi)
     const int sper = (S + NT - 1) / NT, slo = min(tid * sper, S), shi = min(slo + sper, S);
-    uint32_t len = 0;
+    uint32_t len = 0, nh = 0;
     for (int sid = slo; sid < shi; sid++) {
         const uint32_t rec = srec[sid];
-        const int d = (int)((rec >> 20) & 3);
+        int r = (int)(rec & 1023), c = (int)((rec >> 10) & 1023), d = (int)((rec >> 20) & 3);
         int kind = WK_BAD;
-        const int steps = static_walk_len(g, H, W, (int)(rec & 1023), (int)((rec >> 10) & 1023), d, S, kind);
-        wlenk[sid] = (uint32_t)steps | ((uint32_t)kind << 28);
+        const int steps = static_walk_len(g, H, W, r, c, d, S, kind);
+        uint32_t h = 0;
+        for (int k = 0; k <= steps; k++) {
+            h += (s_tbits[(r * W + c) >> 5] >> ((r * W + c) & 31)) & 1u;
+            if (k < steps) { int k2; static_succ(g, H, W, r, c, d, k2); }
+        }
+        wrec[sid].y = (uint32_t)min(steps, 0xFFFF) | ((uint32_t)kind << 16) | (min(h, 255u) << 20);
         len += (uint32_t)steps + 1u;
+        nh += h;
     }
-    uint32_t total;
+    uint32_t total, total_h;
     uint32_t off = block_exclusive_scan<NT>(len, s_part, total);
+    uint32_t hoff = block_exclusive_scan<NT>(nh, s_part, total_h);
     for (int sid = slo; sid < shi; sid++) {
         const uint32_t rec = srec[sid];
         int r = (int)(rec & 1023), c = (int)((rec >> 10) & 1023), d = (int)((rec >> 20) & 3), kind;
-        const int steps = (int)(wlenk[sid] & 0x0FFFFFFFu);
-        wstart[sid] = off;
+        const uint32_t y = wrec[sid].y;
+        const int steps = (int)(y & 0xFFFFu), wk = (int)((y >> 16) & 15u);
+        unsigned kunus = 0xFFFF;
+        const uint32_t w_off = off;
+        whoff[sid] = hoff;
         for (int k = 0; k <= steps; k++) {
-            if (off < (uint32_t)b.wlist_stride) wlist[off] = (uint16_t)(ridx[r * W + c] * 4 + d);
+            const int cell = r * W + c;
+            const unsigned ri = ridx[cell];
+            if (off < (uint32_t)b.wlist_stride) wlist[off] = (uint16_t)(ri * 4 + d);
             off++;
+            if (k < steps && kunus == 0xFFFF && ((srec[ri * 4 + d] >> 26) & 1u)) kunus = (unsigned)k;
+            const int ts = target_slot_at(b, e, s_tbits, cell, W);
+            if (ts >= 0) { if (hoff < (uint32_t)b.whits_stride) whits[hoff] = (uint32_t)k | ((uint32_t)ts << 16); hoff++; }
             if (k < steps) static_succ(g, H, W, r, c, d, kind);
         }
         // children of the node this walk ends in, from its last state (r, c, d)
-        const int wk = (int)(wlenk[sid] >> 28), enb = nibble(g[r * W + c], d);
+        const int enb = nibble(g[r * W + c], d);
+        unsigned ch[3];
         for (int a2 = -1; a2 <= 1; a2++) {
             const int bd = (d + a2) & 3, rb = (bd + 2) & 3;
             int cd = -1;
@@ -169,15 +229,15 @@ __global__ void __launch_bounds__(NT) k_walks(FlBatch b) {
                 const int rr = r + d_row(cd), cc = c + d_col(cd);
                 if (rr >= 0 && cc >= 0 && rr < H && cc < W && ridx[rr * W + cc] != 0xFFFF) cs = ridx[rr * W + cc] * 4u + (unsigned)cd;
             }
-            wchild[sid * 4 + a2 + 1] = (uint16_t)cs;
+            ch[a2 + 1] = cs;
         }
-        wchild[sid * 4 + 3] = 0xFFFF;
+        wrec[sid] = make_uint4(w_off, y, ch[0] | (ch[1] << 16), ch[2] | (kunus << 16));
     }
     for (int sid = S + tid; sid < (int)b.state_stride; sid += NT) {
-        srec[sid] = 0; wstart[sid] = 0; wlenk[sid] = 0;
-        for (int j = 0; j < 4; j++) wchild[sid * 4 + j] = 0xFFFF;
+        srec[sid] = 0; whoff[sid] = 0;
+        wrec[sid] = make_uint4(0u, 0u, 0xFFFFFFFFu, 0xFFFFFFFFu);
     }
-    if (tid == 0) { tot[0] = S; tot[1] = (int)total; }
+    if (tid == 0) { tot[0] = S; tot[1] = (int)total; tot[2] = (int)total_h; tot[3] = 0; }
 }
 
 }  // namespace

@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define FL_ABI_VERSION 1
+#define FL_ABI_VERSION 2
 
 /* fixed by the reference (solution/impl_config.py:4-21, flatland_cutils/src/tool.h:67-93) */
 #define FL_MAX_NODES 31     /* num_tree_obs_nodes = 1 + 3*10 */
@@ -66,9 +66,9 @@ typedef struct FlBatch {
                             >= n_slots*H*W*4, multiple of 8 (16-byte aligned blocks: moved by TMA bulk copies) */
     int64_t *debug_clocks; /* tuning only: [E][16] SM-clock timestamps of k_observe's phases, NULL = off */
     int64_t ridx_stride;   /* uint16 elements per env of ridx, >= H*W, multiple of 8 */
-    int64_t state_stride;  /* elements per env of srec / wstart / wlenk, >= 4 * rail cells, multiple of 4 */
+    int64_t state_stride;  /* elements per env of srec / wrec / whoff / kcls, >= 4 * rail cells, multiple of 8 */
     int64_t wlist_stride;  /* uint16 elements per env of wlist, multiple of 8 */
-    int64_t reserved1;
+    int64_t whits_stride;  /* uint32 elements per env of whits, multiple of 4 */
 
     /* ---- world, static after upload (RailEnv.reset generators stay reference Python) ---- */
     const uint16_t *grid;      /* [E][grid_stride] transition bitmask per cell (core/transition_map.py:144) */
@@ -88,11 +88,15 @@ typedef struct FlBatch {
      * walk from a (cell, direction) state visits (treeobs.cpp:258-610 _explore_branch, rail-only part) */
     uint16_t *ridx;            /* [E][ridx_stride] rail index per cell, 0xFFFF = no rail; state id = 4*ridx + dir */
     uint32_t *srec;            /* [E][state_stride] row | col<<10 | dir<<20 | transitions nibble<<22 | unusable switch<<26 */
-    uint32_t *wstart;          /* [E][state_stride] offset of the state's walk in wlist */
-    uint32_t *wlenk;           /* [E][state_stride] steps of the walk | kind<<28 (1 switch, 2 dead end, 3 cycle, 0 bad cell) */
+    uint32_t *wrec;            /* [E][state_stride][4] per walk: offset in wlist; steps | kind<<16 | target hits<<20
+                                  (kind 1 switch, 2 dead end, 3 cycle, 0 bad cell); child0 | child1<<16;
+                                  child2 | first unusable-switch step<<16 (0xFFFF = null / none).  16-byte aligned. */
+    uint32_t *whoff;           /* [E][state_stride] offset of the walk's target hits in whits */
     uint16_t *wlist;           /* [E][wlist_stride] visited state ids, walk after walk */
-    uint16_t *wchild;          /* [E][state_stride][4] start states of the three children of the node a walk ends in, 0xFFFF = null */
-    int32_t *walk_total;       /* [E][4] written by fl_walk_tables: states, wlist elements needed, 0, 0 */
+    uint32_t *whits;           /* [E][whits_stride] step | slot<<16 of every walk state standing on a slot's target */
+    uint16_t *kcls;            /* [E][state_stride] per rail cell: lowest rail index among the cells sharing the reference's
+                                  prediction key c*W + r (only cells of grids with H > W have partners) */
+    int32_t *walk_total;       /* [E][4] written by fl_walk_tables: states, wlist elements, whits elements, 0 */
 
     /* ---- agent state (agent_utils.py:58-105 and step_utils/*) ---- */
     int16_t *rc;          /* [E][N][2] position, (-1,-1) = None */
@@ -114,18 +118,12 @@ typedef struct FlBatch {
     int32_t *sched_pos;   /* [E] schedule rows consumed so far */
     uint8_t *done_all;    /* [E] dones["__all__"] */
     uint32_t *status;     /* [E] FL_ST_* bits, sticky until cleared by the caller */
-    uint32_t *cellinfo;   /* [E][H*W] occupancy map rebuilt by fl_observe, 0 = empty cell, else
-                                       bits 31..21 highest handle on the cell + 1, 20..11 number of off-map
-                                       agents whose initial cell this is, 10..9 direction, 8 malfunctioning.
-                                       Only touched when the map does not fit in shared memory (large grids). */
-    int32_t *occ_cell;    /* [E][N] cell each agent was entered under in cellinfo, -1 = none (same) */
     int64_t *stats;       /* [E][4] running totals since upload: episodes finished, agents arrived at episode
                                     end, sum of end-of-episode rewards, agent-steps (eval_env.py:81-94 final_metric) */
 
     /* ---- per-step observation workspace (rebuilt by every fl_observe) ---- */
-    uint32_t *key_start;  /* [E][W*W + H + 1] CSR end offsets of predicted-occupancy entries per cell id c*W+r
-                                       (spill space: used only when the index does not fit in shared memory) */
-    uint64_t *entries;    /* [E][ent_cap] predicted-occupancy intervals sorted by cell id (spill space) */
+    uint32_t *entries;    /* [E][ent_cap] predicted-occupancy entries grouped by rail cell (spill space: used only
+                                       when an environment's entries do not fit in shared memory) */
 } FlBatch;
 
 int fl_abi_version(void);
@@ -138,7 +136,7 @@ int fl_distance_map(const FlBatch *b, void *stream);
 
 /* Builds the static branch-walk tables of every environment (reset time, after the grid upload).  Two
  * passes: fill == 0 only writes walk_total (ridx and walk_total must be allocated) so that the caller can
- * size srec / wstart / wlenk / wlist; fill != 0 writes all tables.  No reference counterpart: the reference
+ * size srec / wrec / whoff / wlist / whits; fill != 0 writes all tables.  No reference counterpart: the reference
  * re-walks the rail cell by cell in every _explore_branch call (treeobs.cpp:258-610). */
 int fl_walk_tables(const FlBatch *b, int fill, void *stream);
 
@@ -166,8 +164,8 @@ int fl_observe(const FlBatch *b, float *d_agent_attr, float *d_forest, int32_t *
 
 /* Diagnostics: the shared-memory plan fl_observe uses for this batch.  out[0..19] = threads per CTA, dynamic
  * shared bytes, tree tile (agents), entry capacity, unsorted-entry capacity, byte offsets of grid, occupancy,
- * key counters, entries, distance maps, ridx, srec, wstart, wlenk, wlist (-1 = stays in global memory),
- * agents, deadlock scratch, tree tile, CTAs per SM that fit, lanes per walk group. */
+ * bucket offsets, entries, distance maps, ridx, srec, wrec, whoff, wlist (-1 = stays in global memory),
+ * agents, deadlock scratch, node table, CTAs per SM that fit, whits. */
 int fl_observe_plan(const FlBatch *b, int32_t *out, int n_out);
 
 /* A view of environments [e0, e0+n) of a batch: every pointer advanced by e0 environments, E = n.  The view

@@ -10,7 +10,7 @@ fi
 : > gpurun_out/sweep.txt
 for cfg in ${CONFIGS:-Test_03}; do
 for g in ${GS:-8}; do for nt in ${NTS:-64 128 256}; do for c in ${CTAS:-2 3 4 5 6}; do
-  FL_OBS_G=$g FL_OBS_NT=$nt FL_OBS_CTAS=$c timeout 300 python bench.py --config $cfg --steps 60 --warmup 5 --no-cpu --e2e-steps 3 --profile-steps 20 > gpurun_out/sw.json 2> gpurun_out/sw.err
+  FL_OBS_NT=$nt FL_OBS_CTAS=$c timeout 300 python bench.py --config $cfg --steps 60 --warmup 5 --no-cpu --e2e-steps 3 --profile-steps 20 > gpurun_out/sw.json 2> gpurun_out/sw.err
   python - "$cfg" "g$g-nt$nt" "$c" >> gpurun_out/sweep.txt <<'PY'
 import json,sys
 try:

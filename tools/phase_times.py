@@ -29,7 +29,7 @@ for t in range(steps):
 d = np.stack(acc).astype(np.float64)          # [20, E, 16]
 t0 = d[..., 15]
 names = [("setup+zero", 15, 0), ("tma wait+loader+occupancy", 0, 1), ("prediction walks", 1, 2), ("scan+scatter+sort (+deadlock join)", 2, 3),
-         ("tile init/roots", 3, 4), ("tree walks", 4, 5), ("orders+adjacency", 5, 6), ("attributes", 6, 7)]
+         ("tree structure (4A)", 3, 4), ("node features (4B)", 4, 5), ("attributes", 6, 7)]
 tot = d[..., 7] - t0
 print("%s E=%d N=%d: mean cycles per env %.0f (p50 %.0f, p99 %.0f, max %.0f)" % (cfg, E, N, tot.mean(), np.median(tot), np.percentile(tot, 99), tot.max()))
 for nm, a, b in names:
@@ -37,5 +37,4 @@ for nm, a, b in names:
     print("  %-40s mean %9.0f  p99 %9.0f  (%.1f%%)" % (nm, x.mean(), np.percentile(x, 99), 100 * x.mean() / tot.mean()))
 dl = d[..., 8] - d[..., 1]
 print("  %-40s mean %9.0f  p99 %9.0f" % ("deadlock lane (from occupancy done)", dl.mean(), np.percentile(dl, 99)))
-print("  tree-loop iterations of warp 0: mean %.0f p99 %.0f max %.0f; entries per env: mean %.0f max %.0f" %
-      (d[..., 9].mean(), np.percentile(d[..., 9], 99), d[..., 9].max(), d[..., 10].mean(), d[..., 10].max()))
+print("  entries per env: mean %.0f max %.0f" % (d[..., 10].mean(), d[..., 10].max()))
