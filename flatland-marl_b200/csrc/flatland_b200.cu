@@ -88,42 +88,34 @@ constexpr int SMEM_MAX = 227 * 1024;
 int align_up(int v, int a) { return (v + a - 1) / a * a; }
 
 // Shared-memory plan of k_observe for one configuration.  Mandatory: barrier + scalars, scan partials, the
-// per-agent records, the deadlock scratch, the node table of a tile of agents (which doubles as the unsorted-entry
-// buffer), the occupancy word and the bucket offsets per rail cell.  Optional, in this order while they fit: rail
-// grid, rail index, the sorted predicted-occupancy entries ("core"), the static walk tables, and last the distance
-// maps.  The budget per CTA is the largest that still lets `ctas` CTAs share an SM: the largest ctas >= min_ctas
-// for which core + walk tables fit, else the largest ctas for which the core fits.  FL_OBS_CTAS / FL_OBS_TABLES /
-// FL_OBS_NT override (tuning only).
+// per-agent records, the deadlock scratch, the occupancy word and the bucket offsets per rail cell (and the key
+// classes when H > W).  Then, while they fit: rail grid, rail index, the sorted predicted-occupancy entries at their
+// typical size ("core").  The budget per CTA is the largest that lets `ctas` CTAs share an SM, ctas being the largest
+// count for which the core fits (more resident warps hide the latency of the table lookups, which then go to L2).
+// What is left of the budget takes the static walk tables in the order of their use per visited cell.
+// FL_OBS_CTAS / FL_OBS_TABLES / FL_OBS_NT override (tuning only).
 ObsLayout make_obs_layout(const FlBatch *b, int nt, int *ctas_out = nullptr) {
     const int N = (int)b->N, Rmax = (int)(b->state_stride / 4);
     ObsLayout L;
-    L.tile = N < OBS_MAX_TILE ? N : OBS_MAX_TILE;
     int off = 0;
     auto take = [&](long long bytes) { const int o = off; off = align_up(off + (int)bytes, 128); return o; };
     L.bar = take(32);
     L.part = take(nt * 4);
-    L.ag = take(14 * N * 4);
+    L.ag = take((long long)OBS_AGENT_WORDS * N * 4);
     L.dl = take(18 * N);
-    const long long ent_typ = (long long)N * 56 * 4;
-    long long nodes_b = (long long)L.tile * OBS_NODE_BYTES;
-    if (nodes_b < ent_typ / 4 * 6) nodes_b = ent_typ / 4 * 6;        // also holds the unsorted entries (6 bytes each)
-    L.nodes = take(nodes_b);
-    L.nodes_bytes = (int)nodes_b;
-    L.tmp_cap = (int)(nodes_b / 6);
     L.ci = take((long long)Rmax * 4);
     L.ks = take((long long)(Rmax + 2) * 4);
     L.kcls = b->H > b->W ? take(b->state_stride * 2) : -1;      // key classes of the reference's c*W + r (walks.cuh)
-    const long long grid_b = b->grid_stride * 2, ridx_b = b->ridx_stride * 2, dist_b = b->dist_stride * 2;
+    const long long ent_typ = (long long)N * 56 * 4;
+    const long long grid_b = b->grid_stride * 2, ridx_b = b->ridx_stride * 2;
     const long long st_b = b->state_stride * 4, wl_b = b->wlist_stride * 2, wh_b = b->whits_stride * 4;
-    const long long core = off + grid_b + ridx_b + ent_typ + 4 * 128, tables = 6 * st_b + wl_b + wh_b + 6 * 128;
-    bool want_tables = true;
-    if (const char *s = getenv("FL_OBS_TABLES")) want_tables = atoi(s) != 0;
-    const int max_ctas = nt == 256 ? 4 : nt == 128 ? 8 : 12, min_ctas = nt == 256 ? 2 : 3;
+    const long long sd_b = b->n_slots * b->state_stride * 2;
+    const long long core = off + grid_b + ridx_b + ent_typ + 4 * 128;
+    int want_tables = 0x3F;                                     // bit k: wlist, wrec, sdist, srec, whoff, whits
+    if (const char *s = getenv("FL_OBS_TABLES")) want_tables = atoi(s);
+    const int max_ctas = nt == 256 ? 4 : nt == 128 ? 8 : 12;
     int ctas = 0;
     if (const char *s = getenv("FL_OBS_CTAS")) ctas = atoi(s) > 0 ? atoi(s) : 1;
-    if (!ctas && want_tables)
-        for (int c = max_ctas; c >= min_ctas; c--)
-            if (core + tables <= SMEM_MAX / c - 1024) { ctas = c; break; }
     if (!ctas)
         for (int c = max_ctas; c >= 1; c--)
             if (core <= SMEM_MAX / c - 1024 || c == 1) { ctas = c; break; }
@@ -132,21 +124,24 @@ ObsLayout make_obs_layout(const FlBatch *b, int nt, int *ctas_out = nullptr) {
     auto opt = [&](long long bytes) { if ((long long)off + bytes + 128 > budget) return -1; return take(bytes); };
     L.grid = opt(grid_b);
     L.ridx = opt(ridx_b);
-    const bool tables_fit = want_tables && (long long)off + ent_typ + tables + 128 <= budget;
-    L.srec = L.wrec = L.whoff = L.whits = L.wlist = -1;
-    if (tables_fit) {
-        L.wrec = take(4 * st_b); L.srec = take(st_b); L.whoff = take(st_b); L.whits = take(wh_b); L.wlist = take(wl_b);
-    }
-    // entries: at least the typical size, the rest of the budget when the distance maps do not fit anyway
+    long long reserve = ent_typ + 128;                           // keep room for the entries while placing the tables
+    auto table = [&](int bit, long long bytes) {
+        if (!((want_tables >> bit) & 1) || (long long)off + bytes + 128 + reserve > budget) return -1;
+        return take(bytes);
+    };
+    L.wlist = table(0, wl_b);
+    L.wrec = table(1, 4 * st_b);
+    L.sdist = table(2, sd_b);
+    L.srec = table(3, st_b);
+    L.whoff = table(4, st_b);
+    L.whits = table(5, wh_b);
+    // entries: at least the typical size, at most twice that (more is never needed; larger counts spill to global memory)
     long long ent_b = (long long)budget - off - 128;
-    const bool dist_fits = ent_b - ent_typ >= dist_b + 128;
-    if (dist_fits) ent_b -= dist_b + 128;
+    if (ent_b > 2 * ent_typ) ent_b = 2 * ent_typ;
     if (ent_b > (long long)N * NPRED * 4) ent_b = (long long)N * NPRED * 4;
-    if (ent_b > 2 * ent_typ && !dist_fits) ent_b = 2 * ent_typ;      // more than ever needed: leave the rest to the L1 cache
     if (ent_b < 0) ent_b = 0;
     L.ent = take(ent_b);
     L.ent_cap = (int)(ent_b / 4);
-    L.dist = dist_fits ? opt(dist_b) : -1;
     L.total = off;
     return L;
 }
@@ -228,7 +223,7 @@ int fl_distance_map(const FlBatch *b, void *stream) {
 int fl_walk_tables(const FlBatch *b, int fill, void *stream) {
     if (int rc = check_batch(b)) return rc;
     if (!b->ridx || !b->walk_total) return FL_ERR_BAD_ARG;
-    if (fill && (!b->srec || !b->wrec || !b->whoff || !b->wlist || !b->whits || !b->kcls || b->state_stride <= 0 || b->wlist_stride <= 0 ||
+    if (fill && (!b->srec || !b->wrec || !b->whoff || !b->wlist || !b->whits || !b->kcls || !b->sdist || !b->dist || b->state_stride <= 0 || b->wlist_stride <= 0 ||
                  b->whits_stride <= 0))
         return FL_ERR_BAD_ARG;
     cudaStream_t st = (cudaStream_t)stream;
@@ -271,7 +266,7 @@ int fl_observe(const FlBatch *b, float *d_agent_attr, float *d_forest, int32_t *
     if (int rc = check_batch(b)) return rc;
     if (!d_agent_attr || !d_forest || !d_adjacency || !d_node_order || !d_edge_order || !d_valid_actions || !d_dist_target)
         return FL_ERR_BAD_ARG;
-    if (!b->srec || !b->wrec || !b->whoff || !b->wlist || !b->whits || !b->kcls || !b->ridx || !b->walk_total) return FL_ERR_BAD_ARG;   // fl_walk_tables first
+    if (!b->srec || !b->wrec || !b->whoff || !b->wlist || !b->whits || !b->kcls || !b->sdist || !b->ridx || !b->walk_total) return FL_ERR_BAD_ARG;   // fl_walk_tables first
     cudaStream_t st = (cudaStream_t)stream;
     const int nt = obs_threads(b);
     int ctas = 1;
@@ -303,7 +298,7 @@ int fl_batch_slice(const FlBatch *b, int64_t e0, int64_t n, FlBatch *out) {
     FL_ADV(init_rc, N * 2) FL_ADV(tgt_rc, N * 2) FL_ADV(init_dir, N) FL_ADV(max_count, N) FL_ADV(slot, N) FL_ADV(speed, N)
     FL_ADV(earliest, N) FL_ADV(latest, N) FL_ADV(sched, b->S * N)
     FL_ADV(ridx, b->ridx_stride) FL_ADV(srec, b->state_stride) FL_ADV(wrec, b->state_stride * 4) FL_ADV(whoff, b->state_stride)
-    FL_ADV(wlist, b->wlist_stride) FL_ADV(whits, b->whits_stride) FL_ADV(kcls, b->state_stride) FL_ADV(walk_total, 4)
+    FL_ADV(wlist, b->wlist_stride) FL_ADV(whits, b->whits_stride) FL_ADV(kcls, b->state_stride) FL_ADV(sdist, b->n_slots * b->state_stride) FL_ADV(walk_total, 4)
     FL_ADV(rc, N * 2) FL_ADV(old_rc, N * 2) FL_ADV(dir, N) FL_ADV(old_dir, N) FL_ADV(state, N) FL_ADV(ctr, N) FL_ADV(mal, N)
     FL_ADV(saved, N) FL_ADV(sig_mal, N) FL_ADV(deadlocked, N) FL_ADV(done, N) FL_ADV(nmal, N) FL_ADV(arrival, N)
     FL_ADV(elapsed, 1) FL_ADV(sched_pos, 1) FL_ADV(done_all, 1) FL_ADV(status, 1)
@@ -336,8 +331,8 @@ int fl_observe_plan(const FlBatch *b, int32_t *out, int n_out) {
     const int nt = obs_threads(b);
     int ctas = 1;
     const ObsLayout L = make_obs_layout(b, nt, &ctas);
-    const int v[20] = {nt, L.total, L.tile, L.ent_cap, L.tmp_cap, L.grid, L.ci, L.ks, L.ent, L.dist,
-                       L.ridx, L.srec, L.wrec, L.whoff, L.wlist, L.ag, L.dl, L.nodes, SMEM_MAX / (L.total + 1024), L.whits};
+    const int v[20] = {nt, L.total, ctas, L.ent_cap, L.kcls, L.grid, L.ci, L.ks, L.ent, L.sdist,
+                       L.ridx, L.srec, L.wrec, L.whoff, L.wlist, L.ag, L.dl, L.part, SMEM_MAX / (L.total + 1024), L.whits};
     for (int k = 0; k < 20; k++) out[k] = v[k];
     return FL_OK;
 }

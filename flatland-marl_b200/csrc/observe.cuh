@@ -2,28 +2,28 @@
 // one environment per CTA, the per-environment working set staged in shared memory.
 //
 // Phases of one CTA (= one environment):
-//   0  stage the rail grid, the rail index and (as far as they fit) the static walk tables and distance maps into
-//      shared memory with 1-D TMA bulk copies (cp.async.bulk + mbarrier) while phase 1 reads the agents.
+//   0  stage the rail grid, the rail index and (as far as they fit) the static walk tables into shared memory
+//      with 1-D TMA bulk copies (cp.async.bulk + mbarrier) while phase 1 reads the agents.
 //   1  loader view per agent (loader.cpp:8-179, 221-327): virtual position, valid actions, distance to
-//      target, the occupancy word per RAIL CELL (treeobs.cpp:67-92) built with shared-memory atomics.
+//      target, the occupancy word per RAIL CELL (treeobs.cpp:67-92) built with shared-memory atomics, and the
+//      one-hot part of the attribute vector as three bit masks.
 //   2  the serial, sticky DeadlockChecker (deadlock_checker.cpp:11-110) on lane 0 of the last warp, running
-//      concurrently with phase 3 (its result is only needed by the attribute vector).
-//   3  greedy shortest-path predictions (predictions.cpp:13-235) as occupancy intervals, counting-sorted by
-//      rail cell into a CSR inverse index  rail cell -> intervals, every bucket ordered by start time so that
-//      the tree walk only scans the entries of a three-step time window.  (The reference keys positions by
-//      c * W + r, which makes distinct cells of a grid with H > W share predictions; kcls of walks.cuh maps a
-//      rail cell to its key class so that these false conflicts are reproduced.)
-//   4  the 31-node branch trees (treeobs.cpp:154-610), in two steps:
-//      A  STRUCTURE, one lane per agent: which walk every node stands for, where it ends and what its children
-//         are follows from the static walk tables alone (walks.cuh: steps, kind, children, the steps at which the
-//         walk crosses the target of a slot), so the lane runs the reference's FIFO over <= 31 nodes without
-//         touching a rail cell, and finishes with the evaluation orders (tool.h:468-524).
-//      B  FEATURES, one warp per agent: the cells of all walks of the agent form one flat list (about 130 cells);
-//         the warp takes it 32 cells at a time, one cell per lane — no idle lanes, no queue, no atomics.  The
-//         owner node of a cell follows from a ballot + a bit mask of segment starts; what the lanes find
-//         (trains, predicted conflicts) returns to the lane that owns the node as ballots masked by the node's
-//         segment.  Lane n then writes node n of the forest (three 16-byte stores) and the warp writes the
-//         agent's adjacency / order rows.
+//      concurrently with phases 3 and 4 (its result is only needed by the attribute vector).
+//   3  shortest-path predictions (predictions.cpp:13-235) as occupancy intervals, one lane per agent hopping
+//      from static walk to static walk (walks.cuh): a counting pass, a scan and a scatter pass build a CSR inverse
+//      index  rail cell -> intervals, every bucket ordered by start time so that the tree walk only scans the
+//      entries of a three-step time window.  (The reference keys positions by c * W + r, which makes distinct
+//      cells of a grid with H > W share predictions; kcls of walks.cuh maps a rail cell to its key class so
+//      that these false conflicts are reproduced.)
+//   4  the 31-node branch trees (treeobs.cpp:154-610), one warp per agent taken from a shared counter:
+//      STRUCTURE: node n of the tree lives in lane n.  Which walk a node stands for, where it ends and what its
+//        children are follows from the static walk records alone (steps, kind, children, the steps at which the walk
+//        crosses the target of a slot), so the reference's FIFO becomes one ballot + shuffle round per tree level.
+//      FEATURES: the cells of all walks of the agent form one flat list (about 130 cells); the warp takes it 32
+//        cells at a time, one cell per lane — no idle lanes, no queue, no atomics.  The owner node of a cell follows
+//        from a ballot + a bit mask of segment starts; what the lanes find (trains, predicted conflicts) returns
+//        to the lane that owns the node as ballots masked by the node's segment.  Lane n then writes node n of the
+//        forest (three 16-byte stores), its adjacency row and its evaluation orders (tool.h:468-524).
 //   5  the 83-float attribute vector (feature_parser.cpp:3-98), written with coalesced stores.
 // Arrays that do not fit in shared memory for a configuration (large grids) stay in global memory behind
 // the same generic pointers (ObsLayout offsets < 0).
@@ -33,12 +33,11 @@
 
 namespace {
 
-constexpr int OBS_MAX_TILE = 64;        // agents whose trees are built together (bounds the node table)
 constexpr int I_INF = 0x7fffffff;
 
 struct ObsLayout {   // byte offsets into dynamic shared memory (host: make_obs_layout); < 0 = lives in global memory
-    int bar, part, ag, dl, nodes, nodes_bytes, ci, ks, grid, ridx, ent, ent_cap, tmp_cap, dist, total, tile;
-    int srec, wrec, whoff, whits, wlist, kcls;   // static walk tables (walks.cuh)
+    int bar, part, ag, dl, ci, ks, kcls, grid, ridx, ent, ent_cap, total;
+    int srec, wrec, whoff, whits, wlist, sdist;   // static walk tables (walks.cuh)
 };
 
 // ---- mbarrier + 1-D TMA bulk copy (global -> shared), sm_90+ ------------------------------------
@@ -75,64 +74,59 @@ DEVI uint32_t ld_vol_u32(const uint32_t *p) { return *reinterpret_cast<const vol
 DEVI int ld_vol_i32(const int *p) { return *reinterpret_cast<const volatile int *>(p); }
 DEVI unsigned ld_vol_u16(const uint16_t *p) { return *reinterpret_cast<const volatile uint16_t *>(p); }
 
-// get_valid_move_actions_ (predictions.cpp:13-76), result in std::set order L,F,R
-DEVI int greedy_moves(unsigned cell, int d, int out_d[3]) {
-    const int nb = nibble(cell, d);
-    int k = 0;
-    if (__popc(cell) == 1) {                      // dead end: only way is back
-        const int ex = (d + 2) & 3;
-        if (tbit(nb, ex)) out_d[k++] = ex;
-        return k;
-    }
-#pragma unroll
-    for (int t = -1; t <= 1; t++) {
-        const int nd = (d + t) & 3;
-        if (tbit(nb, nd)) out_d[k++] = nd;
-    }
-    return k;
-}
-
-// Predicted occupancy of one agent as intervals per path element (predictions.cpp:78-235 + the
-// transpose in treeobs.cpp:50-65).  Path element k >= 1 is occupied for prediction rows
-// [1+(k-1)*tpc, k*tpc], the last element until row 500, element 0 for row 0 only (or all rows when
-// the path has a single element).  The reference stops advancing once the cell equals the target.
-// Emit(cell, t0, t1, dir_here, dir_prev, dir_next) is called once per occupied element (cell = r * W + c).
+DEVI uint32_t pack_entry(int agent, int t0, int t1, int dh, int dp, int dn);
+// Predicted occupancy of one agent (predictions.cpp:13-235 + the transpose in treeobs.cpp:50-65) from the static walk
+// tables.  The greedy descent of the distance map is forced inside a walk (one successor per state) and, because the
+// distance of a state is one more than the lowest distance among its successors, always continues at the end of a
+// walk into the child with the lowest distance, the first of equals in the order left, forward, right
+// (predictions.cpp:13-76) — unless the start state cannot reach the target at all, in which case the path is its first
+// element.  The path ends on the agent's target cell (a target hit of the walk) or after 500 moves.  Path element idx >= 1
+// is occupied for prediction rows [1 + (idx-1)*tpc, idx*tpc], the last element until row 500, element 0 for row 0 only
+// (or all rows when the path has a single element).  Emit(rail cell, entry) is called once per occupied element.
 template <class Emit>
-DEVI void walk_prediction(const uint16_t *g, const uint16_t *dm, int W, int vr, int vc, int dir, int tr, int tc,
-                          int tpc, Emit emit) {
-    int r = vr, c = vc, d = dir, k = 0;
-    unsigned best_dist = FL_DIST_INF;
-    int pr = r, pc = c, pd = d, ppd = d;          // pending (previous) element and the one before it
-    bool have_prev = false;
+DEVI void predict_path(const uint4 *wrec, const uint32_t *whoff, const uint32_t *whits, const uint16_t *wlist,
+                       const uint16_t *sd, unsigned sid, unsigned slot, int tpc, int agent, Emit emit) {
+    int dp = (int)(sid & 3u);                        // direction of the previous element (element 0: its own)
+    if (sd[sid] == FL_DIST_INF) {                    // no move lowers the distance: the path is its first element
+        // (a start state on the target has distance 0 and ends through the target hit below)
+        emit(sid >> 2, pack_entry(agent, 0, NPRED - 1, dp, dp, dp));
+        return;
+    }
+    int kk = 0;                                      // path element index of the walk's first state
     while (true) {
-        // element k = (r, c, d) is known here; emit element k-1 now that its successor is known
-        if (have_prev) {
-            const int kk = k - 1;
-            const int t0 = kk == 0 ? 0 : 1 + (kk - 1) * tpc;
-            const int t1 = kk == 0 ? 0 : kk * tpc;
-            if (t0 < NPRED) emit(pr * W + pc, t0, min(t1, NPRED - 1), pd, ppd, d);
-            else return;
-        }
-        bool last = (r == tr && c == tc) || k >= FL_PRED_DEPTH;   // at target, or 500 greedy steps done
-        int nr = r, nc = c, ndir = d;
-        if (!last) {
-            int md[3];
-            const int n = greedy_moves(g[r * W + c], d, md);
-            int best = -1;
-            for (int j = 0; j < n; j++) {
-                const int rr = r + d_row(md[j]), cc = c + d_col(md[j]);
-                const unsigned v = dm[((size_t)(rr * W + cc)) * 4 + md[j]];
-                if (v < best_dist) { best = j; best_dist = v; nr = rr; nc = cc; ndir = md[j]; }
+        const uint4 w = wrec[sid];
+        const int L = (int)(w.y & 0xFFFFu), kind = (int)((w.y >> 16) & 15u), nh = (int)((w.y >> 20) & 255u);
+        int kend = L;
+        bool hit = false;
+        if (nh) {
+            const uint32_t ho = whoff[sid];
+            for (int q = 0; q < nh; q++) {
+                const uint32_t hv = whits[ho + q];
+                if ((hv >> 16) == slot) { kend = (int)(hv & 0xFFFFu); hit = true; break; }
             }
-            if (best < 0) last = true;             // rail disconnected: path ends here
         }
-        if (last) {
-            const int t0 = k == 0 ? 0 : 1 + (k - 1) * tpc;
-            if (t0 < NPRED) emit(r * W + c, t0, NPRED - 1, d, pd, d);
-            return;
+        unsigned nxt = 0xFFFFu;                      // where the path continues after this walk
+        if (!hit && (kind == WK_SWITCH || kind == WK_DEADEND)) {
+            const unsigned ch[3] = {w.z & 0xFFFFu, w.z >> 16, w.w & 0xFFFFu};
+            unsigned best = FL_DIST_INF;
+#pragma unroll
+            for (int j = 0; j < 3; j++)
+                if (ch[j] != 0xFFFFu) { const unsigned v = sd[ch[j]]; if (v < best) { best = v; nxt = ch[j]; } }
         }
-        ppd = pd; pr = r; pc = c; pd = d; have_prev = true;
-        r = nr; c = nc; d = ndir; k++;
+        unsigned s = wlist[w.x];
+        for (int k = 0; k <= kend; k++) {
+            const int idx = kk + k;
+            const int t0 = idx ? 1 + (idx - 1) * tpc : 0;
+            if (t0 >= NPRED) return;
+            const bool last = (k == kend && (hit || nxt == 0xFFFFu)) || idx >= FL_PRED_DEPTH;
+            const unsigned sn = k < kend ? (unsigned)wlist[w.x + k + 1] : nxt;
+            const int d = (int)(s & 3u), dn = last ? d : (int)(sn & 3u);
+            const int t1 = last ? NPRED - 1 : min(idx ? idx * tpc : 0, NPRED - 1);
+            emit(s >> 2, pack_entry(agent, t0, t1, d, dp, dn));
+            if (last) return;
+            dp = d; s = sn;
+        }
+        sid = nxt; kk += kend + 1;
     }
 }
 
@@ -293,9 +287,10 @@ DEVI void store_null_node(float *forest_node) {
 }
 
 // per-agent shared-memory record (struct of arrays, N entries each)
+constexpr int OBS_AGENT_WORDS = 16;
 struct ObsAgents {
     uint32_t *vrc;      // virtual position r | c << 16 (loader.cpp:87-101)
-    uint32_t *tgt;      // target r | c << 16
+    uint32_t *sid0;     // state id of the virtual position and direction (walks.cuh), 0xFFFF = not on a rail cell
     uint32_t *info;     // dir | st << 2 | done << 5 | slot << 8 | tpc << 24
     float *speed;       // (float)speed
     float *dt;          // dist_target, INFINITY = unreachable
@@ -303,18 +298,9 @@ struct ObsAgents {
     int *initcell;      // initial cell index while off map, -1 otherwise
     uint32_t *rec_a;    // st | road << 3 | idir << 7 | od << 9 | ctr << 11 | maxc << 19 | va << 27
     uint32_t *rec_b;    // trans | nmal01 << 16 | mal01 << 17 | sig_mal << 18
-    float *f_earliest, *f_latest, *f_arrival, *f_dist, *f_idist;
+    uint32_t *m0, *m1;  // attribute entries 0..63 as bits (feature_parser.cpp:19-77), entry 41 (deadlocked) left out
+    float *f_earliest, *f_latest, *f_arrival, *f_dist;   // (f_idist follows as the 16th array)
 };
-
-// node table of a tile of agents, written by phase 4A (one lane per agent), read by phase 4B (one warp per agent)
-struct ObsNodes {
-    uint32_t *n_a;      // [tile][31] tot0 (distance walked before the node's branch starts) | kind << 20 | parent << 23 |
-                        //            (action direction + 1) << 28 | null << 30; kind 1 switch, 2 dead end, 3 cycle / bad cell, 4 target
-    uint32_t *n_sk;     // [tile][31] start state id of the node's walk (0xFFFF = null) | step the walk ends on << 16
-    int8_t *norder;     // [tile][32] node_order (tool.h:468-524), -2 = padding row
-    int *count;         // [tile] nodes created (rows >= count are padding)
-};
-constexpr int OBS_NODE_BYTES = 31 * 8 + 32 + 4;   // per agent of a tile
 
 DEVI unsigned warp_excl_scan(unsigned v, int lane, unsigned &total) {
     unsigned x = v;
@@ -333,28 +319,29 @@ __global__ void __launch_bounds__(NT, RES)
 k_observe(FlBatch b, ObsLayout lay, float *__restrict__ out_attr, float *__restrict__ out_forest,
           int32_t *__restrict__ out_adj, int32_t *__restrict__ out_norder, int32_t *__restrict__ out_eorder,
           uint8_t *__restrict__ out_valid, float *__restrict__ out_dist_target) {
-    const int e = blockIdx.x, N = (int)b.N, H = (int)b.H, W = (int)b.W, HW = H * W;
+    const int e = blockIdx.x, N = (int)b.N, H = (int)b.H, W = (int)b.W;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     extern __shared__ __align__(128) unsigned char obs_smem[];
     unsigned char *const smraw = obs_smem;
     const int R = b.walk_total[(size_t)e * 4] >> 2;         // rail cells of this environment
+    const int SS = (int)b.state_stride;
 
     // ---- pointers: shared-memory copy when the layout has room, global memory otherwise ---------
     const uint16_t *g_grid = b.grid + (size_t)e * b.grid_stride;
-    const uint16_t *g_dist = b.dist + (size_t)e * b.dist_stride;
     const uint16_t *g_ridx = b.ridx + (size_t)e * b.ridx_stride;
-    const uint32_t *g_srec = b.srec + (size_t)e * b.state_stride, *g_whoff = b.whoff + (size_t)e * b.state_stride;
-    const uint4 *g_wrec = reinterpret_cast<const uint4 *>(b.wrec) + (size_t)e * b.state_stride;
+    const uint32_t *g_srec = b.srec + (size_t)e * SS, *g_whoff = b.whoff + (size_t)e * SS;
+    const uint4 *g_wrec = reinterpret_cast<const uint4 *>(b.wrec) + (size_t)e * SS;
     const uint16_t *g_wlist = b.wlist + (size_t)e * b.wlist_stride;
     const uint32_t *g_whits = b.whits + (size_t)e * b.whits_stride;
+    const uint16_t *g_sdist = b.sdist + (size_t)e * b.n_slots * SS;
     const uint16_t *grid = lay.grid >= 0 ? reinterpret_cast<const uint16_t *>(smraw + lay.grid) : g_grid;
-    const uint16_t *dist = lay.dist >= 0 ? reinterpret_cast<const uint16_t *>(smraw + lay.dist) : g_dist;
     const uint16_t *ridx = lay.ridx >= 0 ? reinterpret_cast<const uint16_t *>(smraw + lay.ridx) : g_ridx;
     const uint32_t *srec = lay.srec >= 0 ? reinterpret_cast<const uint32_t *>(smraw + lay.srec) : g_srec;
     const uint4 *wrec = lay.wrec >= 0 ? reinterpret_cast<const uint4 *>(smraw + lay.wrec) : g_wrec;
     const uint32_t *whoff = lay.whoff >= 0 ? reinterpret_cast<const uint32_t *>(smraw + lay.whoff) : g_whoff;
     const uint32_t *whits = lay.whits >= 0 ? reinterpret_cast<const uint32_t *>(smraw + lay.whits) : g_whits;
     const uint16_t *wlist = lay.wlist >= 0 ? reinterpret_cast<const uint16_t *>(smraw + lay.wlist) : g_wlist;
+    const uint16_t *sdist = lay.sdist >= 0 ? reinterpret_cast<const uint16_t *>(smraw + lay.sdist) : g_sdist;
     const uint16_t *kcls = lay.kcls >= 0 ? reinterpret_cast<const uint16_t *>(smraw + lay.kcls) : nullptr;   // only when H > W
     uint32_t *ci = reinterpret_cast<uint32_t *>(smraw + lay.ci);             // [R] occupancy word per rail cell
     uint32_t *ks = reinterpret_cast<uint32_t *>(smraw + lay.ks) + 1;         // ks[-1..R]: bucket r = [ks[r-1], ks[r])
@@ -363,15 +350,16 @@ k_observe(FlBatch b, ObsLayout lay, float *__restrict__ out_attr, float *__restr
     int *s_misc = reinterpret_cast<int *>(smraw + lay.bar + 16);
 
     ObsAgents A;
+    float *f_idist;
     {
         uint32_t *p = reinterpret_cast<uint32_t *>(smraw + lay.ag);
-        A.vrc = p; p += N; A.tgt = p; p += N; A.info = p; p += N;
+        A.vrc = p; p += N; A.sid0 = p; p += N; A.info = p; p += N;
         A.speed = reinterpret_cast<float *>(p); p += N; A.dt = reinterpret_cast<float *>(p); p += N;
         A.cellid = reinterpret_cast<int *>(p); p += N; A.initcell = reinterpret_cast<int *>(p); p += N;
-        A.rec_a = p; p += N; A.rec_b = p; p += N;
+        A.rec_a = p; p += N; A.rec_b = p; p += N; A.m0 = p; p += N; A.m1 = p; p += N;
         A.f_earliest = reinterpret_cast<float *>(p); p += N; A.f_latest = reinterpret_cast<float *>(p); p += N;
         A.f_arrival = reinterpret_cast<float *>(p); p += N; A.f_dist = reinterpret_cast<float *>(p); p += N;
-        A.f_idist = reinterpret_cast<float *>(p); p += N;
+        f_idist = reinterpret_cast<float *>(p);     // 16th array
     }
     DeadlockScratch D;
     {
@@ -381,42 +369,34 @@ k_observe(FlBatch b, ObsLayout lay, float *__restrict__ out_attr, float *__restr
         D.checked = q; q += N; D.ndep = q; q += N; D.dl = q; q += N; D.ct = q; q += N; D.stk_d = q; q += N; D.stk_phase = q;
         D.cellid = A.cellid;
     }
-    const int OBS_TILE = lay.tile;
-    ObsNodes T;
-    {
-        uint32_t *p = reinterpret_cast<uint32_t *>(smraw + lay.nodes);
-        T.n_a = p; p += OBS_TILE * 31; T.n_sk = p; p += OBS_TILE * 31;
-        T.count = reinterpret_cast<int *>(p); p += OBS_TILE;
-        T.norder = reinterpret_cast<int8_t *>(p);
-    }
 
     // optional phase timestamps (tuning only): FlBatch.debug_clocks [E][16] int64, NULL = off
     int64_t *dbg = b.debug_clocks ? b.debug_clocks + (size_t)e * 16 : nullptr;
 #define OBS_TICK(k) do { if (dbg && tid == 0) dbg[k] = clock64(); } while (0)
     if (dbg && tid == 0) dbg[15] = clock64();
     // ---- phase 0: TMA bulk copies of the static world ---------------------------------------------
-    const bool use_tma = lay.grid >= 0 || lay.dist >= 0 || lay.ridx >= 0 || lay.srec >= 0 || lay.wrec >= 0 || lay.whoff >= 0 ||
-                         lay.whits >= 0 || lay.wlist >= 0 || lay.kcls >= 0;
+    const bool use_tma = lay.grid >= 0 || lay.ridx >= 0 || lay.srec >= 0 || lay.wrec >= 0 || lay.whoff >= 0 || lay.whits >= 0 ||
+                         lay.wlist >= 0 || lay.kcls >= 0 || lay.sdist >= 0;
     if (use_tma && tid == 0) {
         mbar_init(bar, 1);
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         const uint32_t gb = lay.grid >= 0 ? (uint32_t)(b.grid_stride * 2) : 0u;
-        const uint32_t db = lay.dist >= 0 ? (uint32_t)(b.dist_stride * 2) : 0u;
         const uint32_t rb = lay.ridx >= 0 ? (uint32_t)(b.ridx_stride * 2) : 0u;
-        const uint32_t sb = (uint32_t)(b.state_stride * 4);
+        const uint32_t sb = (uint32_t)(SS * 4);
         const uint32_t lb = lay.wlist >= 0 ? (uint32_t)(b.wlist_stride * 2) : 0u;
         const uint32_t hb = lay.whits >= 0 ? (uint32_t)(b.whits_stride * 4) : 0u;
-        const uint32_t kb = lay.kcls >= 0 ? (uint32_t)(b.state_stride * 2) : 0u;
-        mbar_expect_tx(bar, gb + db + rb + lb + hb + kb + (lay.srec >= 0 ? sb : 0u) + (lay.wrec >= 0 ? 4 * sb : 0u) + (lay.whoff >= 0 ? sb : 0u));
+        const uint32_t kb = lay.kcls >= 0 ? (uint32_t)(SS * 2) : 0u;
+        const uint32_t db = lay.sdist >= 0 ? (uint32_t)(b.n_slots * SS * 2) : 0u;
+        mbar_expect_tx(bar, gb + rb + lb + hb + kb + db + (lay.srec >= 0 ? sb : 0u) + (lay.wrec >= 0 ? 4 * sb : 0u) + (lay.whoff >= 0 ? sb : 0u));
         if (gb) tma_load_1d(smraw + lay.grid, g_grid, gb, bar);
         if (rb) tma_load_1d(smraw + lay.ridx, g_ridx, rb, bar);
-        if (lay.srec >= 0) tma_load_1d(smraw + lay.srec, g_srec, sb, bar);
+        if (kb) tma_load_1d(smraw + lay.kcls, b.kcls + (size_t)e * SS, kb, bar);
+        if (db) tma_load_1d(smraw + lay.sdist, g_sdist, db, bar);
         if (lay.wrec >= 0) tma_load_1d(smraw + lay.wrec, g_wrec, 4 * sb, bar);
+        if (lay.srec >= 0) tma_load_1d(smraw + lay.srec, g_srec, sb, bar);
         if (lay.whoff >= 0) tma_load_1d(smraw + lay.whoff, g_whoff, sb, bar);
         if (hb) tma_load_1d(smraw + lay.whits, g_whits, hb, bar);
-        if (kb) tma_load_1d(smraw + lay.kcls, b.kcls + (size_t)e * b.state_stride, kb, bar);
         if (lb) tma_load_1d(smraw + lay.wlist, g_wlist, lb, bar);
-        if (db) tma_load_1d(smraw + lay.dist, g_dist, db, bar);
     }
     // zero the bucket counters and the occupancy words
     for (int k = tid; k <= R + 1; k += NT) ks[k - 1] = 0;
@@ -424,7 +404,7 @@ k_observe(FlBatch b, ObsLayout lay, float *__restrict__ out_attr, float *__restr
     const float T_ = (float)b.max_steps[e], Nf = (float)N;
     const Scale sc{T_, __frcp_rn(T_), Nf, __frcp_rn(Nf)};
     const int elapsed = b.elapsed[e];
-    if (tid < 4) s_misc[tid] = 0;                  // [0] entries, [1] unsorted entries written, [2] max time per cell, [3] bad cell met
+    if (tid < 4) s_misc[tid] = 0;                  // [0] entries, [1] next agent of phase 4, [2] max time per cell, [3] bad cell met
     __syncthreads();                               // mbarrier initialised, counters zeroed
     OBS_TICK(0);
     if (use_tma) mbar_wait(bar, 0);
@@ -442,9 +422,10 @@ k_observe(FlBatch b, ObsLayout lay, float *__restrict__ out_attr, float *__restr
         int vr, vc;
         if (off_map(st)) { vr = ip.x; vc = ip.y; } else if (on_map(st)) { vr = r; vc = c; } else { vr = tp.x; vc = tp.y; }
         const int tpc = (int)(1.0f / speed);                             // predictions.cpp:184
-        const uint16_t *dm = dist + (size_t)slot * HW * 4;
+        const uint16_t *sd = sdist + (size_t)slot * SS;
+        const unsigned vri = ridx[vr * W + vc], iri = ridx[ip.x * W + ip.y];
         A.vrc[i] = (uint32_t)(vr & 0xFFFF) | ((uint32_t)vc << 16);
-        A.tgt[i] = (uint32_t)(tp.x & 0xFFFF) | ((uint32_t)tp.y << 16);
+        A.sid0[i] = vri != 0xFFFFu ? vri * 4u + (uint32_t)d : 0xFFFFu;
         A.info[i] = (uint32_t)d | ((uint32_t)st << 2) | ((uint32_t)(st == DONE) << 5) | ((uint32_t)slot << 8) |
                     ((uint32_t)min(tpc, 255) << 24);
         A.speed[i] = speed;
@@ -456,29 +437,34 @@ k_observe(FlBatch b, ObsLayout lay, float *__restrict__ out_attr, float *__restr
         D.dl[i] = b.deadlocked[ea]; D.checked[i] = 0; D.ndep[i] = 0;
         const int va = valid_actions_of(grid, W, st, ctr, r, c, d);
         for (int k = 0; k < 5; k++) out_valid[ea * 5 + k] = (va >> k) & 1;
+        const unsigned idv = iri != 0xFFFFu ? sd[iri * 4u + idir] : FL_DIST_INF;
         float dt;                                                        // loader.cpp:163-179
         if (st == DONE) dt = 0.0f;
         else {
-            const unsigned dv = off_map(st) ? dm[((size_t)(ip.x * W + ip.y)) * 4 + idir] : dm[((size_t)(r * W + c)) * 4 + d];
+            const unsigned dv = off_map(st) ? idv : (vri != 0xFFFFu ? (unsigned)sd[vri * 4u + d] : FL_DIST_INF);
             dt = dv == FL_DIST_INF ? INFINITY : (float)dv;
         }
         out_dist_target[ea] = dt;
         A.dt[i] = dt;
         // attribute record (feature_parser.cpp:19-94)
         const int od_raw = b.old_dir[ea], od = od_raw == 255 ? d : od_raw;
-        const int road = r >= 0 ? road_type_of((int)grid[r * W + c]) : 0;
         const int trans_attr = r >= 0 ? (int)grid[r * W + c] : 0;
+        const int road = r >= 0 ? road_type_of(trans_attr) : 0;
+        const int nmal01 = b.nmal[ea] != 0, mal01 = b.mal[ea] != 0, sig_mal = b.sig_mal[ea] != 0;
         A.rec_a[i] = (uint32_t)st | ((uint32_t)road << 3) | ((uint32_t)idir << 7) | ((uint32_t)od << 9) |
                      ((uint32_t)ctr << 11) | ((uint32_t)maxc << 19) | ((uint32_t)va << 27);
-        A.rec_b[i] = (uint32_t)trans_attr | ((uint32_t)(b.nmal[ea] != 0) << 16) | ((uint32_t)(b.mal[ea] != 0) << 17) |
-                     ((uint32_t)(b.sig_mal[ea] != 0) << 18);
+        A.rec_b[i] = (uint32_t)trans_attr | ((uint32_t)nmal01 << 16) | ((uint32_t)mal01 << 17) | ((uint32_t)sig_mal << 18);
+        // entries 0..63 of the attribute vector are one-hot codes and flags: bit k of (m0, m1) = entry k
+        A.m0[i] = (1u << st) | (1u << (7 + road)) | (1u << (18 + nmal01)) | (1u << (28 + idir));
+        A.m1[i] = (1u << d) | (1u << (4 + od)) | ((uint32_t)(st == MOVING) << 8) | ((uint32_t)sig_mal << 10) | ((uint32_t)!mal01 << 11) |
+                  ((uint32_t)(ctr == 0) << 12) | ((uint32_t)(ctr == maxc) << 13) | ((uint32_t)(st == MALFUNCTION || st == MAL_OFF) << 14) |
+                  ((uint32_t)off_map(st) << 15) | ((uint32_t)on_map(st) << 16) | (__brev((unsigned)trans_attr) << 1);
         const float max_dist = (float)((H + W) * 8);
         A.f_earliest[i] = (float)b.earliest[ea] / T_;
         A.f_latest[i] = (float)b.latest[ea] / T_;
         A.f_arrival[i] = (float)b.arrival[ea] / T_;
         A.f_dist[i] = dt == INFINITY ? 8.0f : dt / max_dist;
-        const unsigned idv = dm[((size_t)(ip.x * W + ip.y)) * 4 + idir];
-        A.f_idist[i] = idv == FL_DIST_INF ? 8.0f : (float)idv / max_dist;
+        f_idist[i] = idv == FL_DIST_INF ? 8.0f : (float)idv / max_dist;
     }
     __syncthreads();
     // occupancy word per rail cell (treeobs.cpp:67-92, deadlock_checker.cpp:15-20): the HIGHEST handle standing on the
@@ -507,25 +493,19 @@ k_observe(FlBatch b, ObsLayout lay, float *__restrict__ out_attr, float *__restr
     const bool dl_warp = warp == NT / 32 - 1;
     constexpr int NW = NT - 32;                    // threads walking predictions
     uint32_t *ent = reinterpret_cast<uint32_t *>(smraw + lay.ent);
-    uint32_t *tmp_pay = reinterpret_cast<uint32_t *>(smraw + lay.nodes);         // unsorted entries, aliasing the node table
-    uint16_t *tmp_key = reinterpret_cast<uint16_t *>(tmp_pay + lay.tmp_cap);
     if (dl_warp) {
         if (lane == 0) { update_deadlocks(D, ci, ridx, N, H, W); if (dbg) dbg[8] = clock64(); }
         __syncwarp();
+        asm volatile("bar.sync 2, %0;" ::"r"(NT) : "memory");    // the prediction index is complete (the other warps only arrive)
+        if (s_misc[0] > lay.ent_cap) ent = b.entries + (size_t)e * b.ent_cap;
     } else {
-        for (int i = tid; i < N; i += NW) {        // one greedy walk per agent: count per rail cell, keep the entries unsorted
+        // counting pass: one predicted path per agent, count per rail cell (or key class)
+        for (int i = tid; i < N; i += NW) {
             const uint32_t info = A.info[i];
-            const int vr = (int)(short)(A.vrc[i] & 0xFFFF), vc = (int)(A.vrc[i] >> 16);
-            const int tr = (int)(short)(A.tgt[i] & 0xFFFF), tc = (int)(A.tgt[i] >> 16);
-            walk_prediction(grid, dist + (size_t)((info >> 8) & 0xFFFF) * HW * 4, W, vr, vc, (int)(info & 3), tr, tc,
-                            (int)(info >> 24), [&](int cell, int t0, int t1, int dh, int dp, int dn) {
-                                unsigned key = ridx[cell];
-                                if (key == 0xFFFFu) return;
-                                if (kcls) key = kcls[key];
-                                atomicAdd(&ks[key], 1u);
-                                const int pos = atomicAdd(&s_misc[1], 1);
-                                if (pos < lay.tmp_cap) { tmp_pay[pos] = pack_entry(i, t0, t1, dh, dp, dn); tmp_key[pos] = (uint16_t)key; }
-                            });
+            const unsigned slot = (info >> 8) & 0xFFFFu, s0 = A.sid0[i];
+            if (s0 == 0xFFFFu) continue;
+            predict_path(wrec, whoff, whits, wlist, sdist + (size_t)slot * SS, s0, slot, (int)(info >> 24), i,
+                         [&](unsigned rail, uint32_t) { atomicAdd(&ks[kcls ? (unsigned)kcls[rail] : rail], 1u); });
         }
         named_bar_sync(1, NW);
         OBS_TICK(2);
@@ -546,23 +526,14 @@ k_observe(FlBatch b, ObsLayout lay, float *__restrict__ out_attr, float *__restr
         named_bar_sync(1, NW);
         const int n_ent = (int)s_part[NW - 1];
         if (tid == 0) s_misc[0] = n_ent;
-        // scatter.  ks[key] is advanced to the END of its bucket; bucket r is [ks[r-1], ks[r]) afterwards (ks[-1] = 0).
-        if (n_ent <= lay.tmp_cap && n_ent <= lay.ent_cap) {
-            for (int j = tid; j < n_ent; j += NW) ent[atomicAdd(&ks[tmp_key[j]], 1u)] = tmp_pay[j];
-        } else {                                    // does not fit in shared memory: walk again, scatter into the global spill space
-            ent = b.entries + (size_t)e * b.ent_cap;
-            for (int i = tid; i < N; i += NW) {
-                const uint32_t info = A.info[i];
-                const int vr = (int)(short)(A.vrc[i] & 0xFFFF), vc = (int)(A.vrc[i] >> 16);
-                const int tr = (int)(short)(A.tgt[i] & 0xFFFF), tc = (int)(A.tgt[i] >> 16);
-                walk_prediction(grid, dist + (size_t)((info >> 8) & 0xFFFF) * HW * 4, W, vr, vc, (int)(info & 3), tr, tc,
-                                (int)(info >> 24), [&](int cell, int t0, int t1, int dh, int dp, int dn) {
-                                    unsigned key = ridx[cell];
-                                    if (key == 0xFFFFu) return;
-                                    if (kcls) key = kcls[key];
-                                    ent[atomicAdd(&ks[key], 1u)] = pack_entry(i, t0, t1, dh, dp, dn);
-                                });
-            }
+        if (n_ent > lay.ent_cap) ent = b.entries + (size_t)e * b.ent_cap;   // does not fit in shared memory: global spill space
+        // scatter pass.  ks[key] is advanced to the END of its bucket; bucket r is [ks[r-1], ks[r]) afterwards (ks[-1] = 0).
+        for (int i = tid; i < N; i += NW) {
+            const uint32_t info = A.info[i];
+            const unsigned slot = (info >> 8) & 0xFFFFu, s0 = A.sid0[i];
+            if (s0 == 0xFFFFu) continue;
+            predict_path(wrec, whoff, whits, wlist, sdist + (size_t)slot * SS, s0, slot, (int)(info >> 24), i,
+                         [&](unsigned rail, uint32_t en) { ent[atomicAdd(&ks[kcls ? (unsigned)kcls[rail] : rail], 1u)] = en; });
         }
         named_bar_sync(1, NW);
         // order every bucket: long-lived entries first, then by t0, so that the tree walk scans a time window only
@@ -575,44 +546,48 @@ k_observe(FlBatch b, ObsLayout lay, float *__restrict__ out_attr, float *__restr
                 ent[y + 1] = v;
             }
         }
+        named_bar_sync(1, NW);
+        asm volatile("bar.arrive 2, %0;" ::"r"(NT) : "memory");  // lets the deadlock warp join phase 4 when it is done
     }
-    __syncthreads();
     OBS_TICK(3);
     if (dbg && tid == 0) dbg[10] = s_misc[0];
-    if (dl_warp && !(s_misc[0] <= lay.tmp_cap && s_misc[0] <= lay.ent_cap)) ent = b.entries + (size_t)e * b.ent_cap;
-    const int tpc_max = s_misc[2];
-    for (int i = tid; i < N; i += NT) b.deadlocked[(size_t)e * N + i] = D.dl[i];
+    const int tpc_max = ld_vol_i32(&s_misc[2]);
 
-    // ---- phase 4: branch trees, OBS_TILE agents at a time -----------------------------------------
-    for (int a0 = 0; a0 < N; a0 += OBS_TILE) {
-        const int na = min(OBS_TILE, N - a0);
-        // ---- 4A: tree structure, one lane per agent (treeobs.cpp:171-256 FIFO, 583-608 children) ----
-        for (int la = tid; la < na; la += NT) {
-            const int i = a0 + la;
-            uint32_t *n_a = T.n_a + la * 31, *n_sk = T.n_sk + la * 31;
-            const uint32_t info = A.info[i];
-            const int vr = (int)(short)(A.vrc[i] & 0xFFFF), vc = (int)(A.vrc[i] >> 16), dir = (int)(info & 3);
-            const unsigned slot = (info >> 8) & 0xFFFFu;
+    // ---- phase 4: branch trees, one warp per agent, agents taken from a shared counter --------------------
+    while (true) {
+        int h = 0;
+        if (lane == 0) h = atomicAdd(&s_misc[1], 1);
+        h = __shfl_sync(0xFFFFFFFFu, h, 0);
+        if (h >= N) break;
+        const size_t ea = (size_t)e * N + h;
+        const uint32_t ainfo = A.info[h];
+        const unsigned slot = (ainfo >> 8) & 0xFFFFu;
+        const uint16_t *sd = sdist + (size_t)slot * SS;
+        const float tpc_f = (float)(1.0 / (double)A.speed[h]);                          // treeobs.cpp:304
+        const int n = lane;
+        // ---- structure: node n in lane n; one round per tree level (treeobs.cpp:171-256 FIFO, 583-608 children) ----
+        unsigned sid = 0xFFFFu, wx = 0, kunus = 0xFFFFu, c01 = 0xFFFFFFFFu, c2 = 0xFFFFu;
+        int tot0 = 0, kend = 0, kind = 0, parent = 0, ad = 0, level = 0, cb = 1;          // cb: index of the node's first child
+        if (n >= 1 && n <= 3) {                                                           // roots (treeobs.cpp:171-221)
+            const int vr = (int)(short)(A.vrc[h] & 0xFFFF), vc = (int)(A.vrc[h] >> 16), dir = (int)(ainfo & 3);
             const int nb = nibble(grid[vr * W + vc], dir);
             int orientation = dir;
             if (__popc(nb) == 1) orientation = first_dir(nb);
-            n_a[0] = 0; n_sk[0] = 0xFFFFu;
-            for (int ad = -1; ad <= 1; ad++) {                               // roots (treeobs.cpp:171-221)
-                const int bd = (orientation + ad) & 3, idx = 2 + ad;
-                const uint32_t csid = tbit(nb, bd) ? child_state(ridx, H, W, vr, vc, bd) : 0xFFFFFFFFu;
-                const bool real = csid != 0xFFFFFFFFu;
-                n_a[idx] = 1u | ((uint32_t)(ad + 1) << 28) | ((real ? 0u : 1u) << 30);
-                n_sk[idx] = csid & 0xFFFFu;
-            }
-            int count = 4;
-            bool bad = false;
-            for (int n = 1; n < count; n++) {
-                const uint32_t a = n_a[n];
-                if ((a >> 30) & 1u) continue;
-                const unsigned sid = n_sk[n] & 0xFFFFu;
+            ad = n - 2;
+            const int bd = (orientation + ad) & 3;
+            sid = (tbit(nb, bd) ? child_state(ridx, H, W, vr, vc, bd) : 0xFFFFFFFFu) & 0xFFFFu;
+            tot0 = 1; level = 1; cb = FL_MAX_NODES;
+        }
+        int count = 4, ls = 1, le = 4, cur = 1;
+        bool bad = false;
+        while (true) {
+            const bool real_l = n >= ls && n < le && sid != 0xFFFFu;
+            const unsigned lmask = __ballot_sync(0xFFFFFFFFu, real_l);
+            if (!lmask) break;
+            if (real_l) {
                 const uint4 w = wrec[sid];
                 const int L = (int)(w.y & 0xFFFFu), skind = (int)((w.y >> 16) & 15u), nh = (int)((w.y >> 20) & 255u);
-                int kend = L;
+                kend = L;
                 bool hit = false;
                 if (nh) {                                                    // the observer's own target ends the walk early
                     const uint32_t ho = whoff[sid];
@@ -621,217 +596,190 @@ k_observe(FlBatch b, ObsLayout lay, float *__restrict__ out_attr, float *__restr
                         if ((hv >> 16) == slot) { kend = (int)(hv & 0xFFFFu); hit = true; break; }
                     }
                 }
-                const int kind = hit ? 4 : (skind == WK_BAD ? 3 : skind);
+                kind = hit ? 4 : (skind == WK_BAD ? 3 : skind);
                 if (!hit && skind == WK_BAD) bad = true;                     // treeobs.cpp:527-535 throws
-                n_a[n] = a | ((uint32_t)kind << 20);
-                n_sk[n] = sid | ((uint32_t)kend << 16);
-                if (count < FL_MAX_NODES) {
-                    const uint32_t tot1 = (a & 0xFFFFFu) + (uint32_t)kend + 1u;
-                    const unsigned ch[3] = {w.z & 0xFFFFu, w.z >> 16, w.w & 0xFFFFu};
-#pragma unroll
-                    for (int j = 0; j < 3; j++) {
-                        const int cidx = count + j;
-                        if (cidx < FL_MAX_NODES) {
-                            const unsigned cs = kind <= 2 ? ch[j] : 0xFFFFu;
-                            n_a[cidx] = min(tot1, 0xFFFFFu) | ((uint32_t)n << 23) | ((uint32_t)j << 28) | ((cs == 0xFFFFu ? 1u : 0u) << 30);
-                            n_sk[cidx] = cs;
-                        }
-                    }
-                    count = min(FL_MAX_NODES, count + 3);
-                }
+                wx = w.x; kunus = w.w >> 16; c01 = w.z; c2 = w.w & 0xFFFFu;
+                cb = le + 3 * __popc(lmask & ((1u << n) - 1u));
             }
-            if (bad) s_misc[3] = 1;
-            T.count[la] = count;
-            // evaluation orders (tool.h:468-524): node_order = height above the leaves
-            int8_t *no = T.norder + la * 32;
-            for (int k = 0; k < 32; k++) no[k] = k < count ? 0 : -2;
-            for (int k = count - 1; k >= 1; k--) {
-                const int pa = (int)((n_a[k] >> 23) & 31u);
-                no[pa] = (int8_t)max((int)no[pa], (int)no[k] + 1);
+            if (le >= FL_MAX_NODES) break;
+            const int nle = min(FL_MAX_NODES, le + 3 * __popc(lmask));
+            const bool pull = n >= le && n < nle;
+            const int rt = pull ? (n - le) / 3 : 0, j = pull ? (n - le) - 3 * rt : 0;
+            const int p = pull ? (int)(__fns(lmask, 0, rt + 1) & 31u) : 0;
+            const unsigned pz = __shfl_sync(0xFFFFFFFFu, c01, p), pw = __shfl_sync(0xFFFFFFFFu, c2, p);
+            const int pk = __shfl_sync(0xFFFFFFFFu, kind, p), ptot = __shfl_sync(0xFFFFFFFFu, tot0 + kend + 1, p);
+            if (pull) {
+                unsigned cs = j == 0 ? (pz & 0xFFFFu) : j == 1 ? (pz >> 16) : pw;
+                if (pk > 2) cs = 0xFFFFu;
+                sid = cs; tot0 = ptot; parent = p; ad = j - 1; level = cur + 1; cb = FL_MAX_NODES;
+            }
+            ls = le; le = nle; count = nle; cur++;
+        }
+        if (bad) s_misc[3] = 1;
+        const bool exists = n < count;
+        const bool real = n >= 1 && exists && sid != 0xFFFFu;
+        // evaluation orders (tool.h:468-524): node_order = height above the leaves, bottom level first
+        int order = exists ? 0 : -2;
+        for (int lev = cur; lev >= 0; lev--) {
+            const int c0 = min(cb, 31);
+            const int o0 = __shfl_sync(0xFFFFFFFFu, order, c0), o1 = __shfl_sync(0xFFFFFFFFu, order, min(cb + 1, 31)),
+                      o2 = __shfl_sync(0xFFFFFFFFu, order, min(cb + 2, 31));
+            if (level == lev && (n == 0 || real) && cb < count) {
+                int m = o0;
+                if (cb + 1 < count) m = max(m, o1);
+                if (cb + 2 < count) m = max(m, o2);
+                order = m + 1;
             }
         }
-        __syncthreads();
-        OBS_TICK(4);
-
-        // ---- 4B: node features, one warp per agent over the flat list of the cells of all its walks ----
-        for (int la = warp; la < na; la += NT / 32) {
-            const int h = a0 + la;
-            const size_t ea = (size_t)e * N + h;
-            const int count = T.count[la];
-            const int n = lane;
-            const uint32_t a = n < FL_MAX_NODES ? T.n_a[la * 31 + n] : (1u << 30);
-            const uint32_t sk = n < FL_MAX_NODES ? T.n_sk[la * 31 + n] : 0xFFFFu;
-            const bool real = n >= 1 && n < count && !((a >> 30) & 1u);
-            const int kind = (int)((a >> 20) & 7u), tot0 = (int)(a & 0xFFFFFu), kend = (int)(sk >> 16);
-            const unsigned sid0 = sk & 0xFFFFu;
-            uint4 w = make_uint4(0u, 0u, 0u, 0u);
-            if (real) w = wrec[sid0];
-            const unsigned wbase = w.x, kunus = w.w >> 16;
-            const uint32_t ainfo = A.info[h];
-            const uint16_t *dm = dist + (size_t)((ainfo >> 8) & 0xFFFF) * HW * 4;
-            const float tpc_f = (float)(1.0 / (double)A.speed[h]);                          // treeobs.cpp:304
-            // the state the walk ends on and its distance to the target: loaded now, used when the node is written
-            unsigned dv_end = 0;
-            if (real && kind != 4) {
-                const uint32_t erec = srec[wlist[wbase + kend]];
-                dv_end = dm[((size_t)((int)(erec & 1023) * W + (int)((erec >> 10) & 1023))) * 4 + ((erec >> 20) & 3)];
-            }
-            const unsigned len = real ? (unsigned)kend + 1u : 0u;
-            unsigned total;
-            const unsigned off = warp_excl_scan(len, lane, total);
-            const unsigned real_mask = __ballot_sync(0xFFFFFFFFu, real);
-            const int nreal = __popc(real_mask);
-            // lane q holds the q-th real node's (offset, list base, tot0): the owner of a cell is found by rank
-            const unsigned src = __fns(real_mask, 0, lane + 1) & 31u;
-            const unsigned c_off = __shfl_sync(0xFFFFFFFFu, off, src), c_wb = __shfl_sync(0xFFFFFFFFu, wbase, src);
-            const int c_t0 = __shfl_sync(0xFFFFFFFFu, tot0, src);
-            const bool c_valid = lane < nreal;
-            int k_other = I_INF, k_conf = I_INF, same = 0, opp = 0, malf = 0, rtdn = 0, spd_bits = 0x3F800000;  // min speed starts at 1.0f
-            for (unsigned base = 0; base < total; base += 32) {
-                const unsigned j = base + lane;
-                const int cnt0 = __popc(__ballot_sync(0xFFFFFFFFu, c_valid && c_off <= base));
-                const unsigned starts = __reduce_or_sync(0xFFFFFFFFu, (c_valid && c_off > base && c_off < base + 32) ? 1u << (c_off - base) : 0u);
-                const int rank = cnt0 - 1 + __popc(starts & (0xFFFFFFFFu >> (31 - lane)));
-                const unsigned o_off = __shfl_sync(0xFFFFFFFFu, c_off, rank), o_wb = __shfl_sync(0xFFFFFFFFu, c_wb, rank);
-                const int o_t0 = __shfl_sync(0xFFFFFFFFu, c_t0, rank);
-                const bool valid = j < total;
-                bool f_agent = false, f_same = false, f_malf = false, f_conf = false;
-                int my_rtd = 0, my_spd = 0x3F800000;
-                if (valid) {
-                    const int k = (int)(j - o_off);
-                    const unsigned sidc = wlist[o_wb + k];
-                    const unsigned rail = sidc >> 2;
-                    const int d = (int)(sidc & 3u);
-                    const int tot = o_t0 + k;
-                    const uint32_t cinfo = ci[rail];
-                    if (cinfo) {                   // treeobs.cpp:322-360 (the observer itself counts too)
-                        f_agent = true;
-                        f_malf = (cinfo >> 8) & 1u;
-                        const int cnt = (int)((cinfo >> 11) & 1023u);
-                        my_rtd = cnt ? cnt - 1 : 0;
-                        f_same = (int)((cinfo >> 9) & 3u) == d;
-                        if (f_same) my_spd = __float_as_int(A.speed[(cinfo >> 21) - 1]);
-                    }
-                    const int pt = (int)__fmul_rn((float)tot, tpc_f);               // treeobs.cpp:378
-                    if (pt < NPRED && tot < NPRED) {                                 // treeobs.cpp:379-465
-                        const unsigned bk = kcls ? kcls[rail] : rail;                 // the reference's position key c*W + r
-                        const uint32_t s0 = ks[(int)bk - 1], s1 = ks[bk];
-                        if (s0 < s1) {
-                            const int pre = max(0, pt - 1), post = min(NPRED - 1, pt + 1);
-                            const int nb = (int)((srec[sidc] >> 22) & 15u);
-                            unsigned acc = 0;
-                            auto candidate = [&](uint32_t en, int t0) {
-                                const int ag = (int)(en & 1023);
-                                const uint32_t oinfo = A.info[ag];
-                                const int t1 = ((en >> 19) & 1u) ? NPRED - 1 : (t0 ? t0 + (int)(oinfo >> 24) - 1 : 0);
-                                if (t1 < pre) return;
-                                const int dh = (int)((en >> 20) & 3), dp = (int)((en >> 22) & 3), dn = (int)((en >> 24) & 3);
-                                const bool done = (oinfo >> 5) & 1;
-                                const bool in_cur = t0 <= pt && pt <= t1, in_pre = t0 <= pre && pre <= t1,
-                                           in_post = t0 <= post && post <= t1;
-                                const int pdir = pt < t0 ? dp : (pt > t1 ? dn : dh);  // always the direction at row pt
-                                const bool cf = (d != pdir && tbit(nb, (pdir + 2) & 3)) || done;
-                                const bool other = ag != h;
-                                acc |= (in_cur && other ? 1u : 0u) | (in_pre && other ? 2u : 0u) | (in_post && other ? 4u : 0u) |
-                                       (in_cur && cf ? 8u : 0u) | (in_pre && cf ? 16u : 0u) | (in_post && cf ? 32u : 0u);
-                            };
-                            uint32_t idx = s0;
-                            for (; idx < s1; idx++) {                                    // long-lived entries come first
-                                const uint32_t en = ent[idx];
-                                if (!((en >> 19) & 1u)) break;
-                                const int t0 = (int)((en >> 10) & 511);
-                                if (t0 <= post) candidate(en, t0);
-                            }
-                            // regular entries are ordered by t0: only those with pre - tpc_max < t0 <= post can matter
-                            const int t_lo = pre - tpc_max + 1;
-                            uint32_t lo = idx, hi = s1;
-                            while (lo < hi) {
-                                const uint32_t mid = (lo + hi) >> 1;
-                                if ((int)((ent[mid] >> 10) & 511) < t_lo) lo = mid + 1; else hi = mid;
-                            }
-                            for (idx = lo; idx < s1; idx++) {
-                                const uint32_t en = ent[idx];
-                                const int t0 = (int)((en >> 10) & 511);
-                                if (t0 > post) break;
-                                candidate(en, t0);
-                            }
-                            f_conf = (acc & 1u) ? (acc & 8u) : (acc & 2u) ? (acc & 16u) : (acc & 4u) ? (acc & 32u) : false;
+        const int porder = __shfl_sync(0xFFFFFFFFu, order, parent);
+        // ---- features: the flat list of the cells of all walks of the agent, 32 cells at a time ----
+        // the distance to the target from the state the walk ends on: loaded now, used when the node is written
+        unsigned dv_end = 0;
+        if (real && kind != 4) dv_end = sd[wlist[wx + kend]];
+        const unsigned len = real ? (unsigned)kend + 1u : 0u;
+        unsigned total;
+        const unsigned off = warp_excl_scan(len, lane, total);
+        const unsigned real_mask = __ballot_sync(0xFFFFFFFFu, real);
+        const int nreal = __popc(real_mask);
+        // lane q holds the q-th real node's (offset, list base, tot0): the owner of a cell is found by rank
+        const unsigned src = __fns(real_mask, 0, lane + 1) & 31u;
+        const unsigned c_off = __shfl_sync(0xFFFFFFFFu, off, src), c_wb = __shfl_sync(0xFFFFFFFFu, wx, src);
+        const int c_t0 = __shfl_sync(0xFFFFFFFFu, tot0, src);
+        const bool c_valid = lane < nreal;
+        int k_other = I_INF, k_conf = I_INF, same = 0, opp = 0, malf = 0, rtdn = 0, spd_bits = 0x3F800000;  // min speed starts at 1.0f
+        for (unsigned base = 0; base < total; base += 32) {
+            const unsigned j = base + lane;
+            const int cnt0 = __popc(__ballot_sync(0xFFFFFFFFu, c_valid && c_off <= base));
+            const unsigned starts = __reduce_or_sync(0xFFFFFFFFu, (c_valid && c_off > base && c_off < base + 32) ? 1u << (c_off - base) : 0u);
+            const int rank = cnt0 - 1 + __popc(starts & (0xFFFFFFFFu >> (31 - lane)));
+            const unsigned o_off = __shfl_sync(0xFFFFFFFFu, c_off, rank), o_wb = __shfl_sync(0xFFFFFFFFu, c_wb, rank);
+            const int o_t0 = __shfl_sync(0xFFFFFFFFu, c_t0, rank);
+            const bool valid = j < total;
+            bool f_agent = false, f_same = false, f_malf = false, f_conf = false;
+            int my_rtd = 0, my_spd = 0x3F800000;
+            if (valid) {
+                const int k = (int)(j - o_off);
+                const unsigned sidc = wlist[o_wb + k];
+                const unsigned rail = sidc >> 2;
+                const int d = (int)(sidc & 3u);
+                const int tot = o_t0 + k;
+                const uint32_t cinfo = ci[rail];
+                if (cinfo) {                   // treeobs.cpp:322-360 (the observer itself counts too)
+                    f_agent = true;
+                    f_malf = (cinfo >> 8) & 1u;
+                    const int cnt = (int)((cinfo >> 11) & 1023u);
+                    my_rtd = cnt ? cnt - 1 : 0;
+                    f_same = (int)((cinfo >> 9) & 3u) == d;
+                    if (f_same) my_spd = __float_as_int(A.speed[(cinfo >> 21) - 1]);
+                }
+                const int pt = (int)__fmul_rn((float)tot, tpc_f);               // treeobs.cpp:378
+                if (pt < NPRED && tot < NPRED) {                                 // treeobs.cpp:379-465
+                    const unsigned bk = kcls ? (unsigned)kcls[rail] : rail;    // the reference's position key c*W + r
+                    const uint32_t s0 = ks[(int)bk - 1], s1 = ks[bk];
+                    if (s0 < s1) {
+                        const int pre = max(0, pt - 1), post = min(NPRED - 1, pt + 1);
+                        unsigned acc = 0;
+                        int nb = -1;
+                        auto candidate = [&](uint32_t en, int t0) {
+                            const int ag = (int)(en & 1023);
+                            const uint32_t oinfo = A.info[ag];
+                            const int t1 = ((en >> 19) & 1u) ? NPRED - 1 : (t0 ? t0 + (int)(oinfo >> 24) - 1 : 0);
+                            if (t1 < pre) return;
+                            if (nb < 0) nb = (int)((srec[sidc] >> 22) & 15u);
+                            const int dh = (int)((en >> 20) & 3), dpv = (int)((en >> 22) & 3), dn = (int)((en >> 24) & 3);
+                            const bool done = (oinfo >> 5) & 1;
+                            const bool in_cur = t0 <= pt && pt <= t1, in_pre = t0 <= pre && pre <= t1,
+                                       in_post = t0 <= post && post <= t1;
+                            const int pdir = pt < t0 ? dpv : (pt > t1 ? dn : dh);  // always the direction at row pt
+                            const bool cf = (d != pdir && tbit(nb, (pdir + 2) & 3)) || done;
+                            const bool other = ag != h;
+                            acc |= (in_cur && other ? 1u : 0u) | (in_pre && other ? 2u : 0u) | (in_post && other ? 4u : 0u) |
+                                   (in_cur && cf ? 8u : 0u) | (in_pre && cf ? 16u : 0u) | (in_post && cf ? 32u : 0u);
+                        };
+                        uint32_t idx = s0;
+                        for (; idx < s1; idx++) {                                    // long-lived entries come first
+                            const uint32_t en = ent[idx];
+                            if (!((en >> 19) & 1u)) break;
+                            const int t0 = (int)((en >> 10) & 511);
+                            if (t0 <= post) candidate(en, t0);
                         }
+                        // regular entries are ordered by t0: only those with pre - tpc_max < t0 <= post can matter
+                        const int t_lo = pre - tpc_max + 1;
+                        uint32_t lo = idx, hi = s1;
+                        while (lo < hi) {
+                            const uint32_t mid = (lo + hi) >> 1;
+                            if ((int)((ent[mid] >> 10) & 511) < t_lo) lo = mid + 1; else hi = mid;
+                        }
+                        for (idx = lo; idx < s1; idx++) {
+                            const uint32_t en = ent[idx];
+                            const int t0 = (int)((en >> 10) & 511);
+                            if (t0 > post) break;
+                            candidate(en, t0);
+                        }
+                        f_conf = (acc & 1u) ? (acc & 8u) : (acc & 2u) ? (acc & 16u) : (acc & 4u) ? (acc & 32u) : false;
                     }
                 }
-                // what the lanes found returns to the lane owning the node: ballots masked by the node's segment of this window
-                const unsigned b_agent = __ballot_sync(0xFFFFFFFFu, f_agent);
-                const unsigned b_conf = __ballot_sync(0xFFFFFFFFu, f_conf);
-                const int lo_ = max((int)off - (int)base, 0), hi_ = min((int)(off + len) - (int)base, 32);
-                const unsigned seg = (real && lo_ < hi_) ? ((hi_ == 32 ? 0xFFFFFFFFu : ((1u << hi_) - 1u)) & ~((1u << lo_) - 1u)) : 0u;
-                if (b_agent) {                                                       // warp-uniform
-                    const unsigned b_same = __ballot_sync(0xFFFFFFFFu, f_same), b_malf = __ballot_sync(0xFFFFFFFFu, f_malf);
-                    const unsigned m = b_agent & seg;
-                    if (m) {
-                        k_other = min(k_other, (int)base + __ffs(m) - 1 - (int)off);
-                        same += __popc(b_same & seg); opp += __popc(m & ~b_same);
-                        malf |= (b_malf & seg) != 0u;
-                    }
-                    for (unsigned mm = b_agent; mm; mm &= mm - 1) {                  // few trains per window: values by shuffle
-                        const int s = __ffs(mm) - 1;
-                        const int r_ = __shfl_sync(0xFFFFFFFFu, my_rtd, s), sp = __shfl_sync(0xFFFFFFFFu, my_spd, s);
-                        if ((seg >> s) & 1u) { rtdn += r_; spd_bits = min(spd_bits, sp); }   // positive floats order like their bits
-                    }
-                }
-                const unsigned mc = b_conf & seg;
-                if (mc) k_conf = min(k_conf, (int)base + __ffs(mc) - 1 - (int)off);
             }
-            // ---- lane n writes node n (scale_node, treeobs.cpp:111-152) ----
-            float *forest = out_forest + ea * (FL_MAX_NODES * FL_NODE_F);
-            if (n < FL_MAX_NODES) {
-                float4 v0, v1, v2;
-                if (n == 0) {
-                    const float dtv = A.dt[h];
-                    v0 = make_float4(0.f, 0.f, 0.f, 0.f);
-                    v1 = make_float4(0.f, 0.f, dtv != INFINITY ? dtv / T_ : -1.0f, 0.f);
-                    v2 = make_float4(0.f, (float)((A.rec_b[h] >> 16) & 1u) / Nf, A.speed[h], 0.f);
-                } else if (real) {
-                    const int tot = tot0 + kend;
-                    const bool tb = kind == 4;
-                    int dnb, dmin;
-                    if (tb) { dnb = tot; dmin = 0; }
-                    else {
-                        dmin = dv_end == FL_DIST_INF ? I_INF : (int)dv_end;
-                        dnb = kind == 3 ? I_INF : tot;
-                    }
-                    const bool unus = kunus != 0xFFFFu && (int)kunus < kend;
-                    v0 = make_float4(tb ? scale_i(tot, sc) : -1.0f, -1.0f, k_other != I_INF ? scale_i(tot0 + k_other, sc) : -1.0f,
-                                     k_conf != I_INF ? scale_i(tot0 + k_conf, sc) : -1.0f);
-                    v1 = make_float4(unus ? scale_i(tot0 + (int)kunus, sc) : -1.0f, scale_i(dnb, sc), scale_i(dmin, sc), scale_n(same, sc));
-                    v2 = make_float4(scale_n(opp, sc), scale_n(malf, sc), __int_as_float(spd_bits), scale_n(rtdn, sc));
-                } else {
-                    v0 = v1 = v2 = make_float4(-1.0f, -1.0f, -1.0f, -1.0f);
+            // what the lanes found returns to the lane owning the node: ballots masked by the node's segment of this window
+            const unsigned b_agent = __ballot_sync(0xFFFFFFFFu, f_agent);
+            const unsigned b_conf = __ballot_sync(0xFFFFFFFFu, f_conf);
+            const int lo_ = max((int)off - (int)base, 0), hi_ = min((int)(off + len) - (int)base, 32);
+            const unsigned seg = (real && lo_ < hi_) ? ((hi_ == 32 ? 0xFFFFFFFFu : ((1u << hi_) - 1u)) & ~((1u << lo_) - 1u)) : 0u;
+            if (b_agent) {                                                       // warp-uniform
+                const unsigned b_same = __ballot_sync(0xFFFFFFFFu, f_same), b_malf = __ballot_sync(0xFFFFFFFFu, f_malf);
+                const unsigned m = b_agent & seg;
+                if (m) {
+                    k_other = min(k_other, (int)base + __ffs(m) - 1 - (int)off);
+                    same += __popc(b_same & seg); opp += __popc(m & ~b_same);
+                    malf |= (b_malf & seg) != 0u;
                 }
-                store_node(forest + n * FL_NODE_F, v0, v1, v2);
-            }
-            // ---- adjacency / node_order / edge_order rows of the agent, lanes over the row ----
-            const int8_t *no = T.norder + la * 32;
-            const uint32_t *meta = T.n_a + la * 31;
-            int32_t *adj = out_adj + ea * ((FL_MAX_NODES - 1) * 3);
-            for (int jj = lane; jj < 90; jj += 32) {
-                const int edge = jj / 3, comp = jj - edge * 3, node = edge + 1;
-                int v = -2;
-                if (node < count) {
-                    const uint32_t m = meta[node];
-                    v = comp == 0 ? (int)((m >> 23) & 31u) : comp == 1 ? node : (int)((m >> 28) & 3u) - 1;
+                for (unsigned mm = b_agent; mm; mm &= mm - 1) {                  // few trains per window: values by shuffle
+                    const int s = __ffs(mm) - 1;
+                    const int r_ = __shfl_sync(0xFFFFFFFFu, my_rtd, s), sp = __shfl_sync(0xFFFFFFFFu, my_spd, s);
+                    if ((seg >> s) & 1u) { rtdn += r_; spd_bits = min(spd_bits, sp); }   // positive floats order like their bits
                 }
-                adj[jj] = v;
             }
-            if (lane < FL_MAX_NODES) out_norder[ea * FL_MAX_NODES + lane] = no[lane];
-            if (lane < FL_MAX_NODES - 1) {
-                const int node = lane + 1;
-                out_eorder[ea * (FL_MAX_NODES - 1) + lane] = node < count ? (int)no[(meta[node] >> 23) & 31u] : -2;
+            const unsigned mc = b_conf & seg;
+            if (mc) k_conf = min(k_conf, (int)base + __ffs(mc) - 1 - (int)off);
+        }
+        // ---- lane n writes node n (scale_node, treeobs.cpp:111-152), its adjacency row and its orders ----
+        if (n < FL_MAX_NODES) {
+            float4 v0, v1, v2;
+            if (n == 0) {
+                const float dtv = A.dt[h];
+                v0 = make_float4(0.f, 0.f, 0.f, 0.f);
+                v1 = make_float4(0.f, 0.f, dtv != INFINITY ? dtv / T_ : -1.0f, 0.f);
+                v2 = make_float4(0.f, (float)((A.rec_b[h] >> 16) & 1u) / Nf, A.speed[h], 0.f);
+            } else if (real) {
+                const int tot = tot0 + kend;
+                const bool tb = kind == 4;
+                int dnb, dmin;
+                if (tb) { dnb = tot; dmin = 0; }
+                else {
+                    dmin = dv_end == FL_DIST_INF ? I_INF : (int)dv_end;
+                    dnb = kind == 3 ? I_INF : tot;
+                }
+                const bool unus = kunus != 0xFFFFu && (int)kunus < kend;
+                v0 = make_float4(tb ? scale_i(tot, sc) : -1.0f, -1.0f, k_other != I_INF ? scale_i(tot0 + k_other, sc) : -1.0f,
+                                 k_conf != I_INF ? scale_i(tot0 + k_conf, sc) : -1.0f);
+                v1 = make_float4(unus ? scale_i(tot0 + (int)kunus, sc) : -1.0f, scale_i(dnb, sc), scale_i(dmin, sc), scale_n(same, sc));
+                v2 = make_float4(scale_n(opp, sc), scale_n(malf, sc), __int_as_float(spd_bits), scale_n(rtdn, sc));
+            } else {
+                v0 = v1 = v2 = make_float4(-1.0f, -1.0f, -1.0f, -1.0f);
+            }
+            store_node(out_forest + ea * (FL_MAX_NODES * FL_NODE_F) + n * FL_NODE_F, v0, v1, v2);
+            out_norder[ea * FL_MAX_NODES + n] = order;
+            if (n >= 1) {
+                int32_t *adj = out_adj + ea * ((FL_MAX_NODES - 1) * 3) + (n - 1) * 3;
+                adj[0] = exists ? parent : -2; adj[1] = exists ? n : -2; adj[2] = exists ? ad : -2;
+                out_eorder[ea * (FL_MAX_NODES - 1) + n - 1] = exists ? porder : -2;
             }
         }
-        __syncthreads();
-        OBS_TICK(5);
     }
+    __syncthreads();
+    OBS_TICK(5);
     if (tid == 0 && s_misc[3]) atomicOr(&b.status[e], FL_ST_BAD_CELL);
+    for (int i = tid; i < N; i += NT) b.deadlocked[(size_t)e * N + i] = D.dl[i];
     OBS_TICK(6);
 
     // ---- phase 5: agent attributes (feature_parser.cpp:3-98), coalesced over the environment ---------
@@ -840,47 +788,33 @@ k_observe(FlBatch b, ObsLayout lay, float *__restrict__ out_attr, float *__restr
         const float curr_step = (float)elapsed / T_;
         for (int idx = tid; idx < N * FL_ATTR_F; idx += NT) {
             const int i = idx / FL_ATTR_F, k = idx - i * FL_ATTR_F;
-            const uint32_t ra = A.rec_a[i], rb = A.rec_b[i];
-            const int st = ra & 7, road = (ra >> 3) & 15, idir = (ra >> 7) & 3, od = (ra >> 9) & 3, ctr = (ra >> 11) & 255,
-                      maxc = (ra >> 19) & 255, va = (ra >> 27) & 31, dir = A.info[i] & 3;
-            const int trans = rb & 0xFFFF, nmal01 = (rb >> 16) & 1, mal01 = (rb >> 17) & 1, sig_mal = (rb >> 18) & 1;
             float v;
-            if (k < 7) v = k == st;
-            else if (k < 18) v = (k - 7) == road;
-            else if (k < 28) v = (k - 18) == nmal01;
-            else if (k < 32) v = (k - 28) == idir;
-            else if (k < 36) v = (k - 32) == dir;
-            else if (k < 40) v = (k - 36) == od;
-            else if (k < 49) {
-                switch (k - 40) {
-                case 0: v = st == MOVING; break;
-                case 1: v = D.dl[i] != 0; break;
-                case 2: v = sig_mal; break;
-                case 3: v = !mal01; break;
-                case 4: v = ctr == 0; break;
-                case 5: v = ctr == maxc; break;
-                case 6: v = st == MALFUNCTION || st == MAL_OFF; break;
-                case 7: v = off_map(st); break;
-                default: v = on_map(st); break;
-                }
-            } else if (k < 65) v = (trans >> (15 - (k - 49))) & 1;
-            else if (k < 70) v = (va >> (k - 65)) & 1;
-            else {
-                const float latest = A.f_latest[i], before_late = __fsub_rn(latest, curr_step), dist_f = A.f_dist[i];
-                switch (k - 70) {
-                case 0: v = (float)i / Nf; break;
-                case 1: v = curr_step; break;
-                case 2: v = A.f_earliest[i]; break;
-                case 3: v = latest; break;
-                case 4: v = A.f_arrival[i]; break;
-                case 5: v = before_late; break;
-                case 6: v = dist_f; break;
-                case 7: v = before_late < dist_f ? before_late : dist_f; break;
-                case 8: v = (float)maxc / 10.0f; break;
-                case 9: v = A.speed[i] / 1.0f; break;
-                case 10: v = (float)ctr / 10.0f; break;
-                case 11: v = (float)mal01 / 10.0f; break;
-                default: v = A.f_idist[i]; break;
+            if (k < 64) {
+                const uint32_t m = k < 32 ? A.m0[i] : A.m1[i];
+                v = (float)((m >> (k & 31)) & 1u);
+                if (k == 41) v = D.dl[i] != 0;
+            } else {
+                const uint32_t ra = A.rec_a[i], rb = A.rec_b[i];
+                const int ctr = (ra >> 11) & 255, maxc = (ra >> 19) & 255, va = (ra >> 27) & 31, mal01 = (rb >> 17) & 1;
+                if (k == 64) v = (float)(rb & 1u);
+                else if (k < 70) v = (float)((va >> (k - 65)) & 1);
+                else {
+                    const float latest = A.f_latest[i], before_late = __fsub_rn(latest, curr_step), dist_f = A.f_dist[i];
+                    switch (k - 70) {
+                    case 0: v = (float)i / Nf; break;
+                    case 1: v = curr_step; break;
+                    case 2: v = A.f_earliest[i]; break;
+                    case 3: v = latest; break;
+                    case 4: v = A.f_arrival[i]; break;
+                    case 5: v = before_late; break;
+                    case 6: v = dist_f; break;
+                    case 7: v = before_late < dist_f ? before_late : dist_f; break;
+                    case 8: v = (float)maxc / 10.0f; break;
+                    case 9: v = A.speed[i] / 1.0f; break;
+                    case 10: v = (float)ctr / 10.0f; break;
+                    case 11: v = (float)mal01 / 10.0f; break;
+                    default: v = f_idist[i]; break;
+                    }
                 }
             }
             dst[idx] = v;

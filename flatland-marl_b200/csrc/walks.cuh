@@ -23,6 +23,7 @@
 //   kcls[rail]     the reference keys predicted positions by c * W + r (treeobs.cpp:50-65, 379-465), which is not unique when
 //                  H > W: cells (r, c) and (r + W, c - 1) share a key and conflict with each other's predictions.  kcls maps
 //                  a rail cell to the lowest rail index of its key class (itself when H <= W)
+//   sdist[slot][sid] the distance map of fl_distance_map indexed by state id
 // FILL = false only measures (states, list length, hits) so that the host can size wlist and whits.
 #pragma once
 #include "common.cuh"
@@ -236,6 +237,22 @@ __global__ void __launch_bounds__(NT) k_walks(FlBatch b) {
     for (int sid = S + tid; sid < (int)b.state_stride; sid += NT) {
         srec[sid] = 0; whoff[sid] = 0;
         wrec[sid] = make_uint4(0u, 0u, 0xFFFFFFFFu, 0xFFFFFFFFu);
+    }
+    // the distance map by state id (the observation never needs it off the rail)
+    __syncthreads();
+    {
+        uint16_t *sd = b.sdist + (size_t)e * b.n_slots * b.state_stride;
+        const uint16_t *dist = b.dist + (size_t)e * b.dist_stride;
+        const int ss = (int)b.state_stride, n = (int)b.n_slots * ss;
+        for (int idx = tid; idx < n; idx += NT) {
+            const int s = idx / ss, sid = idx - s * ss;
+            unsigned v = FL_DIST_INF;
+            if (sid < S) {
+                const uint32_t rec = srec[sid];
+                v = dist[((size_t)s * HW + (size_t)((rec & 1023) * W + ((rec >> 10) & 1023))) * 4 + ((rec >> 20) & 3)];
+            }
+            sd[idx] = (uint16_t)v;
+        }
     }
     if (tid == 0) { tot[0] = S; tot[1] = (int)total; tot[2] = (int)total_h; tot[3] = 0; }
 }

@@ -96,6 +96,8 @@ typedef struct FlBatch {
     uint32_t *whits;           /* [E][whits_stride] step | slot<<16 of every walk state standing on a slot's target */
     uint16_t *kcls;            /* [E][state_stride] per rail cell: lowest rail index among the cells sharing the reference's
                                   prediction key c*W + r (only cells of grids with H > W have partners) */
+    uint16_t *sdist;           /* [E][n_slots][state_stride] the distance map indexed by state id (copy of `dist` on the rail
+                                  cells only; fl_walk_tables(fill) runs after fl_distance_map) */
     int32_t *walk_total;       /* [E][4] written by fl_walk_tables: states, wlist elements, whits elements, 0 */
 
     /* ---- agent state (agent_utils.py:58-105 and step_utils/*) ---- */
@@ -136,7 +138,8 @@ int fl_distance_map(const FlBatch *b, void *stream);
 
 /* Builds the static branch-walk tables of every environment (reset time, after the grid upload).  Two
  * passes: fill == 0 only writes walk_total (ridx and walk_total must be allocated) so that the caller can
- * size srec / wrec / whoff / wlist / whits; fill != 0 writes all tables.  No reference counterpart: the reference
+ * size srec / wrec / whoff / wlist / whits; fill != 0 writes all tables, and needs the distance maps (fl_distance_map
+ * earlier on the same stream) for sdist.  No reference counterpart: the reference
  * re-walks the rail cell by cell in every _explore_branch call (treeobs.cpp:258-610). */
 int fl_walk_tables(const FlBatch *b, int fill, void *stream);
 
@@ -163,9 +166,9 @@ int fl_observe(const FlBatch *b, float *d_agent_attr, float *d_forest, int32_t *
                float *d_dist_target, void *stream);
 
 /* Diagnostics: the shared-memory plan fl_observe uses for this batch.  out[0..19] = threads per CTA, dynamic
- * shared bytes, tree tile (agents), entry capacity, unsorted-entry capacity, byte offsets of grid, occupancy,
- * bucket offsets, entries, distance maps, ridx, srec, wrec, whoff, wlist (-1 = stays in global memory),
- * agents, deadlock scratch, node table, CTAs per SM that fit, whits. */
+ * shared bytes, CTAs per SM planned for, entry capacity, byte offsets of key classes, grid, occupancy,
+ * bucket offsets, entries, sdist, ridx, srec, wrec, whoff, wlist (-1 = stays in global memory / unused),
+ * agents, deadlock scratch, scan partials, CTAs per SM that fit, whits. */
 int fl_observe_plan(const FlBatch *b, int32_t *out, int n_out);
 
 /* A view of environments [e0, e0+n) of a batch: every pointer advanced by e0 environments, E = n.  The view

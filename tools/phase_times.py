@@ -28,8 +28,8 @@ for t in range(steps):
         acc.append(batch.debug_clocks.cpu().numpy().copy())
 d = np.stack(acc).astype(np.float64)          # [20, E, 16]
 t0 = d[..., 15]
-names = [("setup+zero", 15, 0), ("tma wait+loader+occupancy", 0, 1), ("prediction walks", 1, 2), ("scan+scatter+sort (+deadlock join)", 2, 3),
-         ("tree structure (4A)", 3, 4), ("node features (4B)", 4, 5), ("attributes", 6, 7)]
+names = [("setup+zero", 15, 0), ("tma wait+loader+occupancy", 0, 1), ("prediction count pass", 1, 2), ("scan+scatter pass+sort", 2, 3),
+         ("trees (structure+features)", 3, 5), ("attributes", 6, 7)]
 tot = d[..., 7] - t0
 print("%s E=%d N=%d: mean cycles per env %.0f (p50 %.0f, p99 %.0f, max %.0f)" % (cfg, E, N, tot.mean(), np.median(tot), np.percentile(tot, 99), tot.max()))
 for nm, a, b in names:
