@@ -105,6 +105,8 @@ ObsLayout make_obs_layout(const FlBatch *b, int nt, int *ctas_out = nullptr) {
     L.dl = take(18 * N);
     L.ci = take((long long)Rmax * 4);
     L.ks = take((long long)(Rmax + 2) * 4);
+    L.bm = take((long long)Rmax * 16);                          // time-slot filter of the prediction index
+    L.sq = take((long long)(nt / 32) * 64 * 8);                 // per-warp queues of the full conflict checks
     L.kcls = b->H > b->W ? take(b->state_stride * 2) : -1;      // key classes of the reference's c*W + r (walks.cuh)
     const long long ent_typ = (long long)N * 56 * 4;
     const long long grid_b = b->grid_stride * 2, ridx_b = b->ridx_stride * 2;

@@ -36,7 +36,7 @@ namespace {
 constexpr int I_INF = 0x7fffffff;
 
 struct ObsLayout {   // byte offsets into dynamic shared memory (host: make_obs_layout); < 0 = lives in global memory
-    int bar, part, ag, dl, ci, ks, kcls, grid, ridx, ent, ent_cap, total;
+    int bar, part, ag, dl, ci, ks, bm, sq, kcls, grid, ridx, ent, ent_cap, total;
     int srec, wrec, whoff, whits, wlist, sdist;   // static walk tables (walks.cuh)
 };
 
@@ -82,14 +82,14 @@ DEVI uint32_t pack_entry(int agent, int t0, int t1, int dh, int dp, int dn);
 // (predictions.cpp:13-76) — unless the start state cannot reach the target at all, in which case the path is its first
 // element.  The path ends on the agent's target cell (a target hit of the walk) or after 500 moves.  Path element idx >= 1
 // is occupied for prediction rows [1 + (idx-1)*tpc, idx*tpc], the last element until row 500, element 0 for row 0 only
-// (or all rows when the path has a single element).  Emit(rail cell, entry) is called once per occupied element.
+// (or all rows when the path has a single element).  Emit(rail cell, t0, t1, entry) is called once per occupied element.
 template <class Emit>
 DEVI void predict_path(const uint4 *wrec, const uint32_t *whoff, const uint32_t *whits, const uint16_t *wlist,
                        const uint16_t *sd, unsigned sid, unsigned slot, int tpc, int agent, Emit emit) {
     int dp = (int)(sid & 3u);                        // direction of the previous element (element 0: its own)
     if (sd[sid] == FL_DIST_INF) {                    // no move lowers the distance: the path is its first element
         // (a start state on the target has distance 0 and ends through the target hit below)
-        emit(sid >> 2, pack_entry(agent, 0, NPRED - 1, dp, dp, dp));
+        emit(sid >> 2, 0, NPRED - 1, pack_entry(agent, 0, NPRED - 1, dp, dp, dp));
         return;
     }
     int kk = 0;                                      // path element index of the walk's first state
@@ -113,18 +113,27 @@ DEVI void predict_path(const uint4 *wrec, const uint32_t *whoff, const uint32_t 
             for (int j = 0; j < 3; j++)
                 if (ch[j] != 0xFFFFu) { const unsigned v = sd[ch[j]]; if (v < best) { best = v; nxt = ch[j]; } }
         }
-        unsigned s = wlist[w.x];
-        for (int k = 0; k <= kend; k++) {
-            const int idx = kk + k;
-            const int t0 = idx ? 1 + (idx - 1) * tpc : 0;
-            if (t0 >= NPRED) return;
-            const bool last = (k == kend && (hit || nxt == 0xFFFFu)) || idx >= FL_PRED_DEPTH;
-            const unsigned sn = k < kend ? (unsigned)wlist[w.x + k + 1] : nxt;
-            const int d = (int)(s & 3u), dn = last ? d : (int)(sn & 3u);
-            const int t1 = last ? NPRED - 1 : min(idx ? idx * tpc : 0, NPRED - 1);
-            emit(s >> 2, pack_entry(agent, t0, t1, d, dp, dn));
-            if (last) return;
-            dp = d; s = sn;
+        // four elements per round: their states are loaded together (one memory latency per round, not per element;
+        // the list has 8 elements of slack at its end, so reading past the walk is harmless)
+        for (int k0 = 0; k0 <= kend; k0 += 4) {
+            unsigned sv[5];
+#pragma unroll
+            for (int u = 0; u < 5; u++) sv[u] = wlist[w.x + k0 + u];
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                const int k = k0 + u;
+                if (k > kend) break;
+                const int idx = kk + k;
+                const int t0 = idx ? 1 + (idx - 1) * tpc : 0;
+                if (t0 >= NPRED) return;
+                const bool last = (k == kend && (hit || nxt == 0xFFFFu)) || idx >= FL_PRED_DEPTH;
+                const unsigned s = sv[u], sn = k < kend ? sv[u + 1] : nxt;
+                const int d = (int)(s & 3u), dn = last ? d : (int)(sn & 3u);
+                const int t1 = last ? NPRED - 1 : min(idx ? idx * tpc : 0, NPRED - 1);
+                emit(s >> 2, t0, t1, pack_entry(agent, t0, t1, d, dp, dn));
+                if (last) return;
+                dp = d;
+            }
         }
         sid = nxt; kk += kend + 1;
     }
@@ -302,6 +311,18 @@ struct ObsAgents {
     float *f_earliest, *f_latest, *f_arrival, *f_dist;   // (f_idist follows as the 16th array)
 };
 
+// position of the n-th (0-based) set bit of m; the caller guarantees that m has more than n set bits.  Five popc
+// steps (the __fns intrinsic is a long software loop).
+DEVI int nth_set_bit(unsigned m, int n) {
+    int pos = 0;
+#pragma unroll
+    for (int s = 16; s >= 1; s >>= 1) {
+        const int c = __popc((m >> pos) & ((1u << s) - 1u));
+        if (n >= c) { n -= c; pos += s; }
+    }
+    return pos;
+}
+
 DEVI unsigned warp_excl_scan(unsigned v, int lane, unsigned &total) {
     unsigned x = v;
 #pragma unroll
@@ -345,6 +366,8 @@ k_observe(FlBatch b, ObsLayout lay, float *__restrict__ out_attr, float *__restr
     const uint16_t *kcls = lay.kcls >= 0 ? reinterpret_cast<const uint16_t *>(smraw + lay.kcls) : nullptr;   // only when H > W
     uint32_t *ci = reinterpret_cast<uint32_t *>(smraw + lay.ci);             // [R] occupancy word per rail cell
     uint32_t *ks = reinterpret_cast<uint32_t *>(smraw + lay.ks) + 1;         // ks[-1..R]: bucket r = [ks[r-1], ks[r])
+    uint32_t *bm = reinterpret_cast<uint32_t *>(smraw + lay.bm);             // [R][4] bit s: some prediction entry of the key overlaps rows 4s..4s+3
+    uint2 *sq = reinterpret_cast<uint2 *>(smraw + lay.sq) + warp * 64;       // this warp's queue of cells that need the full conflict check
     uint32_t *s_part = reinterpret_cast<uint32_t *>(smraw + lay.part);
     uint64_t *bar = reinterpret_cast<uint64_t *>(smraw + lay.bar);
     int *s_misc = reinterpret_cast<int *>(smraw + lay.bar + 16);
@@ -401,6 +424,7 @@ k_observe(FlBatch b, ObsLayout lay, float *__restrict__ out_attr, float *__restr
     // zero the bucket counters and the occupancy words
     for (int k = tid; k <= R + 1; k += NT) ks[k - 1] = 0;
     for (int k = tid; k < R; k += NT) ci[k] = 0;
+    for (int k = tid; k < R * 4; k += NT) bm[k] = 0;
     const float T_ = (float)b.max_steps[e], Nf = (float)N;
     const Scale sc{T_, __frcp_rn(T_), Nf, __frcp_rn(Nf)};
     const int elapsed = b.elapsed[e];
@@ -505,7 +529,7 @@ k_observe(FlBatch b, ObsLayout lay, float *__restrict__ out_attr, float *__restr
             const unsigned slot = (info >> 8) & 0xFFFFu, s0 = A.sid0[i];
             if (s0 == 0xFFFFu) continue;
             predict_path(wrec, whoff, whits, wlist, sdist + (size_t)slot * SS, s0, slot, (int)(info >> 24), i,
-                         [&](unsigned rail, uint32_t) { atomicAdd(&ks[kcls ? (unsigned)kcls[rail] : rail], 1u); });
+                         [&](unsigned rail, int, int, uint32_t) { atomicAdd(&ks[kcls ? (unsigned)kcls[rail] : rail], 1u); });
         }
         named_bar_sync(1, NW);
         OBS_TICK(2);
@@ -533,7 +557,15 @@ k_observe(FlBatch b, ObsLayout lay, float *__restrict__ out_attr, float *__restr
             const unsigned slot = (info >> 8) & 0xFFFFu, s0 = A.sid0[i];
             if (s0 == 0xFFFFu) continue;
             predict_path(wrec, whoff, whits, wlist, sdist + (size_t)slot * SS, s0, slot, (int)(info >> 24), i,
-                         [&](unsigned rail, uint32_t en) { ent[atomicAdd(&ks[kcls ? (unsigned)kcls[rail] : rail], 1u)] = en; });
+                         [&](unsigned rail, int t0, int t1, uint32_t en) {
+                             const unsigned key = kcls ? (unsigned)kcls[rail] : rail;
+                             ent[atomicAdd(&ks[key], 1u)] = en;
+                             const int sa = t0 >> 2, sb = t1 >> 2;             // time slots of 4 rows the entry overlaps
+                             for (int wd = sa >> 5; wd <= sb >> 5; wd++) {
+                                 const int lo_b = max(sa - 32 * wd, 0), hi_b = min(sb - 32 * wd, 31);
+                                 atomicOr(&bm[key * 4 + wd], (0xFFFFFFFFu >> (31 - hi_b)) & (0xFFFFFFFFu << lo_b));
+                             }
+                         });
         }
         named_bar_sync(1, NW);
         // order every bucket: long-lived entries first, then by t0, so that the tree walk scans a time window only
@@ -605,7 +637,7 @@ k_observe(FlBatch b, ObsLayout lay, float *__restrict__ out_attr, float *__restr
             const int nle = min(FL_MAX_NODES, le + 3 * __popc(lmask));
             const bool pull = n >= le && n < nle;
             const int rt = pull ? (n - le) / 3 : 0, j = pull ? (n - le) - 3 * rt : 0;
-            const int p = pull ? (int)(__fns(lmask, 0, rt + 1) & 31u) : 0;
+            const int p = pull ? nth_set_bit(lmask, rt) : 0;
             const unsigned pz = __shfl_sync(0xFFFFFFFFu, c01, p), pw = __shfl_sync(0xFFFFFFFFu, c2, p);
             const int pk = __shfl_sync(0xFFFFFFFFu, kind, p), ptot = __shfl_sync(0xFFFFFFFFu, tot0 + kend + 1, p);
             if (pull) {
@@ -642,105 +674,138 @@ k_observe(FlBatch b, ObsLayout lay, float *__restrict__ out_attr, float *__restr
         const unsigned real_mask = __ballot_sync(0xFFFFFFFFu, real);
         const int nreal = __popc(real_mask);
         // lane q holds the q-th real node's (offset, list base, tot0): the owner of a cell is found by rank
-        const unsigned src = __fns(real_mask, 0, lane + 1) & 31u;
+        const unsigned src = lane < nreal ? (unsigned)nth_set_bit(real_mask, lane) : 31u;
         const unsigned c_off = __shfl_sync(0xFFFFFFFFu, off, src), c_wb = __shfl_sync(0xFFFFFFFFu, wx, src);
         const int c_t0 = __shfl_sync(0xFFFFFFFFu, tot0, src);
         const bool c_valid = lane < nreal;
         int k_other = I_INF, k_conf = I_INF, same = 0, opp = 0, malf = 0, rtdn = 0, spd_bits = 0x3F800000;  // min speed starts at 1.0f
-        for (unsigned base = 0; base < total; base += 32) {
-            const unsigned j = base + lane;
-            const int cnt0 = __popc(__ballot_sync(0xFFFFFFFFu, c_valid && c_off <= base));
-            const unsigned starts = __reduce_or_sync(0xFFFFFFFFu, (c_valid && c_off > base && c_off < base + 32) ? 1u << (c_off - base) : 0u);
-            const int rank = cnt0 - 1 + __popc(starts & (0xFFFFFFFFu >> (31 - lane)));
-            const unsigned o_off = __shfl_sync(0xFFFFFFFFu, c_off, rank), o_wb = __shfl_sync(0xFFFFFFFFu, c_wb, rank);
-            const int o_t0 = __shfl_sync(0xFFFFFFFFu, c_t0, rank);
-            const bool valid = j < total;
-            bool f_agent = false, f_same = false, f_malf = false, f_conf = false;
-            int my_rtd = 0, my_spd = 0x3F800000;
-            if (valid) {
-                const int k = (int)(j - o_off);
-                const unsigned sidc = wlist[o_wb + k];
-                const unsigned rail = sidc >> 2;
-                const int d = (int)(sidc & 3u);
-                const int tot = o_t0 + k;
-                const uint32_t cinfo = ci[rail];
-                if (cinfo) {                   // treeobs.cpp:322-360 (the observer itself counts too)
-                    f_agent = true;
-                    f_malf = (cinfo >> 8) & 1u;
-                    const int cnt = (int)((cinfo >> 11) & 1023u);
-                    my_rtd = cnt ? cnt - 1 : 0;
-                    f_same = (int)((cinfo >> 9) & 3u) == d;
-                    if (f_same) my_spd = __float_as_int(A.speed[(cinfo >> 21) - 1]);
-                }
-                const int pt = (int)__fmul_rn((float)tot, tpc_f);               // treeobs.cpp:378
-                if (pt < NPRED && tot < NPRED) {                                 // treeobs.cpp:379-465
-                    const unsigned bk = kcls ? (unsigned)kcls[rail] : rail;    // the reference's position key c*W + r
-                    const uint32_t s0 = ks[(int)bk - 1], s1 = ks[bk];
-                    if (s0 < s1) {
-                        const int pre = max(0, pt - 1), post = min(NPRED - 1, pt + 1);
-                        unsigned acc = 0;
-                        int nb = -1;
-                        auto candidate = [&](uint32_t en, int t0) {
-                            const int ag = (int)(en & 1023);
-                            const uint32_t oinfo = A.info[ag];
-                            const int t1 = ((en >> 19) & 1u) ? NPRED - 1 : (t0 ? t0 + (int)(oinfo >> 24) - 1 : 0);
-                            if (t1 < pre) return;
-                            if (nb < 0) nb = (int)((srec[sidc] >> 22) & 15u);
-                            const int dh = (int)((en >> 20) & 3), dpv = (int)((en >> 22) & 3), dn = (int)((en >> 24) & 3);
-                            const bool done = (oinfo >> 5) & 1;
-                            const bool in_cur = t0 <= pt && pt <= t1, in_pre = t0 <= pre && pre <= t1,
-                                       in_post = t0 <= post && post <= t1;
-                            const int pdir = pt < t0 ? dpv : (pt > t1 ? dn : dh);  // always the direction at row pt
-                            const bool cf = (d != pdir && tbit(nb, (pdir + 2) & 3)) || done;
-                            const bool other = ag != h;
-                            acc |= (in_cur && other ? 1u : 0u) | (in_pre && other ? 2u : 0u) | (in_post && other ? 4u : 0u) |
-                                   (in_cur && cf ? 8u : 0u) | (in_pre && cf ? 16u : 0u) | (in_post && cf ? 32u : 0u);
-                        };
-                        uint32_t idx = s0;
-                        for (; idx < s1; idx++) {                                    // long-lived entries come first
-                            const uint32_t en = ent[idx];
-                            if (!((en >> 19) & 1u)) break;
-                            const int t0 = (int)((en >> 10) & 511);
-                            if (t0 <= post) candidate(en, t0);
-                        }
-                        // regular entries are ordered by t0: only those with pre - tpc_max < t0 <= post can matter
-                        const int t_lo = pre - tpc_max + 1;
-                        uint32_t lo = idx, hi = s1;
-                        while (lo < hi) {
-                            const uint32_t mid = (lo + hi) >> 1;
-                            if ((int)((ent[mid] >> 10) & 511) < t_lo) lo = mid + 1; else hi = mid;
-                        }
-                        for (idx = lo; idx < s1; idx++) {
-                            const uint32_t en = ent[idx];
-                            const int t0 = (int)((en >> 10) & 511);
-                            if (t0 > post) break;
-                            candidate(en, t0);
-                        }
-                        f_conf = (acc & 1u) ? (acc & 8u) : (acc & 2u) ? (acc & 16u) : (acc & 4u) ? (acc & 32u) : false;
+        const int my_rank = __popc(real_mask & ((1u << lane) - 1u));
+        int qn = 0;                                    // cells waiting in the warp's queue for the full conflict check
+        unsigned base = 0;
+        while (true) {
+            const bool more = base < total;            // warp-uniform
+            if (more) {
+                // ---- stage 1: one cell per lane: trains on the cell, and the time-slot filter of the prediction index ----
+                const unsigned j = base + lane;
+                const int cnt0 = __popc(__ballot_sync(0xFFFFFFFFu, c_valid && c_off <= base));
+                const unsigned starts = __reduce_or_sync(0xFFFFFFFFu, (c_valid && c_off > base && c_off < base + 32) ? 1u << (c_off - base) : 0u);
+                const int rank = cnt0 - 1 + __popc(starts & (0xFFFFFFFFu >> (31 - lane)));
+                const unsigned o_off = __shfl_sync(0xFFFFFFFFu, c_off, rank), o_wb = __shfl_sync(0xFFFFFFFFu, c_wb, rank);
+                const int o_t0 = __shfl_sync(0xFFFFFFFFu, c_t0, rank);
+                bool f_agent = false, f_same = false, f_malf = false, surv = false;
+                int my_rtd = 0, my_spd = 0x3F800000, k = 0, pt = 0;
+                unsigned sidc = 0;
+                if (j < total) {
+                    k = (int)(j - o_off);
+                    sidc = wlist[o_wb + k];
+                    const unsigned rail = sidc >> 2;
+                    const int tot = o_t0 + k;
+                    const uint32_t cinfo = ci[rail];
+                    if (cinfo) {                   // treeobs.cpp:322-360 (the observer itself counts too)
+                        f_agent = true;
+                        f_malf = (cinfo >> 8) & 1u;
+                        const int cnt = (int)((cinfo >> 11) & 1023u);
+                        my_rtd = cnt ? cnt - 1 : 0;
+                        f_same = ((cinfo >> 9) & 3u) == (sidc & 3u);
+                        if (f_same) my_spd = __float_as_int(A.speed[(cinfo >> 21) - 1]);
+                    }
+                    pt = (int)__fmul_rn((float)tot, tpc_f);                         // treeobs.cpp:378
+                    if (pt < NPRED && tot < NPRED) {                                 // treeobs.cpp:379-465
+                        const unsigned bk = kcls ? (unsigned)kcls[rail] : rail;    // the reference's position key c*W + r
+                        const int sa = max(0, pt - 1) >> 2, sb = min(NPRED - 1, pt + 1) >> 2;
+                        surv = ((bm[bk * 4 + (sa >> 5)] >> (sa & 31)) | (bm[bk * 4 + (sb >> 5)] >> (sb & 31))) & 1u;
                     }
                 }
-            }
-            // what the lanes found returns to the lane owning the node: ballots masked by the node's segment of this window
-            const unsigned b_agent = __ballot_sync(0xFFFFFFFFu, f_agent);
-            const unsigned b_conf = __ballot_sync(0xFFFFFFFFu, f_conf);
-            const int lo_ = max((int)off - (int)base, 0), hi_ = min((int)(off + len) - (int)base, 32);
-            const unsigned seg = (real && lo_ < hi_) ? ((hi_ == 32 ? 0xFFFFFFFFu : ((1u << hi_) - 1u)) & ~((1u << lo_) - 1u)) : 0u;
-            if (b_agent) {                                                       // warp-uniform
-                const unsigned b_same = __ballot_sync(0xFFFFFFFFu, f_same), b_malf = __ballot_sync(0xFFFFFFFFu, f_malf);
-                const unsigned m = b_agent & seg;
-                if (m) {
-                    k_other = min(k_other, (int)base + __ffs(m) - 1 - (int)off);
-                    same += __popc(b_same & seg); opp += __popc(m & ~b_same);
-                    malf |= (b_malf & seg) != 0u;
+                // what the lanes found returns to the lane owning the node: ballots masked by the node's segment of this window
+                const unsigned b_agent = __ballot_sync(0xFFFFFFFFu, f_agent);
+                if (b_agent) {                                                       // warp-uniform
+                    const int lo_ = max((int)off - (int)base, 0), hi_ = min((int)(off + len) - (int)base, 32);
+                    const unsigned seg = (real && lo_ < hi_) ? ((hi_ == 32 ? 0xFFFFFFFFu : ((1u << hi_) - 1u)) & ~((1u << lo_) - 1u)) : 0u;
+                    const unsigned b_same = __ballot_sync(0xFFFFFFFFu, f_same), b_malf = __ballot_sync(0xFFFFFFFFu, f_malf);
+                    const unsigned m = b_agent & seg;
+                    if (m) {
+                        k_other = min(k_other, (int)base + __ffs(m) - 1 - (int)off);
+                        same += __popc(b_same & seg); opp += __popc(m & ~b_same);
+                        malf |= (b_malf & seg) != 0u;
+                    }
+                    for (unsigned mm = b_agent; mm; mm &= mm - 1) {                  // few trains per window: values by shuffle
+                        const int s = __ffs(mm) - 1;
+                        const int r_ = __shfl_sync(0xFFFFFFFFu, my_rtd, s), sp = __shfl_sync(0xFFFFFFFFu, my_spd, s);
+                        if ((seg >> s) & 1u) { rtdn += r_; spd_bits = min(spd_bits, sp); }   // positive floats order like their bits
+                    }
                 }
-                for (unsigned mm = b_agent; mm; mm &= mm - 1) {                  // few trains per window: values by shuffle
+                // cells that passed the filter go to the queue: state | owner rank << 16 | row << 21, walk step
+                const unsigned b_surv = __ballot_sync(0xFFFFFFFFu, surv);
+                if (surv) sq[qn + __popc(b_surv & ((1u << lane) - 1u))] = make_uint2(sidc | ((unsigned)rank << 16) | ((unsigned)pt << 21), (unsigned)k);
+                qn += __popc(b_surv);
+                base += 32;
+            }
+            if (qn >= 32 || (!more && qn > 0)) {
+                // ---- stage 2: the full conflict check (treeobs.cpp:379-465) of up to 32 queued cells, one per lane ----
+                __syncwarp();
+                const int nq = min(qn, 32);
+                bool f_conf = false;
+                uint2 q = make_uint2(0u, 0u);
+                if (lane < nq) {
+                    q = sq[lane];
+                    const unsigned sidc = q.x & 0xFFFFu, rail = sidc >> 2;
+                    const int d = (int)(sidc & 3u), pt = (int)(q.x >> 21);
+                    const unsigned bk = kcls ? (unsigned)kcls[rail] : rail;
+                    const uint32_t s0 = ks[(int)bk - 1], s1 = ks[bk];
+                    const int pre = max(0, pt - 1), post = min(NPRED - 1, pt + 1);
+                    unsigned acc = 0;
+                    int nb = -1;
+                    auto candidate = [&](uint32_t en, int t0) {
+                        const int ag = (int)(en & 1023);
+                        const uint32_t oinfo = A.info[ag];
+                        const int t1 = ((en >> 19) & 1u) ? NPRED - 1 : (t0 ? t0 + (int)(oinfo >> 24) - 1 : 0);
+                        if (t1 < pre) return;
+                        if (nb < 0) nb = (int)((srec[sidc] >> 22) & 15u);
+                        const int dh = (int)((en >> 20) & 3), dpv = (int)((en >> 22) & 3), dn = (int)((en >> 24) & 3);
+                        const bool done = (oinfo >> 5) & 1;
+                        const bool in_cur = t0 <= pt && pt <= t1, in_pre = t0 <= pre && pre <= t1,
+                                   in_post = t0 <= post && post <= t1;
+                        const int pdir = pt < t0 ? dpv : (pt > t1 ? dn : dh);  // always the direction at row pt
+                        const bool cf = (d != pdir && tbit(nb, (pdir + 2) & 3)) || done;
+                        const bool other = ag != h;
+                        acc |= (in_cur && other ? 1u : 0u) | (in_pre && other ? 2u : 0u) | (in_post && other ? 4u : 0u) |
+                               (in_cur && cf ? 8u : 0u) | (in_pre && cf ? 16u : 0u) | (in_post && cf ? 32u : 0u);
+                    };
+                    uint32_t idx = s0;
+                    for (; idx < s1; idx++) {                                    // long-lived entries come first
+                        const uint32_t en = ent[idx];
+                        if (!((en >> 19) & 1u)) break;
+                        const int t0 = (int)((en >> 10) & 511);
+                        if (t0 <= post) candidate(en, t0);
+                    }
+                    // regular entries are ordered by t0: only those with pre - tpc_max < t0 <= post can matter
+                    const int t_lo = pre - tpc_max + 1;
+                    uint32_t lo = idx, hi = s1;
+                    while (lo < hi) {
+                        const uint32_t mid = (lo + hi) >> 1;
+                        if ((int)((ent[mid] >> 10) & 511) < t_lo) lo = mid + 1; else hi = mid;
+                    }
+                    for (idx = lo; idx < s1; idx++) {
+                        const uint32_t en = ent[idx];
+                        const int t0 = (int)((en >> 10) & 511);
+                        if (t0 > post) break;
+                        candidate(en, t0);
+                    }
+                    f_conf = (acc & 1u) ? (acc & 8u) : (acc & 2u) ? (acc & 16u) : (acc & 4u) ? (acc & 32u) : false;
+                }
+                for (unsigned mm = __ballot_sync(0xFFFFFFFFu, f_conf); mm; mm &= mm - 1) {   // conflicts are rare: to the owner by shuffle
                     const int s = __ffs(mm) - 1;
-                    const int r_ = __shfl_sync(0xFFFFFFFFu, my_rtd, s), sp = __shfl_sync(0xFFFFFFFFu, my_spd, s);
-                    if ((seg >> s) & 1u) { rtdn += r_; spd_bits = min(spd_bits, sp); }   // positive floats order like their bits
+                    const unsigned qx = __shfl_sync(0xFFFFFFFFu, q.x, s), qk = __shfl_sync(0xFFFFFFFFu, q.y, s);
+                    if (real && my_rank == (int)((qx >> 16) & 31u)) k_conf = min(k_conf, (int)qk);
                 }
-            }
-            const unsigned mc = b_conf & seg;
-            if (mc) k_conf = min(k_conf, (int)base + __ffs(mc) - 1 - (int)off);
+                // the rest of the queue moves to the front
+                uint2 mv = make_uint2(0u, 0u);
+                if (lane + 32 < qn) mv = sq[lane + 32];
+                __syncwarp();
+                if (lane + 32 < qn) sq[lane] = mv;
+                qn -= nq;
+                __syncwarp();
+            } else if (!more) break;
         }
         // ---- lane n writes node n (scale_node, treeobs.cpp:111-152), its adjacency row and its orders ----
         if (n < FL_MAX_NODES) {
