@@ -74,7 +74,7 @@ int check_batch(const FlBatch *b) {
     if (b->N >= FL_MAX_AGENTS) return FL_ERR_TOO_MANY_AGENTS;
     if (b->ent_cap < b->N * (int64_t)NPRED) return FL_ERR_BAD_ARG;
     if (b->H >= 1024 || b->W >= 1024) return FL_ERR_BAD_ARG;   // srec packs row and column in 10 bits each
-    if (b->ridx_stride < b->H * b->W || b->ridx_stride % 8 || b->state_stride % 8 || b->wlist_stride % 8 || b->whits_stride % 4)
+    if (b->ridx_stride < b->H * b->W || b->ridx_stride % 8 || b->state_stride % 8 || b->wlist_stride % 4 || b->whits_stride % 4)
         return FL_ERR_BAD_ARG;
     if (b->state_stride > 0xFFFF) return FL_ERR_BAD_ARG;       // state ids are 16 bit
     // per-environment blocks are 16-byte aligned so that they can be moved with TMA bulk copies
@@ -110,10 +110,10 @@ ObsLayout make_obs_layout(const FlBatch *b, int nt, int *ctas_out = nullptr) {
     L.kcls = b->H > b->W ? take(b->state_stride * 2) : -1;      // key classes of the reference's c*W + r (walks.cuh)
     const long long ent_typ = (long long)N * 56 * 4;
     const long long grid_b = b->grid_stride * 2, ridx_b = b->ridx_stride * 2;
-    const long long st_b = b->state_stride * 4, wl_b = b->wlist_stride * 2, wh_b = b->whits_stride * 4;
+    const long long st_b = b->state_stride * 4, wl_b = b->wlist_stride * 4, wh_b = b->whits_stride * 4;
     const long long sd_b = b->n_slots * b->state_stride * 2;
     const long long core = off + grid_b + ridx_b + ent_typ + 4 * 128;
-    int want_tables = 0x3F;                                     // bit k: wlist, wrec, sdist, srec, whoff, whits
+    int want_tables = 0x37;                                     // bit k: wlist, wrec, sdist, (srec: unused by k_observe), whoff, whits
     if (const char *s = getenv("FL_OBS_TABLES")) want_tables = atoi(s);
     const int max_ctas = nt == 256 ? 4 : nt == 128 ? 8 : 12;
     int ctas = 0;

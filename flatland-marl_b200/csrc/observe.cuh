@@ -84,7 +84,7 @@ DEVI uint32_t pack_entry(int agent, int t0, int t1, int dh, int dp, int dn);
 // is occupied for prediction rows [1 + (idx-1)*tpc, idx*tpc], the last element until row 500, element 0 for row 0 only
 // (or all rows when the path has a single element).  Emit(rail cell, t0, t1, entry) is called once per occupied element.
 template <class Emit>
-DEVI void predict_path(const uint4 *wrec, const uint32_t *whoff, const uint32_t *whits, const uint16_t *wlist,
+DEVI void predict_path(const uint4 *wrec, const uint32_t *whoff, const uint32_t *whits, const uint32_t *wlist,
                        const uint16_t *sd, unsigned sid, unsigned slot, int tpc, int agent, Emit emit) {
     int dp = (int)(sid & 3u);                        // direction of the previous element (element 0: its own)
     if (sd[sid] == FL_DIST_INF) {                    // no move lowers the distance: the path is its first element
@@ -118,7 +118,7 @@ DEVI void predict_path(const uint4 *wrec, const uint32_t *whoff, const uint32_t 
         for (int k0 = 0; k0 <= kend; k0 += 4) {
             unsigned sv[5];
 #pragma unroll
-            for (int u = 0; u < 5; u++) sv[u] = wlist[w.x + k0 + u];
+            for (int u = 0; u < 5; u++) sv[u] = wlist[w.x + k0 + u] & 0xFFFFu;
 #pragma unroll
             for (int u = 0; u < 4; u++) {
                 const int k = k0 + u;
@@ -352,7 +352,7 @@ k_observe(FlBatch b, ObsLayout lay, float *__restrict__ out_attr, float *__restr
     const uint16_t *g_ridx = b.ridx + (size_t)e * b.ridx_stride;
     const uint32_t *g_srec = b.srec + (size_t)e * SS, *g_whoff = b.whoff + (size_t)e * SS;
     const uint4 *g_wrec = reinterpret_cast<const uint4 *>(b.wrec) + (size_t)e * SS;
-    const uint16_t *g_wlist = b.wlist + (size_t)e * b.wlist_stride;
+    const uint32_t *g_wlist = b.wlist + (size_t)e * b.wlist_stride;
     const uint32_t *g_whits = b.whits + (size_t)e * b.whits_stride;
     const uint16_t *g_sdist = b.sdist + (size_t)e * b.n_slots * SS;
     const uint16_t *grid = lay.grid >= 0 ? reinterpret_cast<const uint16_t *>(smraw + lay.grid) : g_grid;
@@ -361,7 +361,7 @@ k_observe(FlBatch b, ObsLayout lay, float *__restrict__ out_attr, float *__restr
     const uint4 *wrec = lay.wrec >= 0 ? reinterpret_cast<const uint4 *>(smraw + lay.wrec) : g_wrec;
     const uint32_t *whoff = lay.whoff >= 0 ? reinterpret_cast<const uint32_t *>(smraw + lay.whoff) : g_whoff;
     const uint32_t *whits = lay.whits >= 0 ? reinterpret_cast<const uint32_t *>(smraw + lay.whits) : g_whits;
-    const uint16_t *wlist = lay.wlist >= 0 ? reinterpret_cast<const uint16_t *>(smraw + lay.wlist) : g_wlist;
+    const uint32_t *wlist = lay.wlist >= 0 ? reinterpret_cast<const uint32_t *>(smraw + lay.wlist) : g_wlist;
     const uint16_t *sdist = lay.sdist >= 0 ? reinterpret_cast<const uint16_t *>(smraw + lay.sdist) : g_sdist;
     const uint16_t *kcls = lay.kcls >= 0 ? reinterpret_cast<const uint16_t *>(smraw + lay.kcls) : nullptr;   // only when H > W
     uint32_t *ci = reinterpret_cast<uint32_t *>(smraw + lay.ci);             // [R] occupancy word per rail cell
@@ -406,7 +406,7 @@ k_observe(FlBatch b, ObsLayout lay, float *__restrict__ out_attr, float *__restr
         const uint32_t gb = lay.grid >= 0 ? (uint32_t)(b.grid_stride * 2) : 0u;
         const uint32_t rb = lay.ridx >= 0 ? (uint32_t)(b.ridx_stride * 2) : 0u;
         const uint32_t sb = (uint32_t)(SS * 4);
-        const uint32_t lb = lay.wlist >= 0 ? (uint32_t)(b.wlist_stride * 2) : 0u;
+        const uint32_t lb = lay.wlist >= 0 ? (uint32_t)(b.wlist_stride * 4) : 0u;
         const uint32_t hb = lay.whits >= 0 ? (uint32_t)(b.whits_stride * 4) : 0u;
         const uint32_t kb = lay.kcls >= 0 ? (uint32_t)(SS * 2) : 0u;
         const uint32_t db = lay.sdist >= 0 ? (uint32_t)(b.n_slots * SS * 2) : 0u;
@@ -517,6 +517,7 @@ k_observe(FlBatch b, ObsLayout lay, float *__restrict__ out_attr, float *__restr
     const bool dl_warp = warp == NT / 32 - 1;
     constexpr int NW = NT - 32;                    // threads walking predictions
     uint32_t *ent = reinterpret_cast<uint32_t *>(smraw + lay.ent);
+    uint32_t *const ent_s = ent;                   // the shared-memory copy (typed loads are cheaper than generic ones)
     if (dl_warp) {
         if (lane == 0) { update_deadlocks(D, ci, ridx, N, H, W); if (dbg) dbg[8] = clock64(); }
         __syncwarp();
@@ -586,6 +587,8 @@ k_observe(FlBatch b, ObsLayout lay, float *__restrict__ out_attr, float *__restr
     const int tpc_max = ld_vol_i32(&s_misc[2]);
 
     // ---- phase 4: branch trees, one warp per agent, agents taken from a shared counter --------------------
+    const bool spill = ent != ent_s;
+    auto ent_at = [&](uint32_t i) { return spill ? ent[i] : ent_s[i]; };
     while (true) {
         int h = 0;
         if (lane == 0) h = atomicAdd(&s_misc[1], 1);
@@ -667,7 +670,7 @@ k_observe(FlBatch b, ObsLayout lay, float *__restrict__ out_attr, float *__restr
         // ---- features: the flat list of the cells of all walks of the agent, 32 cells at a time ----
         // the distance to the target from the state the walk ends on: loaded now, used when the node is written
         unsigned dv_end = 0;
-        if (real && kind != 4) dv_end = sd[wlist[wx + kend]];
+        if (real && kind != 4) dv_end = sd[wlist[wx + kend] & 0xFFFFu];
         const unsigned len = real ? (unsigned)kend + 1u : 0u;
         unsigned total;
         const unsigned off = warp_excl_scan(len, lane, total);
@@ -694,11 +697,11 @@ k_observe(FlBatch b, ObsLayout lay, float *__restrict__ out_attr, float *__restr
                 const int o_t0 = __shfl_sync(0xFFFFFFFFu, c_t0, rank);
                 bool f_agent = false, f_same = false, f_malf = false, surv = false;
                 int my_rtd = 0, my_spd = 0x3F800000, k = 0, pt = 0;
-                unsigned sidc = 0;
+                unsigned sidc = 0;                                                  // state id | transitions nibble << 16
                 if (j < total) {
                     k = (int)(j - o_off);
                     sidc = wlist[o_wb + k];
-                    const unsigned rail = sidc >> 2;
+                    const unsigned rail = (sidc & 0xFFFFu) >> 2;
                     const int tot = o_t0 + k;
                     const uint32_t cinfo = ci[rail];
                     if (cinfo) {                   // treeobs.cpp:322-360 (the observer itself counts too)
@@ -728,15 +731,16 @@ k_observe(FlBatch b, ObsLayout lay, float *__restrict__ out_attr, float *__restr
                         same += __popc(b_same & seg); opp += __popc(m & ~b_same);
                         malf |= (b_malf & seg) != 0u;
                     }
-                    for (unsigned mm = b_agent; mm; mm &= mm - 1) {                  // few trains per window: values by shuffle
+                    // ready-to-depart counts and speeds below 1.0 are rare: to the owner by shuffle
+                    for (unsigned mm = __ballot_sync(0xFFFFFFFFu, my_rtd != 0 || my_spd != 0x3F800000); mm; mm &= mm - 1) {
                         const int s = __ffs(mm) - 1;
                         const int r_ = __shfl_sync(0xFFFFFFFFu, my_rtd, s), sp = __shfl_sync(0xFFFFFFFFu, my_spd, s);
                         if ((seg >> s) & 1u) { rtdn += r_; spd_bits = min(spd_bits, sp); }   // positive floats order like their bits
                     }
                 }
-                // cells that passed the filter go to the queue: state | owner rank << 16 | row << 21, walk step
+                // cells that passed the filter go to the queue: state | owner rank << 16 | row << 21, walk step | transitions nibble << 16
                 const unsigned b_surv = __ballot_sync(0xFFFFFFFFu, surv);
-                if (surv) sq[qn + __popc(b_surv & ((1u << lane) - 1u))] = make_uint2(sidc | ((unsigned)rank << 16) | ((unsigned)pt << 21), (unsigned)k);
+                if (surv) sq[qn + __popc(b_surv & ((1u << lane) - 1u))] = make_uint2((sidc & 0xFFFFu) | ((unsigned)rank << 16) | ((unsigned)pt << 21), (unsigned)k | (sidc & 0xF0000u));
                 qn += __popc(b_surv);
                 base += 32;
             }
@@ -754,13 +758,12 @@ k_observe(FlBatch b, ObsLayout lay, float *__restrict__ out_attr, float *__restr
                     const uint32_t s0 = ks[(int)bk - 1], s1 = ks[bk];
                     const int pre = max(0, pt - 1), post = min(NPRED - 1, pt + 1);
                     unsigned acc = 0;
-                    int nb = -1;
+                    const int nb = (int)((q.y >> 16) & 15u);
                     auto candidate = [&](uint32_t en, int t0) {
                         const int ag = (int)(en & 1023);
                         const uint32_t oinfo = A.info[ag];
                         const int t1 = ((en >> 19) & 1u) ? NPRED - 1 : (t0 ? t0 + (int)(oinfo >> 24) - 1 : 0);
                         if (t1 < pre) return;
-                        if (nb < 0) nb = (int)((srec[sidc] >> 22) & 15u);
                         const int dh = (int)((en >> 20) & 3), dpv = (int)((en >> 22) & 3), dn = (int)((en >> 24) & 3);
                         const bool done = (oinfo >> 5) & 1;
                         const bool in_cur = t0 <= pt && pt <= t1, in_pre = t0 <= pre && pre <= t1,
@@ -773,7 +776,7 @@ k_observe(FlBatch b, ObsLayout lay, float *__restrict__ out_attr, float *__restr
                     };
                     uint32_t idx = s0;
                     for (; idx < s1; idx++) {                                    // long-lived entries come first
-                        const uint32_t en = ent[idx];
+                        const uint32_t en = ent_at(idx);
                         if (!((en >> 19) & 1u)) break;
                         const int t0 = (int)((en >> 10) & 511);
                         if (t0 <= post) candidate(en, t0);
@@ -783,10 +786,10 @@ k_observe(FlBatch b, ObsLayout lay, float *__restrict__ out_attr, float *__restr
                     uint32_t lo = idx, hi = s1;
                     while (lo < hi) {
                         const uint32_t mid = (lo + hi) >> 1;
-                        if ((int)((ent[mid] >> 10) & 511) < t_lo) lo = mid + 1; else hi = mid;
+                        if ((int)((ent_at(mid) >> 10) & 511) < t_lo) lo = mid + 1; else hi = mid;
                     }
                     for (idx = lo; idx < s1; idx++) {
-                        const uint32_t en = ent[idx];
+                        const uint32_t en = ent_at(idx);
                         const int t0 = (int)((en >> 10) & 511);
                         if (t0 > post) break;
                         candidate(en, t0);
@@ -796,7 +799,7 @@ k_observe(FlBatch b, ObsLayout lay, float *__restrict__ out_attr, float *__restr
                 for (unsigned mm = __ballot_sync(0xFFFFFFFFu, f_conf); mm; mm &= mm - 1) {   // conflicts are rare: to the owner by shuffle
                     const int s = __ffs(mm) - 1;
                     const unsigned qx = __shfl_sync(0xFFFFFFFFu, q.x, s), qk = __shfl_sync(0xFFFFFFFFu, q.y, s);
-                    if (real && my_rank == (int)((qx >> 16) & 31u)) k_conf = min(k_conf, (int)qk);
+                    if (real && my_rank == (int)((qx >> 16) & 31u)) k_conf = min(k_conf, (int)(qk & 0xFFFFu));
                 }
                 // the rest of the queue moves to the front
                 uint2 mv = make_uint2(0u, 0u);

@@ -19,7 +19,7 @@
 //   whoff[sid]     offset of the walk's target hits in whits (valid when the record counts any)
 //   whits[...]     step | slot << 16 for every state of the walk standing on the target cell of a unique-target slot, in
 //                  walk order: the observer's own target ends its walk early (treeobs.cpp:467-475, 483-489)
-//   wlist[...]     the visited state ids, walk after walk
+//   wlist[...]     the visited states, walk after walk: state id | transitions nibble of the state << 16
 //   kcls[rail]     the reference keys predicted positions by c * W + r (treeobs.cpp:50-65, 379-465), which is not unique when
 //                  H > W: cells (r, c) and (r + W, c - 1) share a key and conflict with each other's predictions.  kcls maps
 //                  a rail cell to the lowest rail index of its key class (itself when H <= W)
@@ -149,7 +149,7 @@ __global__ void __launch_bounds__(NT) k_walks(FlBatch b) {
     uint32_t *srec = b.srec + (size_t)e * b.state_stride;
     uint4 *wrec = reinterpret_cast<uint4 *>(b.wrec) + (size_t)e * b.state_stride;
     uint32_t *whoff = b.whoff + (size_t)e * b.state_stride;
-    uint16_t *wlist = b.wlist + (size_t)e * b.wlist_stride;
+    uint32_t *wlist = b.wlist + (size_t)e * b.wlist_stride;
     uint32_t *whits = b.whits + (size_t)e * b.whits_stride;
     for (int k = lo; k < hi; k++) {
         const unsigned gc = g[k];
@@ -210,7 +210,7 @@ __global__ void __launch_bounds__(NT) k_walks(FlBatch b) {
         for (int k = 0; k <= steps; k++) {
             const int cell = r * W + c;
             const unsigned ri = ridx[cell];
-            if (off < (uint32_t)b.wlist_stride) wlist[off] = (uint16_t)(ri * 4 + d);
+            if (off < (uint32_t)b.wlist_stride) wlist[off] = (ri * 4 + d) | (((srec[ri * 4 + d] >> 22) & 15u) << 16);
             off++;
             if (k < steps && kunus == 0xFFFF && ((srec[ri * 4 + d] >> 26) & 1u)) kunus = (unsigned)k;
             const int ts = target_slot_at(b, e, s_tbits, cell, W);

@@ -67,7 +67,7 @@ typedef struct FlBatch {
     int64_t *debug_clocks; /* tuning only: [E][16] SM-clock timestamps of k_observe's phases, NULL = off */
     int64_t ridx_stride;   /* uint16 elements per env of ridx, >= H*W, multiple of 8 */
     int64_t state_stride;  /* elements per env of srec / wrec / whoff / kcls, >= 4 * rail cells, multiple of 8 */
-    int64_t wlist_stride;  /* uint16 elements per env of wlist, multiple of 8 */
+    int64_t wlist_stride;  /* uint32 elements per env of wlist, multiple of 4, with 8 elements of slack at the end */
     int64_t whits_stride;  /* uint32 elements per env of whits, multiple of 4 */
 
     /* ---- world, static after upload (RailEnv.reset generators stay reference Python) ---- */
@@ -92,7 +92,7 @@ typedef struct FlBatch {
                                   (kind 1 switch, 2 dead end, 3 cycle, 0 bad cell); child0 | child1<<16;
                                   child2 | first unusable-switch step<<16 (0xFFFF = null / none).  16-byte aligned. */
     uint32_t *whoff;           /* [E][state_stride] offset of the walk's target hits in whits */
-    uint16_t *wlist;           /* [E][wlist_stride] visited state ids, walk after walk */
+    uint32_t *wlist;           /* [E][wlist_stride] visited states, walk after walk: state id | transitions nibble<<16 */
     uint32_t *whits;           /* [E][whits_stride] step | slot<<16 of every walk state standing on a slot's target */
     uint16_t *kcls;            /* [E][state_stride] per rail cell: lowest rail index among the cells sharing the reference's
                                   prediction key c*W + r (only cells of grids with H > W have partners) */
