@@ -16,7 +16,7 @@ _FIELDS = [("E", "i"), ("N", "i"), ("H", "i"), ("W", "i"), ("n_slots", "i"), ("S
            ("dist_stride", "i"), ("debug_clocks", "p"), ("ridx_stride", "i"), ("state_stride", "i"), ("wlist_stride", "i"),
            ("whits_stride", "i")]
 _PTR = ["grid", "slot_rc", "dist", "max_steps", "init_rc", "tgt_rc", "init_dir", "max_count", "slot", "speed",
-        "earliest", "latest", "sched", "ridx", "srec", "wrec", "whoff", "wlist", "whits", "kcls", "sdist", "walk_total",
+        "earliest", "latest", "sched", "ridx", "srec", "wrec", "whoff", "wlist", "whits", "kcls", "sdist", "gtab", "walk_total",
         "rc", "old_rc", "dir", "old_dir", "state", "ctr", "mal", "saved", "sig_mal", "deadlocked", "done", "nmal",
         "arrival",
         "elapsed", "sched_pos", "done_all", "status", "stats",

@@ -74,7 +74,7 @@ int check_batch(const FlBatch *b) {
     if (b->N >= FL_MAX_AGENTS) return FL_ERR_TOO_MANY_AGENTS;
     if (b->ent_cap < b->N * (int64_t)NPRED) return FL_ERR_BAD_ARG;
     if (b->H >= 1024 || b->W >= 1024) return FL_ERR_BAD_ARG;   // srec packs row and column in 10 bits each
-    if (b->ridx_stride < b->H * b->W || b->ridx_stride % 8 || b->state_stride % 8 || b->wlist_stride % 4 || b->whits_stride % 4)
+    if (b->ridx_stride < b->H * b->W || b->ridx_stride % 8 || b->state_stride % 32 || b->wlist_stride % 4 || b->whits_stride % 4)
         return FL_ERR_BAD_ARG;
     if (b->state_stride > 0xFFFF) return FL_ERR_BAD_ARG;       // state ids are 16 bit
     // per-environment blocks are 16-byte aligned so that they can be moved with TMA bulk copies
@@ -106,8 +106,10 @@ ObsLayout make_obs_layout(const FlBatch *b, int nt, int *ctas_out = nullptr) {
     L.ci = take((long long)Rmax * 4);
     L.ks = take((long long)(Rmax + 2) * 4);
     L.bm = take((long long)Rmax * 16);                          // time-slot filter of the prediction index
-    L.sq = take((long long)(nt / 32) * 64 * 8);                 // per-warp queues of the full conflict checks
-    L.kcls = b->H > b->W ? take(b->state_stride * 2) : -1;      // key classes of the reference's c*W + r (walks.cuh)
+    L.seg_cap = 10 * N;                                         // path segments of phase 3 share the room of the phase-4 queues
+    if (L.seg_cap < (nt / 32) * 64) L.seg_cap = (nt / 32) * 64;
+    L.sq = take((long long)L.seg_cap * 8);                      // per-warp queues of the full conflict checks / segment pool
+    L.kcls = b->H > b->W ? take((long long)Rmax * 2) : -1;      // key classes of the reference's c*W + r (walks.cuh)
     const long long ent_typ = (long long)N * 56 * 4;
     const long long grid_b = b->grid_stride * 2, ridx_b = b->ridx_stride * 2;
     const long long st_b = b->state_stride * 4, wl_b = b->wlist_stride * 4, wh_b = b->whits_stride * 4;
@@ -115,7 +117,7 @@ ObsLayout make_obs_layout(const FlBatch *b, int nt, int *ctas_out = nullptr) {
     const long long core = off + grid_b + ridx_b + ent_typ + 4 * 128;
     int want_tables = 0x37;                                     // bit k: wlist, wrec, sdist, (srec: unused by k_observe), whoff, whits
     if (const char *s = getenv("FL_OBS_TABLES")) want_tables = atoi(s);
-    const int max_ctas = nt == 256 ? 4 : nt == 128 ? 8 : 12;
+    const int max_ctas = nt >= 1024 ? 1 : nt == 512 ? 2 : nt == 256 ? 4 : nt == 128 ? 8 : 12;
     int ctas = 0;
     if (const char *s = getenv("FL_OBS_CTAS")) ctas = atoi(s) > 0 ? atoi(s) : 1;
     if (!ctas)
@@ -148,9 +150,19 @@ ObsLayout make_obs_layout(const FlBatch *b, int nt, int *ctas_out = nullptr) {
     return L;
 }
 
+// Threads per CTA: one CTA per environment, so small batches of large environments get more warps per CTA to keep the
+// SM's warp slots filled (about 32 resident warps per SM), small environments get small CTAs.
 int obs_threads(const FlBatch *b) {
-    if (const char *s = getenv("FL_OBS_NT")) { const int v = atoi(s); if (v == 64 || v == 128 || v == 256) return v; }
-    return b->N <= 24 ? 64 : 128;
+    if (const char *s = getenv("FL_OBS_NT")) {
+        const int v = atoi(s);
+        if (v == 64 || v == 128 || v == 256 || v == 512 || v == 1024) return v;
+    }
+    if (b->N <= 24) return 64;
+    const long long per_sm = (b->E + 147) / 148;                // environments per SM (B200: 148 SMs)
+    if (per_sm >= 5) return 128;
+    if (per_sm >= 3) return 256;
+    if (per_sm >= 2) return 512;
+    return b->N > 128 ? 1024 : 512;
 }
 
 int finish(cudaError_t launch_err) { return launch_err == cudaSuccess ? FL_OK : (int)launch_err; }
@@ -225,7 +237,7 @@ int fl_distance_map(const FlBatch *b, void *stream) {
 int fl_walk_tables(const FlBatch *b, int fill, void *stream) {
     if (int rc = check_batch(b)) return rc;
     if (!b->ridx || !b->walk_total) return FL_ERR_BAD_ARG;
-    if (fill && (!b->srec || !b->wrec || !b->whoff || !b->wlist || !b->whits || !b->kcls || !b->sdist || !b->dist || b->state_stride <= 0 || b->wlist_stride <= 0 ||
+    if (fill && (!b->srec || !b->wrec || !b->whoff || !b->wlist || !b->whits || !b->kcls || !b->sdist || !b->gtab || !b->dist || b->state_stride <= 0 || b->wlist_stride <= 0 ||
                  b->whits_stride <= 0))
         return FL_ERR_BAD_ARG;
     cudaStream_t st = (cudaStream_t)stream;
@@ -268,7 +280,7 @@ int fl_observe(const FlBatch *b, float *d_agent_attr, float *d_forest, int32_t *
     if (int rc = check_batch(b)) return rc;
     if (!d_agent_attr || !d_forest || !d_adjacency || !d_node_order || !d_edge_order || !d_valid_actions || !d_dist_target)
         return FL_ERR_BAD_ARG;
-    if (!b->srec || !b->wrec || !b->whoff || !b->wlist || !b->whits || !b->kcls || !b->sdist || !b->ridx || !b->walk_total) return FL_ERR_BAD_ARG;   // fl_walk_tables first
+    if (!b->srec || !b->wrec || !b->whoff || !b->wlist || !b->whits || !b->kcls || !b->sdist || !b->gtab || !b->ridx || !b->walk_total) return FL_ERR_BAD_ARG;   // fl_walk_tables first
     cudaStream_t st = (cudaStream_t)stream;
     const int nt = obs_threads(b);
     int ctas = 1;
@@ -279,7 +291,9 @@ int fl_observe(const FlBatch *b, float *d_agent_attr, float *d_forest, int32_t *
     Kern kern;
     if (nt == 64) kern = ctas > 8 ? k_observe<64, 12> : k_observe<64, 8>;
     else if (nt == 128) kern = ctas > 6 ? k_observe<128, 8> : ctas > 4 ? k_observe<128, 6> : k_observe<128, 4>;
-    else kern = ctas > 3 ? k_observe<256, 4> : ctas > 2 ? k_observe<256, 3> : k_observe<256, 2>;
+    else if (nt == 256) kern = ctas > 3 ? k_observe<256, 4> : ctas > 2 ? k_observe<256, 3> : k_observe<256, 2>;
+    else if (nt == 512) kern = ctas > 1 ? k_observe<512, 2> : k_observe<512, 1>;
+    else kern = k_observe<1024, 1>;
     if (lay.total > 48 * 1024) {
         cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, lay.total);
         if (err != cudaSuccess) return (int)err;
@@ -300,7 +314,7 @@ int fl_batch_slice(const FlBatch *b, int64_t e0, int64_t n, FlBatch *out) {
     FL_ADV(init_rc, N * 2) FL_ADV(tgt_rc, N * 2) FL_ADV(init_dir, N) FL_ADV(max_count, N) FL_ADV(slot, N) FL_ADV(speed, N)
     FL_ADV(earliest, N) FL_ADV(latest, N) FL_ADV(sched, b->S * N)
     FL_ADV(ridx, b->ridx_stride) FL_ADV(srec, b->state_stride) FL_ADV(wrec, b->state_stride * 4) FL_ADV(whoff, b->state_stride)
-    FL_ADV(wlist, b->wlist_stride) FL_ADV(whits, b->whits_stride) FL_ADV(kcls, b->state_stride) FL_ADV(sdist, b->n_slots * b->state_stride) FL_ADV(walk_total, 4)
+    FL_ADV(wlist, b->wlist_stride) FL_ADV(whits, b->whits_stride) FL_ADV(kcls, b->state_stride) FL_ADV(sdist, b->n_slots * b->state_stride) FL_ADV(gtab, b->n_slots * b->state_stride) FL_ADV(walk_total, 4)
     FL_ADV(rc, N * 2) FL_ADV(old_rc, N * 2) FL_ADV(dir, N) FL_ADV(old_dir, N) FL_ADV(state, N) FL_ADV(ctr, N) FL_ADV(mal, N)
     FL_ADV(saved, N) FL_ADV(sig_mal, N) FL_ADV(deadlocked, N) FL_ADV(done, N) FL_ADV(nmal, N) FL_ADV(arrival, N)
     FL_ADV(elapsed, 1) FL_ADV(sched_pos, 1) FL_ADV(done_all, 1) FL_ADV(status, 1)

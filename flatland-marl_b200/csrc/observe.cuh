@@ -36,7 +36,7 @@ namespace {
 constexpr int I_INF = 0x7fffffff;
 
 struct ObsLayout {   // byte offsets into dynamic shared memory (host: make_obs_layout); < 0 = lives in global memory
-    int bar, part, ag, dl, ci, ks, bm, sq, kcls, grid, ridx, ent, ent_cap, total;
+    int bar, part, ag, dl, ci, ks, bm, sq, seg_cap, kcls, grid, ridx, ent, ent_cap, total;
     int srec, wrec, whoff, whits, wlist, sdist;   // static walk tables (walks.cuh)
 };
 
@@ -355,6 +355,7 @@ k_observe(FlBatch b, ObsLayout lay, float *__restrict__ out_attr, float *__restr
     const uint32_t *g_wlist = b.wlist + (size_t)e * b.wlist_stride;
     const uint32_t *g_whits = b.whits + (size_t)e * b.whits_stride;
     const uint16_t *g_sdist = b.sdist + (size_t)e * b.n_slots * SS;
+    const uint32_t *gtab = b.gtab + (size_t)e * b.n_slots * SS;
     const uint16_t *grid = lay.grid >= 0 ? reinterpret_cast<const uint16_t *>(smraw + lay.grid) : g_grid;
     const uint16_t *ridx = lay.ridx >= 0 ? reinterpret_cast<const uint16_t *>(smraw + lay.ridx) : g_ridx;
     const uint32_t *srec = lay.srec >= 0 ? reinterpret_cast<const uint32_t *>(smraw + lay.srec) : g_srec;
@@ -408,7 +409,7 @@ k_observe(FlBatch b, ObsLayout lay, float *__restrict__ out_attr, float *__restr
         const uint32_t sb = (uint32_t)(SS * 4);
         const uint32_t lb = lay.wlist >= 0 ? (uint32_t)(b.wlist_stride * 4) : 0u;
         const uint32_t hb = lay.whits >= 0 ? (uint32_t)(b.whits_stride * 4) : 0u;
-        const uint32_t kb = lay.kcls >= 0 ? (uint32_t)(SS * 2) : 0u;
+        const uint32_t kb = lay.kcls >= 0 ? (uint32_t)(SS / 2) : 0u;     // one uint16 per rail cell
         const uint32_t db = lay.sdist >= 0 ? (uint32_t)(b.n_slots * SS * 2) : 0u;
         mbar_expect_tx(bar, gb + rb + lb + hb + kb + db + (lay.srec >= 0 ? sb : 0u) + (lay.wrec >= 0 ? 4 * sb : 0u) + (lay.whoff >= 0 ? sb : 0u));
         if (gb) tma_load_1d(smraw + lay.grid, g_grid, gb, bar);
@@ -428,7 +429,7 @@ k_observe(FlBatch b, ObsLayout lay, float *__restrict__ out_attr, float *__restr
     const float T_ = (float)b.max_steps[e], Nf = (float)N;
     const Scale sc{T_, __frcp_rn(T_), Nf, __frcp_rn(Nf)};
     const int elapsed = b.elapsed[e];
-    if (tid < 4) s_misc[tid] = 0;                  // [0] entries, [1] next agent of phase 4, [2] max time per cell, [3] bad cell met
+    if (tid < 4) s_misc[tid] = 0;                  // [0] path segments, then entries, [1] next agent of phase 4, [2] max time per cell, [3] bad cell met
     __syncthreads();                               // mbarrier initialised, counters zeroed
     OBS_TICK(0);
     if (use_tma) mbar_wait(bar, 0);
@@ -524,14 +525,75 @@ k_observe(FlBatch b, ObsLayout lay, float *__restrict__ out_attr, float *__restr
         asm volatile("bar.sync 2, %0;" ::"r"(NT) : "memory");    // the prediction index is complete (the other warps only arrive)
         if (s_misc[0] > lay.ent_cap) ent = b.entries + (size_t)e * b.ent_cap;
     } else {
-        // counting pass: one predicted path per agent, count per rail cell (or key class)
+        // Predicted paths as segments (predictions.cpp:13-235): a path is a chain of static walks, gtab tells where it
+        // continues after each of them.  One lane per agent follows the chain (one dependent load per walk) and writes
+        // a segment record per walk into a pool; the occupancy intervals of a segment are then emitted by any thread.
+        uint2 *pool = reinterpret_cast<uint2 *>(smraw + lay.sq);      // state | last step << 16 | direction before << 30,
+                                                                      // agent | first path index << 10 | direction after << 19 | last << 21
         for (int i = tid; i < N; i += NW) {
             const uint32_t info = A.info[i];
-            const unsigned slot = (info >> 8) & 0xFFFFu, s0 = A.sid0[i];
-            if (s0 == 0xFFFFu) continue;
-            predict_path(wrec, whoff, whits, wlist, sdist + (size_t)slot * SS, s0, slot, (int)(info >> 24), i,
-                         [&](unsigned rail, int, int, uint32_t) { atomicAdd(&ks[kcls ? (unsigned)kcls[rail] : rail], 1u); });
+            const unsigned slot = (info >> 8) & 0xFFFFu;
+            unsigned sid = A.sid0[i];
+            if (sid == 0xFFFFu) continue;
+            const int tpc = (int)(info >> 24);
+            const uint32_t *gt = gtab + (size_t)slot * SS;
+            unsigned dp = sid & 3u;
+            int kk = 0;
+            const bool stuck = sdist[(size_t)slot * SS + sid] == FL_DIST_INF;   // no move lowers the distance: a single element
+            while (true) {
+                const uint32_t g = stuck ? 0xFFFFu : gt[sid];
+                const unsigned nxt = g & 0xFFFFu, kend = (g >> 16) & 0x3FFFu;
+                const int pos = atomicAdd(&s_misc[0], 1);
+                if (pos < lay.seg_cap)
+                    pool[pos] = make_uint2(sid | (kend << 16) | (dp << 30),
+                                           (unsigned)i | ((unsigned)kk << 10) | ((nxt & 3u) << 19) | ((nxt == 0xFFFFu ? 1u : 0u) << 21));
+                kk += (int)kend + 1;
+                if (nxt == 0xFFFFu || kk > FL_PRED_DEPTH || 1 + (kk - 1) * tpc >= NPRED) break;
+                dp = g >> 30; sid = nxt;
+            }
         }
+        named_bar_sync(1, NW);
+        const int n_seg = s_misc[0];
+        if (dbg && tid == 0) dbg[11] = n_seg;
+        const bool pooled = n_seg <= lay.seg_cap;  // else: every lane walks its agent's path itself (predict_path), twice
+        // Emit(rail cell, t0, t1, entry) for every occupied element of pool segment j
+        auto emit_segment = [&](int j, auto emit) {
+            const uint2 sg = pool[j];
+            const unsigned sid = sg.x & 0xFFFFu;
+            const int kend = (int)((sg.x >> 16) & 0x3FFFu), agent = (int)(sg.y & 1023u), kk = (int)((sg.y >> 10) & 511u);
+            const bool seg_last = (sg.y >> 21) & 1u;
+            const int tpc = (int)(A.info[agent] >> 24);
+            int dp = (int)(sg.x >> 30);
+            const uint32_t wx = wrec[sid].x;
+            for (int k0 = 0; k0 <= kend; k0 += 4) {  // four states per round: one memory latency per round (8 elements of slack in wlist)
+                unsigned sv[5];
+#pragma unroll
+                for (int u = 0; u < 5; u++) sv[u] = wlist[wx + k0 + u];
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    const int k = k0 + u;
+                    if (k > kend) return;
+                    const int idx = kk + k;
+                    const int t0 = idx ? 1 + (idx - 1) * tpc : 0;
+                    if (t0 >= NPRED) return;
+                    const bool last = (k == kend && seg_last) || idx >= FL_PRED_DEPTH;
+                    const int d = (int)(sv[u] & 3u), dn = last ? d : (k < kend ? (int)(sv[u + 1] & 3u) : (int)((sg.y >> 19) & 3u));
+                    const int t1 = last ? NPRED - 1 : min(idx ? idx * tpc : 0, NPRED - 1);
+                    emit((sv[u] & 0xFFFFu) >> 2, t0, t1, pack_entry(agent, t0, t1, d, dp, dn));
+                    if (last) return;
+                    dp = d;
+                }
+            }
+        };
+        auto count_emit = [&](unsigned rail, int, int, uint32_t) { atomicAdd(&ks[kcls ? (unsigned)kcls[rail] : rail], 1u); };
+        // counting pass: entries per rail cell (or key class)
+        if (pooled) { for (int j = tid; j < n_seg; j += NW) emit_segment(j, count_emit); }
+        else
+            for (int i = tid; i < N; i += NW) {
+                const uint32_t info = A.info[i];
+                const unsigned slot = (info >> 8) & 0xFFFFu, s0 = A.sid0[i];
+                if (s0 != 0xFFFFu) predict_path(wrec, whoff, whits, wlist, sdist + (size_t)slot * SS, s0, slot, (int)(info >> 24), i, count_emit);
+            }
         named_bar_sync(1, NW);
         OBS_TICK(2);
         // exclusive scan of ks[0..R] (R+1 values; the last becomes the total)
@@ -553,21 +615,22 @@ k_observe(FlBatch b, ObsLayout lay, float *__restrict__ out_attr, float *__restr
         if (tid == 0) s_misc[0] = n_ent;
         if (n_ent > lay.ent_cap) ent = b.entries + (size_t)e * b.ent_cap;   // does not fit in shared memory: global spill space
         // scatter pass.  ks[key] is advanced to the END of its bucket; bucket r is [ks[r-1], ks[r]) afterwards (ks[-1] = 0).
-        for (int i = tid; i < N; i += NW) {
-            const uint32_t info = A.info[i];
-            const unsigned slot = (info >> 8) & 0xFFFFu, s0 = A.sid0[i];
-            if (s0 == 0xFFFFu) continue;
-            predict_path(wrec, whoff, whits, wlist, sdist + (size_t)slot * SS, s0, slot, (int)(info >> 24), i,
-                         [&](unsigned rail, int t0, int t1, uint32_t en) {
-                             const unsigned key = kcls ? (unsigned)kcls[rail] : rail;
-                             ent[atomicAdd(&ks[key], 1u)] = en;
-                             const int sa = t0 >> 2, sb = t1 >> 2;             // time slots of 4 rows the entry overlaps
-                             for (int wd = sa >> 5; wd <= sb >> 5; wd++) {
-                                 const int lo_b = max(sa - 32 * wd, 0), hi_b = min(sb - 32 * wd, 31);
-                                 atomicOr(&bm[key * 4 + wd], (0xFFFFFFFFu >> (31 - hi_b)) & (0xFFFFFFFFu << lo_b));
-                             }
-                         });
-        }
+        auto scatter_emit = [&](unsigned rail, int t0, int t1, uint32_t en) {
+            const unsigned key = kcls ? (unsigned)kcls[rail] : rail;
+            ent[atomicAdd(&ks[key], 1u)] = en;
+            const int sa = t0 >> 2, sb = t1 >> 2;             // time slots of 4 rows the entry overlaps
+            for (int wd = sa >> 5; wd <= sb >> 5; wd++) {
+                const int lo_b = max(sa - 32 * wd, 0), hi_b = min(sb - 32 * wd, 31);
+                atomicOr(&bm[key * 4 + wd], (0xFFFFFFFFu >> (31 - hi_b)) & (0xFFFFFFFFu << lo_b));
+            }
+        };
+        if (pooled) { for (int j = tid; j < n_seg; j += NW) emit_segment(j, scatter_emit); }
+        else
+            for (int i = tid; i < N; i += NW) {
+                const uint32_t info = A.info[i];
+                const unsigned slot = (info >> 8) & 0xFFFFu, s0 = A.sid0[i];
+                if (s0 != 0xFFFFu) predict_path(wrec, whoff, whits, wlist, sdist + (size_t)slot * SS, s0, slot, (int)(info >> 24), i, scatter_emit);
+            }
         named_bar_sync(1, NW);
         // order every bucket: long-lived entries first, then by t0, so that the tree walk scans a time window only
         for (int key = tid; key < R; key += NW) {

@@ -24,6 +24,8 @@
 //                  H > W: cells (r, c) and (r + W, c - 1) share a key and conflict with each other's predictions.  kcls maps
 //                  a rail cell to the lowest rail index of its key class (itself when H <= W)
 //   sdist[slot][sid] the distance map of fl_distance_map indexed by state id
+//   gtab[slot][sid]  how the shortest path to the slot's target continues after the walk from sid: next state | last step of
+//                  the walk on the path << 16 | direction of the state at that step << 30
 // FILL = false only measures (states, list length, hits) so that the host can size wlist and whits.
 #pragma once
 #include "common.cuh"
@@ -254,7 +256,45 @@ __global__ void __launch_bounds__(NT) k_walks(FlBatch b) {
             sd[idx] = (uint16_t)v;
         }
     }
-    if (tid == 0) { tot[0] = S; tot[1] = (int)total; tot[2] = (int)total_h; tot[3] = 0; }
+    // where the shortest path to each slot's target continues after the walk from a state (predictions.cpp:13-144): the walk
+    // is followed to its end or to the slot's target; at a switch or dead end the child state with the lowest distance is
+    // taken, the first of equals in the order left, forward, right
+    __syncthreads();
+    __shared__ int s_long;
+    if (tid == 0) s_long = 0;
+    __syncthreads();
+    {
+        uint32_t *gt = b.gtab + (size_t)e * b.n_slots * b.state_stride;
+        const uint16_t *sd = b.sdist + (size_t)e * b.n_slots * b.state_stride;
+        const int ss = (int)b.state_stride, n = (int)b.n_slots * ss;
+        for (int idx = tid; idx < n; idx += NT) {
+            const int s = idx / ss, sid = idx - s * ss;
+            uint32_t g = 0xFFFFu;
+            if (sid < S) {
+                const uint4 w = wrec[sid];
+                const int L = (int)(w.y & 0xFFFFu), kind = (int)((w.y >> 16) & 15u), nh = (int)((w.y >> 20) & 255u);
+                int kend = L;
+                bool hit = false;
+                for (int q = 0; q < nh; q++) {
+                    const uint32_t hv = whits[whoff[sid] + q];
+                    if ((int)(hv >> 16) == s) { kend = (int)(hv & 0xFFFFu); hit = true; break; }
+                }
+                unsigned nxt = 0xFFFFu;
+                if (!hit && (kind == WK_SWITCH || kind == WK_DEADEND)) {
+                    const unsigned ch[3] = {w.z & 0xFFFFu, w.z >> 16, w.w & 0xFFFFu};
+                    unsigned best = FL_DIST_INF;
+                    for (int j = 0; j < 3; j++)
+                        if (ch[j] != 0xFFFFu) { const unsigned v = sd[(size_t)s * ss + ch[j]]; if (v < best) { best = v; nxt = ch[j]; } }
+                }
+                if (kend > 0x3FFF) { s_long = 1; kend = 0x3FFF; }
+                const unsigned edir = wlist[w.x + kend] & 3u;
+                g = nxt | ((uint32_t)kend << 16) | (edir << 30);
+            }
+            gt[idx] = g;
+        }
+    }
+    __syncthreads();
+    if (tid == 0) { tot[0] = S; tot[1] = (int)total; tot[2] = (int)total_h; tot[3] = s_long; }
 }
 
 }  // namespace

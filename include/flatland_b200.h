@@ -66,7 +66,7 @@ typedef struct FlBatch {
                             >= n_slots*H*W*4, multiple of 8 (16-byte aligned blocks: moved by TMA bulk copies) */
     int64_t *debug_clocks; /* tuning only: [E][16] SM-clock timestamps of k_observe's phases, NULL = off */
     int64_t ridx_stride;   /* uint16 elements per env of ridx, >= H*W, multiple of 8 */
-    int64_t state_stride;  /* elements per env of srec / wrec / whoff / kcls, >= 4 * rail cells, multiple of 8 */
+    int64_t state_stride;  /* elements per env of srec / wrec / whoff / kcls, >= 4 * rail cells, multiple of 32 */
     int64_t wlist_stride;  /* uint32 elements per env of wlist, multiple of 4, with 8 elements of slack at the end */
     int64_t whits_stride;  /* uint32 elements per env of whits, multiple of 4 */
 
@@ -98,7 +98,11 @@ typedef struct FlBatch {
                                   prediction key c*W + r (only cells of grids with H > W have partners) */
     uint16_t *sdist;           /* [E][n_slots][state_stride] the distance map indexed by state id (copy of `dist` on the rail
                                   cells only; fl_walk_tables(fill) runs after fl_distance_map) */
-    int32_t *walk_total;       /* [E][4] written by fl_walk_tables: states, wlist elements, whits elements, 0 */
+    uint32_t *gtab;            /* [E][n_slots][state_stride] where the shortest path to the slot's target continues after the
+                                  walk from a state: next state (0xFFFF = the path ends with this walk) | last step of the walk
+                                  on the path<<16 (14 bits) | direction of the state at that step<<30 */
+    int32_t *walk_total;       /* [E][4] written by fl_walk_tables: states, wlist elements, whits elements, 1 if a walk is
+                                  longer than 16383 steps (unsupported) */
 
     /* ---- agent state (agent_utils.py:58-105 and step_utils/*) ---- */
     int16_t *rc;          /* [E][N][2] position, (-1,-1) = None */

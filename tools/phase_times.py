@@ -28,7 +28,7 @@ for t in range(steps):
         acc.append(batch.debug_clocks.cpu().numpy().copy())
 d = np.stack(acc).astype(np.float64)          # [20, E, 16]
 t0 = d[..., 15]
-names = [("setup+zero", 15, 0), ("tma wait+loader+occupancy", 0, 1), ("prediction count pass", 1, 2), ("scan+scatter pass+sort", 2, 3),
+names = [("setup+zero", 15, 0), ("tma wait+loader+occupancy", 0, 1), ("path chains + count pass", 1, 2), ("scan+scatter pass+sort", 2, 3),
          ("trees (structure+features)", 3, 5), ("attributes", 6, 7)]
 tot = d[..., 7] - t0
 print("%s E=%d N=%d: mean cycles per env %.0f (p50 %.0f, p99 %.0f, max %.0f)" % (cfg, E, N, tot.mean(), np.median(tot), np.percentile(tot, 99), tot.max()))
@@ -37,4 +37,5 @@ for nm, a, b in names:
     print("  %-40s mean %9.0f  p99 %9.0f  (%.1f%%)" % (nm, x.mean(), np.percentile(x, 99), 100 * x.mean() / tot.mean()))
 dl = d[..., 8] - d[..., 1]
 print("  %-40s mean %9.0f  p99 %9.0f" % ("deadlock lane (from occupancy done)", dl.mean(), np.percentile(dl, 99)))
-print("  entries per env: mean %.0f max %.0f" % (d[..., 10].mean(), d[..., 10].max()))
+print("  entries per env: mean %.0f max %.0f; path segments per env: mean %.0f p99 %.0f max %.0f" %
+      (d[..., 10].mean(), d[..., 10].max(), d[..., 11].mean(), np.percentile(d[..., 11], 99), d[..., 11].max()))
