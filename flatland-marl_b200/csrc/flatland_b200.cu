@@ -100,12 +100,12 @@ ObsLayout make_obs_layout(const FlBatch *b, int nt, int *ctas_out = nullptr) {
     int off = 0;
     auto take = [&](long long bytes) { const int o = off; off = align_up(off + (int)bytes, 128); return o; };
     L.bar = take(32);
-    L.part = take(nt * 4);
+    L.part = take(128);
     L.ag = take((long long)OBS_AGENT_WORDS * N * 4);
     L.dl = take(18 * N);
     L.ci = take((long long)Rmax * 4);
     L.ks = take((long long)(Rmax + 2) * 4);
-    L.bm = take((long long)Rmax * 16);                          // time-slot filter of the prediction index
+    L.bm = take((long long)Rmax * 32);                          // time-slot filter of the prediction index: one / two entries per slot
     L.seg_cap = 10 * N;                                         // path segments of phase 3 share the room of the phase-4 queues
     if (L.seg_cap < (nt / 32) * 64) L.seg_cap = (nt / 32) * 64;
     L.sq = take((long long)L.seg_cap * 8);                      // per-warp queues of the full conflict checks / segment pool
@@ -114,8 +114,8 @@ ObsLayout make_obs_layout(const FlBatch *b, int nt, int *ctas_out = nullptr) {
     const long long grid_b = b->grid_stride * 2, ridx_b = b->ridx_stride * 2;
     const long long st_b = b->state_stride * 4, wl_b = b->wlist_stride * 4, wh_b = b->whits_stride * 4;
     const long long sd_b = b->n_slots * b->state_stride * 2;
-    const long long core = off + grid_b + ridx_b + ent_typ + 4 * 128;
-    int want_tables = 0x37;                                     // bit k: wlist, wrec, sdist, (srec: unused by k_observe), whoff, whits
+    const long long core = off + ridx_b + ent_typ + 3 * 128;
+    int want_tables = 0x77;                                     // bit k: wlist, wrec, sdist, (srec: unused by k_observe), whoff, whits
     if (const char *s = getenv("FL_OBS_TABLES")) want_tables = atoi(s);
     const int max_ctas = nt >= 1024 ? 1 : nt == 512 ? 2 : nt == 256 ? 4 : nt == 128 ? 8 : 12;
     int ctas = 0;
@@ -126,7 +126,6 @@ ObsLayout make_obs_layout(const FlBatch *b, int nt, int *ctas_out = nullptr) {
     if (ctas_out) *ctas_out = ctas;
     const int budget = SMEM_MAX / ctas - 1024;
     auto opt = [&](long long bytes) { if ((long long)off + bytes + 128 > budget) return -1; return take(bytes); };
-    L.grid = opt(grid_b);
     L.ridx = opt(ridx_b);
     long long reserve = ent_typ + 128;                           // keep room for the entries while placing the tables
     auto table = [&](int bit, long long bytes) {
@@ -139,6 +138,7 @@ ObsLayout make_obs_layout(const FlBatch *b, int nt, int *ctas_out = nullptr) {
     L.srec = table(3, st_b);
     L.whoff = table(4, st_b);
     L.whits = table(5, wh_b);
+    L.grid = table(6, grid_b);                                  // only phase 1 reads the grid
     // entries: at least the typical size, at most twice that (more is never needed; larger counts spill to global memory)
     long long ent_b = (long long)budget - off - 128;
     if (ent_b > 2 * ent_typ) ent_b = 2 * ent_typ;

@@ -296,7 +296,7 @@ DEVI void store_null_node(float *forest_node) {
 }
 
 // per-agent shared-memory record (struct of arrays, N entries each)
-constexpr int OBS_AGENT_WORDS = 16;
+constexpr int OBS_AGENT_WORDS = 11;
 struct ObsAgents {
     uint32_t *vrc;      // virtual position r | c << 16 (loader.cpp:87-101)
     uint32_t *sid0;     // state id of the virtual position and direction (walks.cuh), 0xFFFF = not on a rail cell
@@ -306,9 +306,8 @@ struct ObsAgents {
     int *cellid;        // on-map cell index, -1 otherwise
     int *initcell;      // initial cell index while off map, -1 otherwise
     uint32_t *rec_a;    // st | road << 3 | idir << 7 | od << 9 | ctr << 11 | maxc << 19 | va << 27
-    uint32_t *rec_b;    // trans | nmal01 << 16 | mal01 << 17 | sig_mal << 18
+    uint32_t *rec_b;    // trans | nmal01 << 16 | mal01 << 17 | sig_mal << 18 | transitions nibble of the virtual position << 20
     uint32_t *m0, *m1;  // attribute entries 0..63 as bits (feature_parser.cpp:19-77), entry 41 (deadlocked) left out
-    float *f_earliest, *f_latest, *f_arrival, *f_dist;   // (f_idist follows as the 16th array)
 };
 
 // position of the n-th (0-based) set bit of m; the caller guarantees that m has more than n set bits.  Five popc
@@ -367,23 +366,19 @@ k_observe(FlBatch b, ObsLayout lay, float *__restrict__ out_attr, float *__restr
     const uint16_t *kcls = lay.kcls >= 0 ? reinterpret_cast<const uint16_t *>(smraw + lay.kcls) : nullptr;   // only when H > W
     uint32_t *ci = reinterpret_cast<uint32_t *>(smraw + lay.ci);             // [R] occupancy word per rail cell
     uint32_t *ks = reinterpret_cast<uint32_t *>(smraw + lay.ks) + 1;         // ks[-1..R]: bucket r = [ks[r-1], ks[r])
-    uint32_t *bm = reinterpret_cast<uint32_t *>(smraw + lay.bm);             // [R][4] bit s: some prediction entry of the key overlaps rows 4s..4s+3
+    uint2 *bm = reinterpret_cast<uint2 *>(smraw + lay.bm);                   // [R][4] bit s of .x / .y: at least one / two prediction entries of the key overlap rows 4s..4s+3
     uint2 *sq = reinterpret_cast<uint2 *>(smraw + lay.sq) + warp * 64;       // this warp's queue of cells that need the full conflict check
     uint32_t *s_part = reinterpret_cast<uint32_t *>(smraw + lay.part);
     uint64_t *bar = reinterpret_cast<uint64_t *>(smraw + lay.bar);
     int *s_misc = reinterpret_cast<int *>(smraw + lay.bar + 16);
 
     ObsAgents A;
-    float *f_idist;
     {
         uint32_t *p = reinterpret_cast<uint32_t *>(smraw + lay.ag);
         A.vrc = p; p += N; A.sid0 = p; p += N; A.info = p; p += N;
         A.speed = reinterpret_cast<float *>(p); p += N; A.dt = reinterpret_cast<float *>(p); p += N;
         A.cellid = reinterpret_cast<int *>(p); p += N; A.initcell = reinterpret_cast<int *>(p); p += N;
         A.rec_a = p; p += N; A.rec_b = p; p += N; A.m0 = p; p += N; A.m1 = p; p += N;
-        A.f_earliest = reinterpret_cast<float *>(p); p += N; A.f_latest = reinterpret_cast<float *>(p); p += N;
-        A.f_arrival = reinterpret_cast<float *>(p); p += N; A.f_dist = reinterpret_cast<float *>(p); p += N;
-        f_idist = reinterpret_cast<float *>(p);     // 16th array
     }
     DeadlockScratch D;
     {
@@ -397,7 +392,7 @@ k_observe(FlBatch b, ObsLayout lay, float *__restrict__ out_attr, float *__restr
     // optional phase timestamps (tuning only): FlBatch.debug_clocks [E][16] int64, NULL = off
     int64_t *dbg = b.debug_clocks ? b.debug_clocks + (size_t)e * 16 : nullptr;
 #define OBS_TICK(k) do { if (dbg && tid == 0) dbg[k] = clock64(); } while (0)
-    if (dbg && tid == 0) dbg[15] = clock64();
+    if (dbg && tid == 0) { dbg[15] = clock64(); dbg[12] = 0; dbg[13] = 0; dbg[14] = 0; }
     // ---- phase 0: TMA bulk copies of the static world ---------------------------------------------
     const bool use_tma = lay.grid >= 0 || lay.ridx >= 0 || lay.srec >= 0 || lay.wrec >= 0 || lay.whoff >= 0 || lay.whits >= 0 ||
                          lay.wlist >= 0 || lay.kcls >= 0 || lay.sdist >= 0;
@@ -425,7 +420,7 @@ k_observe(FlBatch b, ObsLayout lay, float *__restrict__ out_attr, float *__restr
     // zero the bucket counters and the occupancy words
     for (int k = tid; k <= R + 1; k += NT) ks[k - 1] = 0;
     for (int k = tid; k < R; k += NT) ci[k] = 0;
-    for (int k = tid; k < R * 4; k += NT) bm[k] = 0;
+    for (int k = tid; k < R * 4; k += NT) bm[k] = make_uint2(0u, 0u);
     const float T_ = (float)b.max_steps[e], Nf = (float)N;
     const Scale sc{T_, __frcp_rn(T_), Nf, __frcp_rn(Nf)};
     const int elapsed = b.elapsed[e];
@@ -478,18 +473,35 @@ k_observe(FlBatch b, ObsLayout lay, float *__restrict__ out_attr, float *__restr
         const int nmal01 = b.nmal[ea] != 0, mal01 = b.mal[ea] != 0, sig_mal = b.sig_mal[ea] != 0;
         A.rec_a[i] = (uint32_t)st | ((uint32_t)road << 3) | ((uint32_t)idir << 7) | ((uint32_t)od << 9) |
                      ((uint32_t)ctr << 11) | ((uint32_t)maxc << 19) | ((uint32_t)va << 27);
-        A.rec_b[i] = (uint32_t)trans_attr | ((uint32_t)nmal01 << 16) | ((uint32_t)mal01 << 17) | ((uint32_t)sig_mal << 18);
+        A.rec_b[i] = (uint32_t)trans_attr | ((uint32_t)nmal01 << 16) | ((uint32_t)mal01 << 17) | ((uint32_t)sig_mal << 18) |
+                     ((uint32_t)nibble(grid[vr * W + vc], d) << 20);
         // entries 0..63 of the attribute vector are one-hot codes and flags: bit k of (m0, m1) = entry k
         A.m0[i] = (1u << st) | (1u << (7 + road)) | (1u << (18 + nmal01)) | (1u << (28 + idir));
         A.m1[i] = (1u << d) | (1u << (4 + od)) | ((uint32_t)(st == MOVING) << 8) | ((uint32_t)sig_mal << 10) | ((uint32_t)!mal01 << 11) |
                   ((uint32_t)(ctr == 0) << 12) | ((uint32_t)(ctr == maxc) << 13) | ((uint32_t)(st == MALFUNCTION || st == MAL_OFF) << 14) |
                   ((uint32_t)off_map(st) << 15) | ((uint32_t)on_map(st) << 16) | (__brev((unsigned)trans_attr) << 1);
-        const float max_dist = (float)((H + W) * 8);
-        A.f_earliest[i] = (float)b.earliest[ea] / T_;
-        A.f_latest[i] = (float)b.latest[ea] / T_;
-        A.f_arrival[i] = (float)b.arrival[ea] / T_;
-        A.f_dist[i] = dt == INFINITY ? 8.0f : dt / max_dist;
-        f_idist[i] = idv == FL_DIST_INF ? 8.0f : (float)idv / max_dist;
+        // entries 70..82 are floats (feature_parser.cpp:78-94): written here by the agent's own lane, every lane in the
+        // same expression at the same time (phase 5 writes the flag entries 0..69)
+        {
+            const float max_dist = (float)((H + W) * 8);
+            const float curr_step = (float)elapsed / T_;
+            const float latest = (float)b.latest[ea] / T_, before_late = __fsub_rn(latest, curr_step);
+            const float dist_f = dt == INFINITY ? 8.0f : dt / max_dist;
+            float *fa = out_attr + ea * FL_ATTR_F + 70;
+            fa[0] = (float)i / Nf;
+            fa[1] = curr_step;
+            fa[2] = (float)b.earliest[ea] / T_;
+            fa[3] = latest;
+            fa[4] = (float)b.arrival[ea] / T_;
+            fa[5] = before_late;
+            fa[6] = dist_f;
+            fa[7] = before_late < dist_f ? before_late : dist_f;
+            fa[8] = (float)maxc / 10.0f;
+            fa[9] = speed / 1.0f;
+            fa[10] = (float)ctr / 10.0f;
+            fa[11] = (float)mal01 / 10.0f;
+            fa[12] = idv == FL_DIST_INF ? 8.0f : (float)idv / max_dist;
+        }
     }
     __syncthreads();
     // occupancy word per rail cell (treeobs.cpp:67-92, deadlock_checker.cpp:15-20): the HIGHEST handle standing on the
@@ -600,18 +612,24 @@ k_observe(FlBatch b, ObsLayout lay, float *__restrict__ out_attr, float *__restr
         const int per = (R + 1 + NW - 1) / NW, lo = min(tid * per, R + 1), hi = min(lo + per, R + 1);
         uint32_t sum = 0;
         for (int k = lo; k < hi; k++) sum += ks[k];
-        s_part[tid] = sum;
-        named_bar_sync(1, NW);
-        for (int off = 1; off < NW; off <<= 1) {   // Hillis-Steele inclusive scan of the partials
-            const uint32_t v = tid >= off ? s_part[tid - off] : 0;
-            named_bar_sync(1, NW);
-            s_part[tid] += v;
-            named_bar_sync(1, NW);
+        uint32_t incl = sum;                        // inclusive scan of the partial sums: shuffles inside the warp, warp totals through shared memory
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+            if (lane >= o) incl += y;
         }
-        uint32_t run = s_part[tid] - sum;
+        if (lane == 31) s_part[warp] = incl;
+        named_bar_sync(1, NW);
+        uint32_t run = incl - sum, n_total = 0;
+#pragma unroll
+        for (int w2 = 0; w2 < NW / 32; w2++) {
+            const uint32_t wt = s_part[w2];
+            if (w2 < warp) run += wt;
+            n_total += wt;
+        }
         for (int k = lo; k < hi; k++) { const uint32_t v = ks[k]; ks[k] = run; run += v; }
         named_bar_sync(1, NW);
-        const int n_ent = (int)s_part[NW - 1];
+        const int n_ent = (int)n_total;
         if (tid == 0) s_misc[0] = n_ent;
         if (n_ent > lay.ent_cap) ent = b.entries + (size_t)e * b.ent_cap;   // does not fit in shared memory: global spill space
         // scatter pass.  ks[key] is advanced to the END of its bucket; bucket r is [ks[r-1], ks[r]) afterwards (ks[-1] = 0).
@@ -621,7 +639,9 @@ k_observe(FlBatch b, ObsLayout lay, float *__restrict__ out_attr, float *__restr
             const int sa = t0 >> 2, sb = t1 >> 2;             // time slots of 4 rows the entry overlaps
             for (int wd = sa >> 5; wd <= sb >> 5; wd++) {
                 const int lo_b = max(sa - 32 * wd, 0), hi_b = min(sb - 32 * wd, 31);
-                atomicOr(&bm[key * 4 + wd], (0xFFFFFFFFu >> (31 - hi_b)) & (0xFFFFFFFFu << lo_b));
+                const uint32_t m = (0xFFFFFFFFu >> (31 - hi_b)) & (0xFFFFFFFFu << lo_b);
+                const uint32_t twice = atomicOr(&bm[key * 4 + wd].x, m) & m;     // slots that already had an entry
+                if (twice) atomicOr(&bm[key * 4 + wd].y, twice);
             }
         };
         if (pooled) { for (int j = tid; j < n_seg; j += NW) emit_segment(j, scatter_emit); }
@@ -666,15 +686,25 @@ k_observe(FlBatch b, ObsLayout lay, float *__restrict__ out_attr, float *__restr
         // ---- structure: node n in lane n; one round per tree level (treeobs.cpp:171-256 FIFO, 583-608 children) ----
         unsigned sid = 0xFFFFu, wx = 0, kunus = 0xFFFFu, c01 = 0xFFFFFFFFu, c2 = 0xFFFFu;
         int tot0 = 0, kend = 0, kind = 0, parent = 0, ad = 0, level = 0, cb = 1;          // cb: index of the node's first child
+        // onp: the node's walk is part of the observer's own predicted path (its cell at distance tot is path element tot),
+        // gnx: the state the own path continues in after the node's walk (0xFFFF: it does not)
+        bool onp = false;
+        unsigned gnx = 0xFFFFu;
+        const uint32_t *gt = gtab + (size_t)slot * SS;
         if (n >= 1 && n <= 3) {                                                           // roots (treeobs.cpp:171-221)
             const int vr = (int)(short)(A.vrc[h] & 0xFFFF), vc = (int)(A.vrc[h] >> 16), dir = (int)(ainfo & 3);
-            const int nb = nibble(grid[vr * W + vc], dir);
+            const int nb = (int)((A.rec_b[h] >> 20) & 15u);
             int orientation = dir;
             if (__popc(nb) == 1) orientation = first_dir(nb);
             ad = n - 2;
             const int bd = (orientation + ad) & 3;
             sid = (tbit(nb, bd) ? child_state(ridx, H, W, vr, vc, bd) : 0xFFFFFFFFu) & 0xFFFFu;
             tot0 = 1; level = 1; cb = FL_MAX_NODES;
+            const unsigned s0 = A.sid0[h];
+            if (sid != 0xFFFFu && s0 != 0xFFFFu && sd[s0] != FL_DIST_INF) {
+                const uint32_t g0 = gt[s0];                                               // how the own path leaves the root cell
+                onp = ((g0 >> 16) & 0x3FFFu) ? true : sid == (g0 & 0xFFFFu);             // along the walk (one child) or into the greedy child
+            }
         }
         int count = 4, ls = 1, le = 4, cur = 1;
         bool bad = false;
@@ -698,6 +728,7 @@ k_observe(FlBatch b, ObsLayout lay, float *__restrict__ out_attr, float *__restr
                 if (!hit && skind == WK_BAD) bad = true;                     // treeobs.cpp:527-535 throws
                 wx = w.x; kunus = w.w >> 16; c01 = w.z; c2 = w.w & 0xFFFFu;
                 cb = le + 3 * __popc(lmask & ((1u << n) - 1u));
+                if (onp && !hit) gnx = gt[sid] & 0xFFFFu;
             }
             if (le >= FL_MAX_NODES) break;
             const int nle = min(FL_MAX_NODES, le + 3 * __popc(lmask));
@@ -706,10 +737,12 @@ k_observe(FlBatch b, ObsLayout lay, float *__restrict__ out_attr, float *__restr
             const int p = pull ? nth_set_bit(lmask, rt) : 0;
             const unsigned pz = __shfl_sync(0xFFFFFFFFu, c01, p), pw = __shfl_sync(0xFFFFFFFFu, c2, p);
             const int pk = __shfl_sync(0xFFFFFFFFu, kind, p), ptot = __shfl_sync(0xFFFFFFFFu, tot0 + kend + 1, p);
+            const unsigned pg = __shfl_sync(0xFFFFFFFFu, gnx, p);
             if (pull) {
                 unsigned cs = j == 0 ? (pz & 0xFFFFu) : j == 1 ? (pz >> 16) : pw;
                 if (pk > 2) cs = 0xFFFFu;
                 sid = cs; tot0 = ptot; parent = p; ad = j - 1; level = cur + 1; cb = FL_MAX_NODES;
+                onp = cs != 0xFFFFu && cs == pg; gnx = 0xFFFFu;
             }
             ls = le; le = nle; count = nle; cur++;
         }
@@ -742,7 +775,7 @@ k_observe(FlBatch b, ObsLayout lay, float *__restrict__ out_attr, float *__restr
         // lane q holds the q-th real node's (offset, list base, tot0): the owner of a cell is found by rank
         const unsigned src = lane < nreal ? (unsigned)nth_set_bit(real_mask, lane) : 31u;
         const unsigned c_off = __shfl_sync(0xFFFFFFFFu, off, src), c_wb = __shfl_sync(0xFFFFFFFFu, wx, src);
-        const int c_t0 = __shfl_sync(0xFFFFFFFFu, tot0, src);
+        const unsigned c_t0 = __shfl_sync(0xFFFFFFFFu, (unsigned)tot0 | ((onp ? 1u : 0u) << 31), src);   // bit 31: node on the own path
         const bool c_valid = lane < nreal;
         int k_other = I_INF, k_conf = I_INF, same = 0, opp = 0, malf = 0, rtdn = 0, spd_bits = 0x3F800000;  // min speed starts at 1.0f
         const int my_rank = __popc(real_mask & ((1u << lane) - 1u));
@@ -757,7 +790,7 @@ k_observe(FlBatch b, ObsLayout lay, float *__restrict__ out_attr, float *__restr
                 const unsigned starts = __reduce_or_sync(0xFFFFFFFFu, (c_valid && c_off > base && c_off < base + 32) ? 1u << (c_off - base) : 0u);
                 const int rank = cnt0 - 1 + __popc(starts & (0xFFFFFFFFu >> (31 - lane)));
                 const unsigned o_off = __shfl_sync(0xFFFFFFFFu, c_off, rank), o_wb = __shfl_sync(0xFFFFFFFFu, c_wb, rank);
-                const int o_t0 = __shfl_sync(0xFFFFFFFFu, c_t0, rank);
+                const unsigned o_t0 = __shfl_sync(0xFFFFFFFFu, c_t0, rank);
                 bool f_agent = false, f_same = false, f_malf = false, surv = false;
                 int my_rtd = 0, my_spd = 0x3F800000, k = 0, pt = 0;
                 unsigned sidc = 0;                                                  // state id | transitions nibble << 16
@@ -765,7 +798,7 @@ k_observe(FlBatch b, ObsLayout lay, float *__restrict__ out_attr, float *__restr
                     k = (int)(j - o_off);
                     sidc = wlist[o_wb + k];
                     const unsigned rail = (sidc & 0xFFFFu) >> 2;
-                    const int tot = o_t0 + k;
+                    const int tot = (int)(o_t0 & 0x7FFFFFFFu) + k;
                     const uint32_t cinfo = ci[rail];
                     if (cinfo) {                   // treeobs.cpp:322-360 (the observer itself counts too)
                         f_agent = true;
@@ -779,7 +812,15 @@ k_observe(FlBatch b, ObsLayout lay, float *__restrict__ out_attr, float *__restr
                     if (pt < NPRED && tot < NPRED) {                                 // treeobs.cpp:379-465
                         const unsigned bk = kcls ? (unsigned)kcls[rail] : rail;    // the reference's position key c*W + r
                         const int sa = max(0, pt - 1) >> 2, sb = min(NPRED - 1, pt + 1) >> 2;
-                        surv = ((bm[bk * 4 + (sa >> 5)] >> (sa & 31)) | (bm[bk * 4 + (sb >> 5)] >> (sb & 31))) & 1u;
+                        const uint2 wa = bm[bk * 4 + (sa >> 5)], wb = bm[bk * 4 + (sb >> 5)];
+                        // On the own path the observer's own entry (path element tot, rows t0o..t1o) is in the index too: a slot it
+                        // covers needs a second entry to matter.  (t1o is a lower bound for the last element: errs towards checking.)
+                        bool own_a = false, own_b = false;
+                        if ((o_t0 >> 31) && tot <= FL_PRED_DEPTH) {
+                            const int tpc_i = (int)(ainfo >> 24), t0o = 1 + (tot - 1) * tpc_i, t1o = min(tot * tpc_i, NPRED - 1);
+                            if (t0o < NPRED) { own_a = sa >= (t0o >> 2) && sa <= (t1o >> 2); own_b = sb >= (t0o >> 2) && sb <= (t1o >> 2); }
+                        }
+                        surv = (((own_a ? wa.y : wa.x) >> (sa & 31)) | ((own_b ? wb.y : wb.x) >> (sb & 31))) & 1u;
                     }
                 }
                 // what the lanes found returns to the lane owning the node: ballots masked by the node's segment of this window
@@ -805,12 +846,14 @@ k_observe(FlBatch b, ObsLayout lay, float *__restrict__ out_attr, float *__restr
                 const unsigned b_surv = __ballot_sync(0xFFFFFFFFu, surv);
                 if (surv) sq[qn + __popc(b_surv & ((1u << lane) - 1u))] = make_uint2((sidc & 0xFFFFu) | ((unsigned)rank << 16) | ((unsigned)pt << 21), (unsigned)k | (sidc & 0xF0000u));
                 qn += __popc(b_surv);
+                if (dbg && lane == 0) { atomicAdd(reinterpret_cast<unsigned long long *>(&dbg[12]), (unsigned long long)__popc(b_surv)); atomicAdd(reinterpret_cast<unsigned long long *>(&dbg[13]), 1ull); }
                 base += 32;
             }
             if (qn >= 32 || (!more && qn > 0)) {
                 // ---- stage 2: the full conflict check (treeobs.cpp:379-465) of up to 32 queued cells, one per lane ----
                 __syncwarp();
                 const int nq = min(qn, 32);
+                if (dbg && lane == 0) atomicAdd(reinterpret_cast<unsigned long long *>(&dbg[14]), 1ull);
                 bool f_conf = false;
                 uint2 q = make_uint2(0u, 0u);
                 if (lane < nq) {
@@ -913,12 +956,11 @@ k_observe(FlBatch b, ObsLayout lay, float *__restrict__ out_attr, float *__restr
     for (int i = tid; i < N; i += NT) b.deadlocked[(size_t)e * N + i] = D.dl[i];
     OBS_TICK(6);
 
-    // ---- phase 5: agent attributes (feature_parser.cpp:3-98), coalesced over the environment ---------
+    // ---- phase 5: the flag entries 0..69 of the agent attributes (feature_parser.cpp:19-77) from the bit masks ---------
     {
         float *dst = out_attr + (size_t)e * N * FL_ATTR_F;
-        const float curr_step = (float)elapsed / T_;
-        for (int idx = tid; idx < N * FL_ATTR_F; idx += NT) {
-            const int i = idx / FL_ATTR_F, k = idx - i * FL_ATTR_F;
+        for (int idx = tid; idx < N * 70; idx += NT) {
+            const int i = idx / 70, k = idx - i * 70;
             float v;
             if (k < 64) {
                 const uint32_t m = k < 32 ? A.m0[i] : A.m1[i];
@@ -926,29 +968,9 @@ k_observe(FlBatch b, ObsLayout lay, float *__restrict__ out_attr, float *__restr
                 if (k == 41) v = D.dl[i] != 0;
             } else {
                 const uint32_t ra = A.rec_a[i], rb = A.rec_b[i];
-                const int ctr = (ra >> 11) & 255, maxc = (ra >> 19) & 255, va = (ra >> 27) & 31, mal01 = (rb >> 17) & 1;
-                if (k == 64) v = (float)(rb & 1u);
-                else if (k < 70) v = (float)((va >> (k - 65)) & 1);
-                else {
-                    const float latest = A.f_latest[i], before_late = __fsub_rn(latest, curr_step), dist_f = A.f_dist[i];
-                    switch (k - 70) {
-                    case 0: v = (float)i / Nf; break;
-                    case 1: v = curr_step; break;
-                    case 2: v = A.f_earliest[i]; break;
-                    case 3: v = latest; break;
-                    case 4: v = A.f_arrival[i]; break;
-                    case 5: v = before_late; break;
-                    case 6: v = dist_f; break;
-                    case 7: v = before_late < dist_f ? before_late : dist_f; break;
-                    case 8: v = (float)maxc / 10.0f; break;
-                    case 9: v = A.speed[i] / 1.0f; break;
-                    case 10: v = (float)ctr / 10.0f; break;
-                    case 11: v = (float)mal01 / 10.0f; break;
-                    default: v = f_idist[i]; break;
-                    }
-                }
+                v = k == 64 ? (float)(rb & 1u) : (float)((ra >> (27 + k - 65)) & 1u);
             }
-            dst[idx] = v;
+            dst[i * FL_ATTR_F + k] = v;
         }
     }
     __syncthreads();

@@ -39,3 +39,5 @@ dl = d[..., 8] - d[..., 1]
 print("  %-40s mean %9.0f  p99 %9.0f" % ("deadlock lane (from occupancy done)", dl.mean(), np.percentile(dl, 99)))
 print("  entries per env: mean %.0f max %.0f; path segments per env: mean %.0f p99 %.0f max %.0f" %
       (d[..., 10].mean(), d[..., 10].max(), d[..., 11].mean(), np.percentile(d[..., 11], 99), d[..., 11].max()))
+print("  per agent: cells %.1f windows %.2f, full conflict checks %.1f in %.2f drains" %
+      (32 * d[..., 13].mean() / N, d[..., 13].mean() / N, d[..., 12].mean() / N, d[..., 14].mean() / N))
