@@ -108,6 +108,8 @@ ObsLayout make_obs_layout(const FlBatch *b, int nt, int *ctas_out = nullptr) {
     L.bm = take((long long)Rmax * 32);                          // time-slot filter of the prediction index: one / two entries per slot
     L.seg_cap = 10 * N;                                         // path segments of phase 3 share the room of the phase-4 queues
     if (L.seg_cap < (nt / 32) * 64) L.seg_cap = (nt / 32) * 64;
+    int seg_cap_use = L.seg_cap;                                // FL_OBS_SEGCAP / FL_OBS_ENTCAP (tests): smaller capacities in
+    if (const char *s = getenv("FL_OBS_SEGCAP")) { const int v = atoi(s); if (v >= 0 && v < seg_cap_use) seg_cap_use = v; }   // the same room,
     L.sq = take((long long)L.seg_cap * 8);                      // per-warp queues of the full conflict checks / segment pool
     L.kcls = b->H > b->W ? take((long long)Rmax * 2) : -1;      // key classes of the reference's c*W + r (walks.cuh)
     const long long ent_typ = (long long)N * 56 * 4;
@@ -146,6 +148,8 @@ ObsLayout make_obs_layout(const FlBatch *b, int nt, int *ctas_out = nullptr) {
     if (ent_b < 0) ent_b = 0;
     L.ent = take(ent_b);
     L.ent_cap = (int)(ent_b / 4);
+    L.seg_cap = seg_cap_use;                                    // to force the per-agent path walk and the global spill of the entries
+    if (const char *s = getenv("FL_OBS_ENTCAP")) { const int v = atoi(s); if (v >= 0 && v < L.ent_cap) L.ent_cap = v; }
     L.total = off;
     return L;
 }

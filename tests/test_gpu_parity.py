@@ -203,3 +203,35 @@ def test_rail_cycle_world_matches_oracle(n_agents):
     sched = np.zeros((w["T"], n_agents), np.uint8)
     sched[7, 0] = 5                                   # one malfunction for good measure
     run_against_oracle([w, w, w], acts, [sched, sched, sched], w["T"])
+
+
+@pytest.mark.parametrize("env", [
+    {"FL_OBS_SEGCAP": "3"},                            # segment pool overflows: every lane walks its agent's path (predict_path)
+    {"FL_OBS_ENTCAP": "16"},                           # the prediction entries spill to global memory
+    {"FL_OBS_SEGCAP": "0", "FL_OBS_ENTCAP": "0"},
+    {"FL_OBS_CTAS": "1"},                              # all static tables staged in shared memory (TMA bulk copies)
+    {"FL_OBS_TABLES": "0"},                            # all static tables read from global memory
+    {"FL_OBS_NT": "64"}, {"FL_OBS_NT": "128"}, {"FL_OBS_NT": "256"}, {"FL_OBS_NT": "512"}, {"FL_OBS_NT": "1024"},
+], ids=lambda d: ",".join("%s=%s" % kv for kv in d.items()))
+def test_every_kernel_plan_matches_oracle(golden, monkeypatch, env):
+    """k_observe picks its shared-memory plan, CTA size and fallbacks from the batch shape; each of them must give
+    the same bytes.  The overrides are read by fl_observe at every call."""
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    g = golden("t03_l1_greedy")
+    rng = np.random.RandomState(77)
+    other = np.where(rng.rand(*g["actions"].shape) < 0.7, 2, rng.randint(0, 5, size=g["actions"].shape)).astype(np.uint8)
+    run_against_oracle([g, g], [g["actions"], other], [g["sched"], g["sched"]], 45, check_every=3)
+
+
+def test_tall_grid_prediction_key_collisions():
+    """The reference keys predicted positions by c * W + r (treeobs.cpp:50-65, 379-465); on a grid with H > W two rail
+    cells can share a key and then see each other's predictions.  Environment 517 of the Test_03 pack (35 x 30) has
+    such a pair on agents' paths from the very first observation (walks.cuh: kcls)."""
+    import bench
+    w = bench.load_worlds("Test_03", 1, offset=517)[0]
+    assert int(w["H"]) > int(w["W"])
+    n = int(w["N"])
+    rng = np.random.RandomState(3)
+    acts = np.where(rng.rand(40, n) < 0.7, 2, rng.randint(0, 5, (40, n))).astype(np.uint8)
+    run_against_oracle([w], [acts], [w["sched"]], 40, check_every=4)
