@@ -148,6 +148,8 @@ ObsLayout make_obs_layout(const FlBatch *b, int nt, int *ctas_out = nullptr) {
     if (ent_b < 0) ent_b = 0;
     L.ent = take(ent_b);
     L.ent_cap = (int)(ent_b / 4);
+    L.sort_small = 40;                                          // buckets up to this size are sorted by one thread
+    if (const char *s = getenv("FL_OBS_SORTSMALL")) { const int v = atoi(s); if (v >= 1) L.sort_small = v; }
     L.seg_cap = seg_cap_use;                                    // to force the per-agent path walk and the global spill of the entries
     if (const char *s = getenv("FL_OBS_ENTCAP")) { const int v = atoi(s); if (v >= 0 && v < L.ent_cap) L.ent_cap = v; }
     L.total = off;
@@ -322,7 +324,7 @@ int fl_batch_slice(const FlBatch *b, int64_t e0, int64_t n, FlBatch *out) {
     FL_ADV(rc, N * 2) FL_ADV(old_rc, N * 2) FL_ADV(dir, N) FL_ADV(old_dir, N) FL_ADV(state, N) FL_ADV(ctr, N) FL_ADV(mal, N)
     FL_ADV(saved, N) FL_ADV(sig_mal, N) FL_ADV(deadlocked, N) FL_ADV(done, N) FL_ADV(nmal, N) FL_ADV(arrival, N)
     FL_ADV(elapsed, 1) FL_ADV(sched_pos, 1) FL_ADV(done_all, 1) FL_ADV(status, 1)
-    FL_ADV(stats, 4) FL_ADV(entries, b->ent_cap) FL_ADV(debug_clocks, 16)
+    FL_ADV(stats, 4) FL_ADV(entries, b->ent_cap) FL_ADV(segs, b->seg_stride) FL_ADV(debug_clocks, 16)
 #undef FL_ADV
     return FL_OK;
 }

@@ -36,7 +36,7 @@ namespace {
 constexpr int I_INF = 0x7fffffff;
 
 struct ObsLayout {   // byte offsets into dynamic shared memory (host: make_obs_layout); < 0 = lives in global memory
-    int bar, part, ag, dl, ci, ks, bm, sq, seg_cap, kcls, grid, ridx, ent, ent_cap, total;
+    int bar, part, ag, dl, ci, ks, bm, sq, seg_cap, sort_small, kcls, grid, ridx, ent, ent_cap, total;
     int srec, wrec, whoff, whits, wlist, sdist;   // static walk tables (walks.cuh)
 };
 
@@ -357,7 +357,6 @@ k_observe(FlBatch b, ObsLayout lay, float *__restrict__ out_attr, float *__restr
     const uint32_t *gtab = b.gtab + (size_t)e * b.n_slots * SS;
     const uint16_t *grid = lay.grid >= 0 ? reinterpret_cast<const uint16_t *>(smraw + lay.grid) : g_grid;
     const uint16_t *ridx = lay.ridx >= 0 ? reinterpret_cast<const uint16_t *>(smraw + lay.ridx) : g_ridx;
-    const uint32_t *srec = lay.srec >= 0 ? reinterpret_cast<const uint32_t *>(smraw + lay.srec) : g_srec;
     const uint4 *wrec = lay.wrec >= 0 ? reinterpret_cast<const uint4 *>(smraw + lay.wrec) : g_wrec;
     const uint32_t *whoff = lay.whoff >= 0 ? reinterpret_cast<const uint32_t *>(smraw + lay.whoff) : g_whoff;
     const uint32_t *whits = lay.whits >= 0 ? reinterpret_cast<const uint32_t *>(smraw + lay.whits) : g_whits;
@@ -542,6 +541,8 @@ k_observe(FlBatch b, ObsLayout lay, float *__restrict__ out_attr, float *__restr
         // a segment record per walk into a pool; the occupancy intervals of a segment are then emitted by any thread.
         uint2 *pool = reinterpret_cast<uint2 *>(smraw + lay.sq);      // state | last step << 16 | direction before << 30,
                                                                       // agent | first path index << 10 | direction after << 19 | last << 21
+        uint2 *pool_g = reinterpret_cast<uint2 *>(b.segs) + (size_t)e * b.seg_stride;   // segments beyond the shared-memory pool
+        const int seg_gcap = b.segs ? (int)b.seg_stride : 0;
         for (int i = tid; i < N; i += NW) {
             const uint32_t info = A.info[i];
             const unsigned slot = (info >> 8) & 0xFFFFu;
@@ -556,9 +557,10 @@ k_observe(FlBatch b, ObsLayout lay, float *__restrict__ out_attr, float *__restr
                 const uint32_t g = stuck ? 0xFFFFu : gt[sid];
                 const unsigned nxt = g & 0xFFFFu, kend = (g >> 16) & 0x3FFFu;
                 const int pos = atomicAdd(&s_misc[0], 1);
-                if (pos < lay.seg_cap)
-                    pool[pos] = make_uint2(sid | (kend << 16) | (dp << 30),
-                                           (unsigned)i | ((unsigned)kk << 10) | ((nxt & 3u) << 19) | ((nxt == 0xFFFFu ? 1u : 0u) << 21));
+                const uint2 rec = make_uint2(sid | (kend << 16) | (dp << 30),
+                                             (unsigned)i | ((unsigned)kk << 10) | ((nxt & 3u) << 19) | ((nxt == 0xFFFFu ? 1u : 0u) << 21));
+                if (pos < lay.seg_cap) pool[pos] = rec;
+                else if (pos - lay.seg_cap < seg_gcap) pool_g[pos - lay.seg_cap] = rec;
                 kk += (int)kend + 1;
                 if (nxt == 0xFFFFu || kk > FL_PRED_DEPTH || 1 + (kk - 1) * tpc >= NPRED) break;
                 dp = g >> 30; sid = nxt;
@@ -567,10 +569,10 @@ k_observe(FlBatch b, ObsLayout lay, float *__restrict__ out_attr, float *__restr
         named_bar_sync(1, NW);
         const int n_seg = s_misc[0];
         if (dbg && tid == 0) dbg[11] = n_seg;
-        const bool pooled = n_seg <= lay.seg_cap;  // else: every lane walks its agent's path itself (predict_path), twice
+        const bool pooled = n_seg <= lay.seg_cap + seg_gcap;  // else: every lane walks its agent's path itself (predict_path), twice
         // Emit(rail cell, t0, t1, entry) for every occupied element of pool segment j
         auto emit_segment = [&](int j, auto emit) {
-            const uint2 sg = pool[j];
+            const uint2 sg = j < lay.seg_cap ? pool[j] : pool_g[j - lay.seg_cap];
             const unsigned sid = sg.x & 0xFFFFu;
             const int kend = (int)((sg.x >> 16) & 0x3FFFu), agent = (int)(sg.y & 1023u), kk = (int)((sg.y >> 10) & 511u);
             const bool seg_last = (sg.y >> 21) & 1u;
@@ -652,16 +654,77 @@ k_observe(FlBatch b, ObsLayout lay, float *__restrict__ out_attr, float *__restr
                 if (s0 != 0xFFFFu) predict_path(wrec, whoff, whits, wlist, sdist + (size_t)slot * SS, s0, slot, (int)(info >> 24), i, scatter_emit);
             }
         named_bar_sync(1, NW);
-        // order every bucket: long-lived entries first, then by t0, so that the tree walk scans a time window only
-        for (int key = tid; key < R; key += NW) {
-            const int s0 = (int)ks[key - 1], s1 = (int)ks[key];
+        // order every bucket: long-lived entries first, then by t0, so that the tree walk scans a time window only.
+        // Small buckets: insertion sort by one thread.  Large buckets (busy cells of large environments) are queued and
+        // sorted by a warp each: bitonic network on a copy padded to a power of two in the free tail of the spill space.
+        constexpr int SORT_BIG = 2048;
+        const int SORT_SMALL = lay.sort_small;
+        uint32_t *bigq = reinterpret_cast<uint32_t *>(smraw + lay.sq);          // the segment pool is no longer needed
+        const int bigq_cap = lay.seg_cap * 2;
+        uint32_t *scratch = b.entries + (size_t)e * b.ent_cap + (ent == ent_s ? 0 : n_ent);
+        const long long scratch_n = b.ent_cap - (ent == ent_s ? 0 : n_ent);
+        auto insertion_sort = [&](int s0, int s1) {
             for (int x = s0 + 1; x < s1; x++) {
                 const uint32_t v = ent[x], kv = entry_sort_key(v);
                 int y = x - 1;
                 while (y >= s0 && entry_sort_key(ent[y]) > kv) { ent[y + 1] = ent[y]; y--; }
                 ent[y + 1] = v;
             }
+        };
+        for (int key = tid; key < R; key += NW) {
+            const int s0 = (int)ks[key - 1], s1 = (int)ks[key];
+            if (s1 - s0 <= SORT_SMALL) { insertion_sort(s0, s1); continue; }
+            const int pos = s1 - s0 <= SORT_BIG ? atomicAdd(&s_misc[1], 1) : bigq_cap;
+            if (pos < bigq_cap) bigq[pos] = (uint32_t)key; else insertion_sort(s0, s1);
         }
+        named_bar_sync(1, NW);
+        {
+            const int n_big = min(ld_vol_i32(&s_misc[1]), bigq_cap);
+            uint32_t *my = scratch + (size_t)warp * (2 * SORT_BIG), *stage = my + SORT_BIG;     // P <= SORT_BIG pairs, n <= SORT_BIG staged entries
+            const bool have_scratch = (long long)(warp + 1) * (2 * SORT_BIG) <= scratch_n;
+            for (int q = warp; q < n_big; q += NW / 32) {
+                const int key = (int)bigq[q], s0 = (int)ks[key - 1], n = (int)ks[key] - s0;
+                if (!have_scratch) { if (lane == 0) insertion_sort(s0, s0 + n); continue; }
+                int P = 64;
+                while (P < n) P <<= 1;
+                for (int x = lane; x < P; x += 32) my[x] = x < n ? ((entry_sort_key(ent[s0 + x]) << 22) | (uint32_t)x) : 0xFFFFFFFFu;   // key | index
+                __syncwarp();
+                for (int kk2 = 2; kk2 <= P; kk2 <<= 1)
+                    for (int jj = kk2 >> 1; jj > 0; jj >>= 1) {
+                        for (int x = lane; x < P; x += 32) {
+                            const int l = x ^ jj;
+                            if (l > x) {
+                                const uint32_t a = my[x], c = my[l];
+                                const bool up = (x & kk2) == 0;
+                                if ((a > c) == up) { my[x] = c; my[l] = a; }
+                            }
+                        }
+                        __syncwarp();
+                    }
+                // permute the bucket: the sorted (key, index) pairs say which entry goes where; entries travel through registers
+                for (int x0 = 0; x0 < n; x0 += 32 * 8) {
+                    uint32_t v[8];
+#pragma unroll
+                    for (int u = 0; u < 8; u++) { const int x = x0 + u * 32 + lane; v[u] = x < n ? ent[s0 + (my[x] & 0x3FFFFFu)] : 0u; }
+                    // all reads of this batch happen before any write only if the batch covers the bucket; otherwise stage through scratch
+                    if (n <= 32 * 8) {
+                        __syncwarp();
+#pragma unroll
+                        for (int u = 0; u < 8; u++) { const int x = x0 + u * 32 + lane; if (x < n) ent[s0 + x] = v[u]; }
+                    } else {
+#pragma unroll
+                        for (int u = 0; u < 8; u++) { const int x = x0 + u * 32 + lane; if (x < n) stage[x] = v[u]; }
+                    }
+                }
+                if (n > 32 * 8) {
+                    __syncwarp();
+                    for (int x = lane; x < n; x += 32) ent[s0 + x] = stage[x];
+                }
+                __syncwarp();
+            }
+        }
+        named_bar_sync(1, NW);
+        if (tid == 0) s_misc[1] = 0;                // phase 4 takes its agents from this counter
         named_bar_sync(1, NW);
         asm volatile("bar.arrive 2, %0;" ::"r"(NT) : "memory");  // lets the deadlock warp join phase 4 when it is done
     }

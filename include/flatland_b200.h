@@ -69,6 +69,7 @@ typedef struct FlBatch {
     int64_t state_stride;  /* elements per env of srec / wrec / whoff / kcls, >= 4 * rail cells, multiple of 32 */
     int64_t wlist_stride;  /* uint32 elements per env of wlist, multiple of 4, with 8 elements of slack at the end */
     int64_t whits_stride;  /* uint32 elements per env of whits, multiple of 4 */
+    int64_t seg_stride;    /* uint64 elements per env of segs (0 = none) */
 
     /* ---- world, static after upload (RailEnv.reset generators stay reference Python) ---- */
     const uint16_t *grid;      /* [E][grid_stride] transition bitmask per cell (core/transition_map.py:144) */
@@ -129,7 +130,9 @@ typedef struct FlBatch {
 
     /* ---- per-step observation workspace (rebuilt by every fl_observe) ---- */
     uint32_t *entries;    /* [E][ent_cap] predicted-occupancy entries grouped by rail cell (spill space: used only
-                                       when an environment's entries do not fit in shared memory) */
+                                       when an environment's entries do not fit in shared memory; its free tail is
+                                       the scratch of the sort of large buckets) */
+    uint64_t *segs;       /* [E][seg_stride] path segments that do not fit in the shared-memory pool (spill space) */
 } FlBatch;
 
 int fl_abi_version(void);

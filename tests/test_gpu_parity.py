@@ -206,9 +206,11 @@ def test_rail_cycle_world_matches_oracle(n_agents):
 
 
 @pytest.mark.parametrize("env", [
-    {"FL_OBS_SEGCAP": "3"},                            # segment pool overflows: every lane walks its agent's path (predict_path)
+    {"FL_OBS_SEGCAP": "3"},                            # segment pool overflows into its global spill space
     {"FL_OBS_ENTCAP": "16"},                           # the prediction entries spill to global memory
     {"FL_OBS_SEGCAP": "0", "FL_OBS_ENTCAP": "0"},
+    {"FL_OBS_SORTSMALL": "1"},                         # every bucket with two or more entries takes the warp sort (bitonic network)
+    {"FL_OBS_SORTSMALL": "1", "FL_OBS_ENTCAP": "0"},   # ... with the entries and the sort scratch sharing the spill space
     {"FL_OBS_CTAS": "1"},                              # all static tables staged in shared memory (TMA bulk copies)
     {"FL_OBS_TABLES": "0"},                            # all static tables read from global memory
     {"FL_OBS_NT": "64"}, {"FL_OBS_NT": "128"}, {"FL_OBS_NT": "256"}, {"FL_OBS_NT": "512"}, {"FL_OBS_NT": "1024"},
