@@ -1,8 +1,6 @@
-mkdir -p gpurun_out
-timeout 1500 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?" >> gpurun_out/pytest_gpu.log
-tail -8 gpurun_out/pytest_gpu.log
-for c in 1 2 4 8 16; do
-  python bench.py --steps 30 --warmup 5 --no-cpu --e2e-steps 40 --e2e-chunks $c --profile-steps 5 2>/dev/null | python -c "
+for v in "" "FL_OBS_CTAS=12" "FL_OBS_CTAS=10" "FL_OBS_NT=128" "FL_OBS_NT=128 FL_OBS_CTAS=8"; do
+  env $v python bench.py --config Test_02 --steps 40 --warmup 5 --no-cpu --e2e-steps 3 --profile-steps 10 2>/dev/null | python -c "
 import json,sys
-d=json.loads(sys.stdin.read()); print('chunks',d['e2e']['chunks'],'e2e %.2fM'%(d['e2e']['value']/1e6),'value %.1fM'%(d['value']/1e6))"
+d=json.loads(sys.stdin.read()); print('$v','value %.1fM'%(d['value']/1e6), {k:round(v['ms_per_launch'],4) for k,v in d['kernels'].items()})"
 done
+python tools/phase_times.py Test_02 2048 100 2>&1 | tail -11
