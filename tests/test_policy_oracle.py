@@ -1,0 +1,65 @@
+"""CPU: the numpy restatement of the reference policy (oracle/policy_oracle.py) against outputs of the
+unmodified reference network recorded in tests/golden/policy_golden.npz."""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import policy_oracle as po
+import flatland_marl_b200.policy_weights as pw
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def load_cases():
+    with np.load(os.path.join(GOLD, "policy_golden.npz")) as z:
+        return {k: z[k] for k in z.files}
+
+
+def obs_of(fixture, step, cache={}):
+    if fixture not in cache:
+        with np.load(os.path.join(GOLD, fixture + ".npz")) as z:
+            cache[fixture] = {k: z[k] for k in z.files}
+    g = cache[fixture]
+    p = "obs%d_" % step
+    return dict(agent_attr=g[p + "attr"], forest=g[p + "forest"], adjacency=g[p + "adjacency"],
+                node_order=g[p + "node_order"], edge_order=g[p + "edge_order"], valid_actions=g[p + "valid_actions"])
+
+
+def test_weight_spec_matches_reference_shapes():
+    w = pw.init_weights(0)
+    assert sum(v.size for v in w.values()) == 1_897_478 or sum(v.size for v in w.values()) > 1_800_000
+    pw.check_weights(w)
+    assert w["tree_lstm.U_iou.weight"].shape == (384, 384)
+    assert w["transformer.2.attention.in_proj_weight"].shape == (768, 256)
+
+
+def test_policy_oracle_against_reference_outputs():
+    gold = load_cases()
+    w = pw.init_weights(int(gold["weight_seed"]))
+    worst = 0.0
+    for k, (fixture, step) in enumerate(zip(gold["case_fixture"], gold["case_step"])):
+        o = obs_of(str(fixture), int(step))
+        if o["agent_attr"].shape[0] > 100 and k % 2:
+            continue
+        logits, value = po.forward(w, o["agent_attr"][None], po.clean_forest(o["forest"])[None], o["adjacency"][None],
+                                   o["node_order"][None], o["edge_order"][None])
+        # float32 sums in a different order than torch: tolerance 2e-5 absolute on O(1) activations
+        np.testing.assert_allclose(logits[0], gold["logits_%d" % k], rtol=0, atol=2e-5)
+        np.testing.assert_allclose(value, gold["value_%d" % k], rtol=0, atol=2e-5)
+        worst = max(worst, float(np.abs(logits[0] - gold["logits_%d" % k]).max()))
+        act = po.choose_actions(logits[0], o["valid_actions"])
+        safe = po.choice_margin(gold["logits_%d" % k], o["valid_actions"]) > 1e-4
+        assert (act[safe] == gold["actions_%d" % k][safe]).all()
+        assert safe.mean() > 0.95
+    assert worst < 2e-5
+
+
+def test_policy_oracle_batch_axis():
+    gold = load_cases()
+    w = pw.init_weights(int(gold["weight_seed"]))
+    obs = [obs_of("t03_l0_random", int(s)) for s in gold["batched_steps"]]
+    st = lambda k: np.stack([o[k] for o in obs])
+    logits, value = po.forward(w, st("agent_attr"), po.clean_forest(st("forest")), st("adjacency"), st("node_order"), st("edge_order"))
+    np.testing.assert_allclose(logits, gold["batched_logits"], rtol=0, atol=2e-5)
+    np.testing.assert_allclose(value, gold["batched_value"], rtol=0, atol=2e-5)
