@@ -9,6 +9,10 @@ ROOT = os.path.dirname(HERE)
 SRC = os.path.join(HERE, "csrc", "flatland_b200.cu")
 HDR = os.path.join(ROOT, "include", "flatland_b200.h")
 LIB = os.path.join(HERE, "csrc", "libflatland_b200.so")
+POLICY_DIR = os.path.join(HERE, "csrc", "policy")
+POLICY_SRC = os.path.join(POLICY_DIR, "policy.cu")
+POLICY_HDR = os.path.join(ROOT, "include", "flatland_policy_b200.h")
+POLICY_LIB = os.path.join(POLICY_DIR, "libflatland_policy_b200.so")
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "--expt-extended-lambda", "-Xcompiler", "-fPIC", "-shared"]
@@ -22,13 +26,23 @@ def needs_build():
     return any(os.path.getmtime(p) > t for p in srcs + [HDR])
 
 
+def policy_needs_build():
+    if not os.path.exists(POLICY_LIB):
+        return True
+    t = os.path.getmtime(POLICY_LIB)
+    srcs = [os.path.join(POLICY_DIR, f) for f in os.listdir(POLICY_DIR) if f.endswith((".cu", ".cuh"))]
+    return any(os.path.getmtime(p) > t for p in srcs + [POLICY_HDR])
+
+
 def build(force=False, verbose=False):
-    if not (force or needs_build()):
-        return LIB
+    """Both libraries: the step/observation path (libflatland_b200.so) and the policy forward pass
+    (policy/libflatland_policy_b200.so, tcgen05 kernels)."""
     nvcc = os.environ.get("NVCC", "nvcc")
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + \
-          ["-I", os.path.join(ROOT, "include"), "-o", LIB, SRC]
-    subprocess.check_call(cmd)
+    extra = ["-Xptxas", "-v"] if verbose else []
+    if force or needs_build():
+        subprocess.check_call([nvcc] + NVCC_FLAGS + extra + ["-I", os.path.join(ROOT, "include"), "-o", LIB, SRC])
+    if force or policy_needs_build():
+        subprocess.check_call([nvcc] + NVCC_FLAGS + extra + ["-I", os.path.join(ROOT, "include"), "-o", POLICY_LIB, POLICY_SRC])
     return LIB
 
 

@@ -1,0 +1,815 @@
+// policy.cu — batched forward pass of the reference policy network on B200 (sm_100a), C ABI of
+// include/flatland_policy_b200.h.  Reference semantics: solution/nn/net_tree.py:73-116 (Network),
+// solution/nn/TreeLSTM.py:34-154 (TreeLSTM), solution/plfActor.py:27-44 (action choice).
+//
+// Every matrix product runs on the 5th-generation tensor cores: tcgen05.mma issued by one thread, bf16 operands
+// staged in shared memory in the 128-byte-swizzled K-major layout, fp32 accumulators in TMEM, read back with
+// tcgen05.ld by four epilogue warps.  Operand rows are gathered with 16-byte cp.async copies (the Tree-LSTM's rows
+// are tree nodes scattered over the batch, which a tiled TMA box cannot address), made visible to the tensor core
+// with fence.proxy.async before the stage's mbarrier is signalled.
+//
+//   k_lin<MODE>   persistent; the CTA's 128 output columns of W stay resident in shared memory, 128-row tiles of A
+//                 stream through a 4-stage ring, two TMEM accumulators so the epilogue of tile i overlaps the MMAs
+//                 of tile i+1.  MODE_LINEAR: dense layers (bias, optional GELU).  MODE_TREE_F: forget gates of one
+//                 tree level, rows = child nodes, epilogue sigmoid(.) * c_child.
+//   k_tree_p      one tree level: i/o/u pre-activations (N = 384) and the W_c reduction (N = 128) of 128 parent
+//                 nodes accumulate side by side in all 512 TMEM columns; the epilogue applies the LSTM gates.
+//   k_attention   4-head attention over the agents of one environment (SIMT, fp32, online softmax).
+//   k_prep / k_tree_plan / k_head_final / k_choose: casts, level lists, final 128->5/1 layers, action choice.
+#include <cuda_runtime.h>
+#include <math_constants.h>
+
+#include "../../../include/flatland_policy_b200.h"
+#include "umma.cuh"
+
+using namespace umma;
+typedef __nv_bfloat16 bf16;
+
+namespace {
+
+constexpr int TILE = 128 * 128;   // bytes of a 128-row x 64-element bf16 tile (one k-block)
+constexpr int LIN_STAGES = 4;
+constexpr int LAG = 2;            // cp.async groups left in flight before a stage is published
+constexpr int P_STAGES = 3;
+constexpr int P_STAGE_BYTES = 4 * TILE;   // A tile + up to 384 rows of B
+constexpr int NODES = 32;         // node slots per tree in the h / c / fc / x scratch (31 used)
+
+unsigned long long g_launches = 0;
+
+enum { MODE_LINEAR = 0, MODE_TREE_F = 1 };
+
+struct LinArgs {
+    const bf16 *a0, *a1, *a2;   // A = [a0 (kb0 k-blocks) | a1 (kb1 k-blocks) | a2 (16 columns, if k16)]
+    int lda0, lda1, lda2;
+    int kb0, kb1, k16;
+    const bf16 *w;              // [n][ldw], the same column order as A
+    int ldw;
+    const float *bias;
+    int rows;
+    const int *rows_dev;        // when set: rows = *rows_dev * rows_mul (tree levels are counted on the device)
+    int rows_mul;
+    int act;
+    bf16 *out;                  // MODE_LINEAR: [rows][ldc]
+    int ldc;
+    const uint32_t *entries;    // MODE_TREE_F: level list (tree | node << 22 | first child << 27)
+    const bf16 *cstate;         //              c of every node [tree][32][128]
+    bf16 *fc;                   //              f * c_child     [tree][32][128]
+};
+
+// entry of a level list
+__device__ __forceinline__ void entry_decode(uint32_t e, uint32_t &tree, uint32_t &node, uint32_t &child0) {
+    tree = e & 0x3FFFFFu;
+    node = (e >> 22) & 31u;
+    child0 = e >> 27;
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(288, 1) k_lin(const LinArgs p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    const int nkb = p.kb0 + p.kb1 + p.k16;
+    const int rows = p.rows_dev ? (*p.rows_dev) * p.rows_mul : p.rows;
+    const int mtiles = (rows + 127) >> 7;
+    if ((int)blockIdx.x >= mtiles) return;
+    uint8_t *sW = smem;
+    uint8_t *sA = smem + (size_t)nkb * TILE;
+    uint64_t *bars = (uint64_t *)(sA + LIN_STAGES * TILE);
+    uint64_t *full = bars, *empty = bars + LIN_STAGES, *wfull = bars + 2 * LIN_STAGES;
+    uint64_t *tfull = wfull + 1, *tempty = tfull + 2;
+    uint32_t *tmem_slot = (uint32_t *)(tempty + 2);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n0 = blockIdx.y * 128;
+
+    if (warp == 8) {
+        if (lane == 0) {
+            for (int s = 0; s < LIN_STAGES; s++) { mbar_init(&full[s], 128); mbar_init(&empty[s], 1); }
+            mbar_init(wfull, 128);
+            for (int b = 0; b < 2; b++) { mbar_init(&tfull[b], 1); mbar_init(&tempty[b], 128); }
+            mbar_init_fence();
+        }
+        __syncwarp();
+        tmem_alloc(tmem_slot, 256);
+    }
+    fence_before_sync();
+    __syncthreads();
+    fence_after_sync();
+    const uint32_t tmem = *tmem_slot;
+
+    if (warp >= 4 && warp < 8) {
+        // ---------------- producers: 128 threads, thread = (16-byte chunk c, rows r0 + 16 i) ----------------
+        const int tp = threadIdx.x - 128;
+        const int c = tp & 7, r0 = tp >> 3;
+        const uint32_t swz = (uint32_t)((c ^ (r0 & 7)) << 4) + (uint32_t)r0 * 128u;
+        for (int kb = 0; kb < nkb; kb++) {
+            const bool narrow = p.k16 && kb == nkb - 1;
+            const bf16 *src = p.w + (size_t)kb * 64 + c * 8;
+            const uint32_t dst = smem_u32(sW + (size_t)kb * TILE) + swz;
+            if (!narrow || c < 2) {
+#pragma unroll
+                for (int i = 0; i < 8; i++) cp_async16(dst + i * 2048, src + (size_t)(n0 + r0 + 16 * i) * p.ldw, 16);
+            }
+        }
+        cp_async_commit();
+        cp_async_wait<0>();
+        fence_proxy_async();
+        mbar_arrive(wfull);
+
+        uint32_t it = 0;
+        for (int mt = blockIdx.x; mt < mtiles; mt += gridDim.x) {
+            uint32_t off0[8], off1[8], off2[8], ok[8];
+#pragma unroll
+            for (int i = 0; i < 8; i++) {
+                const int r = mt * 128 + r0 + 16 * i;
+                ok[i] = r < rows ? 16u : 0u;
+                off0[i] = off1[i] = off2[i] = 0;
+                if (ok[i]) {
+                    if (MODE == MODE_LINEAR) {
+                        off0[i] = (uint32_t)r * (uint32_t)p.lda0;
+                        off1[i] = (uint32_t)r * (uint32_t)p.lda1;
+                        off2[i] = (uint32_t)r * (uint32_t)p.lda2;
+                    } else {
+                        uint32_t t, v, ch0;
+                        entry_decode(__ldg(p.entries + r / 3), t, v, ch0);
+                        off0[i] = ((t * NODES) + ch0 + (uint32_t)(r % 3)) * 128u;
+                        off2[i] = (t * NODES + v) * 16u;
+                    }
+                }
+            }
+            for (int kb = 0; kb < nkb; kb++, it++) {
+                const int s = it % LIN_STAGES;
+                mbar_wait(&empty[s], ((it / LIN_STAGES) & 1) ^ 1);
+                const uint32_t dst = smem_u32(sA + (size_t)s * TILE) + swz;
+                if (kb < p.kb0) {
+                    const bf16 *src = p.a0 + kb * 64 + c * 8;
+#pragma unroll
+                    for (int i = 0; i < 8; i++) cp_async16(dst + i * 2048, src + off0[i], ok[i]);
+                } else if (kb < p.kb0 + p.kb1) {
+                    const bf16 *src = p.a1 + (kb - p.kb0) * 64 + c * 8;
+#pragma unroll
+                    for (int i = 0; i < 8; i++) cp_async16(dst + i * 2048, src + off1[i], ok[i]);
+                } else if (c < 2) {
+                    const bf16 *src = p.a2 + c * 8;
+#pragma unroll
+                    for (int i = 0; i < 8; i++) cp_async16(dst + i * 2048, src + off2[i], ok[i]);
+                }
+                cp_async_commit();
+                if (it >= LAG) {
+                    cp_async_wait<LAG>();
+                    fence_proxy_async();
+                    mbar_arrive(&full[(it - LAG) % LIN_STAGES]);
+                }
+            }
+        }
+        cp_async_wait<0>();
+        fence_proxy_async();
+        for (uint32_t j = it >= LAG ? it - LAG : 0; j < it; j++) mbar_arrive(&full[j % LIN_STAGES]);
+    } else if (warp == 8) {
+        // ---------------- MMA issue: one thread ----------------
+        if (lane == 0) {
+            mbar_wait(wfull, 0);
+            fence_after_sync();
+            const uint32_t idesc = idesc_bf16(128, 128);
+            uint32_t it = 0, tl = 0;
+            for (int mt = blockIdx.x; mt < mtiles; mt += gridDim.x, tl++) {
+                const uint32_t b = tl & 1;
+                mbar_wait(&tempty[b], ((tl >> 1) & 1) ^ 1);
+                fence_after_sync();
+                for (int kb = 0; kb < nkb; kb++, it++) {
+                    const int s = it % LIN_STAGES;
+                    mbar_wait(&full[s], (it / LIN_STAGES) & 1);
+                    fence_after_sync();
+                    const uint64_t ad = desc_sw128(smem_u32(sA + (size_t)s * TILE));
+                    const uint64_t bd = desc_sw128(smem_u32(sW + (size_t)kb * TILE));
+                    const int nk = (p.k16 && kb == nkb - 1) ? 1 : 4;
+                    for (int k = 0; k < nk; k++) mma_bf16(tmem + b * 128, ad + 2 * k, bd + 2 * k, idesc, (uint32_t)((kb | k) != 0));
+                    mma_commit(&empty[s]);
+                }
+                mma_commit(&tfull[b]);
+            }
+        }
+        __syncwarp();
+    } else {
+        // ---------------- epilogue: warp w owns TMEM lanes 32w..32w+31 = rows of the tile ----------------
+        uint32_t tl = 0;
+        for (int mt = blockIdx.x; mt < mtiles; mt += gridDim.x, tl++) {
+            const uint32_t b = tl & 1;
+            const int r = mt * 128 + warp * 32 + lane;
+            const bool valid = r < rows;
+            size_t orow = 0;
+            if (valid) {
+                if (MODE == MODE_LINEAR) {
+                    orow = (size_t)r * p.ldc + n0;
+                } else {
+                    uint32_t t, v, ch0;
+                    entry_decode(__ldg(p.entries + r / 3), t, v, ch0);
+                    orow = ((size_t)t * NODES + ch0 + (r % 3)) * 128;
+                }
+            }
+            mbar_wait(&tfull[b], (tl >> 1) & 1);
+            fence_after_sync();
+            const uint32_t tbase = tmem + ((uint32_t)(warp * 32) << 16) + b * 128;
+#pragma unroll 1
+            for (int ch = 0; ch < 8; ch++) {
+                uint32_t v[16];
+                tmem_ld16(tbase + ch * 16, v);
+                tmem_ld_wait();
+                float f[16];
+#pragma unroll
+                for (int j = 0; j < 16; j++) f[j] = __uint_as_float(v[j]) + __ldg(p.bias + n0 + ch * 16 + j);
+                if (MODE == MODE_LINEAR) {
+                    if (p.act) {
+#pragma unroll
+                        for (int j = 0; j < 16; j++) f[j] = gelu_erf(f[j]);
+                    }
+                    if (valid) {
+                        uint4 *o = reinterpret_cast<uint4 *>(p.out + orow + ch * 16);
+                        o[0] = make_uint4(pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]), pack_bf16(f[4], f[5]), pack_bf16(f[6], f[7]));
+                        o[1] = make_uint4(pack_bf16(f[8], f[9]), pack_bf16(f[10], f[11]), pack_bf16(f[12], f[13]), pack_bf16(f[14], f[15]));
+                    }
+                } else if (valid) {
+                    const uint4 *cin = reinterpret_cast<const uint4 *>(p.cstate + orow + ch * 16);
+                    uint4 c0 = cin[0], c1 = cin[1];
+                    const uint32_t cw[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
+                    uint32_t ow[8];
+#pragma unroll
+                    for (int j = 0; j < 8; j++) {
+                        const float2 cc = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162 *>(&cw[j]));
+                        ow[j] = pack_bf16(sigmoidf(f[2 * j]) * cc.x, sigmoidf(f[2 * j + 1]) * cc.y);
+                    }
+                    uint4 *o = reinterpret_cast<uint4 *>(p.fc + orow + ch * 16);
+                    o[0] = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+                    o[1] = make_uint4(ow[4], ow[5], ow[6], ow[7]);
+                }
+            }
+            fence_before_sync();
+            mbar_arrive(&tempty[b]);
+        }
+    }
+    fence_before_sync();
+    __syncthreads();
+    if (warp == 8) tmem_dealloc(tmem, 256);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+struct TreeArgs {
+    const uint32_t *entries;   // level list
+    const int *count_dev;      // nodes on this level
+    int level;
+    const bf16 *x;             // [tree][32][16]
+    bf16 *h, *c;               // [tree][32][128]
+    const bf16 *fc;            // [tree][32][128]
+    bf16 *emb;                 // root h goes to emb[tree][emb_ld] (+ column offset folded in)
+    int emb_ld;
+    const bf16 *uiou, *wiou, *wc;
+    const float *b_iou, *b_c;
+};
+
+__global__ void __launch_bounds__(288, 1) k_tree_p(const TreeArgs p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    const int rows = *p.count_dev;
+    const int mtiles = (rows + 127) >> 7;
+    if ((int)blockIdx.x >= mtiles) return;
+    uint64_t *bars = (uint64_t *)(smem + P_STAGES * P_STAGE_BYTES);
+    uint64_t *full = bars, *empty = bars + P_STAGES, *tfull = bars + 2 * P_STAGES, *tempty = tfull + 1;
+    uint32_t *tmem_slot = (uint32_t *)(tempty + 1);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int kfirst = p.level == 0 ? 6 : 0, klast = p.level == 0 ? 6 : 12;   // k-iterations: 0-5 h, 6 x, 7-12 fc
+
+    if (warp == 8) {
+        if (lane == 0) {
+            for (int s = 0; s < P_STAGES; s++) { mbar_init(&full[s], 128); mbar_init(&empty[s], 1); }
+            mbar_init(tfull, 1);
+            mbar_init(tempty, 128);
+            mbar_init_fence();
+        }
+        __syncwarp();
+        tmem_alloc(tmem_slot, 512);
+    }
+    fence_before_sync();
+    __syncthreads();
+    fence_after_sync();
+    const uint32_t tmem = *tmem_slot;
+
+    if (warp >= 4 && warp < 8) {
+        const int tp = threadIdx.x - 128;
+        const int c = tp & 7, r0 = tp >> 3;
+        const uint32_t swz = (uint32_t)((c ^ (r0 & 7)) << 4) + (uint32_t)r0 * 128u;
+        uint32_t it = 0;
+        for (int mt = blockIdx.x; mt < mtiles; mt += gridDim.x) {
+            uint32_t offc[8], offx[8], ok[8];
+#pragma unroll
+            for (int i = 0; i < 8; i++) {
+                const int r = mt * 128 + r0 + 16 * i;
+                ok[i] = r < rows ? 16u : 0u;
+                offc[i] = offx[i] = 0;
+                if (ok[i]) {
+                    uint32_t t, v, ch0;
+                    entry_decode(__ldg(p.entries + r), t, v, ch0);
+                    offc[i] = (t * NODES + ch0) * 128u;
+                    offx[i] = (t * NODES + v) * 16u;
+                }
+            }
+            for (int kk = kfirst; kk <= klast; kk++, it++) {
+                const int s = it % P_STAGES;
+                mbar_wait(&empty[s], ((it / P_STAGES) & 1) ^ 1);
+                const uint32_t dstA = smem_u32(smem + (size_t)s * P_STAGE_BYTES) + swz;
+                const uint32_t dstB = dstA + TILE;
+                if (kk < 6) {
+                    const bf16 *src = p.h + kk * 64 + c * 8;
+#pragma unroll
+                    for (int i = 0; i < 8; i++) cp_async16(dstA + i * 2048, src + offc[i], ok[i]);
+                    const bf16 *wsrc = p.uiou + kk * 64 + c * 8;
+#pragma unroll 8
+                    for (int i = 0; i < 24; i++) cp_async16(dstB + i * 2048, wsrc + (size_t)(r0 + 16 * i) * 384, 16);
+                } else if (kk == 6) {
+                    if (c < 2) {
+                        const bf16 *src = p.x + c * 8;
+#pragma unroll
+                        for (int i = 0; i < 8; i++) cp_async16(dstA + i * 2048, src + offx[i], ok[i]);
+                        const bf16 *wsrc = p.wiou + c * 8;
+#pragma unroll 8
+                        for (int i = 0; i < 24; i++) cp_async16(dstB + i * 2048, wsrc + (size_t)(r0 + 16 * i) * 16, 16);
+                    }
+                } else {
+                    const bf16 *src = p.fc + (kk - 7) * 64 + c * 8;
+#pragma unroll
+                    for (int i = 0; i < 8; i++) cp_async16(dstA + i * 2048, src + offc[i], ok[i]);
+                    const bf16 *wsrc = p.wc + (kk - 7) * 64 + c * 8;
+#pragma unroll
+                    for (int i = 0; i < 8; i++) cp_async16(dstB + i * 2048, wsrc + (size_t)(r0 + 16 * i) * 384, 16);
+                }
+                cp_async_commit();
+                if (it >= LAG) {
+                    cp_async_wait<LAG>();
+                    fence_proxy_async();
+                    mbar_arrive(&full[(it - LAG) % P_STAGES]);
+                }
+            }
+        }
+        cp_async_wait<0>();
+        fence_proxy_async();
+        for (uint32_t j = it >= LAG ? it - LAG : 0; j < it; j++) mbar_arrive(&full[j % P_STAGES]);
+    } else if (warp == 8) {
+        if (lane == 0) {
+            const uint32_t id256 = idesc_bf16(128, 256), id128 = idesc_bf16(128, 128);
+            uint32_t it = 0, tl = 0;
+            for (int mt = blockIdx.x; mt < mtiles; mt += gridDim.x, tl++) {
+                mbar_wait(tempty, (tl & 1) ^ 1);
+                fence_after_sync();
+                for (int kk = kfirst; kk <= klast; kk++, it++) {
+                    const int s = it % P_STAGES;
+                    mbar_wait(&full[s], (it / P_STAGES) & 1);
+                    fence_after_sync();
+                    const uint32_t a = smem_u32(smem + (size_t)s * P_STAGE_BYTES);
+                    const uint64_t ad = desc_sw128(a), bd = desc_sw128(a + TILE), bd2 = desc_sw128(a + TILE + 256 * 128);
+                    if (kk <= 6) {
+                        const int nk = kk == 6 ? 1 : 4;
+                        for (int k = 0; k < nk; k++) {
+                            const uint32_t acc = (uint32_t)(kk > kfirst || k > 0);
+                            mma_bf16(tmem, ad + 2 * k, bd + 2 * k, id256, acc);
+                            mma_bf16(tmem + 256, ad + 2 * k, bd2 + 2 * k, id128, acc);
+                        }
+                    } else {
+                        for (int k = 0; k < 4; k++) mma_bf16(tmem + 384, ad + 2 * k, bd + 2 * k, id128, (uint32_t)(kk > 7 || k > 0));
+                    }
+                    mma_commit(&empty[s]);
+                }
+                mma_commit(tfull);
+            }
+        }
+        __syncwarp();
+    } else {
+        uint32_t tl = 0;
+        const bool inner = p.level > 0;
+        for (int mt = blockIdx.x; mt < mtiles; mt += gridDim.x, tl++) {
+            const int r = mt * 128 + warp * 32 + lane;
+            const bool valid = r < rows;
+            uint32_t t = 0, v = 0, ch0 = 0;
+            if (valid) entry_decode(__ldg(p.entries + r), t, v, ch0);
+            const size_t orow = ((size_t)t * NODES + v) * 128;
+            mbar_wait(tfull, tl & 1);
+            fence_after_sync();
+            const uint32_t tbase = tmem + ((uint32_t)(warp * 32) << 16);
+#pragma unroll 1
+            for (int ch = 0; ch < 8; ch++) {
+                uint32_t vi[16], vo[16], vu[16], vc[16];
+                tmem_ld16(tbase + ch * 16, vi);
+                tmem_ld16(tbase + 128 + ch * 16, vo);
+                tmem_ld16(tbase + 256 + ch * 16, vu);
+                if (inner) tmem_ld16(tbase + 384 + ch * 16, vc);
+                tmem_ld_wait();
+                uint32_t hw[8], cw[8];
+#pragma unroll
+                for (int j = 0; j < 16; j += 2) {
+                    float cc[2], hh[2];
+#pragma unroll
+                    for (int q = 0; q < 2; q++) {
+                        const int n = ch * 16 + j + q;
+                        const float gi = sigmoidf(__uint_as_float(vi[j + q]) + __ldg(p.b_iou + n));
+                        const float go = sigmoidf(__uint_as_float(vo[j + q]) + __ldg(p.b_iou + 128 + n));
+                        const float gu = tanhf(__uint_as_float(vu[j + q]) + __ldg(p.b_iou + 256 + n));
+                        float cn = gi * gu;
+                        if (inner) cn += __uint_as_float(vc[j + q]) + __ldg(p.b_c + n);
+                        cc[q] = cn;
+                        hh[q] = go * tanhf(cn);
+                    }
+                    cw[j >> 1] = pack_bf16(cc[0], cc[1]);
+                    hw[j >> 1] = pack_bf16(hh[0], hh[1]);
+                }
+                if (valid) {
+                    uint4 *oc = reinterpret_cast<uint4 *>(p.c + orow + ch * 16);
+                    oc[0] = make_uint4(cw[0], cw[1], cw[2], cw[3]);
+                    oc[1] = make_uint4(cw[4], cw[5], cw[6], cw[7]);
+                    uint4 *oh = reinterpret_cast<uint4 *>(p.h + orow + ch * 16);
+                    oh[0] = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+                    oh[1] = make_uint4(hw[4], hw[5], hw[6], hw[7]);
+                    if (v == 0) {
+                        uint4 *oe = reinterpret_cast<uint4 *>(p.emb + (size_t)t * p.emb_ld + ch * 16);
+                        oe[0] = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+                        oe[1] = make_uint4(hw[4], hw[5], hw[6], hw[7]);
+                    }
+                }
+            }
+            fence_before_sync();
+            mbar_arrive(tempty);
+        }
+    }
+    fence_before_sync();
+    __syncthreads();
+    if (warp == 8) tmem_dealloc(tmem, 512);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// casts: agent_attr f32 [M][83] -> bf16 [M][128] (zero padded); forest f32 [M][31][12] -> bf16 [M][32][16] with
+// +inf -> -1 (eval_env.py:76) and zero padding.
+__global__ void k_prep(const float *__restrict__ attr, const float *__restrict__ forest, bf16 *__restrict__ attr_b,
+                       bf16 *__restrict__ x, long long M) {
+    const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long n_attr = M * 128, n_x = M * NODES * 16;
+    if (tid < n_attr) {
+        const long long m = tid >> 7;
+        const int k = (int)(tid & 127);
+        attr_b[tid] = __float2bfloat16_rn(k < 83 ? attr[m * 83 + k] : 0.0f);
+    } else if (tid < n_attr + n_x) {
+        const long long u = tid - n_attr;
+        const long long m = u / (NODES * 16);
+        const int node = (int)(u / 16 % NODES), k = (int)(u % 16);
+        float val = 0.0f;
+        if (node < 31 && k < 12) {
+            val = forest[(m * 31 + node) * 12 + k];
+            if (val == CUDART_INF_F) val = -1.0f;
+        }
+        x[u] = __float2bfloat16_rn(val);
+    }
+}
+
+// Level lists of the Tree-LSTM: every node with node_order == n >= 0 goes to list n as
+// tree | node << 22 | first child << 27.  The order inside a list is arbitrary (rows are independent).
+__global__ void k_tree_plan(const int32_t *__restrict__ adjacency, const int32_t *__restrict__ node_order, uint32_t *lists,
+                            int *counts, long long M) {
+    __shared__ int cnt[FL_POLICY_MAX_LEVELS], base[FL_POLICY_MAX_LEVELS];
+    if (threadIdx.x < FL_POLICY_MAX_LEVELS) cnt[threadIdx.x] = 0;
+    __syncthreads();
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned char child0[32];
+    unsigned short pos[31];
+    signed char lvl[31];
+    if (t < M) {
+#pragma unroll 1
+        for (int v = 0; v < 32; v++) child0[v] = 0;
+#pragma unroll 1
+        for (int g = 0; g < 10; g++) {
+            const int par = adjacency[(t * 30 + 3 * g) * 3];
+            if (par >= 0 && par < 31) child0[par] = (unsigned char)(3 * g + 1);
+        }
+#pragma unroll 1
+        for (int v = 0; v < 31; v++) {
+            int o = node_order[t * 31 + v];
+            if (o >= FL_POLICY_MAX_LEVELS) o = -1;
+            lvl[v] = (signed char)o;
+            if (o >= 0) pos[v] = (unsigned short)atomicAdd(&cnt[o], 1);
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x < FL_POLICY_MAX_LEVELS) base[threadIdx.x] = cnt[threadIdx.x] ? atomicAdd(&counts[threadIdx.x], cnt[threadIdx.x]) : 0;
+    __syncthreads();
+    if (t < M) {
+#pragma unroll 1
+        for (int v = 0; v < 31; v++) {
+            const int o = lvl[v];
+            if (o < 0) continue;
+            const size_t off = o == 0 ? 0 : (size_t)21 * M + (size_t)(o - 1) * 10 * M;
+            lists[off + base[o] + pos[v]] = (uint32_t)t | ((uint32_t)v << 22) | ((uint32_t)child0[v] << 27);
+        }
+    }
+}
+
+// Attention of one (environment, head): thread = query agent, keys / values of the head staged in shared memory
+// 128 at a time, online softmax in fp32.  qkv [M][768] = q | k | v, out [M][256].
+__global__ void __launch_bounds__(128) k_attention(const bf16 *__restrict__ qkv, bf16 *__restrict__ out, int N) {
+    __shared__ __align__(16) bf16 Ks[128][64];
+    __shared__ __align__(16) bf16 Vs[128][64];
+    const int e = blockIdx.x, hd = blockIdx.y;
+    const size_t row0 = (size_t)e * N;
+    for (int q0 = 0; q0 < N; q0 += blockDim.x) {
+        const int qi = q0 + threadIdx.x;
+        const bool active = qi < N;
+        float q[64], acc[64];
+        if (active) {
+            const uint4 *src = reinterpret_cast<const uint4 *>(qkv + (row0 + qi) * 768 + hd * 64);
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+                const uint4 w = src[j];
+                const uint32_t ww[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162 *>(&ww[k]));
+                    q[j * 8 + 2 * k] = f.x * 0.125f;
+                    q[j * 8 + 2 * k + 1] = f.y * 0.125f;
+                }
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < 64; j++) acc[j] = 0.0f;
+        float mx = -CUDART_INF_F, den = 0.0f;
+        for (int k0 = 0; k0 < N; k0 += 128) {
+            const int cnt = min(128, N - k0);
+            __syncthreads();
+            for (int idx = threadIdx.x; idx < cnt * 8; idx += blockDim.x) {
+                const int kr = idx >> 3, cc = idx & 7;
+                const bf16 *base = qkv + (row0 + k0 + kr) * 768 + hd * 64 + cc * 8;
+                *reinterpret_cast<uint4 *>(&Ks[kr][cc * 8]) = *reinterpret_cast<const uint4 *>(base + 256);
+                *reinterpret_cast<uint4 *>(&Vs[kr][cc * 8]) = *reinterpret_cast<const uint4 *>(base + 512);
+            }
+            __syncthreads();
+            if (active) {
+                for (int kr = 0; kr < cnt; kr++) {
+                    float s = 0.0f;
+                    const __nv_bfloat162 *kp = reinterpret_cast<const __nv_bfloat162 *>(&Ks[kr][0]);
+#pragma unroll
+                    for (int j = 0; j < 32; j++) {
+                        const float2 f = __bfloat1622float2(kp[j]);
+                        s = fmaf(q[2 * j], f.x, s);
+                        s = fmaf(q[2 * j + 1], f.y, s);
+                    }
+                    if (s > mx) {
+                        const float corr = __expf(mx - s);
+                        den *= corr;
+#pragma unroll
+                        for (int j = 0; j < 64; j++) acc[j] *= corr;
+                        mx = s;
+                    }
+                    const float pr = __expf(s - mx);
+                    den += pr;
+                    const __nv_bfloat162 *vp = reinterpret_cast<const __nv_bfloat162 *>(&Vs[kr][0]);
+#pragma unroll
+                    for (int j = 0; j < 32; j++) {
+                        const float2 f = __bfloat1622float2(vp[j]);
+                        acc[2 * j] = fmaf(pr, f.x, acc[2 * j]);
+                        acc[2 * j + 1] = fmaf(pr, f.y, acc[2 * j + 1]);
+                    }
+                }
+            }
+        }
+        if (active) {
+            const float inv = 1.0f / den;
+            uint4 *dst = reinterpret_cast<uint4 *>(out + (row0 + qi) * 256 + hd * 64);
+#pragma unroll
+            for (int j = 0; j < 8; j++)
+                dst[j] = make_uint4(pack_bf16(acc[8 * j] * inv, acc[8 * j + 1] * inv), pack_bf16(acc[8 * j + 2] * inv, acc[8 * j + 3] * inv),
+                                    pack_bf16(acc[8 * j + 4] * inv, acc[8 * j + 5] * inv), pack_bf16(acc[8 * j + 6] * inv, acc[8 * j + 7] * inv));
+        }
+    }
+}
+
+// Last layers: logits = actor_net.4(y2[:, :128]), value = mean over agents of critic_net.4(y2[:, 128:]).
+__global__ void __launch_bounds__(128) k_head_final(const bf16 *__restrict__ y2, const float *__restrict__ w3, const float *__restrict__ b3,
+                                                    float *__restrict__ logits, float *__restrict__ value, int N) {
+    __shared__ float ws[6 * 128];
+    __shared__ float red[128];
+    for (int i = threadIdx.x; i < 6 * 128; i += blockDim.x) ws[i] = w3[i];
+    __syncthreads();
+    const int e = blockIdx.x;
+    float vsum = 0.0f;
+    for (int a = threadIdx.x; a < N; a += blockDim.x) {
+        const bf16 *row = y2 + ((size_t)e * N + a) * 256;
+        float o[6];
+#pragma unroll
+        for (int j = 0; j < 6; j++) o[j] = b3[j];
+        for (int k = 0; k < 128; k += 2) {
+            const float2 fa = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162 *>(row + k));
+            const float2 fv = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162 *>(row + 128 + k));
+#pragma unroll
+            for (int j = 0; j < 5; j++) o[j] = fmaf(fa.y, ws[j * 128 + k + 1], fmaf(fa.x, ws[j * 128 + k], o[j]));
+            o[5] = fmaf(fv.y, ws[5 * 128 + k + 1], fmaf(fv.x, ws[5 * 128 + k], o[5]));
+        }
+        float *lo = logits + ((size_t)e * N + a) * 5;
+#pragma unroll
+        for (int j = 0; j < 5; j++) lo[j] = o[j];
+        vsum += o[5];
+    }
+    red[threadIdx.x] = vsum;
+    __syncthreads();
+    for (int s = 64; s > 0; s >>= 1) {
+        if ((int)threadIdx.x < s) red[threadIdx.x] += red[threadIdx.x + s];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) value[e] = red[0] / (float)N;
+}
+
+// plfActor.py:27-44 soft choice: np.random.seed(42); np.random.choice(valid, p=softmax(logits[valid])) draws one
+// uniform (0.3745401188473625) and returns the first entry whose normalised cumulative probability exceeds it.
+__global__ void k_choose(const float *__restrict__ logits, const uint8_t *__restrict__ valid, uint8_t *__restrict__ actions, long long n) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float x[5];
+    int idx[5], cnt = 0;
+    for (int j = 0; j < 5; j++)
+        if (valid[i * 5 + j]) { x[cnt] = logits[i * 5 + j]; idx[cnt++] = j; }
+    if (cnt == 0) { actions[i] = 0; return; }
+    float mx = x[0];
+    for (int j = 1; j < cnt; j++) mx = fmaxf(mx, x[j]);
+    float ex[5], sum = 0.0f;
+    for (int j = 0; j < cnt; j++) { ex[j] = expf(x[j] - mx); sum += ex[j]; }
+    double cdf[5], run = 0.0;
+    for (int j = 0; j < cnt; j++) { run += (double)(ex[j] / sum); cdf[j] = run; }
+    int pick = cnt - 1;
+    for (int j = 0; j < cnt; j++)
+        if (cdf[j] / run > 0.3745401188473625) { pick = j; break; }
+    actions[i] = (uint8_t)idx[pick];
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+int g_num_sms = 0;
+bool g_attr_set = false;
+
+int setup() {
+    if (!g_num_sms) {
+        int dev = 0;
+        cudaError_t e = cudaGetDevice(&dev);
+        if (e != cudaSuccess) return (int)e;
+        e = cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
+        if (e != cudaSuccess) return (int)e;
+    }
+    if (!g_attr_set) {
+        const int lin_max = 1024 + (8 + LIN_STAGES) * TILE + 256;
+        const int p_bytes = 1024 + P_STAGES * P_STAGE_BYTES + 256;
+        cudaError_t e = cudaFuncSetAttribute(k_lin<MODE_LINEAR>, cudaFuncAttributeMaxDynamicSharedMemorySize, lin_max);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(k_lin<MODE_TREE_F>, cudaFuncAttributeMaxDynamicSharedMemorySize, lin_max);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(k_tree_p, cudaFuncAttributeMaxDynamicSharedMemorySize, p_bytes);
+        if (e != cudaSuccess) return (int)e;
+        g_attr_set = true;
+    }
+    return 0;
+}
+
+size_t lin_smem(int nkb) { return 1024 + (size_t)(nkb + LIN_STAGES) * TILE + 256; }
+
+int launch_linear(const bf16 *a0, int lda0, int k0, const bf16 *a1, int lda1, int k1, const bf16 *w, const float *bias,
+                  bf16 *out, int ldc, long long M, int N, int act, cudaStream_t st) {
+    if (k0 % 64 || k1 % 64 || N % 128 || M <= 0 || M > 0x7FFFFF00LL) return -1;
+    LinArgs p = {};
+    p.a0 = a0; p.a1 = a1; p.a2 = nullptr;
+    p.lda0 = lda0; p.lda1 = lda1; p.lda2 = 0;
+    p.kb0 = k0 / 64; p.kb1 = k1 / 64; p.k16 = 0;
+    p.w = w; p.ldw = k0 + k1; p.bias = bias;
+    p.rows = (int)M; p.rows_dev = nullptr; p.rows_mul = 1; p.act = act;
+    p.out = out; p.ldc = ldc;
+    const int ny = N / 128;
+    const int mtiles = (int)((M + 127) / 128);
+    int nx = g_num_sms / ny;
+    if (nx < 1) nx = 1;
+    if (nx > mtiles) nx = mtiles;
+    k_lin<MODE_LINEAR><<<dim3(nx, ny), 288, lin_smem(p.kb0 + p.kb1), st>>>(p);
+    g_launches++;
+    return (int)cudaGetLastError();
+}
+
+struct Workspace {
+    bf16 *x, *h, *c, *fc, *attr, *a1, *a2, *emb, *qkv, *atto, *proj, *ta, *tb, *y1, *y2;
+    uint32_t *lists;
+    int *counts;
+    size_t bytes;
+};
+
+Workspace carve(void *base, long long M) {
+    Workspace w;
+    size_t off = 0;
+    auto take = [&](size_t n) { size_t o = off; off += (n + 255) & ~(size_t)255; return (uint8_t *)base + o; };
+    const size_t m = (size_t)M;
+    w.counts = (int *)take(64 * sizeof(int));
+    w.lists = (uint32_t *)take((21 + 10 * (FL_POLICY_MAX_LEVELS - 1)) * m * sizeof(uint32_t));
+    w.x = (bf16 *)take(m * NODES * 16 * 2);
+    w.h = (bf16 *)take(m * NODES * 128 * 2);
+    w.c = (bf16 *)take(m * NODES * 128 * 2);
+    w.fc = (bf16 *)take(m * NODES * 128 * 2);
+    w.attr = (bf16 *)take(m * 128 * 2);
+    w.a1 = (bf16 *)take(m * 256 * 2);
+    w.a2 = (bf16 *)take(m * 256 * 2);
+    w.emb = (bf16 *)take(m * 256 * 2);
+    w.qkv = (bf16 *)take(m * 768 * 2);
+    w.atto = (bf16 *)take(m * 256 * 2);
+    w.proj = (bf16 *)take(m * 256 * 2);
+    w.ta = (bf16 *)take(m * 256 * 2);
+    w.tb = (bf16 *)take(m * 256 * 2);
+    w.y1 = (bf16 *)take(m * 512 * 2);
+    w.y2 = (bf16 *)take(m * 256 * 2);
+    w.bytes = off;
+    return w;
+}
+
+}  // namespace
+
+extern "C" {
+
+int fl_policy_abi_version(void) { return FL_POLICY_ABI_VERSION; }
+
+uint64_t fl_policy_launch_count(void) { return g_launches; }
+
+size_t fl_policy_workspace_bytes(int64_t n_agents_total) { return carve(nullptr, n_agents_total).bytes; }
+
+int fl_policy_linear(const uint16_t *d_a, int64_t lda, const uint16_t *d_w, const float *d_bias, uint16_t *d_c, int64_t ldc,
+                     int64_t M, int64_t N, int64_t K, int act, void *stream) {
+    int rc = setup();
+    if (rc) return rc;
+    if (K > 512) return -1;
+    return launch_linear((const bf16 *)d_a, (int)lda, (int)K, nullptr, 0, 0, (const bf16 *)d_w, d_bias, (bf16 *)d_c, (int)ldc, M, (int)N, act,
+                         (cudaStream_t)stream);
+}
+
+int fl_policy_forward(const FlPolicyWeights *w, void *d_workspace, size_t workspace_bytes, int64_t E, int64_t N,
+                      const float *d_agent_attr, const float *d_forest, const int32_t *d_adjacency,
+                      const int32_t *d_node_order, float *d_logits, float *d_value, void *stream) {
+    int rc = setup();
+    if (rc) return rc;
+    const long long M = E * N;
+    if (M <= 0 || M > 0x3FFFFF || !w || !d_workspace) return -1;   // 22-bit tree ids in the level lists
+    Workspace ws = carve(d_workspace, M);
+    if (workspace_bytes < ws.bytes) return -1;
+    cudaStream_t st = (cudaStream_t)stream;
+    cudaError_t e = cudaMemsetAsync(ws.counts, 0, 64 * sizeof(int), st);
+    // a tree without a single edge has node_order -2 everywhere: its root is never evaluated and h stays 0 (TreeLSTM.py:49-50)
+    if (e == cudaSuccess) e = cudaMemsetAsync(ws.emb, 0, (size_t)M * 256 * 2, st);
+    if (e != cudaSuccess) return (int)e;
+    {
+        const long long total = M * 128 + M * NODES * 16;
+        k_prep<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(d_agent_attr, d_forest, ws.attr, ws.x, M);
+        k_tree_plan<<<(unsigned)((M + 127) / 128), 128, 0, st>>>(d_adjacency, d_node_order, ws.lists, ws.counts, M);
+        g_launches += 2;
+    }
+    // ---- Tree-LSTM, level by level (TreeLSTM.py:54-56) ----
+    for (int lv = 0; lv < FL_POLICY_MAX_LEVELS; lv++) {
+        const uint32_t *list = ws.lists + (lv == 0 ? 0 : (size_t)21 * M + (size_t)(lv - 1) * 10 * M);
+        if (lv > 0) {
+            LinArgs p = {};
+            p.a0 = ws.h; p.a2 = ws.x;
+            p.kb0 = 2; p.kb1 = 0; p.k16 = 1;
+            p.w = (const bf16 *)w->tree_ufwf; p.ldw = 144; p.bias = w->tree_b_f;
+            p.rows = 0; p.rows_dev = ws.counts + lv; p.rows_mul = 3;
+            p.entries = list; p.cstate = ws.c; p.fc = ws.fc;
+            k_lin<MODE_TREE_F><<<dim3(g_num_sms, 1), 288, lin_smem(3), st>>>(p);
+            g_launches++;
+        }
+        TreeArgs t = {};
+        t.entries = list; t.count_dev = ws.counts + lv; t.level = lv;
+        t.x = ws.x; t.h = ws.h; t.c = ws.c; t.fc = ws.fc;
+        t.emb = ws.emb + 128; t.emb_ld = 256;
+        t.uiou = (const bf16 *)w->tree_uiou; t.wiou = (const bf16 *)w->tree_wiou; t.wc = (const bf16 *)w->tree_wc;
+        t.b_iou = w->tree_b_iou; t.b_c = w->tree_b_c;
+        k_tree_p<<<g_num_sms, 288, 1024 + P_STAGES * P_STAGE_BYTES + 256, st>>>(t);
+        g_launches++;
+    }
+    // ---- attribute MLP (net_tree.py:41-50) ----
+    if ((rc = launch_linear(ws.attr, 128, 128, nullptr, 0, 0, (const bf16 *)w->attr_w[0], w->attr_b[0], ws.a1, 256, M, 256, 1, st))) return rc;
+    if ((rc = launch_linear(ws.a1, 256, 256, nullptr, 0, 0, (const bf16 *)w->attr_w[1], w->attr_b[1], ws.a2, 256, M, 256, 1, st))) return rc;
+    if ((rc = launch_linear(ws.a2, 256, 256, nullptr, 0, 0, (const bf16 *)w->attr_w[2], w->attr_b[2], ws.a1, 256, M, 256, 1, st))) return rc;
+    if ((rc = launch_linear(ws.a1, 256, 256, nullptr, 0, 0, (const bf16 *)w->attr_w[3], w->attr_b[3], ws.emb, 256, M, 128, 1, st))) return rc;
+    // ---- 3 attention blocks (net_tree.py:10-32, 51-55) ----
+    const bf16 *tin = ws.emb;
+    bf16 *touts[3] = {ws.ta, ws.tb, ws.ta};
+    for (int l = 0; l < FL_POLICY_LAYERS; l++) {
+        if ((rc = launch_linear(tin, 256, 256, nullptr, 0, 0, (const bf16 *)w->tf_wqkv[l], w->tf_bqkv[l], ws.qkv, 768, M, 768, 0, st))) return rc;
+        k_attention<<<dim3((unsigned)E, FL_POLICY_HEADS), 128, 0, st>>>(ws.qkv, ws.atto, (int)N);
+        g_launches++;
+        if ((rc = launch_linear(ws.atto, 256, 256, nullptr, 0, 0, (const bf16 *)w->tf_wo[l], w->tf_bo[l], ws.proj, 256, M, 256, 0, st))) return rc;
+        if ((rc = launch_linear(tin, 256, 256, ws.proj, 256, 256, (const bf16 *)w->tf_wm[l], w->tf_bm[l], touts[l], 256, M, 256, 1, st))) return rc;
+        tin = touts[l];
+    }
+    // ---- actor / critic heads (net_tree.py:56-71, 100-110) ----
+    if ((rc = launch_linear(ws.emb, 256, 256, tin, 256, 256, (const bf16 *)w->head_w1, w->head_b1, ws.y1, 512, M, 512, 1, st))) return rc;
+    if ((rc = launch_linear(ws.y1, 512, 256, nullptr, 0, 0, (const bf16 *)w->head_w2a, w->head_b2, ws.y2, 256, M, 128, 1, st))) return rc;
+    if ((rc = launch_linear(ws.y1 + 256, 512, 256, nullptr, 0, 0, (const bf16 *)w->head_w2c, w->head_b2 + 128, ws.y2 + 128, 256, M, 128, 1, st))) return rc;
+    k_head_final<<<(unsigned)E, 128, 0, st>>>(ws.y2, w->head_w3, w->head_b3, d_logits, d_value, (int)N);
+    g_launches++;
+    return (int)cudaGetLastError();
+}
+
+int fl_policy_choose_actions(const float *d_logits, const uint8_t *d_valid_actions, uint8_t *d_actions, int64_t n, void *stream) {
+    if (n <= 0) return -1;
+    k_choose<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(d_logits, d_valid_actions, d_actions, n);
+    g_launches++;
+    return (int)cudaGetLastError();
+}
+
+}  // extern "C"
