@@ -28,8 +28,6 @@ typedef __nv_bfloat16 bf16;
 namespace {
 
 constexpr int TILE = 128 * 128;   // bytes of a 128-row x 64-element bf16 tile (one k-block)
-constexpr int LIN_STAGES = 4;
-constexpr int LAG = 2;            // cp.async groups left in flight before a stage is published
 constexpr int P_STAGES = 3;
 constexpr int P_STAGE_BYTES = 4 * TILE;   // A tile + up to 384 rows of B
 constexpr int NODES = 32;         // node slots per tree in the h / c / fc / x scratch (31 used)
@@ -49,6 +47,8 @@ struct LinArgs {
     const int *rows_dev;        // when set: rows = *rows_dev * rows_mul (tree levels are counted on the device)
     int rows_mul;
     int act;
+    int stages;                 // A ring depth (<= LIN_MAX_STAGES)
+    long long *dbg;             // tuning only: SM-clock timestamps of CTA (0,0), NULL = off
     bf16 *out;                  // MODE_LINEAR: [rows][ldc]
     int ldc;
     const uint32_t *entries;    // MODE_TREE_F: level list (tree | node << 22 | first child << 27)
@@ -63,28 +63,37 @@ __device__ __forceinline__ void entry_decode(uint32_t e, uint32_t &tree, uint32_
     child0 = e >> 27;
 }
 
+// Warp roles of k_lin: 16 epilogue warps (TMEM lane quarter = warp & 3, 32-column group = warp >> 2),
+// 4 producer warps, 1 MMA warp.
+constexpr int LIN_THREADS = 21 * 32;
+constexpr int LIN_MAX_STAGES = 8;
+constexpr int OUT_PITCH = 272;          // bytes between rows of the staged output tile (256 + 16: conflict-free 16-byte stores)
+
 template <int MODE>
-__global__ void __launch_bounds__(288, 1) k_lin(const LinArgs p) {
+__global__ void __launch_bounds__(LIN_THREADS, 1) k_lin(const LinArgs p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     const int nkb = p.kb0 + p.kb1 + p.k16;
+    const int S = p.stages;
     const int rows = p.rows_dev ? (*p.rows_dev) * p.rows_mul : p.rows;
     const int mtiles = (rows + 127) >> 7;
     if ((int)blockIdx.x >= mtiles) return;
     uint8_t *sW = smem;
     uint8_t *sA = smem + (size_t)nkb * TILE;
-    uint64_t *bars = (uint64_t *)(sA + LIN_STAGES * TILE);
-    uint64_t *full = bars, *empty = bars + LIN_STAGES, *wfull = bars + 2 * LIN_STAGES;
+    uint8_t *sC = sA + (size_t)S * TILE;                 // output tile staging: 128 rows, pitch OUT_PITCH
+    uint64_t *bars = (uint64_t *)(sC + 128 * OUT_PITCH);
+    uint64_t *full = bars, *empty = bars + LIN_MAX_STAGES, *wfull = bars + 2 * LIN_MAX_STAGES;
     uint64_t *tfull = wfull + 1, *tempty = tfull + 2;
     uint32_t *tmem_slot = (uint32_t *)(tempty + 2);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int n0 = blockIdx.y * 128;
+    if (p.dbg && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) p.dbg[3] = clock64();
 
-    if (warp == 8) {
+    if (warp == 20) {
         if (lane == 0) {
-            for (int s = 0; s < LIN_STAGES; s++) { mbar_init(&full[s], 128); mbar_init(&empty[s], 1); }
+            for (int s = 0; s < S; s++) { mbar_init(&full[s], 128); mbar_init(&empty[s], 1); }
             mbar_init(wfull, 128);
-            for (int b = 0; b < 2; b++) { mbar_init(&tfull[b], 1); mbar_init(&tempty[b], 128); }
+            for (int b = 0; b < 2; b++) { mbar_init(&tfull[b], 1); mbar_init(&tempty[b], 512); }
             mbar_init_fence();
         }
         __syncwarp();
@@ -95,9 +104,9 @@ __global__ void __launch_bounds__(288, 1) k_lin(const LinArgs p) {
     fence_after_sync();
     const uint32_t tmem = *tmem_slot;
 
-    if (warp >= 4 && warp < 8) {
+    if (warp >= 16 && warp < 20) {
         // ---------------- producers: 128 threads, thread = (16-byte chunk c, rows r0 + 16 i) ----------------
-        const int tp = threadIdx.x - 128;
+        const int tp = threadIdx.x - 512;
         const int c = tp & 7, r0 = tp >> 3;
         const uint32_t swz = (uint32_t)((c ^ (r0 & 7)) << 4) + (uint32_t)r0 * 128u;
         for (int kb = 0; kb < nkb; kb++) {
@@ -109,10 +118,7 @@ __global__ void __launch_bounds__(288, 1) k_lin(const LinArgs p) {
                 for (int i = 0; i < 8; i++) cp_async16(dst + i * 2048, src + (size_t)(n0 + r0 + 16 * i) * p.ldw, 16);
             }
         }
-        cp_async_commit();
-        cp_async_wait<0>();
-        fence_proxy_async();
-        mbar_arrive(wfull);
+        cp_async_arrive(wfull);
 
         uint32_t it = 0;
         for (int mt = blockIdx.x; mt < mtiles; mt += gridDim.x) {
@@ -136,8 +142,9 @@ __global__ void __launch_bounds__(288, 1) k_lin(const LinArgs p) {
                 }
             }
             for (int kb = 0; kb < nkb; kb++, it++) {
-                const int s = it % LIN_STAGES;
-                mbar_wait(&empty[s], ((it / LIN_STAGES) & 1) ^ 1);
+                const int s = it % S;
+                mbar_wait(&empty[s], ((it / S) & 1) ^ 1);
+                if (p.dbg && tp == 0 && kb == 0 && blockIdx.x == 0 && blockIdx.y == 0 && it / nkb < 8) p.dbg[80 + it / nkb] = clock64();
                 const uint32_t dst = smem_u32(sA + (size_t)s * TILE) + swz;
                 if (kb < p.kb0) {
                     const bf16 *src = p.a0 + kb * 64 + c * 8;
@@ -152,32 +159,31 @@ __global__ void __launch_bounds__(288, 1) k_lin(const LinArgs p) {
 #pragma unroll
                     for (int i = 0; i < 8; i++) cp_async16(dst + i * 2048, src + off2[i], ok[i]);
                 }
-                cp_async_commit();
-                if (it >= LAG) {
-                    cp_async_wait<LAG>();
-                    fence_proxy_async();
-                    mbar_arrive(&full[(it - LAG) % LIN_STAGES]);
-                }
+                cp_async_arrive(&full[s]);
             }
         }
-        cp_async_wait<0>();
-        fence_proxy_async();
-        for (uint32_t j = it >= LAG ? it - LAG : 0; j < it; j++) mbar_arrive(&full[j % LIN_STAGES]);
-    } else if (warp == 8) {
+        cp_async_wait_all();
+    } else if (warp == 20) {
         // ---------------- MMA issue: one thread ----------------
         if (lane == 0) {
+            const bool dbg = p.dbg && blockIdx.x == 0 && blockIdx.y == 0;
+            if (dbg) p.dbg[0] = clock64();
             mbar_wait(wfull, 0);
             fence_after_sync();
+            if (dbg) p.dbg[1] = clock64();
             const uint32_t idesc = idesc_bf16(128, 128);
             uint32_t it = 0, tl = 0;
             for (int mt = blockIdx.x; mt < mtiles; mt += gridDim.x, tl++) {
                 const uint32_t b = tl & 1;
                 mbar_wait(&tempty[b], ((tl >> 1) & 1) ^ 1);
                 fence_after_sync();
+                if (dbg && tl < 8) p.dbg[8 + tl * 4] = clock64();
                 for (int kb = 0; kb < nkb; kb++, it++) {
-                    const int s = it % LIN_STAGES;
-                    mbar_wait(&full[s], (it / LIN_STAGES) & 1);
+                    const int s = it % S;
+                    mbar_wait(&full[s], (it / S) & 1);
                     fence_after_sync();
+                    if (dbg && tl < 8 && kb == 0) p.dbg[8 + tl * 4 + 1] = clock64();
+                    if (dbg && tl < 8 && kb == nkb - 1) p.dbg[8 + tl * 4 + 2] = clock64();
                     const uint64_t ad = desc_sw128(smem_u32(sA + (size_t)s * TILE));
                     const uint64_t bd = desc_sw128(smem_u32(sW + (size_t)kb * TILE));
                     const int nk = (p.k16 && kb == nkb - 1) ? 1 : 4;
@@ -189,11 +195,12 @@ __global__ void __launch_bounds__(288, 1) k_lin(const LinArgs p) {
         }
         __syncwarp();
     } else {
-        // ---------------- epilogue: warp w owns TMEM lanes 32w..32w+31 = rows of the tile ----------------
+        // ---------------- epilogue: warp w owns TMEM lanes 32(w&3).. (rows) and columns 32(w>>2).. ----------------
         uint32_t tl = 0;
+        const int q = warp & 3, cg = warp >> 2;
         for (int mt = blockIdx.x; mt < mtiles; mt += gridDim.x, tl++) {
             const uint32_t b = tl & 1;
-            const int r = mt * 128 + warp * 32 + lane;
+            const int r = mt * 128 + q * 32 + lane;
             const bool valid = r < rows;
             size_t orow = 0;
             if (valid) {
@@ -205,49 +212,246 @@ __global__ void __launch_bounds__(288, 1) k_lin(const LinArgs p) {
                     orow = ((size_t)t * NODES + ch0 + (r % 3)) * 128;
                 }
             }
+            float bias[32];
+#pragma unroll
+            for (int j = 0; j < 8; j++) *reinterpret_cast<float4 *>(&bias[4 * j]) = __ldg(reinterpret_cast<const float4 *>(p.bias + n0 + cg * 32) + j);
+            uint32_t cw[16];
+            if (MODE == MODE_TREE_F && valid) {
+                const uint4 *cin = reinterpret_cast<const uint4 *>(p.cstate + orow + cg * 32);
+#pragma unroll
+                for (int j = 0; j < 4; j++) *reinterpret_cast<uint4 *>(&cw[4 * j]) = cin[j];
+            }
             mbar_wait(&tfull[b], (tl >> 1) & 1);
             fence_after_sync();
-            const uint32_t tbase = tmem + ((uint32_t)(warp * 32) << 16) + b * 128;
-#pragma unroll 1
-            for (int ch = 0; ch < 8; ch++) {
-                uint32_t v[16];
-                tmem_ld16(tbase + ch * 16, v);
-                tmem_ld_wait();
-                float f[16];
-#pragma unroll
-                for (int j = 0; j < 16; j++) f[j] = __uint_as_float(v[j]) + __ldg(p.bias + n0 + ch * 16 + j);
-                if (MODE == MODE_LINEAR) {
-                    if (p.act) {
-#pragma unroll
-                        for (int j = 0; j < 16; j++) f[j] = gelu_erf(f[j]);
-                    }
-                    if (valid) {
-                        uint4 *o = reinterpret_cast<uint4 *>(p.out + orow + ch * 16);
-                        o[0] = make_uint4(pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]), pack_bf16(f[4], f[5]), pack_bf16(f[6], f[7]));
-                        o[1] = make_uint4(pack_bf16(f[8], f[9]), pack_bf16(f[10], f[11]), pack_bf16(f[12], f[13]), pack_bf16(f[14], f[15]));
-                    }
-                } else if (valid) {
-                    const uint4 *cin = reinterpret_cast<const uint4 *>(p.cstate + orow + ch * 16);
-                    uint4 c0 = cin[0], c1 = cin[1];
-                    const uint32_t cw[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
-                    uint32_t ow[8];
-#pragma unroll
-                    for (int j = 0; j < 8; j++) {
-                        const float2 cc = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162 *>(&cw[j]));
-                        ow[j] = pack_bf16(sigmoidf(f[2 * j]) * cc.x, sigmoidf(f[2 * j + 1]) * cc.y);
-                    }
-                    uint4 *o = reinterpret_cast<uint4 *>(p.fc + orow + ch * 16);
-                    o[0] = make_uint4(ow[0], ow[1], ow[2], ow[3]);
-                    o[1] = make_uint4(ow[4], ow[5], ow[6], ow[7]);
-                }
-            }
+            const uint32_t tbase = tmem + ((uint32_t)(q * 32) << 16) + b * 128 + cg * 32;
+            const bool dbg = p.dbg && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0 && tl < 8;
+            if (dbg) p.dbg[48 + tl * 4] = clock64();
+            uint32_t v[32];
+            tmem_ld16(tbase, v);
+            tmem_ld16(tbase + 16, v + 16);
+            tmem_ld_wait();
             fence_before_sync();
-            mbar_arrive(&tempty[b]);
+            mbar_arrive(&tempty[b]);      // the accumulator is in registers: the MMA warp may overwrite the buffer
+            if (dbg) p.dbg[48 + tl * 4 + 1] = clock64();
+            uint32_t ow[16];
+#pragma unroll
+            for (int j = 0; j < 16; j++) {
+                float f0 = __uint_as_float(v[2 * j]) + bias[2 * j], f1 = __uint_as_float(v[2 * j + 1]) + bias[2 * j + 1];
+                if (MODE == MODE_LINEAR) {
+                    if (p.act & 1) { f0 = gelu_erf(f0); f1 = gelu_erf(f1); }
+                } else {
+                    const float2 cc = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162 *>(&cw[j]));
+                    f0 = sigmoidf(f0) * cc.x;
+                    f1 = sigmoidf(f1) * cc.y;
+                }
+                ow[j] = pack_bf16(f0, f1);
+            }
+            // registers -> padded shared-memory tile -> one 256-byte bulk store per row (the direct form, 32 lanes
+            // writing 16 bytes to 32 different rows, ran at half a store transaction per clock and paced the kernel)
+            if (p.act & 4) { if (dbg) p.dbg[48 + tl * 4 + 2] = clock64(); if (ow[3] == 0x12345678u) p.out[0] = bf16(); continue; }
+            if (cg == 0) bulk_wait_read();                 // the previous tile's rows have left the staging buffer
+            named_bar_sync(1, 512);
+            const uint32_t srow = smem_u32(sC) + (uint32_t)(q * 32 + lane) * OUT_PITCH;
+#pragma unroll
+            for (int j = 0; j < 4; j++) st_shared_v4(srow + cg * 64 + j * 16, ow[4 * j], ow[4 * j + 1], ow[4 * j + 2], ow[4 * j + 3]);
+            fence_proxy_async();
+            named_bar_sync(2, 512);
+            if (cg == 0) {
+                if (valid) bulk_store((MODE == MODE_LINEAR ? p.out : p.fc) + orow, srow, 256);
+                bulk_commit();
+            }
+            if (dbg) p.dbg[48 + tl * 4 + 2] = clock64();
         }
+        if (cg == 0) bulk_wait_all();
     }
     fence_before_sync();
     __syncthreads();
-    if (warp == 8) tmem_dealloc(tmem, 256);
+    if (p.dbg && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) p.dbg[2] = clock64();
+    if (warp == 20) tmem_dealloc(tmem, 256);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Leaves of the Tree-LSTM (node_order 0, two thirds of all nodes): iou = W_iou x + b (K = 12, one k16 MMA step),
+// c = sig(i) tanh(u), h = sig(o) tanh(c).  W_iou stays resident; the 128-leaf x tiles stream through a ring; each
+// tile is processed as two halves of 64 hidden units (i | o | u = 192 TMEM columns per half) so that two
+// accumulator buffers fit and the gate epilogue of one half overlaps the MMAs of the next.
+struct LeafArgs {
+    const uint32_t *entries;
+    const int *count_dev;
+    const bf16 *x;
+    bf16 *h, *c;
+    bf16 *emb;
+    int emb_ld;
+    const bf16 *wiou;
+    const float *b_iou;
+};
+constexpr int LEAF_THREADS = 13 * 32;   // 8 epilogue warps, 4 producer warps, 1 MMA warp
+constexpr int LEAF_STAGES = 6;
+constexpr int LEAF_PITCH = 144;         // 128 bytes (64 hidden units) + 16
+
+__global__ void __launch_bounds__(LEAF_THREADS, 1) k_tree_leaf(const LeafArgs p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    const int rows = *p.count_dev;
+    const int mtiles = (rows + 127) >> 7;
+    if ((int)blockIdx.x >= mtiles) return;
+    uint8_t *sW = smem;                       // 384 rows x 128 B (first 32 B of every row used)
+    uint8_t *sA = smem + 3 * TILE;
+    uint8_t *sC = sA + LEAF_STAGES * TILE;    // staged h | c of one half tile: 2 x 128 rows, pitch LEAF_PITCH
+    uint64_t *bars = (uint64_t *)(sC + 2 * 128 * LEAF_PITCH);
+    uint64_t *full = bars, *empty = bars + LEAF_STAGES, *wfull = bars + 2 * LEAF_STAGES;
+    uint64_t *tfull = wfull + 1, *tempty = tfull + 2;
+    uint32_t *tmem_slot = (uint32_t *)(tempty + 2);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    if (warp == 12) {
+        if (lane == 0) {
+            for (int s = 0; s < LEAF_STAGES; s++) { mbar_init(&full[s], 128); mbar_init(&empty[s], 1); }
+            mbar_init(wfull, 128);
+            for (int b = 0; b < 2; b++) { mbar_init(&tfull[b], 1); mbar_init(&tempty[b], 256); }
+            mbar_init_fence();
+        }
+        __syncwarp();
+        tmem_alloc(tmem_slot, 512);
+    }
+    fence_before_sync();
+    __syncthreads();
+    fence_after_sync();
+    const uint32_t tmem = *tmem_slot;
+
+    if (warp >= 8 && warp < 12) {
+        const int tp = threadIdx.x - 256;
+        const int c = tp & 7, r0 = tp >> 3;
+        const uint32_t swz = (uint32_t)((c ^ (r0 & 7)) << 4) + (uint32_t)r0 * 128u;
+        if (c < 2) {
+            const uint32_t dst = smem_u32(sW) + swz;
+#pragma unroll 8
+            for (int i = 0; i < 24; i++) cp_async16(dst + i * 2048, p.wiou + (size_t)(r0 + 16 * i) * 16 + c * 8, 16);
+        }
+        cp_async_arrive(wfull);
+        uint32_t it = 0;
+        for (int mt = blockIdx.x; mt < mtiles; mt += gridDim.x, it++) {
+            const int s = it % LEAF_STAGES;
+            mbar_wait(&empty[s], ((it / LEAF_STAGES) & 1) ^ 1);
+            if (c < 2) {
+                const uint32_t dst = smem_u32(sA + (size_t)s * TILE) + swz;
+#pragma unroll
+                for (int i = 0; i < 8; i++) {
+                    const int r = mt * 128 + r0 + 16 * i;
+                    uint32_t off = 0, ok = 0;
+                    if (r < rows) {
+                        uint32_t t, v, ch0;
+                        entry_decode(__ldg(p.entries + r), t, v, ch0);
+                        off = (t * NODES + v) * 16u;
+                        ok = 16;
+                    }
+                    cp_async16(dst + i * 2048, p.x + off + c * 8, ok);
+                }
+            }
+            cp_async_arrive(&full[s]);
+        }
+        cp_async_wait_all();
+    } else if (warp == 12) {
+        if (lane == 0) {
+            mbar_wait(wfull, 0);
+            fence_after_sync();
+            const uint32_t idesc = idesc_bf16(128, 64);
+            const uint32_t w0 = smem_u32(sW);
+            uint32_t it = 0, hl = 0;
+            for (int mt = blockIdx.x; mt < mtiles; mt += gridDim.x, it++) {
+                const int s = it % LEAF_STAGES;
+                mbar_wait(&full[s], (it / LEAF_STAGES) & 1);
+                fence_after_sync();
+                const uint64_t ad = desc_sw128(smem_u32(sA + (size_t)s * TILE));
+                for (int half = 0; half < 2; half++, hl++) {
+                    const uint32_t b = hl & 1;
+                    mbar_wait(&tempty[b], ((hl >> 1) & 1) ^ 1);
+                    fence_after_sync();
+                    for (int g = 0; g < 3; g++)     // gate g (i, o, u): rows 128 g + 64 half .. of W_iou
+                        mma_bf16(tmem + b * 256 + g * 64, ad, desc_sw128(w0 + (uint32_t)(g * 128 + half * 64) * 128u), idesc, 0u);
+                    if (half == 1) mma_commit(&empty[s]);
+                    mma_commit(&tfull[b]);
+                }
+            }
+        }
+        __syncwarp();
+    } else {
+        const int q = warp & 3, sub = warp >> 2;      // sub: which 32 of the half's 64 hidden units
+        uint32_t hl = 0;
+        for (int mt = blockIdx.x; mt < mtiles; mt += gridDim.x) {
+            const int r = mt * 128 + q * 32 + lane;
+            const bool valid = r < rows;
+            uint32_t t = 0, v = 0, ch0 = 0;
+            if (valid) entry_decode(__ldg(p.entries + r), t, v, ch0);
+            const size_t orow = ((size_t)t * NODES + v) * 128;
+            for (int half = 0; half < 2; half++, hl++) {
+                const uint32_t b = hl & 1;
+                const int n0 = half * 64 + sub * 32;
+                mbar_wait(&tfull[b], (hl >> 1) & 1);
+                fence_after_sync();
+                const uint32_t tbase = tmem + ((uint32_t)(q * 32) << 16) + b * 256 + sub * 32;
+                uint32_t vi[32], vo[32], vu[32];
+                tmem_ld16(tbase, vi);
+                tmem_ld16(tbase + 16, vi + 16);
+                tmem_ld16(tbase + 64, vo);
+                tmem_ld16(tbase + 80, vo + 16);
+                tmem_ld16(tbase + 128, vu);
+                tmem_ld16(tbase + 144, vu + 16);
+                tmem_ld_wait();
+                fence_before_sync();
+                mbar_arrive(&tempty[b]);
+                uint32_t hw[16], cw[16];
+#pragma unroll
+                for (int j = 0; j < 8; j++) {
+                    const float4 bi = __ldg(reinterpret_cast<const float4 *>(p.b_iou + n0) + j);
+                    const float4 bo = __ldg(reinterpret_cast<const float4 *>(p.b_iou + 128 + n0) + j);
+                    const float4 bu = __ldg(reinterpret_cast<const float4 *>(p.b_iou + 256 + n0) + j);
+                    const float bis[4] = {bi.x, bi.y, bi.z, bi.w}, bos[4] = {bo.x, bo.y, bo.z, bo.w}, bus[4] = {bu.x, bu.y, bu.z, bu.w};
+                    float cc[4], hh[4];
+#pragma unroll
+                    for (int k = 0; k < 4; k++) {
+                        const float gi = sigmoidf(__uint_as_float(vi[4 * j + k]) + bis[k]);
+                        const float go = sigmoidf(__uint_as_float(vo[4 * j + k]) + bos[k]);
+                        const float gu = tanh_fast(__uint_as_float(vu[4 * j + k]) + bus[k]);
+                        cc[k] = gi * gu;
+                        hh[k] = go * tanh_fast(cc[k]);
+                    }
+                    cw[2 * j] = pack_bf16(cc[0], cc[1]);
+                    cw[2 * j + 1] = pack_bf16(cc[2], cc[3]);
+                    hw[2 * j] = pack_bf16(hh[0], hh[1]);
+                    hw[2 * j + 1] = pack_bf16(hh[2], hh[3]);
+                }
+                if (sub == 0) bulk_wait_read();
+                named_bar_sync(1, 256);
+                const uint32_t srow = smem_u32(sC) + (uint32_t)(q * 32 + lane) * LEAF_PITCH;
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    st_shared_v4(srow + sub * 64 + j * 16, hw[4 * j], hw[4 * j + 1], hw[4 * j + 2], hw[4 * j + 3]);
+                    st_shared_v4(srow + 128 * LEAF_PITCH + sub * 64 + j * 16, cw[4 * j], cw[4 * j + 1], cw[4 * j + 2], cw[4 * j + 3]);
+                }
+                fence_proxy_async();
+                named_bar_sync(2, 256);
+                if (sub == 0) {
+                    if (valid) {
+                        bulk_store(p.h + orow + half * 64, srow, 128);
+                        bulk_store(p.c + orow + half * 64, srow + 128 * LEAF_PITCH, 128);
+                    }
+                    bulk_commit();
+                }
+                if (valid) {
+                    if (v == 0) {
+                        uint4 *oe = reinterpret_cast<uint4 *>(p.emb + (size_t)t * p.emb_ld + n0);
+#pragma unroll
+                        for (int j = 0; j < 4; j++) oe[j] = make_uint4(hw[4 * j], hw[4 * j + 1], hw[4 * j + 2], hw[4 * j + 3]);
+                    }
+                }
+            }
+        }
+        if (sub == 0) bulk_wait_all();
+    }
+    fence_before_sync();
+    __syncthreads();
+    if (warp == 12) tmem_dealloc(tmem, 512);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -264,7 +468,7 @@ struct TreeArgs {
     const float *b_iou, *b_c;
 };
 
-__global__ void __launch_bounds__(288, 1) k_tree_p(const TreeArgs p) {
+__global__ void __launch_bounds__(416, 1) k_tree_p(const TreeArgs p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     const int rows = *p.count_dev;
@@ -276,11 +480,11 @@ __global__ void __launch_bounds__(288, 1) k_tree_p(const TreeArgs p) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int kfirst = p.level == 0 ? 6 : 0, klast = p.level == 0 ? 6 : 12;   // k-iterations: 0-5 h, 6 x, 7-12 fc
 
-    if (warp == 8) {
+    if (warp == 12) {
         if (lane == 0) {
             for (int s = 0; s < P_STAGES; s++) { mbar_init(&full[s], 128); mbar_init(&empty[s], 1); }
             mbar_init(tfull, 1);
-            mbar_init(tempty, 128);
+            mbar_init(tempty, 256);
             mbar_init_fence();
         }
         __syncwarp();
@@ -291,8 +495,8 @@ __global__ void __launch_bounds__(288, 1) k_tree_p(const TreeArgs p) {
     fence_after_sync();
     const uint32_t tmem = *tmem_slot;
 
-    if (warp >= 4 && warp < 8) {
-        const int tp = threadIdx.x - 128;
+    if (warp >= 8 && warp < 12) {
+        const int tp = threadIdx.x - 256;
         const int c = tp & 7, r0 = tp >> 3;
         const uint32_t swz = (uint32_t)((c ^ (r0 & 7)) << 4) + (uint32_t)r0 * 128u;
         uint32_t it = 0;
@@ -339,18 +543,11 @@ __global__ void __launch_bounds__(288, 1) k_tree_p(const TreeArgs p) {
 #pragma unroll
                     for (int i = 0; i < 8; i++) cp_async16(dstB + i * 2048, wsrc + (size_t)(r0 + 16 * i) * 384, 16);
                 }
-                cp_async_commit();
-                if (it >= LAG) {
-                    cp_async_wait<LAG>();
-                    fence_proxy_async();
-                    mbar_arrive(&full[(it - LAG) % P_STAGES]);
-                }
+                cp_async_arrive(&full[s]);
             }
         }
-        cp_async_wait<0>();
-        fence_proxy_async();
-        for (uint32_t j = it >= LAG ? it - LAG : 0; j < it; j++) mbar_arrive(&full[j % P_STAGES]);
-    } else if (warp == 8) {
+        cp_async_wait_all();
+    } else if (warp == 12) {
         if (lane == 0) {
             const uint32_t id256 = idesc_bf16(128, 256), id128 = idesc_bf16(128, 128);
             uint32_t it = 0, tl = 0;
@@ -383,16 +580,16 @@ __global__ void __launch_bounds__(288, 1) k_tree_p(const TreeArgs p) {
         uint32_t tl = 0;
         const bool inner = p.level > 0;
         for (int mt = blockIdx.x; mt < mtiles; mt += gridDim.x, tl++) {
-            const int r = mt * 128 + warp * 32 + lane;
+            const int r = mt * 128 + (warp & 3) * 32 + lane;
             const bool valid = r < rows;
             uint32_t t = 0, v = 0, ch0 = 0;
             if (valid) entry_decode(__ldg(p.entries + r), t, v, ch0);
             const size_t orow = ((size_t)t * NODES + v) * 128;
             mbar_wait(tfull, tl & 1);
             fence_after_sync();
-            const uint32_t tbase = tmem + ((uint32_t)(warp * 32) << 16);
+            const uint32_t tbase = tmem + ((uint32_t)((warp & 3) * 32) << 16);
 #pragma unroll 1
-            for (int ch = 0; ch < 8; ch++) {
+            for (int ch = (warp >> 2) * 4; ch < (warp >> 2) * 4 + 4; ch++) {
                 uint32_t vi[16], vo[16], vu[16], vc[16];
                 tmem_ld16(tbase + ch * 16, vi);
                 tmem_ld16(tbase + 128 + ch * 16, vo);
@@ -400,19 +597,26 @@ __global__ void __launch_bounds__(288, 1) k_tree_p(const TreeArgs p) {
                 if (inner) tmem_ld16(tbase + 384 + ch * 16, vc);
                 tmem_ld_wait();
                 uint32_t hw[8], cw[8];
+                float bi[16], bo[16], bu[16], bc[16];
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    *reinterpret_cast<float4 *>(&bi[4 * j]) = __ldg(reinterpret_cast<const float4 *>(p.b_iou + ch * 16) + j);
+                    *reinterpret_cast<float4 *>(&bo[4 * j]) = __ldg(reinterpret_cast<const float4 *>(p.b_iou + 128 + ch * 16) + j);
+                    *reinterpret_cast<float4 *>(&bu[4 * j]) = __ldg(reinterpret_cast<const float4 *>(p.b_iou + 256 + ch * 16) + j);
+                    *reinterpret_cast<float4 *>(&bc[4 * j]) = __ldg(reinterpret_cast<const float4 *>(p.b_c + ch * 16) + j);
+                }
 #pragma unroll
                 for (int j = 0; j < 16; j += 2) {
                     float cc[2], hh[2];
 #pragma unroll
                     for (int q = 0; q < 2; q++) {
-                        const int n = ch * 16 + j + q;
-                        const float gi = sigmoidf(__uint_as_float(vi[j + q]) + __ldg(p.b_iou + n));
-                        const float go = sigmoidf(__uint_as_float(vo[j + q]) + __ldg(p.b_iou + 128 + n));
-                        const float gu = tanhf(__uint_as_float(vu[j + q]) + __ldg(p.b_iou + 256 + n));
+                        const float gi = sigmoidf(__uint_as_float(vi[j + q]) + bi[j + q]);
+                        const float go = sigmoidf(__uint_as_float(vo[j + q]) + bo[j + q]);
+                        const float gu = tanh_fast(__uint_as_float(vu[j + q]) + bu[j + q]);
                         float cn = gi * gu;
-                        if (inner) cn += __uint_as_float(vc[j + q]) + __ldg(p.b_c + n);
+                        if (inner) cn += __uint_as_float(vc[j + q]) + bc[j + q];
                         cc[q] = cn;
-                        hh[q] = go * tanhf(cn);
+                        hh[q] = go * tanh_fast(cn);
                     }
                     cw[j >> 1] = pack_bf16(cc[0], cc[1]);
                     hw[j >> 1] = pack_bf16(hh[0], hh[1]);
@@ -437,30 +641,43 @@ __global__ void __launch_bounds__(288, 1) k_tree_p(const TreeArgs p) {
     }
     fence_before_sync();
     __syncthreads();
-    if (warp == 8) tmem_dealloc(tmem, 512);
+    if (warp == 12) tmem_dealloc(tmem, 512);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
 // casts: agent_attr f32 [M][83] -> bf16 [M][128] (zero padded); forest f32 [M][31][12] -> bf16 [M][32][16] with
-// +inf -> -1 (eval_env.py:76) and zero padding.
+// +inf -> -1 (eval_env.py:76) and zero padding.  One thread writes 16 bytes (attr) or one node's 32 bytes (x).
 __global__ void k_prep(const float *__restrict__ attr, const float *__restrict__ forest, bf16 *__restrict__ attr_b,
                        bf16 *__restrict__ x, long long M) {
     const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    const long long n_attr = M * 128, n_x = M * NODES * 16;
+    const long long n_attr = M * 16, n_x = M * NODES;
     if (tid < n_attr) {
-        const long long m = tid >> 7;
-        const int k = (int)(tid & 127);
-        attr_b[tid] = __float2bfloat16_rn(k < 83 ? attr[m * 83 + k] : 0.0f);
+        const long long m = tid >> 4;
+        const int k0 = (int)(tid & 15) * 8;
+        float f[8];
+#pragma unroll
+        for (int j = 0; j < 8; j++) f[j] = k0 + j < 83 ? attr[m * 83 + k0 + j] : 0.0f;
+        reinterpret_cast<uint4 *>(attr_b)[tid] = make_uint4(pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]), pack_bf16(f[4], f[5]), pack_bf16(f[6], f[7]));
     } else if (tid < n_attr + n_x) {
         const long long u = tid - n_attr;
-        const long long m = u / (NODES * 16);
-        const int node = (int)(u / 16 % NODES), k = (int)(u % 16);
-        float val = 0.0f;
-        if (node < 31 && k < 12) {
-            val = forest[(m * 31 + node) * 12 + k];
-            if (val == CUDART_INF_F) val = -1.0f;
+        const long long m = u / NODES;
+        const int node = (int)(u % NODES);
+        float f[12];
+#pragma unroll
+        for (int j = 0; j < 12; j++) f[j] = 0.0f;
+        if (node < 31) {
+            const float4 *src = reinterpret_cast<const float4 *>(forest + (m * 31 + node) * 12);
+#pragma unroll
+            for (int j = 0; j < 3; j++) {
+                const float4 q = src[j];
+                f[4 * j] = q.x; f[4 * j + 1] = q.y; f[4 * j + 2] = q.z; f[4 * j + 3] = q.w;
+            }
+#pragma unroll
+            for (int j = 0; j < 12; j++) f[j] = f[j] == CUDART_INF_F ? -1.0f : f[j];
         }
-        x[u] = __float2bfloat16_rn(val);
+        uint4 *dst = reinterpret_cast<uint4 *>(x + u * 16);
+        dst[0] = make_uint4(pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]), pack_bf16(f[4], f[5]), pack_bf16(f[6], f[7]));
+        dst[1] = make_uint4(pack_bf16(f[8], f[9]), pack_bf16(f[10], f[11]), 0u, 0u);
     }
 }
 
@@ -505,70 +722,83 @@ __global__ void k_tree_plan(const int32_t *__restrict__ adjacency, const int32_t
     }
 }
 
-// Attention of one (environment, head): thread = query agent, keys / values of the head staged in shared memory
-// 128 at a time, online softmax in fp32.  qkv [M][768] = q | k | v, out [M][256].
-__global__ void __launch_bounds__(128) k_attention(const bf16 *__restrict__ qkv, bf16 *__restrict__ out, int N) {
-    __shared__ __align__(16) bf16 Ks[128][64];
-    __shared__ __align__(16) bf16 Vs[128][64];
+// Attention of one (environment, head): thread = query agent, keys / values of the head staged in shared memory as
+// fp32, 64 at a time (read back as broadcast 16-byte loads), online softmax in fp32.  qkv [M][768] = q | k | v,
+// out [M][256].
+__global__ void __launch_bounds__(64) k_attention(const bf16 *__restrict__ qkv, bf16 *__restrict__ out, int N) {
+    __shared__ float4 Ks[64][16];
+    __shared__ float4 Vs[64][16];
     const int e = blockIdx.x, hd = blockIdx.y;
     const size_t row0 = (size_t)e * N;
-    for (int q0 = 0; q0 < N; q0 += blockDim.x) {
+    for (int q0 = 0; q0 < N; q0 += 64) {
         const int qi = q0 + threadIdx.x;
         const bool active = qi < N;
-        float q[64], acc[64];
+        float4 q[16], acc[16];
+#pragma unroll
+        for (int j = 0; j < 16; j++) q[j] = acc[j] = make_float4(0.f, 0.f, 0.f, 0.f);
         if (active) {
             const uint4 *src = reinterpret_cast<const uint4 *>(qkv + (row0 + qi) * 768 + hd * 64);
 #pragma unroll
             for (int j = 0; j < 8; j++) {
                 const uint4 w = src[j];
-                const uint32_t ww[4] = {w.x, w.y, w.z, w.w};
-#pragma unroll
-                for (int k = 0; k < 4; k++) {
-                    const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162 *>(&ww[k]));
-                    q[j * 8 + 2 * k] = f.x * 0.125f;
-                    q[j * 8 + 2 * k + 1] = f.y * 0.125f;
-                }
+                const float2 f0 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162 *>(&w.x));
+                const float2 f1 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162 *>(&w.y));
+                const float2 f2 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162 *>(&w.z));
+                const float2 f3 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162 *>(&w.w));
+                q[2 * j] = make_float4(f0.x * 0.125f, f0.y * 0.125f, f1.x * 0.125f, f1.y * 0.125f);
+                q[2 * j + 1] = make_float4(f2.x * 0.125f, f2.y * 0.125f, f3.x * 0.125f, f3.y * 0.125f);
             }
         }
-#pragma unroll
-        for (int j = 0; j < 64; j++) acc[j] = 0.0f;
         float mx = -CUDART_INF_F, den = 0.0f;
-        for (int k0 = 0; k0 < N; k0 += 128) {
-            const int cnt = min(128, N - k0);
+        for (int k0 = 0; k0 < N; k0 += 64) {
+            const int cnt = min(64, N - k0);
             __syncthreads();
-            for (int idx = threadIdx.x; idx < cnt * 8; idx += blockDim.x) {
+            for (int idx = threadIdx.x; idx < cnt * 8; idx += 64) {
                 const int kr = idx >> 3, cc = idx & 7;
                 const bf16 *base = qkv + (row0 + k0 + kr) * 768 + hd * 64 + cc * 8;
-                *reinterpret_cast<uint4 *>(&Ks[kr][cc * 8]) = *reinterpret_cast<const uint4 *>(base + 256);
-                *reinterpret_cast<uint4 *>(&Vs[kr][cc * 8]) = *reinterpret_cast<const uint4 *>(base + 512);
+                const uint4 kw = *reinterpret_cast<const uint4 *>(base + 256);
+                const uint4 vw = *reinterpret_cast<const uint4 *>(base + 512);
+                float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162 *>(&kw.x));
+                float2 b = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162 *>(&kw.y));
+                Ks[kr][2 * cc] = make_float4(a.x, a.y, b.x, b.y);
+                a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162 *>(&kw.z));
+                b = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162 *>(&kw.w));
+                Ks[kr][2 * cc + 1] = make_float4(a.x, a.y, b.x, b.y);
+                a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162 *>(&vw.x));
+                b = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162 *>(&vw.y));
+                Vs[kr][2 * cc] = make_float4(a.x, a.y, b.x, b.y);
+                a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162 *>(&vw.z));
+                b = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162 *>(&vw.w));
+                Vs[kr][2 * cc + 1] = make_float4(a.x, a.y, b.x, b.y);
             }
             __syncthreads();
-            if (active) {
-                for (int kr = 0; kr < cnt; kr++) {
-                    float s = 0.0f;
-                    const __nv_bfloat162 *kp = reinterpret_cast<const __nv_bfloat162 *>(&Ks[kr][0]);
+            for (int kr = 0; kr < cnt; kr++) {
+                float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
 #pragma unroll
-                    for (int j = 0; j < 32; j++) {
-                        const float2 f = __bfloat1622float2(kp[j]);
-                        s = fmaf(q[2 * j], f.x, s);
-                        s = fmaf(q[2 * j + 1], f.y, s);
-                    }
-                    if (s > mx) {
-                        const float corr = __expf(mx - s);
-                        den *= corr;
+                for (int j = 0; j < 16; j++) {
+                    const float4 kk = Ks[kr][j];
+                    s0 = fmaf(q[j].x, kk.x, s0);
+                    s1 = fmaf(q[j].y, kk.y, s1);
+                    s2 = fmaf(q[j].z, kk.z, s2);
+                    s3 = fmaf(q[j].w, kk.w, s3);
+                }
+                const float s = (s0 + s1) + (s2 + s3);
+                if (s > mx) {
+                    const float corr = __expf(mx - s);
+                    den *= corr;
 #pragma unroll
-                        for (int j = 0; j < 64; j++) acc[j] *= corr;
-                        mx = s;
-                    }
-                    const float pr = __expf(s - mx);
-                    den += pr;
-                    const __nv_bfloat162 *vp = reinterpret_cast<const __nv_bfloat162 *>(&Vs[kr][0]);
+                    for (int j = 0; j < 16; j++) { acc[j].x *= corr; acc[j].y *= corr; acc[j].z *= corr; acc[j].w *= corr; }
+                    mx = s;
+                }
+                const float pr = __expf(s - mx);
+                den += pr;
 #pragma unroll
-                    for (int j = 0; j < 32; j++) {
-                        const float2 f = __bfloat1622float2(vp[j]);
-                        acc[2 * j] = fmaf(pr, f.x, acc[2 * j]);
-                        acc[2 * j + 1] = fmaf(pr, f.y, acc[2 * j + 1]);
-                    }
+                for (int j = 0; j < 16; j++) {
+                    const float4 vv = Vs[kr][j];
+                    acc[j].x = fmaf(pr, vv.x, acc[j].x);
+                    acc[j].y = fmaf(pr, vv.y, acc[j].y);
+                    acc[j].z = fmaf(pr, vv.z, acc[j].z);
+                    acc[j].w = fmaf(pr, vv.w, acc[j].w);
                 }
             }
         }
@@ -577,8 +807,8 @@ __global__ void __launch_bounds__(128) k_attention(const bf16 *__restrict__ qkv,
             uint4 *dst = reinterpret_cast<uint4 *>(out + (row0 + qi) * 256 + hd * 64);
 #pragma unroll
             for (int j = 0; j < 8; j++)
-                dst[j] = make_uint4(pack_bf16(acc[8 * j] * inv, acc[8 * j + 1] * inv), pack_bf16(acc[8 * j + 2] * inv, acc[8 * j + 3] * inv),
-                                    pack_bf16(acc[8 * j + 4] * inv, acc[8 * j + 5] * inv), pack_bf16(acc[8 * j + 6] * inv, acc[8 * j + 7] * inv));
+                dst[j] = make_uint4(pack_bf16(acc[2 * j].x * inv, acc[2 * j].y * inv), pack_bf16(acc[2 * j].z * inv, acc[2 * j].w * inv),
+                                    pack_bf16(acc[2 * j + 1].x * inv, acc[2 * j + 1].y * inv), pack_bf16(acc[2 * j + 1].z * inv, acc[2 * j + 1].w * inv));
         }
     }
 }
@@ -642,6 +872,7 @@ __global__ void k_choose(const float *__restrict__ logits, const uint8_t *__rest
 
 // ---------------------------------------------------------------------------------------------------------------
 int g_num_sms = 0;
+long long *g_dbg = nullptr;
 bool g_attr_set = false;
 
 int setup() {
@@ -653,18 +884,21 @@ int setup() {
         if (e != cudaSuccess) return (int)e;
     }
     if (!g_attr_set) {
-        const int lin_max = 1024 + (8 + LIN_STAGES) * TILE + 256;
+        const int lin_max = 1024 + 11 * TILE + 128 * OUT_PITCH + 512;
         const int p_bytes = 1024 + P_STAGES * P_STAGE_BYTES + 256;
+        const int leaf_bytes = 1024 + (3 + LEAF_STAGES) * TILE + 2 * 128 * LEAF_PITCH + 256;
         cudaError_t e = cudaFuncSetAttribute(k_lin<MODE_LINEAR>, cudaFuncAttributeMaxDynamicSharedMemorySize, lin_max);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(k_lin<MODE_TREE_F>, cudaFuncAttributeMaxDynamicSharedMemorySize, lin_max);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(k_tree_p, cudaFuncAttributeMaxDynamicSharedMemorySize, p_bytes);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(k_tree_leaf, cudaFuncAttributeMaxDynamicSharedMemorySize, leaf_bytes);
         if (e != cudaSuccess) return (int)e;
         g_attr_set = true;
     }
     return 0;
 }
 
-size_t lin_smem(int nkb) { return 1024 + (size_t)(nkb + LIN_STAGES) * TILE + 256; }
+int lin_stages(int nkb) { return nkb <= 3 ? LIN_MAX_STAGES : 11 - nkb; }
+size_t lin_smem(int nkb) { return 1024 + (size_t)(nkb + lin_stages(nkb)) * TILE + 128 * OUT_PITCH + 512; }
 
 int launch_linear(const bf16 *a0, int lda0, int k0, const bf16 *a1, int lda1, int k1, const bf16 *w, const float *bias,
                   bf16 *out, int ldc, long long M, int N, int act, cudaStream_t st) {
@@ -676,12 +910,14 @@ int launch_linear(const bf16 *a0, int lda0, int k0, const bf16 *a1, int lda1, in
     p.w = w; p.ldw = k0 + k1; p.bias = bias;
     p.rows = (int)M; p.rows_dev = nullptr; p.rows_mul = 1; p.act = act;
     p.out = out; p.ldc = ldc;
+    p.stages = lin_stages(p.kb0 + p.kb1);
+    p.dbg = g_dbg;
     const int ny = N / 128;
     const int mtiles = (int)((M + 127) / 128);
     int nx = g_num_sms / ny;
     if (nx < 1) nx = 1;
     if (nx > mtiles) nx = mtiles;
-    k_lin<MODE_LINEAR><<<dim3(nx, ny), 288, lin_smem(p.kb0 + p.kb1), st>>>(p);
+    k_lin<MODE_LINEAR><<<dim3(nx, ny), LIN_THREADS, lin_smem(p.kb0 + p.kb1), st>>>(p);
     g_launches++;
     return (int)cudaGetLastError();
 }
@@ -738,6 +974,17 @@ int fl_policy_linear(const uint16_t *d_a, int64_t lda, const uint16_t *d_w, cons
                          (cudaStream_t)stream);
 }
 
+int fl_policy_linear_debug(const uint16_t *d_a, int64_t lda, const uint16_t *d_w, const float *d_bias, uint16_t *d_c, int64_t ldc,
+                           int64_t M, int64_t N, int64_t K, int act, long long *d_clocks, void *stream) {
+    int rc = setup();
+    if (rc) return rc;
+    g_dbg = d_clocks;
+    rc = launch_linear((const bf16 *)d_a, (int)lda, (int)K, nullptr, 0, 0, (const bf16 *)d_w, d_bias, (bf16 *)d_c, (int)ldc, M, (int)N, act,
+                       (cudaStream_t)stream);
+    g_dbg = nullptr;
+    return rc;
+}
+
 int fl_policy_forward(const FlPolicyWeights *w, void *d_workspace, size_t workspace_bytes, int64_t E, int64_t N,
                       const float *d_agent_attr, const float *d_forest, const int32_t *d_adjacency,
                       const int32_t *d_node_order, float *d_logits, float *d_value, void *stream) {
@@ -753,7 +1000,7 @@ int fl_policy_forward(const FlPolicyWeights *w, void *d_workspace, size_t worksp
     if (e == cudaSuccess) e = cudaMemsetAsync(ws.emb, 0, (size_t)M * 256 * 2, st);
     if (e != cudaSuccess) return (int)e;
     {
-        const long long total = M * 128 + M * NODES * 16;
+        const long long total = M * 16 + M * NODES;
         k_prep<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(d_agent_attr, d_forest, ws.attr, ws.x, M);
         k_tree_plan<<<(unsigned)((M + 127) / 128), 128, 0, st>>>(d_adjacency, d_node_order, ws.lists, ws.counts, M);
         g_launches += 2;
@@ -768,8 +1015,18 @@ int fl_policy_forward(const FlPolicyWeights *w, void *d_workspace, size_t worksp
             p.w = (const bf16 *)w->tree_ufwf; p.ldw = 144; p.bias = w->tree_b_f;
             p.rows = 0; p.rows_dev = ws.counts + lv; p.rows_mul = 3;
             p.entries = list; p.cstate = ws.c; p.fc = ws.fc;
-            k_lin<MODE_TREE_F><<<dim3(g_num_sms, 1), 288, lin_smem(3), st>>>(p);
+            p.stages = lin_stages(3);
+            k_lin<MODE_TREE_F><<<dim3(g_num_sms, 1), LIN_THREADS, lin_smem(3), st>>>(p);
             g_launches++;
+        }
+        if (lv == 0) {
+            LeafArgs lf = {};
+            lf.entries = list; lf.count_dev = ws.counts; lf.x = ws.x; lf.h = ws.h; lf.c = ws.c;
+            lf.emb = ws.emb + 128; lf.emb_ld = 256;
+            lf.wiou = (const bf16 *)w->tree_wiou; lf.b_iou = w->tree_b_iou;
+            k_tree_leaf<<<g_num_sms, LEAF_THREADS, 1024 + (3 + LEAF_STAGES) * TILE + 2 * 128 * LEAF_PITCH + 256, st>>>(lf);
+            g_launches++;
+            continue;
         }
         TreeArgs t = {};
         t.entries = list; t.count_dev = ws.counts + lv; t.level = lv;
@@ -777,7 +1034,7 @@ int fl_policy_forward(const FlPolicyWeights *w, void *d_workspace, size_t worksp
         t.emb = ws.emb + 128; t.emb_ld = 256;
         t.uiou = (const bf16 *)w->tree_uiou; t.wiou = (const bf16 *)w->tree_wiou; t.wc = (const bf16 *)w->tree_wc;
         t.b_iou = w->tree_b_iou; t.b_c = w->tree_b_c;
-        k_tree_p<<<g_num_sms, 288, 1024 + P_STAGES * P_STAGE_BYTES + 256, st>>>(t);
+        k_tree_p<<<g_num_sms, 416, 1024 + P_STAGES * P_STAGE_BYTES + 256, st>>>(t);
         g_launches++;
     }
     // ---- attribute MLP (net_tree.py:41-50) ----
@@ -790,7 +1047,7 @@ int fl_policy_forward(const FlPolicyWeights *w, void *d_workspace, size_t worksp
     bf16 *touts[3] = {ws.ta, ws.tb, ws.ta};
     for (int l = 0; l < FL_POLICY_LAYERS; l++) {
         if ((rc = launch_linear(tin, 256, 256, nullptr, 0, 0, (const bf16 *)w->tf_wqkv[l], w->tf_bqkv[l], ws.qkv, 768, M, 768, 0, st))) return rc;
-        k_attention<<<dim3((unsigned)E, FL_POLICY_HEADS), 128, 0, st>>>(ws.qkv, ws.atto, (int)N);
+        k_attention<<<dim3((unsigned)E, FL_POLICY_HEADS), 64, 0, st>>>(ws.qkv, ws.atto, (int)N);
         g_launches++;
         if ((rc = launch_linear(ws.atto, 256, 256, nullptr, 0, 0, (const bf16 *)w->tf_wo[l], w->tf_bo[l], ws.proj, 256, M, 256, 0, st))) return rc;
         if ((rc = launch_linear(tin, 256, 256, ws.proj, 256, 256, (const bf16 *)w->tf_wm[l], w->tf_bm[l], touts[l], 256, M, 256, 1, st))) return rc;

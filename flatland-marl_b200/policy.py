@@ -19,7 +19,7 @@ LIB_PATH = os.path.join(HERE, "csrc", "policy", "libflatland_policy_b200.so")
 LAYERS = pw.N_TRANSFORMER
 
 EXPORTS = ["fl_policy_abi_version", "fl_policy_workspace_bytes", "fl_policy_forward", "fl_policy_choose_actions",
-           "fl_policy_linear", "fl_policy_launch_count"]
+           "fl_policy_linear", "fl_policy_linear_debug", "fl_policy_launch_count"]
 
 
 class FlPolicyWeights(C.Structure):
@@ -53,6 +53,8 @@ def lib():
     L.fl_policy_choose_actions.argtypes = [P, P, P, C.c_int64, P]
     L.fl_policy_linear.restype = C.c_int
     L.fl_policy_linear.argtypes = [P, C.c_int64, P, P, P, C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_int, P]
+    L.fl_policy_linear_debug.restype = C.c_int
+    L.fl_policy_linear_debug.argtypes = [P, C.c_int64, P, P, P, C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_int, P, P]
     _lib = L
     return L
 

@@ -87,6 +87,13 @@ int fl_policy_choose_actions(const float *d_logits, const uint8_t *d_valid_actio
 int fl_policy_linear(const uint16_t *d_a, int64_t lda, const uint16_t *d_w, const float *d_bias, uint16_t *d_c,
                      int64_t ldc, int64_t M, int64_t N, int64_t K, int act, void *stream);
 
+/* Tuning only: fl_policy_linear that also writes SM-clock timestamps of CTA (0,0) into d_clocks[128]
+ * ([0] MMA warp start, [1] weights resident, [2] end, [3] kernel start; [8+4t..] MMA thread per tile t < 8: accumulator
+ * free, first stage full, last stage full; [48+4t..] epilogue warp 0: accumulator full, read, stored; [80+t] producer
+ * starts tile t). */
+int fl_policy_linear_debug(const uint16_t *d_a, int64_t lda, const uint16_t *d_w, const float *d_bias, uint16_t *d_c,
+                           int64_t ldc, int64_t M, int64_t N, int64_t K, int act, long long *d_clocks, void *stream);
+
 uint64_t fl_policy_launch_count(void);
 
 #ifdef __cplusplus

@@ -16,7 +16,7 @@ def pytest_configure(config):
 
 
 def golden_names():
-    return sorted(f[:-4] for f in os.listdir(GOLDEN_DIR) if f.endswith(".npz") and f != "motion_cases.npz")
+    return sorted(f[:-4] for f in os.listdir(GOLDEN_DIR) if f.endswith(".npz") and f not in ("motion_cases.npz", "policy_golden.npz"))
 
 
 @pytest.fixture(scope="session")

@@ -10,14 +10,9 @@ import pytest
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def declared_symbols():
-    syms = []
-    inc = os.path.join(ROOT, "include")
-    for f in sorted(os.listdir(inc)):
-        if f.endswith(".h"):
-            text = re.sub(r"/\*.*?\*/", "", open(os.path.join(inc, f)).read(), flags=re.S)
-            syms += re.findall(r"\b(fl_[a-z0-9_]+)\s*\(", text)
-    return sorted(set(syms))
+def declared_symbols(header="flatland_b200.h"):
+    text = re.sub(r"/\*.*?\*/", "", open(os.path.join(ROOT, "include", header)).read(), flags=re.S)
+    return sorted(set(re.findall(r"\b(fl_[a-z0-9_]+)\s*\(", text)))
 
 
 @pytest.fixture(scope="module")
@@ -38,6 +33,26 @@ def test_exports_every_declared_symbol(lib):
     for s in syms:
         assert hasattr(lib, s), "libflatland_b200.so does not export %s" % s
     assert sorted(fb._lib.EXPORTS) == syms, "binding list and header disagree"
+
+
+def test_every_header_has_a_library():
+    assert sorted(f for f in os.listdir(os.path.join(ROOT, "include")) if f.endswith(".h")) == \
+        ["flatland_b200.h", "flatland_policy_b200.h"]
+
+
+def test_policy_library_exports_every_declared_symbol(lib):
+    from flatland_marl_b200 import policy
+    L = policy.lib()
+    syms = declared_symbols("flatland_policy_b200.h")
+    assert len(syms) >= 6
+    for s in syms:
+        assert hasattr(L, s), "libflatland_policy_b200.so does not export %s" % s
+    assert sorted(policy.EXPORTS) == syms, "binding list and header disagree"
+    assert L.fl_policy_abi_version() == 1
+    n = L.fl_policy_workspace_bytes(51200)
+    assert n > 51200 * 30000 and n % 256 == 0
+    # argument errors come back as codes before any CUDA call
+    assert L.fl_policy_choose_actions(None, None, None, 0, None) == -1
 
 
 def test_struct_layout_and_version(lib):
