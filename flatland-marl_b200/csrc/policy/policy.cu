@@ -16,6 +16,7 @@
 //                 nodes accumulate side by side in all 512 TMEM columns; the epilogue applies the LSTM gates.
 //   k_attention   4-head attention over the agents of one environment (SIMT, fp32, online softmax).
 //   k_prep / k_tree_plan / k_head_final / k_choose: casts, level lists, final 128->5/1 layers, action choice.
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <math_constants.h>
 
@@ -63,14 +64,19 @@ __device__ __forceinline__ void entry_decode(uint32_t e, uint32_t &tree, uint32_
     child0 = e >> 27;
 }
 
-// Warp roles of k_lin: 16 epilogue warps (TMEM lane quarter = warp & 3, 32-column group = warp >> 2),
-// 4 producer warps, 1 MMA warp.
-constexpr int LIN_THREADS = 21 * 32;
+// Warp roles of k_lin: warps 0-15 epilogue (TMEM lane quarter = warp & 3, 32-column group = warp >> 2), warp 16 MMA
+// issue, warps 17.. producers.
+constexpr int LIN_THREADS = 21 * 32;      // 16 epilogue warps, MMA warp, 4 gather warps
+constexpr int LIN_THREADS_TMA = 18 * 32;  // 16 epilogue warps, MMA warp, TMA warp
 constexpr int LIN_MAX_STAGES = 8;
 constexpr int OUT_PITCH = 272;          // bytes between rows of the staged output tile (256 + 16: conflict-free 16-byte stores)
 
+// MODE_LINEAR: A (one or two dense sources) and W arrive as TMA tiles (tensor maps ta0 / ta1 / tw, one elected
+// producer thread); MODE_TREE_F: rows are gathered by 128 producer threads with cp.async (the LDGSTS path tops out
+// near 16 B/clk per SM, so it is kept for the gathers only).
 template <int MODE>
-__global__ void __launch_bounds__(LIN_THREADS, 1) k_lin(const LinArgs p) {
+__global__ void __launch_bounds__(MODE == MODE_LINEAR ? LIN_THREADS_TMA : LIN_THREADS, 1) k_lin(const LinArgs p, const __grid_constant__ CUtensorMap ta0,
+                                                        const __grid_constant__ CUtensorMap ta1, const __grid_constant__ CUtensorMap tw) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     const int nkb = p.kb0 + p.kb1 + p.k16;
@@ -81,7 +87,8 @@ __global__ void __launch_bounds__(LIN_THREADS, 1) k_lin(const LinArgs p) {
     uint8_t *sW = smem;
     uint8_t *sA = smem + (size_t)nkb * TILE;
     uint8_t *sC = sA + (size_t)S * TILE;                 // output tile staging: 128 rows, pitch OUT_PITCH
-    uint64_t *bars = (uint64_t *)(sC + 128 * OUT_PITCH);
+    unsigned long long *rowptr = (unsigned long long *)(sC + 128 * OUT_PITCH);   // MODE_TREE_F: destination of every row
+    uint64_t *bars = (uint64_t *)(rowptr + 128);
     uint64_t *full = bars, *empty = bars + LIN_MAX_STAGES, *wfull = bars + 2 * LIN_MAX_STAGES;
     uint64_t *tfull = wfull + 1, *tempty = tfull + 2;
     uint32_t *tmem_slot = (uint32_t *)(tempty + 2);
@@ -89,10 +96,11 @@ __global__ void __launch_bounds__(LIN_THREADS, 1) k_lin(const LinArgs p) {
     const int n0 = blockIdx.y * 128;
     if (p.dbg && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) p.dbg[3] = clock64();
 
-    if (warp == 20) {
+    if (warp == 16) {
         if (lane == 0) {
-            for (int s = 0; s < S; s++) { mbar_init(&full[s], 128); mbar_init(&empty[s], 1); }
-            mbar_init(wfull, 128);
+            const uint32_t nprod = MODE == MODE_LINEAR ? 1 : 128;
+            for (int s = 0; s < S; s++) { mbar_init(&full[s], nprod); mbar_init(&empty[s], 1); }
+            mbar_init(wfull, nprod);
             for (int b = 0; b < 2; b++) { mbar_init(&tfull[b], 1); mbar_init(&tempty[b], 512); }
             mbar_init_fence();
         }
@@ -104,9 +112,28 @@ __global__ void __launch_bounds__(LIN_THREADS, 1) k_lin(const LinArgs p) {
     fence_after_sync();
     const uint32_t tmem = *tmem_slot;
 
-    if (warp >= 16 && warp < 20) {
+    if (MODE == MODE_LINEAR && warp >= 17) {
+        // ---------------- producer: one thread issues TMA tile loads ----------------
+        if (threadIdx.x == 544) {
+            tma_prefetch_desc(&ta0);
+            tma_prefetch_desc(&tw);
+            mbar_expect_tx(wfull, (uint32_t)nkb * TILE);
+            for (int kb = 0; kb < nkb; kb++) tma_load_2d(smem_u32(sW + (size_t)kb * TILE), &tw, kb * 64, n0, wfull);
+            uint32_t it = 0;
+            for (int mt = blockIdx.x; mt < mtiles; mt += gridDim.x) {
+                for (int kb = 0; kb < nkb; kb++, it++) {
+                    const int s = it % S;
+                    mbar_wait(&empty[s], ((it / S) & 1) ^ 1);
+                    if (p.dbg && kb == 0 && blockIdx.x == 0 && blockIdx.y == 0 && it / nkb < 8) p.dbg[80 + it / nkb] = clock64();
+                    mbar_expect_tx(&full[s], TILE);
+                    if (kb < p.kb0) tma_load_2d(smem_u32(sA + (size_t)s * TILE), &ta0, kb * 64, mt * 128, &full[s]);
+                    else tma_load_2d(smem_u32(sA + (size_t)s * TILE), &ta1, (kb - p.kb0) * 64, mt * 128, &full[s]);
+                }
+            }
+        }
+    } else if (warp >= 17) {
         // ---------------- producers: 128 threads, thread = (16-byte chunk c, rows r0 + 16 i) ----------------
-        const int tp = threadIdx.x - 512;
+        const int tp = threadIdx.x - 544;
         const int c = tp & 7, r0 = tp >> 3;
         const uint32_t swz = (uint32_t)((c ^ (r0 & 7)) << 4) + (uint32_t)r0 * 128u;
         for (int kb = 0; kb < nkb; kb++) {
@@ -163,7 +190,7 @@ __global__ void __launch_bounds__(LIN_THREADS, 1) k_lin(const LinArgs p) {
             }
         }
         cp_async_wait_all();
-    } else if (warp == 20) {
+    } else if (warp == 16) {
         // ---------------- MMA issue: one thread ----------------
         if (lane == 0) {
             const bool dbg = p.dbg && blockIdx.x == 0 && blockIdx.y == 0;
@@ -246,28 +273,38 @@ __global__ void __launch_bounds__(LIN_THREADS, 1) k_lin(const LinArgs p) {
                 }
                 ow[j] = pack_bf16(f0, f1);
             }
-            // registers -> padded shared-memory tile -> one 256-byte bulk store per row (the direct form, 32 lanes
-            // writing 16 bytes to 32 different rows, ran at half a store transaction per clock and paced the kernel)
-            if (p.act & 4) { if (dbg) p.dbg[48 + tl * 4 + 2] = clock64(); if (ow[3] == 0x12345678u) p.out[0] = bf16(); continue; }
-            if (cg == 0) bulk_wait_read();                 // the previous tile's rows have left the staging buffer
-            named_bar_sync(1, 512);
+            // registers -> padded shared-memory tile -> row-contiguous 16-byte stores (16 lanes cover a 256-byte row).
+            // The direct form, 32 lanes writing 16 bytes to 32 different rows, costs 32 store transactions per
+            // instruction; one bulk copy per row serialises in the uniform datapath (2.5k cycles per tile).
+            if (dbg) p.dbg[96 + tl * 4] = clock64();
+            named_bar_sync(1, 512);                       // everybody has finished reading the previous tile
             const uint32_t srow = smem_u32(sC) + (uint32_t)(q * 32 + lane) * OUT_PITCH;
 #pragma unroll
             for (int j = 0; j < 4; j++) st_shared_v4(srow + cg * 64 + j * 16, ow[4 * j], ow[4 * j + 1], ow[4 * j + 2], ow[4 * j + 3]);
-            fence_proxy_async();
+            if (MODE == MODE_TREE_F && cg == 0) rowptr[q * 32 + lane] = valid ? (unsigned long long)(p.fc + orow) : 0ull;
+            if (dbg) p.dbg[96 + tl * 4 + 1] = clock64();
             named_bar_sync(2, 512);
-            if (cg == 0) {
-                if (valid) bulk_store((MODE == MODE_LINEAR ? p.out : p.fc) + orow, srow, 256);
-                bulk_commit();
+            if (dbg) p.dbg[96 + tl * 4 + 2] = clock64();
+            const int te = warp * 32 + lane;
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                const int ci = te + 512 * j, row = ci >> 4, cc = ci & 15;
+                const uint4 val = ld_shared_v4(smem_u32(sC) + (uint32_t)row * OUT_PITCH + cc * 16);
+                if (MODE == MODE_LINEAR) {
+                    const int gr = mt * 128 + row;
+                    if (gr < rows) *reinterpret_cast<uint4 *>(p.out + (size_t)gr * p.ldc + n0 + cc * 8) = val;
+                } else {
+                    const unsigned long long dst = rowptr[row];
+                    if (dst) *reinterpret_cast<uint4 *>(dst + cc * 16) = val;
+                }
             }
             if (dbg) p.dbg[48 + tl * 4 + 2] = clock64();
         }
-        if (cg == 0) bulk_wait_all();
     }
     fence_before_sync();
     __syncthreads();
     if (p.dbg && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) p.dbg[2] = clock64();
-    if (warp == 20) tmem_dealloc(tmem, 256);
+    if (warp == 16) tmem_dealloc(tmem, 256);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -871,6 +908,10 @@ __global__ void k_choose(const float *__restrict__ logits, const uint8_t *__rest
 }
 
 // ---------------------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                  const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn g_encode = nullptr;
 int g_num_sms = 0;
 long long *g_dbg = nullptr;
 bool g_attr_set = false;
@@ -883,8 +924,17 @@ int setup() {
         e = cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
         if (e != cudaSuccess) return (int)e;
     }
+    if (!g_encode) {
+        // the driver's tensor-map encoder, looked up at run time (no link-time dependency on libcuda)
+        cudaDriverEntryPointQueryResult qres;
+        void *fn = nullptr;
+        cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
+        if (e != cudaSuccess) return (int)e;
+        if (!fn || qres != cudaDriverEntryPointSuccess) return (int)cudaErrorNotSupported;
+        g_encode = (EncodeTiledFn)fn;
+    }
     if (!g_attr_set) {
-        const int lin_max = 1024 + 11 * TILE + 128 * OUT_PITCH + 512;
+        const int lin_max = 1024 + 11 * TILE + 128 * OUT_PITCH + 1024 + 512;
         const int p_bytes = 1024 + P_STAGES * P_STAGE_BYTES + 256;
         const int leaf_bytes = 1024 + (3 + LEAF_STAGES) * TILE + 2 * 128 * LEAF_PITCH + 256;
         cudaError_t e = cudaFuncSetAttribute(k_lin<MODE_LINEAR>, cudaFuncAttributeMaxDynamicSharedMemorySize, lin_max);
@@ -898,7 +948,19 @@ int setup() {
 }
 
 int lin_stages(int nkb) { return nkb <= 3 ? LIN_MAX_STAGES : 11 - nkb; }
-size_t lin_smem(int nkb) { return 1024 + (size_t)(nkb + lin_stages(nkb)) * TILE + 128 * OUT_PITCH + 512; }
+size_t lin_smem(int nkb) { return 1024 + (size_t)(nkb + lin_stages(nkb)) * TILE + 128 * OUT_PITCH + 1024 + 512; }
+
+// 2-D bf16 tensor map: `rows` x `cols` elements, row pitch `ld` elements, box = 64 columns (128 bytes, swizzled) x 128 rows;
+// out-of-range rows read as zero.
+int make_tmap(CUtensorMap *m, const bf16 *base, unsigned long long rows, unsigned long long cols, unsigned long long ld) {
+    cuuint64_t dims[2] = {cols, rows};
+    cuuint64_t strides[1] = {ld * 2};
+    cuuint32_t box[2] = {64, 128};
+    cuuint32_t es[2] = {1, 1};
+    CUresult r = g_encode(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (void *)base, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                          CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? 0 : 700 + (int)r;
+}
 
 int launch_linear(const bf16 *a0, int lda0, int k0, const bf16 *a1, int lda1, int k1, const bf16 *w, const float *bias,
                   bf16 *out, int ldc, long long M, int N, int act, cudaStream_t st) {
@@ -917,7 +979,13 @@ int launch_linear(const bf16 *a0, int lda0, int k0, const bf16 *a1, int lda1, in
     int nx = g_num_sms / ny;
     if (nx < 1) nx = 1;
     if (nx > mtiles) nx = mtiles;
-    k_lin<MODE_LINEAR><<<dim3(nx, ny), LIN_THREADS, lin_smem(p.kb0 + p.kb1), st>>>(p);
+    CUtensorMap ta0, ta1, tw;
+    int rc = make_tmap(&ta0, a0, (unsigned long long)M, (unsigned long long)k0, (unsigned long long)lda0);
+    if (!rc) rc = k1 ? make_tmap(&ta1, a1, (unsigned long long)M, (unsigned long long)k1, (unsigned long long)lda1) : 0;
+    if (!rc) rc = make_tmap(&tw, w, (unsigned long long)N, (unsigned long long)(k0 + k1), (unsigned long long)(k0 + k1));
+    if (rc) return rc;
+    if (!k1) ta1 = ta0;
+    k_lin<MODE_LINEAR><<<dim3(nx, ny), LIN_THREADS_TMA, lin_smem(p.kb0 + p.kb1), st>>>(p, ta0, ta1, tw);
     g_launches++;
     return (int)cudaGetLastError();
 }
@@ -1016,7 +1084,8 @@ int fl_policy_forward(const FlPolicyWeights *w, void *d_workspace, size_t worksp
             p.rows = 0; p.rows_dev = ws.counts + lv; p.rows_mul = 3;
             p.entries = list; p.cstate = ws.c; p.fc = ws.fc;
             p.stages = lin_stages(3);
-            k_lin<MODE_TREE_F><<<dim3(g_num_sms, 1), LIN_THREADS, lin_smem(3), st>>>(p);
+            static CUtensorMap dummy;
+            k_lin<MODE_TREE_F><<<dim3(g_num_sms, 1), LIN_THREADS, lin_smem(3), st>>>(p, dummy, dummy, dummy);
             g_launches++;
         }
         if (lv == 0) {

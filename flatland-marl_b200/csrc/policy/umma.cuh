@@ -57,6 +57,21 @@ __device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t
     asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
 
+// ---- TMA tile loads (2-D tensor map, 128-byte swizzle: the box lands in exactly the layout desc_sw128 describes) ----
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst_smem, const void *tmap, int c0, int c1, uint64_t *bar) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                 ::"r"(dst_smem), "l"(tmap), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const void *tmap) { asm volatile("prefetch.tensormap [%0];" ::"l"(tmap) : "memory"); }
+__device__ __forceinline__ uint4 ld_shared_v4(uint32_t addr) {
+    uint4 v;
+    asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
+    return v;
+}
+
 // ---- tcgen05 ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ void tmem_alloc(uint32_t *slot_in_smem, uint32_t ncols) {   // whole warp
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(slot_in_smem)), "r"(ncols) : "memory");
@@ -104,22 +119,21 @@ __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.
 // ---- math ---------------------------------------------------------------------------------------------------
 // Branch-free forms for the epilogues (one warp per scheduler has no other warps to hide a divergent libm call):
 // tanh.approx.f32 is one MUFU op (max relative error 2^-11, below the bf16 rounding of the stored result);
-// erf by Abramowitz-Stegun 7.1.26 (absolute error 1.5e-7) with ex2 / rcp approximations.
 __device__ __forceinline__ float tanh_fast(float x) {
     float y;
     asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
     return y;
 }
 __device__ __forceinline__ float sigmoidf(float x) { return fmaf(0.5f, tanh_fast(0.5f * x), 0.5f); }
+// GELU (erf form, nn.GELU default) as 0.5 x (1 + tanh(x P(x^2))): P is a quadratic fitted to the erf form (max absolute
+// deviation 2.5e-5 over all x; the textbook tanh form is off by 4.7e-4), x^2 clamped where tanh has saturated.
+// 8 instructions, one MUFU — the erf-by-exp form (17 instructions, two MUFU) made the epilogue the pace of k_lin.
 __device__ __forceinline__ float gelu_erf(float x) {
-    const float ax = fabsf(x) * 0.70710678118654752440f;
-    const float t = __fdividef(1.0f, fmaf(0.3275911f, ax, 1.0f));
-    float poly = fmaf(t, 1.061405429f, -1.453152027f);
-    poly = fmaf(t, poly, 1.421413741f);
-    poly = fmaf(t, poly, -0.284496736f);
-    poly = fmaf(t, poly, 0.254829592f);
-    const float erf_abs = fmaf(-poly * t, __expf(-ax * ax), 1.0f);
-    return 0.5f * x * (1.0f + copysignf(erf_abs, x));
+    const float u = fminf(x * x, 49.0f);
+    float pl = fmaf(u, -3.51516783e-4f, 3.70056460e-2f);
+    pl = fmaf(u, pl, 7.97507884e-1f);
+    const float h = 0.5f * x;
+    return fmaf(h, tanh_fast(x * pl), h);
 }
 __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
     __nv_bfloat162 h = __floats2bfloat162_rn(a, b);

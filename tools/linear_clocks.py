@@ -6,7 +6,7 @@ sys.path.insert(0, ROOT)
 from flatland_marl_b200.policy import BatchedActor
 actor = BatchedActor(None, seed=0)
 dev = actor.device
-for (M, K, N, act) in [(51200, 256, 256, 1), (51200, 256, 256, 0), (51200, 256, 256, 4), (51200, 256, 256, 5), (51200, 64, 128, 4)]:
+for (M, K, N, act) in [(51200, 256, 256, 1), (51200, 256, 768, 0), (51200, 512, 256, 1), (51200, 64, 128, 0)]:
     a = (torch.randn(M, K, device=dev) * 0.5).to(torch.bfloat16)
     w = (torch.randn(N, K, device=dev) / K ** 0.5).to(torch.bfloat16)
     b = torch.randn(N, device=dev)
@@ -28,3 +28,4 @@ for (M, K, N, act) in [(51200, 256, 256, 1), (51200, 256, 256, 0), (51200, 256, 
             break
         print("  tile %d: producer start %6d | mma: acc free %6d first full %6d last full %6d | epi: acc full %6d read %6d stored %6d" %
               (t, c[80 + t] - t0, c[8 + 4 * t] - t0, c[9 + 4 * t] - t0, c[10 + 4 * t] - t0, c[48 + 4 * t] - t0, c[49 + 4 * t] - t0, c[50 + 4 * t] - t0))
+        print("          epilogue detail: math done %6d, staged %6d, bar2 %6d, (unused) %6d" % tuple(c[96 + 4 * t + i] - t0 for i in range(4)))
