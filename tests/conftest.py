@@ -16,7 +16,9 @@ def pytest_configure(config):
 
 
 def golden_names():
-    return sorted(f[:-4] for f in os.listdir(GOLDEN_DIR) if f.endswith(".npz") and f not in ("motion_cases.npz", "policy_golden.npz"))
+    """Episode fixtures recorded from the reference simulator (t*.npz, simple_rail_*.npz); other fixtures in the
+    directory (MotionCheck cases, policy outputs, saved levels) have their own tests."""
+    return sorted(f[:-4] for f in os.listdir(GOLDEN_DIR) if f.endswith(".npz") and (f.startswith("t") or f.startswith("simple_rail")))
 
 
 @pytest.fixture(scope="session")
