@@ -16,6 +16,7 @@
 //                 nodes accumulate side by side in all 512 TMEM columns; the epilogue applies the LSTM gates.
 //   k_attention   4-head attention over the agents of one environment (SIMT, fp32, online softmax).
 //   k_prep / k_tree_plan / k_head_final / k_choose: casts, level lists, final 128->5/1 layers, action choice.
+#include <cstdlib>
 #include <cuda.h>
 #include <cuda_runtime.h>
 #include <math_constants.h>
@@ -979,6 +980,7 @@ int launch_linear(const bf16 *a0, int lda0, int k0, const bf16 *a1, int lda1, in
     int nx = g_num_sms / ny;
     if (nx < 1) nx = 1;
     if (nx > mtiles) nx = mtiles;
+    if (g_dbg && getenv("FL_POLICY_NX")) nx = atoi(getenv("FL_POLICY_NX"));   // tuning only (fl_policy_linear_debug)
     CUtensorMap ta0, ta1, tw;
     int rc = make_tmap(&ta0, a0, (unsigned long long)M, (unsigned long long)k0, (unsigned long long)lda0);
     if (!rc) rc = k1 ? make_tmap(&ta1, a1, (unsigned long long)M, (unsigned long long)k1, (unsigned long long)lda1) : 0;
