@@ -336,7 +336,8 @@ __global__ void __launch_bounds__(LEAF_THREADS, 1) k_tree_leaf(const LeafArgs p)
     uint8_t *sW = smem;                       // 384 rows x 128 B (first 32 B of every row used)
     uint8_t *sA = smem + 3 * TILE;
     uint8_t *sC = sA + LEAF_STAGES * TILE;    // staged h | c of one half tile: 2 x 128 rows, pitch LEAF_PITCH
-    uint64_t *bars = (uint64_t *)(sC + 2 * 128 * LEAF_PITCH);
+    uint32_t *rowoff = (uint32_t *)(sC + 2 * 128 * LEAF_PITCH);   // element offset of every row's node in h / c
+    uint64_t *bars = (uint64_t *)(rowoff + 128);
     uint64_t *full = bars, *empty = bars + LEAF_STAGES, *wfull = bars + 2 * LEAF_STAGES;
     uint64_t *tfull = wfull + 1, *tempty = tfull + 2;
     uint32_t *tmem_slot = (uint32_t *)(tempty + 2);
@@ -459,7 +460,7 @@ __global__ void __launch_bounds__(LEAF_THREADS, 1) k_tree_leaf(const LeafArgs p)
                     hw[2 * j] = pack_bf16(hh[0], hh[1]);
                     hw[2 * j + 1] = pack_bf16(hh[2], hh[3]);
                 }
-                if (sub == 0) bulk_wait_read();
+                // staged through shared memory so that 8 lanes write one 128-byte row segment (see k_lin)
                 named_bar_sync(1, 256);
                 const uint32_t srow = smem_u32(sC) + (uint32_t)(q * 32 + lane) * LEAF_PITCH;
 #pragma unroll
@@ -467,14 +468,17 @@ __global__ void __launch_bounds__(LEAF_THREADS, 1) k_tree_leaf(const LeafArgs p)
                     st_shared_v4(srow + sub * 64 + j * 16, hw[4 * j], hw[4 * j + 1], hw[4 * j + 2], hw[4 * j + 3]);
                     st_shared_v4(srow + 128 * LEAF_PITCH + sub * 64 + j * 16, cw[4 * j], cw[4 * j + 1], cw[4 * j + 2], cw[4 * j + 3]);
                 }
-                fence_proxy_async();
+                if (sub == 0 && half == 0) rowoff[q * 32 + lane] = valid ? (uint32_t)orow : 0xFFFFFFFFu;
                 named_bar_sync(2, 256);
-                if (sub == 0) {
-                    if (valid) {
-                        bulk_store(p.h + orow + half * 64, srow, 128);
-                        bulk_store(p.c + orow + half * 64, srow + 128 * LEAF_PITCH, 128);
+                {
+                    const int te = warp * 32 + lane;
+#pragma unroll
+                    for (int j = 0; j < 8; j++) {
+                        const int ci = te + 256 * j, which = ci >> 10, row = (ci >> 3) & 127, cc = ci & 7;
+                        const uint4 val = ld_shared_v4(smem_u32(sC) + (uint32_t)(which * 128 + row) * LEAF_PITCH + cc * 16);
+                        const uint32_t off = rowoff[row];
+                        if (off != 0xFFFFFFFFu) *reinterpret_cast<uint4 *>((which ? p.c : p.h) + off + half * 64 + cc * 8) = val;
                     }
-                    bulk_commit();
                 }
                 if (valid) {
                     if (v == 0) {
@@ -485,7 +489,6 @@ __global__ void __launch_bounds__(LEAF_THREADS, 1) k_tree_leaf(const LeafArgs p)
                 }
             }
         }
-        if (sub == 0) bulk_wait_all();
     }
     fence_before_sync();
     __syncthreads();
@@ -937,7 +940,7 @@ int setup() {
     if (!g_attr_set) {
         const int lin_max = 1024 + 11 * TILE + 128 * OUT_PITCH + 1024 + 512;
         const int p_bytes = 1024 + P_STAGES * P_STAGE_BYTES + 256;
-        const int leaf_bytes = 1024 + (3 + LEAF_STAGES) * TILE + 2 * 128 * LEAF_PITCH + 256;
+        const int leaf_bytes = 1024 + (3 + LEAF_STAGES) * TILE + 2 * 128 * LEAF_PITCH + 1024;
         cudaError_t e = cudaFuncSetAttribute(k_lin<MODE_LINEAR>, cudaFuncAttributeMaxDynamicSharedMemorySize, lin_max);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(k_lin<MODE_TREE_F>, cudaFuncAttributeMaxDynamicSharedMemorySize, lin_max);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(k_tree_p, cudaFuncAttributeMaxDynamicSharedMemorySize, p_bytes);
@@ -1095,7 +1098,7 @@ int fl_policy_forward(const FlPolicyWeights *w, void *d_workspace, size_t worksp
             lf.entries = list; lf.count_dev = ws.counts; lf.x = ws.x; lf.h = ws.h; lf.c = ws.c;
             lf.emb = ws.emb + 128; lf.emb_ld = 256;
             lf.wiou = (const bf16 *)w->tree_wiou; lf.b_iou = w->tree_b_iou;
-            k_tree_leaf<<<g_num_sms, LEAF_THREADS, 1024 + (3 + LEAF_STAGES) * TILE + 2 * 128 * LEAF_PITCH + 256, st>>>(lf);
+            k_tree_leaf<<<g_num_sms, LEAF_THREADS, 1024 + (3 + LEAF_STAGES) * TILE + 2 * 128 * LEAF_PITCH + 1024, st>>>(lf);
             g_launches++;
             continue;
         }

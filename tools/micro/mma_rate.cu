@@ -6,15 +6,16 @@
 using namespace umma;
 
 template <int N>
-__global__ void __launch_bounds__(128, 1) k_rate(long long *out, int iters, int distinct) {
+__global__ void __launch_bounds__(128, 1) k_rate(long long *out, int iters, int distinct, int commit_every) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     __shared__ uint64_t bar;
+    __shared__ uint64_t bars2[8];
     __shared__ uint32_t slot;
     const int warp = threadIdx.x >> 5;
     for (int i = threadIdx.x; i < (16384 * 6) / 4; i += blockDim.x) ((uint32_t *)smem)[i] = 0x3c003c00u;
     if (warp == 0) {
-        if (threadIdx.x == 0) { mbar_init(&bar, 1); mbar_init_fence(); }
+        if (threadIdx.x == 0) { mbar_init(&bar, 1); for (int i = 0; i < 8; i++) mbar_init(&bars2[i], 1); mbar_init_fence(); }
         __syncwarp();
         tmem_alloc(&slot, 512);
     }
@@ -31,6 +32,7 @@ __global__ void __launch_bounds__(128, 1) k_rate(long long *out, int iters, int 
             const uint32_t st = distinct ? (uint32_t)(i & 1) * 16384u : 0u;
             const uint64_t ad = desc_sw128(a0 + st), bd = desc_sw128(b0 + st * 2);
             for (int k = 0; k < 4; k++) mma_bf16(tmem + (i & 1) * 256, ad + 2 * k, bd + 2 * k, idesc, 1u);
+            if (commit_every && (i % commit_every) == commit_every - 1) mma_commit(&bars2[i & 7]);
         }
         mma_commit(&bar);
         long long t1 = clock64();
@@ -46,12 +48,13 @@ __global__ void __launch_bounds__(128, 1) k_rate(long long *out, int iters, int 
 template <int N> void run(long long *d, int ctas) {
     cudaFuncSetAttribute(k_rate<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, 16384 * 6 + 2048);
     for (int distinct = 0; distinct < 2; distinct++) {
+        const int commit_every = distinct;     // second run: a tcgen05.commit after every 4 MMAs (one k-block), nobody waits on it
         long long h[2];
         const int iters = 2000;
-        k_rate<N><<<ctas, 128, 16384 * 6 + 2048>>>(d, iters, distinct);
+        k_rate<N><<<ctas, 128, 16384 * 6 + 2048>>>(d, iters, distinct, commit_every);
         cudaError_t e = cudaDeviceSynchronize();
         cudaMemcpy(h, d, sizeof(h), cudaMemcpyDeviceToHost);
-        printf("N=%3d ctas=%3d distinct=%d: %s  issue %.1f cyc/MMA, complete %.1f cyc/MMA (floor %d)\n", N, ctas, distinct, cudaGetErrorString(e),
+        printf("N=%3d ctas=%3d distinct stages + commit per k-block=%d: %s  issue %.1f cyc/MMA, complete %.1f cyc/MMA (floor %d)\n", N, ctas, distinct, cudaGetErrorString(e),
                (double)h[0] / (4.0 * iters), (double)h[1] / (4.0 * iters), 128 * N / 256);
     }
 }
