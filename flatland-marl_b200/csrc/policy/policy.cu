@@ -854,6 +854,191 @@ __global__ void __launch_bounds__(64) k_attention(const bf16 *__restrict__ qkv, 
     }
 }
 
+// Attention on the tensor cores.  One CTA = one head of one 128-row query tile: R = G*N query rows (G = 128 / N whole
+// environments when N <= 128, else 128 agents of one environment) against the key tiles of the same environments.
+//   S = Q K^T   tcgen05.mma M=128 N=128 K=64 : Q tile and K tile are 64-column TMA boxes of the qkv buffer
+//   softmax     thread = query row (TMEM lane): scale, mask keys of other environments, max / exp / sum in registers;
+//               with more than one key tile a first pass over S finds the row maximum, a second pass exponentiates
+//   O += P V    P (bf16) written by its row's thread into the swizzled K-major A layout; V is used where the TMA box put
+//               it ([key][64 dims] = MN-major B operand), M=128 N=64 K=128
+// qkv [M][768] = q | k | v, out [M][256].
+struct AttnArgs {
+    bf16 *out;
+    int N;             // agents per environment
+    int E;
+    int rows_per_tile; // R
+    int tiles_per_env; // query tiles per environment (N > 128), else 0
+};
+constexpr int ATTN_SMEM = 1024 + 5 * TILE + 256;   // Q, K, V, P (2 k-blocks)
+
+__global__ void __launch_bounds__(128, 2) k_attn_mma(const AttnArgs p, const __grid_constant__ CUtensorMap tq) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    uint8_t *sQ = smem, *sK = smem + TILE, *sV = smem + 2 * TILE, *sP = smem + 3 * TILE;
+    uint64_t *bar_tma = (uint64_t *)(smem + 5 * TILE), *bar_mma = bar_tma + 1;
+    uint32_t *tmem_slot = (uint32_t *)(bar_mma + 1);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, hd = blockIdx.y;
+    const long long M = (long long)p.E * p.N;
+    // rows of this tile and the key range of their environments
+    long long qb, key0;
+    int nq, nkeys;
+    if (p.tiles_per_env) {
+        const int e = blockIdx.x / p.tiles_per_env, qt = blockIdx.x % p.tiles_per_env;
+        qb = (long long)e * p.N + qt * 128;
+        nq = min(128, p.N - qt * 128);
+        key0 = (long long)e * p.N;
+        nkeys = p.N;
+    } else {
+        qb = (long long)blockIdx.x * p.rows_per_tile;
+        nq = (int)min((long long)p.rows_per_tile, M - qb);
+        key0 = qb;
+        nkeys = nq;
+    }
+    const int ktiles = (nkeys + 127) >> 7;
+    if (warp == 0) {
+        if (lane == 0) { mbar_init(bar_tma, 1); mbar_init(bar_mma, 1); mbar_init_fence(); }
+        __syncwarp();
+        tmem_alloc(tmem_slot, 256);
+    }
+    fence_before_sync();
+    __syncthreads();
+    fence_after_sync();
+    const uint32_t tmem = *tmem_slot;
+    const uint32_t tS = tmem, tO = tmem + 128;
+    const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
+    const int r = threadIdx.x;                       // query row of this thread
+    const long long m = qb + r;
+    // keys this row may attend to: those of its own environment
+    const long long env_lo = (m / p.N) * p.N, env_hi = env_lo + p.N;
+    uint32_t ph_tma = 0, ph_mma = 0;
+    if (threadIdx.x == 0) {
+        tma_prefetch_desc(&tq);
+        mbar_expect_tx(bar_tma, TILE);
+        tma_load_2d(smem_u32(sQ), &tq, hd * 64, (int)qb, bar_tma);
+    }
+    mbar_wait(bar_tma, ph_tma);
+    ph_tma ^= 1;
+    float mx = -CUDART_INF_F, den = 0.0f;
+    const uint32_t id_s = idesc_bf16(128, 128), id_o = idesc_bf16_bmn(128, 64);
+    for (int pass = (ktiles > 1 ? 0 : 1); pass < 2; pass++) {      // pass 0: row maxima only (several key tiles)
+        for (int kt = 0; kt < ktiles; kt++) {
+            const long long kb = key0 + (long long)kt * 128;
+            const int nk = min(128, nkeys - kt * 128);
+            if (threadIdx.x == 0) {
+                mbar_expect_tx(bar_tma, pass ? 2 * TILE : TILE);
+                tma_load_2d(smem_u32(sK), &tq, 256 + hd * 64, (int)kb, bar_tma);
+                if (pass) tma_load_2d(smem_u32(sV), &tq, 512 + hd * 64, (int)kb, bar_tma);
+            }
+            mbar_wait(bar_tma, ph_tma);
+            ph_tma ^= 1;
+            if (threadIdx.x == 0) {
+                fence_after_sync();
+                const uint64_t ad = desc_sw128(smem_u32(sQ)), bd = desc_sw128(smem_u32(sK));
+                for (int k = 0; k < 4; k++) mma_bf16(tS, ad + 2 * k, bd + 2 * k, id_s, (uint32_t)(k != 0));
+                mma_commit(bar_mma);
+            }
+            mbar_wait(bar_mma, ph_mma);
+            ph_mma ^= 1;
+            fence_after_sync();
+            const int jlo = (int)max(0LL, env_lo - kb), jhi = (int)min((long long)nk, env_hi - kb);
+            if (!pass) {
+#pragma unroll 1
+                for (int c0 = 0; c0 < 128; c0 += 16) {
+                    uint32_t v[16];
+                    tmem_ld16(tS + lane_base + c0, v);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int j = 0; j < 16; j++)
+                        if (c0 + j >= jlo && c0 + j < jhi) mx = fmaxf(mx, __uint_as_float(v[j]) * 0.125f);
+                }
+                fence_before_sync();
+                __syncthreads();          // everybody has read S before the next tile's MMA overwrites it
+                continue;
+            }
+            if (ktiles == 1) {
+#pragma unroll 1
+                for (int c0 = 0; c0 < 128; c0 += 16) {
+                    uint32_t v[16];
+                    tmem_ld16(tS + lane_base + c0, v);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int j = 0; j < 16; j++)
+                        if (c0 + j >= jlo && c0 + j < jhi) mx = fmaxf(mx, __uint_as_float(v[j]) * 0.125f);
+                }
+            }
+            // P = exp(S/8 - max) as bf16 into the A-operand layout: row r, 16-byte chunk c at (c & 7) ^ (r & 7) of k-block c >> 3
+            const uint32_t prow = smem_u32(sP) + (uint32_t)r * 128u;
+#pragma unroll 1
+            for (int c0 = 0; c0 < 128; c0 += 16) {
+                uint32_t v[16], w[8];
+                tmem_ld16(tS + lane_base + c0, v);
+                tmem_ld_wait();
+#pragma unroll
+                for (int j = 0; j < 16; j += 2) {
+                    float p0 = 0.0f, p1 = 0.0f;
+                    if (c0 + j >= jlo && c0 + j < jhi) p0 = __expf(__uint_as_float(v[j]) * 0.125f - mx);
+                    if (c0 + j + 1 >= jlo && c0 + j + 1 < jhi) p1 = __expf(__uint_as_float(v[j + 1]) * 0.125f - mx);
+                    // the denominator sums what the MMA will see: the bf16-rounded probabilities
+                    const __nv_bfloat162 pb = __floats2bfloat162_rn(p0, p1);
+                    const float2 pf = __bfloat1622float2(pb);
+                    den += pf.x + pf.y;
+                    w[j >> 1] = *reinterpret_cast<const uint32_t *>(&pb);
+                }
+                const int ch = c0 >> 3;          // two 16-byte chunks per 16 columns
+                st_shared_v4(prow + (uint32_t)(ch >> 3) * TILE + (uint32_t)(((ch & 7) ^ (r & 7)) << 4), w[0], w[1], w[2], w[3]);
+                st_shared_v4(prow + (uint32_t)((ch + 1) >> 3) * TILE + (uint32_t)((((ch + 1) & 7) ^ (r & 7)) << 4), w[4], w[5], w[6], w[7]);
+            }
+            fence_proxy_async();
+            fence_before_sync();
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                fence_after_sync();
+                const uint32_t pa = smem_u32(sP), vb = smem_u32(sV);
+                for (int k = 0; k < 8; k++) {
+                    // A: k-block k >> 2 of P, 16 keys at byte 32 (k & 3) of the row; B: key rows 16 k .. of the V tile
+                    const uint64_t ad = desc_sw128(pa + (uint32_t)(k >> 2) * TILE) + 2 * (k & 3);
+                    const uint64_t bd = desc_sw128(vb + (uint32_t)k * 2048u);
+                    mma_bf16(tO, ad, bd, id_o, (uint32_t)(kt != 0 || k != 0));
+                }
+                mma_commit(bar_mma);
+            }
+            mbar_wait(bar_mma, ph_mma);       // P, K and V may be overwritten after this
+            ph_mma ^= 1;
+            fence_after_sync();
+        }
+    }
+    // O / den -> bf16 -> staged in the (now free) P region -> row-contiguous stores
+    {
+        const float inv = 1.0f / den;
+        const uint32_t orow = smem_u32(sP) + (uint32_t)r * 144u;
+#pragma unroll 1
+        for (int c0 = 0; c0 < 64; c0 += 16) {
+            uint32_t v[16];
+            tmem_ld16(tO + lane_base + c0, v);
+            tmem_ld_wait();
+            st_shared_v4(orow + c0 * 2, pack_bf16(__uint_as_float(v[0]) * inv, __uint_as_float(v[1]) * inv),
+                         pack_bf16(__uint_as_float(v[2]) * inv, __uint_as_float(v[3]) * inv),
+                         pack_bf16(__uint_as_float(v[4]) * inv, __uint_as_float(v[5]) * inv),
+                         pack_bf16(__uint_as_float(v[6]) * inv, __uint_as_float(v[7]) * inv));
+            st_shared_v4(orow + c0 * 2 + 16, pack_bf16(__uint_as_float(v[8]) * inv, __uint_as_float(v[9]) * inv),
+                         pack_bf16(__uint_as_float(v[10]) * inv, __uint_as_float(v[11]) * inv),
+                         pack_bf16(__uint_as_float(v[12]) * inv, __uint_as_float(v[13]) * inv),
+                         pack_bf16(__uint_as_float(v[14]) * inv, __uint_as_float(v[15]) * inv));
+        }
+    }
+    fence_before_sync();
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+        const int ci = threadIdx.x + 128 * j, row = ci >> 3, cc = ci & 7;
+        if (row < nq) {
+            const uint4 val = ld_shared_v4(smem_u32(sP) + (uint32_t)row * 144u + cc * 16);
+            *reinterpret_cast<uint4 *>(p.out + (qb + row) * 256 + hd * 64 + cc * 8) = val;
+        }
+    }
+    if (warp == 0) tmem_dealloc(tmem, 256);
+}
+
 // Last layers: logits = actor_net.4(y2[:, :128]), value = mean over agents of critic_net.4(y2[:, 128:]).
 __global__ void __launch_bounds__(128) k_head_final(const bf16 *__restrict__ y2, const float *__restrict__ w3, const float *__restrict__ b3,
                                                     float *__restrict__ logits, float *__restrict__ value, int N) {
@@ -944,6 +1129,7 @@ int setup() {
         cudaError_t e = cudaFuncSetAttribute(k_lin<MODE_LINEAR>, cudaFuncAttributeMaxDynamicSharedMemorySize, lin_max);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(k_lin<MODE_TREE_F>, cudaFuncAttributeMaxDynamicSharedMemorySize, lin_max);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(k_tree_p, cudaFuncAttributeMaxDynamicSharedMemorySize, p_bytes);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(k_attn_mma, cudaFuncAttributeMaxDynamicSharedMemorySize, ATTN_SMEM);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(k_tree_leaf, cudaFuncAttributeMaxDynamicSharedMemorySize, leaf_bytes);
         if (e != cudaSuccess) return (int)e;
         g_attr_set = true;
@@ -1121,8 +1307,23 @@ int fl_policy_forward(const FlPolicyWeights *w, void *d_workspace, size_t worksp
     bf16 *touts[3] = {ws.ta, ws.tb, ws.ta};
     for (int l = 0; l < FL_POLICY_LAYERS; l++) {
         if ((rc = launch_linear(tin, 256, 256, nullptr, 0, 0, (const bf16 *)w->tf_wqkv[l], w->tf_bqkv[l], ws.qkv, 768, M, 768, 0, st))) return rc;
-        k_attention<<<dim3((unsigned)E, FL_POLICY_HEADS), 64, 0, st>>>(ws.qkv, ws.atto, (int)N);
-        g_launches++;
+        {
+            AttnArgs at = {};
+            at.out = ws.atto; at.N = (int)N; at.E = (int)E;
+            unsigned tiles;
+            if (N <= 128) {
+                const int G = 128 / (int)N;
+                at.rows_per_tile = G * (int)N; at.tiles_per_env = 0;
+                tiles = (unsigned)((E + G - 1) / G);
+            } else {
+                at.rows_per_tile = 128; at.tiles_per_env = (int)((N + 127) / 128);
+                tiles = (unsigned)(E * at.tiles_per_env);
+            }
+            CUtensorMap tq;
+            if ((rc = make_tmap(&tq, ws.qkv, (unsigned long long)M, 768, 768))) return rc;
+            k_attn_mma<<<dim3(tiles, FL_POLICY_HEADS), 128, ATTN_SMEM, st>>>(at, tq);
+            g_launches++;
+        }
         if ((rc = launch_linear(ws.atto, 256, 256, nullptr, 0, 0, (const bf16 *)w->tf_wo[l], w->tf_bo[l], ws.proj, 256, M, 256, 0, st))) return rc;
         if ((rc = launch_linear(tin, 256, 256, ws.proj, 256, 256, (const bf16 *)w->tf_wm[l], w->tf_bm[l], touts[l], 256, M, 256, 1, st))) return rc;
         tin = touts[l];

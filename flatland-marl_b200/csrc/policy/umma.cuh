@@ -98,6 +98,9 @@ __device__ __forceinline__ uint64_t desc_sw128(uint32_t smem_addr) {
 __host__ __device__ constexpr uint32_t idesc_bf16(int M, int N) {
     return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
+// Same, B operand MN-major (its N index is the contiguous one): a [K rows][64 N-elements] tile with the 128-byte swizzle,
+// i.e. exactly what a TMA box of 64 columns x K rows leaves in shared memory.
+__host__ __device__ constexpr uint32_t idesc_bf16_bmn(int M, int N) { return idesc_bf16(M, N) | (1u << 16); }
 __device__ __forceinline__ void mma_bf16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
     asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
                  "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
