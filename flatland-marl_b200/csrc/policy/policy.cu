@@ -14,7 +14,9 @@
 //                 tree level, rows = child nodes, epilogue sigmoid(.) * c_child.
 //   k_tree_p      one tree level: i/o/u pre-activations (N = 384) and the W_c reduction (N = 128) of 128 parent
 //                 nodes accumulate side by side in all 512 TMEM columns; the epilogue applies the LSTM gates.
-//   k_attention   4-head attention over the agents of one environment (SIMT, fp32, online softmax).
+//   k_attn_mma    4-head attention over the agents of one environment: S = QK^T and O = PV as tcgen05 MMAs, softmax by
+//                 the row's thread straight from TMEM.
+//   k_tree_leaf   leaves of the Tree-LSTM (K = 12: one MMA k-step), two 192-column accumulators, 16 epilogue warps.
 //   k_prep / k_tree_plan / k_head_final / k_choose: casts, level lists, final 128->5/1 layers, action choice.
 #include <cstdlib>
 #include <cuda.h>
@@ -241,8 +243,10 @@ __global__ void __launch_bounds__(MODE == MODE_LINEAR ? LIN_THREADS_TMA : LIN_TH
                 }
             }
             float bias[32];
+            if (MODE == MODE_LINEAR) {
 #pragma unroll
-            for (int j = 0; j < 8; j++) *reinterpret_cast<float4 *>(&bias[4 * j]) = __ldg(reinterpret_cast<const float4 *>(p.bias + n0 + cg * 32) + j);
+                for (int j = 0; j < 8; j++) *reinterpret_cast<float4 *>(&bias[4 * j]) = __ldg(reinterpret_cast<const float4 *>(p.bias + n0 + cg * 32) + j);
+            }
             uint32_t cw[16];
             if (MODE == MODE_TREE_F && valid) {
                 const uint4 *cin = reinterpret_cast<const uint4 *>(p.cstate + orow + cg * 32);
@@ -264,13 +268,16 @@ __global__ void __launch_bounds__(MODE == MODE_LINEAR ? LIN_THREADS_TMA : LIN_TH
             uint32_t ow[16];
 #pragma unroll
             for (int j = 0; j < 16; j++) {
-                float f0 = __uint_as_float(v[2 * j]) + bias[2 * j], f1 = __uint_as_float(v[2 * j + 1]) + bias[2 * j + 1];
+                float f0 = 0.0f, f1 = 0.0f;
                 if (MODE == MODE_LINEAR) {
-                    if (p.act & 1) { f0 = gelu_erf(f0); f1 = gelu_erf(f1); }
+                    f0 = __uint_as_float(v[2 * j]) + bias[2 * j];
+                    f1 = __uint_as_float(v[2 * j + 1]) + bias[2 * j + 1];
+                    if (p.act & 1) { const float2 g = gelu2_erf(f0, f1); f0 = g.x; f1 = g.y; }
                 } else {
+                    // forget gate: b_f rides in the MMA and the weights are pre-scaled by 1/2, so f = 0.5 tanh(acc) + 0.5
                     const float2 cc = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162 *>(&cw[j]));
-                    f0 = sigmoidf(f0) * cc.x;
-                    f1 = sigmoidf(f1) * cc.y;
+                    f0 = fmaf(0.5f * cc.x, tanh_fast(__uint_as_float(v[2 * j])), 0.5f * cc.x);
+                    f1 = fmaf(0.5f * cc.y, tanh_fast(__uint_as_float(v[2 * j + 1])), 0.5f * cc.y);
                 }
                 ow[j] = pack_bf16(f0, f1);
             }
@@ -322,8 +329,9 @@ struct LeafArgs {
     int emb_ld;
     const bf16 *wiou;
     const float *b_iou;
+    long long *dbg;            // tuning only: SM-clock stamps of CTA 0 (fl_policy_debug_clocks)
 };
-constexpr int LEAF_THREADS = 13 * 32;   // 8 epilogue warps, 4 producer warps, 1 MMA warp
+constexpr int LEAF_THREADS = 21 * 32;   // 16 epilogue warps (8 per half of the hidden units), MMA warp, 4 producer warps
 constexpr int LEAF_STAGES = 6;
 constexpr int LEAF_PITCH = 144;         // 128 bytes (64 hidden units) + 16
 
@@ -335,15 +343,15 @@ __global__ void __launch_bounds__(LEAF_THREADS, 1) k_tree_leaf(const LeafArgs p)
     if ((int)blockIdx.x >= mtiles) return;
     uint8_t *sW = smem;                       // 384 rows x 128 B (first 32 B of every row used)
     uint8_t *sA = smem + 3 * TILE;
-    uint8_t *sC = sA + LEAF_STAGES * TILE;    // staged h | c of one half tile: 2 x 128 rows, pitch LEAF_PITCH
-    uint32_t *rowoff = (uint32_t *)(sC + 2 * 128 * LEAF_PITCH);   // element offset of every row's node in h / c
-    uint64_t *bars = (uint64_t *)(rowoff + 128);
+    uint8_t *sC = sA + LEAF_STAGES * TILE;    // per half: staged h | c, 2 x 128 rows, pitch LEAF_PITCH
+    uint32_t *rowoff = (uint32_t *)(sC + 4 * 128 * LEAF_PITCH);   // per half: element offset of every row's node in h / c
+    uint64_t *bars = (uint64_t *)(rowoff + 256);
     uint64_t *full = bars, *empty = bars + LEAF_STAGES, *wfull = bars + 2 * LEAF_STAGES;
     uint64_t *tfull = wfull + 1, *tempty = tfull + 2;
     uint32_t *tmem_slot = (uint32_t *)(tempty + 2);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
-    if (warp == 12) {
+    if (warp == 16) {
         if (lane == 0) {
             for (int s = 0; s < LEAF_STAGES; s++) { mbar_init(&full[s], 128); mbar_init(&empty[s], 1); }
             mbar_init(wfull, 128);
@@ -358,8 +366,9 @@ __global__ void __launch_bounds__(LEAF_THREADS, 1) k_tree_leaf(const LeafArgs p)
     fence_after_sync();
     const uint32_t tmem = *tmem_slot;
 
-    if (warp >= 8 && warp < 12) {
-        const int tp = threadIdx.x - 256;
+    if (warp >= 17) {
+        // ---------------- producers ----------------
+        const int tp = threadIdx.x - 544;
         const int c = tp & 7, r0 = tp >> 3;
         const uint32_t swz = (uint32_t)((c ^ (r0 & 7)) << 4) + (uint32_t)r0 * 128u;
         if (c < 2) {
@@ -390,109 +399,110 @@ __global__ void __launch_bounds__(LEAF_THREADS, 1) k_tree_leaf(const LeafArgs p)
             cp_async_arrive(&full[s]);
         }
         cp_async_wait_all();
-    } else if (warp == 12) {
+    } else if (warp == 16) {
+        // ---------------- MMA issue ----------------
         if (lane == 0) {
             mbar_wait(wfull, 0);
             fence_after_sync();
             const uint32_t idesc = idesc_bf16(128, 64);
             const uint32_t w0 = smem_u32(sW);
-            uint32_t it = 0, hl = 0;
+            uint32_t it = 0;
             for (int mt = blockIdx.x; mt < mtiles; mt += gridDim.x, it++) {
                 const int s = it % LEAF_STAGES;
                 mbar_wait(&full[s], (it / LEAF_STAGES) & 1);
                 fence_after_sync();
                 const uint64_t ad = desc_sw128(smem_u32(sA + (size_t)s * TILE));
-                for (int half = 0; half < 2; half++, hl++) {
-                    const uint32_t b = hl & 1;
-                    mbar_wait(&tempty[b], ((hl >> 1) & 1) ^ 1);
+                for (int half = 0; half < 2; half++) {      // accumulator `half` always holds hidden units 64 half ..
+                    mbar_wait(&tempty[half], (it & 1) ^ 1);
                     fence_after_sync();
                     for (int g = 0; g < 3; g++)     // gate g (i, o, u): rows 128 g + 64 half .. of W_iou
-                        mma_bf16(tmem + b * 256 + g * 64, ad, desc_sw128(w0 + (uint32_t)(g * 128 + half * 64) * 128u), idesc, 0u);
+                        mma_bf16(tmem + half * 256 + g * 64, ad, desc_sw128(w0 + (uint32_t)(g * 128 + half * 64) * 128u), idesc, 0u);
                     if (half == 1) mma_commit(&empty[s]);
-                    mma_commit(&tfull[b]);
+                    mma_commit(&tfull[half]);
                 }
             }
         }
         __syncwarp();
     } else {
-        const int q = warp & 3, sub = warp >> 2;      // sub: which 32 of the half's 64 hidden units
-        uint32_t hl = 0;
-        for (int mt = blockIdx.x; mt < mtiles; mt += gridDim.x) {
+        // ---------------- epilogue: warps 0-7 own half 0 (hidden units 0..63) of every tile, warps 8-15 half 1, so the
+        // gate math of one half overlaps the store drain of the other ----------------
+        const int half = warp >> 3, q = warp & 3, sub = (warp >> 2) & 1;   // sub: which 32 of the half's 64 hidden units
+        const int n0 = half * 64 + sub * 32;
+        uint8_t *sCh = sC + (size_t)half * 2 * 128 * LEAF_PITCH;
+        uint32_t *roff = rowoff + half * 128;
+        const int te = (warp & 7) * 32 + lane;
+        uint32_t tl = 0;
+        for (int mt = blockIdx.x; mt < mtiles; mt += gridDim.x, tl++) {
+            const bool dbg = p.dbg && blockIdx.x == 0 && threadIdx.x == 0 && tl >= 8 && tl < 12;
+            long long *dd = p.dbg + (tl >= 8 ? (tl - 8) * 16 : 0);
+            if (dbg) dd[4] = clock64();
             const int r = mt * 128 + q * 32 + lane;
             const bool valid = r < rows;
             uint32_t t = 0, v = 0, ch0 = 0;
             if (valid) entry_decode(__ldg(p.entries + r), t, v, ch0);
             const size_t orow = ((size_t)t * NODES + v) * 128;
-            for (int half = 0; half < 2; half++, hl++) {
-                const uint32_t b = hl & 1;
-                const int n0 = half * 64 + sub * 32;
-                mbar_wait(&tfull[b], (hl >> 1) & 1);
-                fence_after_sync();
-                const uint32_t tbase = tmem + ((uint32_t)(q * 32) << 16) + b * 256 + sub * 32;
-                uint32_t vi[32], vo[32], vu[32];
-                tmem_ld16(tbase, vi);
-                tmem_ld16(tbase + 16, vi + 16);
-                tmem_ld16(tbase + 64, vo);
-                tmem_ld16(tbase + 80, vo + 16);
-                tmem_ld16(tbase + 128, vu);
-                tmem_ld16(tbase + 144, vu + 16);
+            mbar_wait(&tfull[half], tl & 1);
+            fence_after_sync();
+            if (dbg) dd[5] = clock64();
+            const uint32_t tbase = tmem + ((uint32_t)(q * 32) << 16) + half * 256 + sub * 32;
+            uint32_t hw[16], cw[16];
+#pragma unroll
+            for (int u16 = 0; u16 < 2; u16++) {
+                uint32_t vi[16], vo[16], vu[16];
+                tmem_ld16(tbase + u16 * 16, vi);
+                tmem_ld16(tbase + 64 + u16 * 16, vo);
+                tmem_ld16(tbase + 128 + u16 * 16, vu);
                 tmem_ld_wait();
-                fence_before_sync();
-                mbar_arrive(&tempty[b]);
-                uint32_t hw[16], cw[16];
+                if (u16 == 1) {
+                    fence_before_sync();
+                    mbar_arrive(&tempty[half]);
+                }
+                // i and o arrive as half their pre-activation (weights pre-scaled): sigmoid(2z) = 0.5 tanh(z) + 0.5
 #pragma unroll
-                for (int j = 0; j < 8; j++) {
-                    const float4 bi = __ldg(reinterpret_cast<const float4 *>(p.b_iou + n0) + j);
-                    const float4 bo = __ldg(reinterpret_cast<const float4 *>(p.b_iou + 128 + n0) + j);
-                    const float4 bu = __ldg(reinterpret_cast<const float4 *>(p.b_iou + 256 + n0) + j);
-                    const float bis[4] = {bi.x, bi.y, bi.z, bi.w}, bos[4] = {bo.x, bo.y, bo.z, bo.w}, bus[4] = {bu.x, bu.y, bu.z, bu.w};
-                    float cc[4], hh[4];
+                for (int j = 0; j < 16; j += 2) {
+                    float cc[2], hh[2];
 #pragma unroll
-                    for (int k = 0; k < 4; k++) {
-                        const float gi = sigmoidf(__uint_as_float(vi[4 * j + k]) + bis[k]);
-                        const float go = sigmoidf(__uint_as_float(vo[4 * j + k]) + bos[k]);
-                        const float gu = tanh_fast(__uint_as_float(vu[4 * j + k]) + bus[k]);
-                        cc[k] = gi * gu;
-                        hh[k] = go * tanh_fast(cc[k]);
+                    for (int k = 0; k < 2; k++) {
+                        const float ti = tanh_fast(__uint_as_float(vi[j + k])), to = tanh_fast(__uint_as_float(vo[j + k]));
+                        const float tu = tanh_fast(__uint_as_float(vu[j + k]));
+                        cc[k] = fmaf(0.5f * tu, ti, 0.5f * tu);
+                        const float tc = tanh_fast(cc[k]);
+                        hh[k] = fmaf(0.5f * tc, to, 0.5f * tc);
                     }
-                    cw[2 * j] = pack_bf16(cc[0], cc[1]);
-                    cw[2 * j + 1] = pack_bf16(cc[2], cc[3]);
-                    hw[2 * j] = pack_bf16(hh[0], hh[1]);
-                    hw[2 * j + 1] = pack_bf16(hh[2], hh[3]);
+                    cw[u16 * 8 + (j >> 1)] = pack_bf16(cc[0], cc[1]);
+                    hw[u16 * 8 + (j >> 1)] = pack_bf16(hh[0], hh[1]);
                 }
-                // staged through shared memory so that 8 lanes write one 128-byte row segment (see k_lin)
-                named_bar_sync(1, 256);
-                const uint32_t srow = smem_u32(sC) + (uint32_t)(q * 32 + lane) * LEAF_PITCH;
+            }
+            // staged through shared memory so that 8 lanes write one 128-byte row segment (see k_lin)
+            if (dbg) dd[6] = clock64();
+            named_bar_sync(1 + 2 * half, 256);
+            const uint32_t srow = smem_u32(sCh) + (uint32_t)(q * 32 + lane) * LEAF_PITCH;
 #pragma unroll
-                for (int j = 0; j < 4; j++) {
-                    st_shared_v4(srow + sub * 64 + j * 16, hw[4 * j], hw[4 * j + 1], hw[4 * j + 2], hw[4 * j + 3]);
-                    st_shared_v4(srow + 128 * LEAF_PITCH + sub * 64 + j * 16, cw[4 * j], cw[4 * j + 1], cw[4 * j + 2], cw[4 * j + 3]);
-                }
-                if (sub == 0 && half == 0) rowoff[q * 32 + lane] = valid ? (uint32_t)orow : 0xFFFFFFFFu;
-                named_bar_sync(2, 256);
-                {
-                    const int te = warp * 32 + lane;
+            for (int j = 0; j < 4; j++) {
+                st_shared_v4(srow + sub * 64 + j * 16, hw[4 * j], hw[4 * j + 1], hw[4 * j + 2], hw[4 * j + 3]);
+                st_shared_v4(srow + 128 * LEAF_PITCH + sub * 64 + j * 16, cw[4 * j], cw[4 * j + 1], cw[4 * j + 2], cw[4 * j + 3]);
+            }
+            if (sub == 0) roff[q * 32 + lane] = valid ? (uint32_t)orow : 0xFFFFFFFFu;
+            named_bar_sync(2 + 2 * half, 256);
+            if (dbg) dd[8] = clock64();
 #pragma unroll
-                    for (int j = 0; j < 8; j++) {
-                        const int ci = te + 256 * j, which = ci >> 10, row = (ci >> 3) & 127, cc = ci & 7;
-                        const uint4 val = ld_shared_v4(smem_u32(sC) + (uint32_t)(which * 128 + row) * LEAF_PITCH + cc * 16);
-                        const uint32_t off = rowoff[row];
-                        if (off != 0xFFFFFFFFu) *reinterpret_cast<uint4 *>((which ? p.c : p.h) + off + half * 64 + cc * 8) = val;
-                    }
-                }
-                if (valid) {
-                    if (v == 0) {
-                        uint4 *oe = reinterpret_cast<uint4 *>(p.emb + (size_t)t * p.emb_ld + n0);
+            for (int j = 0; j < 8; j++) {
+                const int ci = te + 256 * j, which = ci >> 10, row = (ci >> 3) & 127, cc = ci & 7;
+                const uint4 val = ld_shared_v4(smem_u32(sCh) + (uint32_t)(which * 128 + row) * LEAF_PITCH + cc * 16);
+                const uint32_t off = roff[row];
+                if (off != 0xFFFFFFFFu) *reinterpret_cast<uint4 *>((which ? p.c : p.h) + off + half * 64 + cc * 8) = val;
+            }
+            if (dbg) dd[9] = clock64();
+            if (valid && v == 0) {
+                uint4 *oe = reinterpret_cast<uint4 *>(p.emb + (size_t)t * p.emb_ld + n0);
 #pragma unroll
-                        for (int j = 0; j < 4; j++) oe[j] = make_uint4(hw[4 * j], hw[4 * j + 1], hw[4 * j + 2], hw[4 * j + 3]);
-                    }
-                }
+                for (int j = 0; j < 4; j++) oe[j] = make_uint4(hw[4 * j], hw[4 * j + 1], hw[4 * j + 2], hw[4 * j + 3]);
             }
         }
     }
     fence_before_sync();
     __syncthreads();
-    if (warp == 12) tmem_dealloc(tmem, 512);
+    if (warp == 16) tmem_dealloc(tmem, 512);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -638,26 +648,22 @@ __global__ void __launch_bounds__(416, 1) k_tree_p(const TreeArgs p) {
                 if (inner) tmem_ld16(tbase + 384 + ch * 16, vc);
                 tmem_ld_wait();
                 uint32_t hw[8], cw[8];
-                float bi[16], bo[16], bu[16], bc[16];
+                float bc[16];
 #pragma unroll
-                for (int j = 0; j < 4; j++) {
-                    *reinterpret_cast<float4 *>(&bi[4 * j]) = __ldg(reinterpret_cast<const float4 *>(p.b_iou + ch * 16) + j);
-                    *reinterpret_cast<float4 *>(&bo[4 * j]) = __ldg(reinterpret_cast<const float4 *>(p.b_iou + 128 + ch * 16) + j);
-                    *reinterpret_cast<float4 *>(&bu[4 * j]) = __ldg(reinterpret_cast<const float4 *>(p.b_iou + 256 + ch * 16) + j);
-                    *reinterpret_cast<float4 *>(&bc[4 * j]) = __ldg(reinterpret_cast<const float4 *>(p.b_c + ch * 16) + j);
-                }
+                for (int j = 0; j < 4; j++) *reinterpret_cast<float4 *>(&bc[4 * j]) = __ldg(reinterpret_cast<const float4 *>(p.b_c + ch * 16) + j);
+                // b_iou rides in the MMA (x column 12); i and o arrive as half their pre-activation
 #pragma unroll
                 for (int j = 0; j < 16; j += 2) {
                     float cc[2], hh[2];
 #pragma unroll
-                    for (int q = 0; q < 2; q++) {
-                        const float gi = sigmoidf(__uint_as_float(vi[j + q]) + bi[j + q]);
-                        const float go = sigmoidf(__uint_as_float(vo[j + q]) + bo[j + q]);
-                        const float gu = tanh_fast(__uint_as_float(vu[j + q]) + bu[j + q]);
-                        float cn = gi * gu;
-                        if (inner) cn += __uint_as_float(vc[j + q]) + bc[j + q];
-                        cc[q] = cn;
-                        hh[q] = go * tanh_fast(cn);
+                    for (int k = 0; k < 2; k++) {
+                        const float ti = tanh_fast(__uint_as_float(vi[j + k])), to = tanh_fast(__uint_as_float(vo[j + k]));
+                        const float tu = tanh_fast(__uint_as_float(vu[j + k]));
+                        float cn = fmaf(0.5f * tu, ti, 0.5f * tu);
+                        if (inner) cn += __uint_as_float(vc[j + k]) + bc[j + k];
+                        cc[k] = cn;
+                        const float tc = tanh_fast(cn);
+                        hh[k] = fmaf(0.5f * tc, to, 0.5f * tc);
                     }
                     cw[j >> 1] = pack_bf16(cc[0], cc[1]);
                     hw[j >> 1] = pack_bf16(hh[0], hh[1]);
@@ -716,9 +722,10 @@ __global__ void k_prep(const float *__restrict__ attr, const float *__restrict__
 #pragma unroll
             for (int j = 0; j < 12; j++) f[j] = f[j] == CUDART_INF_F ? -1.0f : f[j];
         }
+        // column 12 is the constant 1 that multiplies the bias column of W_iou / W_f (the biases ride in the MMA)
         uint4 *dst = reinterpret_cast<uint4 *>(x + u * 16);
         dst[0] = make_uint4(pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]), pack_bf16(f[4], f[5]), pack_bf16(f[6], f[7]));
-        dst[1] = make_uint4(pack_bf16(f[8], f[9]), pack_bf16(f[10], f[11]), 0u, 0u);
+        dst[1] = make_uint4(pack_bf16(f[8], f[9]), pack_bf16(f[10], f[11]), pack_bf16(node < 31 ? 1.0f : 0.0f, 0.0f), 0u);
     }
 }
 
@@ -759,97 +766,6 @@ __global__ void k_tree_plan(const int32_t *__restrict__ adjacency, const int32_t
             if (o < 0) continue;
             const size_t off = o == 0 ? 0 : (size_t)21 * M + (size_t)(o - 1) * 10 * M;
             lists[off + base[o] + pos[v]] = (uint32_t)t | ((uint32_t)v << 22) | ((uint32_t)child0[v] << 27);
-        }
-    }
-}
-
-// Attention of one (environment, head): thread = query agent, keys / values of the head staged in shared memory as
-// fp32, 64 at a time (read back as broadcast 16-byte loads), online softmax in fp32.  qkv [M][768] = q | k | v,
-// out [M][256].
-__global__ void __launch_bounds__(64) k_attention(const bf16 *__restrict__ qkv, bf16 *__restrict__ out, int N) {
-    __shared__ float4 Ks[64][16];
-    __shared__ float4 Vs[64][16];
-    const int e = blockIdx.x, hd = blockIdx.y;
-    const size_t row0 = (size_t)e * N;
-    for (int q0 = 0; q0 < N; q0 += 64) {
-        const int qi = q0 + threadIdx.x;
-        const bool active = qi < N;
-        float4 q[16], acc[16];
-#pragma unroll
-        for (int j = 0; j < 16; j++) q[j] = acc[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (active) {
-            const uint4 *src = reinterpret_cast<const uint4 *>(qkv + (row0 + qi) * 768 + hd * 64);
-#pragma unroll
-            for (int j = 0; j < 8; j++) {
-                const uint4 w = src[j];
-                const float2 f0 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162 *>(&w.x));
-                const float2 f1 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162 *>(&w.y));
-                const float2 f2 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162 *>(&w.z));
-                const float2 f3 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162 *>(&w.w));
-                q[2 * j] = make_float4(f0.x * 0.125f, f0.y * 0.125f, f1.x * 0.125f, f1.y * 0.125f);
-                q[2 * j + 1] = make_float4(f2.x * 0.125f, f2.y * 0.125f, f3.x * 0.125f, f3.y * 0.125f);
-            }
-        }
-        float mx = -CUDART_INF_F, den = 0.0f;
-        for (int k0 = 0; k0 < N; k0 += 64) {
-            const int cnt = min(64, N - k0);
-            __syncthreads();
-            for (int idx = threadIdx.x; idx < cnt * 8; idx += 64) {
-                const int kr = idx >> 3, cc = idx & 7;
-                const bf16 *base = qkv + (row0 + k0 + kr) * 768 + hd * 64 + cc * 8;
-                const uint4 kw = *reinterpret_cast<const uint4 *>(base + 256);
-                const uint4 vw = *reinterpret_cast<const uint4 *>(base + 512);
-                float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162 *>(&kw.x));
-                float2 b = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162 *>(&kw.y));
-                Ks[kr][2 * cc] = make_float4(a.x, a.y, b.x, b.y);
-                a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162 *>(&kw.z));
-                b = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162 *>(&kw.w));
-                Ks[kr][2 * cc + 1] = make_float4(a.x, a.y, b.x, b.y);
-                a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162 *>(&vw.x));
-                b = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162 *>(&vw.y));
-                Vs[kr][2 * cc] = make_float4(a.x, a.y, b.x, b.y);
-                a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162 *>(&vw.z));
-                b = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162 *>(&vw.w));
-                Vs[kr][2 * cc + 1] = make_float4(a.x, a.y, b.x, b.y);
-            }
-            __syncthreads();
-            for (int kr = 0; kr < cnt; kr++) {
-                float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
-#pragma unroll
-                for (int j = 0; j < 16; j++) {
-                    const float4 kk = Ks[kr][j];
-                    s0 = fmaf(q[j].x, kk.x, s0);
-                    s1 = fmaf(q[j].y, kk.y, s1);
-                    s2 = fmaf(q[j].z, kk.z, s2);
-                    s3 = fmaf(q[j].w, kk.w, s3);
-                }
-                const float s = (s0 + s1) + (s2 + s3);
-                if (s > mx) {
-                    const float corr = __expf(mx - s);
-                    den *= corr;
-#pragma unroll
-                    for (int j = 0; j < 16; j++) { acc[j].x *= corr; acc[j].y *= corr; acc[j].z *= corr; acc[j].w *= corr; }
-                    mx = s;
-                }
-                const float pr = __expf(s - mx);
-                den += pr;
-#pragma unroll
-                for (int j = 0; j < 16; j++) {
-                    const float4 vv = Vs[kr][j];
-                    acc[j].x = fmaf(pr, vv.x, acc[j].x);
-                    acc[j].y = fmaf(pr, vv.y, acc[j].y);
-                    acc[j].z = fmaf(pr, vv.z, acc[j].z);
-                    acc[j].w = fmaf(pr, vv.w, acc[j].w);
-                }
-            }
-        }
-        if (active) {
-            const float inv = 1.0f / den;
-            uint4 *dst = reinterpret_cast<uint4 *>(out + (row0 + qi) * 256 + hd * 64);
-#pragma unroll
-            for (int j = 0; j < 8; j++)
-                dst[j] = make_uint4(pack_bf16(acc[2 * j].x * inv, acc[2 * j].y * inv), pack_bf16(acc[2 * j].z * inv, acc[2 * j].w * inv),
-                                    pack_bf16(acc[2 * j + 1].x * inv, acc[2 * j + 1].y * inv), pack_bf16(acc[2 * j + 1].z * inv, acc[2 * j + 1].w * inv));
         }
     }
 }
@@ -1102,7 +1018,8 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 EncodeTiledFn g_encode = nullptr;
 int g_num_sms = 0;
-long long *g_dbg = nullptr;
+long long *g_dbg = nullptr;       // k_lin timeline (fl_policy_linear_debug)
+long long *g_leaf_dbg = nullptr;  // k_tree_leaf timeline (fl_policy_debug_clocks)
 bool g_attr_set = false;
 
 int setup() {
@@ -1125,7 +1042,7 @@ int setup() {
     if (!g_attr_set) {
         const int lin_max = 1024 + 11 * TILE + 128 * OUT_PITCH + 1024 + 512;
         const int p_bytes = 1024 + P_STAGES * P_STAGE_BYTES + 256;
-        const int leaf_bytes = 1024 + (3 + LEAF_STAGES) * TILE + 2 * 128 * LEAF_PITCH + 1024;
+        const int leaf_bytes = 1024 + (3 + LEAF_STAGES) * TILE + 4 * 128 * LEAF_PITCH + 2048;
         cudaError_t e = cudaFuncSetAttribute(k_lin<MODE_LINEAR>, cudaFuncAttributeMaxDynamicSharedMemorySize, lin_max);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(k_lin<MODE_TREE_F>, cudaFuncAttributeMaxDynamicSharedMemorySize, lin_max);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(k_tree_p, cudaFuncAttributeMaxDynamicSharedMemorySize, p_bytes);
@@ -1244,6 +1161,8 @@ int fl_policy_linear_debug(const uint16_t *d_a, int64_t lda, const uint16_t *d_w
     return rc;
 }
 
+void fl_policy_debug_clocks(long long *d_clocks) { g_leaf_dbg = d_clocks; }
+
 int fl_policy_forward(const FlPolicyWeights *w, void *d_workspace, size_t workspace_bytes, int64_t E, int64_t N,
                       const float *d_agent_attr, const float *d_forest, const int32_t *d_adjacency,
                       const int32_t *d_node_order, float *d_logits, float *d_value, void *stream) {
@@ -1283,8 +1202,8 @@ int fl_policy_forward(const FlPolicyWeights *w, void *d_workspace, size_t worksp
             LeafArgs lf = {};
             lf.entries = list; lf.count_dev = ws.counts; lf.x = ws.x; lf.h = ws.h; lf.c = ws.c;
             lf.emb = ws.emb + 128; lf.emb_ld = 256;
-            lf.wiou = (const bf16 *)w->tree_wiou; lf.b_iou = w->tree_b_iou;
-            k_tree_leaf<<<g_num_sms, LEAF_THREADS, 1024 + (3 + LEAF_STAGES) * TILE + 2 * 128 * LEAF_PITCH + 1024, st>>>(lf);
+            lf.wiou = (const bf16 *)w->tree_wiou; lf.b_iou = w->tree_b_iou; lf.dbg = g_leaf_dbg;
+            k_tree_leaf<<<g_num_sms, LEAF_THREADS, 1024 + (3 + LEAF_STAGES) * TILE + 4 * 128 * LEAF_PITCH + 2048, st>>>(lf);
             g_launches++;
             continue;
         }

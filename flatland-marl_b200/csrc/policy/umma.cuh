@@ -3,6 +3,7 @@
 // Descriptor bit layouts follow the PTX ISA "tcgen05 matrix descriptors" (K-major operands, 128-byte swizzle).
 #pragma once
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <stdint.h>
 
 namespace umma {
@@ -128,6 +129,28 @@ __device__ __forceinline__ float tanh_fast(float x) {
     return y;
 }
 __device__ __forceinline__ float sigmoidf(float x) { return fmaf(0.5f, tanh_fast(0.5f * x), 0.5f); }
+// Two tanh per MUFU operation (tanh.approx.f16x2).  The special-function unit retires 16 lanes per clock per SM, and the
+// LSTM gates need four transcendentals per hidden unit: with scalar tanh.approx.f32 the leaf kernel alone is 4096 MUFU
+// cycles per 128-node tile.  The f16 result carries the same ~2^-11 relative error as tanh.approx.f32.
+__device__ __forceinline__ float2 tanh2_fast(float a, float b) {
+    const __half2 h = __floats2half2_rn(a, b);
+    uint32_t r;
+    asm("tanh.approx.f16x2 %0, %1;" : "=r"(r) : "r"(*reinterpret_cast<const uint32_t *>(&h)));
+    return __half22float2(*reinterpret_cast<const __half2 *>(&r));
+}
+__device__ __forceinline__ float2 sigmoid2_fast(float a, float b) {
+    const float2 t = tanh2_fast(0.5f * a, 0.5f * b);
+    return make_float2(fmaf(0.5f, t.x, 0.5f), fmaf(0.5f, t.y, 0.5f));
+}
+__device__ __forceinline__ float2 gelu2_erf(float x, float y) {
+    const float ux = fminf(x * x, 49.0f), uy = fminf(y * y, 49.0f);
+    float px = fmaf(ux, -3.51516783e-4f, 3.70056460e-2f), py = fmaf(uy, -3.51516783e-4f, 3.70056460e-2f);
+    px = fmaf(ux, px, 7.97507884e-1f);
+    py = fmaf(uy, py, 7.97507884e-1f);
+    const float2 t = tanh2_fast(x * px, y * py);
+    const float hx = 0.5f * x, hy = 0.5f * y;
+    return make_float2(fmaf(hx, t.x, hx), fmaf(hy, t.y, hy));
+}
 // GELU (erf form, nn.GELU default) as 0.5 x (1 + tanh(x P(x^2))): P is a quadratic fitted to the erf form (max absolute
 // deviation 2.5e-5 over all x; the textbook tanh form is off by 4.7e-4), x^2 clamped where tanh has saturated.
 // 8 instructions, one MUFU — the erf-by-exp form (17 instructions, two MUFU) made the epilogue the pace of k_lin.

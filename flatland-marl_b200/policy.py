@@ -19,7 +19,7 @@ LIB_PATH = os.path.join(HERE, "csrc", "policy", "libflatland_policy_b200.so")
 LAYERS = pw.N_TRANSFORMER
 
 EXPORTS = ["fl_policy_abi_version", "fl_policy_workspace_bytes", "fl_policy_forward", "fl_policy_choose_actions",
-           "fl_policy_linear", "fl_policy_linear_debug", "fl_policy_launch_count"]
+           "fl_policy_linear", "fl_policy_linear_debug", "fl_policy_debug_clocks", "fl_policy_launch_count"]
 
 
 class FlPolicyWeights(C.Structure):
@@ -53,6 +53,8 @@ def lib():
     L.fl_policy_choose_actions.argtypes = [P, P, P, C.c_int64, P]
     L.fl_policy_linear.restype = C.c_int
     L.fl_policy_linear.argtypes = [P, C.c_int64, P, P, P, C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_int, P]
+    L.fl_policy_debug_clocks.restype = None
+    L.fl_policy_debug_clocks.argtypes = [P]
     L.fl_policy_linear_debug.restype = C.c_int
     L.fl_policy_linear_debug.argtypes = [P, C.c_int64, P, P, P, C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_int, P, P]
     _lib = L
@@ -74,10 +76,19 @@ def pack_weights(w):
         out[:, : m.shape[1]] = m
         return out
 
+    # Tree-LSTM: biases become column 12 of the node-feature weights (the kernels feed a constant 1 there), and the
+    # sigmoid gates' rows are halved: sigmoid(2z) = 0.5 tanh(z) + 0.5 (see include/flatland_policy_b200.h)
+    wiou = pad_in(w["tree_lstm.W_iou.weight"], 16)
+    wiou[:, 12] = w["tree_lstm.W_iou.bias"]
+    uiou = w["tree_lstm.U_iou.weight"].copy()
+    wiou[:256] *= 0.5
+    uiou[:256] *= 0.5
+    wf = pad_in(w["tree_lstm.W_f.weight"], 16)
+    wf[:, 12] = w["tree_lstm.W_f.bias"]
     d = {
-        "tree_uiou": w["tree_lstm.U_iou.weight"], "tree_wiou": pad_in(w["tree_lstm.W_iou.weight"], 16),
+        "tree_uiou": uiou, "tree_wiou": wiou,
         "tree_wc": w["tree_lstm.W_c.weight"],
-        "tree_ufwf": np.concatenate([w["tree_lstm.U_f.weight"], pad_in(w["tree_lstm.W_f.weight"], 16)], axis=1),
+        "tree_ufwf": 0.5 * np.concatenate([w["tree_lstm.U_f.weight"], wf], axis=1),
         "tree_b_iou": w["tree_lstm.W_iou.bias"], "tree_b_c": w["tree_lstm.W_c.bias"], "tree_b_f": w["tree_lstm.W_f.bias"],
         "head_w1": np.concatenate([w["actor_net.0.weight"], w["critic_net.0.weight"]], axis=0),
         "head_b1": np.concatenate([w["actor_net.0.bias"], w["critic_net.0.bias"]]),

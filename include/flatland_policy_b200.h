@@ -38,13 +38,17 @@ extern "C" {
  * them, `in` zero-padded to the stated width; biases are fp32.  flatland-marl_b200/policy.py packs them from a
  * reference state_dict. */
 typedef struct FlPolicyWeights {
-    const uint16_t *tree_uiou;  /* [384][384]  tree_lstm.U_iou.weight */
-    const uint16_t *tree_wiou;  /* [384][16]   tree_lstm.W_iou.weight (12 inputs used) */
+    /* Tree-LSTM.  The gate biases ride in the matrix product: the node-feature operand carries a constant 1 in column 12
+     * and column 12 of tree_wiou / column 140 of tree_ufwf holds the bias.  Rows of the sigmoid gates (i: 0..127, o:
+     * 128..255 of tree_uiou / tree_wiou, and all of tree_ufwf) are stored multiplied by 1/2, because the kernels
+     * evaluate sigmoid(2z) as 0.5 tanh(z) + 0.5 (one MUFU operation). */
+    const uint16_t *tree_uiou;  /* [384][384]  tree_lstm.U_iou.weight (i, o rows x 1/2) */
+    const uint16_t *tree_wiou;  /* [384][16]   tree_lstm.W_iou.weight | col 12: W_iou.bias (i, o rows x 1/2) */
     const uint16_t *tree_wc;    /* [128][384]  tree_lstm.W_c.weight */
-    const uint16_t *tree_ufwf;  /* [128][144]  tree_lstm.U_f.weight | tree_lstm.W_f.weight (12 of the last 16 used) */
-    const float *tree_b_iou;    /* [384] */
+    const uint16_t *tree_ufwf;  /* [128][144]  (tree_lstm.U_f.weight | tree_lstm.W_f.weight | col 140: W_f.bias) x 1/2 */
+    const float *tree_b_iou;    /* [384] unscaled, kept for reference (not read by the kernels) */
     const float *tree_b_c;      /* [128] */
-    const float *tree_b_f;      /* [128] */
+    const float *tree_b_f;      /* [128] unscaled, kept for reference (not read by the kernels) */
     const uint16_t *attr_w[4];  /* [256][128 (83 used)], [256][256], [256][256], [128][256]  attr_embedding.{0,2,4,6} */
     const float *attr_b[4];
     const uint16_t *tf_wqkv[FL_POLICY_LAYERS]; /* [768][256] transformer.l.attention.in_proj_weight */
@@ -93,6 +97,9 @@ int fl_policy_linear(const uint16_t *d_a, int64_t lda, const uint16_t *d_w, cons
  * starts tile t). */
 int fl_policy_linear_debug(const uint16_t *d_a, int64_t lda, const uint16_t *d_w, const float *d_bias, uint16_t *d_c,
                            int64_t ldc, int64_t M, int64_t N, int64_t K, int act, long long *d_clocks, void *stream);
+
+/* Tuning only: while set (non-NULL), k_tree_leaf of later forwards writes SM-clock stamps of its CTA 0 into d_clocks[128]. */
+void fl_policy_debug_clocks(long long *d_clocks);
 
 uint64_t fl_policy_launch_count(void);
 
