@@ -32,7 +32,7 @@ typedef __nv_bfloat16 bf16;
 namespace {
 
 constexpr int TILE = 128 * 128;   // bytes of a 128-row x 64-element bf16 tile (one k-block)
-constexpr int P_STAGES = 3;
+constexpr int P_STAGES = 2;
 constexpr int P_STAGE_BYTES = 4 * TILE;   // A tile + up to 384 rows of B
 constexpr int NODES = 32;         // node slots per tree in the h / c / fc / x scratch (31 used)
 
@@ -525,7 +525,9 @@ __global__ void __launch_bounds__(416, 1) k_tree_p(const TreeArgs p) {
     const int rows = *p.count_dev;
     const int mtiles = (rows + 127) >> 7;
     if ((int)blockIdx.x >= mtiles) return;
-    uint64_t *bars = (uint64_t *)(smem + P_STAGES * P_STAGE_BYTES);
+    uint8_t *sC = smem + P_STAGES * P_STAGE_BYTES;          // staged h | c of the tile: 2 x 128 rows, pitch OUT_PITCH
+    uint32_t *rowoff = (uint32_t *)(sC + 2 * 128 * OUT_PITCH);
+    uint64_t *bars = (uint64_t *)(rowoff + 128);
     uint64_t *full = bars, *empty = bars + P_STAGES, *tfull = bars + 2 * P_STAGES, *tempty = tfull + 1;
     uint32_t *tmem_slot = (uint32_t *)(tempty + 1);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -639,6 +641,7 @@ __global__ void __launch_bounds__(416, 1) k_tree_p(const TreeArgs p) {
             mbar_wait(tfull, tl & 1);
             fence_after_sync();
             const uint32_t tbase = tmem + ((uint32_t)((warp & 3) * 32) << 16);
+            const uint32_t srow = smem_u32(sC) + (uint32_t)((warp & 3) * 32 + lane) * OUT_PITCH;
 #pragma unroll 1
             for (int ch = (warp >> 2) * 4; ch < (warp >> 2) * 4 + 4; ch++) {
                 uint32_t vi[16], vo[16], vu[16], vc[16];
@@ -668,22 +671,32 @@ __global__ void __launch_bounds__(416, 1) k_tree_p(const TreeArgs p) {
                     cw[j >> 1] = pack_bf16(cc[0], cc[1]);
                     hw[j >> 1] = pack_bf16(hh[0], hh[1]);
                 }
-                if (valid) {
-                    uint4 *oc = reinterpret_cast<uint4 *>(p.c + orow + ch * 16);
-                    oc[0] = make_uint4(cw[0], cw[1], cw[2], cw[3]);
-                    oc[1] = make_uint4(cw[4], cw[5], cw[6], cw[7]);
-                    uint4 *oh = reinterpret_cast<uint4 *>(p.h + orow + ch * 16);
-                    oh[0] = make_uint4(hw[0], hw[1], hw[2], hw[3]);
-                    oh[1] = make_uint4(hw[4], hw[5], hw[6], hw[7]);
-                    if (v == 0) {
-                        uint4 *oe = reinterpret_cast<uint4 *>(p.emb + (size_t)t * p.emb_ld + ch * 16);
-                        oe[0] = make_uint4(hw[0], hw[1], hw[2], hw[3]);
-                        oe[1] = make_uint4(hw[4], hw[5], hw[6], hw[7]);
-                    }
+                // staged: the rows leave through row-contiguous stores below (see k_lin)
+                st_shared_v4(srow + ch * 32, hw[0], hw[1], hw[2], hw[3]);
+                st_shared_v4(srow + ch * 32 + 16, hw[4], hw[5], hw[6], hw[7]);
+                st_shared_v4(srow + 128 * OUT_PITCH + ch * 32, cw[0], cw[1], cw[2], cw[3]);
+                st_shared_v4(srow + 128 * OUT_PITCH + ch * 32 + 16, cw[4], cw[5], cw[6], cw[7]);
+                if (valid && v == 0) {
+                    uint4 *oe = reinterpret_cast<uint4 *>(p.emb + (size_t)t * p.emb_ld + ch * 16);
+                    oe[0] = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+                    oe[1] = make_uint4(hw[4], hw[5], hw[6], hw[7]);
                 }
             }
             fence_before_sync();
-            mbar_arrive(tempty);
+            mbar_arrive(tempty);                          // every accumulator column of this thread's rows is in shared memory
+            if (warp < 4) rowoff[warp * 32 + lane] = valid ? (uint32_t)orow : 0xFFFFFFFFu;
+            named_bar_sync(1, 256);
+            {
+                const int te = warp * 32 + lane;
+#pragma unroll 4
+                for (int j = 0; j < 16; j++) {
+                    const int ci = te + 256 * j, which = ci >> 11, row = (ci >> 4) & 127, cc = ci & 15;
+                    const uint4 val = ld_shared_v4(smem_u32(sC) + (uint32_t)(which * 128 + row) * OUT_PITCH + cc * 16);
+                    const uint32_t off = rowoff[row];
+                    if (off != 0xFFFFFFFFu) *reinterpret_cast<uint4 *>((which ? p.c : p.h) + off + cc * 8) = val;
+                }
+            }
+            named_bar_sync(2, 256);                       // the staging tile may be overwritten
         }
     }
     fence_before_sync();
@@ -1041,7 +1054,7 @@ int setup() {
     }
     if (!g_attr_set) {
         const int lin_max = 1024 + 11 * TILE + 128 * OUT_PITCH + 1024 + 512;
-        const int p_bytes = 1024 + P_STAGES * P_STAGE_BYTES + 256;
+        const int p_bytes = 1024 + P_STAGES * P_STAGE_BYTES + 2 * 128 * OUT_PITCH + 1024;
         const int leaf_bytes = 1024 + (3 + LEAF_STAGES) * TILE + 4 * 128 * LEAF_PITCH + 2048;
         cudaError_t e = cudaFuncSetAttribute(k_lin<MODE_LINEAR>, cudaFuncAttributeMaxDynamicSharedMemorySize, lin_max);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(k_lin<MODE_TREE_F>, cudaFuncAttributeMaxDynamicSharedMemorySize, lin_max);
@@ -1194,6 +1207,7 @@ int fl_policy_forward(const FlPolicyWeights *w, void *d_workspace, size_t worksp
             p.rows = 0; p.rows_dev = ws.counts + lv; p.rows_mul = 3;
             p.entries = list; p.cstate = ws.c; p.fc = ws.fc;
             p.stages = lin_stages(3);
+            p.dbg = (lv == 1 && g_leaf_dbg && getenv("FL_POLICY_DBG_F")) ? g_leaf_dbg : nullptr;   // tuning only
             static CUtensorMap dummy;
             k_lin<MODE_TREE_F><<<dim3(g_num_sms, 1), LIN_THREADS, lin_smem(3), st>>>(p, dummy, dummy, dummy);
             g_launches++;
@@ -1202,7 +1216,7 @@ int fl_policy_forward(const FlPolicyWeights *w, void *d_workspace, size_t worksp
             LeafArgs lf = {};
             lf.entries = list; lf.count_dev = ws.counts; lf.x = ws.x; lf.h = ws.h; lf.c = ws.c;
             lf.emb = ws.emb + 128; lf.emb_ld = 256;
-            lf.wiou = (const bf16 *)w->tree_wiou; lf.b_iou = w->tree_b_iou; lf.dbg = g_leaf_dbg;
+            lf.wiou = (const bf16 *)w->tree_wiou; lf.b_iou = w->tree_b_iou; lf.dbg = (g_leaf_dbg && !getenv("FL_POLICY_DBG_F")) ? g_leaf_dbg : nullptr;
             k_tree_leaf<<<g_num_sms, LEAF_THREADS, 1024 + (3 + LEAF_STAGES) * TILE + 4 * 128 * LEAF_PITCH + 2048, st>>>(lf);
             g_launches++;
             continue;
@@ -1213,7 +1227,7 @@ int fl_policy_forward(const FlPolicyWeights *w, void *d_workspace, size_t worksp
         t.emb = ws.emb + 128; t.emb_ld = 256;
         t.uiou = (const bf16 *)w->tree_uiou; t.wiou = (const bf16 *)w->tree_wiou; t.wc = (const bf16 *)w->tree_wc;
         t.b_iou = w->tree_b_iou; t.b_c = w->tree_b_c;
-        k_tree_p<<<g_num_sms, 416, 1024 + P_STAGES * P_STAGE_BYTES + 256, st>>>(t);
+        k_tree_p<<<g_num_sms, 416, 1024 + P_STAGES * P_STAGE_BYTES + 2 * 128 * OUT_PITCH + 1024, st>>>(t);
         g_launches++;
     }
     // ---- attribute MLP (net_tree.py:41-50) ----

@@ -22,6 +22,15 @@ torch.cuda.synchronize()
 actor.lib.fl_policy_debug_clocks(None)
 c = clk.cpu().numpy().reshape(8, 16)
 t0 = c[0][0]
+if os.environ.get("FL_POLICY_DBG_F"):
+    c = clk.cpu().numpy()
+    t0 = c[3]
+    print("k_lin<TREE_F> level 1, CTA 0: mma warp start %d, weights resident %d" % (c[0] - t0, c[1] - t0))
+    for t in range(8):
+        print("  tile %d: producer start %6d | mma: acc free %6d first full %6d last full %6d | epi: acc full %6d read %6d math %6d staged %6d bar2 %6d stored %6d" %
+              (t, c[80 + t] - t0, c[8 + 4 * t] - t0, c[9 + 4 * t] - t0, c[10 + 4 * t] - t0, c[48 + 4 * t] - t0, c[49 + 4 * t] - t0,
+               c[96 + 4 * t] - t0, c[97 + 4 * t] - t0, c[98 + 4 * t] - t0, c[50 + 4 * t] - t0))
+    sys.exit(0)
 for t in range(4):
     print("tile %d (epilogue warp 0, half 0): start %d, accumulator full %d, gates done %d, staged %d, stored %d" %
           (8 + t, c[t][4] - c[0][4], c[t][5] - c[0][4], c[t][6] - c[0][4], c[t][8] - c[0][4], c[t][9] - c[0][4]))
