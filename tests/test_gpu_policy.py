@@ -132,3 +132,34 @@ def test_rollout_with_policy_in_the_loop(actor, golden):
         s, os_ = batch.state_numpy(0), env.state()
         for k in ("pos", "dir", "state"):
             assert (s[k] == os_[k]).all()
+
+
+@pytest.mark.parametrize("config,n_envs,sample", [("Test_03", 1024, (0, 517, 1023)), ("Test_14", 64, (63,)), ("Test_02", 8192, (1, 8191))])
+def test_full_batch_policy_on_sampled_envs(actor, config, n_envs, sample):
+    """BASELINE.json's batch sizes: after 40 lock-step steps with the policy in the loop, the logits of sampled
+    environments equal (bit for bit) those of a batch-1 forward on the same observation, agree with the numpy
+    oracle of the reference network within the stated tolerance, and the chosen actions are the oracle's wherever the
+    choice is not marginal."""
+    import bench
+    import flatland_marl_b200 as fb
+    worlds = bench.load_worlds(config, n_envs)
+    batch = fb.BatchedRailEnv(worlds, auto_reset=True)
+    obs = batch.reset()
+    for _ in range(40):
+        obs, _, _ = batch.step(actor.get_actions(obs))
+    logits, value = actor.forward(obs)
+    acts = actor.choose_actions(logits, obs["valid_actions"]).cpu().numpy()
+    lg_all, v_all = logits.cpu().numpy().copy(), value.cpu().numpy().copy()
+    assert np.isfinite(lg_all).all() and np.isfinite(v_all).all()
+    for e in sample:
+        one = {k: obs[k][e:e + 1].contiguous() for k in ("agent_attr", "forest", "adjacency", "node_order", "valid_actions")}
+        lg1, v1 = actor.forward(one)
+        assert (lg1[0].cpu().numpy() == lg_all[e]).all() and float(v1[0].item()) == float(v_all[e])
+        o = {k: v[0].cpu().numpy() for k, v in one.items()}
+        eo = obs["edge_order"][e].cpu().numpy()
+        want, wval = po.forward(actor.weights, o["agent_attr"][None], po.clean_forest(o["forest"])[None], o["adjacency"][None],
+                                o["node_order"][None], eo[None])
+        np.testing.assert_allclose(lg_all[e], want[0], rtol=0, atol=LOGIT_ATOL)
+        assert abs(float(v_all[e]) - float(wval[0])) < LOGIT_ATOL
+        safe = po.choice_margin(want[0], o["valid_actions"]) > 0.02
+        assert (acts[e][safe] == po.choose_actions(want[0], o["valid_actions"])[safe]).all()
