@@ -1,0 +1,114 @@
+"""Lock-step reset pipeline: environments that finish their episode are given a NEW world while the
+rest of the batch keeps stepping, instead of replaying the same world (FL_FLAG_AUTO_RESET).
+
+World generation stays what it is in the reference — Python (`sparse_rail_generator`, line and timetable generators,
+rail_env.py:260-357) — so it is taken off the critical path: a `WorldSource` hands out finished world dicts; `PackSource`
+cycles through pre-generated worlds, `GeneratorPool` runs any picklable `make_world(seed) -> world` function (e.g.
+`world_from_reference_env(make_env(...))` where flatland-rl is installed) in worker processes ahead of demand.  The
+expensive part of a reset, the per-target distance maps (distance_map.py:57-160: 16.9 s in Python at Test_14), is rebuilt
+on the GPU for the replaced slots only (`BatchedRailEnv.replace_worlds`).
+"""
+import multiprocessing as mp
+import queue
+
+
+class WorldSource:
+    def take(self, n):
+        """Up to n worlds that are ready now (never blocks)."""
+        raise NotImplementedError
+
+    def close(self):
+        pass
+
+
+class PackSource(WorldSource):
+    """Cycles through a list of pre-generated worlds (e.g. `load_worlds_npz`, `load_level`)."""
+
+    def __init__(self, worlds, start=0):
+        if not worlds:
+            raise ValueError("empty world list")
+        self.worlds, self.pos = list(worlds), int(start)
+
+    def take(self, n):
+        out = [self.worlds[(self.pos + k) % len(self.worlds)] for k in range(n)]
+        self.pos = (self.pos + n) % len(self.worlds)
+        return out
+
+
+def _pool_worker(make_world, seeds, out):
+    for seed in iter(seeds.get, None):
+        try:
+            out.put((seed, make_world(seed), None))
+        except Exception as e:  # noqa: BLE001 — reported to the consumer, the worker keeps going
+            out.put((seed, None, repr(e)))
+
+
+class GeneratorPool(WorldSource):
+    """Runs `make_world(seed)` in `n_workers` processes, `ahead` worlds in advance; worlds come back in completion
+    order.  `make_world` must be picklable (a module-level function)."""
+
+    def __init__(self, make_world, first_seed=0, n_workers=2, ahead=8, context="spawn"):
+        ctx = mp.get_context(context)
+        self._seeds, self._out = ctx.Queue(), ctx.Queue()
+        self._next_seed, self._pending, self.ahead = int(first_seed), 0, int(ahead)
+        self._procs = [ctx.Process(target=_pool_worker, args=(make_world, self._seeds, self._out), daemon=True)
+                       for _ in range(int(n_workers))]
+        for p in self._procs:
+            p.start()
+        self._refill()
+
+    def _refill(self):
+        while self._pending < self.ahead:
+            self._seeds.put(self._next_seed)
+            self._next_seed += 1
+            self._pending += 1
+
+    def take(self, n, timeout=0.0):
+        out = []
+        while len(out) < n:
+            try:
+                seed, world, err = self._out.get(timeout=timeout) if timeout else self._out.get_nowait()
+            except queue.Empty:
+                break
+            self._pending -= 1
+            if err is not None:
+                self._refill()
+                raise RuntimeError("world generator failed for seed %s: %s" % (seed, err))
+            out.append(world)
+        self._refill()
+        return out
+
+    def close(self):
+        for _ in self._procs:
+            self._seeds.put(None)
+        for p in self._procs:
+            p.join(timeout=5)
+            if p.is_alive():
+                p.terminate()
+
+
+class ResetPipeline:
+    """Drives a `BatchedRailEnv` (built with auto_reset=True and some `reserve`) so that finished environments get
+    fresh worlds from `source` when one is ready, and are reset in place otherwise."""
+
+    def __init__(self, batch, source):
+        self.batch, self.source = batch, source
+        self.replaced = 0
+
+    def reset(self):
+        return self.batch.reset()
+
+    def step(self, actions):
+        """One lock-step step; returns (obs, rewards, dones) like BatchedRailEnv.step.  Environments whose episode ended
+        in this step (dones[:, N]) are replaced before the next step when the source has worlds ready; their observation
+        in the returned dict is then already the new world's first observation."""
+        b = self.batch
+        obs, rewards, dones = b.step(actions)
+        finished = b.t["done_all"].nonzero().flatten().tolist()      # E bytes to the host: the one sync of the pipeline
+        if finished:
+            worlds = self.source.take(len(finished))
+            if worlds:
+                b.replace_worlds(finished[: len(worlds)], worlds)
+                self.replaced += len(worlds)
+                obs = b.observe()
+        return obs, rewards, dones
