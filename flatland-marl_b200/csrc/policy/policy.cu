@@ -35,6 +35,7 @@ constexpr int TILE = 128 * 128;   // bytes of a 128-row x 64-element bf16 tile (
 constexpr int P_STAGES = 2;
 constexpr int P_STAGE_BYTES = 4 * TILE;   // A tile + up to 384 rows of B
 constexpr int NODES = 32;         // node slots per tree in the h / c / fc / x scratch (31 used)
+constexpr int NULL_COPIES = 1024; // copies of the shared null-node row (one hot row serialises in its L2 slice)
 
 unsigned long long g_launches = 0;
 
@@ -58,6 +59,8 @@ struct LinArgs {
     const uint32_t *entries;    // MODE_TREE_F: level list (tree | node << 22 | first child << 27)
     const bf16 *cstate;         //              c of every node [tree][32][128]
     bf16 *fc;                   //              f * c_child     [tree][32][128]
+    const uint8_t *eflags;      //              per list entry: bit j = child j of the node is a null node (shared h / c row)
+    uint32_t null_off;          //              element offset of that shared row in h / c
 };
 
 // entry of a level list
@@ -166,7 +169,8 @@ __global__ void __launch_bounds__(MODE == MODE_LINEAR ? LIN_THREADS_TMA : LIN_TH
                     } else {
                         uint32_t t, v, ch0;
                         entry_decode(__ldg(p.entries + r / 3), t, v, ch0);
-                        off0[i] = ((t * NODES) + ch0 + (uint32_t)(r % 3)) * 128u;
+                        const uint32_t child = ch0 + (uint32_t)(r % 3);
+                        off0[i] = ((__ldg(p.eflags + r / 3) >> (r % 3)) & 1u) ? p.null_off + (t & (NULL_COPIES - 1)) * (NODES * 128u) : (t * NODES + child) * 128u;
                         off2[i] = (t * NODES + v) * 16u;
                     }
                 }
@@ -232,14 +236,16 @@ __global__ void __launch_bounds__(MODE == MODE_LINEAR ? LIN_THREADS_TMA : LIN_TH
             const uint32_t b = tl & 1;
             const int r = mt * 128 + q * 32 + lane;
             const bool valid = r < rows;
-            size_t orow = 0;
+            size_t orow = 0, crow = 0;
             if (valid) {
                 if (MODE == MODE_LINEAR) {
                     orow = (size_t)r * p.ldc + n0;
                 } else {
                     uint32_t t, v, ch0;
                     entry_decode(__ldg(p.entries + r / 3), t, v, ch0);
-                    orow = ((size_t)t * NODES + ch0 + (r % 3)) * 128;
+                    const uint32_t child = ch0 + (uint32_t)(r % 3);
+                    orow = ((size_t)t * NODES + child) * 128;
+                    crow = ((__ldg(p.eflags + r / 3) >> (r % 3)) & 1u) ? (size_t)p.null_off + (size_t)(t & (NULL_COPIES - 1)) * (NODES * 128) : orow;
                 }
             }
             float bias[32];
@@ -249,7 +255,7 @@ __global__ void __launch_bounds__(MODE == MODE_LINEAR ? LIN_THREADS_TMA : LIN_TH
             }
             uint32_t cw[16];
             if (MODE == MODE_TREE_F && valid) {
-                const uint4 *cin = reinterpret_cast<const uint4 *>(p.cstate + orow + cg * 32);
+                const uint4 *cin = reinterpret_cast<const uint4 *>(p.cstate + crow + cg * 32);
 #pragma unroll
                 for (int j = 0; j < 4; j++) *reinterpret_cast<uint4 *>(&cw[4 * j]) = cin[j];
             }
@@ -517,6 +523,8 @@ struct TreeArgs {
     int emb_ld;
     const bf16 *uiou, *wiou, *wc;
     const float *b_iou, *b_c;
+    const uint8_t *eflags;     // per list entry: bit j = child j of the node is a null node: its h is a shared row at null_off
+    uint32_t null_off;
 };
 
 __global__ void __launch_bounds__(416, 1) k_tree_p(const TreeArgs p) {
@@ -554,17 +562,19 @@ __global__ void __launch_bounds__(416, 1) k_tree_p(const TreeArgs p) {
         const uint32_t swz = (uint32_t)((c ^ (r0 & 7)) << 4) + (uint32_t)r0 * 128u;
         uint32_t it = 0;
         for (int mt = blockIdx.x; mt < mtiles; mt += gridDim.x) {
-            uint32_t offc[8], offx[8], ok[8];
+            uint32_t offc[8], offx[8], ok[8], nul[8], offn[8];
 #pragma unroll
             for (int i = 0; i < 8; i++) {
                 const int r = mt * 128 + r0 + 16 * i;
                 ok[i] = r < rows ? 16u : 0u;
-                offc[i] = offx[i] = 0;
+                offc[i] = offx[i] = nul[i] = offn[i] = 0;
                 if (ok[i]) {
                     uint32_t t, v, ch0;
                     entry_decode(__ldg(p.entries + r), t, v, ch0);
                     offc[i] = (t * NODES + ch0) * 128u;
                     offx[i] = (t * NODES + v) * 16u;
+                    nul[i] = __ldg(p.eflags + r);                      // which of the three children are null nodes
+                    offn[i] = p.null_off + (t & (NULL_COPIES - 1)) * (NODES * 128u);
                 }
             }
             for (int kk = kfirst; kk <= klast; kk++, it++) {
@@ -573,9 +583,12 @@ __global__ void __launch_bounds__(416, 1) k_tree_p(const TreeArgs p) {
                 const uint32_t dstA = smem_u32(smem + (size_t)s * P_STAGE_BYTES) + swz;
                 const uint32_t dstB = dstA + TILE;
                 if (kk < 6) {
+                    // child kk >> 1 of every parent: its own h row, or the shared row of the null nodes
+                    const int cj = kk >> 1;
                     const bf16 *src = p.h + kk * 64 + c * 8;
+                    const bf16 *nsrc = p.h + (kk & 1) * 64 + c * 8;
 #pragma unroll
-                    for (int i = 0; i < 8; i++) cp_async16(dstA + i * 2048, src + offc[i], ok[i]);
+                    for (int i = 0; i < 8; i++) cp_async16(dstA + i * 2048, ((nul[i] >> cj) & 1u) ? nsrc + offn[i] : src + offc[i], ok[i]);
                     const bf16 *wsrc = p.uiou + kk * 64 + c * 8;
 #pragma unroll 8
                     for (int i = 0; i < 24; i++) cp_async16(dstB + i * 2048, wsrc + (size_t)(r0 + 16 * i) * 384, 16);
@@ -708,24 +721,31 @@ __global__ void __launch_bounds__(416, 1) k_tree_p(const TreeArgs p) {
 // casts: agent_attr f32 [M][83] -> bf16 [M][128] (zero padded); forest f32 [M][31][12] -> bf16 [M][32][16] with
 // +inf -> -1 (eval_env.py:76) and zero padding.  One thread writes 16 bytes (attr) or one node's 32 bytes (x).
 __global__ void k_prep(const float *__restrict__ attr, const float *__restrict__ forest, bf16 *__restrict__ attr_b,
-                       bf16 *__restrict__ x, long long M) {
+                       bf16 *__restrict__ x, uint32_t *__restrict__ nullmask, long long M) {
     const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    const long long n_attr = M * 16, n_x = M * NODES;
-    if (tid < n_attr) {
+    const long long n_attr = (M * 16 + 31) & ~31LL, n_x = (M + NULL_COPIES) * NODES;     // x part: one warp per tree (32 node slots)
+    if (tid < M * 16) {
         const long long m = tid >> 4;
         const int k0 = (int)(tid & 15) * 8;
         float f[8];
 #pragma unroll
         for (int j = 0; j < 8; j++) f[j] = k0 + j < 83 ? attr[m * 83 + k0 + j] : 0.0f;
         reinterpret_cast<uint4 *>(attr_b)[tid] = make_uint4(pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]), pack_bf16(f[4], f[5]), pack_bf16(f[6], f[7]));
-    } else if (tid < n_attr + n_x) {
+    } else if (tid >= n_attr && tid < n_attr + n_x) {
         const long long u = tid - n_attr;
         const long long m = u / NODES;
         const int node = (int)(u % NODES);
         float f[12];
 #pragma unroll
         for (int j = 0; j < 12; j++) f[j] = 0.0f;
-        if (node < 31) {
+        bool real = node < 31;
+        if (m >= M) {
+            // trees M.. are not trees: their node 1 carries the null-node features (treeobs.cpp null node: seven inf, five -1),
+            // so that the leaf kernel computes the h / c row all null nodes share
+            real = node == 1;
+#pragma unroll
+            for (int j = 0; j < 12; j++) f[j] = real ? -1.0f : 0.0f;
+        } else if (real) {
             const float4 *src = reinterpret_cast<const float4 *>(forest + (m * 31 + node) * 12);
 #pragma unroll
             for (int j = 0; j < 3; j++) {
@@ -735,17 +755,22 @@ __global__ void k_prep(const float *__restrict__ attr, const float *__restrict__
 #pragma unroll
             for (int j = 0; j < 12; j++) f[j] = f[j] == CUDART_INF_F ? -1.0f : f[j];
         }
+        bool is_null = real;
+#pragma unroll
+        for (int j = 0; j < 12; j++) is_null = is_null && f[j] == -1.0f;
+        const uint32_t mask = __ballot_sync(0xFFFFFFFFu, is_null && node != 0 && m < M);   // the root is never shared
+        if (node == 0 && m < M) nullmask[m] = mask;
         // column 12 is the constant 1 that multiplies the bias column of W_iou / W_f (the biases ride in the MMA)
         uint4 *dst = reinterpret_cast<uint4 *>(x + u * 16);
         dst[0] = make_uint4(pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]), pack_bf16(f[4], f[5]), pack_bf16(f[6], f[7]));
-        dst[1] = make_uint4(pack_bf16(f[8], f[9]), pack_bf16(f[10], f[11]), pack_bf16(node < 31 ? 1.0f : 0.0f, 0.0f), 0u);
+        dst[1] = make_uint4(pack_bf16(f[8], f[9]), pack_bf16(f[10], f[11]), pack_bf16(real ? 1.0f : 0.0f, 0.0f), 0u);
     }
 }
 
 // Level lists of the Tree-LSTM: every node with node_order == n >= 0 goes to list n as
 // tree | node << 22 | first child << 27.  The order inside a list is arbitrary (rows are independent).
-__global__ void k_tree_plan(const int32_t *__restrict__ adjacency, const int32_t *__restrict__ node_order, uint32_t *lists,
-                            int *counts, long long M) {
+__global__ void k_tree_plan(const int32_t *__restrict__ adjacency, const int32_t *__restrict__ node_order,
+                            const uint32_t *__restrict__ nullmask, uint32_t *lists, uint8_t *eflags, int *counts, long long M) {
     __shared__ int cnt[FL_POLICY_MAX_LEVELS], base[FL_POLICY_MAX_LEVELS];
     if (threadIdx.x < FL_POLICY_MAX_LEVELS) cnt[threadIdx.x] = 0;
     __syncthreads();
@@ -753,6 +778,7 @@ __global__ void k_tree_plan(const int32_t *__restrict__ adjacency, const int32_t
     unsigned char child0[32];
     unsigned short pos[31];
     signed char lvl[31];
+    uint32_t nm = 0;
     if (t < M) {
 #pragma unroll 1
         for (int v = 0; v < 32; v++) child0[v] = 0;
@@ -761,24 +787,33 @@ __global__ void k_tree_plan(const int32_t *__restrict__ adjacency, const int32_t
             const int par = adjacency[(t * 30 + 3 * g) * 3];
             if (par >= 0 && par < 31) child0[par] = (unsigned char)(3 * g + 1);
         }
+        nm = nullmask[t];
 #pragma unroll 1
         for (int v = 0; v < 31; v++) {
             int o = node_order[t * 31 + v];
             if (o >= FL_POLICY_MAX_LEVELS) o = -1;
+            if (o == 0 && ((nm >> v) & 1u)) o = -1;       // a null leaf: its h / c is the shared row, nothing to compute
             lvl[v] = (signed char)o;
             if (o >= 0) pos[v] = (unsigned short)atomicAdd(&cnt[o], 1);
         }
+    } else if (t < M + NULL_COPIES) {
+        // the shared null-node rows: "trees" M.., node 1 (k_prep), one extra leaf each
+        for (int v = 0; v < 31; v++) lvl[v] = -1;
+        for (int v = 0; v < 32; v++) child0[v] = 0;
+        lvl[1] = 0;
+        pos[1] = (unsigned short)atomicAdd(&cnt[0], 1);
     }
     __syncthreads();
     if (threadIdx.x < FL_POLICY_MAX_LEVELS) base[threadIdx.x] = cnt[threadIdx.x] ? atomicAdd(&counts[threadIdx.x], cnt[threadIdx.x]) : 0;
     __syncthreads();
-    if (t < M) {
+    if (t < M + NULL_COPIES) {
 #pragma unroll 1
         for (int v = 0; v < 31; v++) {
             const int o = lvl[v];
             if (o < 0) continue;
-            const size_t off = o == 0 ? 0 : (size_t)21 * M + (size_t)(o - 1) * 10 * M;
+            const size_t off = o == 0 ? 0 : (size_t)21 * M + NULL_COPIES + (size_t)(o - 1) * 10 * M;
             lists[off + base[o] + pos[v]] = (uint32_t)t | ((uint32_t)v << 22) | ((uint32_t)child0[v] << 27);
+            eflags[off + base[o] + pos[v]] = (uint8_t)(o > 0 ? (nm >> child0[v]) & 7u : 0u);
         }
     }
 }
@@ -1113,7 +1148,8 @@ int launch_linear(const bf16 *a0, int lda0, int k0, const bf16 *a1, int lda1, in
 
 struct Workspace {
     bf16 *x, *h, *c, *fc, *attr, *a1, *a2, *emb, *qkv, *atto, *proj, *ta, *tb, *y1, *y2;
-    uint32_t *lists;
+    uint32_t *lists, *nullmask;
+    uint8_t *eflags;
     int *counts;
     size_t bytes;
 };
@@ -1124,10 +1160,12 @@ Workspace carve(void *base, long long M) {
     auto take = [&](size_t n) { size_t o = off; off += (n + 255) & ~(size_t)255; return (uint8_t *)base + o; };
     const size_t m = (size_t)M;
     w.counts = (int *)take(64 * sizeof(int));
-    w.lists = (uint32_t *)take((21 + 10 * (FL_POLICY_MAX_LEVELS - 1)) * m * sizeof(uint32_t));
-    w.x = (bf16 *)take(m * NODES * 16 * 2);
-    w.h = (bf16 *)take(m * NODES * 128 * 2);
-    w.c = (bf16 *)take(m * NODES * 128 * 2);
+    w.lists = (uint32_t *)take(((21 + 10 * (FL_POLICY_MAX_LEVELS - 1)) * m + NULL_COPIES) * sizeof(uint32_t));
+    w.nullmask = (uint32_t *)take((m + 1) * sizeof(uint32_t));
+    w.eflags = (uint8_t *)take((21 + 10 * (FL_POLICY_MAX_LEVELS - 1)) * m + NULL_COPIES);
+    w.x = (bf16 *)take((m + NULL_COPIES) * NODES * 16 * 2);          // extra "trees": the shared null-node rows
+    w.h = (bf16 *)take((m + NULL_COPIES) * NODES * 128 * 2);
+    w.c = (bf16 *)take((m + NULL_COPIES) * NODES * 128 * 2);
     w.fc = (bf16 *)take(m * NODES * 128 * 2);
     w.attr = (bf16 *)take(m * 128 * 2);
     w.a1 = (bf16 *)take(m * 256 * 2);
@@ -1182,7 +1220,7 @@ int fl_policy_forward(const FlPolicyWeights *w, void *d_workspace, size_t worksp
     int rc = setup();
     if (rc) return rc;
     const long long M = E * N;
-    if (M <= 0 || M > 0x3FFFFF || !w || !d_workspace) return -1;   // 22-bit tree ids in the level lists
+    if (M <= 0 || M > 0x3FFFFF - NULL_COPIES || !w || !d_workspace) return -1;   // 22-bit tree ids in the level lists
     Workspace ws = carve(d_workspace, M);
     if (workspace_bytes < ws.bytes) return -1;
     cudaStream_t st = (cudaStream_t)stream;
@@ -1191,14 +1229,15 @@ int fl_policy_forward(const FlPolicyWeights *w, void *d_workspace, size_t worksp
     if (e == cudaSuccess) e = cudaMemsetAsync(ws.emb, 0, (size_t)M * 256 * 2, st);
     if (e != cudaSuccess) return (int)e;
     {
-        const long long total = M * 16 + M * NODES;
-        k_prep<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(d_agent_attr, d_forest, ws.attr, ws.x, M);
-        k_tree_plan<<<(unsigned)((M + 127) / 128), 128, 0, st>>>(d_adjacency, d_node_order, ws.lists, ws.counts, M);
+        const long long total = ((M * 16 + 31) & ~31LL) + (M + NULL_COPIES) * NODES;
+        k_prep<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(d_agent_attr, d_forest, ws.attr, ws.x, ws.nullmask, M);
+        k_tree_plan<<<(unsigned)((M + NULL_COPIES + 127) / 128), 128, 0, st>>>(d_adjacency, d_node_order, ws.nullmask, ws.lists, ws.eflags, ws.counts, M);
         g_launches += 2;
     }
     // ---- Tree-LSTM, level by level (TreeLSTM.py:54-56) ----
     for (int lv = 0; lv < FL_POLICY_MAX_LEVELS; lv++) {
-        const uint32_t *list = ws.lists + (lv == 0 ? 0 : (size_t)21 * M + (size_t)(lv - 1) * 10 * M);
+        const uint32_t *list = ws.lists + (lv == 0 ? 0 : (size_t)21 * M + NULL_COPIES + (size_t)(lv - 1) * 10 * M);
+        const uint32_t null_off = (uint32_t)((M * NODES + 1) * 128);
         if (lv > 0) {
             LinArgs p = {};
             p.a0 = ws.h; p.a2 = ws.x;
@@ -1206,6 +1245,7 @@ int fl_policy_forward(const FlPolicyWeights *w, void *d_workspace, size_t worksp
             p.w = (const bf16 *)w->tree_ufwf; p.ldw = 144; p.bias = w->tree_b_f;
             p.rows = 0; p.rows_dev = ws.counts + lv; p.rows_mul = 3;
             p.entries = list; p.cstate = ws.c; p.fc = ws.fc;
+            p.eflags = ws.eflags + (list - ws.lists); p.null_off = null_off;
             p.stages = lin_stages(3);
             p.dbg = (lv == 1 && g_leaf_dbg && getenv("FL_POLICY_DBG_F")) ? g_leaf_dbg : nullptr;   // tuning only
             static CUtensorMap dummy;
@@ -1227,6 +1267,7 @@ int fl_policy_forward(const FlPolicyWeights *w, void *d_workspace, size_t worksp
         t.emb = ws.emb + 128; t.emb_ld = 256;
         t.uiou = (const bf16 *)w->tree_uiou; t.wiou = (const bf16 *)w->tree_wiou; t.wc = (const bf16 *)w->tree_wc;
         t.b_iou = w->tree_b_iou; t.b_c = w->tree_b_c;
+        t.eflags = ws.eflags + (list - ws.lists); t.null_off = null_off;
         k_tree_p<<<g_num_sms, 416, 1024 + P_STAGES * P_STAGE_BYTES + 2 * 128 * OUT_PITCH + 1024, st>>>(t);
         g_launches++;
     }
