@@ -80,7 +80,9 @@ constexpr int OUT_PITCH = 272;          // bytes between rows of the staged outp
 // MODE_LINEAR: A (one or two dense sources) and W arrive as TMA tiles (tensor maps ta0 / ta1 / tw, one elected
 // producer thread); MODE_TREE_F: rows are gathered by 128 producer threads with cp.async (the LDGSTS path tops out
 // near 16 B/clk per SM, so it is kept for the gathers only).
-template <int MODE>
+// BN = output columns per CTA: 128, or 256 for the dense layers with K <= 256 (one 128x256x16 MMA reads 96 B/clk of
+// shared memory instead of 128 and amortises the per-k-block hand-off; A is read half as often).
+template <int MODE, int BN>
 __global__ void __launch_bounds__(MODE == MODE_LINEAR ? LIN_THREADS_TMA : LIN_THREADS, 1) k_lin(const LinArgs p, const __grid_constant__ CUtensorMap ta0,
                                                         const __grid_constant__ CUtensorMap ta1, const __grid_constant__ CUtensorMap tw) {
     extern __shared__ uint8_t smem_raw[];
@@ -91,7 +93,8 @@ __global__ void __launch_bounds__(MODE == MODE_LINEAR ? LIN_THREADS_TMA : LIN_TH
     const int mtiles = (rows + 127) >> 7;
     if ((int)blockIdx.x >= mtiles) return;
     uint8_t *sW = smem;
-    uint8_t *sA = smem + (size_t)nkb * TILE;
+    constexpr int WT = BN / 128;                            // 16 KB tiles per k-block of W
+    uint8_t *sA = smem + (size_t)nkb * WT * TILE;
     uint8_t *sC = sA + (size_t)S * TILE;                 // output tile staging: 128 rows, pitch OUT_PITCH
     unsigned long long *rowptr = (unsigned long long *)(sC + 128 * OUT_PITCH);   // MODE_TREE_F: destination of every row
     uint64_t *bars = (uint64_t *)(rowptr + 128);
@@ -99,7 +102,7 @@ __global__ void __launch_bounds__(MODE == MODE_LINEAR ? LIN_THREADS_TMA : LIN_TH
     uint64_t *tfull = wfull + 1, *tempty = tfull + 2;
     uint32_t *tmem_slot = (uint32_t *)(tempty + 2);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int n0 = blockIdx.y * 128;
+    const int n0 = blockIdx.y * BN;
     if (p.dbg && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) p.dbg[3] = clock64();
 
     if (warp == 16) {
@@ -111,7 +114,7 @@ __global__ void __launch_bounds__(MODE == MODE_LINEAR ? LIN_THREADS_TMA : LIN_TH
             mbar_init_fence();
         }
         __syncwarp();
-        tmem_alloc(tmem_slot, 256);
+        tmem_alloc(tmem_slot, 2 * BN);
     }
     fence_before_sync();
     __syncthreads();
@@ -123,8 +126,9 @@ __global__ void __launch_bounds__(MODE == MODE_LINEAR ? LIN_THREADS_TMA : LIN_TH
         if (threadIdx.x == 544) {
             tma_prefetch_desc(&ta0);
             tma_prefetch_desc(&tw);
-            mbar_expect_tx(wfull, (uint32_t)nkb * TILE);
-            for (int kb = 0; kb < nkb; kb++) tma_load_2d(smem_u32(sW + (size_t)kb * TILE), &tw, kb * 64, n0, wfull);
+            mbar_expect_tx(wfull, (uint32_t)nkb * WT * TILE);
+            for (int kb = 0; kb < nkb; kb++)
+                for (int hh = 0; hh < WT; hh++) tma_load_2d(smem_u32(sW + (size_t)(kb * WT + hh) * TILE), &tw, kb * 64, n0 + hh * 128, wfull);
             uint32_t it = 0;
             for (int mt = blockIdx.x; mt < mtiles; mt += gridDim.x) {
                 for (int kb = 0; kb < nkb; kb++, it++) {
@@ -205,7 +209,7 @@ __global__ void __launch_bounds__(MODE == MODE_LINEAR ? LIN_THREADS_TMA : LIN_TH
             mbar_wait(wfull, 0);
             fence_after_sync();
             if (dbg) p.dbg[1] = clock64();
-            const uint32_t idesc = idesc_bf16(128, 128);
+            const uint32_t idesc = idesc_bf16(128, BN);
             uint32_t it = 0, tl = 0;
             for (int mt = blockIdx.x; mt < mtiles; mt += gridDim.x, tl++) {
                 const uint32_t b = tl & 1;
@@ -219,9 +223,9 @@ __global__ void __launch_bounds__(MODE == MODE_LINEAR ? LIN_THREADS_TMA : LIN_TH
                     if (dbg && tl < 8 && kb == 0) p.dbg[8 + tl * 4 + 1] = clock64();
                     if (dbg && tl < 8 && kb == nkb - 1) p.dbg[8 + tl * 4 + 2] = clock64();
                     const uint64_t ad = desc_sw128(smem_u32(sA + (size_t)s * TILE));
-                    const uint64_t bd = desc_sw128(smem_u32(sW + (size_t)kb * TILE));
+                    const uint64_t bd = desc_sw128(smem_u32(sW + (size_t)kb * WT * TILE));
                     const int nk = (p.k16 && kb == nkb - 1) ? 1 : 4;
-                    for (int k = 0; k < nk; k++) mma_bf16(tmem + b * 128, ad + 2 * k, bd + 2 * k, idesc, (uint32_t)((kb | k) != 0));
+                    for (int k = 0; k < nk; k++) mma_bf16(tmem + b * BN, ad + 2 * k, bd + 2 * k, idesc, (uint32_t)((kb | k) != 0));
                     mma_commit(&empty[s]);
                 }
                 mma_commit(&tfull[b]);
@@ -249,7 +253,7 @@ __global__ void __launch_bounds__(MODE == MODE_LINEAR ? LIN_THREADS_TMA : LIN_TH
                 }
             }
             float bias[32];
-            if (MODE == MODE_LINEAR) {
+            if (MODE == MODE_LINEAR && WT == 1) {
 #pragma unroll
                 for (int j = 0; j < 8; j++) *reinterpret_cast<float4 *>(&bias[4 * j]) = __ldg(reinterpret_cast<const float4 *>(p.bias + n0 + cg * 32) + j);
             }
@@ -261,15 +265,24 @@ __global__ void __launch_bounds__(MODE == MODE_LINEAR ? LIN_THREADS_TMA : LIN_TH
             }
             mbar_wait(&tfull[b], (tl >> 1) & 1);
             fence_after_sync();
-            const uint32_t tbase = tmem + ((uint32_t)(q * 32) << 16) + b * 128 + cg * 32;
             const bool dbg = p.dbg && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0 && tl < 8;
             if (dbg) p.dbg[48 + tl * 4] = clock64();
+#pragma unroll 1
+            for (int round = 0; round < WT; round++) {          // 128 output columns per round
+            const int nr = n0 + round * 128;
+            const uint32_t tbase = tmem + ((uint32_t)(q * 32) << 16) + b * BN + round * 128 + cg * 32;
             uint32_t v[32];
             tmem_ld16(tbase, v);
             tmem_ld16(tbase + 16, v + 16);
+            if (WT > 1) {
+#pragma unroll
+                for (int j = 0; j < 8; j++) *reinterpret_cast<float4 *>(&bias[4 * j]) = __ldg(reinterpret_cast<const float4 *>(p.bias + nr + cg * 32) + j);
+            }
             tmem_ld_wait();
-            fence_before_sync();
-            mbar_arrive(&tempty[b]);      // the accumulator is in registers: the MMA warp may overwrite the buffer
+            if (round == WT - 1) {
+                fence_before_sync();
+                mbar_arrive(&tempty[b]);  // the accumulator is in registers: the MMA warp may overwrite the buffer
+            }
             if (dbg) p.dbg[48 + tl * 4 + 1] = clock64();
             uint32_t ow[16];
 #pragma unroll
@@ -306,19 +319,20 @@ __global__ void __launch_bounds__(MODE == MODE_LINEAR ? LIN_THREADS_TMA : LIN_TH
                 const uint4 val = ld_shared_v4(smem_u32(sC) + (uint32_t)row * OUT_PITCH + cc * 16);
                 if (MODE == MODE_LINEAR) {
                     const int gr = mt * 128 + row;
-                    if (gr < rows) *reinterpret_cast<uint4 *>(p.out + (size_t)gr * p.ldc + n0 + cc * 8) = val;
+                    if (gr < rows) *reinterpret_cast<uint4 *>(p.out + (size_t)gr * p.ldc + nr + cc * 8) = val;
                 } else {
                     const unsigned long long dst = rowptr[row];
                     if (dst) *reinterpret_cast<uint4 *>(dst + cc * 16) = val;
                 }
             }
+            }   // round
             if (dbg) p.dbg[48 + tl * 4 + 2] = clock64();
         }
     }
     fence_before_sync();
     __syncthreads();
     if (p.dbg && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) p.dbg[2] = clock64();
-    if (warp == 16) tmem_dealloc(tmem, 256);
+    if (warp == 16) tmem_dealloc(tmem, 2 * BN);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -1091,8 +1105,9 @@ int setup() {
         const int lin_max = 1024 + 11 * TILE + 128 * OUT_PITCH + 1024 + 512;
         const int p_bytes = 1024 + P_STAGES * P_STAGE_BYTES + 2 * 128 * OUT_PITCH + 1024;
         const int leaf_bytes = 1024 + (3 + LEAF_STAGES) * TILE + 4 * 128 * LEAF_PITCH + 2048;
-        cudaError_t e = cudaFuncSetAttribute(k_lin<MODE_LINEAR>, cudaFuncAttributeMaxDynamicSharedMemorySize, lin_max);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(k_lin<MODE_TREE_F>, cudaFuncAttributeMaxDynamicSharedMemorySize, lin_max);
+        cudaError_t e = cudaFuncSetAttribute(k_lin<MODE_LINEAR, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, lin_max);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(k_lin<MODE_LINEAR, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, lin_max);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(k_lin<MODE_TREE_F, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, lin_max);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(k_tree_p, cudaFuncAttributeMaxDynamicSharedMemorySize, p_bytes);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(k_attn_mma, cudaFuncAttributeMaxDynamicSharedMemorySize, ATTN_SMEM);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(k_tree_leaf, cudaFuncAttributeMaxDynamicSharedMemorySize, leaf_bytes);
@@ -1102,6 +1117,7 @@ int setup() {
     return 0;
 }
 
+// nkb = 16 KB tiles of resident W; the A ring takes what is left of 11 tiles beside the staging tile
 int lin_stages(int nkb) { return nkb <= 3 ? LIN_MAX_STAGES : 11 - nkb; }
 size_t lin_smem(int nkb) { return 1024 + (size_t)(nkb + lin_stages(nkb)) * TILE + 128 * OUT_PITCH + 1024 + 512; }
 
@@ -1127,9 +1143,11 @@ int launch_linear(const bf16 *a0, int lda0, int k0, const bf16 *a1, int lda1, in
     p.w = w; p.ldw = k0 + k1; p.bias = bias;
     p.rows = (int)M; p.rows_dev = nullptr; p.rows_mul = 1; p.act = act;
     p.out = out; p.ldc = ldc;
-    p.stages = lin_stages(p.kb0 + p.kb1);
+    const bool wide = N % 256 == 0 && p.kb0 + p.kb1 <= 4 && !getenv("FL_POLICY_BN128");   // 256 columns per CTA
+    const int wtiles = (p.kb0 + p.kb1) * (wide ? 2 : 1);
+    p.stages = lin_stages(wtiles);
     p.dbg = g_dbg;
-    const int ny = N / 128;
+    const int ny = N / (wide ? 256 : 128);
     const int mtiles = (int)((M + 127) / 128);
     int nx = g_num_sms / ny;
     if (nx < 1) nx = 1;
@@ -1141,7 +1159,8 @@ int launch_linear(const bf16 *a0, int lda0, int k0, const bf16 *a1, int lda1, in
     if (!rc) rc = make_tmap(&tw, w, (unsigned long long)N, (unsigned long long)(k0 + k1), (unsigned long long)(k0 + k1));
     if (rc) return rc;
     if (!k1) ta1 = ta0;
-    k_lin<MODE_LINEAR><<<dim3(nx, ny), LIN_THREADS_TMA, lin_smem(p.kb0 + p.kb1), st>>>(p, ta0, ta1, tw);
+    if (wide) k_lin<MODE_LINEAR, 256><<<dim3(nx, ny), LIN_THREADS_TMA, lin_smem(wtiles), st>>>(p, ta0, ta1, tw);
+    else k_lin<MODE_LINEAR, 128><<<dim3(nx, ny), LIN_THREADS_TMA, lin_smem(wtiles), st>>>(p, ta0, ta1, tw);
     g_launches++;
     return (int)cudaGetLastError();
 }
@@ -1249,7 +1268,7 @@ int fl_policy_forward(const FlPolicyWeights *w, void *d_workspace, size_t worksp
             p.stages = lin_stages(3);
             p.dbg = (lv == 1 && g_leaf_dbg && getenv("FL_POLICY_DBG_F")) ? g_leaf_dbg : nullptr;   // tuning only
             static CUtensorMap dummy;
-            k_lin<MODE_TREE_F><<<dim3(g_num_sms, 1), LIN_THREADS, lin_smem(3), st>>>(p, dummy, dummy, dummy);
+            k_lin<MODE_TREE_F, 128><<<dim3(g_num_sms, 1), LIN_THREADS, lin_smem(3), st>>>(p, dummy, dummy, dummy);
             g_launches++;
         }
         if (lv == 0) {
@@ -1298,8 +1317,8 @@ int fl_policy_forward(const FlPolicyWeights *w, void *d_workspace, size_t worksp
             k_attn_mma<<<dim3(tiles, FL_POLICY_HEADS), 128, ATTN_SMEM, st>>>(at, tq);
             g_launches++;
         }
-        if ((rc = launch_linear(ws.atto, 256, 256, nullptr, 0, 0, (const bf16 *)w->tf_wo[l], w->tf_bo[l], ws.proj, 256, M, 256, 0, st))) return rc;
-        if ((rc = launch_linear(tin, 256, 256, ws.proj, 256, 256, (const bf16 *)w->tf_wm[l], w->tf_bm[l], touts[l], 256, M, 256, 1, st))) return rc;
+        // out_proj is folded into att_mlp's weights at pack time (policy.py:pack_weights): cat(input, heads) -> GELU
+        if ((rc = launch_linear(tin, 256, 256, ws.atto, 256, 256, (const bf16 *)w->tf_wm[l], w->tf_bm[l], touts[l], 256, M, 256, 1, st))) return rc;
         tin = touts[l];
     }
     // ---- actor / critic heads (net_tree.py:56-71, 100-110) ----

@@ -104,8 +104,15 @@ def pack_weights(w):
     for l in range(LAYERS):
         p = "transformer.%d." % l
         d["tf_wqkv%d" % l], d["tf_bqkv%d" % l] = w[p + "attention.in_proj_weight"], w[p + "attention.in_proj_bias"]
-        d["tf_wo%d" % l], d["tf_bo%d" % l] = w[p + "attention.out_proj.weight"], w[p + "attention.out_proj.bias"]
-        d["tf_wm%d" % l], d["tf_bm%d" % l] = w[p + "att_mlp.0.weight"], w[p + "att_mlp.0.bias"]
+        wo, bo = w[p + "attention.out_proj.weight"].astype(np.float64), w[p + "attention.out_proj.bias"].astype(np.float64)
+        wm, bm = w[p + "att_mlp.0.weight"].astype(np.float64), w[p + "att_mlp.0.bias"].astype(np.float64)
+        d["tf_wo%d" % l], d["tf_bo%d" % l] = wo, bo
+        # Transformer.forward (net_tree.py:20-32) applies att_mlp to cat(input, out_proj(heads)) with nothing in between:
+        # cat(x, a Wo^T + bo) [W1 | W2]^T = x W1^T + a (W2 Wo)^T + (bm + W2 bo) — the out-projection is folded into the
+        # second half of att_mlp's weights here, in float64, and the kernels run one layer instead of two
+        e = wo.shape[0]
+        d["tf_wm%d" % l] = np.concatenate([wm[:, :e], wm[:, e:] @ wo], axis=1)
+        d["tf_bm%d" % l] = bm + wm[:, e:] @ bo
     return {k: np.ascontiguousarray(v, dtype=np.float32) for k, v in d.items()}
 
 

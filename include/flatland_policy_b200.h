@@ -53,10 +53,11 @@ typedef struct FlPolicyWeights {
     const float *attr_b[4];
     const uint16_t *tf_wqkv[FL_POLICY_LAYERS]; /* [768][256] transformer.l.attention.in_proj_weight */
     const float *tf_bqkv[FL_POLICY_LAYERS];
-    const uint16_t *tf_wo[FL_POLICY_LAYERS];   /* [256][256] attention.out_proj.weight */
+    const uint16_t *tf_wo[FL_POLICY_LAYERS];   /* [256][256] attention.out_proj.weight (kept for reference, not read: folded below) */
     const float *tf_bo[FL_POLICY_LAYERS];
-    const uint16_t *tf_wm[FL_POLICY_LAYERS];   /* [256][512] att_mlp.0.weight */
-    const float *tf_bm[FL_POLICY_LAYERS];
+    const uint16_t *tf_wm[FL_POLICY_LAYERS];   /* [256][512] att_mlp.0.weight with the out-projection folded in:
+                                                  [W1 | W2 Wo], so that the layer reads cat(input, attention heads) */
+    const float *tf_bm[FL_POLICY_LAYERS];      /* att_mlp.0.bias + W2 out_proj.bias */
     const uint16_t *head_w1;    /* [512][512] rows 0..255 actor_net.0.weight, rows 256..511 critic_net.0.weight */
     const float *head_b1;       /* [512] */
     const uint16_t *head_w2a;   /* [128][256] actor_net.2.weight */
