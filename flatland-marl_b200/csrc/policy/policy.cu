@@ -97,7 +97,9 @@ __global__ void __launch_bounds__(MODE == MODE_LINEAR ? LIN_THREADS_TMA : LIN_TH
     uint8_t *sA = smem + (size_t)nkb * WT * TILE;
     uint8_t *sC = sA + (size_t)S * TILE;                 // output tile staging: 128 rows, pitch OUT_PITCH
     unsigned long long *rowptr = (unsigned long long *)(sC + 128 * OUT_PITCH);   // MODE_TREE_F: destination of every row
-    uint64_t *bars = (uint64_t *)(rowptr + 128);
+    uint8_t *sCc = (uint8_t *)(rowptr + 128);              // MODE_TREE_F: c of the tile's child rows, pitch OUT_PITCH
+    uint32_t *crowoff = (uint32_t *)(sCc + (MODE == MODE_TREE_F ? 128 * OUT_PITCH : 0));
+    uint64_t *bars = (uint64_t *)(crowoff + (MODE == MODE_TREE_F ? 128 : 0));
     uint64_t *full = bars, *empty = bars + LIN_MAX_STAGES, *wfull = bars + 2 * LIN_MAX_STAGES;
     uint64_t *tfull = wfull + 1, *tempty = tfull + 2;
     uint32_t *tmem_slot = (uint32_t *)(tempty + 2);
@@ -258,10 +260,28 @@ __global__ void __launch_bounds__(MODE == MODE_LINEAR ? LIN_THREADS_TMA : LIN_TH
                 for (int j = 0; j < 8; j++) *reinterpret_cast<float4 *>(&bias[4 * j]) = __ldg(reinterpret_cast<const float4 *>(p.bias + n0 + cg * 32) + j);
             }
             uint32_t cw[16];
-            if (MODE == MODE_TREE_F && valid) {
-                const uint4 *cin = reinterpret_cast<const uint4 *>(p.cstate + crow + cg * 32);
+            if (MODE == MODE_TREE_F) {
+                // c of the 128 child rows: fetched row-contiguously (16 lanes per 256-byte row) into shared memory, then
+                // every thread picks up its own 64 bytes (a direct read is 32 rows x 16 bytes per instruction)
+                if (cg == 0) crowoff[q * 32 + lane] = valid ? (uint32_t)crow : 0xFFFFFFFFu;
+                named_bar_sync(3, 512);
+                const int te0 = warp * 32 + lane;
+                uint4 cv[4];
 #pragma unroll
-                for (int j = 0; j < 4; j++) *reinterpret_cast<uint4 *>(&cw[4 * j]) = cin[j];
+                for (int j = 0; j < 4; j++) {
+                    const int ci = te0 + 512 * j, row = ci >> 4, cc = ci & 15;
+                    const uint32_t off = crowoff[row];
+                    cv[j] = off != 0xFFFFFFFFu ? __ldg(reinterpret_cast<const uint4 *>(p.cstate + off) + cc) : make_uint4(0u, 0u, 0u, 0u);
+                }
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    const int ci = te0 + 512 * j, row = ci >> 4, cc = ci & 15;
+                    st_shared_v4(smem_u32(sCc) + (uint32_t)row * OUT_PITCH + cc * 16, cv[j].x, cv[j].y, cv[j].z, cv[j].w);
+                }
+                named_bar_sync(4, 512);
+                const uint32_t crd = smem_u32(sCc) + (uint32_t)(q * 32 + lane) * OUT_PITCH + cg * 64;
+#pragma unroll
+                for (int j = 0; j < 4; j++) *reinterpret_cast<uint4 *>(&cw[4 * j]) = ld_shared_v4(crd + j * 16);
             }
             mbar_wait(&tfull[b], (tl >> 1) & 1);
             fence_after_sync();
@@ -1107,7 +1127,7 @@ int setup() {
         const int leaf_bytes = 1024 + (3 + LEAF_STAGES) * TILE + 4 * 128 * LEAF_PITCH + 2048;
         cudaError_t e = cudaFuncSetAttribute(k_lin<MODE_LINEAR, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, lin_max);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(k_lin<MODE_LINEAR, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, lin_max);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(k_lin<MODE_TREE_F, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, lin_max);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(k_lin<MODE_TREE_F, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 1024 + 9 * TILE + 2 * 128 * OUT_PITCH + 2048 + 512);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(k_tree_p, cudaFuncAttributeMaxDynamicSharedMemorySize, p_bytes);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(k_attn_mma, cudaFuncAttributeMaxDynamicSharedMemorySize, ATTN_SMEM);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(k_tree_leaf, cudaFuncAttributeMaxDynamicSharedMemorySize, leaf_bytes);
@@ -1265,10 +1285,10 @@ int fl_policy_forward(const FlPolicyWeights *w, void *d_workspace, size_t worksp
             p.rows = 0; p.rows_dev = ws.counts + lv; p.rows_mul = 3;
             p.entries = list; p.cstate = ws.c; p.fc = ws.fc;
             p.eflags = ws.eflags + (list - ws.lists); p.null_off = null_off;
-            p.stages = lin_stages(3);
+            p.stages = 6;                                   // W 3 tiles + 6 stages + output and c staging tiles
             p.dbg = (lv == 1 && g_leaf_dbg && getenv("FL_POLICY_DBG_F")) ? g_leaf_dbg : nullptr;   // tuning only
             static CUtensorMap dummy;
-            k_lin<MODE_TREE_F, 128><<<dim3(g_num_sms, 1), LIN_THREADS, lin_smem(3), st>>>(p, dummy, dummy, dummy);
+            k_lin<MODE_TREE_F, 128><<<dim3(g_num_sms, 1), LIN_THREADS, 1024 + 9 * TILE + 2 * 128 * OUT_PITCH + 2048 + 512, st>>>(p, dummy, dummy, dummy);
             g_launches++;
         }
         if (lv == 0) {
