@@ -1037,39 +1037,57 @@ __global__ void __launch_bounds__(128, 2) k_attn_mma(const AttnArgs p, const __g
     if (warp == 0) tmem_dealloc(tmem, 256);
 }
 
-// Last layers: logits = actor_net.4(y2[:, :128]), value = mean over agents of critic_net.4(y2[:, 128:]).
-__global__ void __launch_bounds__(128) k_head_final(const bf16 *__restrict__ y2, const float *__restrict__ w3, const float *__restrict__ b3,
+// Last layers: logits = actor_net.4(y2[:, :128]), value = mean over agents of critic_net.4(y2[:, 128:]).  One CTA per
+// environment, one warp per agent at a time: the 512-byte row is read once, 16 bytes per lane (lanes 0-15 hold the actor
+// half, 16-31 the critic half), partial dot products reduced with shuffles; the critic mean is a fixed-order sum.
+__global__ void __launch_bounds__(256) k_head_final(const bf16 *__restrict__ y2, const float *__restrict__ w3, const float *__restrict__ b3,
                                                     float *__restrict__ logits, float *__restrict__ value, int N) {
-    __shared__ float ws[6 * 128];
-    __shared__ float red[128];
-    for (int i = threadIdx.x; i < 6 * 128; i += blockDim.x) ws[i] = w3[i];
-    __syncthreads();
-    const int e = blockIdx.x;
-    float vsum = 0.0f;
-    for (int a = threadIdx.x; a < N; a += blockDim.x) {
-        const bf16 *row = y2 + ((size_t)e * N + a) * 256;
-        float o[6];
+    extern __shared__ float vals[];          // per-agent critic outputs
+    const int e = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+    const int half = lane >> 4, k0 = (lane & 15) * 8;
+    // this lane's 8 weights of every output it contributes to: actor rows 0..4 (lanes 0-15) or the critic row (16-31)
+    float wreg[5][8];
 #pragma unroll
-        for (int j = 0; j < 6; j++) o[j] = b3[j];
-        for (int k = 0; k < 128; k += 2) {
-            const float2 fa = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162 *>(row + k));
-            const float2 fv = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162 *>(row + 128 + k));
+    for (int j = 0; j < 5; j++)
 #pragma unroll
-            for (int j = 0; j < 5; j++) o[j] = fmaf(fa.y, ws[j * 128 + k + 1], fmaf(fa.x, ws[j * 128 + k], o[j]));
-            o[5] = fmaf(fv.y, ws[5 * 128 + k + 1], fmaf(fv.x, ws[5 * 128 + k], o[5]));
+        for (int k = 0; k < 8; k++) wreg[j][k] = half == 0 ? w3[j * 128 + k0 + k] : (j == 0 ? w3[5 * 128 + k0 + k] : 0.0f);
+    for (int a = warp; a < N; a += nw) {
+        const uint4 raw = *reinterpret_cast<const uint4 *>(y2 + ((size_t)e * N + a) * 256 + lane * 8);
+        const uint32_t rw[4] = {raw.x, raw.y, raw.z, raw.w};
+        float x[8];
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162 *>(&rw[k]));
+            x[2 * k] = f.x;
+            x[2 * k + 1] = f.y;
         }
-        float *lo = logits + ((size_t)e * N + a) * 5;
+        float o[5];
 #pragma unroll
-        for (int j = 0; j < 5; j++) lo[j] = o[j];
-        vsum += o[5];
+        for (int j = 0; j < 5; j++) {
+            float acc = 0.0f;
+#pragma unroll
+            for (int k = 0; k < 8; k++) acc = fmaf(x[k], wreg[j][k], acc);
+            o[j] = acc;
+        }
+#pragma unroll
+        for (int j = 0; j < 5; j++)
+#pragma unroll
+            for (int d = 8; d > 0; d >>= 1) o[j] += __shfl_xor_sync(0xFFFFFFFFu, o[j], d);     // within each 16-lane half
+        if (lane == 0) {
+            float *lo = logits + ((size_t)e * N + a) * 5;
+#pragma unroll
+            for (int j = 0; j < 5; j++) lo[j] = o[j] + b3[j];
+        }
+        if (lane == 16) vals[a] = o[0] + b3[5];
     }
-    red[threadIdx.x] = vsum;
     __syncthreads();
-    for (int s = 64; s > 0; s >>= 1) {
-        if ((int)threadIdx.x < s) red[threadIdx.x] += red[threadIdx.x + s];
-        __syncthreads();
+    if (warp == 0) {
+        float sacc = 0.0f;
+        for (int a = lane; a < N; a += 32) sacc += vals[a];
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) sacc += __shfl_xor_sync(0xFFFFFFFFu, sacc, d);
+        if (lane == 0) value[e] = sacc / (float)N;
     }
-    if (threadIdx.x == 0) value[e] = red[0] / (float)N;
 }
 
 // plfActor.py:27-44 soft choice: np.random.seed(42); np.random.choice(valid, p=softmax(logits[valid])) draws one
@@ -1345,7 +1363,7 @@ int fl_policy_forward(const FlPolicyWeights *w, void *d_workspace, size_t worksp
     if ((rc = launch_linear(ws.emb, 256, 256, tin, 256, 256, (const bf16 *)w->head_w1, w->head_b1, ws.y1, 512, M, 512, 1, st))) return rc;
     if ((rc = launch_linear(ws.y1, 512, 256, nullptr, 0, 0, (const bf16 *)w->head_w2a, w->head_b2, ws.y2, 256, M, 128, 1, st))) return rc;
     if ((rc = launch_linear(ws.y1 + 256, 512, 256, nullptr, 0, 0, (const bf16 *)w->head_w2c, w->head_b2 + 128, ws.y2 + 128, 256, M, 128, 1, st))) return rc;
-    k_head_final<<<(unsigned)E, 128, 0, st>>>(ws.y2, w->head_w3, w->head_b3, d_logits, d_value, (int)N);
+    k_head_final<<<(unsigned)E, 256, (size_t)N * sizeof(float), st>>>(ws.y2, w->head_w3, w->head_b3, d_logits, d_value, (int)N);
     g_launches++;
     return (int)cudaGetLastError();
 }
