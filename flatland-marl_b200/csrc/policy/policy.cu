@@ -561,7 +561,9 @@ struct TreeArgs {
     uint32_t null_off;
 };
 
-__global__ void __launch_bounds__(416, 1) k_tree_p(const TreeArgs p) {
+// The weight k-blocks (U_iou: 384 rows, W_c: 128 rows) come as TMA tiles issued by one producer thread — they are dense and
+// would otherwise share the cp.async path (about 16 B/clk per SM) with the gathered node rows.
+__global__ void __launch_bounds__(416, 1) k_tree_p(const TreeArgs p, const __grid_constant__ CUtensorMap tu, const __grid_constant__ CUtensorMap tc) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     const int rows = *p.count_dev;
@@ -577,7 +579,7 @@ __global__ void __launch_bounds__(416, 1) k_tree_p(const TreeArgs p) {
 
     if (warp == 12) {
         if (lane == 0) {
-            for (int s = 0; s < P_STAGES; s++) { mbar_init(&full[s], 128); mbar_init(&empty[s], 1); }
+            for (int s = 0; s < P_STAGES; s++) { mbar_init(&full[s], 129); mbar_init(&empty[s], 1); }   // 128 gather threads + the TMA issuer
             mbar_init(tfull, 1);
             mbar_init(tempty, 256);
             mbar_init_fence();
@@ -623,9 +625,11 @@ __global__ void __launch_bounds__(416, 1) k_tree_p(const TreeArgs p) {
                     const bf16 *nsrc = p.h + (kk & 1) * 64 + c * 8;
 #pragma unroll
                     for (int i = 0; i < 8; i++) cp_async16(dstA + i * 2048, ((nul[i] >> cj) & 1u) ? nsrc + offn[i] : src + offc[i], ok[i]);
-                    const bf16 *wsrc = p.uiou + kk * 64 + c * 8;
-#pragma unroll 8
-                    for (int i = 0; i < 24; i++) cp_async16(dstB + i * 2048, wsrc + (size_t)(r0 + 16 * i) * 384, 16);
+                    if (tp == 0) {
+                        const uint32_t bB = smem_u32(smem + (size_t)s * P_STAGE_BYTES) + TILE;
+                        mbar_expect_tx(&full[s], 3 * TILE);
+                        for (int hh = 0; hh < 3; hh++) tma_load_2d(bB + hh * TILE, &tu, kk * 64, hh * 128, &full[s]);
+                    }
                 } else if (kk == 6) {
                     if (c < 2) {
                         const bf16 *src = p.x + c * 8;
@@ -635,13 +639,15 @@ __global__ void __launch_bounds__(416, 1) k_tree_p(const TreeArgs p) {
 #pragma unroll 8
                         for (int i = 0; i < 24; i++) cp_async16(dstB + i * 2048, wsrc + (size_t)(r0 + 16 * i) * 16, 16);
                     }
+                    if (tp == 0) mbar_arrive(&full[s]);        // no TMA tile in this stage: the issuer's arrival only
                 } else {
                     const bf16 *src = p.fc + (kk - 7) * 64 + c * 8;
 #pragma unroll
                     for (int i = 0; i < 8; i++) cp_async16(dstA + i * 2048, src + offc[i], ok[i]);
-                    const bf16 *wsrc = p.wc + (kk - 7) * 64 + c * 8;
-#pragma unroll
-                    for (int i = 0; i < 8; i++) cp_async16(dstB + i * 2048, wsrc + (size_t)(r0 + 16 * i) * 384, 16);
+                    if (tp == 0) {
+                        mbar_expect_tx(&full[s], TILE);
+                        tma_load_2d(smem_u32(smem + (size_t)s * P_STAGE_BYTES) + TILE, &tc, (kk - 7) * 64, 0, &full[s]);
+                    }
                 }
                 cp_async_arrive(&full[s]);
             }
@@ -1325,7 +1331,10 @@ int fl_policy_forward(const FlPolicyWeights *w, void *d_workspace, size_t worksp
         t.uiou = (const bf16 *)w->tree_uiou; t.wiou = (const bf16 *)w->tree_wiou; t.wc = (const bf16 *)w->tree_wc;
         t.b_iou = w->tree_b_iou; t.b_c = w->tree_b_c;
         t.eflags = ws.eflags + (list - ws.lists); t.null_off = null_off;
-        k_tree_p<<<g_num_sms, 416, 1024 + P_STAGES * P_STAGE_BYTES + 2 * 128 * OUT_PITCH + 1024, st>>>(t);
+        CUtensorMap tu, tc;
+        if ((rc = make_tmap(&tu, (const bf16 *)w->tree_uiou, 384, 384, 384))) return rc;
+        if ((rc = make_tmap(&tc, (const bf16 *)w->tree_wc, 128, 384, 384))) return rc;
+        k_tree_p<<<g_num_sms, 416, 1024 + P_STAGES * P_STAGE_BYTES + 2 * 128 * OUT_PITCH + 1024, st>>>(t, tu, tc);
         g_launches++;
     }
     // ---- attribute MLP (net_tree.py:41-50) ----
