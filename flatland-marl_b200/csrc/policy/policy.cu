@@ -32,7 +32,7 @@ typedef __nv_bfloat16 bf16;
 namespace {
 
 constexpr int TILE = 128 * 128;   // bytes of a 128-row x 64-element bf16 tile (one k-block)
-constexpr int P_STAGES = 2;
+constexpr int P_STAGES = 3;       // the ring is what paces k_tree_p: a stage takes ~2.5k cycles to arrive, its MMAs 768
 constexpr int P_STAGE_BYTES = 4 * TILE;   // A tile + up to 384 rows of B
 constexpr int NODES = 32;         // node slots per tree in the h / c / fc / x scratch (31 used)
 constexpr int NULL_COPIES = 1024; // copies of the shared null-node row (one hot row serialises in its L2 slice)
@@ -564,13 +564,16 @@ struct TreeArgs {
 // The weight k-blocks (U_iou: 384 rows, W_c: 128 rows) come as TMA tiles issued by one producer thread — they are dense and
 // would otherwise share the cp.async path (about 16 B/clk per SM) with the gathered node rows.
 __global__ void __launch_bounds__(416, 1) k_tree_p(const TreeArgs p, const __grid_constant__ CUtensorMap tu, const __grid_constant__ CUtensorMap tc) {
-    extern __shared__ uint8_t smem_raw[];
-    uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    // three 64 KB stages + one staging tile fill the 227 KB of the SM to within 500 bytes: no slack for re-aligning the
+    // base, which the driver places 1024-aligned when the kernel has no static shared memory (checked, not assumed)
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t *smem = smem_raw;
+    if ((smem_u32(smem) & 1023u) != 0) __trap();
     const int rows = *p.count_dev;
     const int mtiles = (rows + 127) >> 7;
     if ((int)blockIdx.x >= mtiles) return;
-    uint8_t *sC = smem + P_STAGES * P_STAGE_BYTES;          // staged h | c of the tile: 2 x 128 rows, pitch OUT_PITCH
-    uint32_t *rowoff = (uint32_t *)(sC + 2 * 128 * OUT_PITCH);
+    uint8_t *sC = smem + P_STAGES * P_STAGE_BYTES;          // staged h, then c, of the tile: 128 rows, pitch OUT_PITCH
+    uint32_t *rowoff = (uint32_t *)(sC + 128 * OUT_PITCH);
     uint64_t *bars = (uint64_t *)(rowoff + 128);
     uint64_t *full = bars, *empty = bars + P_STAGES, *tfull = bars + 2 * P_STAGES, *tempty = tfull + 1;
     uint32_t *tmem_slot = (uint32_t *)(tempty + 1);
@@ -695,7 +698,8 @@ __global__ void __launch_bounds__(416, 1) k_tree_p(const TreeArgs p, const __gri
             fence_after_sync();
             const uint32_t tbase = tmem + ((uint32_t)((warp & 3) * 32) << 16);
             const uint32_t srow = smem_u32(sC) + (uint32_t)((warp & 3) * 32 + lane) * OUT_PITCH;
-#pragma unroll 1
+            uint32_t cwk[4][8];                            // c of this thread's 64 hidden units waits here while h drains
+#pragma unroll
             for (int ch = (warp >> 2) * 4; ch < (warp >> 2) * 4 + 4; ch++) {
                 uint32_t vi[16], vo[16], vu[16], vc[16];
                 tmem_ld16(tbase + ch * 16, vi);
@@ -703,7 +707,8 @@ __global__ void __launch_bounds__(416, 1) k_tree_p(const TreeArgs p, const __gri
                 tmem_ld16(tbase + 256 + ch * 16, vu);
                 if (inner) tmem_ld16(tbase + 384 + ch * 16, vc);
                 tmem_ld_wait();
-                uint32_t hw[8], cw[8];
+                uint32_t hw[8];
+                uint32_t *cw = cwk[ch & 3];
                 float bc[16];
 #pragma unroll
                 for (int j = 0; j < 4; j++) *reinterpret_cast<float4 *>(&bc[4 * j]) = __ldg(reinterpret_cast<const float4 *>(p.b_c + ch * 16) + j);
@@ -727,8 +732,6 @@ __global__ void __launch_bounds__(416, 1) k_tree_p(const TreeArgs p, const __gri
                 // staged: the rows leave through row-contiguous stores below (see k_lin)
                 st_shared_v4(srow + ch * 32, hw[0], hw[1], hw[2], hw[3]);
                 st_shared_v4(srow + ch * 32 + 16, hw[4], hw[5], hw[6], hw[7]);
-                st_shared_v4(srow + 128 * OUT_PITCH + ch * 32, cw[0], cw[1], cw[2], cw[3]);
-                st_shared_v4(srow + 128 * OUT_PITCH + ch * 32 + 16, cw[4], cw[5], cw[6], cw[7]);
                 if (valid && v == 0) {
                     uint4 *oe = reinterpret_cast<uint4 *>(p.emb + (size_t)t * p.emb_ld + ch * 16);
                     oe[0] = make_uint4(hw[0], hw[1], hw[2], hw[3]);
@@ -738,18 +741,27 @@ __global__ void __launch_bounds__(416, 1) k_tree_p(const TreeArgs p, const __gri
             fence_before_sync();
             mbar_arrive(tempty);                          // every accumulator column of this thread's rows is in shared memory
             if (warp < 4) rowoff[warp * 32 + lane] = valid ? (uint32_t)orow : 0xFFFFFFFFu;
-            named_bar_sync(1, 256);
-            {
-                const int te = warp * 32 + lane;
+            const int te = warp * 32 + lane;
+#pragma unroll 1
+            for (int which = 0; which < 2; which++) {      // h, then c, through the one staging tile
+                if (which) {
+#pragma unroll
+                    for (int k = 0; k < 4; k++) {
+                        const int ch = (warp >> 2) * 4 + k;
+                        st_shared_v4(srow + ch * 32, cwk[k][0], cwk[k][1], cwk[k][2], cwk[k][3]);
+                        st_shared_v4(srow + ch * 32 + 16, cwk[k][4], cwk[k][5], cwk[k][6], cwk[k][7]);
+                    }
+                }
+                named_bar_sync(1, 256);
 #pragma unroll 4
-                for (int j = 0; j < 16; j++) {
-                    const int ci = te + 256 * j, which = ci >> 11, row = (ci >> 4) & 127, cc = ci & 15;
-                    const uint4 val = ld_shared_v4(smem_u32(sC) + (uint32_t)(which * 128 + row) * OUT_PITCH + cc * 16);
+                for (int j = 0; j < 8; j++) {
+                    const int ci = te + 256 * j, row = ci >> 4, cc = ci & 15;
+                    const uint4 val = ld_shared_v4(smem_u32(sC) + (uint32_t)row * OUT_PITCH + cc * 16);
                     const uint32_t off = rowoff[row];
                     if (off != 0xFFFFFFFFu) *reinterpret_cast<uint4 *>((which ? p.c : p.h) + off + cc * 8) = val;
                 }
+                named_bar_sync(2, 256);                   // the staging tile may be overwritten
             }
-            named_bar_sync(2, 256);                       // the staging tile may be overwritten
         }
     }
     fence_before_sync();
@@ -1147,7 +1159,7 @@ int setup() {
     }
     if (!g_attr_set) {
         const int lin_max = 1024 + 11 * TILE + 128 * OUT_PITCH + 1024 + 512;
-        const int p_bytes = 1024 + P_STAGES * P_STAGE_BYTES + 2 * 128 * OUT_PITCH + 1024;
+        const int p_bytes = P_STAGES * P_STAGE_BYTES + 128 * OUT_PITCH + 512 + 128;
         const int leaf_bytes = 1024 + (3 + LEAF_STAGES) * TILE + 4 * 128 * LEAF_PITCH + 2048;
         cudaError_t e = cudaFuncSetAttribute(k_lin<MODE_LINEAR, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, lin_max);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(k_lin<MODE_LINEAR, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, lin_max);
@@ -1334,7 +1346,7 @@ int fl_policy_forward(const FlPolicyWeights *w, void *d_workspace, size_t worksp
         CUtensorMap tu, tc;
         if ((rc = make_tmap(&tu, (const bf16 *)w->tree_uiou, 384, 384, 384))) return rc;
         if ((rc = make_tmap(&tc, (const bf16 *)w->tree_wc, 128, 384, 384))) return rc;
-        k_tree_p<<<g_num_sms, 416, 1024 + P_STAGES * P_STAGE_BYTES + 2 * 128 * OUT_PITCH + 1024, st>>>(t, tu, tc);
+        k_tree_p<<<g_num_sms, 416, P_STAGES * P_STAGE_BYTES + 128 * OUT_PITCH + 512 + 128, st>>>(t, tu, tc);
         g_launches++;
     }
     // ---- attribute MLP (net_tree.py:41-50) ----
