@@ -160,6 +160,15 @@ __global__ void __launch_bounds__(MODE == MODE_LINEAR ? LIN_THREADS_TMA : LIN_TH
         cp_async_arrive(wfull);
 
         uint32_t it = 0;
+        uint32_t ent[8], efl[8];                           // MODE_TREE_F: list entries / null flags of the tile, fetched one tile ahead
+        if (MODE == MODE_TREE_F) {
+#pragma unroll
+            for (int i = 0; i < 8; i++) {
+                const int r = (int)blockIdx.x * 128 + r0 + 16 * i;
+                ent[i] = efl[i] = 0;
+                if (r < rows) { ent[i] = ldg_u32_now(p.entries + r / 3); efl[i] = ldg_u8_now(p.eflags + r / 3); }
+            }
+        }
         for (int mt = blockIdx.x; mt < mtiles; mt += gridDim.x) {
             uint32_t off0[8], off1[8], off2[8], ok[8];
 #pragma unroll
@@ -174,11 +183,18 @@ __global__ void __launch_bounds__(MODE == MODE_LINEAR ? LIN_THREADS_TMA : LIN_TH
                         off2[i] = (uint32_t)r * (uint32_t)p.lda2;
                     } else {
                         uint32_t t, v, ch0;
-                        entry_decode(__ldg(p.entries + r / 3), t, v, ch0);
+                        entry_decode(ent[i], t, v, ch0);
                         const uint32_t child = ch0 + (uint32_t)(r % 3);
-                        off0[i] = ((__ldg(p.eflags + r / 3) >> (r % 3)) & 1u) ? p.null_off + (t & (NULL_COPIES - 1)) * (NODES * 128u) : (t * NODES + child) * 128u;
+                        off0[i] = ((efl[i] >> (r % 3)) & 1u) ? p.null_off + (t & (NULL_COPIES - 1)) * (NODES * 128u) : (t * NODES + child) * 128u;
                         off2[i] = (t * NODES + v) * 16u;
                     }
+                }
+            }
+            if (MODE == MODE_TREE_F) {
+#pragma unroll
+                for (int i = 0; i < 8; i++) {
+                    const int r = (mt + (int)gridDim.x) * 128 + r0 + 16 * i;
+                    if (r < rows) { ent[i] = ldg_u32_now(p.entries + r / 3); efl[i] = ldg_u8_now(p.eflags + r / 3); }
                 }
             }
             for (int kb = 0; kb < nkb; kb++, it++) {
@@ -418,23 +434,33 @@ __global__ void __launch_bounds__(LEAF_THREADS, 1) k_tree_leaf(const LeafArgs p)
         }
         cp_async_arrive(wfull);
         uint32_t it = 0;
+        uint32_t ent[8];                                   // list entries of the tile, fetched one tile ahead
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            const int r = (int)blockIdx.x * 128 + r0 + 16 * i;
+            ent[i] = (c < 2 && r < rows) ? ldg_u32_now(p.entries + r) : 0u;
+        }
         for (int mt = blockIdx.x; mt < mtiles; mt += gridDim.x, it++) {
             const int s = it % LEAF_STAGES;
+            uint32_t off[8], ok[8];
+#pragma unroll
+            for (int i = 0; i < 8; i++) {
+                const int r = mt * 128 + r0 + 16 * i;
+                uint32_t t, v, ch0;
+                entry_decode(ent[i], t, v, ch0);
+                ok[i] = r < rows ? 16u : 0u;
+                off[i] = ok[i] ? (t * NODES + v) * 16u : 0u;
+            }
+#pragma unroll
+            for (int i = 0; i < 8; i++) {
+                const int r = (mt + (int)gridDim.x) * 128 + r0 + 16 * i;
+                if (c < 2 && r < rows) ent[i] = ldg_u32_now(p.entries + r);
+            }
             mbar_wait(&empty[s], ((it / LEAF_STAGES) & 1) ^ 1);
             if (c < 2) {
                 const uint32_t dst = smem_u32(sA + (size_t)s * TILE) + swz;
 #pragma unroll
-                for (int i = 0; i < 8; i++) {
-                    const int r = mt * 128 + r0 + 16 * i;
-                    uint32_t off = 0, ok = 0;
-                    if (r < rows) {
-                        uint32_t t, v, ch0;
-                        entry_decode(__ldg(p.entries + r), t, v, ch0);
-                        off = (t * NODES + v) * 16u;
-                        ok = 16;
-                    }
-                    cp_async16(dst + i * 2048, p.x + off + c * 8, ok);
-                }
+                for (int i = 0; i < 8; i++) cp_async16(dst + i * 2048, p.x + off[i] + c * 8, ok[i]);
             }
             cp_async_arrive(&full[s]);
         }
@@ -600,6 +626,13 @@ __global__ void __launch_bounds__(416, 1) k_tree_p(const TreeArgs p, const __gri
         const int c = tp & 7, r0 = tp >> 3;
         const uint32_t swz = (uint32_t)((c ^ (r0 & 7)) << 4) + (uint32_t)r0 * 128u;
         uint32_t it = 0;
+        uint32_t ent[8], efl[8];                           // list entries / null flags of the tile, fetched one tile ahead
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            const int r = (int)blockIdx.x * 128 + r0 + 16 * i;
+            ent[i] = efl[i] = 0;
+            if (r < rows) { ent[i] = ldg_u32_now(p.entries + r); efl[i] = ldg_u8_now(p.eflags + r); }
+        }
         for (int mt = blockIdx.x; mt < mtiles; mt += gridDim.x) {
             uint32_t offc[8], offx[8], ok[8], nul[8], offn[8];
 #pragma unroll
@@ -609,12 +642,17 @@ __global__ void __launch_bounds__(416, 1) k_tree_p(const TreeArgs p, const __gri
                 offc[i] = offx[i] = nul[i] = offn[i] = 0;
                 if (ok[i]) {
                     uint32_t t, v, ch0;
-                    entry_decode(__ldg(p.entries + r), t, v, ch0);
+                    entry_decode(ent[i], t, v, ch0);
                     offc[i] = (t * NODES + ch0) * 128u;
                     offx[i] = (t * NODES + v) * 16u;
-                    nul[i] = __ldg(p.eflags + r);                      // which of the three children are null nodes
+                    nul[i] = efl[i];                                   // which of the three children are null nodes
                     offn[i] = p.null_off + (t & (NULL_COPIES - 1)) * (NODES * 128u);
                 }
+            }
+#pragma unroll
+            for (int i = 0; i < 8; i++) {
+                const int r = (mt + (int)gridDim.x) * 128 + r0 + 16 * i;
+                if (r < rows) { ent[i] = ldg_u32_now(p.entries + r); efl[i] = ldg_u8_now(p.eflags + r); }
             }
             for (int kk = kfirst; kk <= klast; kk++, it++) {
                 const int s = it % P_STAGES;

@@ -46,6 +46,20 @@ __device__ __forceinline__ void cp_async_arrive(uint64_t *bar) {
 }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
+// Loads that are issued where they are written (the compiler may not sink them to their first use): the producers fetch
+// the list entries of the NEXT tile before they queue the current tile's cp.async gathers, because a load queued behind
+// two dozen gathers comes back only when they do.
+__device__ __forceinline__ uint32_t ldg_u32_now(const uint32_t *p) {
+    uint32_t v;
+    asm volatile("ld.global.nc.u32 %0, [%1];" : "=r"(v) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ uint32_t ldg_u8_now(const uint8_t *p) {
+    uint32_t v;
+    asm volatile("ld.global.nc.u8 %0, [%1];" : "=r"(v) : "l"(p));
+    return v;
+}
+
 // ---- bulk stores shared -> global (TMA engine, 1-D): one thread moves a whole row of the output tile ----------
 __device__ __forceinline__ void bulk_store(void *dst_global, uint32_t src_smem, uint32_t bytes) {
     asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst_global), "r"(src_smem), "r"(bytes) : "memory");
