@@ -63,3 +63,43 @@ def test_policy_oracle_batch_axis():
     logits, value = po.forward(w, st("agent_attr"), po.clean_forest(st("forest")), st("adjacency"), st("node_order"), st("edge_order"))
     np.testing.assert_allclose(logits, gold["batched_logits"], rtol=0, atol=2e-5)
     np.testing.assert_allclose(value, gold["batched_value"], rtol=0, atol=2e-5)
+
+
+def test_pack_weights_folds_are_exact():
+    """Host-side weight packing (policy.pack_weights) against the layer-by-layer form: the attention out-projection folded
+    into att_mlp, the Tree-LSTM gate biases moved into weight column 12, the halved sigmoid-gate rows."""
+    from flatland_marl_b200.policy import pack_weights
+    w = pw.init_weights(3)
+    d = pack_weights(w)
+    rng = np.random.RandomState(0)
+    x, a = rng.randn(5, 256), rng.randn(5, 256)
+    for l in range(3):
+        p = "transformer.%d." % l
+        proj = a @ w[p + "attention.out_proj.weight"].T.astype(np.float64) + w[p + "attention.out_proj.bias"]
+        want = np.concatenate([x, proj], axis=1) @ w[p + "att_mlp.0.weight"].T.astype(np.float64) + w[p + "att_mlp.0.bias"]
+        got = np.concatenate([x, a], axis=1) @ d["tf_wm%d" % l].T.astype(np.float64) + d["tf_bm%d" % l]
+        np.testing.assert_allclose(got, want, rtol=0, atol=2e-5)
+    # tree: [x | 1 | 0 0 0] @ wiou^T reproduces W_iou x + b, with the i and o rows halved
+    xn = rng.randn(4, 12)
+    xe = np.concatenate([xn, np.ones((4, 1)), np.zeros((4, 3))], axis=1)
+    pre = xn @ w["tree_lstm.W_iou.weight"].T.astype(np.float64) + w["tree_lstm.W_iou.bias"]
+    got = xe @ d["tree_wiou"].T.astype(np.float64)
+    np.testing.assert_allclose(got[:, :256], 0.5 * pre[:, :256], rtol=0, atol=1e-6)
+    np.testing.assert_allclose(got[:, 256:], pre[:, 256:], rtol=0, atol=1e-6)
+    assert (d["tree_uiou"][:256] == 0.5 * w["tree_lstm.U_iou.weight"][:256]).all()
+    assert (d["tree_uiou"][256:] == w["tree_lstm.U_iou.weight"][256:]).all()
+    hc = rng.randn(4, 128)
+    f_pre = hc @ w["tree_lstm.U_f.weight"].T.astype(np.float64) + xn @ w["tree_lstm.W_f.weight"].T.astype(np.float64) + w["tree_lstm.W_f.bias"]
+    got = np.concatenate([hc, xe], axis=1) @ d["tree_ufwf"].T.astype(np.float64)
+    np.testing.assert_allclose(got, 0.5 * f_pre, rtol=0, atol=1e-6)
+    # sigmoid(2z) = 0.5 tanh(z) + 0.5, the identity the kernels evaluate
+    z = rng.randn(100)
+    np.testing.assert_allclose(0.5 * np.tanh(0.5 * z) + 0.5, 1.0 / (1.0 + np.exp(-z)), rtol=0, atol=1e-12)
+
+
+def test_gelu_fit_used_by_the_kernels():
+    """The kernels' GELU, 0.5 x (1 + tanh(x P(x^2))) with x^2 clamped at 49 (csrc/policy/umma.cuh), against the erf form."""
+    x = np.linspace(-12, 12, 200001)
+    u = np.minimum(x * x, 49.0)
+    fit = 0.5 * x * (1 + np.tanh(x * (7.97507884e-1 + u * (3.70056460e-2 + u * -3.51516783e-4))))
+    assert np.abs(fit - po.gelu(x.astype(np.float32)).astype(np.float64)).max() < 4e-5
