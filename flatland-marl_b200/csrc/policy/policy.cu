@@ -4,14 +4,14 @@
 //
 // Every matrix product runs on the 5th-generation tensor cores: tcgen05.mma issued by one thread, bf16 operands
 // staged in shared memory in the 128-byte-swizzled K-major layout, fp32 accumulators in TMEM, read back with
-// tcgen05.ld by four epilogue warps.  Operand rows are gathered with 16-byte cp.async copies (the Tree-LSTM's rows
-// are tree nodes scattered over the batch, which a tiled TMA box cannot address), made visible to the tensor core
-// with fence.proxy.async before the stage's mbarrier is signalled.
+// tcgen05.ld by the epilogue warps.  Dense operands arrive as TMA tiles (cp.async.bulk.tensor, tensor maps from the
+// driver entry point); the Tree-LSTM's rows are tree nodes scattered over the batch, which a tiled TMA box cannot
+// address, so they are gathered with 16-byte cp.async copies that arrive on the stage's mbarrier.
 //
-//   k_lin<MODE>   persistent; the CTA's 128 output columns of W stay resident in shared memory, 128-row tiles of A
-//                 stream through a 4-stage ring, two TMEM accumulators so the epilogue of tile i overlaps the MMAs
-//                 of tile i+1.  MODE_LINEAR: dense layers (bias, optional GELU).  MODE_TREE_F: forget gates of one
-//                 tree level, rows = child nodes, epilogue sigmoid(.) * c_child.
+//   k_lin<MODE,BN> persistent; the CTA's BN (128 / 256) output columns of W stay resident in shared memory, 128-row
+//                 tiles of A stream through a ring, two TMEM accumulators so the epilogue of tile i (16 warps) overlaps
+//                 the MMAs of tile i+1.  MODE_LINEAR: dense layers (bias, optional GELU).  MODE_TREE_F: forget gates of
+//                 one tree level, rows = child nodes, epilogue sigmoid(.) * c_child.
 //   k_tree_p      one tree level: i/o/u pre-activations (N = 384) and the W_c reduction (N = 128) of 128 parent
 //                 nodes accumulate side by side in all 512 TMEM columns; the epilogue applies the LSTM gates.
 //   k_attn_mma    4-head attention over the agents of one environment: S = QK^T and O = PV as tcgen05 MMAs, softmax by
