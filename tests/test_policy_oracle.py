@@ -103,3 +103,26 @@ def test_gelu_fit_used_by_the_kernels():
     u = np.minimum(x * x, 49.0)
     fit = 0.5 * x * (1 + np.tanh(x * (7.97507884e-1 + u * (3.70056460e-2 + u * -3.51516783e-4))))
     assert np.abs(fit - po.gelu(x.astype(np.float32)).astype(np.float64)).max() < 4e-5
+
+
+def test_load_weights_from_reference_checkpoint_formats(tmp_path):
+    """A reference checkpoint is `torch.save(net.state_dict())` (plfActor.py:10-13); .npz with the same keys also loads;
+    a missing or mis-shaped tensor is an error, not a silent default."""
+    import torch
+    w = pw.init_weights(5)
+    pt = tmp_path / "phase-III-50.pt"
+    torch.save({k: torch.from_numpy(v) for k, v in w.items()}, str(pt))
+    got = pw.load_weights(str(pt))
+    assert set(got) == set(w) and all((got[k] == w[k]).all() for k in w)
+    npz = tmp_path / "w.npz"
+    np.savez(str(npz), **w)
+    got = pw.load_weights(str(npz))
+    assert all((got[k] == w[k]).all() for k in w)
+    bad = dict(w)
+    del bad["tree_lstm.U_f.weight"]
+    with pytest.raises(KeyError):
+        pw.check_weights(bad)
+    bad = dict(w)
+    bad["actor_net.4.weight"] = np.zeros((4, 128), np.float32)
+    with pytest.raises(ValueError):
+        pw.check_weights(bad)
