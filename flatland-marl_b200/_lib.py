@@ -9,7 +9,8 @@ LIB_PATH = os.path.join(HERE, "csrc", "libflatland_b200.so")
 MAX_NODES, NODE_F, ATTR_F, PRED_DEPTH = 31, 12, 83, 500
 ACTION_ABSENT = 255
 ST_STEP_AFTER_DONE, ST_AUTO_RESET, ST_BAD_CELL = 1, 2, 4
-FLAG_AUTO_RESET = 1
+FLAG_AUTO_RESET, FLAG_FRESH_AGENTS = 1, 2
+RESET_KEEP_SCHEDULE, RESET_KEEP_ARRIVAL = 1, 2
 
 # field order of struct FlBatch (include/flatland_b200.h)
 _FIELDS = [("E", "i"), ("N", "i"), ("H", "i"), ("W", "i"), ("n_slots", "i"), ("S", "i"), ("ent_cap", "i"), ("grid_stride", "i"),
@@ -33,8 +34,8 @@ class FlObsBuffers(C.Structure):
                                           "valid_actions", "dist_target", "rewards", "dones")]
 
 
-EXPORTS = ["fl_abi_version", "fl_batch_sizeof", "fl_error_string", "fl_distance_map", "fl_walk_tables", "fl_reset", "fl_step",
-           "fl_observe", "fl_observe_plan", "fl_batch_slice", "fl_step_observe_host", "fl_launch_count", "fl_profile_num_kernels", "fl_profile_kernel_name",
+EXPORTS = ["fl_abi_version", "fl_batch_sizeof", "fl_error_string", "fl_distance_map", "fl_walk_tables", "fl_reset", "fl_reset_ex", "fl_step",
+           "fl_observe", "fl_observe_override", "fl_observe_plan", "fl_batch_slice", "fl_step_observe_host", "fl_launch_count", "fl_profile_num_kernels", "fl_profile_kernel_name",
            "fl_profile_enable", "fl_profile_collect"]
 
 _lib = None
@@ -61,6 +62,8 @@ def lib():
     L.fl_launch_count.restype = C.c_uint64
     L.fl_distance_map.argtypes = [C.POINTER(FlBatch), P]
     L.fl_reset.argtypes = [C.POINTER(FlBatch), P, P]
+    L.fl_reset_ex.argtypes = [C.POINTER(FlBatch), P, C.c_uint32, P]
+    L.fl_observe_override.argtypes = [C.c_char_p, C.c_int]
     L.fl_walk_tables.argtypes = [C.POINTER(FlBatch), C.c_int, P]
     L.fl_step.argtypes = [C.POINTER(FlBatch), P, P, P, C.c_uint32, P]
     L.fl_observe.argtypes = [C.POINTER(FlBatch)] + [P] * 8
@@ -76,7 +79,7 @@ def lib():
     L.fl_profile_enable.restype = None
     L.fl_profile_collect.argtypes = [P, P, C.c_int]
     L.fl_profile_collect.restype = C.c_int
-    for f in ("fl_distance_map", "fl_walk_tables", "fl_reset", "fl_step", "fl_observe", "fl_step_observe_host", "fl_batch_slice"):
+    for f in ("fl_distance_map", "fl_walk_tables", "fl_reset", "fl_reset_ex", "fl_step", "fl_observe", "fl_step_observe_host", "fl_batch_slice"):
         getattr(L, f).restype = C.c_int
     if L.fl_batch_sizeof() != C.sizeof(FlBatch):
         raise FlatlandB200Error("FlBatch layout mismatch: library %d bytes, binding %d bytes"

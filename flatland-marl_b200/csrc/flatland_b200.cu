@@ -23,6 +23,7 @@
 
 #include <atomic>
 #include <cstdlib>
+#include <cstring>
 #include <mutex>
 #include <vector>
 
@@ -87,13 +88,29 @@ constexpr int SMEM_MAX = 227 * 1024;
 
 int align_up(int v, int a) { return (v + a - 1) / a * a; }
 
+// Plan overrides (fl_observe_override; tuning and tests only).  -1 = default.  Seeded once from FL_OBS_<KEY> environment
+// variables when the library is loaded; the launch path reads these atomics, never the environment.
+enum ObsKnob : int { KNOB_NT = 0, KNOB_CTAS, KNOB_TABLES, KNOB_SEGCAP, KNOB_ENTCAP, KNOB_SORTSMALL, KNOB_PARTS, KNOB_COUNT };
+const char *const kKnobNames[KNOB_COUNT] = {"nt", "ctas", "tables", "segcap", "entcap", "sortsmall", "parts"};
+const char *const kKnobEnv[KNOB_COUNT] = {"FL_OBS_NT", "FL_OBS_CTAS", "FL_OBS_TABLES", "FL_OBS_SEGCAP", "FL_OBS_ENTCAP", "FL_OBS_SORTSMALL", "FL_OBS_PARTS"};
+std::atomic<int> g_knob[KNOB_COUNT];
+struct KnobInit {
+    KnobInit() {
+        for (int k = 0; k < KNOB_COUNT; k++) {
+            const char *s = getenv(kKnobEnv[k]);
+            g_knob[k].store(s && *s ? atoi(s) : -1);
+        }
+    }
+} g_knob_init;
+int knob(int k) { return g_knob[k].load(std::memory_order_relaxed); }
+
 // Shared-memory plan of k_observe for one configuration.  Mandatory: barrier + scalars, scan partials, the
 // per-agent records, the deadlock scratch, the occupancy word and the bucket offsets per rail cell (and the key
 // classes when H > W).  Then, while they fit: rail grid, rail index, the sorted predicted-occupancy entries at their
 // typical size ("core").  The budget per CTA is the largest that lets `ctas` CTAs share an SM, ctas being the largest
 // count for which the core fits (more resident warps hide the latency of the table lookups, which then go to L2).
 // What is left of the budget takes the static walk tables in the order of their use per visited cell.
-// FL_OBS_CTAS / FL_OBS_TABLES / FL_OBS_NT override (tuning only).
+// fl_observe_override("ctas" / "tables" / "nt", ...) override (tuning only).
 ObsLayout make_obs_layout(const FlBatch *b, int nt, int *ctas_out = nullptr) {
     const int N = (int)b->N, Rmax = (int)(b->state_stride / 4);
     ObsLayout L;
@@ -108,8 +125,8 @@ ObsLayout make_obs_layout(const FlBatch *b, int nt, int *ctas_out = nullptr) {
     L.bm = take((long long)Rmax * 32);                          // time-slot filter of the prediction index: one / two entries per slot
     L.seg_cap = 10 * N;                                         // path segments of phase 3 share the room of the phase-4 queues
     if (L.seg_cap < (nt / 32) * 64) L.seg_cap = (nt / 32) * 64;
-    int seg_cap_use = L.seg_cap;                                // FL_OBS_SEGCAP / FL_OBS_ENTCAP (tests): smaller capacities in
-    if (const char *s = getenv("FL_OBS_SEGCAP")) { const int v = atoi(s); if (v >= 0 && v < seg_cap_use) seg_cap_use = v; }   // the same room,
+    int seg_cap_use = L.seg_cap;                                // "segcap" / "entcap" overrides (tests): smaller capacities in
+    if (knob(KNOB_SEGCAP) >= 0 && knob(KNOB_SEGCAP) < seg_cap_use) seg_cap_use = knob(KNOB_SEGCAP);                            // the same room,
     L.sq = take((long long)L.seg_cap * 8);                      // per-warp queues of the full conflict checks / segment pool
     L.kcls = b->H > b->W ? take((long long)Rmax * 2) : -1;      // key classes of the reference's c*W + r (walks.cuh)
     const long long ent_typ = (long long)N * 56 * 4;
@@ -118,10 +135,10 @@ ObsLayout make_obs_layout(const FlBatch *b, int nt, int *ctas_out = nullptr) {
     const long long sd_b = b->n_slots * b->state_stride * 2;
     const long long core = off + ridx_b + ent_typ + 3 * 128;
     int want_tables = 0x77;                                     // bit k: wlist, wrec, sdist, (srec: unused by k_observe), whoff, whits
-    if (const char *s = getenv("FL_OBS_TABLES")) want_tables = atoi(s);
+    if (knob(KNOB_TABLES) >= 0) want_tables = knob(KNOB_TABLES);
     const int max_ctas = nt >= 1024 ? 1 : nt == 512 ? 2 : nt == 256 ? 4 : nt == 128 ? 8 : 12;
     int ctas = 0;
-    if (const char *s = getenv("FL_OBS_CTAS")) ctas = atoi(s) > 0 ? atoi(s) : 1;
+    if (knob(KNOB_CTAS) >= 0) ctas = knob(KNOB_CTAS) > 0 ? knob(KNOB_CTAS) : 1;
     if (!ctas)
         for (int c = max_ctas; c >= 1; c--)
             if (core <= SMEM_MAX / c - 1024 || c == 1) { ctas = c; break; }
@@ -149,9 +166,9 @@ ObsLayout make_obs_layout(const FlBatch *b, int nt, int *ctas_out = nullptr) {
     L.ent = take(ent_b);
     L.ent_cap = (int)(ent_b / 4);
     L.sort_small = 40;                                          // buckets up to this size are sorted by one thread
-    if (const char *s = getenv("FL_OBS_SORTSMALL")) { const int v = atoi(s); if (v >= 1) L.sort_small = v; }
+    if (knob(KNOB_SORTSMALL) >= 1) L.sort_small = knob(KNOB_SORTSMALL);
     L.seg_cap = seg_cap_use;                                    // to force the per-agent path walk and the global spill of the entries
-    if (const char *s = getenv("FL_OBS_ENTCAP")) { const int v = atoi(s); if (v >= 0 && v < L.ent_cap) L.ent_cap = v; }
+    if (knob(KNOB_ENTCAP) >= 0 && knob(KNOB_ENTCAP) < L.ent_cap) L.ent_cap = knob(KNOB_ENTCAP);
     L.total = off;
     return L;
 }
@@ -160,8 +177,8 @@ ObsLayout make_obs_layout(const FlBatch *b, int nt, int *ctas_out = nullptr) {
 // SM's warp slots filled (about 32 resident warps per SM); only tiny environments (up to 8 agents) get 64-thread CTAs
 // (Test_02's 20 agents: 115.7 M agent-steps/s with 128 threads against 92 M with 64).
 int obs_threads(const FlBatch *b) {
-    if (const char *s = getenv("FL_OBS_NT")) {
-        const int v = atoi(s);
+    {
+        const int v = knob(KNOB_NT);
         if (v == 64 || v == 128 || v == 256 || v == 512 || v == 1024) return v;
     }
     if (b->N <= 8) return 64;
@@ -181,6 +198,13 @@ extern "C" {
 int fl_abi_version(void) { return FL_ABI_VERSION; }
 size_t fl_batch_sizeof(void) { return sizeof(FlBatch); }
 uint64_t fl_launch_count(void) { return g_launches.load(); }
+
+int fl_observe_override(const char *key, int value) {
+    if (!key) return FL_ERR_BAD_ARG;
+    for (int k = 0; k < KNOB_COUNT; k++)
+        if (!strcmp(key, kKnobNames[k])) { g_knob[k].store(value < 0 ? -1 : value); return FL_OK; }
+    return FL_ERR_BAD_ARG;
+}
 
 int fl_profile_num_kernels(void) { return K_COUNT; }
 const char *fl_profile_kernel_name(int k) { return k >= 0 && k < K_COUNT ? kKernelNames[k] : ""; }
@@ -261,14 +285,16 @@ int fl_walk_tables(const FlBatch *b, int fill, void *stream) {
     return finish(cudaGetLastError());
 }
 
-int fl_reset(const FlBatch *b, const uint8_t *d_env_mask, void *stream) {
+int fl_reset_ex(const FlBatch *b, const uint8_t *d_env_mask, uint32_t flags, void *stream) {
     if (int rc = check_batch(b)) return rc;
     {
         LaunchScope ls(K_RESET, (cudaStream_t)stream);
-        k_reset<<<(unsigned)b->E, 128, 0, (cudaStream_t)stream>>>(*b, d_env_mask);
+        k_reset<<<(unsigned)b->E, 128, 0, (cudaStream_t)stream>>>(*b, d_env_mask, flags);
     }
     return finish(cudaGetLastError());
 }
+
+int fl_reset(const FlBatch *b, const uint8_t *d_env_mask, void *stream) { return fl_reset_ex(b, d_env_mask, 0u, stream); }
 
 int fl_step(const FlBatch *b, const uint8_t *d_actions, int32_t *d_rewards, uint8_t *d_dones, uint32_t flags,
             void *stream) {

@@ -1176,16 +1176,21 @@ EncodeTiledFn g_encode = nullptr;
 int g_num_sms = 0;
 long long *g_dbg = nullptr;       // k_lin timeline (fl_policy_linear_debug)
 long long *g_leaf_dbg = nullptr;  // k_tree_leaf timeline (fl_policy_debug_clocks)
-bool g_attr_set = false;
+// the dynamic shared-memory opt-in of a kernel is per DEVICE: one bit per device ordinal, so that a process driving several
+// devices opts in on each of them (all B200s of a box have the same SM count)
+unsigned long long g_attr_set_mask = 0;
 
 int setup() {
-    if (!g_num_sms) {
-        int dev = 0;
+    int dev = 0;
+    {
         cudaError_t e = cudaGetDevice(&dev);
         if (e != cudaSuccess) return (int)e;
-        e = cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
+    }
+    if (!g_num_sms) {
+        cudaError_t e = cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
         if (e != cudaSuccess) return (int)e;
     }
+    const bool g_attr_set = dev < 64 && ((g_attr_set_mask >> dev) & 1ull);
     if (!g_encode) {
         // the driver's tensor-map encoder, looked up at run time (no link-time dependency on libcuda)
         cudaDriverEntryPointQueryResult qres;
@@ -1206,7 +1211,7 @@ int setup() {
         if (e == cudaSuccess) e = cudaFuncSetAttribute(k_attn_mma, cudaFuncAttributeMaxDynamicSharedMemorySize, ATTN_SMEM);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(k_tree_leaf, cudaFuncAttributeMaxDynamicSharedMemorySize, leaf_bytes);
         if (e != cudaSuccess) return (int)e;
-        g_attr_set = true;
+        if (dev < 64) g_attr_set_mask |= 1ull << dev;
     }
     return 0;
 }

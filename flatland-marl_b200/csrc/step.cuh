@@ -44,8 +44,11 @@ DEVI int fsm(int s, bool in_mal, bool mal_done, bool edr, bool stop, bool valid_
 }
 
 // EnvAgent.reset for every agent of env e + cleared maps (agent_utils.py:90-105, rail_env.py:335-344,
-// treeobs.cpp:22-28).  Called by all threads of a CTA.
-DEVI void reset_env(const FlBatch &b, int e, bool rewind_schedule) {
+// treeobs.cpp:22-28).  Called by all threads of a CTA.  keep_arrival: EnvAgent.reset does not touch arrival_time, so
+// after reset(False, False) a train that arrived in the previous episode still carries its old arrival_time (and
+// handle_done_state, rail_env.py:493-499, then leaves it standing on its target cell when it arrives again); fresh
+// agent objects (a regenerating reset, an upload) start with arrival_time None.
+DEVI void reset_env(const FlBatch &b, int e, bool rewind_schedule, bool keep_arrival) {
     const int N = (int)b.N;
     for (int i = threadIdx.x; i < N; i += blockDim.x) {
         const size_t ea = (size_t)e * N + i;
@@ -53,7 +56,8 @@ DEVI void reset_env(const FlBatch &b, int e, bool rewind_schedule) {
         b.old_rc[2 * ea] = -1; b.old_rc[2 * ea + 1] = -1;
         b.dir[ea] = b.init_dir[ea]; b.old_dir[ea] = 255;
         b.state[ea] = WAITING; b.ctr[ea] = 0; b.mal[ea] = 0; b.saved[ea] = 0; b.sig_mal[ea] = 0;
-        b.deadlocked[ea] = 0; b.done[ea] = 0; b.nmal[ea] = 0; b.arrival[ea] = -1;
+        b.deadlocked[ea] = 0; b.done[ea] = 0; b.nmal[ea] = 0;
+        if (!keep_arrival) b.arrival[ea] = -1;
     }
     if (threadIdx.x == 0) {
         b.elapsed[e] = 0; b.done_all[e] = 0;
@@ -61,10 +65,10 @@ DEVI void reset_env(const FlBatch &b, int e, bool rewind_schedule) {
     }
 }
 
-__global__ void k_reset(FlBatch b, const uint8_t *__restrict__ mask) {
+__global__ void k_reset(FlBatch b, const uint8_t *__restrict__ mask, uint32_t flags) {
     const int e = blockIdx.x;
     if (mask && !mask[e]) return;
-    reset_env(b, e, true);
+    reset_env(b, e, !(flags & FL_RESET_KEEP_SCHEDULE), (flags & FL_RESET_KEEP_ARRIVAL) != 0);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -87,7 +91,7 @@ k_step(FlBatch b, const uint8_t *__restrict__ actions, int32_t *__restrict__ rew
     __syncthreads();
     if (was_done) {  // rail_env.py:508-509 raises; here: status bit, or in-place reset
         if (flags & FL_FLAG_AUTO_RESET) {
-            reset_env(b, e, false);
+            reset_env(b, e, false, !(flags & FL_FLAG_FRESH_AGENTS));
             if (i == 0) atomicOr(&b.status[e], FL_ST_AUTO_RESET);
             if (act) { rewards[ea] = 0; dones[(size_t)e * (N + 1) + i] = 0; }
             if (i == 0) dones[(size_t)e * (N + 1) + N] = 0;
@@ -211,9 +215,12 @@ k_step(FlBatch b, const uint8_t *__restrict__ actions, int32_t *__restrict__ rew
                 rew = off_map(st) ? -tt : (b.latest[ea] - elapsed) - tt;
             }
             b.done[ea] = 1;
-            // episode statistics (eval_env.py:81-94 final_metric): arrivals and total reward
+            // episode statistics (eval_env.py:81-94 final_metric): total reward, and "arrivals" with the reference's own
+            // predicate `a.position is None and a.state != READY_TO_DEPART` — which also counts trains that never left
+            // (WAITING, MALFUNCTION_OFF_MAP) and does not count a train standing on its target in state DONE (the
+            // second-episode case described at reset_env)
             unsigned long long *stt = reinterpret_cast<unsigned long long *>(b.stats + (size_t)e * 4);
-            if (st == DONE) atomicAdd(stt + 1, 1ull);
+            if (r < 0 && st != READY) atomicAdd(stt + 1, 1ull);
             if (rew) atomicAdd(stt + 2, (unsigned long long)(long long)rew);
         }
         rewards[ea] = rew;

@@ -4,8 +4,9 @@ save_distance_maps=True)` files as written by solution/debug-environments/genera
 
 The pickle references the reference's own classes (`flatland.envs.agent_utils.Agent`, `SpeedCounter`,
 `TrainStateMachine`, ...).  flatland-rl need not be installed: a restricted unpickler maps every `flatland.*` global
-to an inert stand-in that only records the pickled state, and refuses anything that is not flatland, numpy or a
-builtin container — a level file is data, not code.
+to an inert stand-in that only records the pickled state, and refuses every other global except an exact list of
+(module, name) pairs: the ndarray / dtype / scalar reconstructors of numpy and the builtin containers — a level file is
+data, not code.
 
 What a level file holds, and what it does not (persistence.py:196-217): grid, the agents with their timetable
 (earliest_departure / latest_arrival), `max_episode_steps`, the malfunction *parameters* (rate, min, max) and optionally
@@ -47,6 +48,14 @@ def _inert_enum(value):
 _SAFE_BUILTINS = {"list", "dict", "tuple", "set", "frozenset", "int", "float", "bool", "str", "bytes", "complex", "slice", "range"}
 
 
+# exactly what a pickled ndarray / numpy scalar needs (numpy < 2 writes numpy.core.*, numpy >= 2 numpy._core.*); everything
+# else under numpy is refused: numpy.testing / numpy.f2py / numpy.load hold helpers that run code
+_SAFE_NUMPY = {(m, n) for m in ("numpy.core.multiarray", "numpy._core.multiarray") for n in ("_reconstruct", "scalar")} | \
+    {("numpy", "ndarray"), ("numpy", "dtype")} | \
+    {("numpy", n) for n in ("bool_", "int8", "int16", "int32", "int64", "uint8", "uint16", "uint32", "uint64", "float16",
+                            "float32", "float64", "intc", "uintc", "longlong", "ulonglong")}
+
+
 class _LevelUnpickler(pickle.Unpickler):
     def find_class(self, module, name):
         if module.startswith("flatland."):
@@ -57,7 +66,7 @@ class _LevelUnpickler(pickle.Unpickler):
             if name in ("Grid4TransitionsEnum", "TrainState", "RailEnvActions"):
                 return _inert_enum
             return type(name, (_Inert,), {})
-        if module.split(".")[0] == "numpy":
+        if (module, name) in _SAFE_NUMPY:
             return super().find_class(module, name)
         if module in ("builtins", "__builtin__") and name in _SAFE_BUILTINS:
             return super().find_class(module, name)

@@ -63,6 +63,9 @@ def check_weights(w):
             raise KeyError("policy weights: missing %s" % name)
         if tuple(w[name].shape) != tuple(shape):
             raise ValueError("policy weights: %s has shape %s, expected %s" % (name, tuple(w[name].shape), shape))
+    extra = sorted(set(w) - {name for name, _, _ in weight_spec()})
+    if extra:
+        raise KeyError("policy weights: unexpected keys %s (not a checkpoint of the reference Network)" % ", ".join(extra[:5]))
     return w
 
 
@@ -73,6 +76,6 @@ def load_weights(path):
             w = {k: np.asarray(z[k], np.float32) for k in z.files}
     else:
         import torch
-        sd = torch.load(path, map_location="cpu")
+        sd = torch.load(path, map_location="cpu", weights_only=True)
         w = {k: v.detach().cpu().numpy().astype(np.float32) for k, v in sd.items()}
     return check_weights(w)

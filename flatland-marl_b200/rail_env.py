@@ -178,6 +178,7 @@ class RailEnv:
         self._max_episode_steps = None if world is None else int(world["T"])
         self._elapsed_steps = 0
         self._cache = {}
+        self._was_reset = False
 
     # -- constructors ----------------------------------------------------------------------------
     @classmethod
@@ -250,14 +251,19 @@ class RailEnv:
         if self._gen_args is not None:
             self.world = self._generate_world(regenerate_rail, regenerate_schedule, random_seed)
             self._batch = None
+        # reset(False, False) on a world that is already resident keeps the agent objects and the malfunction generator of
+        # the reference (rail_env.py:260-357: nothing regenerated, no RNG consumed): the schedule carries on and
+        # arrival_time survives.  Every other reset builds fresh agents.
+        same_agents = self._batch is not None and self._was_reset and not regenerate_rail and not regenerate_schedule
         if own_batch:
             if self._batch is None:
                 self._batch, self._e = BatchedRailEnv([self.world], device=self.device), 0
-            self._batch.reset()
+            self._batch.reset(same_agents=same_agents)
         else:
             mask = np.zeros(self._batch.E, np.uint8)
             mask[self._e] = 1
-            self._batch.reset(env_mask=mask)
+            self._batch.reset(env_mask=mask, same_agents=same_agents)
+        self._was_reset = True
         w = self.world
         self.height, self.width, self.number_of_agents = int(w["H"]), int(w["W"]), int(w["N"])
         self._max_episode_steps, self._elapsed_steps = int(w["T"]), 0

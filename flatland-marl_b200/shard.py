@@ -38,11 +38,19 @@ def max_over_ranks(value_ms, device="cpu", group=None):
     return float(t.item())
 
 
-def final_metric(stats, n_agents_per_env):
-    """eval_env.py:81-94 final_metric aggregated over all finished episodes: arrival ratio and mean
-    end-of-episode reward per episode."""
-    episodes, arrivals, reward_sum, _ = (int(x) for x in stats.tolist())
+def final_metric(stats, n_agents_per_env, max_steps=None):
+    """eval_env.py:81-94 final_metric aggregated over all finished episodes: arrival ratio (the reference's predicate:
+    position is None and state != READY_TO_DEPART, which also counts trains that never left), mean end-of-episode reward
+    per episode and — when `max_steps` (T per environment, for per-environment stats [E, 4]) is given — the mean of
+    norm_reward = 1 + total_reward / T / n_agents."""
+    st = stats.reshape(-1, 4) if hasattr(stats, "reshape") else torch.as_tensor(stats).reshape(-1, 4)
+    episodes, arrivals, reward_sum = (int(st[:, k].sum().item()) for k in range(3))
     if episodes == 0:
-        return {"episodes": 0, "arrival_ratio": None, "mean_total_reward": None}
-    return {"episodes": episodes, "arrival_ratio": arrivals / (episodes * n_agents_per_env),
-            "mean_total_reward": reward_sum / episodes}
+        return {"episodes": 0, "arrival_ratio": None, "mean_total_reward": None, "mean_norm_reward": None}
+    out = {"episodes": episodes, "arrival_ratio": arrivals / (episodes * n_agents_per_env),
+           "mean_total_reward": reward_sum / episodes, "mean_norm_reward": None}
+    if max_steps is not None:
+        T = torch.as_tensor(max_steps, dtype=torch.float64, device=st.device).reshape(-1)
+        norm = st[:, 0].double() + st[:, 2].double() / T / n_agents_per_env
+        out["mean_norm_reward"] = float(norm.sum().item()) / episodes
+    return out

@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define FL_ABI_VERSION 2
+#define FL_ABI_VERSION 3
 
 /* fixed by the reference (solution/impl_config.py:4-21, flatland_cutils/src/tool.h:67-93) */
 #define FL_MAX_NODES 31     /* num_tree_obs_nodes = 1 + 3*10 */
@@ -51,7 +51,17 @@ enum FlStatus {
 #define FL_ST_BAD_CELL 4u        /* tree walk met a cell with 0 transitions (treeobs.cpp:527-535 throws) */
 
 /* fl_step flags */
-#define FL_FLAG_AUTO_RESET 1u /* a finished env is reset in place (reset(False, False)) instead of stepped */
+#define FL_FLAG_AUTO_RESET 1u   /* a finished env is reset in place instead of stepped: env.reset(False, False) of the
+                                   reference (rail_env.py:260-357 with nothing regenerated) — no schedule rows are consumed by
+                                   the call, and, as in the reference, EnvAgent.reset (agent_utils.py:90-105) keeps arrival_time:
+                                   a train that arrived in the previous episode carries its old arrival_time, so when it
+                                   reaches its target again handle_done_state (rail_env.py:493-499) leaves it standing there */
+#define FL_FLAG_FRESH_AGENTS 2u /* with FL_FLAG_AUTO_RESET: arrival_time is cleared too (fresh agent objects, what a reset that
+                                   regenerates the schedule gives: EnvAgent.from_line, rail_env.py:315-317) */
+
+/* fl_reset_ex flags */
+#define FL_RESET_KEEP_SCHEDULE 1u /* do not rewind the malfunction schedule (the reference's generator carries on) */
+#define FL_RESET_KEEP_ARRIVAL 2u  /* keep arrival_time (EnvAgent.reset semantics, see FL_FLAG_AUTO_RESET) */
 
 /* Device-resident state of E lock-step environments of one configuration (same N, H, W).
  * Struct of arrays; E is the slowest index everywhere.  "rc" arrays hold (row, col) int16 pairs.
@@ -125,8 +135,10 @@ typedef struct FlBatch {
     int32_t *sched_pos;   /* [E] schedule rows consumed so far */
     uint8_t *done_all;    /* [E] dones["__all__"] */
     uint32_t *status;     /* [E] FL_ST_* bits, sticky until cleared by the caller */
-    int64_t *stats;       /* [E][4] running totals since upload: episodes finished, agents arrived at episode
-                                    end, sum of end-of-episode rewards, agent-steps (eval_env.py:81-94 final_metric) */
+    int64_t *stats;       /* [E][4] running totals since upload: episodes finished, "arrived" agents at episode end with
+                                    the predicate of eval_env.py:81-94 final_metric (position is None and state !=
+                                    READY_TO_DEPART: includes trains that never left), sum of end-of-episode rewards,
+                                    agent-steps */
 
     /* ---- per-step observation workspace (rebuilt by every fl_observe) ---- */
     uint32_t *entries;    /* [E][ent_cap] predicted-occupancy entries grouped by rail cell (spill space: used only
@@ -154,6 +166,9 @@ int fl_walk_tables(const FlBatch *b, int fill, void *stream);
  * dones cleared) and TreeObsForRailEnv::reset (flatland_cutils/src/treeobs.cpp:22-28: a fresh
  * DeadlockChecker).  d_env_mask: [E] bytes, non-zero = reset this env; NULL = all. */
 int fl_reset(const FlBatch *b, const uint8_t *d_env_mask, void *stream);
+/* The same with flags: FL_RESET_KEEP_SCHEDULE | FL_RESET_KEEP_ARRIVAL is env.reset(False, False) on the reference (the
+ * agent objects and the malfunction generator live on); 0 is fl_reset (fresh agents, schedule rewound: a new upload). */
+int fl_reset_ex(const FlBatch *b, const uint8_t *d_env_mask, uint32_t flags, void *stream);
 
 /* Replaces RailEnv.step(action_dict) up to but excluding the observation
  * (flatland/envs/rail_env.py:501-632, step_utils/*, agent_chains.py MotionCheck).
@@ -171,6 +186,15 @@ int fl_step(const FlBatch *b, const uint8_t *d_actions, int32_t *d_rewards, uint
 int fl_observe(const FlBatch *b, float *d_agent_attr, float *d_forest, int32_t *d_adjacency,
                int32_t *d_node_order, int32_t *d_edge_order, uint8_t *d_valid_actions,
                float *d_dist_target, void *stream);
+
+/* Tuning and test hook (no reference counterpart): overrides one knob of the shared-memory / launch plan fl_observe derives
+ * from the batch shape, process-wide, value < 0 = back to the default.  Keys: "nt" (threads per CTA: 64..1024), "ctas"
+ * (CTAs per SM the plan is cut for), "tables" (bit mask of the static tables staged in shared memory), "segcap", "entcap"
+ * (capacities of the shared-memory segment pool / entry array, to force the global spill paths), "sortsmall" (largest bucket
+ * sorted by one thread), "parts" (CTAs per environment for the tree phase).  The same knobs are read ONCE from the
+ * environment variables FL_OBS_<KEY> when the library is loaded; fl_observe itself never calls getenv.
+ * Returns 0, or FL_ERR_BAD_ARG for an unknown key. */
+int fl_observe_override(const char *key, int value);
 
 /* Diagnostics: the shared-memory plan fl_observe uses for this batch.  out[0..19] = threads per CTA, dynamic
  * shared bytes, CTAs per SM planned for, entry capacity, byte offsets of key classes, grid, occupancy,

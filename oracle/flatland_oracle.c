@@ -143,6 +143,7 @@ FoEnv *fo_create(int H, int W, int N, int T, const uint16_t *grid, const int16_t
         e->init_r[i] = init_pos[2 * i]; e->init_c[i] = init_pos[2 * i + 1]; e->init_dir[i] = init_dir[i];
         e->tgt_r[i] = target[2 * i]; e->tgt_c[i] = target[2 * i + 1];
         e->speed[i] = speed[i]; e->earliest[i] = earliest[i]; e->latest[i] = latest[i];
+        e->arrival[i] = -1;   /* EnvAgent.arrival_time: attrib default None, set once per agent OBJECT (see reset_dynamic) */
     }
     return e;
 }
@@ -158,12 +159,15 @@ void fo_free(FoEnv *e) {
 }
 
 static void reset_dynamic(FoEnv *e) {
-    /* EnvAgent.reset (agent_utils.py:90-105); arrival_time starts as None (attrib default) */
+    /* EnvAgent.reset (agent_utils.py:90-105).  It does NOT touch arrival_time: the attribute starts as None when the
+     * agent object is made (EnvAgent.from_line at a regenerating reset) and survives reset(False, False).  A train that
+     * arrived in the previous episode therefore keeps its old arrival_time, and when it reaches its target again
+     * handle_done_state (rail_env.py:493-499) does nothing: it stays on its target cell in state DONE. */
     for (int i = 0; i < e->N; i++) {
         e->r[i] = e->c[i] = -1; e->dir[i] = e->init_dir[i];
         e->old_r[i] = e->old_c[i] = -1; e->old_dir[i] = -1;
         e->state[i] = WAITING; e->ctr[i] = 0; e->mal[i] = 0; e->nmal[i] = 0; e->saved[i] = 0;
-        e->arrival[i] = -1; e->sig_mal[i] = 0; e->done[i] = 0; e->deadlocked[i] = 0;
+        e->sig_mal[i] = 0; e->done[i] = 0; e->deadlocked[i] = 0;
     }
     e->elapsed = 0; e->done_all = 0;
 }
@@ -284,7 +288,7 @@ void fo_motion_check(int n, const int16_t *cur, const int16_t *nxt, uint8_t *can
     }
     int nn = g.n_nodes;
     uint8_t *stops = calloc(nn, 1), *swaps = calloc(nn, 1), *blocked = calloc(nn, 1);
-    for (int u = 0; u < nn; u++) if (mg_edge(&g, u, u)) stops[u] = 1;          /* find_stops2 */
+    for (int k = 0; k < n; k++) if (g.cur_node[k] == g.nxt_node[k]) stops[g.cur_node[k]] = 1;   /* find_stops2: self loops */
     for (int k = 0; k < n; k++) {                                               /* find_swaps: 2-cycles */
         int u = g.cur_node[k], v = g.nxt_node[k];
         if (u != v && mg_edge(&g, v, u)) { swaps[u] = 1; swaps[v] = 1; }
@@ -293,8 +297,15 @@ void fo_motion_check(int n, const int16_t *cur, const int16_t *nxt, uint8_t *can
     for (int u = 0; u < nn; u++) if (stops[u]) mg_reverse_closure(&g, u, blocked); /* find_stop_preds */
     int *preds = IALLOC(nn + 1);
     for (int v = 0; v < nn; v++) {                      /* G.pred.items() in node insertion order */
-        int np = 0;
-        for (int w = 0; w < nn; w++) if (mg_edge(&g, w, v)) preds[np++] = w;
+        int np = 0;                                     /* predecessors of v in node insertion order, each once */
+        for (int k = 0; k < n; k++) {
+            if (g.nxt_node[k] != v) continue;
+            int w = g.cur_node[k], at = np;
+            while (at > 0 && preds[at - 1] >= w) at--;
+            if (at < np && preds[at] == w) continue;    /* several trains on one cell heading the same way: one edge */
+            for (int q = np; q > at; q--) preds[q] = preds[q - 1];
+            preds[at] = w; np++;
+        }
         if (blocked[v]) {
             g.color[v] = COL_RED;
         } else if (np > 1) {

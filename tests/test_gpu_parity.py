@@ -205,21 +205,39 @@ def test_rail_cycle_world_matches_oracle(n_agents):
     run_against_oracle([w, w, w], acts, [sched, sched, sched], w["T"])
 
 
-@pytest.mark.parametrize("env", [
-    {"FL_OBS_SEGCAP": "3"},                            # segment pool overflows into its global spill space
-    {"FL_OBS_ENTCAP": "16"},                           # the prediction entries spill to global memory
-    {"FL_OBS_SEGCAP": "0", "FL_OBS_ENTCAP": "0"},
-    {"FL_OBS_SORTSMALL": "1"},                         # every bucket with two or more entries takes the warp sort (bitonic network)
-    {"FL_OBS_SORTSMALL": "1", "FL_OBS_ENTCAP": "0"},   # ... with the entries and the sort scratch sharing the spill space
-    {"FL_OBS_CTAS": "1"},                              # all static tables staged in shared memory (TMA bulk copies)
-    {"FL_OBS_TABLES": "0"},                            # all static tables read from global memory
-    {"FL_OBS_NT": "64"}, {"FL_OBS_NT": "128"}, {"FL_OBS_NT": "256"}, {"FL_OBS_NT": "512"}, {"FL_OBS_NT": "1024"},
-], ids=lambda d: ",".join("%s=%s" % kv for kv in d.items()))
-def test_every_kernel_plan_matches_oracle(golden, monkeypatch, env):
+PLANS = [
+    {"segcap": 3},                            # segment pool overflows into its global spill space
+    {"entcap": 16},                           # the prediction entries spill to global memory
+    {"segcap": 0, "entcap": 0},
+    {"sortsmall": 1},                         # every bucket with two or more entries takes the warp sort (bitonic network)
+    {"sortsmall": 1, "entcap": 0},            # ... with the entries and the sort scratch sharing the spill space
+    {"ctas": 1},                              # all static tables staged in shared memory (TMA bulk copies)
+    {"tables": 0},                            # all static tables read from global memory
+    {"nt": 64}, {"nt": 128}, {"nt": 256}, {"nt": 512}, {"nt": 1024},
+]
+
+
+@pytest.fixture
+def obs_plan():
+    """Sets fl_observe_override knobs for one test and puts the defaults back afterwards."""
+    import flatland_marl_b200 as fb
+    lib = fb._lib.lib()
+    used = []
+
+    def set_plan(plan):
+        for k, v in plan.items():
+            assert lib.fl_observe_override(k.encode(), int(v)) == 0
+            used.append(k)
+    yield set_plan
+    for k in used:
+        lib.fl_observe_override(k.encode(), -1)
+
+
+@pytest.mark.parametrize("plan", PLANS, ids=lambda d: ",".join("%s=%s" % kv for kv in d.items()))
+def test_every_kernel_plan_matches_oracle(golden, obs_plan, plan):
     """k_observe picks its shared-memory plan, CTA size and fallbacks from the batch shape; each of them must give
-    the same bytes.  The overrides are read by fl_observe at every call."""
-    for k, v in env.items():
-        monkeypatch.setenv(k, v)
+    the same bytes.  The overrides go through fl_observe_override (the launch path never reads the environment)."""
+    obs_plan(plan)
     g = golden("t03_l1_greedy")
     rng = np.random.RandomState(77)
     other = np.where(rng.rand(*g["actions"].shape) < 0.7, 2, rng.randint(0, 5, size=g["actions"].shape)).astype(np.uint8)

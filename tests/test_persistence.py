@@ -48,6 +48,23 @@ def test_unpickler_refuses_foreign_globals(tmp_path):
         p.load_env_dict(str(bad))
     with pytest.raises(ValueError):
         p.load_env_dict(str(tmp_path / "level.mpk"))
+    # numpy is not a free pass: only the ndarray / dtype / scalar reconstructors are let through, not helpers that run code
+    class Gadget:
+        def __reduce__(self):
+            import numpy.testing._private.utils as u
+            return (u.runstring, ("import os; os.environ['FL_PWNED'] = '1'", {}))
+    bad.write_bytes(pickle.dumps({"grid": [[0]], "agents": [], "x": Gadget()}))
+    with pytest.raises(pickle.UnpicklingError):
+        p.load_env_dict(str(bad))
+    assert "FL_PWNED" not in os.environ
+    for mod, name in (("numpy", "load"), ("numpy.lib.npyio", "load"), ("numpy.f2py", "run_main"), ("numpy.core.multiarray", "frombuffer")):
+        with pytest.raises(pickle.UnpicklingError):
+            p._LevelUnpickler(__import__("io").BytesIO(b"")).find_class(mod, name)
+    # what real level files need still loads
+    ok = tmp_path / "ok.pkl"
+    ok.write_bytes(pickle.dumps({"grid": np.zeros((2, 2), np.uint16), "agents": [], "n": np.int64(3), "f": np.float64(0.5)}))
+    d = p.load_env_dict(str(ok))
+    assert d["grid"].shape == (2, 2) and int(d["n"]) == 3
 
 
 @pytest.mark.gpu

@@ -12,7 +12,7 @@ import bench  # noqa: E402
 import flatland_marl_b200 as fb  # noqa: E402
 
 cfg = sys.argv[1] if len(sys.argv) > 1 else "Test_03"
-E = int(sys.argv[2]) if len(sys.argv) > 2 else bench.CONFIGS[cfg]["envs"]
+E = int(sys.argv[2]) if len(sys.argv) > 2 and int(sys.argv[2]) > 0 else bench.CONFIGS[cfg]["envs"]
 steps = int(sys.argv[3]) if len(sys.argv) > 3 else 150
 worlds = bench.load_worlds(cfg, E)
 batch = fb.BatchedRailEnv(worlds, auto_reset=True, debug_clocks=True)
