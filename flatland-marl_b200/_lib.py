@@ -15,13 +15,13 @@ RESET_KEEP_SCHEDULE, RESET_KEEP_ARRIVAL = 1, 2
 # field order of struct FlBatch (include/flatland_b200.h)
 _FIELDS = [("E", "i"), ("N", "i"), ("H", "i"), ("W", "i"), ("n_slots", "i"), ("S", "i"), ("ent_cap", "i"), ("grid_stride", "i"),
            ("dist_stride", "i"), ("debug_clocks", "p"), ("ridx_stride", "i"), ("state_stride", "i"), ("wlist_stride", "i"),
-           ("whits_stride", "i"), ("seg_stride", "i")]
+           ("whits_stride", "i"), ("seg_stride", "i"), ("ws_stride", "i")]
 _PTR = ["grid", "slot_rc", "dist", "max_steps", "init_rc", "tgt_rc", "init_dir", "max_count", "slot", "speed",
         "earliest", "latest", "sched", "ridx", "srec", "wrec", "whoff", "wlist", "whits", "kcls", "sdist", "gtab", "walk_total",
         "rc", "old_rc", "dir", "old_dir", "state", "ctr", "mal", "saved", "sig_mal", "deadlocked", "done", "nmal",
         "arrival",
         "elapsed", "sched_pos", "done_all", "status", "stats",
-        "entries", "segs"]
+        "entries", "segs", "obs_ws"]
 
 
 class FlBatch(C.Structure):
@@ -35,7 +35,7 @@ class FlObsBuffers(C.Structure):
 
 
 EXPORTS = ["fl_abi_version", "fl_batch_sizeof", "fl_error_string", "fl_distance_map", "fl_walk_tables", "fl_reset", "fl_reset_ex", "fl_step",
-           "fl_observe", "fl_observe_override", "fl_observe_plan", "fl_batch_slice", "fl_step_observe_host", "fl_launch_count", "fl_profile_num_kernels", "fl_profile_kernel_name",
+           "fl_observe", "fl_observe_override", "fl_observe_plan", "fl_observe_ws_words", "fl_batch_slice", "fl_step_observe_host", "fl_launch_count", "fl_profile_num_kernels", "fl_profile_kernel_name",
            "fl_profile_enable", "fl_profile_collect"]
 
 _lib = None
@@ -64,6 +64,8 @@ def lib():
     L.fl_reset.argtypes = [C.POINTER(FlBatch), P, P]
     L.fl_reset_ex.argtypes = [C.POINTER(FlBatch), P, C.c_uint32, P]
     L.fl_observe_override.argtypes = [C.c_char_p, C.c_int]
+    L.fl_observe_ws_words.argtypes = [C.POINTER(FlBatch)]
+    L.fl_observe_ws_words.restype = C.c_int64
     L.fl_walk_tables.argtypes = [C.POINTER(FlBatch), C.c_int, P]
     L.fl_step.argtypes = [C.POINTER(FlBatch), P, P, P, C.c_uint32, P]
     L.fl_observe.argtypes = [C.POINTER(FlBatch)] + [P] * 8

@@ -38,8 +38,8 @@ std::atomic<uint64_t> g_launches{0};
 
 // Optional per-kernel timing (fl_profile_*): every launch is bracketed by CUDA events recorded on the
 // launching stream; fl_profile_collect turns them into per-kernel totals.  Off by default.
-enum KernelId : int { K_BFS = 0, K_RESET, K_STEP, K_OBSERVE, K_WALKS, K_COUNT };
-const char *const kKernelNames[K_COUNT] = {"k_bfs", "k_reset", "k_step", "k_observe", "k_walks"};
+enum KernelId : int { K_BFS = 0, K_RESET, K_STEP, K_OBSERVE, K_WALKS, K_OBSERVE_INDEX, K_OBSERVE_TREES, K_COUNT };
+const char *const kKernelNames[K_COUNT] = {"k_bfs", "k_reset", "k_step", "k_observe", "k_walks", "k_observe_index", "k_observe_trees"};
 struct ProfRec { int id; cudaEvent_t a, b; };
 std::mutex g_prof_mu;
 bool g_prof_on = false;
@@ -111,20 +111,25 @@ int knob(int k) { return g_knob[k].load(std::memory_order_relaxed); }
 // count for which the core fits (more resident warps hide the latency of the table lookups, which then go to L2).
 // What is left of the budget takes the static walk tables in the order of their use per visited cell.
 // fl_observe_override("ctas" / "tables" / "nt", ...) override (tuning only).
-ObsLayout make_obs_layout(const FlBatch *b, int nt, int *ctas_out = nullptr) {
-    const int N = (int)b->N, Rmax = (int)(b->state_stride / 4);
+ObsLayout make_obs_layout(const FlBatch *b, int nt, int mode, int parts, int *ctas_out = nullptr) {
+    const int N = (int)b->N, Rmax = (int)(b->state_stride / 4), Np = (N + 3) & ~3;
     ObsLayout L;
     int off = 0;
     auto take = [&](long long bytes) { const int o = off; off = align_up(off + (int)bytes, 128); return o; };
+    L.parts = mode == OBS_FUSED ? 0 : parts;
+    // FlBatch.obs_ws of the split launch: [header 16 B | six agent arrays] [occupancy words | bucket offsets | filter]
+    L.ws_ag = 0; L.ws_ag_bytes = (4 + 6 * Np) * 4;
+    L.ws_idx = L.ws_ag_bytes; L.ws_idx_bytes = Rmax * 4 + (Rmax + 4) * 4 + Rmax * 32;
     L.bar = take(32);
     L.part = take(128);
-    L.ag = take((long long)OBS_AGENT_WORDS * N * 4);
-    L.dl = take(18 * N);
+    L.ag = take(mode == OBS_TREES ? (long long)L.ws_ag_bytes : (long long)(4 + 6 * Np + 5 * N) * 4);
+    L.dl = mode == OBS_TREES ? 0 : take(26 * N + 8);
     L.ci = take((long long)Rmax * 4);
-    L.ks = take((long long)(Rmax + 2) * 4);
+    L.ks = take((long long)(Rmax + 4) * 4);
     L.bm = take((long long)Rmax * 32);                          // time-slot filter of the prediction index: one / two entries per slot
-    L.seg_cap = 10 * N;                                         // path segments of phase 3 share the room of the phase-4 queues
+    L.seg_cap = mode == OBS_TREES ? 0 : 10 * N;                 // path segments of phase 3 share the room of the phase-4 queues
     if (L.seg_cap < (nt / 32) * 64) L.seg_cap = (nt / 32) * 64;
+    L.sq_words = L.seg_cap * 2;
     int seg_cap_use = L.seg_cap;                                // "segcap" / "entcap" overrides (tests): smaller capacities in
     if (knob(KNOB_SEGCAP) >= 0 && knob(KNOB_SEGCAP) < seg_cap_use) seg_cap_use = knob(KNOB_SEGCAP);                            // the same room,
     L.sq = take((long long)L.seg_cap * 8);                      // per-warp queues of the full conflict checks / segment pool
@@ -136,6 +141,7 @@ ObsLayout make_obs_layout(const FlBatch *b, int nt, int *ctas_out = nullptr) {
     const long long core = off + ridx_b + ent_typ + 3 * 128;
     int want_tables = 0x77;                                     // bit k: wlist, wrec, sdist, (srec: unused by k_observe), whoff, whits
     if (knob(KNOB_TABLES) >= 0) want_tables = knob(KNOB_TABLES);
+    if (mode == OBS_TREES) want_tables &= ~0x40;                // the tree kernel never reads the grid
     const int max_ctas = nt >= 1024 ? 1 : nt == 512 ? 2 : nt == 256 ? 4 : nt == 128 ? 8 : 12;
     int ctas = 0;
     if (knob(KNOB_CTAS) >= 0) ctas = knob(KNOB_CTAS) > 0 ? knob(KNOB_CTAS) : 1;
@@ -187,6 +193,31 @@ int obs_threads(const FlBatch *b) {
     if (per_sm >= 3) return 256;
     if (per_sm >= 2) return 512;
     return b->N > 128 ? 1024 : 512;
+}
+
+// CTAs per environment of the tree kernel (0 = fused kernel).  Fused is the default while a wave of one-CTA-per-environment
+// fills the chip's CTA slots; few large environments are split so that the trees of one environment spread over several SMs.
+int obs_parts(const FlBatch *b) {
+    if (!b->obs_ws || b->ws_stride <= 0) return 0;
+    const int v = knob(KNOB_PARTS);
+    if (v >= 0) return v > 32 ? 32 : v;
+    if (b->E >= 2 * 148) return 0;
+    int p = (int)(148 / b->E);                                   // one wave of tree CTAs over the SMs
+    const int by_agents = (int)(b->N / 16) > 0 ? (int)(b->N / 16) : 1;
+    if (p > by_agents) p = by_agents;
+    if (p > 32) p = 32;
+    return p <= 1 ? 0 : p;
+}
+
+// threads per CTA of the tree kernel: one warp per agent at a time; enough warps to cover its share of the agents
+int tree_threads(const FlBatch *b, int parts) {
+    const int v = knob(KNOB_NT);
+    if (v == 64 || v == 128 || v == 256 || v == 512 || v == 1024) return v;
+    const long long per = (b->N + parts - 1) / parts;           // agents per CTA
+    if (per >= 192) return 1024;
+    if (per >= 96) return 512;
+    if (per >= 32) return 256;
+    return 128;
 }
 
 int finish(cudaError_t launch_err) { return launch_err == cudaSuccess ? FL_OK : (int)launch_err; }
@@ -315,26 +346,42 @@ int fl_observe(const FlBatch *b, float *d_agent_attr, float *d_forest, int32_t *
         return FL_ERR_BAD_ARG;
     if (!b->srec || !b->wrec || !b->whoff || !b->wlist || !b->whits || !b->kcls || !b->sdist || !b->gtab || !b->ridx || !b->walk_total) return FL_ERR_BAD_ARG;   // fl_walk_tables first
     cudaStream_t st = (cudaStream_t)stream;
-    const int nt = obs_threads(b);
-    int ctas = 1;
-    const ObsLayout lay = make_obs_layout(b, nt, &ctas);
-    if (lay.total > SMEM_MAX) return FL_ERR_SMEM;
     using Kern = void (*)(FlBatch, ObsLayout, float *, float *, int32_t *, int32_t *, int32_t *, uint8_t *, float *);
-    // the register budget follows the number of CTAs the shared-memory plan lets share an SM
-    Kern kern;
-    if (nt == 64) kern = ctas > 8 ? k_observe<64, 12> : k_observe<64, 8>;
-    else if (nt == 128) kern = ctas > 6 ? k_observe<128, 8> : ctas > 4 ? k_observe<128, 6> : k_observe<128, 4>;
-    else if (nt == 256) kern = ctas > 3 ? k_observe<256, 4> : ctas > 2 ? k_observe<256, 3> : k_observe<256, 2>;
-    else if (nt == 512) kern = ctas > 1 ? k_observe<512, 2> : k_observe<512, 1>;
-    else kern = k_observe<1024, 1>;
-    if (lay.total > 48 * 1024) {
-        cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, lay.total);
-        if (err != cudaSuccess) return (int)err;
-    }
-    LaunchScope ls(K_OBSERVE, st);
-    kern<<<(unsigned)b->E, nt, lay.total, st>>>(*b, lay, d_agent_attr, d_forest, d_adjacency, d_node_order, d_edge_order,
-                                                d_valid_actions, d_dist_target);
-    return finish(cudaGetLastError());
+    auto pick = [](int nt, int ctas, int mode) -> Kern {
+        // the register budget follows the number of CTAs the shared-memory plan lets share an SM
+#define FL_K(NT_, RES_) (mode == OBS_FUSED ? (Kern)k_observe<NT_, RES_, OBS_FUSED> : mode == OBS_INDEX ? (Kern)k_observe<NT_, RES_, OBS_INDEX> : (Kern)k_observe<NT_, RES_, OBS_TREES>)
+        if (nt == 64) return ctas > 8 ? FL_K(64, 12) : FL_K(64, 8);
+        if (nt == 128) return ctas > 6 ? FL_K(128, 8) : ctas > 4 ? FL_K(128, 6) : FL_K(128, 4);
+        if (nt == 256) return ctas > 3 ? FL_K(256, 4) : ctas > 2 ? FL_K(256, 3) : FL_K(256, 2);
+        if (nt == 512) return ctas > 1 ? FL_K(512, 2) : FL_K(512, 1);
+        return FL_K(1024, 1);
+#undef FL_K
+    };
+    auto launch = [&](int mode, int nt, int parts, int kid) -> int {
+        int ctas = 1;
+        const ObsLayout lay = make_obs_layout(b, nt, mode, parts, &ctas);
+        if (lay.total > SMEM_MAX) return FL_ERR_SMEM;
+        Kern kern = pick(nt, ctas, mode);
+        if (lay.total > 48 * 1024) {
+            cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, lay.total);
+            if (err != cudaSuccess) return (int)err;
+        }
+        LaunchScope ls(kid, st);
+        kern<<<(unsigned)(b->E * (mode == OBS_TREES ? parts : 1)), nt, lay.total, st>>>(*b, lay, d_agent_attr, d_forest, d_adjacency, d_node_order,
+                                                                                       d_edge_order, d_valid_actions, d_dist_target);
+        return finish(cudaGetLastError());
+    };
+    const int parts = obs_parts(b);
+    if (parts == 0) return launch(OBS_FUSED, obs_threads(b), 0, K_OBSERVE);
+    if (b->ws_stride < fl_observe_ws_words(b)) return FL_ERR_BAD_ARG;
+    if (int rc = launch(OBS_INDEX, obs_threads(b), parts, K_OBSERVE_INDEX)) return rc;
+    return launch(OBS_TREES, tree_threads(b, parts), parts, K_OBSERVE_TREES);
+}
+
+int64_t fl_observe_ws_words(const FlBatch *b) {
+    if (!b || b->N <= 0 || b->state_stride <= 0) return 0;
+    const int64_t Np = (b->N + 3) & ~(int64_t)3, Rmax = b->state_stride / 4;
+    return 4 + 6 * Np + Rmax + (Rmax + 4) + 8 * Rmax;
 }
 
 int fl_batch_slice(const FlBatch *b, int64_t e0, int64_t n, FlBatch *out) {
@@ -351,7 +398,7 @@ int fl_batch_slice(const FlBatch *b, int64_t e0, int64_t n, FlBatch *out) {
     FL_ADV(rc, N * 2) FL_ADV(old_rc, N * 2) FL_ADV(dir, N) FL_ADV(old_dir, N) FL_ADV(state, N) FL_ADV(ctr, N) FL_ADV(mal, N)
     FL_ADV(saved, N) FL_ADV(sig_mal, N) FL_ADV(deadlocked, N) FL_ADV(done, N) FL_ADV(nmal, N) FL_ADV(arrival, N)
     FL_ADV(elapsed, 1) FL_ADV(sched_pos, 1) FL_ADV(done_all, 1) FL_ADV(status, 1)
-    FL_ADV(stats, 4) FL_ADV(entries, b->ent_cap) FL_ADV(segs, b->seg_stride) FL_ADV(debug_clocks, 16)
+    FL_ADV(stats, 4) FL_ADV(entries, b->ent_cap) FL_ADV(segs, b->seg_stride) FL_ADV(debug_clocks, 32) FL_ADV(obs_ws, b->ws_stride)
 #undef FL_ADV
     return FL_OK;
 }
@@ -377,12 +424,18 @@ cudaEvent_t chunk_event(int k) {
 int fl_observe_plan(const FlBatch *b, int32_t *out, int n_out) {
     if (int rc = check_batch(b)) return rc;
     if (!out || n_out < 20) return FL_ERR_BAD_ARG;
-    const int nt = obs_threads(b);
+    const int nt = obs_threads(b), parts = obs_parts(b);
     int ctas = 1;
-    const ObsLayout L = make_obs_layout(b, nt, &ctas);
+    const ObsLayout L = make_obs_layout(b, nt, parts ? OBS_INDEX : OBS_FUSED, parts, &ctas);
     const int v[20] = {nt, L.total, ctas, L.ent_cap, L.kcls, L.grid, L.ci, L.ks, L.ent, L.sdist,
                        L.ridx, L.srec, L.wrec, L.whoff, L.wlist, L.ag, L.dl, L.part, SMEM_MAX / (L.total + 1024), L.whits};
     for (int k = 0; k < 20; k++) out[k] = v[k];
+    if (n_out >= 24) {                                          // the split launch: parts, and the tree kernel's threads / bytes / CTAs per SM
+        int tctas = 0;
+        const int tnt = parts ? tree_threads(b, parts) : 0;
+        const ObsLayout T = parts ? make_obs_layout(b, tnt, OBS_TREES, parts, &tctas) : L;
+        out[20] = parts; out[21] = tnt; out[22] = parts ? T.total : 0; out[23] = tctas;
+    }
     return FL_OK;
 }
 

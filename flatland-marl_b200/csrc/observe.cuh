@@ -38,7 +38,18 @@ constexpr int I_INF = 0x7fffffff;
 struct ObsLayout {   // byte offsets into dynamic shared memory (host: make_obs_layout); < 0 = lives in global memory
     int bar, part, ag, dl, ci, ks, bm, sq, seg_cap, sort_small, kcls, grid, ridx, ent, ent_cap, total;
     int srec, wrec, whoff, whits, wlist, sdist;   // static walk tables (walks.cuh)
+    int sq_words;                                 // uint32 words of the sq region (seg_cap may be lowered by a test override)
+    int parts;                                    // split launch: CTAs per environment of the tree kernel (0 = fused kernel)
+    int ws_ag, ws_idx, ws_ag_bytes, ws_idx_bytes; // split launch: byte offsets / sizes of the two blocks of FlBatch.obs_ws
 };
+
+// k_observe comes in three shapes.  OBS_FUSED: one CTA per environment does everything (the headline shape: all of the
+// working set stays in shared memory).  OBS_INDEX + OBS_TREES: the same code cut after phase 3 — the first kernel (one CTA
+// per environment) builds the loader view, the deadlock flags, the prediction index and the attribute vectors and leaves
+// the index in FlBatch.obs_ws; the second (`parts` CTAs per environment) stages it back into shared memory with bulk
+// copies and walks the trees of every parts-th agent.  Few large environments (Test_14: 64 x 425 agents) then fill the
+// chip, and many small ones are cut into more, smaller units of work than there are CTA slots.
+enum : int { OBS_FUSED = 0, OBS_INDEX = 1, OBS_TREES = 2 };
 
 // ---- mbarrier + 1-D TMA bulk copy (global -> shared), sm_90+ ------------------------------------
 DEVI uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -175,32 +186,27 @@ DEVI int valid_actions_of(const uint16_t *g, int W, int st, int ctr, int r, int 
 // _check_blocked / _fix_deps (deadlock_checker.cpp:11-110) with the recursion turned into an explicit
 // stack.  Runs on one lane per environment while the other warps walk predictions and trees.
 struct DeadlockScratch {
-    uint8_t *checked, *ndep, *dl, *ct, *stk_d, *stk_phase;
+    uint8_t *checked, *ndep, *dl, *ct, *stk_d, *stk_phase;   // ct: transitions nibble of the agent's (cell, direction) | 16 if the agent is ACTIVE (on the map)
     uint16_t *dep, *stk_h, *stk_opp;
-    const int *cellid;
+    int16_t *opp;      // [N][4] the ACTIVE agent standing on the neighbour cell in direction dd (highest handle), -1 = none:
+                       // filled by all threads before the serial lane starts (deadlock_checker.cpp:15-20 agent_positions)
 };
 
-DEVI void update_deadlocks(const DeadlockScratch &x, const uint32_t *ci, const uint16_t *ridx, int N, int H, int W) {
+DEVI void update_deadlocks(const DeadlockScratch &x, int N) {
     for (int a0 = 0; a0 < N; a0++) {
-        if (x.cellid[a0] < 0 || x.dl[a0] || x.checked[a0]) continue;
+        if (!(x.ct[a0] & 16) || x.dl[a0] || x.checked[a0]) continue;
         int sp = 0;
         x.stk_h[0] = a0; x.stk_d[0] = 0; x.stk_phase[0] = 0; x.checked[a0] = 1; sp = 1;
         while (sp > 0) {
             const int f = sp - 1, h = x.stk_h[f];
-            const int hr = x.cellid[h] / W, hc = x.cellid[h] % W;
             bool popped = false, pushed = false;
             while (x.stk_d[f] < 4) {
                 const int dd = x.stk_d[f];
                 int opp;
                 if (x.stk_phase[f] == 1) { opp = x.stk_opp[f]; x.stk_phase[f] = 0; }
                 else {
-                    if (!tbit(x.ct[h], dd)) { x.stk_d[f]++; continue; }
-                    const int rr = hr + d_row(dd), cc = hc + d_col(dd);
-                    opp = -1;
-                    if (rr >= 0 && cc >= 0 && rr < H && cc < W) {
-                        const unsigned ri = ridx[rr * W + cc];
-                        if (ri != 0xFFFFu) opp = (int)(ci[ri] >> 21) - 1;
-                    }
+                    if (!tbit(x.ct[h] & 15, dd)) { x.stk_d[f]++; continue; }
+                    opp = x.opp[h * 4 + dd];
                     if (opp < 0) { x.checked[h] = 2; popped = true; break; }           // road is free
                     if (x.dl[opp]) { x.stk_d[f]++; continue; }                          // road is blocked
                     if (x.checked[opp] == 0) {                                          // recurse
@@ -217,7 +223,7 @@ DEVI void update_deadlocks(const DeadlockScratch &x, const uint32_t *ci, const u
             if (pushed) continue;
             if (!popped && x.ndep[h] == 0) {
                 x.checked[h] = 2;
-                if (x.ct[h] != 0) x.dl[h] = 1;
+                if ((x.ct[h] & 15) != 0) x.dl[h] = 1;
             }
             sp--;
         }
@@ -333,13 +339,15 @@ DEVI unsigned warp_excl_scan(unsigned v, int lane, unsigned &total) {
     return x - v;
 }
 
-// NT threads per CTA, RES CTAs per SM the register budget is cut for
-template <int NT, int RES>
+// NT threads per CTA, RES CTAs per SM the register budget is cut for, MODE: OBS_FUSED / OBS_INDEX / OBS_TREES
+template <int NT, int RES, int MODE>
 __global__ void __launch_bounds__(NT, RES)
 k_observe(FlBatch b, ObsLayout lay, float *__restrict__ out_attr, float *__restrict__ out_forest,
           int32_t *__restrict__ out_adj, int32_t *__restrict__ out_norder, int32_t *__restrict__ out_eorder,
           uint8_t *__restrict__ out_valid, float *__restrict__ out_dist_target) {
-    const int e = blockIdx.x, N = (int)b.N, H = (int)b.H, W = (int)b.W;
+    const int e = MODE == OBS_TREES ? (int)blockIdx.x / lay.parts : (int)blockIdx.x;
+    const int part = MODE == OBS_TREES ? (int)blockIdx.x - e * lay.parts : 0, n_parts = MODE == OBS_TREES ? lay.parts : 1;
+    const int N = (int)b.N, H = (int)b.H, W = (int)b.W;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     extern __shared__ __align__(128) unsigned char obs_smem[];
     unsigned char *const smraw = obs_smem;
@@ -371,30 +379,42 @@ k_observe(FlBatch b, ObsLayout lay, float *__restrict__ out_attr, float *__restr
     uint64_t *bar = reinterpret_cast<uint64_t *>(smraw + lay.bar);
     int *s_misc = reinterpret_cast<int *>(smraw + lay.bar + 16);
 
+    // the first six arrays (+ a 16-byte header in front of them: entries, longest time per cell) are what the tree phase
+    // reads; the split launch hands exactly this block from the index kernel to the tree kernel
+    const int Np = (N + 3) & ~3;
+    uint32_t *ws_hdr = reinterpret_cast<uint32_t *>(smraw + lay.ag);
     ObsAgents A;
     {
-        uint32_t *p = reinterpret_cast<uint32_t *>(smraw + lay.ag);
-        A.vrc = p; p += N; A.sid0 = p; p += N; A.info = p; p += N;
-        A.speed = reinterpret_cast<float *>(p); p += N; A.dt = reinterpret_cast<float *>(p); p += N;
+        uint32_t *p = ws_hdr + 4;
+        A.vrc = p; p += Np; A.sid0 = p; p += Np; A.info = p; p += Np;
+        A.speed = reinterpret_cast<float *>(p); p += Np; A.dt = reinterpret_cast<float *>(p); p += Np;
+        A.rec_b = p; p += Np;
         A.cellid = reinterpret_cast<int *>(p); p += N; A.initcell = reinterpret_cast<int *>(p); p += N;
-        A.rec_a = p; p += N; A.rec_b = p; p += N; A.m0 = p; p += N; A.m1 = p; p += N;
+        A.rec_a = p; p += N; A.m0 = p; p += N; A.m1 = p; p += N;
     }
+    uint32_t *g_ws = b.obs_ws ? b.obs_ws + (size_t)e * b.ws_stride : nullptr;
     DeadlockScratch D;
     {
         uint16_t *p = reinterpret_cast<uint16_t *>(smraw + lay.dl);
         D.dep = p; p += 4 * N; D.stk_h = p; p += N; D.stk_opp = p; p += N;
         uint8_t *q = reinterpret_cast<uint8_t *>(p);
-        D.checked = q; q += N; D.ndep = q; q += N; D.dl = q; q += N; D.ct = q; q += N; D.stk_d = q; q += N; D.stk_phase = q;
-        D.cellid = A.cellid;
+        D.checked = q; q += N; D.ndep = q; q += N; D.dl = q; q += N; D.ct = q; q += N; D.stk_d = q; q += N; D.stk_phase = q; q += N;
+        D.opp = reinterpret_cast<int16_t *>(q + (N & 1));
     }
 
     // optional phase timestamps (tuning only): FlBatch.debug_clocks [E][16] int64, NULL = off
-    int64_t *dbg = b.debug_clocks ? b.debug_clocks + (size_t)e * 16 : nullptr;
-#define OBS_TICK(k) do { if (dbg && tid == 0) dbg[k] = clock64(); } while (0)
-    if (dbg && tid == 0) { dbg[15] = clock64(); dbg[12] = 0; dbg[13] = 0; dbg[14] = 0; }
+    // [E][32]: slots 0..15 of the fused / index kernel, 16.. of the tree kernel of a split launch (its CTA 0 of the environment)
+    int64_t *dbg = b.debug_clocks && part == 0 ? b.debug_clocks + (size_t)e * 32 : nullptr;
+#define OBS_TICK(k) do { if (dbg && tid == 0) dbg[(MODE == OBS_TREES ? 16 : 0) + (k)] = clock64(); } while (0)
+    if (dbg && tid == 0) {
+        dbg[MODE == OBS_TREES ? 31 : 15] = clock64();
+        if (MODE != OBS_TREES || n_parts == 1) { dbg[12] = 0; dbg[13] = 0; dbg[14] = 0; }
+    }
     // ---- phase 0: TMA bulk copies of the static world ---------------------------------------------
-    const bool use_tma = lay.grid >= 0 || lay.ridx >= 0 || lay.srec >= 0 || lay.wrec >= 0 || lay.whoff >= 0 || lay.whits >= 0 ||
-                         lay.wlist >= 0 || lay.kcls >= 0 || lay.sdist >= 0;
+    const bool use_tma = MODE == OBS_TREES || lay.grid >= 0 || lay.ridx >= 0 || lay.srec >= 0 || lay.wrec >= 0 || lay.whoff >= 0 ||
+                         lay.whits >= 0 || lay.wlist >= 0 || lay.kcls >= 0 || lay.sdist >= 0;
+    uint32_t *ent = reinterpret_cast<uint32_t *>(smraw + lay.ent);
+    uint32_t *const ent_s = ent;                   // the shared-memory copy (typed loads are cheaper than generic ones)
     if (use_tma && tid == 0) {
         mbar_init(bar, 1);
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -405,7 +425,24 @@ k_observe(FlBatch b, ObsLayout lay, float *__restrict__ out_attr, float *__restr
         const uint32_t hb = lay.whits >= 0 ? (uint32_t)(b.whits_stride * 4) : 0u;
         const uint32_t kb = lay.kcls >= 0 ? (uint32_t)(SS / 2) : 0u;     // one uint16 per rail cell
         const uint32_t db = lay.sdist >= 0 ? (uint32_t)(b.n_slots * SS * 2) : 0u;
-        mbar_expect_tx(bar, gb + rb + lb + hb + kb + db + (lay.srec >= 0 ? sb : 0u) + (lay.wrec >= 0 ? 4 * sb : 0u) + (lay.whoff >= 0 ? sb : 0u));
+        // split launch, tree kernel: the index the first kernel left in FlBatch.obs_ws comes back with four bulk copies
+        // (agent block, occupancy words, bucket offsets, time-slot filter) and the entries with a fifth when they fit
+        uint32_t wsb = 0, eb = 0;
+        if (MODE == OBS_TREES) {
+            const int n_ent_g = (int)g_ws[0];
+            wsb = (uint32_t)(lay.ws_ag_bytes + lay.ws_idx_bytes);
+            eb = (n_ent_g <= lay.ent_cap && !(b.ent_cap & 3)) ? (uint32_t)((n_ent_g * 4 + 15) & ~15) : 0u;   // 16-byte aligned blocks only
+        }
+        mbar_expect_tx(bar, wsb + eb + gb + rb + lb + hb + kb + db + (lay.srec >= 0 ? sb : 0u) + (lay.wrec >= 0 ? 4 * sb : 0u) + (lay.whoff >= 0 ? sb : 0u));
+        if (MODE == OBS_TREES) {
+            const unsigned char *gw = reinterpret_cast<const unsigned char *>(g_ws);
+            const uint32_t Rb = (uint32_t)(SS / 4) * 4u;                     // bytes of one uint32 per rail cell (capacity)
+            tma_load_1d(smraw + lay.ag, gw, (uint32_t)lay.ws_ag_bytes, bar);
+            tma_load_1d(smraw + lay.ci, gw + lay.ws_idx, Rb, bar);
+            tma_load_1d(smraw + lay.ks, gw + lay.ws_idx + Rb, Rb + 16u, bar);
+            tma_load_1d(smraw + lay.bm, gw + lay.ws_idx + 2u * Rb + 16u, 8u * Rb, bar);
+            if (eb) tma_load_1d(smraw + lay.ent, b.entries + (size_t)e * b.ent_cap, eb, bar);
+        }
         if (gb) tma_load_1d(smraw + lay.grid, g_grid, gb, bar);
         if (rb) tma_load_1d(smraw + lay.ridx, g_ridx, rb, bar);
         if (kb) tma_load_1d(smraw + lay.kcls, b.kcls + (size_t)e * SS, kb, bar);
@@ -417,9 +454,11 @@ k_observe(FlBatch b, ObsLayout lay, float *__restrict__ out_attr, float *__restr
         if (lb) tma_load_1d(smraw + lay.wlist, g_wlist, lb, bar);
     }
     // zero the bucket counters and the occupancy words
-    for (int k = tid; k <= R + 1; k += NT) ks[k - 1] = 0;
-    for (int k = tid; k < R; k += NT) ci[k] = 0;
-    for (int k = tid; k < R * 4; k += NT) bm[k] = make_uint2(0u, 0u);
+    if (MODE != OBS_TREES) {
+        for (int k = tid; k <= R + 1; k += NT) ks[k - 1] = 0;
+        for (int k = tid; k < R; k += NT) ci[k] = 0;
+        for (int k = tid; k < R * 4; k += NT) bm[k] = make_uint2(0u, 0u);
+    }
     const float T_ = (float)b.max_steps[e], Nf = (float)N;
     const Scale sc{T_, __frcp_rn(T_), Nf, __frcp_rn(Nf)};
     const int elapsed = b.elapsed[e];
@@ -427,6 +466,8 @@ k_observe(FlBatch b, ObsLayout lay, float *__restrict__ out_attr, float *__restr
     __syncthreads();                               // mbarrier initialised, counters zeroed
     OBS_TICK(0);
     if (use_tma) mbar_wait(bar, 0);
+    int tpc_max = 0;
+    if (MODE != OBS_TREES) {
 
     // ---- phase 1: loader view (loader.cpp:8-179, 221-327) -----------------------------------------
     for (int i = tid; i < N; i += NT) {
@@ -449,10 +490,13 @@ k_observe(FlBatch b, ObsLayout lay, float *__restrict__ out_attr, float *__restr
                     ((uint32_t)min(tpc, 255) << 24);
         A.speed[i] = speed;
         atomicMax(&s_misc[2], min(tpc, 255));
-        A.cellid[i] = on_map(st) ? r * W + c : -1;
+        // the tree's occupancy maps take every agent that is not off the map and has a position (treeobs.cpp:74-80): the trains
+        // on the map and — a case only the second episode after an in-place reset produces — a train standing on its target
+        // in state DONE (see reset_env in step.cuh); the deadlock checker looks at ACTIVE agents only (D.ct bit 4)
+        A.cellid[i] = (!off_map(st) && r >= 0) ? r * W + c : -1;
         A.initcell[i] = off_map(st) ? ip.x * W + ip.y : -1;
         const int trans = on_map(st) ? (int)grid[r * W + c] : 0;
-        D.ct[i] = on_map(st) ? (uint8_t)nibble(trans, d) : 0;
+        D.ct[i] = on_map(st) ? (uint8_t)(nibble(trans, d) | 16) : 0;
         D.dl[i] = b.deadlocked[ea]; D.checked[i] = 0; D.ndep[i] = 0;
         const int va = valid_actions_of(grid, W, st, ctr, r, c, d);
         for (int k = 0; k < 5; k++) out_valid[ea * 5 + k] = (va >> k) & 1;
@@ -523,15 +567,36 @@ k_observe(FlBatch b, ObsLayout lay, float *__restrict__ out_attr, float *__restr
         }
     }
     __syncthreads();
+    // deadlock_checker.cpp:15-20 agent_positions, hoisted out of the serial lane: the highest ACTIVE handle per rail cell (in
+    // the still unused bucket counters), then for every active agent the occupant of each neighbour cell its transitions lead to
+    {
+        uint32_t *ca = ks;                            // ks[0..R) is zero until the counting pass of phase 3
+        for (int i = tid; i < N; i += NT)
+            if (D.ct[i] & 16) { const unsigned ri = ridx[A.cellid[i]]; if (ri != 0xFFFFu) atomicMax(&ca[ri], (uint32_t)(i + 1)); }
+        __syncthreads();
+        for (int k = tid; k < N * 4; k += NT) {
+            const int i = k >> 2, dd = k & 3;
+            int opp = -1;
+            if ((D.ct[i] & 16) && tbit(D.ct[i] & 15, dd)) {
+                const int cid = A.cellid[i], rr = cid / W + d_row(dd), cc = cid % W + d_col(dd);
+                if (rr >= 0 && cc >= 0 && rr < H && cc < W) {
+                    const unsigned ri = ridx[rr * W + cc];
+                    if (ri != 0xFFFFu) opp = (int)ld_vol_u32(&ca[ri]) - 1;
+                }
+            }
+            D.opp[k] = (int16_t)opp;
+        }
+        __syncthreads();
+        for (int k = tid; k < R; k += NT) ca[k] = 0;
+        __syncthreads();
+    }
     OBS_TICK(1);
 
     // ---- phase 2 (last warp, lane 0) || phase 3 (all other warps, named barrier 1): deadlocks, predictions ----
     const bool dl_warp = warp == NT / 32 - 1;
     constexpr int NW = NT - 32;                    // threads walking predictions
-    uint32_t *ent = reinterpret_cast<uint32_t *>(smraw + lay.ent);
-    uint32_t *const ent_s = ent;                   // the shared-memory copy (typed loads are cheaper than generic ones)
     if (dl_warp) {
-        if (lane == 0) { update_deadlocks(D, ci, ridx, N, H, W); if (dbg) dbg[8] = clock64(); }
+        if (lane == 0) { update_deadlocks(D, N); if (dbg) dbg[8] = clock64(); }
         __syncwarp();
         asm volatile("bar.sync 2, %0;" ::"r"(NT) : "memory");    // the prediction index is complete (the other warps only arrive)
         if (s_misc[0] > lay.ent_cap) ent = b.entries + (size_t)e * b.ent_cap;
@@ -654,15 +719,23 @@ k_observe(FlBatch b, ObsLayout lay, float *__restrict__ out_attr, float *__restr
                 if (s0 != 0xFFFFu) predict_path(wrec, whoff, whits, wlist, sdist + (size_t)slot * SS, s0, slot, (int)(info >> 24), i, scatter_emit);
             }
         named_bar_sync(1, NW);
+        OBS_TICK(4);
         // order every bucket: long-lived entries first, then by t0, so that the tree walk scans a time window only.
-        // Small buckets: insertion sort by one thread.  Large buckets (busy cells of large environments) are queued and
-        // sorted by a warp each: bitonic network on a copy padded to a power of two in the free tail of the spill space.
-        constexpr int SORT_BIG = 2048;
+        // Entries in shared memory: buckets up to sort_small by one thread each (insertion sort: 32 buckets per warp at a
+        // time), larger ones queued and sorted by a warp.  Entries spilled to global memory (large environments), where a
+        // dependent chain of loads per compare would cost an L2 round trip each: every bucket by a warp — up to 32 entries as
+        // one load, a bitonic network of register shuffles and one store; longer ones by a two-pass radix sort (5 + 5 bits
+        // of the 10-bit key) that streams the bucket through a scratch copy with coalesced loads.
         const int SORT_SMALL = lay.sort_small;
+        const bool in_smem = ent == ent_s;
         uint32_t *bigq = reinterpret_cast<uint32_t *>(smraw + lay.sq);          // the segment pool is no longer needed
-        const int bigq_cap = lay.seg_cap * 2;
-        uint32_t *scratch = b.entries + (size_t)e * b.ent_cap + (ent == ent_s ? 0 : n_ent);
-        const long long scratch_n = b.ent_cap - (ent == ent_s ? 0 : n_ent);
+        const int bigq_cap = lay.sq_words - 32 * (NT / 32);                     // its tail: 32 digit counters per warp
+        uint32_t *hist = bigq + bigq_cap + 32 * warp;
+        // scratch copy of a bucket at the same offsets: the free tail of the shared-memory entries, else the environment's
+        // global spill space (all of it while the entries are in shared memory, its tail otherwise)
+        uint32_t *g_ent = b.entries + (size_t)e * b.ent_cap;
+        uint32_t *scratch = in_smem ? (2 * n_ent <= lay.ent_cap ? ent_s + n_ent : g_ent)
+                                    : (2ll * n_ent <= (long long)b.ent_cap ? g_ent + n_ent : nullptr);
         auto insertion_sort = [&](int s0, int s1) {
             for (int x = s0 + 1; x < s1; x++) {
                 const uint32_t v = ent[x], kv = entry_sort_key(v);
@@ -671,73 +744,112 @@ k_observe(FlBatch b, ObsLayout lay, float *__restrict__ out_attr, float *__restr
                 ent[y + 1] = v;
             }
         };
-        for (int key = tid; key < R; key += NW) {
-            const int s0 = (int)ks[key - 1], s1 = (int)ks[key];
-            if (s1 - s0 <= SORT_SMALL) { insertion_sort(s0, s1); continue; }
-            const int pos = s1 - s0 <= SORT_BIG ? atomicAdd(&s_misc[1], 1) : bigq_cap;
-            if (pos < bigq_cap) bigq[pos] = (uint32_t)key; else insertion_sort(s0, s1);
-        }
-        named_bar_sync(1, NW);
-        {
-            const int n_big = min(ld_vol_i32(&s_misc[1]), bigq_cap);
-            uint32_t *my = scratch + (size_t)warp * (2 * SORT_BIG), *stage = my + SORT_BIG;     // P <= SORT_BIG pairs, n <= SORT_BIG staged entries
-            const bool have_scratch = (long long)(warp + 1) * (2 * SORT_BIG) <= scratch_n;
-            for (int q = warp; q < n_big; q += NW / 32) {
-                const int key = (int)bigq[q], s0 = (int)ks[key - 1], n = (int)ks[key] - s0;
-                if (!have_scratch) { if (lane == 0) insertion_sort(s0, s0 + n); continue; }
-                int P = 64;
-                while (P < n) P <<= 1;
-                for (int x = lane; x < P; x += 32) my[x] = x < n ? ((entry_sort_key(ent[s0 + x]) << 22) | (uint32_t)x) : 0xFFFFFFFFu;   // key | index
+        // a whole warp sorts bucket [s0, s0 + n)
+        auto warp_sort = [&](int s0, int n) {
+            if (n <= 32) {                                                      // bitonic network in registers
+                const uint32_t v0 = lane < n ? ent[s0 + lane] : 0u;
+                uint32_t kv = lane < n ? ((entry_sort_key(v0) << 5) | (uint32_t)lane) : 0xFFFFFFFFu;   // key | source lane
+#pragma unroll
+                for (int k2 = 2; k2 <= 32; k2 <<= 1)
+#pragma unroll
+                    for (int j2 = k2 >> 1; j2 > 0; j2 >>= 1) {
+                        const uint32_t o = __shfl_xor_sync(0xFFFFFFFFu, kv, j2);
+                        const bool up = (lane & k2) == 0, low = (lane & j2) == 0;
+                        kv = (low == up) ? min(kv, o) : max(kv, o);
+                    }
+                const uint32_t v = __shfl_sync(0xFFFFFFFFu, v0, kv & 31u);
+                if (lane < n) ent[s0 + lane] = v;
+                return;
+            }
+            if (!scratch) { if (lane == 0) insertion_sort(s0, s0 + n); __syncwarp(); return; }
+            uint32_t *bufa = ent + s0, *bufb = scratch + s0;
+#pragma unroll 1
+            for (int pass = 0; pass < 2; pass++) {
+                const uint32_t *src = pass ? bufb : bufa;
+                uint32_t *dst = pass ? bufa : bufb;
+                const int sh = 5 * pass;
+                hist[lane] = 0;
                 __syncwarp();
-                for (int kk2 = 2; kk2 <= P; kk2 <<= 1)
-                    for (int jj = kk2 >> 1; jj > 0; jj >>= 1) {
-                        for (int x = lane; x < P; x += 32) {
-                            const int l = x ^ jj;
-                            if (l > x) {
-                                const uint32_t a = my[x], c = my[l];
-                                const bool up = (x & kk2) == 0;
-                                if ((a > c) == up) { my[x] = c; my[l] = a; }
-                            }
-                        }
-                        __syncwarp();
-                    }
-                // permute the bucket: the sorted (key, index) pairs say which entry goes where; entries travel through registers
-                for (int x0 = 0; x0 < n; x0 += 32 * 8) {
-                    uint32_t v[8];
-#pragma unroll
-                    for (int u = 0; u < 8; u++) { const int x = x0 + u * 32 + lane; v[u] = x < n ? ent[s0 + (my[x] & 0x3FFFFFu)] : 0u; }
-                    // all reads of this batch happen before any write only if the batch covers the bucket; otherwise stage through scratch
-                    if (n <= 32 * 8) {
-                        __syncwarp();
-#pragma unroll
-                        for (int u = 0; u < 8; u++) { const int x = x0 + u * 32 + lane; if (x < n) ent[s0 + x] = v[u]; }
-                    } else {
-#pragma unroll
-                        for (int u = 0; u < 8; u++) { const int x = x0 + u * 32 + lane; if (x < n) stage[x] = v[u]; }
-                    }
-                }
-                if (n > 32 * 8) {
+                for (int x = lane; x < n; x += 32) atomicAdd(&hist[(entry_sort_key(src[x]) >> sh) & 31u], 1u);
+                __syncwarp();
+                unsigned tot;
+                const unsigned c = hist[lane], base = warp_excl_scan(c, lane, tot);
+                __syncwarp();
+                hist[lane] = base;
+                __syncwarp();
+                for (int x0 = 0; x0 < n; x0 += 32) {                            // in order: the radix passes must be stable
+                    const int x = x0 + lane;
+                    const bool valid = x < n;
+                    const uint32_t v = valid ? src[x] : 0u;
+                    const unsigned dg = valid ? ((entry_sort_key(v) >> sh) & 31u) : 32u + (unsigned)lane;
+                    const unsigned m = __match_any_sync(0xFFFFFFFFu, dg);
+                    const int rank = __popc(m & ((1u << lane) - 1u));
+                    if (valid) dst[hist[dg] + rank] = v;
                     __syncwarp();
-                    for (int x = lane; x < n; x += 32) ent[s0 + x] = stage[x];
+                    if (valid && rank == 0) hist[dg] += (unsigned)__popc(m);
+                    __syncwarp();
                 }
-                __syncwarp();
+            }
+        };
+        if (in_smem) {
+            for (int key = tid; key < R; key += NW) {
+                const int s0 = (int)ks[key - 1], s1 = (int)ks[key];
+                if (s1 - s0 <= SORT_SMALL) { insertion_sort(s0, s1); continue; }
+                const int pos = atomicAdd(&s_misc[1], 1);
+                if (pos < bigq_cap) bigq[pos] = (uint32_t)key; else insertion_sort(s0, s1);
+            }
+            named_bar_sync(1, NW);
+            OBS_TICK(9);
+            const int n_big = min(ld_vol_i32(&s_misc[1]), bigq_cap);
+            for (int q = warp; q < n_big; q += NW / 32) {
+                const int key = (int)bigq[q], s0 = (int)ks[key - 1];
+                warp_sort(s0, (int)ks[key] - s0);
+            }
+        } else {
+            OBS_TICK(9);
+            for (int key = warp; key < R; key += NW / 32) {
+                const int s0 = (int)ks[key - 1], n = (int)ks[key] - s0;
+                if (n >= 2) warp_sort(s0, n);
             }
         }
         named_bar_sync(1, NW);
         if (tid == 0) s_misc[1] = 0;                // phase 4 takes its agents from this counter
         named_bar_sync(1, NW);
+        if (MODE == OBS_INDEX) {
+            // split launch: the index goes to FlBatch.obs_ws in the layout the tree kernel's bulk copies expect
+            // (header + agent block | occupancy words | bucket offsets from ks[-1] | time-slot filter), the entries to
+            // FlBatch.entries unless they already spilled there
+            const int Rcap = SS / 4;
+            if (tid == 0) { g_ws[0] = (uint32_t)n_ent; g_ws[1] = (uint32_t)ld_vol_i32(&s_misc[2]); g_ws[2] = 0u; g_ws[3] = 0u; }
+            for (int k = 4 + tid; k < 4 + 6 * Np; k += NW) g_ws[k] = ws_hdr[k];
+            uint32_t *gi = g_ws + lay.ws_idx / 4;
+            for (int k = tid; k < R; k += NW) gi[k] = ci[k];
+            for (int k = tid; k <= R + 1; k += NW) gi[Rcap + k] = ks[k - 1];
+            uint2 *gb = reinterpret_cast<uint2 *>(gi + 2 * Rcap + 4);
+            for (int k = tid; k < 4 * R; k += NW) gb[k] = bm[k];
+            if (ent == ent_s) {
+                uint32_t *ge = b.entries + (size_t)e * b.ent_cap;
+                for (int k = tid; k < n_ent; k += NW) ge[k] = ent_s[k];
+            }
+        }
         asm volatile("bar.arrive 2, %0;" ::"r"(NT) : "memory");  // lets the deadlock warp join phase 4 when it is done
     }
     OBS_TICK(3);
     if (dbg && tid == 0) dbg[10] = s_misc[0];
-    const int tpc_max = ld_vol_i32(&s_misc[2]);
+    tpc_max = ld_vol_i32(&s_misc[2]);
+    } else {
+        // tree kernel of the split launch: everything above arrived through the bulk copies
+        const int n_ent_g = (int)ws_hdr[0];
+        tpc_max = (int)ws_hdr[1];
+        if (n_ent_g > lay.ent_cap || (b.ent_cap & 3)) ent = b.entries + (size_t)e * b.ent_cap;
+    }
 
     // ---- phase 4: branch trees, one warp per agent, agents taken from a shared counter --------------------
     const bool spill = ent != ent_s;
     auto ent_at = [&](uint32_t i) { return spill ? ent[i] : ent_s[i]; };
-    while (true) {
+    while (MODE != OBS_INDEX) {
         int h = 0;
-        if (lane == 0) h = atomicAdd(&s_misc[1], 1);
+        if (lane == 0) h = part + n_parts * atomicAdd(&s_misc[1], 1);     // the tree kernel's CTA `part` takes every n_parts-th agent
         h = __shfl_sync(0xFFFFFFFFu, h, 0);
         if (h >= N) break;
         const size_t ea = (size_t)e * N + h;
@@ -1016,6 +1128,7 @@ k_observe(FlBatch b, ObsLayout lay, float *__restrict__ out_attr, float *__restr
     __syncthreads();
     OBS_TICK(5);
     if (tid == 0 && s_misc[3]) atomicOr(&b.status[e], FL_ST_BAD_CELL);
+    if (MODE == OBS_TREES) return;
     for (int i = tid; i < N; i += NT) b.deadlocked[(size_t)e * N + i] = D.dl[i];
     OBS_TICK(6);
 

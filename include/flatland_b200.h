@@ -74,12 +74,13 @@ typedef struct FlBatch {
     int64_t grid_stride; /* uint16 elements between the grids of consecutive envs, >= H*W, multiple of 8 */
     int64_t dist_stride; /* uint16 elements between the distance maps of consecutive envs,
                             >= n_slots*H*W*4, multiple of 8 (16-byte aligned blocks: moved by TMA bulk copies) */
-    int64_t *debug_clocks; /* tuning only: [E][16] SM-clock timestamps of k_observe's phases, NULL = off */
+    int64_t *debug_clocks; /* tuning only: [E][32] SM-clock timestamps of k_observe's phases, NULL = off */
     int64_t ridx_stride;   /* uint16 elements per env of ridx, >= H*W, multiple of 8 */
     int64_t state_stride;  /* elements per env of srec / wrec / whoff / kcls, >= 4 * rail cells, multiple of 32 */
     int64_t wlist_stride;  /* uint32 elements per env of wlist, multiple of 4, with 8 elements of slack at the end */
     int64_t whits_stride;  /* uint32 elements per env of whits, multiple of 4 */
     int64_t seg_stride;    /* uint64 elements per env of segs (0 = none) */
+    int64_t ws_stride;     /* uint32 elements per env of obs_ws: >= fl_observe_ws_words(b), multiple of 4 (0 = none: fused kernel only) */
 
     /* ---- world, static after upload (RailEnv.reset generators stay reference Python) ---- */
     const uint16_t *grid;      /* [E][grid_stride] transition bitmask per cell (core/transition_map.py:144) */
@@ -145,6 +146,9 @@ typedef struct FlBatch {
                                        when an environment's entries do not fit in shared memory; its free tail is
                                        the scratch of the sort of large buckets) */
     uint64_t *segs;       /* [E][seg_stride] path segments that do not fit in the shared-memory pool (spill space) */
+    uint32_t *obs_ws;     /* [E][ws_stride] split launch of fl_observe (k_observe as two kernels, see csrc/observe.cuh): the
+                                       prediction index of an environment between the index kernel and the tree kernel.
+                                       NULL = fl_observe always runs the fused kernel */
 } FlBatch;
 
 int fl_abi_version(void);
@@ -186,6 +190,10 @@ int fl_step(const FlBatch *b, const uint8_t *d_actions, int32_t *d_rewards, uint
 int fl_observe(const FlBatch *b, float *d_agent_attr, float *d_forest, int32_t *d_adjacency,
                int32_t *d_node_order, int32_t *d_edge_order, uint8_t *d_valid_actions,
                float *d_dist_target, void *stream);
+
+/* uint32 words per environment fl_observe's split launch needs in FlBatch.obs_ws (depends on N and state_stride: call it after
+ * fl_walk_tables sized the static tables). */
+int64_t fl_observe_ws_words(const FlBatch *b);
 
 /* Tuning and test hook (no reference counterpart): overrides one knob of the shared-memory / launch plan fl_observe derives
  * from the batch shape, process-wide, value < 0 = back to the default.  Keys: "nt" (threads per CTA: 64..1024), "ctas"

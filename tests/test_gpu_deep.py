@@ -55,10 +55,13 @@ def compare_row(g, batch, e, row, rew, don, name):
     assert crc(don) == int(g["crc_dones"][row]), "%s row %d dones" % (name, row)
 
 
-@pytest.mark.parametrize("name", deep_names())
-def test_cuda_matches_reference_deep_episode_and_second_episode(name):
+@pytest.mark.parametrize("name,parts", [(n, None) for n in deep_names()] + [("deep_t00_l1", 0), ("deep_t08_l0", 0), ("deep_t14_l0", 0)])
+def test_cuda_matches_reference_deep_episode_and_second_episode(obs_plan, name, parts):
+    """parts = None: the launch shape fl_observe picks for this small batch (the split launch); 0: the fused kernel."""
     import torch
     import flatland_marl_b200 as fb
+    if parts is not None:
+        obs_plan({"parts": parts})
     g = load_deep(name)
     N = int(g["N"])
     batch = fb.BatchedRailEnv([dict(g), dict(g)], sched_rows=len(g["sched"]), auto_reset=True)

@@ -18,6 +18,37 @@ RTOL = 1e-6          # the contract (BASELINE.json north_star): float features t
 BIT_EXACT_FLOATS = True   # what the kernels actually deliver, and what these tests demand: the same float32 bits
 
 
+PLANS = [
+    {"segcap": 3},                            # segment pool overflows into its global spill space
+    {"entcap": 16},                           # the prediction entries spill to global memory
+    {"segcap": 0, "entcap": 0},
+    {"sortsmall": 1},                         # every bucket with two or more entries takes the warp sort (bitonic network)
+    {"sortsmall": 1, "entcap": 0},            # ... with the entries and the sort scratch sharing the spill space
+    {"ctas": 1},                              # all static tables staged in shared memory (TMA bulk copies)
+    {"tables": 0},                            # all static tables read from global memory
+    {"nt": 64}, {"nt": 128}, {"nt": 256}, {"nt": 512}, {"nt": 1024},
+    # fused kernel / split launch (index kernel + `parts` tree CTAs per environment), forced either way
+    {"parts": 0}, {"parts": 0, "entcap": 0, "sortsmall": 1}, {"parts": 1}, {"parts": 2}, {"parts": 3, "nt": 64}, {"parts": 7, "entcap": 0},
+    {"parts": 2, "tables": 0}, {"parts": 4, "ctas": 1}, {"parts": 2, "sortsmall": 1, "segcap": 0},
+]
+
+
+@pytest.fixture
+def obs_plan():
+    """Sets fl_observe_override knobs for one test and puts the defaults back afterwards."""
+    import flatland_marl_b200 as fb
+    lib = fb._lib.lib()
+    used = []
+
+    def set_plan(plan):
+        for k, v in plan.items():
+            assert lib.fl_observe_override(k.encode(), int(v)) == 0
+            used.append(k)
+    yield set_plan
+    for k in used:
+        lib.fl_observe_override(k.encode(), -1)
+
+
 def _first_bad(a, b):
     bad = np.argwhere(np.asarray(a) != np.asarray(b))
     return None if len(bad) == 0 else tuple(int(x) for x in bad[0])
@@ -102,9 +133,13 @@ def run_against_oracle(worlds, actions, scheds, n_steps, check_every=1):
     return batch
 
 
-@pytest.mark.parametrize("name", golden_names())
-def test_cuda_matches_golden_and_oracle(golden, name):
-    """Same world, actions and schedule as the reference run that produced the fixture."""
+@pytest.mark.parametrize("name,parts", [(n, None) for n in golden_names()] +
+                         [(n, 0) for n in ("t00_l1_greedy", "t02_l2_stacking", "t03_l0_random", "t08_l0_greedy", "simple_rail_n4")])
+def test_cuda_matches_golden_and_oracle(golden, obs_plan, name, parts):
+    """Same world, actions and schedule as the reference run that produced the fixture.  parts = None: the launch shape
+    fl_observe picks for a two-environment batch (the split launch); parts = 0: the fused kernel of the large batches."""
+    if parts is not None:
+        obs_plan({"parts": parts})
     g = golden(name)
     n_steps = int(g["n_steps"])
     # env 0 replays the golden action stream; env 1 a different stream on the same world
@@ -203,34 +238,6 @@ def test_rail_cycle_world_matches_oracle(n_agents):
     sched = np.zeros((w["T"], n_agents), np.uint8)
     sched[7, 0] = 5                                   # one malfunction for good measure
     run_against_oracle([w, w, w], acts, [sched, sched, sched], w["T"])
-
-
-PLANS = [
-    {"segcap": 3},                            # segment pool overflows into its global spill space
-    {"entcap": 16},                           # the prediction entries spill to global memory
-    {"segcap": 0, "entcap": 0},
-    {"sortsmall": 1},                         # every bucket with two or more entries takes the warp sort (bitonic network)
-    {"sortsmall": 1, "entcap": 0},            # ... with the entries and the sort scratch sharing the spill space
-    {"ctas": 1},                              # all static tables staged in shared memory (TMA bulk copies)
-    {"tables": 0},                            # all static tables read from global memory
-    {"nt": 64}, {"nt": 128}, {"nt": 256}, {"nt": 512}, {"nt": 1024},
-]
-
-
-@pytest.fixture
-def obs_plan():
-    """Sets fl_observe_override knobs for one test and puts the defaults back afterwards."""
-    import flatland_marl_b200 as fb
-    lib = fb._lib.lib()
-    used = []
-
-    def set_plan(plan):
-        for k, v in plan.items():
-            assert lib.fl_observe_override(k.encode(), int(v)) == 0
-            used.append(k)
-    yield set_plan
-    for k in used:
-        lib.fl_observe_override(k.encode(), -1)
 
 
 @pytest.mark.parametrize("plan", PLANS, ids=lambda d: ",".join("%s=%s" % kv for kv in d.items()))

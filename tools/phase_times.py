@@ -26,11 +26,16 @@ for t in range(steps):
     batch.step(a)
     if t >= steps - 20:
         acc.append(batch.debug_clocks.cpu().numpy().copy())
-d = np.stack(acc).astype(np.float64)          # [20, E, 16]
+d = np.stack(acc).astype(np.float64)          # [20, E, 32]
+split = batch.observe_plan().get("parts", 0) > 0
 t0 = d[..., 15]
-names = [("setup+zero", 15, 0), ("tma wait+loader+occupancy", 0, 1), ("path chains + count pass", 1, 2), ("scan+scatter pass+sort", 2, 3),
+names = [("setup+zero", 15, 0), ("tma wait+loader+occupancy+deadlock neighbours", 0, 1), ("path chains + count pass", 1, 2),
+         ("scan+scatter pass", 2, 4), ("small sorts (thread per bucket)", 4, 9), ("warp sorts", 9, 3),
          ("trees (structure+features)", 3, 5), ("attributes", 6, 7)]
-tot = d[..., 7] - t0
+if split:
+    names[6] = ("index dump", 3, 5)
+    names += [("TREES kernel: bulk loads", 31, 16), ("TREES kernel: trees (CTA 0 of the env)", 16, 21)]
+tot = d[..., 7] - t0 + ((d[..., 21] - d[..., 31]) if split else 0)
 print("%s E=%d N=%d: mean cycles per env %.0f (p50 %.0f, p99 %.0f, max %.0f)" % (cfg, E, N, tot.mean(), np.median(tot), np.percentile(tot, 99), tot.max()))
 for nm, a, b in names:
     x = d[..., b] - d[..., a]
