@@ -35,7 +35,7 @@ class FlObsBuffers(C.Structure):
 
 
 EXPORTS = ["fl_abi_version", "fl_batch_sizeof", "fl_error_string", "fl_distance_map", "fl_walk_tables", "fl_reset", "fl_reset_ex", "fl_step",
-           "fl_observe", "fl_observe_override", "fl_observe_plan", "fl_observe_ws_words", "fl_batch_slice", "fl_step_observe_host", "fl_launch_count", "fl_profile_num_kernels", "fl_profile_kernel_name",
+           "fl_observe", "fl_observe_override", "fl_observe_plan", "fl_observe_ws_words", "fl_batch_slice", "fl_step_observe_host", "fl_step_observe_host_compact", "fl_wire_bytes", "fl_host_threads", "fl_launch_count", "fl_profile_num_kernels", "fl_profile_kernel_name",
            "fl_profile_enable", "fl_profile_collect"]
 
 _lib = None
@@ -71,6 +71,13 @@ def lib():
     L.fl_observe.argtypes = [C.POINTER(FlBatch)] + [P] * 8
     L.fl_step_observe_host.argtypes = [C.POINTER(FlBatch), P, P, C.POINTER(FlObsBuffers), C.POINTER(FlObsBuffers),
                                        C.c_uint32, C.c_int, P, P]
+    L.fl_step_observe_host_compact.argtypes = [C.POINTER(FlBatch), P, P, C.POINTER(FlObsBuffers), C.POINTER(FlObsBuffers), P, P,
+                                               C.POINTER(C.c_uint64), C.c_uint32, C.c_int, P, P]
+    L.fl_step_observe_host_compact.restype = C.c_int
+    L.fl_wire_bytes.argtypes = [C.POINTER(FlBatch), C.c_int]
+    L.fl_wire_bytes.restype = C.c_size_t
+    L.fl_host_threads.argtypes = [C.c_int]
+    L.fl_host_threads.restype = C.c_int
     L.fl_observe_plan.argtypes = [C.POINTER(FlBatch), P, C.c_int]
     L.fl_observe_plan.restype = C.c_int
     L.fl_batch_slice.argtypes = [C.POINTER(FlBatch), C.c_int64, C.c_int64, C.POINTER(FlBatch)]

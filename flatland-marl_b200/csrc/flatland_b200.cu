@@ -31,6 +31,11 @@
 #include "step.cuh"
 #include "observe.cuh"
 #include "bfs.cuh"
+#include "wire.cuh"
+
+#include <condition_variable>
+#include <functional>
+#include <thread>
 
 namespace {
 
@@ -38,8 +43,8 @@ std::atomic<uint64_t> g_launches{0};
 
 // Optional per-kernel timing (fl_profile_*): every launch is bracketed by CUDA events recorded on the
 // launching stream; fl_profile_collect turns them into per-kernel totals.  Off by default.
-enum KernelId : int { K_BFS = 0, K_RESET, K_STEP, K_OBSERVE, K_WALKS, K_OBSERVE_INDEX, K_OBSERVE_TREES, K_COUNT };
-const char *const kKernelNames[K_COUNT] = {"k_bfs", "k_reset", "k_step", "k_observe", "k_walks", "k_observe_index", "k_observe_trees"};
+enum KernelId : int { K_BFS = 0, K_RESET, K_STEP, K_OBSERVE, K_WALKS, K_OBSERVE_INDEX, K_OBSERVE_TREES, K_PACK, K_COUNT };
+const char *const kKernelNames[K_COUNT] = {"k_bfs", "k_reset", "k_step", "k_observe", "k_walks", "k_observe_index", "k_observe_trees", "k_pack"};
 struct ProfRec { int id; cudaEvent_t a, b; };
 std::mutex g_prof_mu;
 bool g_prof_on = false;
@@ -115,13 +120,14 @@ ObsLayout make_obs_layout(const FlBatch *b, int nt, int mode, int parts, int *ct
     const int N = (int)b->N, Rmax = (int)(b->state_stride / 4), Np = (N + 3) & ~3;
     ObsLayout L;
     int off = 0;
-    auto take = [&](long long bytes) { const int o = off; off = align_up(off + (int)bytes, 128); return o; };
+    // regions are 16-byte aligned (what the bulk copies need); every byte counts towards one more resident CTA per SM
+    auto take = [&](long long bytes) { const int o = off; off = align_up(off + (int)bytes, 16); return o; };
     L.parts = mode == OBS_FUSED ? 0 : parts;
     // FlBatch.obs_ws of the split launch: [header 16 B | six agent arrays] [occupancy words | bucket offsets | filter]
     L.ws_ag = 0; L.ws_ag_bytes = (4 + 6 * Np) * 4;
     L.ws_idx = L.ws_ag_bytes; L.ws_idx_bytes = Rmax * 4 + (Rmax + 4) * 4 + Rmax * 32;
     L.bar = take(32);
-    L.part = take(128);
+    L.part = take(128);                                         // one scan partial per warp
     L.ag = take(mode == OBS_TREES ? (long long)L.ws_ag_bytes : (long long)(4 + 6 * Np + 5 * N) * 4);
     L.dl = mode == OBS_TREES ? 0 : take(26 * N + 8);
     L.ci = take((long long)Rmax * 4);
@@ -138,7 +144,7 @@ ObsLayout make_obs_layout(const FlBatch *b, int nt, int mode, int parts, int *ct
     const long long grid_b = b->grid_stride * 2, ridx_b = b->ridx_stride * 2;
     const long long st_b = b->state_stride * 4, wl_b = b->wlist_stride * 4, wh_b = b->whits_stride * 4;
     const long long sd_b = b->n_slots * b->state_stride * 2;
-    const long long core = off + ridx_b + ent_typ + 3 * 128;
+    const long long core = off + ridx_b + ent_typ + 3 * 16;
     int want_tables = 0x77;                                     // bit k: wlist, wrec, sdist, (srec: unused by k_observe), whoff, whits
     if (knob(KNOB_TABLES) >= 0) want_tables = knob(KNOB_TABLES);
     if (mode == OBS_TREES) want_tables &= ~0x40;                // the tree kernel never reads the grid
@@ -150,11 +156,11 @@ ObsLayout make_obs_layout(const FlBatch *b, int nt, int mode, int parts, int *ct
             if (core <= SMEM_MAX / c - 1024 || c == 1) { ctas = c; break; }
     if (ctas_out) *ctas_out = ctas;
     const int budget = SMEM_MAX / ctas - 1024;
-    auto opt = [&](long long bytes) { if ((long long)off + bytes + 128 > budget) return -1; return take(bytes); };
+    auto opt = [&](long long bytes) { if ((long long)off + bytes + 16 > budget) return -1; return take(bytes); };
     L.ridx = opt(ridx_b);
-    long long reserve = ent_typ + 128;                           // keep room for the entries while placing the tables
+    long long reserve = ent_typ + 16;                            // keep room for the entries while placing the tables
     auto table = [&](int bit, long long bytes) {
-        if (!((want_tables >> bit) & 1) || (long long)off + bytes + 128 + reserve > budget) return -1;
+        if (!((want_tables >> bit) & 1) || (long long)off + bytes + 16 + reserve > budget) return -1;
         return take(bytes);
     };
     L.wlist = table(0, wl_b);
@@ -165,7 +171,7 @@ ObsLayout make_obs_layout(const FlBatch *b, int nt, int mode, int parts, int *ct
     L.whits = table(5, wh_b);
     L.grid = table(6, grid_b);                                  // only phase 1 reads the grid
     // entries: at least the typical size, at most twice that (more is never needed; larger counts spill to global memory)
-    long long ent_b = (long long)budget - off - 128;
+    long long ent_b = ((long long)budget - off - 16) & ~15ll;
     if (ent_b > 2 * ent_typ) ent_b = 2 * ent_typ;
     if (ent_b > (long long)N * NPRED * 4) ent_b = (long long)N * NPRED * 4;
     if (ent_b < 0) ent_b = 0;
@@ -420,6 +426,159 @@ cudaEvent_t chunk_event(int k) {
     return pool[dev][k];
 }
 }  // namespace
+
+namespace {
+// Host threads that expand the compact wire format (wire.cuh) into the caller's tensors: persistent, woken per job, the
+// calling thread works along.  One pool per process; fl_host_threads sets its size before first use.
+class ExpandPool {
+  public:
+    void set_threads(int n) {
+        std::lock_guard<std::mutex> lk(mu_);
+        if (th_.empty()) want_ = n < 1 ? 1 : (n > 64 ? 64 : n);
+    }
+    int threads() {
+        std::lock_guard<std::mutex> lk(mu_);
+        return want_ ? want_ : default_threads();
+    }
+    void parallel_for(int n, const std::function<void(int)> &fn) {
+        if (n <= 0) return;
+        {
+            std::unique_lock<std::mutex> lk(mu_);
+            if (th_.empty()) start_locked();
+            fn_ = &fn; n_ = n; next_.store(0); left_.store(n); gen_++;
+        }
+        cv_.notify_all();
+        work();
+        std::unique_lock<std::mutex> lk(mu_);
+        done_cv_.wait(lk, [&] { return left_.load() == 0 && busy_ == 0; });
+        fn_ = nullptr;
+    }
+    ~ExpandPool() {
+        { std::lock_guard<std::mutex> lk(mu_); stop_ = true; }
+        cv_.notify_all();
+        for (auto &t : th_) t.join();
+    }
+
+  private:
+    static int default_threads() {
+        unsigned hc = std::thread::hardware_concurrency();
+        int n = hc ? (int)hc : 4;
+        if (const char *s = getenv("LOCAL_WORLD_SIZE")) { const int w = atoi(s); if (w > 1) n = n / w > 2 ? n / w : 2; }
+        return n > 32 ? 32 : n;
+    }
+    void start_locked() {
+        if (!want_) want_ = default_threads();
+        for (int k = 1; k < want_; k++) th_.emplace_back([this] { loop(); });
+    }
+    void work() {
+        const std::function<void(int)> *fn = fn_;
+        for (;;) {
+            const int k = next_.fetch_add(1);
+            if (k >= n_) break;
+            (*fn)(k);
+            left_.fetch_sub(1);
+        }
+    }
+    void loop() {
+        uint64_t seen = 0;
+        std::unique_lock<std::mutex> lk(mu_);
+        for (;;) {
+            cv_.wait(lk, [&] { return stop_ || gen_ != seen; });
+            if (stop_) return;
+            seen = gen_;
+            busy_++;
+            lk.unlock();
+            work();
+            lk.lock();
+            busy_--;
+            if (left_.load() == 0 && busy_ == 0) done_cv_.notify_all();
+        }
+    }
+    std::mutex mu_;
+    std::condition_variable cv_, done_cv_;
+    std::vector<std::thread> th_;
+    const std::function<void(int)> *fn_ = nullptr;
+    std::atomic<int> next_{0}, left_{0};
+    int n_ = 0, want_ = 0, busy_ = 0;
+    uint64_t gen_ = 0;
+    bool stop_ = false;
+};
+ExpandPool g_pool;
+}  // namespace
+
+int fl_host_threads(int n) {
+    if (n > 0) g_pool.set_threads(n);
+    return g_pool.threads();
+}
+
+size_t fl_wire_bytes(const FlBatch *b, int n_chunks) {
+    if (!b || b->E <= 0 || b->N <= 0) return 0;
+    (void)n_chunks;
+    return ((size_t)b->E * (size_t)b->N * WIRE_MAX_WORDS + (size_t)b->E + 64) * 4;   // worst case: every node of every tree is real
+}
+
+int fl_step_observe_host_compact(const FlBatch *b, const uint8_t *h_actions, uint8_t *d_actions, const FlObsBuffers *d_out,
+                                 const FlObsBuffers *h_out, void *h_wire, uint32_t *d_cursor, uint64_t *wire_bytes_out,
+                                 uint32_t flags, int n_chunks, void *stream, void *copy_stream) {
+    if (int rc = check_batch(b)) return rc;
+    if (!h_actions || !d_actions || !d_out || !h_out || !h_wire || !d_cursor) return FL_ERR_BAD_ARG;
+    cudaStream_t st = (cudaStream_t)stream, cs = copy_stream ? (cudaStream_t)copy_stream : st;
+    if (n_chunks < 1) n_chunks = 1;
+    if (n_chunks > 64) n_chunks = 64;
+    if (n_chunks > b->E) n_chunks = (int)b->E;
+    uint32_t *wire_dev = nullptr;
+    cudaError_t err = cudaHostGetDevicePointer((void **)&wire_dev, h_wire, 0);      // pinned + mapped host memory (UVA)
+    if (err != cudaSuccess) return (int)err;
+    const size_t N = (size_t)b->N;
+    const int smem = (int)((2 * ((N + 3) & ~(size_t)3) + 4 + (PACK_THREADS / 32) * (WIRE_MAX_WORDS + 2)) * 4);
+    if ((err = cudaMemcpyAsync(d_actions, h_actions, (size_t)b->E * N, cudaMemcpyHostToDevice, st)) != cudaSuccess) return (int)err;
+    if ((err = cudaMemsetAsync(d_cursor, 0, sizeof(uint32_t) * (size_t)n_chunks, st)) != cudaSuccess) return (int)err;
+    std::vector<size_t> chunk_word0((size_t)n_chunks);
+    for (int c = 0; c < n_chunks; c++) {
+        const int64_t e0 = b->E * c / n_chunks, e1 = b->E * (c + 1) / n_chunks, n = e1 - e0;
+        const size_t a0 = (size_t)e0 * N;
+        chunk_word0[c] = a0 * WIRE_MAX_WORDS + (size_t)e0;                          // worst-case prefix: regions never overlap
+        FlBatch sub;
+        if (int rc = fl_batch_slice(b, e0, n, &sub)) return rc;
+        if (int rc = fl_step(&sub, d_actions + a0, d_out->rewards + a0, d_out->dones + (size_t)e0 * (N + 1), flags, stream)) return rc;
+        if (int rc = fl_observe(&sub, d_out->agent_attr + a0 * FL_ATTR_F, d_out->forest + a0 * FL_MAX_NODES * FL_NODE_F,
+                                d_out->adjacency + a0 * (FL_MAX_NODES - 1) * 3, d_out->node_order + a0 * FL_MAX_NODES,
+                                d_out->edge_order + a0 * (FL_MAX_NODES - 1), d_out->valid_actions + a0 * 5,
+                                d_out->dist_target + a0, stream))
+            return rc;
+        if (cs != st) {
+            cudaEvent_t ev = chunk_event(c);
+            if ((err = cudaEventRecord(ev, st)) != cudaSuccess) return (int)err;
+            if ((err = cudaStreamWaitEvent(cs, ev, 0)) != cudaSuccess) return (int)err;
+        }
+        WireSrc src{d_out->agent_attr + a0 * FL_ATTR_F, d_out->forest + a0 * FL_MAX_NODES * FL_NODE_F, d_out->dist_target + a0,
+                    d_out->adjacency + a0 * (FL_MAX_NODES - 1) * 3, d_out->node_order + a0 * FL_MAX_NODES,
+                    d_out->edge_order + a0 * (FL_MAX_NODES - 1), d_out->rewards + a0, d_out->dones + (size_t)e0 * (N + 1)};
+        {
+            LaunchScope ls(K_PACK, cs);
+            k_pack<<<(unsigned)n, PACK_THREADS, smem, cs>>>(src, (int)N, (int)n, wire_dev + chunk_word0[c], d_cursor + c);
+        }
+        if ((err = cudaGetLastError()) != cudaSuccess) return (int)err;
+        if ((err = cudaEventRecord(chunk_event(64 + c), cs)) != cudaSuccess) return (int)err;
+    }
+    // expansion on the host while the device works on the later chunks
+    const WireDst dst{h_out->agent_attr, h_out->forest, h_out->dist_target, h_out->adjacency, h_out->node_order, h_out->edge_order,
+                      h_out->rewards, h_out->valid_actions, h_out->dones};
+    std::atomic<uint64_t> words{0};
+    for (int c = 0; c < n_chunks; c++) {
+        if ((err = cudaEventSynchronize(chunk_event(64 + c))) != cudaSuccess) return (int)err;
+        const int64_t e0 = b->E * c / n_chunks, e1 = b->E * (c + 1) / n_chunks;
+        const uint32_t *wire = reinterpret_cast<const uint32_t *>(h_wire) + chunk_word0[c];
+        const int Ni = (int)N;
+        const std::function<void(int)> job = [&](int el) { words.fetch_add(expand_env(wire, el, e0 + el, Ni, dst) + 1); };
+        g_pool.parallel_for((int)(e1 - e0), job);
+    }
+    if (wire_bytes_out) *wire_bytes_out = words.load() * 4;
+    if (cs != st) {
+        if ((err = cudaStreamWaitEvent(st, chunk_event(64 + n_chunks - 1), 0)) != cudaSuccess) return (int)err;
+    }
+    return FL_OK;
+}
 
 int fl_observe_plan(const FlBatch *b, int32_t *out, int n_out) {
     if (int rc = check_batch(b)) return rc;

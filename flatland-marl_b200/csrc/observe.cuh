@@ -399,7 +399,7 @@ k_observe(FlBatch b, ObsLayout lay, float *__restrict__ out_attr, float *__restr
         D.dep = p; p += 4 * N; D.stk_h = p; p += N; D.stk_opp = p; p += N;
         uint8_t *q = reinterpret_cast<uint8_t *>(p);
         D.checked = q; q += N; D.ndep = q; q += N; D.dl = q; q += N; D.ct = q; q += N; D.stk_d = q; q += N; D.stk_phase = q; q += N;
-        D.opp = reinterpret_cast<int16_t *>(q + (N & 1));
+        D.opp = reinterpret_cast<int16_t *>(q);      // byte offset 18 N from a 128-byte aligned base: even
     }
 
     // optional phase timestamps (tuning only): FlBatch.debug_clocks [E][16] int64, NULL = off

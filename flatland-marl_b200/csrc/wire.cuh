@@ -1,0 +1,153 @@
+// wire.cuh — compact device-to-host format of one observation step, and its expansion on the host.
+//
+// fl_step_observe_host ships 2,438 bytes per agent over PCIe (every observation tensor as f32 / i32, the layout the policy
+// reads).  Most of those bytes carry no information: about 40 % of the 31 tree nodes are the constant "no branch here"
+// vector (twelve times -1), adjacency / evaluation orders are small integers stored as i32, 70 of the 83 attribute entries
+// are 0/1 flags.  k_pack rewrites one environment range into a byte stream of ~1.1 KB per agent — bit-exact, every float
+// that is not a flag or a -1 travels as its own 32 bits — straight into pinned host memory (the kernel's stores go over
+// PCIe; nothing is staged in device memory, no size has to be known to the host beforehand), and expand_env() rebuilds
+// the f32 / i32 tensors in the caller's host buffers, one environment per task of a small thread pool.
+//
+// Stream layout of a chunk (uint32 words): table[n_env] (word offset of the environment's block inside the chunk | dones
+// ["__all__"] << 31), then the blocks in the order the CTAs finished.  A block is N agent records back to back:
+//   w[0]      node mask, bit n = tree node n differs from the all -1 vector
+//   w[1..3]   attribute entries 0..69 as bits (feature_parser.cpp:19-77: one-hot codes and flags, exactly 0.0 or 1.0)
+//   w[4..16]  attribute entries 70..82 (floats)
+//   w[17]     dist_target (float)      w[18] reward (int32)      w[19] dones[i]
+//   w[20..57] 151 bytes: adjacency[30][3], node_order[31], edge_order[30] as int8 (values -2..30)
+//   then 12 floats per set bit of the node mask, in node order.
+#pragma once
+#include "common.cuh"
+
+#include <cstring>
+
+namespace {
+
+constexpr int WIRE_FIXED_WORDS = 58;
+constexpr int WIRE_MAX_WORDS = WIRE_FIXED_WORDS + FL_MAX_NODES * FL_NODE_F;   // 430
+
+struct WireSrc {   // device pointers of the environment range being packed (already advanced to its first environment)
+    const float *attr, *forest, *dist_target;
+    const int32_t *adjacency, *node_order, *edge_order, *rewards;
+    const uint8_t *dones;
+};
+
+constexpr int PACK_THREADS = 128;
+
+__global__ void __launch_bounds__(PACK_THREADS)
+k_pack(WireSrc src, int N, int n_env, uint32_t *__restrict__ wire, uint32_t *__restrict__ cursor) {
+    const int el = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    extern __shared__ uint32_t pk_smem[];
+    const int Np = (N + 3) & ~3;                       // keeps the staging areas 16-byte aligned
+    uint32_t *s_mask = pk_smem, *s_off = pk_smem + Np, *stage = pk_smem + 2 * Np + 4 + warp * (WIRE_MAX_WORDS + 2);
+    uint32_t *s_base = pk_smem + 2 * Np;
+    const size_t a0 = (size_t)el * N;
+    // pass 1: which nodes are not the all -1 vector
+    for (int i = warp; i < N; i += PACK_THREADS / 32) {
+        bool real = false;
+        if (lane < FL_MAX_NODES) {
+            const float4 *p = reinterpret_cast<const float4 *>(src.forest + (a0 + i) * (FL_MAX_NODES * FL_NODE_F) + lane * FL_NODE_F);
+            const float4 x = p[0], y = p[1], z = p[2];
+            real = x.x != -1.f || x.y != -1.f || x.z != -1.f || x.w != -1.f || y.x != -1.f || y.y != -1.f || y.z != -1.f ||
+                   y.w != -1.f || z.x != -1.f || z.y != -1.f || z.z != -1.f || z.w != -1.f;
+        }
+        const unsigned m = __ballot_sync(0xFFFFFFFFu, real);
+        if (lane == 0) s_mask[i] = m;
+    }
+    __syncthreads();
+    if (warp == 0) {                                   // offsets of the agent records inside the block
+        unsigned run = 0;
+        for (int i0 = 0; i0 < N; i0 += 32) {
+            const int i = i0 + lane;
+            const unsigned len = i < N ? WIRE_FIXED_WORDS + FL_NODE_F * __popc(s_mask[i]) : 0u;
+            unsigned x = len;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const unsigned y = __shfl_up_sync(0xFFFFFFFFu, x, o); if (lane >= o) x += y; }
+            if (i < N) s_off[i] = run + x - len;
+            run += __shfl_sync(0xFFFFFFFFu, x, 31);
+        }
+        if (lane == 0) {
+            const unsigned base = (unsigned)n_env + atomicAdd(cursor, run);
+            s_base[0] = base;
+            wire[el] = base | ((uint32_t)(src.dones[(size_t)el * (N + 1) + N] != 0) << 31);
+        }
+    }
+    __syncthreads();
+    const unsigned base = s_base[0];
+    // pass 2: one warp per agent stages the record in shared memory and streams it out with coalesced stores
+    for (int i = warp; i < N; i += PACK_THREADS / 32) {
+        const size_t ea = a0 + i;
+        const unsigned mask = s_mask[i];
+        const float *at = src.attr + ea * FL_ATTR_F;
+        const unsigned b0 = __ballot_sync(0xFFFFFFFFu, at[lane] != 0.0f), b1 = __ballot_sync(0xFFFFFFFFu, at[32 + lane] != 0.0f);
+        const unsigned b2 = __ballot_sync(0xFFFFFFFFu, lane < 6 && at[64 + lane] != 0.0f);
+        if (lane == 0) { stage[0] = mask; stage[1] = b0; stage[2] = b1; stage[3] = b2; }
+        if (lane < 13) stage[4 + lane] = __float_as_uint(at[70 + lane]);
+        if (lane == 13) stage[17] = __float_as_uint(src.dist_target[ea]);
+        if (lane == 14) stage[18] = (uint32_t)src.rewards[ea];
+        if (lane == 15) stage[19] = src.dones[(size_t)el * (N + 1) + i];
+        uint8_t *sb = reinterpret_cast<uint8_t *>(stage + 20);
+        const int32_t *adj = src.adjacency + ea * ((FL_MAX_NODES - 1) * 3);
+        for (int k = lane; k < 90; k += 32) sb[k] = (uint8_t)(int8_t)adj[k];
+        if (lane < FL_MAX_NODES) sb[90 + lane] = (uint8_t)(int8_t)src.node_order[ea * FL_MAX_NODES + lane];
+        if (lane < FL_MAX_NODES - 1) sb[121 + lane] = (uint8_t)(int8_t)src.edge_order[ea * (FL_MAX_NODES - 1) + lane];
+        if (lane == 31) sb[151] = 0;
+        if (lane < FL_MAX_NODES && ((mask >> lane) & 1u)) {
+            const float4 *p = reinterpret_cast<const float4 *>(src.forest + ea * (FL_MAX_NODES * FL_NODE_F) + lane * FL_NODE_F);
+            float4 *q = reinterpret_cast<float4 *>(stage + WIRE_FIXED_WORDS + 2 + FL_NODE_F * __popc(mask & ((1u << lane) - 1u)));
+            q[0] = p[0]; q[1] = p[1]; q[2] = p[2];
+        }
+        __syncwarp();
+        const int nodes_w = FL_NODE_F * __popc(mask);
+        uint32_t *out = wire + base + s_off[i];
+        for (int k = lane; k < WIRE_FIXED_WORDS; k += 32) out[k] = stage[k];
+        for (int k = lane; k < nodes_w; k += 32) out[WIRE_FIXED_WORDS + k] = stage[WIRE_FIXED_WORDS + 2 + k];   // (+2: the node part is 16-byte aligned in the stage)
+        __syncwarp();
+    }
+}
+
+// ---- host side ---------------------------------------------------------------------------------------------------
+struct WireDst {   // host pointers of the WHOLE batch (the reference-facing layout of FlObsBuffers)
+    float *attr, *forest, *dist_target;
+    int32_t *adjacency, *node_order, *edge_order, *rewards;
+    uint8_t *valid_actions, *dones;
+};
+
+// Rebuilds environment `e_global` (local index el of the chunk whose stream starts at `wire`) in the host tensors.
+inline uint64_t expand_env(const uint32_t *wire, int el, long long e_global, int N, const WireDst &d) {
+    const uint32_t tw = wire[el];
+    const uint32_t *p = wire + (tw & 0x7FFFFFFFu);
+    const uint32_t *const p0 = p;
+    if (d.dones) d.dones[(size_t)e_global * (N + 1) + N] = (uint8_t)(tw >> 31);
+    for (int i = 0; i < N; i++) {
+        const size_t ea = (size_t)e_global * N + i;
+        const uint32_t mask = p[0];
+        if (d.attr) {
+            float *a = d.attr + ea * FL_ATTR_F;
+            for (int k = 0; k < 32; k++) a[k] = (float)((p[1] >> k) & 1u);
+            for (int k = 0; k < 32; k++) a[32 + k] = (float)((p[2] >> k) & 1u);
+            for (int k = 0; k < 6; k++) a[64 + k] = (float)((p[3] >> k) & 1u);
+            std::memcpy(a + 70, p + 4, 13 * sizeof(float));
+        }
+        if (d.valid_actions) for (int k = 0; k < 5; k++) d.valid_actions[ea * 5 + k] = (uint8_t)((p[3] >> (1 + k)) & 1u);
+        if (d.dist_target) std::memcpy(d.dist_target + ea, p + 17, 4);
+        if (d.rewards) d.rewards[ea] = (int32_t)p[18];
+        if (d.dones) d.dones[(size_t)e_global * (N + 1) + i] = (uint8_t)p[19];
+        const int8_t *sb = reinterpret_cast<const int8_t *>(p + 20);
+        if (d.adjacency) { int32_t *q = d.adjacency + ea * ((FL_MAX_NODES - 1) * 3); for (int k = 0; k < 90; k++) q[k] = sb[k]; }
+        if (d.node_order) { int32_t *q = d.node_order + ea * FL_MAX_NODES; for (int k = 0; k < FL_MAX_NODES; k++) q[k] = sb[90 + k]; }
+        if (d.edge_order) { int32_t *q = d.edge_order + ea * (FL_MAX_NODES - 1); for (int k = 0; k < FL_MAX_NODES - 1; k++) q[k] = sb[121 + k]; }
+        const uint32_t *nodes = p + WIRE_FIXED_WORDS;
+        if (d.forest) {
+            float *f = d.forest + ea * (FL_MAX_NODES * FL_NODE_F);
+            for (int n = 0; n < FL_MAX_NODES; n++) {
+                if ((mask >> n) & 1u) { std::memcpy(f + n * FL_NODE_F, nodes, FL_NODE_F * sizeof(float)); nodes += FL_NODE_F; }
+                else for (int k = 0; k < FL_NODE_F; k++) f[n * FL_NODE_F + k] = -1.0f;
+            }
+        }
+        p += WIRE_FIXED_WORDS + FL_NODE_F * __builtin_popcount(mask);
+    }
+    return (uint64_t)(p - p0);
+}
+
+}  // namespace

@@ -236,6 +236,21 @@ int fl_step_observe_host(const FlBatch *b, const uint8_t *h_actions, uint8_t *d_
                          const FlObsBuffers *d_out, const FlObsBuffers *h_out, uint32_t flags,
                          int n_chunks, void *stream, void *copy_stream);
 
+/* The same step with a compact device-to-host format (csrc/wire.cuh): instead of copying 2,438 bytes per agent, a pack
+ * kernel rewrites each environment range into ~1.1 KB per agent — tree nodes that are the all -1 "no branch" vector as one
+ * bit, adjacency / orders as int8, the 70 flag entries of the attribute vector as bits, every other float as its own 32
+ * bits — straight into `h_wire` (pinned, device-mapped host memory of at least fl_wire_bytes(b) bytes, e.g. cudaHostAlloc /
+ * torch pin_memory), and host threads of this library (fl_host_threads) expand it into the same h_out tensors, bit for bit
+ * what fl_step_observe_host delivers, while the device works on the next range.  d_cursor: device uint32[64] scratch.
+ * SYNCHRONOUS: every h_out tensor is complete when the call returns.  wire_bytes_out (may be NULL): bytes that crossed PCIe. */
+int fl_step_observe_host_compact(const FlBatch *b, const uint8_t *h_actions, uint8_t *d_actions,
+                                 const FlObsBuffers *d_out, const FlObsBuffers *h_out, void *h_wire, uint32_t *d_cursor,
+                                 uint64_t *wire_bytes_out, uint32_t flags, int n_chunks, void *stream, void *copy_stream);
+size_t fl_wire_bytes(const FlBatch *b, int n_chunks);
+/* Host threads of the expansion: n > 0 sets the count (before the first compact step; default: hardware threads divided by
+ * LOCAL_WORLD_SIZE, at most 32); returns the count in use. */
+int fl_host_threads(int n);
+
 /* Number of kernel launches issued by this library since load (bench.py reports it as gpu_launches). */
 uint64_t fl_launch_count(void);
 

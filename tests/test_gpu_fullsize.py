@@ -68,14 +68,15 @@ def test_full_batch_matches_oracle_on_sampled_envs(config, n_envs, n_steps, samp
 
 
 def test_chunked_host_step_equals_device_step():
-    """fl_step_observe_host with 1, 3 and 8 chunks (copies overlapped on a second stream) returns the same
-    bytes as the device-resident path on the full Test_03 batch."""
+    """fl_step_observe_host with 1, 3 and 8 chunks (copies overlapped on a second stream) and fl_step_observe_host_compact
+    (compact wire format, expanded by the library's host threads) return the same bytes as the device-resident path."""
     import torch
     import flatland_marl_b200 as fb
     worlds = _load("Test_03", 256)
     N = int(worlds[0]["N"])
     ref = fb.BatchedRailEnv(worlds)
-    others = {c: fb.BatchedRailEnv(worlds) for c in (1, 3, 8)}
+    # (chunks, wire): the full copies, and the compact wire format packed on the device and expanded by host threads
+    others = {c: fb.BatchedRailEnv(worlds) for c in ((1, "full"), (3, "full"), (8, "full"), (1, "compact"), (4, "compact"), (7, "compact"))}
     ref.reset()
     for b in others.values():
         b.reset()
@@ -84,8 +85,10 @@ def test_chunked_host_step_equals_device_step():
         act = np.where(rng.rand(256, N) < 0.7, 2, rng.randint(0, 5, (256, N))).astype(np.uint8)
         ref.step(torch.from_numpy(act).to(ref.device))
         for c, b in others.items():
-            h = b.step_host(act, n_chunks=c)
+            h = b.step_host(act, n_chunks=c[0], wire=c[1])
+            if c[1] == "compact":
+                assert 0 < b.last_wire_bytes < 0.6 * b.d2h_bytes_per_step
             for k in ref.obs:
-                np.testing.assert_array_equal(h[k].numpy(), ref.obs[k].cpu().numpy(), err_msg="%s chunks=%d step %d" % (k, c, t))
+                np.testing.assert_array_equal(h[k].numpy(), ref.obs[k].cpu().numpy(), err_msg="%s chunks=%s step %d" % (k, c, t))
             np.testing.assert_array_equal(h["rewards"].numpy(), ref.rewards.cpu().numpy())
             np.testing.assert_array_equal(h["dones"].numpy(), ref.dones.cpu().numpy())

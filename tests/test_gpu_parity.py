@@ -220,7 +220,7 @@ def test_host_buffer_step_matches_device_step(golden):
     for t in range(40):
         act = np.repeat(g["actions"][t][None], 3, 0)
         a.step(torch.from_numpy(act).to(a.device))
-        h = b.step_host(act)
+        h = b.step_host(act, wire="compact" if t % 2 else "full", n_chunks=1 + t % 3)
         for k in a.obs:
             np.testing.assert_array_equal(h[k].numpy(), a.obs[k].cpu().numpy(), err_msg="%s step %d" % (k, t))
         np.testing.assert_array_equal(h["rewards"].numpy(), a.rewards.cpu().numpy())
