@@ -95,9 +95,10 @@ int align_up(int v, int a) { return (v + a - 1) / a * a; }
 
 // Plan overrides (fl_observe_override; tuning and tests only).  -1 = default.  Seeded once from FL_OBS_<KEY> environment
 // variables when the library is loaded; the launch path reads these atomics, never the environment.
-enum ObsKnob : int { KNOB_NT = 0, KNOB_CTAS, KNOB_TABLES, KNOB_SEGCAP, KNOB_ENTCAP, KNOB_SORTSMALL, KNOB_PARTS, KNOB_COUNT };
-const char *const kKnobNames[KNOB_COUNT] = {"nt", "ctas", "tables", "segcap", "entcap", "sortsmall", "parts"};
-const char *const kKnobEnv[KNOB_COUNT] = {"FL_OBS_NT", "FL_OBS_CTAS", "FL_OBS_TABLES", "FL_OBS_SEGCAP", "FL_OBS_ENTCAP", "FL_OBS_SORTSMALL", "FL_OBS_PARTS"};
+enum ObsKnob : int { KNOB_NT = 0, KNOB_CTAS, KNOB_TABLES, KNOB_SEGCAP, KNOB_ENTCAP, KNOB_SORTSMALL, KNOB_PARTS, KNOB_BMGLOBAL, KNOB_TREENT, KNOB_COUNT };
+const char *const kKnobNames[KNOB_COUNT] = {"nt", "ctas", "tables", "segcap", "entcap", "sortsmall", "parts", "bmglobal", "treent"};
+const char *const kKnobEnv[KNOB_COUNT] = {"FL_OBS_NT", "FL_OBS_CTAS", "FL_OBS_TABLES", "FL_OBS_SEGCAP", "FL_OBS_ENTCAP", "FL_OBS_SORTSMALL", "FL_OBS_PARTS",
+                                          "FL_OBS_BMGLOBAL", "FL_OBS_TREENT"};
 std::atomic<int> g_knob[KNOB_COUNT];
 struct KnobInit {
     KnobInit() {
@@ -132,7 +133,10 @@ ObsLayout make_obs_layout(const FlBatch *b, int nt, int mode, int parts, int *ct
     L.dl = mode == OBS_TREES ? 0 : take(26 * N + 8);
     L.ci = take((long long)Rmax * 4);
     L.ks = take((long long)(Rmax + 4) * 4);
-    L.bm = take((long long)Rmax * 32);                          // time-slot filter of the prediction index: one / two entries per slot
+    // time-slot filter of the prediction index: one / two entries per slot.  The tree kernel may read it from the workspace
+    // instead ("bmglobal" knob; default: when it is larger than 48 KB, i.e. would cost the tree kernel a resident CTA)
+    const bool bm_global = mode == OBS_TREES && (knob(KNOB_BMGLOBAL) >= 0 ? knob(KNOB_BMGLOBAL) != 0 : (long long)Rmax * 32 > 48 * 1024);
+    L.bm = bm_global ? -1 : take((long long)Rmax * 32);
     L.seg_cap = mode == OBS_TREES ? 0 : 10 * N;                 // path segments of phase 3 share the room of the phase-4 queues
     if (L.seg_cap < (nt / 32) * 64) L.seg_cap = (nt / 32) * 64;
     L.sq_words = L.seg_cap * 2;
@@ -217,8 +221,8 @@ int obs_parts(const FlBatch *b) {
 
 // threads per CTA of the tree kernel: one warp per agent at a time; enough warps to cover its share of the agents
 int tree_threads(const FlBatch *b, int parts) {
-    const int v = knob(KNOB_NT);
-    if (v == 64 || v == 128 || v == 256 || v == 512 || v == 1024) return v;
+    for (int v : {knob(KNOB_TREENT), knob(KNOB_NT)})
+        if (v == 64 || v == 128 || v == 256 || v == 512 || v == 1024) return v;
     const long long per = (b->N + parts - 1) / parts;           // agents per CTA
     if (per >= 192) return 1024;
     if (per >= 96) return 512;

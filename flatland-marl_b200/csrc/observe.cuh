@@ -374,6 +374,11 @@ k_observe(FlBatch b, ObsLayout lay, float *__restrict__ out_attr, float *__restr
     uint32_t *ci = reinterpret_cast<uint32_t *>(smraw + lay.ci);             // [R] occupancy word per rail cell
     uint32_t *ks = reinterpret_cast<uint32_t *>(smraw + lay.ks) + 1;         // ks[-1..R]: bucket r = [ks[r-1], ks[r])
     uint2 *bm = reinterpret_cast<uint2 *>(smraw + lay.bm);                   // [R][4] bit s of .x / .y: at least one / two prediction entries of the key overlap rows 4s..4s+3
+    // the tree kernel of a split launch can leave the filter in the workspace (L2) when its 32 bytes per rail cell would cost
+    // a resident CTA (lay.bm < 0): it is read twice per visited cell, with independent loads
+    const uint2 *bm_r = (MODE == OBS_TREES && lay.bm < 0)
+                            ? reinterpret_cast<const uint2 *>(b.obs_ws + (size_t)e * b.ws_stride + lay.ws_idx / 4 + 2 * (SS / 4) + 4)
+                            : bm;
     uint2 *sq = reinterpret_cast<uint2 *>(smraw + lay.sq) + warp * 64;       // this warp's queue of cells that need the full conflict check
     uint32_t *s_part = reinterpret_cast<uint32_t *>(smraw + lay.part);
     uint64_t *bar = reinterpret_cast<uint64_t *>(smraw + lay.bar);
@@ -430,7 +435,7 @@ k_observe(FlBatch b, ObsLayout lay, float *__restrict__ out_attr, float *__restr
         uint32_t wsb = 0, eb = 0;
         if (MODE == OBS_TREES) {
             const int n_ent_g = (int)g_ws[0];
-            wsb = (uint32_t)(lay.ws_ag_bytes + lay.ws_idx_bytes);
+            wsb = (uint32_t)(lay.ws_ag_bytes + lay.ws_idx_bytes) - (lay.bm >= 0 ? 0u : 8u * (uint32_t)(SS / 4) * 4u);
             eb = (n_ent_g <= lay.ent_cap && !(b.ent_cap & 3)) ? (uint32_t)((n_ent_g * 4 + 15) & ~15) : 0u;   // 16-byte aligned blocks only
         }
         mbar_expect_tx(bar, wsb + eb + gb + rb + lb + hb + kb + db + (lay.srec >= 0 ? sb : 0u) + (lay.wrec >= 0 ? 4 * sb : 0u) + (lay.whoff >= 0 ? sb : 0u));
@@ -440,7 +445,7 @@ k_observe(FlBatch b, ObsLayout lay, float *__restrict__ out_attr, float *__restr
             tma_load_1d(smraw + lay.ag, gw, (uint32_t)lay.ws_ag_bytes, bar);
             tma_load_1d(smraw + lay.ci, gw + lay.ws_idx, Rb, bar);
             tma_load_1d(smraw + lay.ks, gw + lay.ws_idx + Rb, Rb + 16u, bar);
-            tma_load_1d(smraw + lay.bm, gw + lay.ws_idx + 2u * Rb + 16u, 8u * Rb, bar);
+            if (lay.bm >= 0) tma_load_1d(smraw + lay.bm, gw + lay.ws_idx + 2u * Rb + 16u, 8u * Rb, bar);
             if (eb) tma_load_1d(smraw + lay.ent, b.entries + (size_t)e * b.ent_cap, eb, bar);
         }
         if (gb) tma_load_1d(smraw + lay.grid, g_grid, gb, bar);
@@ -987,7 +992,7 @@ k_observe(FlBatch b, ObsLayout lay, float *__restrict__ out_attr, float *__restr
                     if (pt < NPRED && tot < NPRED) {                                 // treeobs.cpp:379-465
                         const unsigned bk = kcls ? (unsigned)kcls[rail] : rail;    // the reference's position key c*W + r
                         const int sa = max(0, pt - 1) >> 2, sb = min(NPRED - 1, pt + 1) >> 2;
-                        const uint2 wa = bm[bk * 4 + (sa >> 5)], wb = bm[bk * 4 + (sb >> 5)];
+                        const uint2 wa = bm_r[bk * 4 + (sa >> 5)], wb = bm_r[bk * 4 + (sb >> 5)];
                         // On the own path the observer's own entry (path element tot, rows t0o..t1o) is in the index too: a slot it
                         // covers needs a second entry to matter.  (t1o is a lower bound for the last element: errs towards checking.)
                         bool own_a = false, own_b = false;

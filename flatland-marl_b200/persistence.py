@@ -76,9 +76,15 @@ class _LevelUnpickler(pickle.Unpickler):
 
 
 def load_env_dict(path):
-    """RailEnvPersister.load_env_dict (persistence.py:132-161) for .pkl files, without importing flatland."""
+    """RailEnvPersister.load_env_dict (persistence.py:132-161) for .pkl files, without importing flatland.
+
+    .mpk (msgpack) files are refused: the reference itself can neither write nor read them with its own pinned
+    dependencies — `RailEnvPersister.save` packs the env dict with `msgpack.packb`, which has no encoder for the
+    SpeedCounter / TrainStateMachine objects inside the Agent tuples, and `load_env_dict` calls
+    `msgpack.unpackb(..., encoding="utf-8")`, a keyword msgpack >= 1.0 (requirements_dev.txt:11 pins >=1.0,<2) no longer
+    accepts (tests/test_persistence.py::test_reference_cannot_read_mpk shows both on the unmodified reference)."""
     if not str(path).endswith(".pkl"):
-        raise ValueError("only .pkl level files are supported (%s)" % path)
+        raise ValueError("only .pkl level files are supported (%s); see load_env_dict's docstring for .mpk" % path)
     with open(path, "rb") as f:
         d = _LevelUnpickler(io.BytesIO(f.read())).load()
     if not isinstance(d, dict) or "grid" not in d or "agents" not in d:
@@ -128,3 +134,25 @@ def world_from_env_dict(d, sched_rows=None, malfunction_seed=0):
 def load_level(path, sched_rows=None, malfunction_seed=0):
     """One saved level -> world dict."""
     return world_from_env_dict(load_env_dict(path), sched_rows=sched_rows, malfunction_seed=malfunction_seed)
+
+
+class RailEnvPersister:
+    """`flatland.envs.persistence.RailEnvPersister` for the hot path's consumers (solution/demo.py:89:
+    `env, _ = RailEnvPersister.load_new(args.env); env.obs_builder = TreeCutils(...)`): the level file becomes a
+    `flatland_marl_b200.RailEnv` on the GPU.  `load_new` returns (env, env_dict) like the reference
+    (persistence.py:105-129).  The reference's loaded env regenerates its timetable on the next default `reset()` from an
+    unseeded RandomState (rail_env.py:260-330 with `rail_from_file` / `line_from_file`), i.e. differently on every run;
+    this env keeps the timetable stored in the file."""
+
+    @classmethod
+    def load_new(cls, filename, load_from_package=None, device="cuda:0", malfunction_seed=0):
+        if load_from_package is not None:
+            raise ValueError("load_from_package is not supported: pass a file path")
+        from .rail_env import RailEnv
+        env_dict = load_env_dict(filename)
+        world = world_from_env_dict(env_dict, malfunction_seed=malfunction_seed)
+        return RailEnv.from_world(world, device=device), env_dict
+
+    @classmethod
+    def load_env_dict(cls, filename, load_from_package=None):
+        return load_env_dict(filename)

@@ -199,7 +199,8 @@ int64_t fl_observe_ws_words(const FlBatch *b);
  * from the batch shape, process-wide, value < 0 = back to the default.  Keys: "nt" (threads per CTA: 64..1024), "ctas"
  * (CTAs per SM the plan is cut for), "tables" (bit mask of the static tables staged in shared memory), "segcap", "entcap"
  * (capacities of the shared-memory segment pool / entry array, to force the global spill paths), "sortsmall" (largest bucket
- * sorted by one thread), "parts" (CTAs per environment for the tree phase).  The same knobs are read ONCE from the
+ * sorted by one thread), "parts" (CTAs per environment of the tree kernel; 0 = fused kernel), "treent" (threads per CTA of the
+ * tree kernel), "bmglobal" (1: the tree kernel reads the time-slot filter from the workspace instead of shared memory).  The same knobs are read ONCE from the
  * environment variables FL_OBS_<KEY> when the library is loaded; fl_observe itself never calls getenv.
  * Returns 0, or FL_ERR_BAD_ARG for an unknown key. */
 int fl_observe_override(const char *key, int value);

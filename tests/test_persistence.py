@@ -84,3 +84,40 @@ def test_loaded_level_runs_and_distance_map_matches_the_file():
     for t in range(20):
         obs, rew, don = batch.step(torch.full((2, int(w["N"])), 2, dtype=torch.uint8, device=batch.device))
     assert int(batch.t["elapsed"][0].item()) == 20
+
+
+@pytest.mark.reference
+def test_reference_cannot_read_mpk(tmp_path):
+    """Why .mpk level files are refused: the unmodified reference can neither read nor write them with the msgpack its own
+    requirements pin (>= 1.0): load_env_dict passes `encoding=` to msgpack.unpackb (persistence.py:142), which msgpack 1.x
+    rejects, and save() hands msgpack objects it has no encoder for."""
+    import msgpack
+    from oracle import ref_harness as rh
+    if not rh.available():
+        pytest.skip("needs the reference tree (build container)")
+    rh.load()
+    from flatland.envs.persistence import RailEnvPersister
+    assert msgpack.version >= (1, 0, 0)
+    f = tmp_path / "level.mpk"
+    f.write_bytes(msgpack.packb({"grid": [[0]], "agents": []}))
+    with pytest.raises(TypeError):
+        RailEnvPersister.load_env_dict(str(f))
+    env = rh.make_env("Test_00", rh.csv_seed(0, 0))
+    env.reset()
+    with pytest.raises(TypeError):
+        RailEnvPersister.save(env, str(tmp_path / "out.mpk"))
+
+
+@pytest.mark.gpu
+def test_load_new_facade_runs_the_demo_calls():
+    """solution/demo.py:89-113 with --env: RailEnvPersister.load_new, obs_builder assignment, reset, steps."""
+    import flatland_marl_b200 as fb
+    env, env_dict = fb.RailEnvPersister.load_new(os.path.join(GOLD, "level_t00.pkl"))
+    env.obs_builder = fb.TreeObsForRailEnv(31, 500)
+    assert set(env_dict) >= {"grid", "agents", "malfunction", "max_episode_steps"}
+    obs, info = env.reset()
+    n = env.get_num_agents()
+    assert n == len(env_dict["agents"]) and env._max_episode_steps == int(env_dict["max_episode_steps"])
+    for t in range(10):
+        obs, rew, done, info = env.step({i: 2 for i in range(n)})
+    assert np.array(obs[0]).shape == (n, 83) and not done["__all__"]
