@@ -33,7 +33,9 @@
 #include "bfs.cuh"
 #include "wire.cuh"
 
+#include <chrono>
 #include <condition_variable>
+#include <cstdio>
 #include <functional>
 #include <thread>
 
@@ -361,7 +363,7 @@ int fl_observe(const FlBatch *b, float *d_agent_attr, float *d_forest, int32_t *
         // the register budget follows the number of CTAs the shared-memory plan lets share an SM
 #define FL_K(NT_, RES_) (mode == OBS_FUSED ? (Kern)k_observe<NT_, RES_, OBS_FUSED> : mode == OBS_INDEX ? (Kern)k_observe<NT_, RES_, OBS_INDEX> : (Kern)k_observe<NT_, RES_, OBS_TREES>)
         if (nt == 64) return ctas > 8 ? FL_K(64, 12) : FL_K(64, 8);
-        if (nt == 128) return ctas > 6 ? FL_K(128, 8) : ctas > 4 ? FL_K(128, 6) : FL_K(128, 4);
+        if (nt == 128) return ctas > 7 ? FL_K(128, 8) : ctas > 6 ? FL_K(128, 7) : ctas > 4 ? FL_K(128, 6) : FL_K(128, 4);
         if (nt == 256) return ctas > 3 ? FL_K(256, 4) : ctas > 2 ? FL_K(256, 3) : FL_K(256, 2);
         if (nt == 512) return ctas > 1 ? FL_K(512, 2) : FL_K(512, 1);
         return FL_K(1024, 1);
@@ -518,7 +520,7 @@ int fl_host_threads(int n) {
 size_t fl_wire_bytes(const FlBatch *b, int n_chunks) {
     if (!b || b->E <= 0 || b->N <= 0) return 0;
     (void)n_chunks;
-    return ((size_t)b->E * (size_t)b->N * WIRE_MAX_WORDS + (size_t)b->E + 64) * 4;   // worst case: every node of every tree is real
+    return ((size_t)b->E * (size_t)b->N * WIRE_MAX_WORDS + (size_t)b->E + 64 * 16 + 64) * 4;   // worst case: every node of every tree is real
 }
 
 int fl_step_observe_host_compact(const FlBatch *b, const uint8_t *h_actions, uint8_t *d_actions, const FlObsBuffers *d_out,
@@ -534,14 +536,19 @@ int fl_step_observe_host_compact(const FlBatch *b, const uint8_t *h_actions, uin
     cudaError_t err = cudaHostGetDevicePointer((void **)&wire_dev, h_wire, 0);      // pinned + mapped host memory (UVA)
     if (err != cudaSuccess) return (int)err;
     const size_t N = (size_t)b->N;
-    const int smem = (int)((2 * ((N + 3) & ~(size_t)3) + 4 + (PACK_THREADS / 32) * (WIRE_MAX_WORDS + 2)) * 4);
+    const int smem = (int)((2 * ((N + 3) & ~(size_t)3) + 4 + (PACK_THREADS / 32) * WIRE_MAX_WORDS) * 4);
+    // expansion: 2 = AVX2 + non-temporal forest stores (default), 1 = AVX2, 0 = portable; FL_WIRE_TIMING=1 prints where a call's time goes
+    static const int expand_mode = getenv("FL_WIRE_EXPAND") ? atoi(getenv("FL_WIRE_EXPAND")) : 2;
+    static const bool timing = getenv("FL_WIRE_TIMING") != nullptr;
+    const auto t_start = std::chrono::steady_clock::now();
+    double t_wait = 0.0, t_expand = 0.0;
     if ((err = cudaMemcpyAsync(d_actions, h_actions, (size_t)b->E * N, cudaMemcpyHostToDevice, st)) != cudaSuccess) return (int)err;
     if ((err = cudaMemsetAsync(d_cursor, 0, sizeof(uint32_t) * (size_t)n_chunks, st)) != cudaSuccess) return (int)err;
     std::vector<size_t> chunk_word0((size_t)n_chunks);
     for (int c = 0; c < n_chunks; c++) {
         const int64_t e0 = b->E * c / n_chunks, e1 = b->E * (c + 1) / n_chunks, n = e1 - e0;
         const size_t a0 = (size_t)e0 * N;
-        chunk_word0[c] = a0 * WIRE_MAX_WORDS + (size_t)e0;                          // worst-case prefix: regions never overlap
+        chunk_word0[c] = ((a0 * WIRE_MAX_WORDS + (size_t)e0 + 7) & ~(size_t)7) + 16 * (size_t)c;   // worst-case prefix, 32-byte aligned: regions never overlap
         FlBatch sub;
         if (int rc = fl_batch_slice(b, e0, n, &sub)) return rc;
         if (int rc = fl_step(&sub, d_actions + a0, d_out->rewards + a0, d_out->dones + (size_t)e0 * (N + 1), flags, stream)) return rc;
@@ -569,14 +576,23 @@ int fl_step_observe_host_compact(const FlBatch *b, const uint8_t *h_actions, uin
     const WireDst dst{h_out->agent_attr, h_out->forest, h_out->dist_target, h_out->adjacency, h_out->node_order, h_out->edge_order,
                       h_out->rewards, h_out->valid_actions, h_out->dones};
     std::atomic<uint64_t> words{0};
+    const auto t_launched = std::chrono::steady_clock::now();
     for (int c = 0; c < n_chunks; c++) {
+        const auto t0 = std::chrono::steady_clock::now();
         if ((err = cudaEventSynchronize(chunk_event(64 + c))) != cudaSuccess) return (int)err;
+        const auto t1 = std::chrono::steady_clock::now();
         const int64_t e0 = b->E * c / n_chunks, e1 = b->E * (c + 1) / n_chunks;
         const uint32_t *wire = reinterpret_cast<const uint32_t *>(h_wire) + chunk_word0[c];
         const int Ni = (int)N;
-        const std::function<void(int)> job = [&](int el) { words.fetch_add(expand_env(wire, el, e0 + el, Ni, dst) + 1); };
+        const std::function<void(int)> job = [&](int el) { words.fetch_add(expand_env(wire, el, e0 + el, Ni, dst, expand_mode) + 1); };
         g_pool.parallel_for((int)(e1 - e0), job);
+        t_wait += std::chrono::duration<double>(t1 - t0).count();
+        t_expand += std::chrono::duration<double>(std::chrono::steady_clock::now() - t1).count();
     }
+    if (timing)
+        fprintf(stderr, "fl_step_observe_host_compact: launch %.3f ms, waiting for the device %.3f ms, expanding %.3f ms (%d chunks, %d threads, %.1f MB wire)\n",
+                1e3 * std::chrono::duration<double>(t_launched - t_start).count(), 1e3 * t_wait, 1e3 * t_expand, n_chunks, g_pool.threads(),
+                words.load() * 4 / 1e6);
     if (wire_bytes_out) *wire_bytes_out = words.load() * 4;
     if (cs != st) {
         if ((err = cudaStreamWaitEvent(st, chunk_event(64 + n_chunks - 1), 0)) != cudaSuccess) return (int)err;

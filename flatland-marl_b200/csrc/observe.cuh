@@ -749,23 +749,24 @@ k_observe(FlBatch b, ObsLayout lay, float *__restrict__ out_attr, float *__restr
                 ent[y + 1] = v;
             }
         };
-        // a whole warp sorts bucket [s0, s0 + n)
-        auto warp_sort = [&](int s0, int n) {
-            if (n <= 32) {                                                      // bitonic network in registers
-                const uint32_t v0 = lane < n ? ent[s0 + lane] : 0u;
-                uint32_t kv = lane < n ? ((entry_sort_key(v0) << 5) | (uint32_t)lane) : 0xFFFFFFFFu;   // key | source lane
+        // up to 32 entries, one per lane (v0: the lane's entry, already loaded): bitonic network of register shuffles
+        auto warp_sort_regs = [&](int s0, int n, uint32_t v0) {
+            uint32_t kv = lane < n ? ((entry_sort_key(v0) << 5) | (uint32_t)lane) : 0xFFFFFFFFu;   // key | source lane
 #pragma unroll
-                for (int k2 = 2; k2 <= 32; k2 <<= 1)
+            for (int k2 = 2; k2 <= 32; k2 <<= 1)
 #pragma unroll
-                    for (int j2 = k2 >> 1; j2 > 0; j2 >>= 1) {
-                        const uint32_t o = __shfl_xor_sync(0xFFFFFFFFu, kv, j2);
-                        const bool up = (lane & k2) == 0, low = (lane & j2) == 0;
-                        kv = (low == up) ? min(kv, o) : max(kv, o);
-                    }
-                const uint32_t v = __shfl_sync(0xFFFFFFFFu, v0, kv & 31u);
-                if (lane < n) ent[s0 + lane] = v;
-                return;
-            }
+                for (int j2 = k2 >> 1; j2 > 0; j2 >>= 1) {
+                    const uint32_t o = __shfl_xor_sync(0xFFFFFFFFu, kv, j2);
+                    const bool up = (lane & k2) == 0, low = (lane & j2) == 0;
+                    kv = (low == up) ? min(kv, o) : max(kv, o);
+                }
+            const uint32_t v = __shfl_sync(0xFFFFFFFFu, v0, kv & 31u);
+            if (lane < n) ent[s0 + lane] = v;
+        };
+        // more than 32 entries: two stable radix passes (5 + 5 bits of the 10-bit key) through the scratch copy, the bucket
+        // taken 256 entries at a time so that eight loads per lane are in flight (one memory round trip per 256 entries and
+        // loop instead of one per 32)
+        auto warp_sort_radix = [&](int s0, int n) {
             if (!scratch) { if (lane == 0) insertion_sort(s0, s0 + n); __syncwarp(); return; }
             uint32_t *bufa = ent + s0, *bufb = scratch + s0;
 #pragma unroll 1
@@ -775,27 +776,40 @@ k_observe(FlBatch b, ObsLayout lay, float *__restrict__ out_attr, float *__restr
                 const int sh = 5 * pass;
                 hist[lane] = 0;
                 __syncwarp();
-                for (int x = lane; x < n; x += 32) atomicAdd(&hist[(entry_sort_key(src[x]) >> sh) & 31u], 1u);
+                for (int x0 = 0; x0 < n; x0 += 256) {
+                    uint32_t v[8];
+#pragma unroll
+                    for (int u = 0; u < 8; u++) { const int x = x0 + u * 32 + lane; v[u] = x < n ? src[x] : 0u; }
+#pragma unroll
+                    for (int u = 0; u < 8; u++)
+                        if (x0 + u * 32 + lane < n) atomicAdd(&hist[(entry_sort_key(v[u]) >> sh) & 31u], 1u);
+                }
                 __syncwarp();
                 unsigned tot;
                 const unsigned c = hist[lane], base = warp_excl_scan(c, lane, tot);
                 __syncwarp();
                 hist[lane] = base;
                 __syncwarp();
-                for (int x0 = 0; x0 < n; x0 += 32) {                            // in order: the radix passes must be stable
-                    const int x = x0 + lane;
-                    const bool valid = x < n;
-                    const uint32_t v = valid ? src[x] : 0u;
-                    const unsigned dg = valid ? ((entry_sort_key(v) >> sh) & 31u) : 32u + (unsigned)lane;
-                    const unsigned m = __match_any_sync(0xFFFFFFFFu, dg);
-                    const int rank = __popc(m & ((1u << lane) - 1u));
-                    if (valid) dst[hist[dg] + rank] = v;
-                    __syncwarp();
-                    if (valid && rank == 0) hist[dg] += (unsigned)__popc(m);
-                    __syncwarp();
+                for (int x0 = 0; x0 < n; x0 += 256) {
+                    uint32_t v[8];
+#pragma unroll
+                    for (int u = 0; u < 8; u++) { const int x = x0 + u * 32 + lane; v[u] = x < n ? src[x] : 0u; }
+#pragma unroll
+                    for (int u = 0; u < 8; u++) {                               // in order: the passes must be stable
+                        if (x0 + u * 32 >= n) break;                            // warp-uniform
+                        const bool valid = x0 + u * 32 + lane < n;
+                        const unsigned dg = valid ? ((entry_sort_key(v[u]) >> sh) & 31u) : 32u + (unsigned)lane;
+                        const unsigned m = __match_any_sync(0xFFFFFFFFu, dg);
+                        const int rank = __popc(m & ((1u << lane) - 1u));
+                        if (valid) dst[hist[dg] + rank] = v[u];
+                        __syncwarp();
+                        if (valid && rank == 0) hist[dg] += (unsigned)__popc(m);
+                        __syncwarp();
+                    }
                 }
             }
         };
+        constexpr int NWARPS = NW / 32;
         if (in_smem) {
             for (int key = tid; key < R; key += NW) {
                 const int s0 = (int)ks[key - 1], s1 = (int)ks[key];
@@ -806,15 +820,27 @@ k_observe(FlBatch b, ObsLayout lay, float *__restrict__ out_attr, float *__restr
             named_bar_sync(1, NW);
             OBS_TICK(9);
             const int n_big = min(ld_vol_i32(&s_misc[1]), bigq_cap);
-            for (int q = warp; q < n_big; q += NW / 32) {
-                const int key = (int)bigq[q], s0 = (int)ks[key - 1];
-                warp_sort(s0, (int)ks[key] - s0);
+            for (int q = warp; q < n_big; q += NWARPS) {
+                const int key = (int)bigq[q], s0 = (int)ks[key - 1], n = (int)ks[key] - s0;
+                if (n <= 32) warp_sort_regs(s0, n, lane < n ? ent[s0 + lane] : 0u);
+                else warp_sort_radix(s0, n);
             }
         } else {
             OBS_TICK(9);
-            for (int key = warp; key < R; key += NW / 32) {
-                const int s0 = (int)ks[key - 1], n = (int)ks[key] - s0;
-                if (n >= 2) warp_sort(s0, n);
+            // every bucket by a warp; the entries of the warp's next bucket are fetched while the current one is sorted
+            auto fetch = [&](int key, int &s0, int &n, uint32_t &v) {
+                n = 0; v = 0u; s0 = 0;
+                if (key < R) { s0 = (int)ks[key - 1]; n = (int)ks[key] - s0; if (n >= 2 && n <= 32 && lane < n) v = ent[s0 + lane]; }
+            };
+            int s0c, nc;
+            uint32_t vc;
+            fetch(warp, s0c, nc, vc);
+            for (int key = warp; key < R; key += NWARPS) {
+                int s0x, nx;
+                uint32_t vx;
+                fetch(key + NWARPS, s0x, nx, vx);
+                if (nc >= 2) { if (nc <= 32) warp_sort_regs(s0c, nc, vc); else warp_sort_radix(s0c, nc); }
+                s0c = s0x; nc = nx; vc = vx;
             }
         }
         named_bar_sync(1, NW);

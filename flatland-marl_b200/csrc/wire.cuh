@@ -14,8 +14,9 @@
 //   w[1..3]   attribute entries 0..69 as bits (feature_parser.cpp:19-77: one-hot codes and flags, exactly 0.0 or 1.0)
 //   w[4..16]  attribute entries 70..82 (floats)
 //   w[17]     dist_target (float)      w[18] reward (int32)      w[19] dones[i]
-//   w[20..57] 151 bytes: adjacency[30][3], node_order[31], edge_order[30] as int8 (values -2..30)
-//   then 12 floats per set bit of the node mask, in node order.
+//   w[20..57] 151 bytes: adjacency[30][3], node_order[31], edge_order[30] as int8 (values -2..30);  w[58..63] zero
+//   then 12 floats per set bit of the node mask, in node order; the record is padded to a multiple of 8 words, so that
+//   every record starts on a 32-byte boundary and every store instruction of the pack kernel covers whole sectors.
 #pragma once
 #include "common.cuh"
 
@@ -23,8 +24,9 @@
 
 namespace {
 
-constexpr int WIRE_FIXED_WORDS = 58;
-constexpr int WIRE_MAX_WORDS = WIRE_FIXED_WORDS + FL_MAX_NODES * FL_NODE_F;   // 430
+constexpr int WIRE_FIXED_WORDS = 64;
+constexpr int WIRE_MAX_WORDS = (WIRE_FIXED_WORDS + FL_MAX_NODES * FL_NODE_F + 7) & ~7;   // 440
+__host__ __device__ inline int wire_record_words(unsigned mask) { return (WIRE_FIXED_WORDS + FL_NODE_F * __builtin_popcount(mask) + 7) & ~7; }
 
 struct WireSrc {   // device pointers of the environment range being packed (already advanced to its first environment)
     const float *attr, *forest, *dist_target;
@@ -39,7 +41,7 @@ k_pack(WireSrc src, int N, int n_env, uint32_t *__restrict__ wire, uint32_t *__r
     const int el = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     extern __shared__ uint32_t pk_smem[];
     const int Np = (N + 3) & ~3;                       // keeps the staging areas 16-byte aligned
-    uint32_t *s_mask = pk_smem, *s_off = pk_smem + Np, *stage = pk_smem + 2 * Np + 4 + warp * (WIRE_MAX_WORDS + 2);
+    uint32_t *s_mask = pk_smem, *s_off = pk_smem + Np, *stage = pk_smem + 2 * Np + 4 + warp * WIRE_MAX_WORDS;
     uint32_t *s_base = pk_smem + 2 * Np;
     const size_t a0 = (size_t)el * N;
     // pass 1: which nodes are not the all -1 vector
@@ -59,7 +61,7 @@ k_pack(WireSrc src, int N, int n_env, uint32_t *__restrict__ wire, uint32_t *__r
         unsigned run = 0;
         for (int i0 = 0; i0 < N; i0 += 32) {
             const int i = i0 + lane;
-            const unsigned len = i < N ? WIRE_FIXED_WORDS + FL_NODE_F * __popc(s_mask[i]) : 0u;
+            const unsigned len = i < N ? (unsigned)((WIRE_FIXED_WORDS + FL_NODE_F * __popc(s_mask[i]) + 7) & ~7) : 0u;
             unsigned x = len;
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) { const unsigned y = __shfl_up_sync(0xFFFFFFFFu, x, o); if (lane >= o) x += y; }
@@ -67,7 +69,7 @@ k_pack(WireSrc src, int N, int n_env, uint32_t *__restrict__ wire, uint32_t *__r
             run += __shfl_sync(0xFFFFFFFFu, x, 31);
         }
         if (lane == 0) {
-            const unsigned base = (unsigned)n_env + atomicAdd(cursor, run);
+            const unsigned base = (unsigned)((n_env + 7) & ~7) + atomicAdd(cursor, run);
             s_base[0] = base;
             wire[el] = base | ((uint32_t)(src.dones[(size_t)el * (N + 1) + N] != 0) << 31);
         }
@@ -92,16 +94,17 @@ k_pack(WireSrc src, int N, int n_env, uint32_t *__restrict__ wire, uint32_t *__r
         if (lane < FL_MAX_NODES) sb[90 + lane] = (uint8_t)(int8_t)src.node_order[ea * FL_MAX_NODES + lane];
         if (lane < FL_MAX_NODES - 1) sb[121 + lane] = (uint8_t)(int8_t)src.edge_order[ea * (FL_MAX_NODES - 1) + lane];
         if (lane == 31) sb[151] = 0;
+        if (lane >= 26) stage[58 + lane - 26] = 0u;
         if (lane < FL_MAX_NODES && ((mask >> lane) & 1u)) {
             const float4 *p = reinterpret_cast<const float4 *>(src.forest + ea * (FL_MAX_NODES * FL_NODE_F) + lane * FL_NODE_F);
-            float4 *q = reinterpret_cast<float4 *>(stage + WIRE_FIXED_WORDS + 2 + FL_NODE_F * __popc(mask & ((1u << lane) - 1u)));
+            float4 *q = reinterpret_cast<float4 *>(stage + WIRE_FIXED_WORDS + FL_NODE_F * __popc(mask & ((1u << lane) - 1u)));
             q[0] = p[0]; q[1] = p[1]; q[2] = p[2];
         }
         __syncwarp();
-        const int nodes_w = FL_NODE_F * __popc(mask);
-        uint32_t *out = wire + base + s_off[i];
-        for (int k = lane; k < WIRE_FIXED_WORDS; k += 32) out[k] = stage[k];
-        for (int k = lane; k < nodes_w; k += 32) out[WIRE_FIXED_WORDS + k] = stage[WIRE_FIXED_WORDS + 2 + k];   // (+2: the node part is 16-byte aligned in the stage)
+        const int len = (WIRE_FIXED_WORDS + FL_NODE_F * __popc(mask) + 7) & ~7;   // the padding words carry stale bytes of the stage
+        uint4 *out = reinterpret_cast<uint4 *>(wire + base + s_off[i]);
+        const uint4 *st4 = reinterpret_cast<const uint4 *>(stage);
+        for (int k = lane; k < len / 4; k += 32) out[k] = st4[k];                  // 16 bytes per lane, 512 contiguous bytes per store
         __syncwarp();
     }
 }
@@ -113,8 +116,9 @@ struct WireDst {   // host pointers of the WHOLE batch (the reference-facing lay
     uint8_t *valid_actions, *dones;
 };
 
-// Rebuilds environment `e_global` (local index el of the chunk whose stream starts at `wire`) in the host tensors.
-inline uint64_t expand_env(const uint32_t *wire, int el, long long e_global, int N, const WireDst &d) {
+// Rebuilds environment `e_global` (local index el of the chunk whose stream starts at `wire`) in the host tensors; returns
+// the words consumed.  Portable version.
+inline uint64_t expand_env_scalar(const uint32_t *wire, int el, long long e_global, int N, const WireDst &d) {
     const uint32_t tw = wire[el];
     const uint32_t *p = wire + (tw & 0x7FFFFFFFu);
     const uint32_t *const p0 = p;
@@ -145,9 +149,81 @@ inline uint64_t expand_env(const uint32_t *wire, int el, long long e_global, int
                 else for (int k = 0; k < FL_NODE_F; k++) f[n * FL_NODE_F + k] = -1.0f;
             }
         }
-        p += WIRE_FIXED_WORDS + FL_NODE_F * __builtin_popcount(mask);
+        p += wire_record_words(mask);
     }
     return (uint64_t)(p - p0);
+}
+
+#if defined(__x86_64__) && !defined(__CUDA_ARCH__)
+}  // namespace
+#include <immintrin.h>
+namespace {
+struct WireBitLut {   // byte -> eight floats 0.0 / 1.0
+    alignas(32) float f[256][8];
+    WireBitLut() { for (int b = 0; b < 256; b++) for (int k = 0; k < 8; k++) f[b][k] = (float)((b >> k) & 1); }
+};
+inline const WireBitLut &wire_bit_lut() { static const WireBitLut lut; return lut; }
+
+__attribute__((target("avx2")))
+inline void wire_widen(int32_t *q, const int8_t *src, int n) {   // int8 -> int32, eight at a time
+    int k = 0;
+    for (; k + 8 <= n; k += 8)
+        _mm256_storeu_si256(reinterpret_cast<__m256i *>(q + k), _mm256_cvtepi8_epi32(_mm_loadl_epi64(reinterpret_cast<const __m128i *>(src + k))));
+    for (; k < n; k++) q[k] = src[k];
+}
+
+// The same with AVX2: flags through a byte -> 8 floats table, int8 -> int32 eight at a time, and the forest rows (61 % of
+// the bytes; every 48-byte node slot is 16-byte aligned) with non-temporal stores when `nt` is set, so that 125 MB per step
+// do not first pull their cache lines in.
+__attribute__((target("avx2")))
+inline uint64_t expand_env_avx2(const uint32_t *wire, int el, long long e_global, int N, const WireDst &d, bool nt) {
+    const WireBitLut &lut = wire_bit_lut();
+    const uint32_t tw = wire[el];
+    const uint32_t *p = wire + (tw & 0x7FFFFFFFu);
+    const uint32_t *const p0 = p;
+    if (d.dones) d.dones[(size_t)e_global * (N + 1) + N] = (uint8_t)(tw >> 31);
+    const __m128 minus1 = _mm_set1_ps(-1.0f);
+    nt = nt && d.forest && (reinterpret_cast<uintptr_t>(d.forest) & 15) == 0;
+    for (int i = 0; i < N; i++) {
+        const size_t ea = (size_t)e_global * N + i;
+        const uint32_t mask = p[0];
+        if (d.attr) {
+            float *a = d.attr + ea * FL_ATTR_F;
+            const uint8_t *bits = reinterpret_cast<const uint8_t *>(p + 1);          // bytes 0..8: entries 0..71 (70, 71 are zero bits)
+            for (int k = 0; k < 9; k++) _mm256_storeu_ps(a + 8 * k, _mm256_load_ps(lut.f[bits[k]]));
+            std::memcpy(a + 70, p + 4, 13 * sizeof(float));
+        }
+        if (d.valid_actions) for (int k = 0; k < 5; k++) d.valid_actions[ea * 5 + k] = (uint8_t)((p[3] >> (1 + k)) & 1u);
+        if (d.dist_target) std::memcpy(d.dist_target + ea, p + 17, 4);
+        if (d.rewards) d.rewards[ea] = (int32_t)p[18];
+        if (d.dones) d.dones[(size_t)e_global * (N + 1) + i] = (uint8_t)p[19];
+        const int8_t *sb = reinterpret_cast<const int8_t *>(p + 20);
+        if (d.adjacency) wire_widen(d.adjacency + ea * ((FL_MAX_NODES - 1) * 3), sb, 90);
+        if (d.node_order) wire_widen(d.node_order + ea * FL_MAX_NODES, sb + 90, FL_MAX_NODES);
+        if (d.edge_order) wire_widen(d.edge_order + ea * (FL_MAX_NODES - 1), sb + 121, FL_MAX_NODES - 1);
+        const float *nodes = reinterpret_cast<const float *>(p + WIRE_FIXED_WORDS);
+        if (d.forest) {
+            float *f = d.forest + ea * (FL_MAX_NODES * FL_NODE_F);
+            for (int n = 0; n < FL_MAX_NODES; n++, f += FL_NODE_F) {
+                __m128 x = minus1, y = minus1, z = minus1;
+                if ((mask >> n) & 1u) { x = _mm_loadu_ps(nodes); y = _mm_loadu_ps(nodes + 4); z = _mm_loadu_ps(nodes + 8); nodes += FL_NODE_F; }
+                if (nt) { _mm_stream_ps(f, x); _mm_stream_ps(f + 4, y); _mm_stream_ps(f + 8, z); }
+                else { _mm_storeu_ps(f, x); _mm_storeu_ps(f + 4, y); _mm_storeu_ps(f + 8, z); }
+            }
+        }
+        p += wire_record_words(mask);
+    }
+    if (nt) _mm_sfence();
+    return (uint64_t)(p - p0);
+}
+#define FL_WIRE_HAVE_AVX2 1
+#endif
+
+inline uint64_t expand_env(const uint32_t *wire, int el, long long e_global, int N, const WireDst &d, int mode) {
+#ifdef FL_WIRE_HAVE_AVX2
+    if (mode > 0 && __builtin_cpu_supports("avx2")) return expand_env_avx2(wire, el, e_global, N, d, mode > 1);
+#endif
+    return expand_env_scalar(wire, el, e_global, N, d);
 }
 
 }  // namespace
