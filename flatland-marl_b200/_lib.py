@@ -34,7 +34,7 @@ class FlObsBuffers(C.Structure):
                                           "valid_actions", "dist_target", "rewards", "dones")]
 
 
-EXPORTS = ["fl_abi_version", "fl_batch_sizeof", "fl_error_string", "fl_distance_map", "fl_walk_tables", "fl_reset", "fl_reset_ex", "fl_step",
+EXPORTS = ["fl_abi_version", "fl_batch_sizeof", "fl_error_string", "fl_distance_map", "fl_distance_map_ids", "fl_walk_tables", "fl_walk_tables_ids", "fl_reset", "fl_reset_ex", "fl_step",
            "fl_observe", "fl_observe_override", "fl_observe_plan", "fl_observe_ws_words", "fl_batch_slice", "fl_step_observe_host", "fl_step_observe_host_compact", "fl_wire_bytes", "fl_host_threads", "fl_launch_count", "fl_profile_num_kernels", "fl_profile_kernel_name",
            "fl_profile_enable", "fl_profile_collect"]
 
@@ -67,6 +67,8 @@ def lib():
     L.fl_observe_ws_words.argtypes = [C.POINTER(FlBatch)]
     L.fl_observe_ws_words.restype = C.c_int64
     L.fl_walk_tables.argtypes = [C.POINTER(FlBatch), C.c_int, P]
+    L.fl_distance_map_ids.argtypes = [C.POINTER(FlBatch), P, C.c_int64, P]
+    L.fl_walk_tables_ids.argtypes = [C.POINTER(FlBatch), C.c_int, P, C.c_int64, P]
     L.fl_step.argtypes = [C.POINTER(FlBatch), P, P, P, C.c_uint32, P]
     L.fl_observe.argtypes = [C.POINTER(FlBatch)] + [P] * 8
     L.fl_step_observe_host.argtypes = [C.POINTER(FlBatch), P, P, C.POINTER(FlObsBuffers), C.POINTER(FlObsBuffers),
@@ -88,7 +90,7 @@ def lib():
     L.fl_profile_enable.restype = None
     L.fl_profile_collect.argtypes = [P, P, C.c_int]
     L.fl_profile_collect.restype = C.c_int
-    for f in ("fl_distance_map", "fl_walk_tables", "fl_reset", "fl_reset_ex", "fl_step", "fl_observe", "fl_step_observe_host", "fl_batch_slice"):
+    for f in ("fl_distance_map", "fl_distance_map_ids", "fl_walk_tables", "fl_walk_tables_ids", "fl_reset", "fl_reset_ex", "fl_step", "fl_observe", "fl_step_observe_host", "fl_batch_slice"):
         getattr(L, f).restype = C.c_int
     if L.fl_batch_sizeof() != C.sizeof(FlBatch):
         raise FlatlandB200Error("FlBatch layout mismatch: library %d bytes, binding %d bytes"

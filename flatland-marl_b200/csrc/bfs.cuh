@@ -8,9 +8,9 @@ namespace {
 // k_bfs: DistanceMap (distance_map.py:57-160) as a level-synchronous pull BFS over (cell, orientation)
 // ---------------------------------------------------------------------------------------------
 template <bool SMEM>
-__global__ void __launch_bounds__(1024) k_bfs(FlBatch b) {
+__global__ void __launch_bounds__(1024) k_bfs(FlBatch b, const int32_t *__restrict__ env_ids) {
     const int H = (int)b.H, W = (int)b.W, HW = H * W, ns = (int)b.n_slots;
-    const int e = blockIdx.x / ns, s = blockIdx.x % ns;
+    const int e = env_ids ? env_ids[blockIdx.x / ns] : (int)(blockIdx.x / ns), s = blockIdx.x % ns;   // env_ids: only the listed environments
     extern __shared__ __align__(16) unsigned char smraw[];
     uint16_t *out = b.dist + (size_t)e * b.dist_stride + (size_t)s * HW * 4;
     uint16_t *dd = SMEM ? reinterpret_cast<uint16_t *>(smraw) : out;

@@ -287,30 +287,34 @@ const char *fl_error_string(int code) {
     }
 }
 
-int fl_distance_map(const FlBatch *b, void *stream) {
+int fl_distance_map_ids(const FlBatch *b, const int32_t *d_env_ids, int64_t n_ids, void *stream) {
     if (int rc = check_batch(b)) return rc;
+    if (d_env_ids && (n_ids <= 0 || n_ids > b->E)) return FL_ERR_BAD_ARG;
     cudaStream_t st = (cudaStream_t)stream;
     const int HW = (int)(b->H * b->W);
     const size_t smem = (size_t)HW * 4 * sizeof(uint16_t);
     const int nt = HW >= 4096 ? 1024 : 256;
-    const unsigned grid = (unsigned)(b->E * b->n_slots);
+    const unsigned grid = (unsigned)((d_env_ids ? n_ids : b->E) * b->n_slots);
     if (smem <= 227 * 1024) {
         if (smem > 48 * 1024) {
             cudaError_t err = cudaFuncSetAttribute(k_bfs<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             if (err != cudaSuccess) return (int)err;
         }
         LaunchScope ls(K_BFS, st);
-        k_bfs<true><<<grid, nt, smem, st>>>(*b);
+        k_bfs<true><<<grid, nt, smem, st>>>(*b, d_env_ids);
     } else {
         LaunchScope ls(K_BFS, st);
-        k_bfs<false><<<grid, nt, 0, st>>>(*b);
+        k_bfs<false><<<grid, nt, 0, st>>>(*b, d_env_ids);
     }
     return finish(cudaGetLastError());
 }
 
-int fl_walk_tables(const FlBatch *b, int fill, void *stream) {
+int fl_distance_map(const FlBatch *b, void *stream) { return fl_distance_map_ids(b, nullptr, 0, stream); }
+
+int fl_walk_tables_ids(const FlBatch *b, int fill, const int32_t *d_env_ids, int64_t n_ids, void *stream) {
     if (int rc = check_batch(b)) return rc;
     if (!b->ridx || !b->walk_total) return FL_ERR_BAD_ARG;
+    if (d_env_ids && (n_ids <= 0 || n_ids > b->E)) return FL_ERR_BAD_ARG;
     if (fill && (!b->srec || !b->wrec || !b->whoff || !b->wlist || !b->whits || !b->kcls || !b->sdist || !b->gtab || !b->dist || b->state_stride <= 0 || b->wlist_stride <= 0 ||
                  b->whits_stride <= 0))
         return FL_ERR_BAD_ARG;
@@ -322,11 +326,14 @@ int fl_walk_tables(const FlBatch *b, int fill, void *stream) {
         if (err == cudaSuccess) err = cudaFuncSetAttribute(k_walks<false, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (err != cudaSuccess) return (int)err;
     }
+    const unsigned grid = (unsigned)(d_env_ids ? n_ids : b->E);
     LaunchScope ls(K_WALKS, st);
-    if (fill) k_walks<true, 256><<<(unsigned)b->E, 256, smem, st>>>(*b);
-    else k_walks<false, 256><<<(unsigned)b->E, 256, smem, st>>>(*b);
+    if (fill) k_walks<true, 256><<<grid, 256, smem, st>>>(*b, d_env_ids);
+    else k_walks<false, 256><<<grid, 256, smem, st>>>(*b, d_env_ids);
     return finish(cudaGetLastError());
 }
+
+int fl_walk_tables(const FlBatch *b, int fill, void *stream) { return fl_walk_tables_ids(b, fill, nullptr, 0, stream); }
 
 int fl_reset_ex(const FlBatch *b, const uint8_t *d_env_mask, uint32_t flags, void *stream) {
     if (int rc = check_batch(b)) return rc;
@@ -537,7 +544,8 @@ int fl_step_observe_host_compact(const FlBatch *b, const uint8_t *h_actions, uin
     if (err != cudaSuccess) return (int)err;
     const size_t N = (size_t)b->N;
     const int smem = (int)((2 * ((N + 3) & ~(size_t)3) + 4 + (PACK_THREADS / 32) * WIRE_MAX_WORDS) * 4);
-    // expansion: 2 = AVX2 + non-temporal forest stores (default), 1 = AVX2, 0 = portable; FL_WIRE_TIMING=1 prints where a call's time goes
+    // expansion: 3 = AVX2 + non-temporal stores for every tensor, 2 = AVX2 + non-temporal forest stores (default), 1 = AVX2,
+    // 0 = portable; FL_WIRE_TIMING=1 prints where a call's time goes
     static const int expand_mode = getenv("FL_WIRE_EXPAND") ? atoi(getenv("FL_WIRE_EXPAND")) : 2;
     static const bool timing = getenv("FL_WIRE_TIMING") != nullptr;
     const auto t_start = std::chrono::steady_clock::now();

@@ -85,7 +85,8 @@ DEVI uint32_t ld_vol_u32(const uint32_t *p) { return *reinterpret_cast<const vol
 DEVI int ld_vol_i32(const int *p) { return *reinterpret_cast<const volatile int *>(p); }
 DEVI unsigned ld_vol_u16(const uint16_t *p) { return *reinterpret_cast<const volatile uint16_t *>(p); }
 
-DEVI uint32_t pack_entry(int agent, int t0, int t1, int dh, int dp, int dn);
+DEVI uint32_t pack_entry(int agent, int t0, int t1, int dh, int dp, int dn, uint32_t extra);
+DEVI uint32_t entry_extra(int tpc, bool done);
 // Predicted occupancy of one agent (predictions.cpp:13-235 + the transpose in treeobs.cpp:50-65) from the static walk
 // tables.  The greedy descent of the distance map is forced inside a walk (one successor per state) and, because the
 // distance of a state is one more than the lowest distance among its successors, always continues at the end of a
@@ -96,11 +97,11 @@ DEVI uint32_t pack_entry(int agent, int t0, int t1, int dh, int dp, int dn);
 // (or all rows when the path has a single element).  Emit(rail cell, t0, t1, entry) is called once per occupied element.
 template <class Emit>
 DEVI void predict_path(const uint4 *wrec, const uint32_t *whoff, const uint32_t *whits, const uint32_t *wlist,
-                       const uint16_t *sd, unsigned sid, unsigned slot, int tpc, int agent, Emit emit) {
+                       const uint16_t *sd, unsigned sid, unsigned slot, int tpc, int agent, uint32_t extra, Emit emit) {
     int dp = (int)(sid & 3u);                        // direction of the previous element (element 0: its own)
     if (sd[sid] == FL_DIST_INF) {                    // no move lowers the distance: the path is its first element
         // (a start state on the target has distance 0 and ends through the target hit below)
-        emit(sid >> 2, 0, NPRED - 1, pack_entry(agent, 0, NPRED - 1, dp, dp, dp));
+        emit(sid >> 2, 0, NPRED - 1, pack_entry(agent, 0, NPRED - 1, dp, dp, dp, extra));
         return;
     }
     int kk = 0;                                      // path element index of the walk's first state
@@ -141,7 +142,7 @@ DEVI void predict_path(const uint4 *wrec, const uint32_t *whoff, const uint32_t 
                 const unsigned s = sv[u], sn = k < kend ? sv[u + 1] : nxt;
                 const int d = (int)(s & 3u), dn = last ? d : (int)(sn & 3u);
                 const int t1 = last ? NPRED - 1 : min(idx ? idx * tpc : 0, NPRED - 1);
-                emit(s >> 2, t0, t1, pack_entry(agent, t0, t1, d, dp, dn));
+                emit(s >> 2, t0, t1, pack_entry(agent, t0, t1, d, dp, dn, extra));
                 if (last) return;
                 dp = d;
             }
@@ -150,12 +151,18 @@ DEVI void predict_path(const uint4 *wrec, const uint32_t *whoff, const uint32_t 
     }
 }
 
-// Predicted-occupancy entry, 4 bytes: agent | t0 << 10 | last << 19 | dir_here << 20 | dir_prev << 22 | dir_next << 24.
+// Predicted-occupancy entry, 4 bytes: agent | t0 << 10 | last << 19 | dir_here << 20 | dir_prev << 22 | dir_next << 24 |
+// (rows per cell - 1) << 26 | agent is DONE << 29 | rows per cell > 8 (read it from the agent record instead) << 30.
 // The interval end is implied: 500 for the last element of a path ("last"), 0 for element 0, t0 + tpc - 1 otherwise.
-DEVI uint32_t pack_entry(int agent, int t0, int t1, int dh, int dp, int dn) {
+DEVI uint32_t pack_entry(int agent, int t0, int t1, int dh, int dp, int dn, uint32_t extra) {
     return (uint32_t)agent | ((uint32_t)t0 << 10) | ((uint32_t)(t1 == NPRED - 1) << 19) | ((uint32_t)dh << 20) |
-           ((uint32_t)dp << 22) | ((uint32_t)dn << 24);
+           ((uint32_t)dp << 22) | ((uint32_t)dn << 24) | extra;
 }
+DEVI uint32_t entry_extra(int tpc, bool done) {
+    return (tpc <= 8 ? (uint32_t)(tpc - 1) << 26 : 1u << 30) | ((uint32_t)done << 29);
+}
+// rows an entry's agent spends per cell (info: the agents' records, only read for speeds below 1/8)
+DEVI int entry_tpc(uint32_t en, const uint32_t *info) { return ((en >> 30) & 1u) ? (int)(info[en & 1023u] >> 24) : (int)((en >> 26) & 7u) + 1; }
 DEVI uint32_t entry_sort_key(uint32_t en) { return (((en >> 19) & 1u) ? 0u : 512u) + ((en >> 10) & 511u); }  // long-lived first, then by t0
 
 // loader.cpp:273-312: valid-action mask, bit a = action a allowed
@@ -646,7 +653,9 @@ k_observe(FlBatch b, ObsLayout lay, float *__restrict__ out_attr, float *__restr
             const unsigned sid = sg.x & 0xFFFFu;
             const int kend = (int)((sg.x >> 16) & 0x3FFFu), agent = (int)(sg.y & 1023u), kk = (int)((sg.y >> 10) & 511u);
             const bool seg_last = (sg.y >> 21) & 1u;
-            const int tpc = (int)(A.info[agent] >> 24);
+            const uint32_t ainf = A.info[agent];
+            const int tpc = (int)(ainf >> 24);
+            const uint32_t extra = entry_extra(tpc, (ainf >> 5) & 1u);
             int dp = (int)(sg.x >> 30);
             const uint32_t wx = wrec[sid].x;
             for (int k0 = 0; k0 <= kend; k0 += 4) {  // four states per round: one memory latency per round (8 elements of slack in wlist)
@@ -663,7 +672,7 @@ k_observe(FlBatch b, ObsLayout lay, float *__restrict__ out_attr, float *__restr
                     const bool last = (k == kend && seg_last) || idx >= FL_PRED_DEPTH;
                     const int d = (int)(sv[u] & 3u), dn = last ? d : (k < kend ? (int)(sv[u + 1] & 3u) : (int)((sg.y >> 19) & 3u));
                     const int t1 = last ? NPRED - 1 : min(idx ? idx * tpc : 0, NPRED - 1);
-                    emit((sv[u] & 0xFFFFu) >> 2, t0, t1, pack_entry(agent, t0, t1, d, dp, dn));
+                    emit((sv[u] & 0xFFFFu) >> 2, t0, t1, pack_entry(agent, t0, t1, d, dp, dn, extra));
                     if (last) return;
                     dp = d;
                 }
@@ -676,7 +685,7 @@ k_observe(FlBatch b, ObsLayout lay, float *__restrict__ out_attr, float *__restr
             for (int i = tid; i < N; i += NW) {
                 const uint32_t info = A.info[i];
                 const unsigned slot = (info >> 8) & 0xFFFFu, s0 = A.sid0[i];
-                if (s0 != 0xFFFFu) predict_path(wrec, whoff, whits, wlist, sdist + (size_t)slot * SS, s0, slot, (int)(info >> 24), i, count_emit);
+                if (s0 != 0xFFFFu) predict_path(wrec, whoff, whits, wlist, sdist + (size_t)slot * SS, s0, slot, (int)(info >> 24), i, entry_extra((int)(info >> 24), (info >> 5) & 1u), count_emit);
             }
         named_bar_sync(1, NW);
         OBS_TICK(2);
@@ -705,23 +714,16 @@ k_observe(FlBatch b, ObsLayout lay, float *__restrict__ out_attr, float *__restr
         if (tid == 0) s_misc[0] = n_ent;
         if (n_ent > lay.ent_cap) ent = b.entries + (size_t)e * b.ent_cap;   // does not fit in shared memory: global spill space
         // scatter pass.  ks[key] is advanced to the END of its bucket; bucket r is [ks[r-1], ks[r]) afterwards (ks[-1] = 0).
-        auto scatter_emit = [&](unsigned rail, int t0, int t1, uint32_t en) {
+        auto scatter_emit = [&](unsigned rail, int, int, uint32_t en) {
             const unsigned key = kcls ? (unsigned)kcls[rail] : rail;
             ent[atomicAdd(&ks[key], 1u)] = en;
-            const int sa = t0 >> 2, sb = t1 >> 2;             // time slots of 4 rows the entry overlaps
-            for (int wd = sa >> 5; wd <= sb >> 5; wd++) {
-                const int lo_b = max(sa - 32 * wd, 0), hi_b = min(sb - 32 * wd, 31);
-                const uint32_t m = (0xFFFFFFFFu >> (31 - hi_b)) & (0xFFFFFFFFu << lo_b);
-                const uint32_t twice = atomicOr(&bm[key * 4 + wd].x, m) & m;     // slots that already had an entry
-                if (twice) atomicOr(&bm[key * 4 + wd].y, twice);
-            }
         };
         if (pooled) { for (int j = tid; j < n_seg; j += NW) emit_segment(j, scatter_emit); }
         else
             for (int i = tid; i < N; i += NW) {
                 const uint32_t info = A.info[i];
                 const unsigned slot = (info >> 8) & 0xFFFFu, s0 = A.sid0[i];
-                if (s0 != 0xFFFFu) predict_path(wrec, whoff, whits, wlist, sdist + (size_t)slot * SS, s0, slot, (int)(info >> 24), i, scatter_emit);
+                if (s0 != 0xFFFFu) predict_path(wrec, whoff, whits, wlist, sdist + (size_t)slot * SS, s0, slot, (int)(info >> 24), i, entry_extra((int)(info >> 24), (info >> 5) & 1u), scatter_emit);
             }
         named_bar_sync(1, NW);
         OBS_TICK(4);
@@ -749,8 +751,51 @@ k_observe(FlBatch b, ObsLayout lay, float *__restrict__ out_attr, float *__restr
                 ent[y + 1] = v;
             }
         };
+        // The time-slot filter of a bucket (bm: bit s of .x / .y of word w = at least one / two entries of the key overlap rows
+        // 4 (32 w + s) .. + 3) is computed from the bucket once it is sorted — by the thread or warp that sorted it, without
+        // atomics (two shared-memory atomics per entry in the scatter pass cost more than the whole sort at Test_14).
+        // rows an entry covers: t0 .. 500 for the last element of a path, row 0 for element 0, else t0 .. t0 + tpc - 1
+        auto entry_slots = [&](uint32_t en, int &sa, int &sb) {
+            const int t0 = (int)((en >> 10) & 511u);
+            const int t1 = ((en >> 19) & 1u) ? NPRED - 1 : (t0 ? min(t0 + entry_tpc(en, A.info) - 1, NPRED - 1) : 0);
+            sa = t0 >> 2; sb = t1 >> 2;
+        };
+        auto slot_mask = [](int sa, int sb, int w) -> uint32_t {
+            const int lo_b = max(sa - 32 * w, 0), hi_b = min(sb - 32 * w, 31);
+            return lo_b <= hi_b ? ((0xFFFFFFFFu >> (31 - hi_b)) & (0xFFFFFFFFu << lo_b)) : 0u;
+        };
+        auto filter_serial = [&](int key, int s0, int s1) {                   // one thread, bucket [s0, s1)
+            uint32_t x0 = 0, x1 = 0, x2 = 0, x3 = 0, y0 = 0, y1 = 0, y2 = 0, y3 = 0;
+            for (int idx = s0; idx < s1; idx++) {
+                int sa, sb;
+                entry_slots(ent[idx], sa, sb);
+                const uint32_t m0 = slot_mask(sa, sb, 0), m1 = slot_mask(sa, sb, 1), m2 = slot_mask(sa, sb, 2), m3 = slot_mask(sa, sb, 3);
+                y0 |= x0 & m0; x0 |= m0; y1 |= x1 & m1; x1 |= m1; y2 |= x2 & m2; x2 |= m2; y3 |= x3 & m3; x3 |= m3;
+            }
+            bm[key * 4 + 0] = make_uint2(x0, y0); bm[key * 4 + 1] = make_uint2(x1, y1);
+            bm[key * 4 + 2] = make_uint2(x2, y2); bm[key * 4 + 3] = make_uint2(x3, y3);
+        };
+        // a warp, one entry per lane and round: lane w < 4 accumulates word w (seen / twice) over the rounds
+        struct FilterAcc { uint32_t seen, twice; };
+        auto filter_round = [&](FilterAcc &acc, bool valid, uint32_t en) {
+            int sa = 1, sb = 0;
+            if (valid) entry_slots(en, sa, sb);
+#pragma unroll
+            for (int w = 0; w < 4; w++) {
+                const uint32_t m = valid ? slot_mask(sa, sb, w) : 0u;
+                uint32_t incl = m;                                            // OR of the masks of lanes 0..lane
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) { const uint32_t q = __shfl_up_sync(0xFFFFFFFFu, incl, o); if (lane >= o) incl |= q; }
+                uint32_t excl = __shfl_up_sync(0xFFFFFFFFu, incl, 1);
+                if (lane == 0) excl = 0u;
+                const uint32_t all = __shfl_sync(0xFFFFFFFFu, incl, 31);
+                const uint32_t tw = __reduce_or_sync(0xFFFFFFFFu, m & excl);
+                if (lane == w) { acc.twice |= tw | (acc.seen & all); acc.seen |= all; }
+            }
+        };
+        auto filter_store = [&](int key, const FilterAcc &acc) { if (lane < 4) bm[key * 4 + lane] = make_uint2(acc.seen, acc.twice); };
         // up to 32 entries, one per lane (v0: the lane's entry, already loaded): bitonic network of register shuffles
-        auto warp_sort_regs = [&](int s0, int n, uint32_t v0) {
+        auto warp_sort_regs = [&](int key, int s0, int n, uint32_t v0) {
             uint32_t kv = lane < n ? ((entry_sort_key(v0) << 5) | (uint32_t)lane) : 0xFFFFFFFFu;   // key | source lane
 #pragma unroll
             for (int k2 = 2; k2 <= 32; k2 <<= 1)
@@ -762,12 +807,15 @@ k_observe(FlBatch b, ObsLayout lay, float *__restrict__ out_attr, float *__restr
                 }
             const uint32_t v = __shfl_sync(0xFFFFFFFFu, v0, kv & 31u);
             if (lane < n) ent[s0 + lane] = v;
+            FilterAcc acc{0u, 0u};
+            filter_round(acc, lane < n, v);
+            filter_store(key, acc);
         };
         // more than 32 entries: two stable radix passes (5 + 5 bits of the 10-bit key) through the scratch copy, the bucket
         // taken 256 entries at a time so that eight loads per lane are in flight (one memory round trip per 256 entries and
         // loop instead of one per 32)
-        auto warp_sort_radix = [&](int s0, int n) {
-            if (!scratch) { if (lane == 0) insertion_sort(s0, s0 + n); __syncwarp(); return; }
+        auto warp_sort_radix = [&](int key, int s0, int n) {
+            if (!scratch) { if (lane == 0) { insertion_sort(s0, s0 + n); filter_serial(key, s0, s0 + n); } __syncwarp(); return; }
             uint32_t *bufa = ent + s0, *bufb = scratch + s0;
 #pragma unroll 1
             for (int pass = 0; pass < 2; pass++) {
@@ -808,39 +856,55 @@ k_observe(FlBatch b, ObsLayout lay, float *__restrict__ out_attr, float *__restr
                     }
                 }
             }
+            FilterAcc acc{0u, 0u};                                              // the sorted bucket once more, for its filter
+            for (int x0 = 0; x0 < n; x0 += 256) {
+                uint32_t v[8];
+#pragma unroll
+                for (int u = 0; u < 8; u++) { const int x = x0 + u * 32 + lane; v[u] = x < n ? bufa[x] : 0u; }
+#pragma unroll
+                for (int u = 0; u < 8; u++) {
+                    if (x0 + u * 32 >= n) break;
+                    filter_round(acc, x0 + u * 32 + lane < n, v[u]);
+                }
+            }
+            filter_store(key, acc);
         };
         constexpr int NWARPS = NW / 32;
         if (in_smem) {
             for (int key = tid; key < R; key += NW) {
                 const int s0 = (int)ks[key - 1], s1 = (int)ks[key];
-                if (s1 - s0 <= SORT_SMALL) { insertion_sort(s0, s1); continue; }
+                if (s1 == s0) continue;                                         // empty: its filter words were zeroed at the start
+                if (s1 - s0 <= SORT_SMALL) { insertion_sort(s0, s1); filter_serial(key, s0, s1); continue; }
                 const int pos = atomicAdd(&s_misc[1], 1);
-                if (pos < bigq_cap) bigq[pos] = (uint32_t)key; else insertion_sort(s0, s1);
+                if (pos < bigq_cap) bigq[pos] = (uint32_t)key; else { insertion_sort(s0, s1); filter_serial(key, s0, s1); }
             }
             named_bar_sync(1, NW);
             OBS_TICK(9);
             const int n_big = min(ld_vol_i32(&s_misc[1]), bigq_cap);
             for (int q = warp; q < n_big; q += NWARPS) {
                 const int key = (int)bigq[q], s0 = (int)ks[key - 1], n = (int)ks[key] - s0;
-                if (n <= 32) warp_sort_regs(s0, n, lane < n ? ent[s0 + lane] : 0u);
-                else warp_sort_radix(s0, n);
+                if (n <= 32) warp_sort_regs(key, s0, n, lane < n ? ent[s0 + lane] : 0u);
+                else warp_sort_radix(key, s0, n);
             }
         } else {
             OBS_TICK(9);
-            // every bucket by a warp; the entries of the warp's next bucket are fetched while the current one is sorted
+            // every non-empty bucket by a warp; the entries of the warp's next two buckets are in flight while the current
+            // one is sorted (a bucket costs one L2 / DRAM round trip that nothing else hides at 32 warps per SM)
             auto fetch = [&](int key, int &s0, int &n, uint32_t &v) {
                 n = 0; v = 0u; s0 = 0;
-                if (key < R) { s0 = (int)ks[key - 1]; n = (int)ks[key] - s0; if (n >= 2 && n <= 32 && lane < n) v = ent[s0 + lane]; }
+                if (key < R) { s0 = (int)ks[key - 1]; n = (int)ks[key] - s0; if (n >= 1 && n <= 32 && lane < n) v = ent[s0 + lane]; }
             };
-            int s0c, nc;
-            uint32_t vc;
-            fetch(warp, s0c, nc, vc);
+            int s0a, na, s0b, nb;
+            uint32_t va, vb;
+            fetch(warp, s0a, na, va);
+            fetch(warp + NWARPS, s0b, nb, vb);
             for (int key = warp; key < R; key += NWARPS) {
                 int s0x, nx;
                 uint32_t vx;
-                fetch(key + NWARPS, s0x, nx, vx);
-                if (nc >= 2) { if (nc <= 32) warp_sort_regs(s0c, nc, vc); else warp_sort_radix(s0c, nc); }
-                s0c = s0x; nc = nx; vc = vx;
+                fetch(key + 2 * NWARPS, s0x, nx, vx);
+                if (na >= 1) { if (na <= 32) warp_sort_regs(key, s0a, na, va); else warp_sort_radix(key, s0a, na); }
+                s0a = s0b; na = nb; va = vb;
+                s0b = s0x; nb = nx; vb = vx;
             }
         }
         named_bar_sync(1, NW);
@@ -1073,11 +1137,10 @@ k_observe(FlBatch b, ObsLayout lay, float *__restrict__ out_attr, float *__restr
                     const int nb = (int)((q.y >> 16) & 15u);
                     auto candidate = [&](uint32_t en, int t0) {
                         const int ag = (int)(en & 1023);
-                        const uint32_t oinfo = A.info[ag];
-                        const int t1 = ((en >> 19) & 1u) ? NPRED - 1 : (t0 ? t0 + (int)(oinfo >> 24) - 1 : 0);
+                        const int t1 = ((en >> 19) & 1u) ? NPRED - 1 : (t0 ? t0 + entry_tpc(en, A.info) - 1 : 0);
                         if (t1 < pre) return;
                         const int dh = (int)((en >> 20) & 3), dpv = (int)((en >> 22) & 3), dn = (int)((en >> 24) & 3);
-                        const bool done = (oinfo >> 5) & 1;
+                        const bool done = (en >> 29) & 1u;
                         const bool in_cur = t0 <= pt && pt <= t1, in_pre = t0 <= pre && pre <= t1,
                                    in_post = t0 <= post && post <= t1;
                         const int pdir = pt < t0 ? dpv : (pt > t1 ? dn : dh);  // always the direction at row pt
@@ -1091,14 +1154,17 @@ k_observe(FlBatch b, ObsLayout lay, float *__restrict__ out_attr, float *__restr
                         const uint32_t en = ent_at(idx);
                         if (!((en >> 19) & 1u)) break;
                         const int t0 = (int)((en >> 10) & 511);
-                        if (t0 <= post) candidate(en, t0);
+                        if (t0 > post) break;                                    // ordered by t0: none of the rest has started yet
+                        candidate(en, t0);
                     }
-                    // regular entries are ordered by t0: only those with pre - tpc_max < t0 <= post can matter
+                    // regular entries follow, ordered by t0: only those with pre - tpc_max < t0 <= post can matter.  The search runs
+                    // on the bucket's sort key (long-lived entries first), so long-lived entries still ahead of idx are skipped too
                     const int t_lo = pre - tpc_max + 1;
+                    const uint32_t key_lo = (uint32_t)(512 + max(t_lo, 0));
                     uint32_t lo = idx, hi = s1;
                     while (lo < hi) {
                         const uint32_t mid = (lo + hi) >> 1;
-                        if ((int)((ent_at(mid) >> 10) & 511) < t_lo) lo = mid + 1; else hi = mid;
+                        if (entry_sort_key(ent_at(mid)) < key_lo) lo = mid + 1; else hi = mid;
                     }
                     for (idx = lo; idx < s1; idx++) {
                         const uint32_t en = ent_at(idx);

@@ -107,8 +107,8 @@ DEVI int target_slot_at(const FlBatch &b, int e, const uint32_t *tbits, int cell
 }
 
 template <bool FILL, int NT>
-__global__ void __launch_bounds__(NT) k_walks(FlBatch b) {
-    const int e = blockIdx.x, H = (int)b.H, W = (int)b.W, HW = H * W, tid = threadIdx.x;
+__global__ void __launch_bounds__(NT) k_walks(FlBatch b, const int32_t *__restrict__ env_ids) {
+    const int e = env_ids ? env_ids[blockIdx.x] : (int)blockIdx.x, H = (int)b.H, W = (int)b.W, HW = H * W, tid = threadIdx.x;
     __shared__ uint32_t s_part[NT];
     extern __shared__ uint32_t s_tbits[];            // (HW + 31) / 32 words: cells holding the target of a slot
     const uint16_t *__restrict__ g = b.grid + (size_t)e * b.grid_stride;

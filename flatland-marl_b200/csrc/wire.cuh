@@ -21,6 +21,7 @@
 #include "common.cuh"
 
 #include <cstring>
+#include <vector>
 
 namespace {
 
@@ -172,23 +173,51 @@ inline void wire_widen(int32_t *q, const int8_t *src, int n) {   // int8 -> int3
     for (; k < n; k++) q[k] = src[k];
 }
 
-// The same with AVX2: flags through a byte -> 8 floats table, int8 -> int32 eight at a time, and the forest rows (61 % of
-// the bytes; every 48-byte node slot is 16-byte aligned) with non-temporal stores when `nt` is set, so that 125 MB per step
-// do not first pull their cache lines in.
+// dst <- src with non-temporal 16-byte stores where dst is aligned (head and tail: ordinary stores); both 4-byte aligned
 __attribute__((target("avx2")))
-inline uint64_t expand_env_avx2(const uint32_t *wire, int el, long long e_global, int N, const WireDst &d, bool nt) {
+inline void wire_stream_copy(void *dst, const void *src, size_t bytes) {
+    unsigned char *d = static_cast<unsigned char *>(dst);
+    const unsigned char *s = static_cast<const unsigned char *>(src);
+    size_t head = (16 - (reinterpret_cast<uintptr_t>(d) & 15)) & 15;
+    if (head > bytes) head = bytes;
+    std::memcpy(d, s, head);
+    d += head; s += head; bytes -= head;
+    for (; bytes >= 16; bytes -= 16, d += 16, s += 16)
+        _mm_stream_si128(reinterpret_cast<__m128i *>(d), _mm_loadu_si128(reinterpret_cast<const __m128i *>(s)));
+    std::memcpy(d, s, bytes);
+}
+
+// The same with AVX2: flags through a byte -> 8 floats table, int8 -> int32 eight at a time, and non-temporal stores so that
+// 125 MB per step do not first pull their cache lines in: nt_f for the forest rows (61 % of the bytes; every 48-byte node
+// slot is 16-byte aligned), nt for the other tensors as well (staged per environment, see below).
+__attribute__((target("avx2")))
+inline uint64_t expand_env_avx2(const uint32_t *wire, int el, long long e_global, int N, const WireDst &d, bool nt_f, bool nt) {
     const WireBitLut &lut = wire_bit_lut();
     const uint32_t tw = wire[el];
     const uint32_t *p = wire + (tw & 0x7FFFFFFFu);
     const uint32_t *const p0 = p;
     if (d.dones) d.dones[(size_t)e_global * (N + 1) + N] = (uint8_t)(tw >> 31);
     const __m128 minus1 = _mm_set1_ps(-1.0f);
-    nt = nt && d.forest && (reinterpret_cast<uintptr_t>(d.forest) & 15) == 0;
+    const bool nt_forest = nt_f && d.forest && (reinterpret_cast<uintptr_t>(d.forest) & 15) == 0;
+    // with non-temporal stores the small tensors of the environment (attributes, adjacency, orders: rows that are not multiples
+    // of a cache line) are assembled in a thread-local block first and leave as ONE sequential stream per tensor, so that the
+    // write-combining buffers always see whole lines; the forest rows are 16-byte aligned and stream directly
+    static thread_local std::vector<int32_t> scratch;
+    float *s_attr = nullptr;
+    int32_t *s_adj = nullptr, *s_no = nullptr, *s_eo = nullptr;
+    if (nt) {
+        const size_t need = (size_t)N * (FL_ATTR_F + 90 + FL_MAX_NODES + FL_MAX_NODES - 1) + 64;
+        if (scratch.size() < need) scratch.resize(need);
+        s_attr = reinterpret_cast<float *>(scratch.data());
+        s_adj = scratch.data() + (size_t)N * FL_ATTR_F + 8;
+        s_no = s_adj + (size_t)N * 90 + 8;
+        s_eo = s_no + (size_t)N * FL_MAX_NODES + 8;
+    }
     for (int i = 0; i < N; i++) {
         const size_t ea = (size_t)e_global * N + i;
         const uint32_t mask = p[0];
         if (d.attr) {
-            float *a = d.attr + ea * FL_ATTR_F;
+            float *a = nt ? s_attr + (size_t)i * FL_ATTR_F : d.attr + ea * FL_ATTR_F;
             const uint8_t *bits = reinterpret_cast<const uint8_t *>(p + 1);          // bytes 0..8: entries 0..71 (70, 71 are zero bits)
             for (int k = 0; k < 9; k++) _mm256_storeu_ps(a + 8 * k, _mm256_load_ps(lut.f[bits[k]]));
             std::memcpy(a + 70, p + 4, 13 * sizeof(float));
@@ -198,22 +227,36 @@ inline uint64_t expand_env_avx2(const uint32_t *wire, int el, long long e_global
         if (d.rewards) d.rewards[ea] = (int32_t)p[18];
         if (d.dones) d.dones[(size_t)e_global * (N + 1) + i] = (uint8_t)p[19];
         const int8_t *sb = reinterpret_cast<const int8_t *>(p + 20);
-        if (d.adjacency) wire_widen(d.adjacency + ea * ((FL_MAX_NODES - 1) * 3), sb, 90);
-        if (d.node_order) wire_widen(d.node_order + ea * FL_MAX_NODES, sb + 90, FL_MAX_NODES);
-        if (d.edge_order) wire_widen(d.edge_order + ea * (FL_MAX_NODES - 1), sb + 121, FL_MAX_NODES - 1);
+        if (nt) {
+            wire_widen(s_adj + (size_t)i * 90, sb, 90);
+            wire_widen(s_no + (size_t)i * FL_MAX_NODES, sb + 90, FL_MAX_NODES);
+            wire_widen(s_eo + (size_t)i * (FL_MAX_NODES - 1), sb + 121, FL_MAX_NODES - 1);
+        } else {
+            if (d.adjacency) wire_widen(d.adjacency + ea * ((FL_MAX_NODES - 1) * 3), sb, 90);
+            if (d.node_order) wire_widen(d.node_order + ea * FL_MAX_NODES, sb + 90, FL_MAX_NODES);
+            if (d.edge_order) wire_widen(d.edge_order + ea * (FL_MAX_NODES - 1), sb + 121, FL_MAX_NODES - 1);
+        }
         const float *nodes = reinterpret_cast<const float *>(p + WIRE_FIXED_WORDS);
         if (d.forest) {
             float *f = d.forest + ea * (FL_MAX_NODES * FL_NODE_F);
             for (int n = 0; n < FL_MAX_NODES; n++, f += FL_NODE_F) {
                 __m128 x = minus1, y = minus1, z = minus1;
                 if ((mask >> n) & 1u) { x = _mm_loadu_ps(nodes); y = _mm_loadu_ps(nodes + 4); z = _mm_loadu_ps(nodes + 8); nodes += FL_NODE_F; }
-                if (nt) { _mm_stream_ps(f, x); _mm_stream_ps(f + 4, y); _mm_stream_ps(f + 8, z); }
+                if (nt_forest) { _mm_stream_ps(f, x); _mm_stream_ps(f + 4, y); _mm_stream_ps(f + 8, z); }
                 else { _mm_storeu_ps(f, x); _mm_storeu_ps(f + 4, y); _mm_storeu_ps(f + 8, z); }
             }
         }
         p += wire_record_words(mask);
     }
-    if (nt) _mm_sfence();
+    if (nt_forest && !nt) _mm_sfence();
+    if (nt) {
+        const size_t a0 = (size_t)e_global * N;
+        if (d.attr) wire_stream_copy(d.attr + a0 * FL_ATTR_F, s_attr, (size_t)N * FL_ATTR_F * 4);
+        if (d.adjacency) wire_stream_copy(d.adjacency + a0 * 90, s_adj, (size_t)N * 90 * 4);
+        if (d.node_order) wire_stream_copy(d.node_order + a0 * FL_MAX_NODES, s_no, (size_t)N * FL_MAX_NODES * 4);
+        if (d.edge_order) wire_stream_copy(d.edge_order + a0 * (FL_MAX_NODES - 1), s_eo, (size_t)N * (FL_MAX_NODES - 1) * 4);
+        _mm_sfence();
+    }
     return (uint64_t)(p - p0);
 }
 #define FL_WIRE_HAVE_AVX2 1
@@ -221,7 +264,7 @@ inline uint64_t expand_env_avx2(const uint32_t *wire, int el, long long e_global
 
 inline uint64_t expand_env(const uint32_t *wire, int el, long long e_global, int N, const WireDst &d, int mode) {
 #ifdef FL_WIRE_HAVE_AVX2
-    if (mode > 0 && __builtin_cpu_supports("avx2")) return expand_env_avx2(wire, el, e_global, N, d, mode > 1);
+    if (mode > 0 && __builtin_cpu_supports("avx2")) return expand_env_avx2(wire, el, e_global, N, d, mode > 1, mode > 2);
 #endif
     return expand_env_scalar(wire, el, e_global, N, d);
 }

@@ -89,26 +89,45 @@ class GeneratorPool(WorldSource):
 
 class ResetPipeline:
     """Drives a `BatchedRailEnv` (built with auto_reset=True and some `reserve`) so that finished environments get
-    fresh worlds from `source` when one is ready, and are reset in place otherwise."""
+    fresh worlds from `source` when one is ready, and are reset in place otherwise.
+
+    No host synchronisation on the stepping path: the per-environment `dones["__all__"]` flags of a step travel to pinned
+    host memory with an asynchronous copy and are looked at one step later, when they have long arrived.  An environment
+    whose episode ended in step t restarts in place in step t+1 (FL_FLAG_AUTO_RESET) and — if the source has a world ready
+    — is given the new world right after that same call, so the observation step t+1 returns for it is already the new
+    world's first observation: the consumer sees `done` at t and a fresh episode at t+1, never the replayed world.
+    `replace_worlds` itself synchronises once per call (table-size check), i.e. once per batch of finished episodes."""
 
     def __init__(self, batch, source):
+        import torch
         self.batch, self.source = batch, source
         self.replaced = 0
+        self._flags = [torch.zeros(batch.E, dtype=torch.uint8).pin_memory() for _ in range(2)]
+        self._events = [torch.cuda.Event() for _ in range(2)]
+        self._pending = [False, False]
+        self._t = 0
 
     def reset(self):
+        self._pending = [False, False]
         return self.batch.reset()
 
     def step(self, actions):
-        """One lock-step step; returns (obs, rewards, dones) like BatchedRailEnv.step.  Environments whose episode ended
-        in this step (dones[:, N]) are replaced before the next step when the source has worlds ready; their observation
-        in the returned dict is then already the new world's first observation."""
+        """One lock-step step; returns (obs, rewards, dones) like BatchedRailEnv.step."""
         b = self.batch
+        cur, prev = self._t & 1, (self._t & 1) ^ 1
         obs, rewards, dones = b.step(actions)
-        finished = b.t["done_all"].nonzero().flatten().tolist()      # E bytes to the host: the one sync of the pipeline
-        if finished:
-            worlds = self.source.take(len(finished))
-            if worlds:
-                b.replace_worlds(finished[: len(worlds)], worlds)
-                self.replaced += len(worlds)
-                obs = b.observe()
+        self._flags[cur].copy_(dones[:, b.N], non_blocking=True)      # this step's "__all__" flags, read next step
+        self._events[cur].record()
+        self._pending[cur] = True
+        if self._pending[prev]:
+            self._events[prev].synchronize()                           # recorded a whole step ago
+            self._pending[prev] = False
+            finished = self._flags[prev].nonzero().flatten().tolist()
+            if finished:
+                worlds = self.source.take(len(finished))
+                if worlds:
+                    b.replace_worlds(finished[: len(worlds)], worlds)
+                    self.replaced += len(worlds)
+                    obs = b.observe()
+        self._t += 1
         return obs, rewards, dones

@@ -166,6 +166,12 @@ int fl_distance_map(const FlBatch *b, void *stream);
  * re-walks the rail cell by cell in every _explore_branch call (treeobs.cpp:258-610). */
 int fl_walk_tables(const FlBatch *b, int fill, void *stream);
 
+/* The same two for a list of environments of the batch only (d_env_ids: device int32[n_ids], distinct indices), one launch
+ * each: what RailEnv.reset(regenerate_rail=True, ...) costs for SOME environments of a running batch (rail_env.py:260-357;
+ * distance_map.py:57-160 is 16.9 s of Python per reset at Test_14).  Used by the reset pipeline (BatchedRailEnv.replace_worlds). */
+int fl_distance_map_ids(const FlBatch *b, const int32_t *d_env_ids, int64_t n_ids, void *stream);
+int fl_walk_tables_ids(const FlBatch *b, int fill, const int32_t *d_env_ids, int64_t n_ids, void *stream);
+
 /* Replaces the tail of RailEnv.reset (flatland/envs/rail_env.py:335-347: reset_agents, elapsed=0,
  * dones cleared) and TreeObsForRailEnv::reset (flatland_cutils/src/treeobs.cpp:22-28: a fresh
  * DeadlockChecker).  d_env_mask: [E] bytes, non-zero = reset this env; NULL = all. */

@@ -95,21 +95,77 @@ def test_replace_worlds_equals_fresh_batch(golden):
 
 @pytest.mark.gpu
 def test_pipeline_replaces_finished_environments():
+    """Every slot of the pipeline against the oracle of the world it currently holds: an episode that ends in step t
+    is followed in step t+1 by the first observation of the NEXT world of the source (no host synchronisation on the
+    stepping path: the done flags are read one step late), and that world then runs bit-exactly."""
     import torch
     import bench
     import flatland_marl_b200 as fb
-    worlds = bench.load_worlds("Test_00", 12)
+    from oracle import oracle as orc
+    from test_gpu_parity import compare_obs, compare_state
+    worlds = bench.load_worlds("Test_00", 16)
     for w in worlds:
         w["T"] = 40                                  # short episodes so that resets happen within the test
     batch = fb.BatchedRailEnv(worlds[:6], auto_reset=True, reserve=1.0, min_slots=8)
-    pipe = fb.ResetPipeline(batch, fb.PackSource(worlds[6:]))
+    src = fb.PackSource(worlds[6:])
+    pipe = fb.ResetPipeline(batch, src)
     obs = pipe.reset()
+    envs = [orc.OracleEnv(w) for w in worlds[:6]]
+    held = list(worlds[:6])
+    rows = [0] * 6                                   # schedule row of each slot's current world
+    for e in envs:
+        e.reset()
+    nxt = 0                                          # next world of the source (PackSource hands them out in order)
     rng = np.random.RandomState(2)
-    episodes = 0
+    episodes, pending = 0, []
     for t in range(130):
-        a = torch.from_numpy(rng.randint(0, 5, (6, batch.N)).astype(np.uint8)).to(batch.device)
-        obs, rew, don = pipe.step(a)
-        episodes += int(don[:, batch.N].sum().item())
+        act = rng.randint(0, 5, (6, batch.N)).astype(np.uint8)
+        obs, rew, don = pipe.step(torch.from_numpy(act).to(batch.device))
+        don = don.cpu().numpy()
+        for e in pending:                            # finished last step: this call handed the slot the next world
+            held[e] = worlds[6 + nxt % 10]
+            nxt += 1
+            envs[e] = orc.OracleEnv(held[e])
+            envs[e].reset()
+            rows[e] = 0
+            compare_obs(batch, e, envs[e].obs(), "slot %d step %d: first observation of the new world" % (e, t))
+            compare_state(batch, e, envs[e].state(), "slot %d step %d new world" % (e, t))
+        fresh = set(pending)
+        pending = []
+        for e in range(6):
+            if e in fresh:
+                continue
+            orew, odon = envs[e].step(act[e], held[e]["sched"][rows[e]])
+            rows[e] += 1
+            assert (rew[e].cpu().numpy() == orew).all() and (don[e] == odon).all(), (t, e)
+            if t % 7 == 0 or odon[-1]:
+                compare_obs(batch, e, envs[e].obs(), "slot %d step %d" % (e, t))
+            if odon[-1]:
+                episodes += 1
+                pending.append(e)
         assert int(batch.t["status"].max().item()) & 5 == 0      # no step-after-done, no bad cell
-    assert episodes >= 12 and pipe.replaced == episodes
+    assert episodes >= 12 and pipe.replaced == episodes - len(pending)
     assert np.isfinite(obs["agent_attr"].cpu().numpy()).all()
+
+
+@pytest.mark.gpu
+def test_replace_worlds_refuses_oversized_world_and_leaves_the_batch_untouched():
+    import torch
+    import bench
+    import flatland_marl_b200 as fb
+    small = bench.load_worlds("Test_00", 4)
+    batch = fb.BatchedRailEnv(small[:3], min_slots=8)              # no reserve: tables sized for these three worlds
+    batch.reset()
+    a = torch.full((3, batch.N), 2, dtype=torch.uint8, device=batch.device)
+    for _ in range(5):
+        batch.step(a)
+    before = {k: v.clone() for k, v in batch.t.items()}
+    big = dict(small[3])
+    g = np.array(big["grid"], np.uint16).copy()
+    g[g == 0] = 0x8421                                             # every empty cell becomes a crossing: far more rail states
+    big["grid"] = g
+    with pytest.raises(fb.FlatlandB200Error):
+        batch.replace_worlds([1], [big])
+    for k, v in before.items():
+        assert torch.equal(batch.t[k], v), k + " changed although the replacement was refused"
+    batch.step(a)                                                  # and the batch still steps
