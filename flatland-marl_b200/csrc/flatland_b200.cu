@@ -135,9 +135,12 @@ ObsLayout make_obs_layout(const FlBatch *b, int nt, int mode, int parts, int *ct
     L.dl = mode == OBS_TREES ? 0 : take(26 * N + 8);
     L.ci = take((long long)Rmax * 4);
     L.ks = take((long long)(Rmax + 4) * 4);
-    // time-slot filter of the prediction index: one / two entries per slot.  The tree kernel may read it from the workspace
-    // instead ("bmglobal" knob; default: when it is larger than 48 KB, i.e. would cost the tree kernel a resident CTA)
-    const bool bm_global = mode == OBS_TREES && (knob(KNOB_BMGLOBAL) >= 0 ? knob(KNOB_BMGLOBAL) != 0 : (long long)Rmax * 32 > 48 * 1024);
+    // time-slot filter of the prediction index: one / two entries per slot; it may stay in the workspace (global memory)
+    // ("bmglobal" knob; in every mode it stays in the workspace when the mandatory regions would not fit beside it: it is
+    // written with plain stores once its bucket is sorted, so it can live anywhere)
+    const long long sq_bytes = (long long)(mode == OBS_TREES ? (nt / 32) * 64 : (10 * N > (nt / 32) * 64 ? 10 * N : (nt / 32) * 64)) * 8;
+    const bool bm_fits = (long long)off + (long long)Rmax * 32 + sq_bytes + (b->H > b->W ? Rmax * 2 : 0) + 4096 <= SMEM_MAX;
+    const bool bm_global = b->obs_ws && b->ws_stride > 0 && (knob(KNOB_BMGLOBAL) >= 0 ? knob(KNOB_BMGLOBAL) != 0 : !bm_fits);
     L.bm = bm_global ? -1 : take((long long)Rmax * 32);
     L.seg_cap = mode == OBS_TREES ? 0 : 10 * N;                 // path segments of phase 3 share the room of the phase-4 queues
     if (L.seg_cap < (nt / 32) * 64) L.seg_cap = (nt / 32) * 64;

@@ -380,12 +380,12 @@ k_observe(FlBatch b, ObsLayout lay, float *__restrict__ out_attr, float *__restr
     const uint16_t *kcls = lay.kcls >= 0 ? reinterpret_cast<const uint16_t *>(smraw + lay.kcls) : nullptr;   // only when H > W
     uint32_t *ci = reinterpret_cast<uint32_t *>(smraw + lay.ci);             // [R] occupancy word per rail cell
     uint32_t *ks = reinterpret_cast<uint32_t *>(smraw + lay.ks) + 1;         // ks[-1..R]: bucket r = [ks[r-1], ks[r])
-    uint2 *bm = reinterpret_cast<uint2 *>(smraw + lay.bm);                   // [R][4] bit s of .x / .y: at least one / two prediction entries of the key overlap rows 4s..4s+3
-    // the tree kernel of a split launch can leave the filter in the workspace (L2) when its 32 bytes per rail cell would cost
-    // a resident CTA (lay.bm < 0): it is read twice per visited cell, with independent loads
-    const uint2 *bm_r = (MODE == OBS_TREES && lay.bm < 0)
-                            ? reinterpret_cast<const uint2 *>(b.obs_ws + (size_t)e * b.ws_stride + lay.ws_idx / 4 + 2 * (SS / 4) + 4)
-                            : bm;
+    // [R][4] bit s of .x / .y: at least one / two prediction entries of the key overlap rows 4s..4s+3.  In shared memory, or —
+    // when its 32 bytes per rail cell do not fit beside the mandatory regions (lay.bm < 0: large worlds) — in its place in
+    // the workspace: it is written with plain stores and read twice per visited cell with independent loads
+    uint2 *bm = lay.bm >= 0 ? reinterpret_cast<uint2 *>(smraw + lay.bm)
+                            : reinterpret_cast<uint2 *>(b.obs_ws + (size_t)e * b.ws_stride + lay.ws_idx / 4 + 2 * (SS / 4) + 4);
+    const uint2 *bm_r = bm;
     uint2 *sq = reinterpret_cast<uint2 *>(smraw + lay.sq) + warp * 64;       // this warp's queue of cells that need the full conflict check
     uint32_t *s_part = reinterpret_cast<uint32_t *>(smraw + lay.part);
     uint64_t *bar = reinterpret_cast<uint64_t *>(smraw + lay.bar);
@@ -647,40 +647,64 @@ k_observe(FlBatch b, ObsLayout lay, float *__restrict__ out_attr, float *__restr
         const int n_seg = s_misc[0];
         if (dbg && tid == 0) dbg[11] = n_seg;
         const bool pooled = n_seg <= lay.seg_cap + seg_gcap;  // else: every lane walks its agent's path itself (predict_path), twice
-        // Emit(rail cell, t0, t1, entry) for every occupied element of pool segment j
-        auto emit_segment = [&](int j, auto emit) {
-            const uint2 sg = j < lay.seg_cap ? pool[j] : pool_g[j - lay.seg_cap];
-            const unsigned sid = sg.x & 0xFFFFu;
-            const int kend = (int)((sg.x >> 16) & 0x3FFFu), agent = (int)(sg.y & 1023u), kk = (int)((sg.y >> 10) & 511u);
-            const bool seg_last = (sg.y >> 21) & 1u;
-            const uint32_t ainf = A.info[agent];
-            const int tpc = (int)(ainf >> 24);
-            const uint32_t extra = entry_extra(tpc, (ainf >> 5) & 1u);
-            int dp = (int)(sg.x >> 30);
-            const uint32_t wx = wrec[sid].x;
-            for (int k0 = 0; k0 <= kend; k0 += 4) {  // four states per round: one memory latency per round (8 elements of slack in wlist)
-                unsigned sv[5];
-#pragma unroll
-                for (int u = 0; u < 5; u++) sv[u] = wlist[wx + k0 + u];
-#pragma unroll
-                for (int u = 0; u < 4; u++) {
-                    const int k = k0 + u;
-                    if (k > kend) return;
-                    const int idx = kk + k;
-                    const int t0 = idx ? 1 + (idx - 1) * tpc : 0;
-                    if (t0 >= NPRED) return;
-                    const bool last = (k == kend && seg_last) || idx >= FL_PRED_DEPTH;
-                    const int d = (int)(sv[u] & 3u), dn = last ? d : (k < kend ? (int)(sv[u + 1] & 3u) : (int)((sg.y >> 19) & 3u));
-                    const int t1 = last ? NPRED - 1 : min(idx ? idx * tpc : 0, NPRED - 1);
-                    emit((sv[u] & 0xFFFFu) >> 2, t0, t1, pack_entry(agent, t0, t1, d, dp, dn, extra));
-                    if (last) return;
-                    dp = d;
+        // Emit(rail cell, t0, t1, entry) for every occupied element of every pool segment, a warp at a time: 32 segments per batch, their occupied elements as one flat list, one
+        // element per lane and round — every load of a round is independent, so a batch costs about three memory round trips
+        // (segment record -> walk offset -> states) instead of three per segment and thread.  dirs: the entry's directions are
+        // needed (scatter pass) or only its rail cell (counting pass).
+        auto emit_pool_flat = [&](bool dirs, auto emit) {
+            constexpr int NWP = NW / 32;
+            for (int j0 = warp * 32; j0 < n_seg; j0 += NWP * 32) {
+                const int j = j0 + lane;
+                const bool has = j < n_seg;
+                uint2 sg = make_uint2(0u, 0u);
+                if (has) sg = j < lay.seg_cap ? pool[j] : pool_g[j - lay.seg_cap];
+                const unsigned sid = sg.x & 0xFFFFu;
+                const int kend = (int)((sg.x >> 16) & 0x3FFFu), agent = (int)(sg.y & 1023u), kk = (int)((sg.y >> 10) & 511u);
+                const uint32_t ainf = has ? A.info[agent] : (1u << 24);
+                const int tpc = max((int)(ainf >> 24), 1);
+                const uint32_t wx = has ? wrec[sid].x : 0u;
+                // elements kk .. last_idx of the path are emitted: up to the end of the segment, path element 500, and row 500
+                const int last_idx = min(min(kk + kend, FL_PRED_DEPTH), (NPRED - 2) / tpc + 1);
+                const unsigned cnt = has ? (unsigned)max(last_idx - kk + 1, 0) : 0u;
+                unsigned total;
+                const unsigned off = warp_excl_scan(cnt, lane, total);
+                const unsigned nonempty = __ballot_sync(0xFFFFFFFFu, cnt > 0);
+                // what an element needs of its segment, fetched from the owner lane: a = walk offset, b = first step's offset in the
+                // flat list, c = kk | kend << 9 | tpc << 23, d = the segment record's second word (agent, next direction, last),
+                // e = direction before the segment
+                const uint32_t rc_ = (uint32_t)kk | ((uint32_t)kend << 9) | ((uint32_t)min(tpc, 255) << 23);
+                for (unsigned base = 0; base < total; base += 32) {
+                    const unsigned f = base + lane;
+                    const int cnt0 = __popc(__ballot_sync(0xFFFFFFFFu, cnt > 0 && off <= base));
+                    const unsigned starts = __reduce_or_sync(0xFFFFFFFFu, (cnt > 0 && off > base && off < base + 32) ? 1u << (off - base) : 0u);
+                    const int rank = cnt0 - 1 + __popc(starts & (0xFFFFFFFFu >> (31 - lane)));
+                    const int owner = f < total ? nth_set_bit(nonempty, rank) : 0;
+                    const uint32_t o_wx = __shfl_sync(0xFFFFFFFFu, wx, owner), o_off = __shfl_sync(0xFFFFFFFFu, off, owner);
+                    const uint32_t o_c = __shfl_sync(0xFFFFFFFFu, rc_, owner), o_y = __shfl_sync(0xFFFFFFFFu, sg.y, owner);
+                    const uint32_t o_dp = __shfl_sync(0xFFFFFFFFu, sg.x >> 30, owner);
+                    if (f < total) {
+                        const int k = (int)(f - o_off), o_kk = (int)(o_c & 511u), o_kend = (int)((o_c >> 9) & 0x3FFFu), o_tpc = (int)(o_c >> 23);
+                        const int idx = o_kk + k;
+                        const unsigned sv = wlist[o_wx + k];
+                        unsigned sn = 0, sp = 0;
+                        if (dirs) {
+                            if (k < o_kend) sn = wlist[o_wx + k + 1];
+                            if (k > 0) sp = wlist[o_wx + k - 1];
+                        }
+                        const int t0 = idx ? 1 + (idx - 1) * o_tpc : 0;
+                        const bool last = (k == o_kend && ((o_y >> 21) & 1u)) || idx >= FL_PRED_DEPTH;
+                        const int d = (int)(sv & 3u), dn = last ? d : (k < o_kend ? (int)(sn & 3u) : (int)((o_y >> 19) & 3u));
+                        const int dp = k > 0 ? (int)(sp & 3u) : (int)o_dp;
+                        const int t1 = last ? NPRED - 1 : min(idx ? idx * o_tpc : 0, NPRED - 1);
+                        const int ag = (int)(o_y & 1023u);
+                        emit((sv & 0xFFFFu) >> 2, t0, t1, dirs ? pack_entry(ag, t0, t1, d, dp, dn, entry_extra((int)(A.info[ag] >> 24), (A.info[ag] >> 5) & 1u)) : 0u);
+                    }
                 }
             }
         };
         auto count_emit = [&](unsigned rail, int, int, uint32_t) { atomicAdd(&ks[kcls ? (unsigned)kcls[rail] : rail], 1u); };
         // counting pass: entries per rail cell (or key class)
-        if (pooled) { for (int j = tid; j < n_seg; j += NW) emit_segment(j, count_emit); }
+        if (pooled) emit_pool_flat(false, count_emit);
         else
             for (int i = tid; i < N; i += NW) {
                 const uint32_t info = A.info[i];
@@ -718,7 +742,7 @@ k_observe(FlBatch b, ObsLayout lay, float *__restrict__ out_attr, float *__restr
             const unsigned key = kcls ? (unsigned)kcls[rail] : rail;
             ent[atomicAdd(&ks[key], 1u)] = en;
         };
-        if (pooled) { for (int j = tid; j < n_seg; j += NW) emit_segment(j, scatter_emit); }
+        if (pooled) emit_pool_flat(true, scatter_emit);
         else
             for (int i = tid; i < N; i += NW) {
                 const uint32_t info = A.info[i];
@@ -766,11 +790,18 @@ k_observe(FlBatch b, ObsLayout lay, float *__restrict__ out_attr, float *__restr
         };
         auto filter_serial = [&](int key, int s0, int s1) {                   // one thread, bucket [s0, s1)
             uint32_t x0 = 0, x1 = 0, x2 = 0, x3 = 0, y0 = 0, y1 = 0, y2 = 0, y3 = 0;
-            for (int idx = s0; idx < s1; idx++) {
-                int sa, sb;
-                entry_slots(ent[idx], sa, sb);
-                const uint32_t m0 = slot_mask(sa, sb, 0), m1 = slot_mask(sa, sb, 1), m2 = slot_mask(sa, sb, 2), m3 = slot_mask(sa, sb, 3);
-                y0 |= x0 & m0; x0 |= m0; y1 |= x1 & m1; x1 |= m1; y2 |= x2 & m2; x2 |= m2; y3 |= x3 & m3; x3 |= m3;
+            for (int i0 = s0; i0 < s1; i0 += 4) {                              // four loads in flight (the entries may live in global memory)
+                uint32_t en[4];
+#pragma unroll
+                for (int u = 0; u < 4; u++) en[u] = i0 + u < s1 ? ent[i0 + u] : 0u;
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    if (i0 + u >= s1) break;
+                    int sa, sb;
+                    entry_slots(en[u], sa, sb);
+                    const uint32_t m0 = slot_mask(sa, sb, 0), m1 = slot_mask(sa, sb, 1), m2 = slot_mask(sa, sb, 2), m3 = slot_mask(sa, sb, 3);
+                    y0 |= x0 & m0; x0 |= m0; y1 |= x1 & m1; x1 |= m1; y2 |= x2 & m2; x2 |= m2; y3 |= x3 & m3; x3 |= m3;
+                }
             }
             bm[key * 4 + 0] = make_uint2(x0, y0); bm[key * 4 + 1] = make_uint2(x1, y1);
             bm[key * 4 + 2] = make_uint2(x2, y2); bm[key * 4 + 3] = make_uint2(x3, y3);
@@ -794,6 +825,9 @@ k_observe(FlBatch b, ObsLayout lay, float *__restrict__ out_attr, float *__restr
             }
         };
         auto filter_store = [&](int key, const FilterAcc &acc) { if (lane < 4) bm[key * 4 + lane] = make_uint2(acc.seen, acc.twice); };
+        // A warp-wide filter round costs ~100 instructions whatever the bucket holds; below this size one thread per bucket
+        // is cheaper (32 buckets per warp at a time)
+        constexpr int FILTER_WARP_MIN = 12;
         // up to 32 entries, one per lane (v0: the lane's entry, already loaded): bitonic network of register shuffles
         auto warp_sort_regs = [&](int key, int s0, int n, uint32_t v0) {
             uint32_t kv = lane < n ? ((entry_sort_key(v0) << 5) | (uint32_t)lane) : 0xFFFFFFFFu;   // key | source lane
@@ -807,9 +841,11 @@ k_observe(FlBatch b, ObsLayout lay, float *__restrict__ out_attr, float *__restr
                 }
             const uint32_t v = __shfl_sync(0xFFFFFFFFu, v0, kv & 31u);
             if (lane < n) ent[s0 + lane] = v;
-            FilterAcc acc{0u, 0u};
-            filter_round(acc, lane < n, v);
-            filter_store(key, acc);
+            if (n > FILTER_WARP_MIN) {                                          // smaller buckets: filter_serial in a thread-per-bucket pass
+                FilterAcc acc{0u, 0u};
+                filter_round(acc, lane < n, v);
+                filter_store(key, acc);
+            }
         };
         // more than 32 entries: two stable radix passes (5 + 5 bits of the 10-bit key) through the scratch copy, the bucket
         // taken 256 entries at a time so that eight loads per lane are in flight (one memory round trip per 256 entries and
@@ -883,8 +919,10 @@ k_observe(FlBatch b, ObsLayout lay, float *__restrict__ out_attr, float *__restr
             const int n_big = min(ld_vol_i32(&s_misc[1]), bigq_cap);
             for (int q = warp; q < n_big; q += NWARPS) {
                 const int key = (int)bigq[q], s0 = (int)ks[key - 1], n = (int)ks[key] - s0;
-                if (n <= 32) warp_sort_regs(key, s0, n, lane < n ? ent[s0 + lane] : 0u);
-                else warp_sort_radix(key, s0, n);
+                if (n <= 32) {
+                    warp_sort_regs(key, s0, n, lane < n ? ent[s0 + lane] : 0u);
+                    if (n <= FILTER_WARP_MIN) { __syncwarp(); if (lane == 0) filter_serial(key, s0, s0 + n); }
+                } else warp_sort_radix(key, s0, n);
             }
         } else {
             OBS_TICK(9);
@@ -892,7 +930,7 @@ k_observe(FlBatch b, ObsLayout lay, float *__restrict__ out_attr, float *__restr
             // one is sorted (a bucket costs one L2 / DRAM round trip that nothing else hides at 32 warps per SM)
             auto fetch = [&](int key, int &s0, int &n, uint32_t &v) {
                 n = 0; v = 0u; s0 = 0;
-                if (key < R) { s0 = (int)ks[key - 1]; n = (int)ks[key] - s0; if (n >= 1 && n <= 32 && lane < n) v = ent[s0 + lane]; }
+                if (key < R) { s0 = (int)ks[key - 1]; n = (int)ks[key] - s0; if (n >= 2 && n <= 32 && lane < n) v = ent[s0 + lane]; }
             };
             int s0a, na, s0b, nb;
             uint32_t va, vb;
@@ -902,9 +940,15 @@ k_observe(FlBatch b, ObsLayout lay, float *__restrict__ out_attr, float *__restr
                 int s0x, nx;
                 uint32_t vx;
                 fetch(key + 2 * NWARPS, s0x, nx, vx);
-                if (na >= 1) { if (na <= 32) warp_sort_regs(key, s0a, na, va); else warp_sort_radix(key, s0a, na); }
+                if (na > 32) warp_sort_radix(key, s0a, na);
+                else if (na >= 2) warp_sort_regs(key, s0a, na, va);
                 s0a = s0b; na = nb; va = vb;
                 s0b = s0x; nb = nx; vb = vx;
+            }
+            named_bar_sync(1, NW);                                              // the sorted buckets are visible to every thread
+            for (int key = tid; key < R; key += NW) {
+                const int s0 = (int)ks[key - 1], s1 = (int)ks[key];
+                if (s1 > s0 && s1 - s0 <= FILTER_WARP_MIN) filter_serial(key, s0, s1);
             }
         }
         named_bar_sync(1, NW);
@@ -921,7 +965,7 @@ k_observe(FlBatch b, ObsLayout lay, float *__restrict__ out_attr, float *__restr
             for (int k = tid; k < R; k += NW) gi[k] = ci[k];
             for (int k = tid; k <= R + 1; k += NW) gi[Rcap + k] = ks[k - 1];
             uint2 *gb = reinterpret_cast<uint2 *>(gi + 2 * Rcap + 4);
-            for (int k = tid; k < 4 * R; k += NW) gb[k] = bm[k];
+            if (lay.bm >= 0) for (int k = tid; k < 4 * R; k += NW) gb[k] = bm[k];     // else it was built there
             if (ent == ent_s) {
                 uint32_t *ge = b.entries + (size_t)e * b.ent_cap;
                 for (int k = tid; k < n_ent; k += NW) ge[k] = ent_s[k];

@@ -18,7 +18,7 @@ cfg = sys.argv[1] if len(sys.argv) > 1 else "Test_14"
 E = int(sys.argv[2]) if len(sys.argv) > 2 and int(sys.argv[2]) > 0 else bench.CONFIGS[cfg]["envs"]
 rounds = int(sys.argv[3]) if len(sys.argv) > 3 else 5
 worlds = bench.load_worlds(cfg, 2 * E)
-batch = fb.BatchedRailEnv(worlds[:E], auto_reset=True, reserve=0.6, min_slots=max(len(fb.unique_target_slots(w)[0]) for w in worlds))
+batch = fb.BatchedRailEnv(worlds[:E], auto_reset=True, reserve=0.3, min_slots=max(len(fb.unique_target_slots(w)[0]) for w in worlds))
 batch.reset()
 a = torch.full((E, batch.N), 2, dtype=torch.uint8, device=batch.device)
 for _ in range(5):
