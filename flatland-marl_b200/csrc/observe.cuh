@@ -39,6 +39,7 @@ struct ObsLayout {   // byte offsets into dynamic shared memory (host: make_obs_
     int bar, part, ag, dl, ci, ks, bm, sq, seg_cap, sort_small, kcls, grid, ridx, ent, ent_cap, total;
     int srec, wrec, whoff, whits, wlist, sdist;   // static walk tables (walks.cuh)
     int sq_words;                                 // uint32 words of the sq region (seg_cap may be lowered by a test override)
+    int flat_walk;                                // path segments walked by warps as flat lists: bit 0 counting pass, bit 1 scatter pass
     int parts;                                    // split launch: CTAs per environment of the tree kernel (0 = fused kernel)
     int ws_ag, ws_idx, ws_ag_bytes, ws_idx_bytes; // split launch: byte offsets / sizes of the two blocks of FlBatch.obs_ws
 };
@@ -620,15 +621,33 @@ k_observe(FlBatch b, ObsLayout lay, float *__restrict__ out_attr, float *__restr
                                                                       // agent | first path index << 10 | direction after << 19 | last << 21
         uint2 *pool_g = reinterpret_cast<uint2 *>(b.segs) + (size_t)e * b.seg_stride;   // segments beyond the shared-memory pool
         const int seg_gcap = b.segs ? (int)b.seg_stride : 0;
+        // The chain of an agent is a function of its start state alone (and of static data), and most trains stand still from
+        // one step to the next (waiting to depart, stopped, deadlocked): FlBatch.chain_cache keeps every agent's last chain
+        // ([E][N][CHAIN_SLOTS] uint2: slot 0 = start state | 1 << 31, number of segments; then the segment records), so that
+        // following the chain again — one dependent, mostly DRAM-missing load per walk — is only needed after a move.
+        constexpr int CHAIN_SLOTS = 64;
+        uint2 *chain = b.chain_cache ? reinterpret_cast<uint2 *>(b.chain_cache) + (size_t)e * b.chain_stride : nullptr;
+        int *job_pos = A.cellid, *job_n = A.initcell;           // free since phase 1: where a cached chain goes in the pool
         for (int i = tid; i < N; i += NW) {
             const uint32_t info = A.info[i];
             const unsigned slot = (info >> 8) & 0xFFFFu;
             unsigned sid = A.sid0[i];
+            job_pos[i] = -1;
             if (sid == 0xFFFFu) continue;
+            uint2 *cc = chain ? chain + (size_t)i * CHAIN_SLOTS : nullptr;
+            if (cc) {
+                const uint2 hd = cc[0];
+                if (hd.x == (sid | 0x80000000u)) {                                // cached: copied below by a warp
+                    job_pos[i] = atomicAdd(&s_misc[0], (int)hd.y);
+                    job_n[i] = (int)hd.y;
+                    continue;
+                }
+            }
+            const unsigned sid_start = sid;
             const int tpc = (int)(info >> 24);
             const uint32_t *gt = gtab + (size_t)slot * SS;
             unsigned dp = sid & 3u;
-            int kk = 0;
+            int kk = 0, cnt = 0;
             const bool stuck = sdist[(size_t)slot * SS + sid] == FL_DIST_INF;   // no move lowers the distance: a single element
             while (true) {
                 const uint32_t g = stuck ? 0xFFFFu : gt[sid];
@@ -638,16 +657,63 @@ k_observe(FlBatch b, ObsLayout lay, float *__restrict__ out_attr, float *__restr
                                              (unsigned)i | ((unsigned)kk << 10) | ((nxt & 3u) << 19) | ((nxt == 0xFFFFu ? 1u : 0u) << 21));
                 if (pos < lay.seg_cap) pool[pos] = rec;
                 else if (pos - lay.seg_cap < seg_gcap) pool_g[pos - lay.seg_cap] = rec;
+                cnt++;
+                if (cc && cnt < CHAIN_SLOTS) cc[cnt] = rec;
                 kk += (int)kend + 1;
                 if (nxt == 0xFFFFu || kk > FL_PRED_DEPTH || 1 + (kk - 1) * tpc >= NPRED) break;
                 dp = g >> 30; sid = nxt;
             }
+            if (cc) cc[0] = cnt < CHAIN_SLOTS ? make_uint2(sid_start | 0x80000000u, (unsigned)cnt) : make_uint2(0u, 0u);
         }
+        named_bar_sync(1, NW);
+        if (chain)
+            for (int i = warp; i < N; i += NW / 32) {          // cached chains into the pool, a warp per agent, coalesced
+                const int pos = job_pos[i], n = job_n[i];
+                if (pos < 0) continue;
+                const uint2 *cc = chain + (size_t)i * CHAIN_SLOTS + 1;
+                for (int k = lane; k < n; k += 32) {
+                    const uint2 rec = cc[k];
+                    const int q = pos + k;
+                    if (q < lay.seg_cap) pool[q] = rec;
+                    else if (q - lay.seg_cap < seg_gcap) pool_g[q - lay.seg_cap] = rec;
+                }
+            }
         named_bar_sync(1, NW);
         const int n_seg = s_misc[0];
         if (dbg && tid == 0) dbg[11] = n_seg;
         const bool pooled = n_seg <= lay.seg_cap + seg_gcap;  // else: every lane walks its agent's path itself (predict_path), twice
-        // Emit(rail cell, t0, t1, entry) for every occupied element of every pool segment, a warp at a time: 32 segments per batch, their occupied elements as one flat list, one
+        // Emit(rail cell, t0, t1, entry) for every occupied element of pool segment j (one thread per segment)
+        auto emit_segment = [&](int j, auto emit) {
+            const uint2 sg = j < lay.seg_cap ? pool[j] : pool_g[j - lay.seg_cap];
+            const unsigned sid = sg.x & 0xFFFFu;
+            const int kend = (int)((sg.x >> 16) & 0x3FFFu), agent = (int)(sg.y & 1023u), kk = (int)((sg.y >> 10) & 511u);
+            const bool seg_last = (sg.y >> 21) & 1u;
+            const uint32_t ainf = A.info[agent];
+            const int tpc = (int)(ainf >> 24);
+            const uint32_t extra = entry_extra(tpc, (ainf >> 5) & 1u);
+            int dp = (int)(sg.x >> 30);
+            const uint32_t wx = wrec[sid].x;
+            for (int k0 = 0; k0 <= kend; k0 += 4) {  // four states per round: one memory latency per round (8 elements of slack in wlist)
+                unsigned sv[5];
+#pragma unroll
+                for (int u = 0; u < 5; u++) sv[u] = wlist[wx + k0 + u];
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    const int k = k0 + u;
+                    if (k > kend) return;
+                    const int idx = kk + k;
+                    const int t0 = idx ? 1 + (idx - 1) * tpc : 0;
+                    if (t0 >= NPRED) return;
+                    const bool last = (k == kend && seg_last) || idx >= FL_PRED_DEPTH;
+                    const int d = (int)(sv[u] & 3u), dn = last ? d : (k < kend ? (int)(sv[u + 1] & 3u) : (int)((sg.y >> 19) & 3u));
+                    const int t1 = last ? NPRED - 1 : min(idx ? idx * tpc : 0, NPRED - 1);
+                    emit((sv[u] & 0xFFFFu) >> 2, t0, t1, pack_entry(agent, t0, t1, d, dp, dn, extra));
+                    if (last) return;
+                    dp = d;
+                }
+            }
+        };
+        // The same for every pool segment, a warp at a time (lay.flat_walk bit 0: counting pass, bit 1: scatter pass): 32 segments per batch, their occupied elements as one flat list, one
         // element per lane and round — every load of a round is independent, so a batch costs about three memory round trips
         // (segment record -> walk offset -> states) instead of three per segment and thread.  dirs: the entry's directions are
         // needed (scatter pass) or only its rail cell (counting pass).
@@ -704,7 +770,7 @@ k_observe(FlBatch b, ObsLayout lay, float *__restrict__ out_attr, float *__restr
         };
         auto count_emit = [&](unsigned rail, int, int, uint32_t) { atomicAdd(&ks[kcls ? (unsigned)kcls[rail] : rail], 1u); };
         // counting pass: entries per rail cell (or key class)
-        if (pooled) emit_pool_flat(false, count_emit);
+        if (pooled) { if (lay.flat_walk & 1) emit_pool_flat(false, count_emit); else for (int j = tid; j < n_seg; j += NW) emit_segment(j, count_emit); }
         else
             for (int i = tid; i < N; i += NW) {
                 const uint32_t info = A.info[i];
@@ -738,11 +804,18 @@ k_observe(FlBatch b, ObsLayout lay, float *__restrict__ out_attr, float *__restr
         if (tid == 0) s_misc[0] = n_ent;
         if (n_ent > lay.ent_cap) ent = b.entries + (size_t)e * b.ent_cap;   // does not fit in shared memory: global spill space
         // scatter pass.  ks[key] is advanced to the END of its bucket; bucket r is [ks[r-1], ks[r]) afterwards (ks[-1] = 0).
-        auto scatter_emit = [&](unsigned rail, int, int, uint32_t en) {
+        auto scatter_emit = [&](unsigned rail, int t0, int t1, uint32_t en) {
             const unsigned key = kcls ? (unsigned)kcls[rail] : rail;
             ent[atomicAdd(&ks[key], 1u)] = en;
+            const int sa = t0 >> 2, sb = t1 >> 2;             // time slots of 4 rows the entry overlaps
+            for (int wd = sa >> 5; wd <= sb >> 5; wd++) {
+                const int lo_b = max(sa - 32 * wd, 0), hi_b = min(sb - 32 * wd, 31);
+                const uint32_t m = (0xFFFFFFFFu >> (31 - hi_b)) & (0xFFFFFFFFu << lo_b);
+                const uint32_t twice = atomicOr(&bm[key * 4 + wd].x, m) & m;     // slots that already had an entry
+                if (twice) atomicOr(&bm[key * 4 + wd].y, twice);
+            }
         };
-        if (pooled) emit_pool_flat(true, scatter_emit);
+        if (pooled) { if (lay.flat_walk & 2) emit_pool_flat(true, scatter_emit); else for (int j = tid; j < n_seg; j += NW) emit_segment(j, scatter_emit); }
         else
             for (int i = tid; i < N; i += NW) {
                 const uint32_t info = A.info[i];
@@ -775,59 +848,6 @@ k_observe(FlBatch b, ObsLayout lay, float *__restrict__ out_attr, float *__restr
                 ent[y + 1] = v;
             }
         };
-        // The time-slot filter of a bucket (bm: bit s of .x / .y of word w = at least one / two entries of the key overlap rows
-        // 4 (32 w + s) .. + 3) is computed from the bucket once it is sorted — by the thread or warp that sorted it, without
-        // atomics (two shared-memory atomics per entry in the scatter pass cost more than the whole sort at Test_14).
-        // rows an entry covers: t0 .. 500 for the last element of a path, row 0 for element 0, else t0 .. t0 + tpc - 1
-        auto entry_slots = [&](uint32_t en, int &sa, int &sb) {
-            const int t0 = (int)((en >> 10) & 511u);
-            const int t1 = ((en >> 19) & 1u) ? NPRED - 1 : (t0 ? min(t0 + entry_tpc(en, A.info) - 1, NPRED - 1) : 0);
-            sa = t0 >> 2; sb = t1 >> 2;
-        };
-        auto slot_mask = [](int sa, int sb, int w) -> uint32_t {
-            const int lo_b = max(sa - 32 * w, 0), hi_b = min(sb - 32 * w, 31);
-            return lo_b <= hi_b ? ((0xFFFFFFFFu >> (31 - hi_b)) & (0xFFFFFFFFu << lo_b)) : 0u;
-        };
-        auto filter_serial = [&](int key, int s0, int s1) {                   // one thread, bucket [s0, s1)
-            uint32_t x0 = 0, x1 = 0, x2 = 0, x3 = 0, y0 = 0, y1 = 0, y2 = 0, y3 = 0;
-            for (int i0 = s0; i0 < s1; i0 += 4) {                              // four loads in flight (the entries may live in global memory)
-                uint32_t en[4];
-#pragma unroll
-                for (int u = 0; u < 4; u++) en[u] = i0 + u < s1 ? ent[i0 + u] : 0u;
-#pragma unroll
-                for (int u = 0; u < 4; u++) {
-                    if (i0 + u >= s1) break;
-                    int sa, sb;
-                    entry_slots(en[u], sa, sb);
-                    const uint32_t m0 = slot_mask(sa, sb, 0), m1 = slot_mask(sa, sb, 1), m2 = slot_mask(sa, sb, 2), m3 = slot_mask(sa, sb, 3);
-                    y0 |= x0 & m0; x0 |= m0; y1 |= x1 & m1; x1 |= m1; y2 |= x2 & m2; x2 |= m2; y3 |= x3 & m3; x3 |= m3;
-                }
-            }
-            bm[key * 4 + 0] = make_uint2(x0, y0); bm[key * 4 + 1] = make_uint2(x1, y1);
-            bm[key * 4 + 2] = make_uint2(x2, y2); bm[key * 4 + 3] = make_uint2(x3, y3);
-        };
-        // a warp, one entry per lane and round: lane w < 4 accumulates word w (seen / twice) over the rounds
-        struct FilterAcc { uint32_t seen, twice; };
-        auto filter_round = [&](FilterAcc &acc, bool valid, uint32_t en) {
-            int sa = 1, sb = 0;
-            if (valid) entry_slots(en, sa, sb);
-#pragma unroll
-            for (int w = 0; w < 4; w++) {
-                const uint32_t m = valid ? slot_mask(sa, sb, w) : 0u;
-                uint32_t incl = m;                                            // OR of the masks of lanes 0..lane
-#pragma unroll
-                for (int o = 1; o < 32; o <<= 1) { const uint32_t q = __shfl_up_sync(0xFFFFFFFFu, incl, o); if (lane >= o) incl |= q; }
-                uint32_t excl = __shfl_up_sync(0xFFFFFFFFu, incl, 1);
-                if (lane == 0) excl = 0u;
-                const uint32_t all = __shfl_sync(0xFFFFFFFFu, incl, 31);
-                const uint32_t tw = __reduce_or_sync(0xFFFFFFFFu, m & excl);
-                if (lane == w) { acc.twice |= tw | (acc.seen & all); acc.seen |= all; }
-            }
-        };
-        auto filter_store = [&](int key, const FilterAcc &acc) { if (lane < 4) bm[key * 4 + lane] = make_uint2(acc.seen, acc.twice); };
-        // A warp-wide filter round costs ~100 instructions whatever the bucket holds; below this size one thread per bucket
-        // is cheaper (32 buckets per warp at a time)
-        constexpr int FILTER_WARP_MIN = 12;
         // up to 32 entries, one per lane (v0: the lane's entry, already loaded): bitonic network of register shuffles
         auto warp_sort_regs = [&](int key, int s0, int n, uint32_t v0) {
             uint32_t kv = lane < n ? ((entry_sort_key(v0) << 5) | (uint32_t)lane) : 0xFFFFFFFFu;   // key | source lane
@@ -841,17 +861,12 @@ k_observe(FlBatch b, ObsLayout lay, float *__restrict__ out_attr, float *__restr
                 }
             const uint32_t v = __shfl_sync(0xFFFFFFFFu, v0, kv & 31u);
             if (lane < n) ent[s0 + lane] = v;
-            if (n > FILTER_WARP_MIN) {                                          // smaller buckets: filter_serial in a thread-per-bucket pass
-                FilterAcc acc{0u, 0u};
-                filter_round(acc, lane < n, v);
-                filter_store(key, acc);
-            }
         };
         // more than 32 entries: two stable radix passes (5 + 5 bits of the 10-bit key) through the scratch copy, the bucket
         // taken 256 entries at a time so that eight loads per lane are in flight (one memory round trip per 256 entries and
         // loop instead of one per 32)
         auto warp_sort_radix = [&](int key, int s0, int n) {
-            if (!scratch) { if (lane == 0) { insertion_sort(s0, s0 + n); filter_serial(key, s0, s0 + n); } __syncwarp(); return; }
+            if (!scratch) { if (lane == 0) insertion_sort(s0, s0 + n); __syncwarp(); return; }
             uint32_t *bufa = ent + s0, *bufb = scratch + s0;
 #pragma unroll 1
             for (int pass = 0; pass < 2; pass++) {
@@ -892,37 +907,22 @@ k_observe(FlBatch b, ObsLayout lay, float *__restrict__ out_attr, float *__restr
                     }
                 }
             }
-            FilterAcc acc{0u, 0u};                                              // the sorted bucket once more, for its filter
-            for (int x0 = 0; x0 < n; x0 += 256) {
-                uint32_t v[8];
-#pragma unroll
-                for (int u = 0; u < 8; u++) { const int x = x0 + u * 32 + lane; v[u] = x < n ? bufa[x] : 0u; }
-#pragma unroll
-                for (int u = 0; u < 8; u++) {
-                    if (x0 + u * 32 >= n) break;
-                    filter_round(acc, x0 + u * 32 + lane < n, v[u]);
-                }
-            }
-            filter_store(key, acc);
         };
         constexpr int NWARPS = NW / 32;
         if (in_smem) {
             for (int key = tid; key < R; key += NW) {
                 const int s0 = (int)ks[key - 1], s1 = (int)ks[key];
-                if (s1 == s0) continue;                                         // empty: its filter words were zeroed at the start
-                if (s1 - s0 <= SORT_SMALL) { insertion_sort(s0, s1); filter_serial(key, s0, s1); continue; }
+                if (s1 - s0 <= SORT_SMALL) { insertion_sort(s0, s1); continue; }
                 const int pos = atomicAdd(&s_misc[1], 1);
-                if (pos < bigq_cap) bigq[pos] = (uint32_t)key; else { insertion_sort(s0, s1); filter_serial(key, s0, s1); }
+                if (pos < bigq_cap) bigq[pos] = (uint32_t)key; else insertion_sort(s0, s1);
             }
             named_bar_sync(1, NW);
             OBS_TICK(9);
             const int n_big = min(ld_vol_i32(&s_misc[1]), bigq_cap);
             for (int q = warp; q < n_big; q += NWARPS) {
                 const int key = (int)bigq[q], s0 = (int)ks[key - 1], n = (int)ks[key] - s0;
-                if (n <= 32) {
-                    warp_sort_regs(key, s0, n, lane < n ? ent[s0 + lane] : 0u);
-                    if (n <= FILTER_WARP_MIN) { __syncwarp(); if (lane == 0) filter_serial(key, s0, s0 + n); }
-                } else warp_sort_radix(key, s0, n);
+                if (n <= 32) warp_sort_regs(key, s0, n, lane < n ? ent[s0 + lane] : 0u);
+                else warp_sort_radix(key, s0, n);
             }
         } else {
             OBS_TICK(9);
@@ -944,11 +944,6 @@ k_observe(FlBatch b, ObsLayout lay, float *__restrict__ out_attr, float *__restr
                 else if (na >= 2) warp_sort_regs(key, s0a, na, va);
                 s0a = s0b; na = nb; va = vb;
                 s0b = s0x; nb = nx; vb = vx;
-            }
-            named_bar_sync(1, NW);                                              // the sorted buckets are visible to every thread
-            for (int key = tid; key < R; key += NW) {
-                const int s0 = (int)ks[key - 1], s1 = (int)ks[key];
-                if (s1 > s0 && s1 - s0 <= FILTER_WARP_MIN) filter_serial(key, s0, s1);
             }
         }
         named_bar_sync(1, NW);

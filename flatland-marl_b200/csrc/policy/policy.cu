@@ -1302,6 +1302,8 @@ Workspace carve(void *base, long long M) {
 
 }  // namespace
 
+#include "policy_f32.cuh"
+
 extern "C" {
 
 int fl_policy_abi_version(void) { return FL_POLICY_ABI_VERSION; }
@@ -1428,6 +1430,89 @@ int fl_policy_forward(const FlPolicyWeights *w, void *d_workspace, size_t worksp
     if ((rc = launch_linear(ws.y1, 512, 256, nullptr, 0, 0, (const bf16 *)w->head_w2a, w->head_b2, ws.y2, 256, M, 128, 1, st))) return rc;
     if ((rc = launch_linear(ws.y1 + 256, 512, 256, nullptr, 0, 0, (const bf16 *)w->head_w2c, w->head_b2 + 128, ws.y2 + 128, 256, M, 128, 1, st))) return rc;
     k_head_final<<<(unsigned)E, 256, (size_t)N * sizeof(float), st>>>(ws.y2, w->head_w3, w->head_b3, d_logits, d_value, (int)N);
+    g_launches++;
+    return (int)cudaGetLastError();
+}
+
+// ---- the same forward pass in fp32 on the CUDA cores (policy_f32.cuh) --------------------------------------------------
+size_t fl_policy_workspace_bytes_f32(int64_t n_agents_total) {
+    if (n_agents_total <= 0) return 0;
+    f32path::Ws w;
+    return f32path::carve(w, nullptr, n_agents_total);
+}
+
+int fl_policy_forward_f32(const float *const *wts, void *d_workspace, size_t workspace_bytes, int64_t E, int64_t N,
+                          const float *d_agent_attr, const float *d_forest, const int32_t *d_adjacency,
+                          const int32_t *d_node_order, float *d_logits, float *d_value, void *stream) {
+    using namespace f32path;
+    if (!wts || !d_workspace || E <= 0 || N <= 0 || !d_agent_attr || !d_forest || !d_adjacency || !d_node_order || !d_logits || !d_value) return -1;
+    const long long T = E * N;
+    Ws ws;
+    if (carve(ws, (unsigned char *)d_workspace, T) > workspace_bytes) return -1;
+    cudaStream_t st = (cudaStream_t)stream;
+    auto gemm = [&](const float *a1, const int32_t *idx1, long long lda1, int K1, const float *a2, long long lda2, int K2,
+                    const float *w, const float *bias, float *c, long long ldc, long long M, int Nn, int act) {
+        if (M <= 0) return;
+        GemmArgs g{a1, idx1, lda1, K1, a2, lda2, K2, w, bias, c, ldc, M, nullptr, Nn, act};
+        k_gemm_f32<<<dim3((unsigned)((M + 63) / 64), (unsigned)((Nn + 63) / 64)), 256, 0, st>>>(g);
+        g_launches++;
+    };
+    // reference state_dict order (policy_weights.weight_spec)
+    const float *W_iou = wts[0], *b_iou = wts[1], *U_iou = wts[2], *W_c = wts[3], *b_c = wts[4], *W_f = wts[5], *b_f = wts[6], *U_f = wts[7];
+    // ---- Tree-LSTM (TreeLSTM.py:34-154) ----
+    const long long nodes = T * f32path::NODES;
+    cudaMemsetAsync(ws.h, 0, (size_t)nodes * T_H * 4, st);
+    cudaMemsetAsync(ws.c, 0, (size_t)nodes * T_H * 4, st);
+    cudaMemsetAsync(ws.counts, 0, 64 * 4, st);
+    k_tree_lists<<<(unsigned)((T + 127) / 128), 128, 0, st>>>(d_adjacency, d_node_order, T, ws.child_base, ws.lists, ws.counts, ws.cap);
+    k_tree_leaves<<<(unsigned)nodes, 128, 0, st>>>(d_forest, d_node_order, nodes, W_iou, b_iou, ws.h, ws.c);
+    g_launches += 2;
+    int32_t counts[MAX_LEVELS];
+    cudaError_t err = cudaMemcpyAsync(counts, ws.counts, sizeof(counts), cudaMemcpyDeviceToHost, st);
+    if (err == cudaSuccess) err = cudaStreamSynchronize(st);        // per-level sizes of the launches below (the fp32 path is not the fast path)
+    if (err != cudaSuccess) return (int)err;
+    for (int lv = 1; lv < MAX_LEVELS; lv++) {
+        const long long M = counts[lv];
+        if (M <= 0) continue;
+        if (M > ws.cap) return -1;
+        const int32_t *list = ws.lists + (long long)lv * ws.cap, *dM = ws.counts + lv;
+        k_level_rows<<<(unsigned)((M + 127) / 128), 128, 0, st>>>(list, dM, ws.child_base, ws.merge_row, ws.child_row);
+        g_launches++;
+        gemm(ws.h, ws.merge_row, T_H, 3 * T_H, nullptr, 0, 0, U_iou, nullptr, ws.iou, 3 * T_H, M, 3 * T_H, 0);          // U_iou [h_c0 | h_c1 | h_c2]
+        gemm(ws.h, ws.child_row, T_H, T_H, nullptr, 0, 0, U_f, nullptr, ws.fraw, T_H, 3 * M, T_H, 0);                    // U_f h_child
+        k_forget<<<(unsigned)M, 384, 0, st>>>(ws.fraw, list, ws.child_row, dM, d_forest, W_f, b_f, ws.c, ws.fc);
+        gemm(ws.fc, nullptr, 3 * T_H, 3 * T_H, nullptr, 0, 0, W_c, nullptr, ws.craw, T_H, M, T_H, 0);                    // W_c [f c]_merge
+        k_inner<<<(unsigned)M, 128, 0, st>>>(ws.iou, ws.craw, list, dM, d_forest, W_iou, b_iou, b_c, ws.h, ws.c);
+        g_launches += 2;
+    }
+    // ---- attribute MLP (net_tree.py:41-50), emb = cat(attr embedding, h of the root) ----
+    gemm(d_agent_attr, nullptr, 83, 83, nullptr, 0, 0, wts[8], wts[9], ws.a0, 256, T, 256, 1);
+    gemm(ws.a0, nullptr, 256, 256, nullptr, 0, 0, wts[10], wts[11], ws.a1, 256, T, 256, 1);
+    gemm(ws.a1, nullptr, 256, 256, nullptr, 0, 0, wts[12], wts[13], ws.a0, 256, T, 256, 1);
+    gemm(ws.a0, nullptr, 256, 256, nullptr, 0, 0, wts[14], wts[15], ws.emb, 256, T, 128, 1);
+    k_copy_cols<<<(unsigned)((T * 128 + 255) / 256), 256, 0, st>>>(ws.h, (long long)f32path::NODES * T_H, ws.emb + 128, 256, T, 128);
+    g_launches++;
+    // ---- three attention blocks (net_tree.py:20-32) ----
+    const float *x = ws.emb;
+    float *outs[3] = {ws.x0, ws.x1, ws.x0};
+    for (int l = 0; l < 3; l++) {
+        const float *const *tw = wts + 16 + 6 * l;
+        gemm(x, nullptr, 256, 256, nullptr, 0, 0, tw[0], tw[1], ws.qkv, 768, T, 768, 0);
+        k_attention<<<(unsigned)((T * 4 * 32 + 255) / 256), 256, 0, st>>>(ws.qkv, ws.y1, 256, E, (int)N);              // heads -> y1 [T][256]
+        g_launches++;
+        gemm(ws.y1, nullptr, 256, 256, nullptr, 0, 0, tw[2], tw[3], ws.cat + 256, 512, T, 256, 0);                         // out_proj -> cat[:, 256:]
+        k_copy_cols<<<(unsigned)((T * 256 + 255) / 256), 256, 0, st>>>(x, 256, ws.cat, 512, T, 256);                   // cat[:, :256] = input
+        g_launches++;
+        gemm(ws.cat, nullptr, 512, 512, nullptr, 0, 0, tw[4], tw[5], outs[l], 256, T, 256, 1);
+        x = outs[l];
+    }
+    // ---- heads on cat(emb, att) (net_tree.py:56-71, 100-110) ----
+    const float *const *aw = wts + 34, *const *cw = wts + 40;
+    gemm(ws.emb, nullptr, 256, 256, x, 256, 256, aw[0], aw[1], ws.y1, 256, T, 256, 1);
+    gemm(ws.y1, nullptr, 256, 256, nullptr, 0, 0, aw[2], aw[3], ws.y2a, 128, T, 128, 1);
+    gemm(ws.emb, nullptr, 256, 256, x, 256, 256, cw[0], cw[1], ws.y1, 256, T, 256, 1);
+    gemm(ws.y1, nullptr, 256, 256, nullptr, 0, 0, cw[2], cw[3], ws.y2c, 128, T, 128, 1);
+    k_heads_final<<<(unsigned)E, 256, (size_t)N * sizeof(float), st>>>(ws.y2a, ws.y2c, aw[4], aw[5], cw[4], cw[5], d_logits, d_value, (int)N);
     g_launches++;
     return (int)cudaGetLastError();
 }

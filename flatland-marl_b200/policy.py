@@ -18,7 +18,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "csrc", "policy", "libflatland_policy_b200.so")
 LAYERS = pw.N_TRANSFORMER
 
-EXPORTS = ["fl_policy_abi_version", "fl_policy_workspace_bytes", "fl_policy_forward", "fl_policy_choose_actions",
+EXPORTS = ["fl_policy_abi_version", "fl_policy_workspace_bytes", "fl_policy_forward", "fl_policy_workspace_bytes_f32",
+           "fl_policy_forward_f32", "fl_policy_choose_actions",
            "fl_policy_linear", "fl_policy_linear_debug", "fl_policy_debug_clocks", "fl_policy_launch_count"]
 
 
@@ -49,6 +50,10 @@ def lib():
     L.fl_policy_workspace_bytes.argtypes = [C.c_int64]
     L.fl_policy_forward.restype = C.c_int
     L.fl_policy_forward.argtypes = [C.POINTER(FlPolicyWeights), P, C.c_size_t, C.c_int64, C.c_int64, P, P, P, P, P, P, P]
+    L.fl_policy_workspace_bytes_f32.restype = C.c_size_t
+    L.fl_policy_workspace_bytes_f32.argtypes = [C.c_int64]
+    L.fl_policy_forward_f32.restype = C.c_int
+    L.fl_policy_forward_f32.argtypes = [P, P, C.c_size_t, C.c_int64, C.c_int64, P, P, P, P, P, P, P]
     L.fl_policy_choose_actions.restype = C.c_int
     L.fl_policy_choose_actions.argtypes = [P, P, P, C.c_int64, P]
     L.fl_policy_linear.restype = C.c_int
@@ -125,7 +130,13 @@ class BatchedActor:
     weights: a reference checkpoint path (.pt state_dict or .npz), a state_dict-like dict of arrays, or None for
     `init_weights(seed)`."""
 
-    def __init__(self, weights=None, device="cuda:0", seed=0):
+    def __init__(self, weights=None, device="cuda:0", seed=0, precision="bf16"):
+        """precision: "bf16" — bf16 operands, fp32 accumulation on the tensor cores (the fast path; logits within about 1e-2
+        of the reference network); "fp32" — the reference's own arithmetic on the CUDA cores (fl_policy_forward_f32: logits
+        within summation-order rounding of the reference, about ten times slower)."""
+        if precision not in ("bf16", "fp32"):
+            raise ValueError("precision must be 'bf16' or 'fp32'")
+        self.precision = precision
         if not torch.cuda.is_available():
             raise FlatlandB200Error("BatchedActor needs a CUDA device (no CPU fallback on the policy path)")
         self.lib = lib()
@@ -154,6 +165,12 @@ class BatchedActor:
                     getattr(s, name)[l] = self.t["%s%d" % (name, l)].data_ptr()
             else:
                 setattr(s, name, self.t[name].data_ptr())
+        # fp32 path: the reference state_dict as it is, in registration order
+        self._f32 = None
+        if precision == "fp32":
+            tens = [torch.from_numpy(np.ascontiguousarray(weights[name], dtype=np.float32)).to(self.device) for name, _, _ in pw.weight_spec()]
+            ptrs = (C.c_void_p * len(tens))(*[t.data_ptr() for t in tens])
+            self._f32 = (tens, ptrs)
         self._ws = None
         self._out = None
 
@@ -161,7 +178,7 @@ class BatchedActor:
         return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
 
     def _buffers(self, E, N):
-        need = int(self.lib.fl_policy_workspace_bytes(E * N))
+        need = int((self.lib.fl_policy_workspace_bytes_f32 if self.precision == "fp32" else self.lib.fl_policy_workspace_bytes)(E * N))
         if self._ws is None or self._ws.numel() < need:
             self._ws = torch.empty(need, dtype=torch.uint8, device=self.device)
         if self._out is None or self._out[0].shape[:2] != (E, N):
@@ -181,6 +198,11 @@ class BatchedActor:
                 raise ValueError("%s must be a contiguous %s tensor on %s" % (name, dt, self.device))
         E, N = int(a.shape[0]), int(a.shape[1])
         ws, (logits, value, _) = self._buffers(E, N)
+        if self.precision == "fp32":
+            _check(self.lib.fl_policy_forward_f32(self._f32[1], ws.data_ptr(), ws.numel(), E, N, a.data_ptr(), f.data_ptr(),
+                                                  adj.data_ptr(), no.data_ptr(), logits.data_ptr(), value.data_ptr(), self._stream()),
+                   "fl_policy_forward_f32")
+            return logits, value
         _check(self.lib.fl_policy_forward(C.byref(self.struct), ws.data_ptr(), ws.numel(), E, N, a.data_ptr(), f.data_ptr(),
                                           adj.data_ptr(), no.data_ptr(), logits.data_ptr(), value.data_ptr(), self._stream()),
                "fl_policy_forward")

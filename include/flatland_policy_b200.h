@@ -81,6 +81,18 @@ int fl_policy_forward(const FlPolicyWeights *w, void *d_workspace, size_t worksp
                       const float *d_agent_attr, const float *d_forest, const int32_t *d_adjacency,
                       const int32_t *d_node_order, float *d_logits, float *d_value, void *stream);
 
+/* The same forward pass in the reference's own arithmetic: fp32 operands and accumulation on the CUDA cores, exact erf-GELU /
+ * sigmoid / tanh, the reference's unfolded parameters (csrc/policy/policy_f32.cuh).  d_weights: FL_POLICY_F32_TENSORS device
+ * pointers to the fp32 tensors of the reference state_dict in its registration order (solution/nn/net_tree.py:33-72,
+ * TreeLSTM.py:12-32; flatland-marl_b200/policy_weights.py:weight_spec lists names and shapes).  Logits and values agree with
+ * the reference network to summation-order rounding (tests: 1e-4 absolute); about ten times slower than the tensor-core
+ * path.  Synchronises `stream` once (per-level node counts). */
+#define FL_POLICY_F32_TENSORS 46
+size_t fl_policy_workspace_bytes_f32(int64_t n_agents_total);
+int fl_policy_forward_f32(const float *const *d_weights, void *d_workspace, size_t workspace_bytes, int64_t E, int64_t N,
+                          const float *d_agent_attr, const float *d_forest, const int32_t *d_adjacency,
+                          const int32_t *d_node_order, float *d_logits, float *d_value, void *stream);
+
 /* Actor._choose_action in "soft" mode for every agent (plfActor.py:27-44): masked softmax over the valid actions,
  * then numpy's choice with the generator re-seeded to 42, i.e. the first action whose cumulative probability
  * exceeds 0.3745401188473625; no valid action -> 0.  d_valid_actions [n][5] u8, d_actions [n] u8. */

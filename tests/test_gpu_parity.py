@@ -30,6 +30,7 @@ PLANS = [
     # fused kernel / split launch (index kernel + `parts` tree CTAs per environment), forced either way
     {"parts": 0}, {"parts": 0, "entcap": 0, "sortsmall": 1}, {"parts": 1}, {"parts": 2}, {"parts": 3, "nt": 64}, {"parts": 7, "entcap": 0},
     {"parts": 2, "tables": 0}, {"parts": 4, "ctas": 1}, {"parts": 2, "sortsmall": 1, "segcap": 0},
+    {"flatwalk": 3}, {"flatwalk": 1, "parts": 2}, {"flatwalk": 2, "entcap": 0, "segcap": 3}, {"bmglobal": 1}, {"bmglobal": 1, "parts": 3},
 ]
 
 

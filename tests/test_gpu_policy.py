@@ -163,3 +163,48 @@ def test_full_batch_policy_on_sampled_envs(actor, config, n_envs, sample):
         assert abs(float(v_all[e]) - float(wval[0])) < LOGIT_ATOL
         safe = po.choice_margin(want[0], o["valid_actions"]) > 0.02
         assert (acts[e][safe] == po.choose_actions(want[0], o["valid_actions"])[safe]).all()
+
+
+# ---- the fp32 path: the reference's own arithmetic (fl_policy_forward_f32) -------------------------------------------
+F32_ATOL = 1e-4      # summation-order rounding only: measured differences are a few 1e-6
+
+
+@pytest.fixture(scope="module")
+def actor_f32():
+    from flatland_marl_b200.policy import BatchedActor
+    return BatchedActor(None, seed=0, precision="fp32")
+
+
+def test_fp32_forward_matches_reference_outputs_to_1e4(actor_f32, gold, golden):
+    """Logits and values within 1e-4 absolute of the UNMODIFIED reference network's outputs on all recorded observations,
+    and the same chosen action for every agent whose choice is not within 1e-4 of a cumulative-probability step."""
+    worst = 0.0
+    for k, (fixture, step) in enumerate(zip(gold["case_fixture"], gold["case_step"])):
+        obs = obs_of(golden, str(fixture), int(step))
+        d = to_dev([obs], actor_f32.device)
+        logits, value = actor_f32.forward(d)
+        acts = actor_f32.choose_actions(logits, d["valid_actions"])[0].cpu().numpy()
+        lg = logits[0].cpu().numpy()
+        ref = gold["logits_%d" % k]
+        np.testing.assert_allclose(lg, ref, rtol=0, atol=F32_ATOL, err_msg="%s step %d logits" % (fixture, step))
+        np.testing.assert_allclose(value.cpu().numpy(), gold["value_%d" % k], rtol=0, atol=F32_ATOL)
+        worst = max(worst, float(np.abs(lg - ref).max()))
+        safe = po.choice_margin(ref, obs["valid_actions"]) > 1e-4
+        assert (acts[safe] == gold["actions_%d" % k][safe]).all()
+    assert worst < F32_ATOL
+    print("fp32 path: worst |logit - reference| = %.2e" % worst)
+
+
+def test_fp32_forward_is_batch_independent_and_close_to_bf16(actor, actor_f32, golden):
+    """A batch of different observations gives every environment the bytes it gets alone; and the bf16 tensor-core path stays
+    within its stated tolerance of the fp32 path on a deep tree (relative bound: 3e-2 of the largest |logit| + 1e-2)."""
+    obs = [obs_of(golden, "t03_l0_random", s) for s in (0, 89, 176)]
+    d3 = to_dev(obs, actor_f32.device)
+    l3, v3 = actor_f32.forward(d3)
+    l3, v3 = l3.clone(), v3.clone()
+    for j, o in enumerate(obs):
+        l1, v1 = actor_f32.forward(to_dev([o], actor_f32.device))
+        assert torch.equal(l1[0], l3[j]) and torch.equal(v1[0], v3[j])
+    lb, _ = actor.forward(d3)
+    scale = float(l3.abs().max())
+    assert float((lb - l3).abs().max()) <= 3e-2 * scale + 1e-2
