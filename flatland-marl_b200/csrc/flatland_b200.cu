@@ -145,7 +145,7 @@ ObsLayout make_obs_layout(const FlBatch *b, int nt, int mode, int parts, int *ct
     L.seg_cap = mode == OBS_TREES ? 0 : 10 * N;                 // path segments of phase 3 share the room of the phase-4 queues
     if (L.seg_cap < (nt / 32) * 64) L.seg_cap = (nt / 32) * 64;
     L.sq_words = L.seg_cap * 2;
-    L.flat_walk = knob(KNOB_FLATWALK) >= 0 ? knob(KNOB_FLATWALK) : 0;
+    L.flat_walk = knob(KNOB_FLATWALK) >= 0 ? knob(KNOB_FLATWALK) : 3;
     int seg_cap_use = L.seg_cap;                                // "segcap" / "entcap" overrides (tests): smaller capacities in
     if (knob(KNOB_SEGCAP) >= 0 && knob(KNOB_SEGCAP) < seg_cap_use) seg_cap_use = knob(KNOB_SEGCAP);                            // the same room,
     L.sq = take((long long)L.seg_cap * 8);                      // per-warp queues of the full conflict checks / segment pool
@@ -211,18 +211,29 @@ int obs_threads(const FlBatch *b) {
     return b->N > 128 ? 1024 : 512;
 }
 
-// CTAs per environment of the tree kernel (0 = fused kernel).  Fused is the default while a wave of one-CTA-per-environment
-// fills the chip's CTA slots; few large environments are split so that the trees of one environment spread over several SMs.
+// CTAs per environment of the tree kernel (0 = fused kernel).  Measured on B200 (profiles/r02_launch_shapes.txt): the fused
+// kernel wins when one-CTA-per-environment fills the chip's CTA slots in whole waves and an environment has enough agents
+// to keep its CTA's warps busy (Test_03: 1024 environments on 148 x 7 slots); otherwise the split launch does — few large
+// environments spread their trees over more SMs (Test_14), a ragged last wave is cut into smaller units (Test_08), and
+// small environments no longer hold 128-thread CTAs through their serial phases (Test_02).
 int obs_parts(const FlBatch *b) {
     if (!b->obs_ws || b->ws_stride <= 0) return 0;
     const int v = knob(KNOB_PARTS);
     if (v >= 0) return v > 32 ? 32 : v;
-    if (b->E >= 2 * 148) return 0;
-    int p = (int)(148 / b->E);                                   // one wave of tree CTAs over the SMs
-    const int by_agents = (int)(b->N / 16) > 0 ? (int)(b->N / 16) : 1;
-    if (p > by_agents) p = by_agents;
-    if (p > 32) p = 32;
-    return p <= 1 ? 0 : p;
+    if (b->N < 16) return 0;
+    const int by_agents = (int)(b->N / 16);
+    if (b->E < 148) {                                            // one wave of tree CTAs over the SMs
+        int p = (int)(148 / b->E);
+        if (p > by_agents) p = by_agents;
+        if (p > 32) p = 32;
+        return p <= 1 ? 0 : p;
+    }
+    int ctas = 1;
+    make_obs_layout(b, obs_threads(b), OBS_FUSED, 0, &ctas);
+    const double waves = (double)b->E / (148.0 * ctas), frac = waves - (double)(long long)waves;
+    const bool whole_waves = waves >= 0.95 && (frac <= 0.03 || frac >= 0.95);
+    if (whole_waves && b->N >= 32) return 0;
+    return by_agents >= 2 ? 2 : 0;
 }
 
 // threads per CTA of the tree kernel: one warp per agent at a time; enough warps to cover its share of the agents
@@ -421,7 +432,7 @@ int fl_batch_slice(const FlBatch *b, int64_t e0, int64_t n, FlBatch *out) {
     FL_ADV(rc, N * 2) FL_ADV(old_rc, N * 2) FL_ADV(dir, N) FL_ADV(old_dir, N) FL_ADV(state, N) FL_ADV(ctr, N) FL_ADV(mal, N)
     FL_ADV(saved, N) FL_ADV(sig_mal, N) FL_ADV(deadlocked, N) FL_ADV(done, N) FL_ADV(nmal, N) FL_ADV(arrival, N)
     FL_ADV(elapsed, 1) FL_ADV(sched_pos, 1) FL_ADV(done_all, 1) FL_ADV(status, 1)
-    FL_ADV(stats, 4) FL_ADV(entries, b->ent_cap) FL_ADV(segs, b->seg_stride) FL_ADV(debug_clocks, 32) FL_ADV(obs_ws, b->ws_stride) FL_ADV(chain_cache, b->chain_stride)
+    FL_ADV(stats, 4) FL_ADV(entries, b->ent_cap) FL_ADV(segs, b->seg_stride) FL_ADV(debug_clocks, 32) FL_ADV(obs_ws, b->ws_stride)
 #undef FL_ADV
     return FL_OK;
 }

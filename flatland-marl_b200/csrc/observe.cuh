@@ -386,7 +386,8 @@ k_observe(FlBatch b, ObsLayout lay, float *__restrict__ out_attr, float *__restr
     // the workspace: it is written with plain stores and read twice per visited cell with independent loads
     uint2 *bm = lay.bm >= 0 ? reinterpret_cast<uint2 *>(smraw + lay.bm)
                             : reinterpret_cast<uint2 *>(b.obs_ws + (size_t)e * b.ws_stride + lay.ws_idx / 4 + 2 * (SS / 4) + 4);
-    const uint2 *bm_r = bm;
+    const bool bm_smem = lay.bm >= 0;               // reads and atomics go through typed shared-memory accesses when they can
+    uint2 *const bm_s = reinterpret_cast<uint2 *>(smraw + (bm_smem ? lay.bm : 0));
     uint2 *sq = reinterpret_cast<uint2 *>(smraw + lay.sq) + warp * 64;       // this warp's queue of cells that need the full conflict check
     uint32_t *s_part = reinterpret_cast<uint32_t *>(smraw + lay.part);
     uint64_t *bar = reinterpret_cast<uint64_t *>(smraw + lay.bar);
@@ -621,33 +622,15 @@ k_observe(FlBatch b, ObsLayout lay, float *__restrict__ out_attr, float *__restr
                                                                       // agent | first path index << 10 | direction after << 19 | last << 21
         uint2 *pool_g = reinterpret_cast<uint2 *>(b.segs) + (size_t)e * b.seg_stride;   // segments beyond the shared-memory pool
         const int seg_gcap = b.segs ? (int)b.seg_stride : 0;
-        // The chain of an agent is a function of its start state alone (and of static data), and most trains stand still from
-        // one step to the next (waiting to depart, stopped, deadlocked): FlBatch.chain_cache keeps every agent's last chain
-        // ([E][N][CHAIN_SLOTS] uint2: slot 0 = start state | 1 << 31, number of segments; then the segment records), so that
-        // following the chain again — one dependent, mostly DRAM-missing load per walk — is only needed after a move.
-        constexpr int CHAIN_SLOTS = 64;
-        uint2 *chain = b.chain_cache ? reinterpret_cast<uint2 *>(b.chain_cache) + (size_t)e * b.chain_stride : nullptr;
-        int *job_pos = A.cellid, *job_n = A.initcell;           // free since phase 1: where a cached chain goes in the pool
         for (int i = tid; i < N; i += NW) {
             const uint32_t info = A.info[i];
             const unsigned slot = (info >> 8) & 0xFFFFu;
             unsigned sid = A.sid0[i];
-            job_pos[i] = -1;
             if (sid == 0xFFFFu) continue;
-            uint2 *cc = chain ? chain + (size_t)i * CHAIN_SLOTS : nullptr;
-            if (cc) {
-                const uint2 hd = cc[0];
-                if (hd.x == (sid | 0x80000000u)) {                                // cached: copied below by a warp
-                    job_pos[i] = atomicAdd(&s_misc[0], (int)hd.y);
-                    job_n[i] = (int)hd.y;
-                    continue;
-                }
-            }
-            const unsigned sid_start = sid;
             const int tpc = (int)(info >> 24);
             const uint32_t *gt = gtab + (size_t)slot * SS;
             unsigned dp = sid & 3u;
-            int kk = 0, cnt = 0;
+            int kk = 0;
             const bool stuck = sdist[(size_t)slot * SS + sid] == FL_DIST_INF;   // no move lowers the distance: a single element
             while (true) {
                 const uint32_t g = stuck ? 0xFFFFu : gt[sid];
@@ -657,27 +640,11 @@ k_observe(FlBatch b, ObsLayout lay, float *__restrict__ out_attr, float *__restr
                                              (unsigned)i | ((unsigned)kk << 10) | ((nxt & 3u) << 19) | ((nxt == 0xFFFFu ? 1u : 0u) << 21));
                 if (pos < lay.seg_cap) pool[pos] = rec;
                 else if (pos - lay.seg_cap < seg_gcap) pool_g[pos - lay.seg_cap] = rec;
-                cnt++;
-                if (cc && cnt < CHAIN_SLOTS) cc[cnt] = rec;
                 kk += (int)kend + 1;
                 if (nxt == 0xFFFFu || kk > FL_PRED_DEPTH || 1 + (kk - 1) * tpc >= NPRED) break;
                 dp = g >> 30; sid = nxt;
             }
-            if (cc) cc[0] = cnt < CHAIN_SLOTS ? make_uint2(sid_start | 0x80000000u, (unsigned)cnt) : make_uint2(0u, 0u);
         }
-        named_bar_sync(1, NW);
-        if (chain)
-            for (int i = warp; i < N; i += NW / 32) {          // cached chains into the pool, a warp per agent, coalesced
-                const int pos = job_pos[i], n = job_n[i];
-                if (pos < 0) continue;
-                const uint2 *cc = chain + (size_t)i * CHAIN_SLOTS + 1;
-                for (int k = lane; k < n; k += 32) {
-                    const uint2 rec = cc[k];
-                    const int q = pos + k;
-                    if (q < lay.seg_cap) pool[q] = rec;
-                    else if (q - lay.seg_cap < seg_gcap) pool_g[q - lay.seg_cap] = rec;
-                }
-            }
         named_bar_sync(1, NW);
         const int n_seg = s_misc[0];
         if (dbg && tid == 0) dbg[11] = n_seg;
@@ -739,31 +706,50 @@ k_observe(FlBatch b, ObsLayout lay, float *__restrict__ out_attr, float *__restr
                 // flat list, c = kk | kend << 9 | tpc << 23, d = the segment record's second word (agent, next direction, last),
                 // e = direction before the segment
                 const uint32_t rc_ = (uint32_t)kk | ((uint32_t)kend << 9) | ((uint32_t)min(tpc, 255) << 23);
-                for (unsigned base = 0; base < total; base += 32) {
-                    const unsigned f = base + lane;
-                    const int cnt0 = __popc(__ballot_sync(0xFFFFFFFFu, cnt > 0 && off <= base));
-                    const unsigned starts = __reduce_or_sync(0xFFFFFFFFu, (cnt > 0 && off > base && off < base + 32) ? 1u << (off - base) : 0u);
-                    const int rank = cnt0 - 1 + __popc(starts & (0xFFFFFFFFu >> (31 - lane)));
-                    const int owner = f < total ? nth_set_bit(nonempty, rank) : 0;
-                    const uint32_t o_wx = __shfl_sync(0xFFFFFFFFu, wx, owner), o_off = __shfl_sync(0xFFFFFFFFu, off, owner);
-                    const uint32_t o_c = __shfl_sync(0xFFFFFFFFu, rc_, owner), o_y = __shfl_sync(0xFFFFFFFFu, sg.y, owner);
-                    const uint32_t o_dp = __shfl_sync(0xFFFFFFFFu, sg.x >> 30, owner);
-                    if (f < total) {
-                        const int k = (int)(f - o_off), o_kk = (int)(o_c & 511u), o_kend = (int)((o_c >> 9) & 0x3FFFu), o_tpc = (int)(o_c >> 23);
-                        const int idx = o_kk + k;
-                        const unsigned sv = wlist[o_wx + k];
-                        unsigned sn = 0, sp = 0;
-                        if (dirs) {
-                            if (k < o_kend) sn = wlist[o_wx + k + 1];
-                            if (k > 0) sp = wlist[o_wx + k - 1];
+                // four rounds of 32 elements at a time: owners and addresses first, then all loads, then the emits — the loads
+                // of a batch of rounds are in flight together
+                for (unsigned base0 = 0; base0 < total; base0 += 128) {
+                    uint32_t o_off[4], o_c[4], o_y[4], o_dp[4], o_wx[4];
+                    unsigned sv[4], sn[4], sp[4];
+#pragma unroll
+                    for (int r = 0; r < 4; r++) {
+                        const unsigned base = base0 + 32u * r, f = base + lane;
+                        if (base >= total) { o_off[r] = 0; o_c[r] = 0; o_y[r] = 0; o_dp[r] = 0; o_wx[r] = 0; continue; }   // warp-uniform
+                        const int cnt0 = __popc(__ballot_sync(0xFFFFFFFFu, cnt > 0 && off <= base));
+                        const unsigned starts = __reduce_or_sync(0xFFFFFFFFu, (cnt > 0 && off > base && off < base + 32) ? 1u << (off - base) : 0u);
+                        const int rank = cnt0 - 1 + __popc(starts & (0xFFFFFFFFu >> (31 - lane)));
+                        const int owner = f < total ? nth_set_bit(nonempty, rank) : 0;
+                        o_wx[r] = __shfl_sync(0xFFFFFFFFu, wx, owner); o_off[r] = __shfl_sync(0xFFFFFFFFu, off, owner);
+                        o_c[r] = __shfl_sync(0xFFFFFFFFu, rc_, owner); o_y[r] = __shfl_sync(0xFFFFFFFFu, sg.y, owner);
+                        o_dp[r] = __shfl_sync(0xFFFFFFFFu, sg.x >> 30, owner);
+                    }
+#pragma unroll
+                    for (int r = 0; r < 4; r++) {
+                        const unsigned f = base0 + 32u * r + lane;
+                        sv[r] = 0; sn[r] = 0; sp[r] = 0;
+                        if (f < total) {
+                            const int k = (int)(f - o_off[r]), o_kend = (int)((o_c[r] >> 9) & 0x3FFFu);
+                            sv[r] = wlist[o_wx[r] + k];
+                            if (dirs) {
+                                if (k < o_kend) sn[r] = wlist[o_wx[r] + k + 1];
+                                if (k > 0) sp[r] = wlist[o_wx[r] + k - 1];
+                            }
                         }
-                        const int t0 = idx ? 1 + (idx - 1) * o_tpc : 0;
-                        const bool last = (k == o_kend && ((o_y >> 21) & 1u)) || idx >= FL_PRED_DEPTH;
-                        const int d = (int)(sv & 3u), dn = last ? d : (k < o_kend ? (int)(sn & 3u) : (int)((o_y >> 19) & 3u));
-                        const int dp = k > 0 ? (int)(sp & 3u) : (int)o_dp;
-                        const int t1 = last ? NPRED - 1 : min(idx ? idx * o_tpc : 0, NPRED - 1);
-                        const int ag = (int)(o_y & 1023u);
-                        emit((sv & 0xFFFFu) >> 2, t0, t1, dirs ? pack_entry(ag, t0, t1, d, dp, dn, entry_extra((int)(A.info[ag] >> 24), (A.info[ag] >> 5) & 1u)) : 0u);
+                    }
+#pragma unroll
+                    for (int r = 0; r < 4; r++) {
+                        const unsigned f = base0 + 32u * r + lane;
+                        if (f < total) {
+                            const int k = (int)(f - o_off[r]), o_kk = (int)(o_c[r] & 511u), o_kend = (int)((o_c[r] >> 9) & 0x3FFFu), o_tpc = (int)(o_c[r] >> 23);
+                            const int idx = o_kk + k;
+                            const int t0 = idx ? 1 + (idx - 1) * o_tpc : 0;
+                            const bool last = (k == o_kend && ((o_y[r] >> 21) & 1u)) || idx >= FL_PRED_DEPTH;
+                            const int d = (int)(sv[r] & 3u), dn = last ? d : (k < o_kend ? (int)(sn[r] & 3u) : (int)((o_y[r] >> 19) & 3u));
+                            const int dp = k > 0 ? (int)(sp[r] & 3u) : (int)o_dp[r];
+                            const int t1 = last ? NPRED - 1 : min(idx ? idx * o_tpc : 0, NPRED - 1);
+                            const int ag = (int)(o_y[r] & 1023u);
+                            emit((sv[r] & 0xFFFFu) >> 2, t0, t1, dirs ? pack_entry(ag, t0, t1, d, dp, dn, entry_extra((int)(A.info[ag] >> 24), (A.info[ag] >> 5) & 1u)) : 0u);
+                        }
                     }
                 }
             }
@@ -811,8 +797,9 @@ k_observe(FlBatch b, ObsLayout lay, float *__restrict__ out_attr, float *__restr
             for (int wd = sa >> 5; wd <= sb >> 5; wd++) {
                 const int lo_b = max(sa - 32 * wd, 0), hi_b = min(sb - 32 * wd, 31);
                 const uint32_t m = (0xFFFFFFFFu >> (31 - hi_b)) & (0xFFFFFFFFu << lo_b);
-                const uint32_t twice = atomicOr(&bm[key * 4 + wd].x, m) & m;     // slots that already had an entry
-                if (twice) atomicOr(&bm[key * 4 + wd].y, twice);
+                uint2 *w2 = (bm_smem ? bm_s : bm) + key * 4 + wd;
+                const uint32_t twice = (bm_smem ? atomicOr(&bm_s[key * 4 + wd].x, m) : atomicOr(&w2->x, m)) & m;     // slots that already had an entry
+                if (twice) { if (bm_smem) atomicOr(&bm_s[key * 4 + wd].y, twice); else atomicOr(&w2->y, twice); }
             }
         };
         if (pooled) { if (lay.flat_walk & 2) emit_pool_flat(true, scatter_emit); else for (int j = tid; j < n_seg; j += NW) emit_segment(j, scatter_emit); }
@@ -1121,7 +1108,8 @@ k_observe(FlBatch b, ObsLayout lay, float *__restrict__ out_attr, float *__restr
                     if (pt < NPRED && tot < NPRED) {                                 // treeobs.cpp:379-465
                         const unsigned bk = kcls ? (unsigned)kcls[rail] : rail;    // the reference's position key c*W + r
                         const int sa = max(0, pt - 1) >> 2, sb = min(NPRED - 1, pt + 1) >> 2;
-                        const uint2 wa = bm_r[bk * 4 + (sa >> 5)], wb = bm_r[bk * 4 + (sb >> 5)];
+                        const uint2 wa = bm_smem ? bm_s[bk * 4 + (sa >> 5)] : bm[bk * 4 + (sa >> 5)];
+                        const uint2 wb = bm_smem ? bm_s[bk * 4 + (sb >> 5)] : bm[bk * 4 + (sb >> 5)];
                         // On the own path the observer's own entry (path element tot, rows t0o..t1o) is in the index too: a slot it
                         // covers needs a second entry to matter.  (t1o is a lower bound for the last element: errs towards checking.)
                         bool own_a = false, own_b = false;

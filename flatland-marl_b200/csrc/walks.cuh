@@ -116,8 +116,6 @@ __global__ void __launch_bounds__(NT) k_walks(FlBatch b, const int32_t *__restri
     int32_t *tot = b.walk_total + (size_t)e * 4;
 
     for (int k = tid; k < (HW + 31) / 32; k += NT) s_tbits[k] = 0;
-    if (FILL && b.chain_cache)                       // a new world: the cached chains of its agents (observe.cuh phase 3) are void
-        for (int i = tid; i < (int)b.N; i += NT) b.chain_cache[(size_t)e * b.chain_stride + (size_t)i * 64] = 0ull;
     __syncthreads();
     for (int s = tid; s < (int)b.n_slots; s += NT) {
         const int r = b.slot_rc[((size_t)e * b.n_slots + s) * 2], c = b.slot_rc[((size_t)e * b.n_slots + s) * 2 + 1];

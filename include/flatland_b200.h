@@ -81,7 +81,6 @@ typedef struct FlBatch {
     int64_t whits_stride;  /* uint32 elements per env of whits, multiple of 4 */
     int64_t seg_stride;    /* uint64 elements per env of segs (0 = none) */
     int64_t ws_stride;     /* uint32 elements per env of obs_ws: >= fl_observe_ws_words(b), multiple of 4 (0 = none: fused kernel only) */
-    int64_t chain_stride;  /* uint64 elements per env of chain_cache: N * 64 (0 = none) */
 
     /* ---- world, static after upload (RailEnv.reset generators stay reference Python) ---- */
     const uint16_t *grid;      /* [E][grid_stride] transition bitmask per cell (core/transition_map.py:144) */
@@ -150,9 +149,6 @@ typedef struct FlBatch {
     uint32_t *obs_ws;     /* [E][ws_stride] split launch of fl_observe (k_observe as two kernels, see csrc/observe.cuh): the
                                        prediction index of an environment between the index kernel and the tree kernel.
                                        NULL = fl_observe always runs the fused kernel */
-    uint64_t *chain_cache;/* [E][chain_stride] per agent 64 slots: the chain of walk segments of its last predicted path, keyed by its
-                                       start state (csrc/observe.cuh phase 3); zero-initialised by the caller, cleared for an
-                                       environment by fl_walk_tables(fill) (new world).  NULL = every chain is followed every step */
 } FlBatch;
 
 int fl_abi_version(void);
