@@ -14,7 +14,7 @@ POLICY_SRC = os.path.join(POLICY_DIR, "policy.cu")
 POLICY_HDR = os.path.join(ROOT, "include", "flatland_policy_b200.h")
 POLICY_LIB = os.path.join(POLICY_DIR, "libflatland_policy_b200.so")
 
-NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+NVCC_FLAGS = ["--split-compile", "0", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "--expt-extended-lambda", "-Xcompiler", "-fPIC", "-shared"]
 
 

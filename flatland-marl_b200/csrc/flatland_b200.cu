@@ -97,10 +97,10 @@ int align_up(int v, int a) { return (v + a - 1) / a * a; }
 
 // Plan overrides (fl_observe_override; tuning and tests only).  -1 = default.  Seeded once from FL_OBS_<KEY> environment
 // variables when the library is loaded; the launch path reads these atomics, never the environment.
-enum ObsKnob : int { KNOB_NT = 0, KNOB_CTAS, KNOB_TABLES, KNOB_SEGCAP, KNOB_ENTCAP, KNOB_SORTSMALL, KNOB_PARTS, KNOB_BMGLOBAL, KNOB_TREENT, KNOB_FLATWALK, KNOB_COUNT };
-const char *const kKnobNames[KNOB_COUNT] = {"nt", "ctas", "tables", "segcap", "entcap", "sortsmall", "parts", "bmglobal", "treent", "flatwalk"};
+enum ObsKnob : int { KNOB_NT = 0, KNOB_CTAS, KNOB_TABLES, KNOB_SEGCAP, KNOB_ENTCAP, KNOB_SORTSMALL, KNOB_PARTS, KNOB_BMGLOBAL, KNOB_TREENT, KNOB_FLATWALK, KNOB_GROUP, KNOB_COUNT };
+const char *const kKnobNames[KNOB_COUNT] = {"nt", "ctas", "tables", "segcap", "entcap", "sortsmall", "parts", "bmglobal", "treent", "flatwalk", "group"};
 const char *const kKnobEnv[KNOB_COUNT] = {"FL_OBS_NT", "FL_OBS_CTAS", "FL_OBS_TABLES", "FL_OBS_SEGCAP", "FL_OBS_ENTCAP", "FL_OBS_SORTSMALL", "FL_OBS_PARTS",
-                                          "FL_OBS_BMGLOBAL", "FL_OBS_TREENT", "FL_OBS_FLATWALK"};
+                                          "FL_OBS_BMGLOBAL", "FL_OBS_TREENT", "FL_OBS_FLATWALK", "FL_OBS_GROUP"};
 std::atomic<int> g_knob[KNOB_COUNT];
 struct KnobInit {
     KnobInit() {
@@ -119,7 +119,9 @@ int knob(int k) { return g_knob[k].load(std::memory_order_relaxed); }
 // count for which the core fits (more resident warps hide the latency of the table lookups, which then go to L2).
 // What is left of the budget takes the static walk tables in the order of their use per visited cell.
 // fl_observe_override("ctas" / "tables" / "nt", ...) override (tuning only).
-ObsLayout make_obs_layout(const FlBatch *b, int nt, int mode, int parts, int *ctas_out = nullptr) {
+// group > 1: the plan of ONE environment of a group-mode CTA (k_observe<..., G>): `group` copies of it, each a multiple of
+// 128 bytes, share the CTA's shared memory.
+ObsLayout make_obs_layout(const FlBatch *b, int nt, int mode, int parts, int *ctas_out = nullptr, int group = 1) {
     const int N = (int)b->N, Rmax = (int)(b->state_stride / 4), Np = (N + 3) & ~3;
     ObsLayout L;
     int off = 0;
@@ -129,7 +131,7 @@ ObsLayout make_obs_layout(const FlBatch *b, int nt, int mode, int parts, int *ct
     // FlBatch.obs_ws of the split launch: [header 16 B | six agent arrays] [occupancy words | bucket offsets | filter]
     L.ws_ag = 0; L.ws_ag_bytes = (4 + 6 * Np) * 4;
     L.ws_idx = L.ws_ag_bytes; L.ws_idx_bytes = Rmax * 4 + (Rmax + 4) * 4 + Rmax * 32;
-    L.bar = take(32);
+    L.bar = take(16 + 4 * OBS_MISC_WORDS);                     // mbarrier, then the scalars of the environment
     L.part = take(128);                                         // one scan partial per warp
     L.ag = take(mode == OBS_TREES ? (long long)L.ws_ag_bytes : (long long)(4 + 6 * Np + 5 * N) * 4);
     L.dl = mode == OBS_TREES ? 0 : take(26 * N + 8);
@@ -164,8 +166,9 @@ ObsLayout make_obs_layout(const FlBatch *b, int nt, int mode, int parts, int *ct
     if (!ctas)
         for (int c = max_ctas; c >= 1; c--)
             if (core <= SMEM_MAX / c - 1024 || c == 1) { ctas = c; break; }
+    if (group > 1) ctas = group;
     if (ctas_out) *ctas_out = ctas;
-    const int budget = SMEM_MAX / ctas - 1024;
+    const int budget = group > 1 ? (((SMEM_MAX - 1024) / group) & ~127) : SMEM_MAX / ctas - 1024;
     auto opt = [&](long long bytes) { if ((long long)off + bytes + 16 > budget) return -1; return take(bytes); };
     L.ridx = opt(ridx_b);
     long long reserve = ent_typ + 16;                            // keep room for the entries while placing the tables
@@ -191,7 +194,7 @@ ObsLayout make_obs_layout(const FlBatch *b, int nt, int mode, int parts, int *ct
     if (knob(KNOB_SORTSMALL) >= 1) L.sort_small = knob(KNOB_SORTSMALL);
     L.seg_cap = seg_cap_use;                                    // to force the per-agent path walk and the global spill of the entries
     if (knob(KNOB_ENTCAP) >= 0 && knob(KNOB_ENTCAP) < L.ent_cap) L.ent_cap = knob(KNOB_ENTCAP);
-    L.total = off;
+    L.total = group > 1 ? align_up(off, 128) : off;
     return L;
 }
 
@@ -233,7 +236,31 @@ int obs_parts(const FlBatch *b) {
     const double waves = (double)b->E / (148.0 * ctas), frac = waves - (double)(long long)waves;
     const bool whole_waves = waves >= 0.95 && (frac <= 0.03 || frac >= 0.95);
     if (whole_waves && b->N >= 32) return 0;
-    return by_agents >= 2 ? 2 : 0;
+    // Test_02 (8192 x 20 agents): split 140 M agent-steps/s against 102-117 M fused (profiles/r02_g_sweep.txt, r02_h_sweep.txt)
+    return b->N >= 20 ? 2 : 0;
+}
+
+// Environments per CTA of the fused kernel (group mode, observe.cuh; 1 = one CTA per environment).  As many as the
+// one-CTA-per-environment plan would put on an SM, so that the launch shape on the chip is the same and only the tree
+// phase is shared; needs the fused plan (no split launch) and at least one full group per SM.
+int obs_group(const FlBatch *b, int nt) {
+    const int v = knob(KNOB_GROUP);
+    if (v == 0 || v == 1) return 1;
+    int ctas = 1;
+    make_obs_layout(b, nt, OBS_FUSED, 0, &ctas);
+    int g = v > 1 ? v : ctas;
+    if (g > 7) g = 7;
+    while (g > 1 && g * nt > 1024) g--;
+    if (nt == 128) { if (g < 4) return 1; }
+    else if (nt == 256) { if (g < 2) return 1; }
+    else if (nt == 64) { if (g < 7) return 1; }
+    else return 1;
+    {   // the mandatory regions + typical entries must fit the group's per-environment budget
+        const ObsLayout L = make_obs_layout(b, nt, OBS_FUSED, 0, nullptr, g);
+        if (L.total * g > SMEM_MAX - 1024 || L.ent_cap < (int)b->N * 8) return 1;
+    }
+    if (v > 1) return g;
+    return 1;                                                   // default: off until measured (profiles/)
 }
 
 // threads per CTA of the tree kernel: one warp per agent at a time; enough warps to cover its share of the agents
@@ -391,22 +418,33 @@ int fl_observe(const FlBatch *b, float *d_agent_attr, float *d_forest, int32_t *
         return FL_K(1024, 1);
 #undef FL_K
     };
-    auto launch = [&](int mode, int nt, int parts, int kid) -> int {
+    auto pick_group = [](int nt, int g) -> Kern {
+        if (nt == 128) return g == 7 ? (Kern)k_observe<128, 1, OBS_FUSED, 7> : g == 6 ? (Kern)k_observe<128, 1, OBS_FUSED, 6>
+                            : g == 5 ? (Kern)k_observe<128, 1, OBS_FUSED, 5> : (Kern)k_observe<128, 1, OBS_FUSED, 4>;
+        if (nt == 256) return g == 3 ? (Kern)k_observe<256, 1, OBS_FUSED, 3> : (Kern)k_observe<256, 1, OBS_FUSED, 2>;
+        return (Kern)k_observe<64, 1, OBS_FUSED, 7>;
+    };
+    auto launch = [&](int mode, int nt, int parts, int kid, int group = 1) -> int {
         int ctas = 1;
-        const ObsLayout lay = make_obs_layout(b, nt, mode, parts, &ctas);
-        if (lay.total > SMEM_MAX) return FL_ERR_SMEM;
-        Kern kern = pick(nt, ctas, mode);
-        if (lay.total > 48 * 1024) {
-            cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, lay.total);
+        const ObsLayout lay = make_obs_layout(b, nt, mode, parts, &ctas, group);
+        const int smem = lay.total * group;
+        if (smem > SMEM_MAX) return FL_ERR_SMEM;
+        Kern kern = group > 1 ? pick_group(nt, group) : pick(nt, ctas, mode);
+        if (smem > 48 * 1024) {
+            cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
             if (err != cudaSuccess) return (int)err;
         }
         LaunchScope ls(kid, st);
-        kern<<<(unsigned)(b->E * (mode == OBS_TREES ? parts : 1)), nt, lay.total, st>>>(*b, lay, d_agent_attr, d_forest, d_adjacency, d_node_order,
-                                                                                       d_edge_order, d_valid_actions, d_dist_target);
+        const unsigned grid = group > 1 ? (unsigned)((b->E + group - 1) / group) : (unsigned)(b->E * (mode == OBS_TREES ? parts : 1));
+        kern<<<grid, nt * group, smem, st>>>(*b, lay, d_agent_attr, d_forest, d_adjacency, d_node_order, d_edge_order, d_valid_actions,
+                                             d_dist_target);
         return finish(cudaGetLastError());
     };
     const int parts = obs_parts(b);
-    if (parts == 0) return launch(OBS_FUSED, obs_threads(b), 0, K_OBSERVE);
+    if (parts == 0) {
+        const int nt = obs_threads(b);
+        return launch(OBS_FUSED, nt, 0, K_OBSERVE, obs_group(b, nt));
+    }
     if (b->ws_stride < fl_observe_ws_words(b)) return FL_ERR_BAD_ARG;
     if (int rc = launch(OBS_INDEX, obs_threads(b), parts, K_OBSERVE_INDEX)) return rc;
     return launch(OBS_TREES, tree_threads(b, parts), parts, K_OBSERVE_TREES);
@@ -627,8 +665,9 @@ int fl_observe_plan(const FlBatch *b, int32_t *out, int n_out) {
     if (int rc = check_batch(b)) return rc;
     if (!out || n_out < 20) return FL_ERR_BAD_ARG;
     const int nt = obs_threads(b), parts = obs_parts(b);
+    const int group = parts ? 1 : obs_group(b, nt);
     int ctas = 1;
-    const ObsLayout L = make_obs_layout(b, nt, parts ? OBS_INDEX : OBS_FUSED, parts, &ctas);
+    const ObsLayout L = make_obs_layout(b, nt, parts ? OBS_INDEX : OBS_FUSED, parts, &ctas, group);
     const int v[20] = {nt, L.total, ctas, L.ent_cap, L.kcls, L.grid, L.ci, L.ks, L.ent, L.sdist,
                        L.ridx, L.srec, L.wrec, L.whoff, L.wlist, L.ag, L.dl, L.part, SMEM_MAX / (L.total + 1024), L.whits};
     for (int k = 0; k < 20; k++) out[k] = v[k];
@@ -638,6 +677,7 @@ int fl_observe_plan(const FlBatch *b, int32_t *out, int n_out) {
         const ObsLayout T = parts ? make_obs_layout(b, tnt, OBS_TREES, parts, &tctas) : L;
         out[20] = parts; out[21] = tnt; out[22] = parts ? T.total : 0; out[23] = tctas;
     }
+    if (n_out >= 25) out[24] = group;                           // environments per CTA of the fused kernel
     return FL_OK;
 }
 

@@ -51,6 +51,14 @@ struct ObsLayout {   // byte offsets into dynamic shared memory (host: make_obs_
 // copies and walks the trees of every parts-th agent.  Few large environments (Test_14: 64 x 425 agents) then fill the
 // chip, and many small ones are cut into more, smaller units of work than there are CTA slots.
 enum : int { OBS_FUSED = 0, OBS_INDEX = 1, OBS_TREES = 2 };
+// The fused kernel also runs as a GROUP (template parameter G > 1): one CTA of G x NT threads holds G environments side by
+// side — G copies of the shared-memory plan, the index phases of each behind its own pair of named barriers — and the tree
+// phase takes (environment, agent) pairs from all of them: a warp whose own environment has no agent left walks the trees
+// of its neighbours.  With one CTA per environment the warps of an environment that finishes early leave the SM while the
+// slowest environment of the SM (the launch is one wave) runs on at a quarter of the SM's issue rate; as a group the SM's
+// warps stay busy until all of its environments are done.
+constexpr int OBS_MISC_WORDS = 8;   // [0] path segments, then entries  [1] next agent of phase 4  [2] max rows per cell  [3] bad cell met
+                                    // [4] group mode: the index is complete, trees may be taken by any warp of the CTA
 
 // ---- mbarrier + 1-D TMA bulk copy (global -> shared), sm_90+ ------------------------------------
 DEVI uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -324,6 +332,52 @@ struct ObsAgents {
     uint32_t *m0, *m1;  // attribute entries 0..63 as bits (feature_parser.cpp:19-77), entry 41 (deadlocked) left out
 };
 
+DEVI ObsAgents obs_agents_at(uint32_t *ws_hdr, int N) {
+    const int Np = (N + 3) & ~3;
+    ObsAgents A;
+    uint32_t *p = ws_hdr + 4;
+    A.vrc = p; p += Np; A.sid0 = p; p += Np; A.info = p; p += Np;
+    A.speed = reinterpret_cast<float *>(p); p += Np; A.dt = reinterpret_cast<float *>(p); p += Np;
+    A.rec_b = p; p += Np;
+    A.cellid = reinterpret_cast<int *>(p); p += N; A.initcell = reinterpret_cast<int *>(p); p += N;
+    A.rec_a = p; p += N; A.m0 = p; p += N; A.m1 = p; p += N;
+    return A;
+}
+
+// What the tree phase reads of one environment: static tables (shared-memory copy when the layout has room, else global
+// memory), the prediction index and the agent block.  Group mode builds it for whichever environment of the CTA an agent
+// belongs to.
+struct ObsEnv {
+    const uint16_t *ridx, *sdist, *kcls;
+    const uint4 *wrec;
+    const uint32_t *whoff, *whits, *wlist, *gtab;
+    uint32_t *ci, *ks, *ent_s, *ent_g;
+    uint2 *bm, *bm_s;
+    int *misc;
+    ObsAgents A;
+};
+DEVI ObsEnv obs_env_of(const FlBatch &b, const ObsLayout &lay, unsigned char *sm, int e) {
+    const int SS = (int)b.state_stride;
+    ObsEnv V;
+    V.ridx = lay.ridx >= 0 ? reinterpret_cast<const uint16_t *>(sm + lay.ridx) : b.ridx + (size_t)e * b.ridx_stride;
+    V.wrec = lay.wrec >= 0 ? reinterpret_cast<const uint4 *>(sm + lay.wrec) : reinterpret_cast<const uint4 *>(b.wrec) + (size_t)e * SS;
+    V.whoff = lay.whoff >= 0 ? reinterpret_cast<const uint32_t *>(sm + lay.whoff) : b.whoff + (size_t)e * SS;
+    V.whits = lay.whits >= 0 ? reinterpret_cast<const uint32_t *>(sm + lay.whits) : b.whits + (size_t)e * b.whits_stride;
+    V.wlist = lay.wlist >= 0 ? reinterpret_cast<const uint32_t *>(sm + lay.wlist) : b.wlist + (size_t)e * b.wlist_stride;
+    V.sdist = lay.sdist >= 0 ? reinterpret_cast<const uint16_t *>(sm + lay.sdist) : b.sdist + (size_t)e * b.n_slots * SS;
+    V.kcls = lay.kcls >= 0 ? reinterpret_cast<const uint16_t *>(sm + lay.kcls) : nullptr;   // only when H > W
+    V.gtab = b.gtab + (size_t)e * b.n_slots * SS;
+    V.ci = reinterpret_cast<uint32_t *>(sm + lay.ci);
+    V.ks = reinterpret_cast<uint32_t *>(sm + lay.ks) + 1;
+    V.bm_s = reinterpret_cast<uint2 *>(sm + (lay.bm >= 0 ? lay.bm : 0));
+    V.bm = lay.bm >= 0 ? V.bm_s : reinterpret_cast<uint2 *>(b.obs_ws + (size_t)e * b.ws_stride + lay.ws_idx / 4 + 2 * (SS / 4) + 4);
+    V.ent_s = reinterpret_cast<uint32_t *>(sm + lay.ent);
+    V.ent_g = b.entries + (size_t)e * b.ent_cap;
+    V.misc = reinterpret_cast<int *>(sm + lay.bar + 16);
+    V.A = obs_agents_at(reinterpret_cast<uint32_t *>(sm + lay.ag), (int)b.N);
+    return V;
+}
+
 // position of the n-th (0-based) set bit of m; the caller guarantees that m has more than n set bits.  Five popc
 // steps (the __fns intrinsic is a long software loop).
 DEVI int nth_set_bit(unsigned m, int n) {
@@ -347,18 +401,28 @@ DEVI unsigned warp_excl_scan(unsigned v, int lane, unsigned &total) {
     return x - v;
 }
 
-// NT threads per CTA, RES CTAs per SM the register budget is cut for, MODE: OBS_FUSED / OBS_INDEX / OBS_TREES
-template <int NT, int RES, int MODE>
-__global__ void __launch_bounds__(NT, RES)
+// NT threads per environment, RES CTAs per SM the register budget is cut for, MODE: OBS_FUSED / OBS_INDEX / OBS_TREES,
+// G environments per CTA (group mode, fused kernel only; the CTA has G * NT threads)
+template <int NT, int RES, int MODE, int G = 1>
+__global__ void __launch_bounds__(NT * G, RES)
 k_observe(FlBatch b, ObsLayout lay, float *__restrict__ out_attr, float *__restrict__ out_forest,
           int32_t *__restrict__ out_adj, int32_t *__restrict__ out_norder, int32_t *__restrict__ out_eorder,
           uint8_t *__restrict__ out_valid, float *__restrict__ out_dist_target) {
-    const int e = MODE == OBS_TREES ? (int)blockIdx.x / lay.parts : (int)blockIdx.x;
+    static_assert(G == 1 || (MODE == OBS_FUSED && G <= 7 && NT * G <= 1024), "group mode: fused kernel, two named barriers per environment");
+    const int sub = G > 1 ? (int)threadIdx.x / NT : 0;                 // which environment of the group this thread belongs to
+    const int e_raw = MODE == OBS_TREES ? (int)blockIdx.x / lay.parts : (int)blockIdx.x * G + sub;
+    const bool live = G == 1 || e_raw < (int)b.E;                       // the last group may be ragged: its spare threads only walk trees
+    const int e = live ? e_raw : (int)b.E - 1;                          // (addresses only; a spare thread never dereferences them)
     const int part = MODE == OBS_TREES ? (int)blockIdx.x - e * lay.parts : 0, n_parts = MODE == OBS_TREES ? lay.parts : 1;
     const int N = (int)b.N, H = (int)b.H, W = (int)b.W;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tid = (int)threadIdx.x - sub * NT, lane = tid & 31, warp = tid >> 5;
     extern __shared__ __align__(128) unsigned char obs_smem[];
-    unsigned char *const smraw = obs_smem;
+    unsigned char *const smraw = obs_smem + (G > 1 ? (size_t)sub * lay.total : 0);
+    // barriers of one environment: A = all of its NT threads, B = the NT - 32 threads that build the prediction index, C = the
+    // hand-over index -> deadlock warp (arrive / sync over NT).  Group mode has 16 hardware barriers for G environments: C
+    // reuses A (between phase 1 and the hand-over nobody waits on A), 0 stays the CTA-wide barrier.
+    const int BAR_A = G > 1 ? 1 + 2 * sub : 0, BAR_B = G > 1 ? 2 + 2 * sub : 1, BAR_C = G > 1 ? BAR_A : 2;
+    auto env_sync = [&]() { if (G > 1) named_bar_sync(BAR_A, NT); else __syncthreads(); };
     const int R = b.walk_total[(size_t)e * 4] >> 2;         // rail cells of this environment
     const int SS = (int)b.state_stride;
 
@@ -371,23 +435,20 @@ k_observe(FlBatch b, ObsLayout lay, float *__restrict__ out_attr, float *__restr
     const uint32_t *g_whits = b.whits + (size_t)e * b.whits_stride;
     const uint16_t *g_sdist = b.sdist + (size_t)e * b.n_slots * SS;
     const uint32_t *gtab = b.gtab + (size_t)e * b.n_slots * SS;
+    (void)g_srec; (void)g_sdist;
     const uint16_t *grid = lay.grid >= 0 ? reinterpret_cast<const uint16_t *>(smraw + lay.grid) : g_grid;
-    const uint16_t *ridx = lay.ridx >= 0 ? reinterpret_cast<const uint16_t *>(smraw + lay.ridx) : g_ridx;
-    const uint4 *wrec = lay.wrec >= 0 ? reinterpret_cast<const uint4 *>(smraw + lay.wrec) : g_wrec;
-    const uint32_t *whoff = lay.whoff >= 0 ? reinterpret_cast<const uint32_t *>(smraw + lay.whoff) : g_whoff;
-    const uint32_t *whits = lay.whits >= 0 ? reinterpret_cast<const uint32_t *>(smraw + lay.whits) : g_whits;
-    const uint32_t *wlist = lay.wlist >= 0 ? reinterpret_cast<const uint32_t *>(smraw + lay.wlist) : g_wlist;
-    const uint16_t *sdist = lay.sdist >= 0 ? reinterpret_cast<const uint16_t *>(smraw + lay.sdist) : g_sdist;
-    const uint16_t *kcls = lay.kcls >= 0 ? reinterpret_cast<const uint16_t *>(smraw + lay.kcls) : nullptr;   // only when H > W
-    uint32_t *ci = reinterpret_cast<uint32_t *>(smraw + lay.ci);             // [R] occupancy word per rail cell
-    uint32_t *ks = reinterpret_cast<uint32_t *>(smraw + lay.ks) + 1;         // ks[-1..R]: bucket r = [ks[r-1], ks[r])
+    const ObsEnv X = obs_env_of(b, lay, smraw, e);
+    const uint16_t *ridx = X.ridx, *sdist = X.sdist, *kcls = X.kcls;
+    const uint4 *wrec = X.wrec;
+    const uint32_t *whoff = X.whoff, *whits = X.whits, *wlist = X.wlist;
+    uint32_t *ci = X.ci;                            // [R] occupancy word per rail cell
+    uint32_t *ks = X.ks;                            // ks[-1..R]: bucket r = [ks[r-1], ks[r])
     // [R][4] bit s of .x / .y: at least one / two prediction entries of the key overlap rows 4s..4s+3.  In shared memory, or —
     // when its 32 bytes per rail cell do not fit beside the mandatory regions (lay.bm < 0: large worlds) — in its place in
     // the workspace: it is written with plain stores and read twice per visited cell with independent loads
-    uint2 *bm = lay.bm >= 0 ? reinterpret_cast<uint2 *>(smraw + lay.bm)
-                            : reinterpret_cast<uint2 *>(b.obs_ws + (size_t)e * b.ws_stride + lay.ws_idx / 4 + 2 * (SS / 4) + 4);
+    uint2 *bm = X.bm;
     const bool bm_smem = lay.bm >= 0;               // reads and atomics go through typed shared-memory accesses when they can
-    uint2 *const bm_s = reinterpret_cast<uint2 *>(smraw + (bm_smem ? lay.bm : 0));
+    uint2 *const bm_s = X.bm_s;
     uint2 *sq = reinterpret_cast<uint2 *>(smraw + lay.sq) + warp * 64;       // this warp's queue of cells that need the full conflict check
     uint32_t *s_part = reinterpret_cast<uint32_t *>(smraw + lay.part);
     uint64_t *bar = reinterpret_cast<uint64_t *>(smraw + lay.bar);
@@ -397,15 +458,7 @@ k_observe(FlBatch b, ObsLayout lay, float *__restrict__ out_attr, float *__restr
     // reads; the split launch hands exactly this block from the index kernel to the tree kernel
     const int Np = (N + 3) & ~3;
     uint32_t *ws_hdr = reinterpret_cast<uint32_t *>(smraw + lay.ag);
-    ObsAgents A;
-    {
-        uint32_t *p = ws_hdr + 4;
-        A.vrc = p; p += Np; A.sid0 = p; p += Np; A.info = p; p += Np;
-        A.speed = reinterpret_cast<float *>(p); p += Np; A.dt = reinterpret_cast<float *>(p); p += Np;
-        A.rec_b = p; p += Np;
-        A.cellid = reinterpret_cast<int *>(p); p += N; A.initcell = reinterpret_cast<int *>(p); p += N;
-        A.rec_a = p; p += N; A.m0 = p; p += N; A.m1 = p; p += N;
-    }
+    const ObsAgents A = X.A;
     uint32_t *g_ws = b.obs_ws ? b.obs_ws + (size_t)e * b.ws_stride : nullptr;
     DeadlockScratch D;
     {
@@ -418,7 +471,7 @@ k_observe(FlBatch b, ObsLayout lay, float *__restrict__ out_attr, float *__restr
 
     // optional phase timestamps (tuning only): FlBatch.debug_clocks [E][16] int64, NULL = off
     // [E][32]: slots 0..15 of the fused / index kernel, 16.. of the tree kernel of a split launch (its CTA 0 of the environment)
-    int64_t *dbg = b.debug_clocks && part == 0 ? b.debug_clocks + (size_t)e * 32 : nullptr;
+    int64_t *dbg = b.debug_clocks && part == 0 && live ? b.debug_clocks + (size_t)e * 32 : nullptr;
 #define OBS_TICK(k) do { if (dbg && tid == 0) dbg[(MODE == OBS_TREES ? 16 : 0) + (k)] = clock64(); } while (0)
     if (dbg && tid == 0) {
         dbg[MODE == OBS_TREES ? 31 : 15] = clock64();
@@ -429,7 +482,7 @@ k_observe(FlBatch b, ObsLayout lay, float *__restrict__ out_attr, float *__restr
                          lay.whits >= 0 || lay.wlist >= 0 || lay.kcls >= 0 || lay.sdist >= 0;
     uint32_t *ent = reinterpret_cast<uint32_t *>(smraw + lay.ent);
     uint32_t *const ent_s = ent;                   // the shared-memory copy (typed loads are cheaper than generic ones)
-    if (use_tma && tid == 0) {
+    if (use_tma && tid == 0 && live) {
         mbar_init(bar, 1);
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         const uint32_t gb = lay.grid >= 0 ? (uint32_t)(b.grid_stride * 2) : 0u;
@@ -468,7 +521,7 @@ k_observe(FlBatch b, ObsLayout lay, float *__restrict__ out_attr, float *__restr
         if (lb) tma_load_1d(smraw + lay.wlist, g_wlist, lb, bar);
     }
     // zero the bucket counters and the occupancy words
-    if (MODE != OBS_TREES) {
+    if (MODE != OBS_TREES && live) {
         for (int k = tid; k <= R + 1; k += NT) ks[k - 1] = 0;
         for (int k = tid; k < R; k += NT) ci[k] = 0;
         for (int k = tid; k < R * 4; k += NT) bm[k] = make_uint2(0u, 0u);
@@ -476,12 +529,13 @@ k_observe(FlBatch b, ObsLayout lay, float *__restrict__ out_attr, float *__restr
     const float T_ = (float)b.max_steps[e], Nf = (float)N;
     const Scale sc{T_, __frcp_rn(T_), Nf, __frcp_rn(Nf)};
     const int elapsed = b.elapsed[e];
-    if (tid < 4) s_misc[tid] = 0;                  // [0] path segments, then entries, [1] next agent of phase 4, [2] max time per cell, [3] bad cell met
-    __syncthreads();                               // mbarrier initialised, counters zeroed
+    // OBS_MISC_WORDS scalars; a spare environment slot of a ragged group reads "ready, no agent left"
+    if (tid < OBS_MISC_WORDS) s_misc[tid] = live ? 0 : (tid == 1 ? N : tid == 4 ? 1 : 0);
+    __syncthreads();                               // (the whole CTA) mbarrier initialised, counters zeroed
     OBS_TICK(0);
-    if (use_tma) mbar_wait(bar, 0);
+    if (use_tma && live) mbar_wait(bar, 0);
     int tpc_max = 0;
-    if (MODE != OBS_TREES) {
+    if (MODE != OBS_TREES && live) {
 
     // ---- phase 1: loader view (loader.cpp:8-179, 221-327) -----------------------------------------
     for (int i = tid; i < N; i += NT) {
@@ -560,7 +614,7 @@ k_observe(FlBatch b, ObsLayout lay, float *__restrict__ out_attr, float *__restr
             fa[12] = idv == FL_DIST_INF ? 8.0f : (float)idv / max_dist;
         }
     }
-    __syncthreads();
+    env_sync();
     // occupancy word per rail cell (treeobs.cpp:67-92, deadlock_checker.cpp:15-20): the HIGHEST handle standing on the
     // cell (std::map assignment in handle order = last writer) in the top bits so atomicMax picks it, its
     // direction and malfunction flag; then the number of off-map trains whose initial cell it is.
@@ -572,7 +626,7 @@ k_observe(FlBatch b, ObsLayout lay, float *__restrict__ out_attr, float *__restr
                 atomicMax(&ci[ri], ((uint32_t)(i + 1) << 21) | ((A.info[i] & 3u) << 9) | (((A.rec_b[i] >> 17) & 1u) << 8));
         }
     }
-    __syncthreads();
+    env_sync();
     for (int i = tid; i < N; i += NT) {
         const int ic = A.initcell[i];
         if (ic >= 0) {
@@ -580,14 +634,14 @@ k_observe(FlBatch b, ObsLayout lay, float *__restrict__ out_attr, float *__restr
             if (ri != 0xFFFFu && ld_vol_u32(&ci[ri]) != 0) atomicAdd(&ci[ri], 1u << 11);
         }
     }
-    __syncthreads();
+    env_sync();
     // deadlock_checker.cpp:15-20 agent_positions, hoisted out of the serial lane: the highest ACTIVE handle per rail cell (in
     // the still unused bucket counters), then for every active agent the occupant of each neighbour cell its transitions lead to
     {
         uint32_t *ca = ks;                            // ks[0..R) is zero until the counting pass of phase 3
         for (int i = tid; i < N; i += NT)
             if (D.ct[i] & 16) { const unsigned ri = ridx[A.cellid[i]]; if (ri != 0xFFFFu) atomicMax(&ca[ri], (uint32_t)(i + 1)); }
-        __syncthreads();
+        env_sync();
         for (int k = tid; k < N * 4; k += NT) {
             const int i = k >> 2, dd = k & 3;
             int opp = -1;
@@ -600,9 +654,9 @@ k_observe(FlBatch b, ObsLayout lay, float *__restrict__ out_attr, float *__restr
             }
             D.opp[k] = (int16_t)opp;
         }
-        __syncthreads();
+        env_sync();
         for (int k = tid; k < R; k += NT) ca[k] = 0;
-        __syncthreads();
+        env_sync();
     }
     OBS_TICK(1);
 
@@ -612,7 +666,26 @@ k_observe(FlBatch b, ObsLayout lay, float *__restrict__ out_attr, float *__restr
     if (dl_warp) {
         if (lane == 0) { update_deadlocks(D, N); if (dbg) dbg[8] = clock64(); }
         __syncwarp();
-        asm volatile("bar.sync 2, %0;" ::"r"(NT) : "memory");    // the prediction index is complete (the other warps only arrive)
+        if (G > 1) {
+            // group mode has no common end of the tree phase: the sticky flags go back to the agent records and the flag
+            // entries of the attribute vectors (phase 5 below) are written here, by the warp that computed the flags
+            for (int i = lane; i < N; i += 32) b.deadlocked[(size_t)e * N + i] = D.dl[i];
+            float *dst = out_attr + (size_t)e * N * FL_ATTR_F;
+            for (int idx = lane; idx < N * 70; idx += 32) {
+                const int i = idx / 70, k = idx - i * 70;
+                float v;
+                if (k < 64) {
+                    const uint32_t m = k < 32 ? A.m0[i] : A.m1[i];
+                    v = (float)((m >> (k & 31)) & 1u);
+                    if (k == 41) v = D.dl[i] != 0;
+                } else {
+                    const uint32_t ra = A.rec_a[i], rb = A.rec_b[i];
+                    v = k == 64 ? (float)(rb & 1u) : (float)((ra >> (27 + k - 65)) & 1u);
+                }
+                dst[i * FL_ATTR_F + k] = v;
+            }
+        }
+        asm volatile("bar.sync %0, %1;" ::"r"(BAR_C), "r"(NT) : "memory");    // the prediction index is complete (the other warps only arrive)
         if (s_misc[0] > lay.ent_cap) ent = b.entries + (size_t)e * b.ent_cap;
     } else {
         // Predicted paths as segments (predictions.cpp:13-235): a path is a chain of static walks, gtab tells where it
@@ -645,7 +718,7 @@ k_observe(FlBatch b, ObsLayout lay, float *__restrict__ out_attr, float *__restr
                 dp = g >> 30; sid = nxt;
             }
         }
-        named_bar_sync(1, NW);
+        named_bar_sync(BAR_B, NW);
         const int n_seg = s_misc[0];
         if (dbg && tid == 0) dbg[11] = n_seg;
         const bool pooled = n_seg <= lay.seg_cap + seg_gcap;  // else: every lane walks its agent's path itself (predict_path), twice
@@ -763,7 +836,7 @@ k_observe(FlBatch b, ObsLayout lay, float *__restrict__ out_attr, float *__restr
                 const unsigned slot = (info >> 8) & 0xFFFFu, s0 = A.sid0[i];
                 if (s0 != 0xFFFFu) predict_path(wrec, whoff, whits, wlist, sdist + (size_t)slot * SS, s0, slot, (int)(info >> 24), i, entry_extra((int)(info >> 24), (info >> 5) & 1u), count_emit);
             }
-        named_bar_sync(1, NW);
+        named_bar_sync(BAR_B, NW);
         OBS_TICK(2);
         // exclusive scan of ks[0..R] (R+1 values; the last becomes the total)
         const int per = (R + 1 + NW - 1) / NW, lo = min(tid * per, R + 1), hi = min(lo + per, R + 1);
@@ -776,7 +849,7 @@ k_observe(FlBatch b, ObsLayout lay, float *__restrict__ out_attr, float *__restr
             if (lane >= o) incl += y;
         }
         if (lane == 31) s_part[warp] = incl;
-        named_bar_sync(1, NW);
+        named_bar_sync(BAR_B, NW);
         uint32_t run = incl - sum, n_total = 0;
 #pragma unroll
         for (int w2 = 0; w2 < NW / 32; w2++) {
@@ -785,7 +858,7 @@ k_observe(FlBatch b, ObsLayout lay, float *__restrict__ out_attr, float *__restr
             n_total += wt;
         }
         for (int k = lo; k < hi; k++) { const uint32_t v = ks[k]; ks[k] = run; run += v; }
-        named_bar_sync(1, NW);
+        named_bar_sync(BAR_B, NW);
         const int n_ent = (int)n_total;
         if (tid == 0) s_misc[0] = n_ent;
         if (n_ent > lay.ent_cap) ent = b.entries + (size_t)e * b.ent_cap;   // does not fit in shared memory: global spill space
@@ -809,7 +882,7 @@ k_observe(FlBatch b, ObsLayout lay, float *__restrict__ out_attr, float *__restr
                 const unsigned slot = (info >> 8) & 0xFFFFu, s0 = A.sid0[i];
                 if (s0 != 0xFFFFu) predict_path(wrec, whoff, whits, wlist, sdist + (size_t)slot * SS, s0, slot, (int)(info >> 24), i, entry_extra((int)(info >> 24), (info >> 5) & 1u), scatter_emit);
             }
-        named_bar_sync(1, NW);
+        named_bar_sync(BAR_B, NW);
         OBS_TICK(4);
         // order every bucket: long-lived entries first, then by t0, so that the tree walk scans a time window only.
         // Entries in shared memory: buckets up to sort_small by one thread each (insertion sort: 32 buckets per warp at a
@@ -903,7 +976,7 @@ k_observe(FlBatch b, ObsLayout lay, float *__restrict__ out_attr, float *__restr
                 const int pos = atomicAdd(&s_misc[1], 1);
                 if (pos < bigq_cap) bigq[pos] = (uint32_t)key; else insertion_sort(s0, s1);
             }
-            named_bar_sync(1, NW);
+            named_bar_sync(BAR_B, NW);
             OBS_TICK(9);
             const int n_big = min(ld_vol_i32(&s_misc[1]), bigq_cap);
             for (int q = warp; q < n_big; q += NWARPS) {
@@ -933,9 +1006,13 @@ k_observe(FlBatch b, ObsLayout lay, float *__restrict__ out_attr, float *__restr
                 s0b = s0x; nb = nx; vb = vx;
             }
         }
-        named_bar_sync(1, NW);
+        named_bar_sync(BAR_B, NW);
         if (tid == 0) s_misc[1] = 0;                // phase 4 takes its agents from this counter
-        named_bar_sync(1, NW);
+        named_bar_sync(BAR_B, NW);
+        if (G > 1 && tid == 0) {                    // publish: every write of the index phases happened before the barrier above
+            __threadfence_block();
+            *reinterpret_cast<volatile int *>(&s_misc[4]) = 1;
+        }
         if (MODE == OBS_INDEX) {
             // split launch: the index goes to FlBatch.obs_ws in the layout the tree kernel's bulk copies expect
             // (header + agent block | occupancy words | bucket offsets from ks[-1] | time-slot filter), the entries to
@@ -953,12 +1030,12 @@ k_observe(FlBatch b, ObsLayout lay, float *__restrict__ out_attr, float *__restr
                 for (int k = tid; k < n_ent; k += NW) ge[k] = ent_s[k];
             }
         }
-        asm volatile("bar.arrive 2, %0;" ::"r"(NT) : "memory");  // lets the deadlock warp join phase 4 when it is done
+        asm volatile("bar.arrive %0, %1;" ::"r"(BAR_C), "r"(NT) : "memory");  // lets the deadlock warp join phase 4 when it is done
     }
     OBS_TICK(3);
     if (dbg && tid == 0) dbg[10] = s_misc[0];
     tpc_max = ld_vol_i32(&s_misc[2]);
-    } else {
+    } else if (MODE == OBS_TREES) {
         // tree kernel of the split launch: everything above arrived through the bulk copies
         const int n_ent_g = (int)ws_hdr[0];
         tpc_max = (int)ws_hdr[1];
@@ -966,13 +1043,57 @@ k_observe(FlBatch b, ObsLayout lay, float *__restrict__ out_attr, float *__restr
     }
 
     // ---- phase 4: branch trees, one warp per agent, agents taken from a shared counter --------------------
-    const bool spill = ent != ent_s;
-    auto ent_at = [&](uint32_t i) { return spill ? ent[i] : ent_s[i]; };
+    const bool spill_home = ent != ent_s;
+    uint32_t *const ent_home = ent;
+    const int tpc_max_home = tpc_max;
+    uint2 *const sq_home = sq;
     while (MODE != OBS_INDEX) {
-        int h = 0;
-        if (lane == 0) h = part + n_parts * atomicAdd(&s_misc[1], 1);     // the tree kernel's CTA `part` takes every n_parts-th agent
-        h = __shfl_sync(0xFFFFFFFFu, h, 0);
-        if (h >= N) break;
+        int h = 0, s_sel = sub;
+        if (G == 1) {
+            if (lane == 0) h = part + n_parts * atomicAdd(&s_misc[1], 1);     // the tree kernel's CTA `part` takes every n_parts-th agent
+            h = __shfl_sync(0xFFFFFFFFu, h, 0);
+            if (h >= N) break;
+        } else {
+            // group mode: the next agent of the warp's own environment, else of the first neighbour that has one left; an
+            // environment whose index is still being built is waited for (its own warps are on it)
+            int found = -1;
+            if (lane == 0) {
+                while (true) {
+                    bool pending = false;
+                    for (int k = 0; k < G; k++) {
+                        const int s2 = sub + k < G ? sub + k : sub + k - G;
+                        int *m = reinterpret_cast<int *>(obs_smem + (size_t)s2 * lay.total + lay.bar + 16);
+                        if (!ld_vol_i32(&m[4])) { pending = true; continue; }
+                        if (ld_vol_i32(&m[1]) >= N) continue;
+                        const int hh = atomicAdd(&m[1], 1);
+                        if (hh < N) { found = s2 | (hh << 4); break; }
+                    }
+                    if (found >= 0 || !pending) break;
+                    __nanosleep(200);
+                }
+            }
+            found = __shfl_sync(0xFFFFFFFFu, found, 0);
+            if (found < 0) break;
+            s_sel = found & 15; h = found >> 4;
+            __threadfence_block();                  // acquire: the index was published before its ready flag
+        }
+        // ---- the environment the agent belongs to (group mode: possibly a neighbour's) shadows the home environment's names ----
+        const int e_home = e;
+        const ObsEnv V = G > 1 ? obs_env_of(b, lay, obs_smem + (size_t)s_sel * lay.total, (int)blockIdx.x * G + s_sel) : X;
+        const int e = G > 1 ? (int)blockIdx.x * G + s_sel : e_home;
+        const uint16_t *const ridx = V.ridx, *const sdist = V.sdist, *const kcls = V.kcls;
+        const uint4 *const wrec = V.wrec;
+        const uint32_t *const whoff = V.whoff, *const whits = V.whits, *const wlist = V.wlist, *const gtab = V.gtab;
+        uint32_t *const ci = V.ci, *const ks = V.ks, *const ent_s = V.ent_s;
+        uint2 *const bm = V.bm, *const bm_s = V.bm_s;
+        const ObsAgents A = V.A;
+        const bool spill = G > 1 ? ld_vol_i32(&V.misc[0]) > lay.ent_cap : spill_home;
+        uint32_t *const ent = G > 1 ? (spill ? V.ent_g : V.ent_s) : ent_home;
+        const int tpc_max = G > 1 ? ld_vol_i32(&V.misc[2]) : tpc_max_home;
+        uint2 *const sq = sq_home;                  // the queue stays the warp's own
+        const float T_ = G > 1 ? (float)b.max_steps[e] : (float)b.max_steps[e_home];
+        const Scale sc{T_, __frcp_rn(T_), Nf, __frcp_rn(Nf)};
+        auto ent_at = [&](uint32_t i) { return spill ? ent[i] : ent_s[i]; };
         const size_t ea = (size_t)e * N + h;
         const uint32_t ainfo = A.info[h];
         const unsigned slot = (ainfo >> 8) & 0xFFFFu;
@@ -1042,7 +1163,7 @@ k_observe(FlBatch b, ObsLayout lay, float *__restrict__ out_attr, float *__restr
             }
             ls = le; le = nle; count = nle; cur++;
         }
-        if (bad) s_misc[3] = 1;
+        if (bad) { if (G > 1) atomicOr(&b.status[e], FL_ST_BAD_CELL); else s_misc[3] = 1; }
         const bool exists = n < count;
         const bool real = n >= 1 && exists && sid != 0xFFFFu;
         // evaluation orders (tool.h:468-524): node_order = height above the leaves, bottom level first
@@ -1248,6 +1369,10 @@ k_observe(FlBatch b, ObsLayout lay, float *__restrict__ out_attr, float *__restr
                 out_eorder[ea * (FL_MAX_NODES - 1) + n - 1] = exists ? porder : -2;
             }
         }
+    }
+    if (G > 1) {                                    // group mode: a warp leaves when no environment of the CTA has an agent left
+        if (dbg && lane == 0) for (int k = 5; k <= 7; k++) atomicMax(reinterpret_cast<unsigned long long *>(&dbg[k]), (unsigned long long)clock64());
+        return;
     }
     __syncthreads();
     OBS_TICK(5);

@@ -1,6 +1,8 @@
 """Per-source-line totals of a kernel from an ncu report: joins the SASS source page (stall samples,
 instructions executed) with nvdisasm's line table of the in-tree library.
-usage: python profiles/hot_lines.py <report.ncu-rep> <kernel regex> [top N]"""
+usage: python profiles/hot_lines.py <report.ncu-rep> <kernel regex> [top N]
+(the regex selects the function in the library's line table by its MANGLED name, e.g. k_observeILi128ELi7ELi0; NCU_KRE, default the
+same regex, selects the launch in the report by its base name, e.g. k_observe)"""
 import csv
 import os
 import re
@@ -39,7 +41,7 @@ def line_table(kernel_re):
 def main():
     rep, kre = sys.argv[1], sys.argv[2]
     top = int(sys.argv[3]) if len(sys.argv) > 3 else 40
-    out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--kernel-name", "regex:" + kre],
+    out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--kernel-name", "regex:" + os.environ.get("NCU_KRE", kre)],
                          capture_output=True, text=True).stdout
     rows = list(csv.reader(out.splitlines()))
     hi = next(i for i, r in enumerate(rows) if r and r[0] == "Address")
@@ -66,6 +68,13 @@ def main():
     print("%-24s %8s %7s %12s %7s %6s" % ("file:line", "samples", "%", "warp-inst", "%", "thr/in"))
     for key, (s, ex, th) in sorted(agg.items(), key=lambda x: -x[1][0])[:top]:
         print("%-24s %8d %6.2f%% %12d %6.2f%% %6.1f" % ("%s:%d" % key, s, 100.0 * s / max(tot_s, 1), ex, 100.0 * ex / max(tot_e, 1), th / max(ex, 1)))
+    print("\n# by warp instructions")
+    for key, (s, ex, th) in sorted(agg.items(), key=lambda x: -x[1][1])[:top]:
+        print("%-24s %8d %6.2f%% %12d %6.2f%% %6.1f" % ("%s:%d" % key, s, 100.0 * s / max(tot_s, 1), ex, 100.0 * ex / max(tot_e, 1), th / max(ex, 1)))
+    print("\n# in source order (lines with at least 0.1 %% of the samples or instructions)")
+    for key, (s, ex, th) in sorted(agg.items()):
+        if s >= tot_s / 1000 or ex >= tot_e / 1000:
+            print("%-24s %8d %6.2f%% %12d %6.2f%% %6.1f" % ("%s:%d" % key, s, 100.0 * s / max(tot_s, 1), ex, 100.0 * ex / max(tot_e, 1), th / max(ex, 1)))
 
 
 if __name__ == "__main__":

@@ -31,6 +31,11 @@ PLANS = [
     {"parts": 0}, {"parts": 0, "entcap": 0, "sortsmall": 1}, {"parts": 1}, {"parts": 2}, {"parts": 3, "nt": 64}, {"parts": 7, "entcap": 0},
     {"parts": 2, "tables": 0}, {"parts": 4, "ctas": 1}, {"parts": 2, "sortsmall": 1, "segcap": 0},
     {"flatwalk": 3}, {"flatwalk": 1, "parts": 2}, {"flatwalk": 2, "entcap": 0, "segcap": 3}, {"bmglobal": 1}, {"bmglobal": 1, "parts": 3},
+    # group mode of the fused kernel: G environments per CTA, the tree phase shared by all of its warps (the two test
+    # environments leave spare slots in the group: the ragged case)
+    {"parts": 0, "nt": 128, "group": 7}, {"parts": 0, "nt": 128, "group": 4}, {"parts": 0, "nt": 128, "group": 7, "entcap": 0},
+    {"parts": 0, "nt": 128, "group": 5, "segcap": 3, "sortsmall": 1}, {"parts": 0, "group": 3, "nt": 256}, {"parts": 0, "group": 7, "nt": 64},
+    {"parts": 0, "nt": 128, "group": 6, "tables": 0}, {"parts": 0, "group": 2, "nt": 256},
 ]
 
 
@@ -250,6 +255,19 @@ def test_every_kernel_plan_matches_oracle(golden, obs_plan, plan):
     rng = np.random.RandomState(77)
     other = np.where(rng.rand(*g["actions"].shape) < 0.7, 2, rng.randint(0, 5, size=g["actions"].shape)).astype(np.uint8)
     run_against_oracle([g, g], [g["actions"], other], [g["sched"], g["sched"]], 45, check_every=3)
+
+
+@pytest.mark.parametrize("group", [4, 7])
+def test_group_mode_full_and_ragged_groups(golden, obs_plan, group):
+    """Group mode with more environments than one CTA holds: 9 environments are two full groups and a ragged one at G = 4,
+    one full and one ragged group at G = 7; warps walk the trees of their neighbours' agents, the bytes stay the same."""
+    obs_plan({"parts": 0, "nt": 128, "group": group})
+    g = golden("t03_l1_greedy")
+    rng = np.random.RandomState(11)
+    acts = [g["actions"]] + [np.where(rng.rand(*g["actions"].shape) < p, 2, rng.randint(0, 5, size=g["actions"].shape)).astype(np.uint8)
+                             for p in (0.9, 0.8, 0.7, 0.6, 0.5, 0.4, 0.3, 0.2)]
+    b = run_against_oracle([g] * 9, acts, [g["sched"]] * 9, 36, check_every=4)
+    assert b.observe_plan()["group"] == group
 
 
 def test_tall_grid_prediction_key_collisions():
