@@ -97,10 +97,10 @@ int align_up(int v, int a) { return (v + a - 1) / a * a; }
 
 // Plan overrides (fl_observe_override; tuning and tests only).  -1 = default.  Seeded once from FL_OBS_<KEY> environment
 // variables when the library is loaded; the launch path reads these atomics, never the environment.
-enum ObsKnob : int { KNOB_NT = 0, KNOB_CTAS, KNOB_TABLES, KNOB_SEGCAP, KNOB_ENTCAP, KNOB_SORTSMALL, KNOB_PARTS, KNOB_BMGLOBAL, KNOB_TREENT, KNOB_FLATWALK, KNOB_GROUP, KNOB_COUNT };
-const char *const kKnobNames[KNOB_COUNT] = {"nt", "ctas", "tables", "segcap", "entcap", "sortsmall", "parts", "bmglobal", "treent", "flatwalk", "group"};
+enum ObsKnob : int { KNOB_NT = 0, KNOB_CTAS, KNOB_TABLES, KNOB_SEGCAP, KNOB_ENTCAP, KNOB_SORTSMALL, KNOB_PARTS, KNOB_BMGLOBAL, KNOB_TREENT, KNOB_FLATWALK, KNOB_GROUP, KNOB_EXP, KNOB_COUNT };
+const char *const kKnobNames[KNOB_COUNT] = {"nt", "ctas", "tables", "segcap", "entcap", "sortsmall", "parts", "bmglobal", "treent", "flatwalk", "group", "exp"};
 const char *const kKnobEnv[KNOB_COUNT] = {"FL_OBS_NT", "FL_OBS_CTAS", "FL_OBS_TABLES", "FL_OBS_SEGCAP", "FL_OBS_ENTCAP", "FL_OBS_SORTSMALL", "FL_OBS_PARTS",
-                                          "FL_OBS_BMGLOBAL", "FL_OBS_TREENT", "FL_OBS_FLATWALK", "FL_OBS_GROUP"};
+                                          "FL_OBS_BMGLOBAL", "FL_OBS_TREENT", "FL_OBS_FLATWALK", "FL_OBS_GROUP", "FL_OBS_EXP"};
 std::atomic<int> g_knob[KNOB_COUNT];
 struct KnobInit {
     KnobInit() {
@@ -141,6 +141,7 @@ ObsLayout make_obs_layout(const FlBatch *b, int nt, int mode, int parts, int *ct
     // ("bmglobal" knob; in every mode it stays in the workspace when the mandatory regions would not fit beside it: it is
     // written with plain stores once its bucket is sorted, so it can live anywhere)
     const long long sq_bytes = (long long)(mode == OBS_TREES ? (nt / 32) * 64 : (10 * N > (nt / 32) * 64 ? 10 * N : (nt / 32) * 64)) * 8;
+    L.cmp = take((nt / 32) * 32);                               // per warp: "r-th lane of a ballot" table
     const bool bm_fits = (long long)off + (long long)Rmax * 32 + sq_bytes + (b->H > b->W ? Rmax * 2 : 0) + 4096 <= SMEM_MAX;
     const bool bm_global = b->obs_ws && b->ws_stride > 0 && (knob(KNOB_BMGLOBAL) >= 0 ? knob(KNOB_BMGLOBAL) != 0 : !bm_fits);
     L.bm = bm_global ? -1 : take((long long)Rmax * 32);
@@ -148,6 +149,7 @@ ObsLayout make_obs_layout(const FlBatch *b, int nt, int mode, int parts, int *ct
     if (L.seg_cap < (nt / 32) * 64) L.seg_cap = (nt / 32) * 64;
     L.sq_words = L.seg_cap * 2;
     L.flat_walk = knob(KNOB_FLATWALK) >= 0 ? knob(KNOB_FLATWALK) : 3;
+    L.exp = knob(KNOB_EXP) >= 0 ? knob(KNOB_EXP) : 0;
     int seg_cap_use = L.seg_cap;                                // "segcap" / "entcap" overrides (tests): smaller capacities in
     if (knob(KNOB_SEGCAP) >= 0 && knob(KNOB_SEGCAP) < seg_cap_use) seg_cap_use = knob(KNOB_SEGCAP);                            // the same room,
     L.sq = take((long long)L.seg_cap * 8);                      // per-warp queues of the full conflict checks / segment pool
@@ -160,7 +162,7 @@ ObsLayout make_obs_layout(const FlBatch *b, int nt, int mode, int parts, int *ct
     int want_tables = 0x77;                                     // bit k: wlist, wrec, sdist, (srec: unused by k_observe), whoff, whits
     if (knob(KNOB_TABLES) >= 0) want_tables = knob(KNOB_TABLES);
     if (mode == OBS_TREES) want_tables &= ~0x40;                // the tree kernel never reads the grid
-    const int max_ctas = nt >= 1024 ? 1 : nt == 512 ? 2 : nt == 256 ? 4 : nt == 128 ? 8 : 12;
+    const int max_ctas = nt >= 1024 ? 1 : nt == 512 ? 2 : nt == 256 ? 4 : nt == 192 || nt == 160 ? 7 : nt == 128 ? 8 : 12;
     int ctas = 0;
     if (knob(KNOB_CTAS) >= 0) ctas = knob(KNOB_CTAS) > 0 ? knob(KNOB_CTAS) : 1;
     if (!ctas)
@@ -190,7 +192,7 @@ ObsLayout make_obs_layout(const FlBatch *b, int nt, int mode, int parts, int *ct
     if (ent_b < 0) ent_b = 0;
     L.ent = take(ent_b);
     L.ent_cap = (int)(ent_b / 4);
-    L.sort_small = 40;                                          // buckets up to this size are sorted by one thread
+    L.sort_small = 16;                                          // buckets up to this size are sorted by one thread (40: +2..4 % time, profiles/r02_l_experiments.txt)
     if (knob(KNOB_SORTSMALL) >= 1) L.sort_small = knob(KNOB_SORTSMALL);
     L.seg_cap = seg_cap_use;                                    // to force the per-agent path walk and the global spill of the entries
     if (knob(KNOB_ENTCAP) >= 0 && knob(KNOB_ENTCAP) < L.ent_cap) L.ent_cap = knob(KNOB_ENTCAP);
@@ -204,7 +206,7 @@ ObsLayout make_obs_layout(const FlBatch *b, int nt, int mode, int parts, int *ct
 int obs_threads(const FlBatch *b) {
     {
         const int v = knob(KNOB_NT);
-        if (v == 64 || v == 128 || v == 256 || v == 512 || v == 1024) return v;
+        if (v == 64 || v == 128 || v == 160 || v == 192 || v == 256 || v == 512 || v == 1024) return v;
     }
     if (b->N <= 8) return 64;
     const long long per_sm = (b->E + 147) / 148;                // environments per SM (B200: 148 SMs)
@@ -272,6 +274,20 @@ int tree_threads(const FlBatch *b, int parts) {
     if (per >= 96) return 512;
     if (per >= 32) return 256;
     return 128;
+}
+
+// Threads per environment of the launch that obs_parts chose.  The fused kernel at the headline shape (128 threads, seven
+// environments per SM, all environments resident in one wave) runs with FIVE warps per environment: 35 instead of 28 warps
+// per SM hide more of the latency the kernel is bound by (ncu: issue slots 62.7 % instead of 59.4 % busy, -4 % time,
+// profiles/r02_m_sweep.txt); the register budget is then 56 per thread.  160 / 192 threads exist for the fused kernel only.
+int obs_threads_for(const FlBatch *b, int parts) {
+    int nt = obs_threads(b);
+    if (parts) return nt == 160 || nt == 192 ? 128 : nt;
+    if (knob(KNOB_NT) >= 0 || nt != 128 || b->N < 32) return nt;
+    int ctas = 1, ctas160 = 1;
+    make_obs_layout(b, 128, OBS_FUSED, 0, &ctas);
+    make_obs_layout(b, 160, OBS_FUSED, 0, &ctas160);
+    return ctas == 7 && ctas160 == 7 && knob(KNOB_CTAS) < 0 ? 160 : nt;
 }
 
 int finish(cudaError_t launch_err) { return launch_err == cudaSuccess ? FL_OK : (int)launch_err; }
@@ -412,6 +428,9 @@ int fl_observe(const FlBatch *b, float *d_agent_attr, float *d_forest, int32_t *
         // the register budget follows the number of CTAs the shared-memory plan lets share an SM
 #define FL_K(NT_, RES_) (mode == OBS_FUSED ? (Kern)k_observe<NT_, RES_, OBS_FUSED> : mode == OBS_INDEX ? (Kern)k_observe<NT_, RES_, OBS_INDEX> : (Kern)k_observe<NT_, RES_, OBS_TREES>)
         if (nt == 64) return ctas > 8 ? FL_K(64, 12) : FL_K(64, 8);
+        // five / six warps per environment, seven environments per SM: fused kernel only (the "nt" knob; tuning)
+        if (nt == 160) return mode == OBS_FUSED ? (Kern)k_observe<160, 7, OBS_FUSED> : nullptr;
+        if (nt == 192) return mode == OBS_FUSED ? (Kern)k_observe<192, 7, OBS_FUSED> : nullptr;
         if (nt == 128) return ctas > 7 ? FL_K(128, 8) : ctas > 6 ? FL_K(128, 7) : ctas > 4 ? FL_K(128, 6) : FL_K(128, 4);
         if (nt == 256) return ctas > 3 ? FL_K(256, 4) : ctas > 2 ? FL_K(256, 3) : FL_K(256, 2);
         if (nt == 512) return ctas > 1 ? FL_K(512, 2) : FL_K(512, 1);
@@ -430,6 +449,7 @@ int fl_observe(const FlBatch *b, float *d_agent_attr, float *d_forest, int32_t *
         const int smem = lay.total * group;
         if (smem > SMEM_MAX) return FL_ERR_SMEM;
         Kern kern = group > 1 ? pick_group(nt, group) : pick(nt, ctas, mode);
+        if (!kern) return FL_ERR_BAD_ARG;
         if (smem > 48 * 1024) {
             cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
             if (err != cudaSuccess) return (int)err;
@@ -442,11 +462,11 @@ int fl_observe(const FlBatch *b, float *d_agent_attr, float *d_forest, int32_t *
     };
     const int parts = obs_parts(b);
     if (parts == 0) {
-        const int nt = obs_threads(b);
+        const int nt = obs_threads_for(b, 0);
         return launch(OBS_FUSED, nt, 0, K_OBSERVE, obs_group(b, nt));
     }
     if (b->ws_stride < fl_observe_ws_words(b)) return FL_ERR_BAD_ARG;
-    if (int rc = launch(OBS_INDEX, obs_threads(b), parts, K_OBSERVE_INDEX)) return rc;
+    if (int rc = launch(OBS_INDEX, obs_threads_for(b, parts), parts, K_OBSERVE_INDEX)) return rc;
     return launch(OBS_TREES, tree_threads(b, parts), parts, K_OBSERVE_TREES);
 }
 
@@ -664,7 +684,7 @@ int fl_step_observe_host_compact(const FlBatch *b, const uint8_t *h_actions, uin
 int fl_observe_plan(const FlBatch *b, int32_t *out, int n_out) {
     if (int rc = check_batch(b)) return rc;
     if (!out || n_out < 20) return FL_ERR_BAD_ARG;
-    const int nt = obs_threads(b), parts = obs_parts(b);
+    const int parts = obs_parts(b), nt = obs_threads_for(b, parts);
     const int group = parts ? 1 : obs_group(b, nt);
     int ctas = 1;
     const ObsLayout L = make_obs_layout(b, nt, parts ? OBS_INDEX : OBS_FUSED, parts, &ctas, group);

@@ -36,9 +36,10 @@ namespace {
 constexpr int I_INF = 0x7fffffff;
 
 struct ObsLayout {   // byte offsets into dynamic shared memory (host: make_obs_layout); < 0 = lives in global memory
-    int bar, part, ag, dl, ci, ks, bm, sq, seg_cap, sort_small, kcls, grid, ridx, ent, ent_cap, total;
+    int bar, part, cmp, ag, dl, ci, ks, bm, sq, seg_cap, sort_small, kcls, grid, ridx, ent, ent_cap, total;
     int srec, wrec, whoff, whits, wlist, sdist;   // static walk tables (walks.cuh)
     int sq_words;                                 // uint32 words of the sq region (seg_cap may be lowered by a test override)
+    int exp;                                      // experiment switches (fl_observe_override "exp"; tuning only, none in use)
     int flat_walk;                                // path segments walked by warps as flat lists: bit 0 counting pass, bit 1 scatter pass
     int parts;                                    // split launch: CTAs per environment of the tree kernel (0 = fused kernel)
     int ws_ag, ws_idx, ws_ag_bytes, ws_idx_bytes; // split launch: byte offsets / sizes of the two blocks of FlBatch.obs_ws
@@ -160,19 +161,23 @@ DEVI void predict_path(const uint4 *wrec, const uint32_t *whoff, const uint32_t 
     }
 }
 
-// Predicted-occupancy entry, 4 bytes: agent | t0 << 10 | last << 19 | dir_here << 20 | dir_prev << 22 | dir_next << 24 |
-// (rows per cell - 1) << 26 | agent is DONE << 29 | rows per cell > 8 (read it from the agent record instead) << 30.
-// The interval end is implied: 500 for the last element of a path ("last"), 0 for element 0, t0 + tpc - 1 otherwise.
+// Predicted-occupancy entry, 4 bytes, laid out so that entries order like their sort key (long-lived entries first, then by
+// start row): regular << 31 | t0 << 22 | (bit 21 free) | rows per cell > 8 (read it from the agent record instead) << 20 |
+// agent is DONE << 19 | (rows per cell - 1) << 16 | dir_next << 14 | dir_prev << 12 | dir_here << 10 | agent.
+// "regular" is 0 for the last element of a path, which stays occupied until row 500 (long-lived).  The interval end is
+// implied: 500 for a long-lived entry, 0 for element 0, t0 + tpc - 1 otherwise.
 DEVI uint32_t pack_entry(int agent, int t0, int t1, int dh, int dp, int dn, uint32_t extra) {
-    return (uint32_t)agent | ((uint32_t)t0 << 10) | ((uint32_t)(t1 == NPRED - 1) << 19) | ((uint32_t)dh << 20) |
-           ((uint32_t)dp << 22) | ((uint32_t)dn << 24) | extra;
+    return (uint32_t)agent | ((uint32_t)dh << 10) | ((uint32_t)dp << 12) | ((uint32_t)dn << 14) | ((uint32_t)t0 << 22) |
+           ((uint32_t)(t1 != NPRED - 1) << 31) | extra;
 }
 DEVI uint32_t entry_extra(int tpc, bool done) {
-    return (tpc <= 8 ? (uint32_t)(tpc - 1) << 26 : 1u << 30) | ((uint32_t)done << 29);
+    return (tpc <= 8 ? (uint32_t)(tpc - 1) << 16 : 1u << 20) | ((uint32_t)done << 19);
 }
 // rows an entry's agent spends per cell (info: the agents' records, only read for speeds below 1/8)
-DEVI int entry_tpc(uint32_t en, const uint32_t *info) { return ((en >> 30) & 1u) ? (int)(info[en & 1023u] >> 24) : (int)((en >> 26) & 7u) + 1; }
-DEVI uint32_t entry_sort_key(uint32_t en) { return (((en >> 19) & 1u) ? 0u : 512u) + ((en >> 10) & 511u); }  // long-lived first, then by t0
+DEVI int entry_tpc(uint32_t en, const uint32_t *info) { return ((en >> 20) & 1u) ? (int)(info[en & 1023u] >> 24) : (int)((en >> 16) & 7u) + 1; }
+DEVI uint32_t entry_sort_key(uint32_t en) { return en >> 22; }          // 10 bits: long-lived first, then by t0
+DEVI bool entry_long_lived(uint32_t en) { return !(en >> 31); }
+DEVI int entry_t0(uint32_t en) { return (int)((en >> 22) & 511u); }
 
 // loader.cpp:273-312: valid-action mask, bit a = action a allowed
 DEVI int valid_actions_of(const uint16_t *g, int W, int st, int ctr, int r, int c, int d) {
@@ -378,18 +383,6 @@ DEVI ObsEnv obs_env_of(const FlBatch &b, const ObsLayout &lay, unsigned char *sm
     return V;
 }
 
-// position of the n-th (0-based) set bit of m; the caller guarantees that m has more than n set bits.  Five popc
-// steps (the __fns intrinsic is a long software loop).
-DEVI int nth_set_bit(unsigned m, int n) {
-    int pos = 0;
-#pragma unroll
-    for (int s = 16; s >= 1; s >>= 1) {
-        const int c = __popc((m >> pos) & ((1u << s) - 1u));
-        if (n >= c) { n -= c; pos += s; }
-    }
-    return pos;
-}
-
 DEVI unsigned warp_excl_scan(unsigned v, int lane, unsigned &total) {
     unsigned x = v;
 #pragma unroll
@@ -450,6 +443,8 @@ k_observe(FlBatch b, ObsLayout lay, float *__restrict__ out_attr, float *__restr
     const bool bm_smem = lay.bm >= 0;               // reads and atomics go through typed shared-memory accesses when they can
     uint2 *const bm_s = X.bm_s;
     uint2 *sq = reinterpret_cast<uint2 *>(smraw + lay.sq) + warp * 64;       // this warp's queue of cells that need the full conflict check
+    // per warp: a 32-byte table "r-th set lane of a ballot" (five popc steps per look-up otherwise: 9 % of the kernel's instructions)
+    uint8_t *const cmp_s = smraw + lay.cmp + warp * 32;
     uint32_t *s_part = reinterpret_cast<uint32_t *>(smraw + lay.part);
     uint64_t *bar = reinterpret_cast<uint64_t *>(smraw + lay.bar);
     int *s_misc = reinterpret_cast<int *>(smraw + lay.bar + 16);
@@ -660,10 +655,18 @@ k_observe(FlBatch b, ObsLayout lay, float *__restrict__ out_attr, float *__restr
     }
     OBS_TICK(1);
 
-    // ---- phase 2 (last warp, lane 0) || phase 3 (all other warps, named barrier 1): deadlocks, predictions ----
+    // ---- phase 2 (lane 0 of the last warp): deadlocks; phase 3: predictions ----
+    // Split launch (index kernel): the last warp runs the serial deadlock lane WHILE the other warps build the prediction index
+    // (named barrier B) and joins them afterwards.  Fused kernel: all warps build the index, then the last warp runs the
+    // deadlock lane while the others already walk trees — a quarter more threads on the index (4 instead of 3 warps at the
+    // headline shape), and the serial lane still hides behind parallel work.
+#ifndef FL_DL_LATE
+#define FL_DL_LATE 0    // measured on one box: 0.429 ms with, 0.400 ms without (profiles/r02_n_ab.txt)
+#endif
+    constexpr bool DL_LATE = MODE == OBS_FUSED && FL_DL_LATE;
     const bool dl_warp = warp == NT / 32 - 1;
-    constexpr int NW = NT - 32;                    // threads walking predictions
-    if (dl_warp) {
+    constexpr int NW = DL_LATE ? NT : NT - 32;     // threads walking predictions
+    auto run_deadlocks = [&]() {
         if (lane == 0) { update_deadlocks(D, N); if (dbg) dbg[8] = clock64(); }
         __syncwarp();
         if (G > 1) {
@@ -685,6 +688,9 @@ k_observe(FlBatch b, ObsLayout lay, float *__restrict__ out_attr, float *__restr
                 dst[i * FL_ATTR_F + k] = v;
             }
         }
+    };
+    if (dl_warp && !DL_LATE) {
+        run_deadlocks();
         asm volatile("bar.sync %0, %1;" ::"r"(BAR_C), "r"(NT) : "memory");    // the prediction index is complete (the other warps only arrive)
         if (s_misc[0] > lay.ent_cap) ent = b.entries + (size_t)e * b.ent_cap;
     } else {
@@ -775,6 +781,9 @@ k_observe(FlBatch b, ObsLayout lay, float *__restrict__ out_attr, float *__restr
                 unsigned total;
                 const unsigned off = warp_excl_scan(cnt, lane, total);
                 const unsigned nonempty = __ballot_sync(0xFFFFFFFFu, cnt > 0);
+                __syncwarp();
+                if (cnt > 0) cmp_s[__popc(nonempty & ((1u << lane) - 1u))] = (uint8_t)lane;   // r-th segment with elements
+                __syncwarp();
                 // what an element needs of its segment, fetched from the owner lane: a = walk offset, b = first step's offset in the
                 // flat list, c = kk | kend << 9 | tpc << 23, d = the segment record's second word (agent, next direction, last),
                 // e = direction before the segment
@@ -791,7 +800,7 @@ k_observe(FlBatch b, ObsLayout lay, float *__restrict__ out_attr, float *__restr
                         const int cnt0 = __popc(__ballot_sync(0xFFFFFFFFu, cnt > 0 && off <= base));
                         const unsigned starts = __reduce_or_sync(0xFFFFFFFFu, (cnt > 0 && off > base && off < base + 32) ? 1u << (off - base) : 0u);
                         const int rank = cnt0 - 1 + __popc(starts & (0xFFFFFFFFu >> (31 - lane)));
-                        const int owner = f < total ? nth_set_bit(nonempty, rank) : 0;
+                        const int owner = f < total ? (int)cmp_s[rank] : 0;
                         o_wx[r] = __shfl_sync(0xFFFFFFFFu, wx, owner); o_off[r] = __shfl_sync(0xFFFFFFFFu, off, owner);
                         o_c[r] = __shfl_sync(0xFFFFFFFFu, rc_, owner); o_y[r] = __shfl_sync(0xFFFFFFFFu, sg.y, owner);
                         o_dp[r] = __shfl_sync(0xFFFFFFFFu, sg.x >> 30, owner);
@@ -902,15 +911,15 @@ k_observe(FlBatch b, ObsLayout lay, float *__restrict__ out_attr, float *__restr
                                     : (2ll * n_ent <= (long long)b.ent_cap ? g_ent + n_ent : nullptr);
         auto insertion_sort = [&](int s0, int s1) {
             for (int x = s0 + 1; x < s1; x++) {
-                const uint32_t v = ent[x], kv = entry_sort_key(v);
+                const uint32_t v = ent[x];                   // entries order like their keys (ties: by their low bits, any order will do)
                 int y = x - 1;
-                while (y >= s0 && entry_sort_key(ent[y]) > kv) { ent[y + 1] = ent[y]; y--; }
+                while (y >= s0 && ent[y] > v) { ent[y + 1] = ent[y]; y--; }
                 ent[y + 1] = v;
             }
         };
         // up to 32 entries, one per lane (v0: the lane's entry, already loaded): bitonic network of register shuffles
         auto warp_sort_regs = [&](int key, int s0, int n, uint32_t v0) {
-            uint32_t kv = lane < n ? ((entry_sort_key(v0) << 5) | (uint32_t)lane) : 0xFFFFFFFFu;   // key | source lane
+            uint32_t kv = lane < n ? v0 : 0xFFFFFFFFu;                   // entries order like their keys; no entry is all ones (t0 <= 500)
 #pragma unroll
             for (int k2 = 2; k2 <= 32; k2 <<= 1)
 #pragma unroll
@@ -919,8 +928,7 @@ k_observe(FlBatch b, ObsLayout lay, float *__restrict__ out_attr, float *__restr
                     const bool up = (lane & k2) == 0, low = (lane & j2) == 0;
                     kv = (low == up) ? min(kv, o) : max(kv, o);
                 }
-            const uint32_t v = __shfl_sync(0xFFFFFFFFu, v0, kv & 31u);
-            if (lane < n) ent[s0 + lane] = v;
+            if (lane < n) ent[s0 + lane] = kv;
         };
         // more than 32 entries: two stable radix passes (5 + 5 bits of the 10-bit key) through the scratch copy, the bucket
         // taken 256 entries at a time so that eight loads per lane are in flight (one memory round trip per 256 entries and
@@ -1030,7 +1038,8 @@ k_observe(FlBatch b, ObsLayout lay, float *__restrict__ out_attr, float *__restr
                 for (int k = tid; k < n_ent; k += NW) ge[k] = ent_s[k];
             }
         }
-        asm volatile("bar.arrive %0, %1;" ::"r"(BAR_C), "r"(NT) : "memory");  // lets the deadlock warp join phase 4 when it is done
+        if (!DL_LATE) asm volatile("bar.arrive %0, %1;" ::"r"(BAR_C), "r"(NT) : "memory");  // lets the deadlock warp go on when it is done
+        if (DL_LATE && dl_warp) run_deadlocks();
     }
     OBS_TICK(3);
     if (dbg && tid == 0) dbg[10] = s_misc[0];
@@ -1093,7 +1102,15 @@ k_observe(FlBatch b, ObsLayout lay, float *__restrict__ out_attr, float *__restr
         uint2 *const sq = sq_home;                  // the queue stays the warp's own
         const float T_ = G > 1 ? (float)b.max_steps[e] : (float)b.max_steps[e_home];
         const Scale sc{T_, __frcp_rn(T_), Nf, __frcp_rn(Nf)};
-        auto ent_at = [&](uint32_t i) { return spill ? ent[i] : ent_s[i]; };
+        // one generic load (address + LD) wherever the entries live; selecting between a typed shared-memory load and a global
+        // one per access compiles to a branch with a reconvergence point around every load: 8 instructions instead of 2
+#ifndef FL_V_GENERIC
+#define FL_V_GENERIC 1
+#endif
+#ifndef FL_V_ACC
+#define FL_V_ACC 1
+#endif
+        auto ent_at = [&](uint32_t i) { return FL_V_GENERIC ? ent[i] : (spill ? ent[i] : ent_s[i]); };
         const size_t ea = (size_t)e * N + h;
         const uint32_t ainfo = A.info[h];
         const unsigned slot = (ainfo >> 8) & 0xFFFFu;
@@ -1151,7 +1168,10 @@ k_observe(FlBatch b, ObsLayout lay, float *__restrict__ out_attr, float *__restr
             const int nle = min(FL_MAX_NODES, le + 3 * __popc(lmask));
             const bool pull = n >= le && n < nle;
             const int rt = pull ? (n - le) / 3 : 0, j = pull ? (n - le) - 3 * rt : 0;
-            const int p = pull ? nth_set_bit(lmask, rt) : 0;
+            if (real_l) cmp_s[__popc(lmask & ((1u << n) - 1u))] = (uint8_t)n;     // r-th real node of the level
+            __syncwarp();
+            const int p = pull ? (int)cmp_s[rt] : 0;
+            __syncwarp();
             const unsigned pz = __shfl_sync(0xFFFFFFFFu, c01, p), pw = __shfl_sync(0xFFFFFFFFu, c2, p);
             const int pk = __shfl_sync(0xFFFFFFFFu, kind, p), ptot = __shfl_sync(0xFFFFFFFFu, tot0 + kend + 1, p);
             const unsigned pg = __shfl_sync(0xFFFFFFFFu, gnx, p);
@@ -1190,7 +1210,10 @@ k_observe(FlBatch b, ObsLayout lay, float *__restrict__ out_attr, float *__restr
         const unsigned real_mask = __ballot_sync(0xFFFFFFFFu, real);
         const int nreal = __popc(real_mask);
         // lane q holds the q-th real node's (offset, list base, tot0): the owner of a cell is found by rank
-        const unsigned src = lane < nreal ? (unsigned)nth_set_bit(real_mask, lane) : 31u;
+        if (real) cmp_s[__popc(real_mask & ((1u << lane) - 1u))] = (uint8_t)lane;
+        __syncwarp();
+        const unsigned src = lane < nreal ? (unsigned)cmp_s[lane] : 31u;
+        __syncwarp();
         const unsigned c_off = __shfl_sync(0xFFFFFFFFu, off, src), c_wb = __shfl_sync(0xFFFFFFFFu, wx, src);
         const unsigned c_t0 = __shfl_sync(0xFFFFFFFFu, (unsigned)tot0 | ((onp ? 1u : 0u) << 31), src);   // bit 31: node on the own path
         const bool c_valid = lane < nreal;
@@ -1229,8 +1252,8 @@ k_observe(FlBatch b, ObsLayout lay, float *__restrict__ out_attr, float *__restr
                     if (pt < NPRED && tot < NPRED) {                                 // treeobs.cpp:379-465
                         const unsigned bk = kcls ? (unsigned)kcls[rail] : rail;    // the reference's position key c*W + r
                         const int sa = max(0, pt - 1) >> 2, sb = min(NPRED - 1, pt + 1) >> 2;
-                        const uint2 wa = bm_smem ? bm_s[bk * 4 + (sa >> 5)] : bm[bk * 4 + (sa >> 5)];
-                        const uint2 wb = bm_smem ? bm_s[bk * 4 + (sb >> 5)] : bm[bk * 4 + (sb >> 5)];
+                        const uint2 wa = FL_V_GENERIC ? bm[bk * 4 + (sa >> 5)] : (bm_smem ? bm_s[bk * 4 + (sa >> 5)] : bm[bk * 4 + (sa >> 5)]);
+                        const uint2 wb = FL_V_GENERIC ? bm[bk * 4 + (sb >> 5)] : (bm_smem ? bm_s[bk * 4 + (sb >> 5)] : bm[bk * 4 + (sb >> 5)]);
                         // On the own path the observer's own entry (path element tot, rows t0o..t1o) is in the index too: a slot it
                         // covers needs a second entry to matter.  (t1o is a lower bound for the last element: errs towards checking.)
                         bool own_a = false, own_b = false;
@@ -1269,6 +1292,8 @@ k_observe(FlBatch b, ObsLayout lay, float *__restrict__ out_attr, float *__restr
             }
             if (qn >= 32 || (!more && qn > 0)) {
                 // ---- stage 2: the full conflict check (treeobs.cpp:379-465) of up to 32 queued cells, one per lane ----
+                // (a flat list of (cell, candidate) pairs over the lanes was measured too: 22.7 instead of 19 active lanes per
+                // instruction, but 3 % MORE instructions and the same time — profiles/r02_l_experiments.txt)
                 __syncwarp();
                 const int nq = min(qn, 32);
                 if (dbg && lane == 0) atomicAdd(reinterpret_cast<unsigned long long *>(&dbg[14]), 1ull);
@@ -1285,23 +1310,27 @@ k_observe(FlBatch b, ObsLayout lay, float *__restrict__ out_attr, float *__restr
                     const int nb = (int)((q.y >> 16) & 15u);
                     auto candidate = [&](uint32_t en, int t0) {
                         const int ag = (int)(en & 1023);
-                        const int t1 = ((en >> 19) & 1u) ? NPRED - 1 : (t0 ? t0 + entry_tpc(en, A.info) - 1 : 0);
+                        const int t1 = entry_long_lived(en) ? NPRED - 1 : (t0 ? t0 + entry_tpc(en, A.info) - 1 : 0);
                         if (t1 < pre) return;
-                        const int dh = (int)((en >> 20) & 3), dpv = (int)((en >> 22) & 3), dn = (int)((en >> 24) & 3);
-                        const bool done = (en >> 29) & 1u;
+                        const int dh = (int)((en >> 10) & 3), dpv = (int)((en >> 12) & 3), dn = (int)((en >> 14) & 3);
+                        const bool done = (en >> 19) & 1u;
                         const bool in_cur = t0 <= pt && pt <= t1, in_pre = t0 <= pre && pre <= t1,
                                    in_post = t0 <= post && post <= t1;
                         const int pdir = pt < t0 ? dpv : (pt > t1 ? dn : dh);  // always the direction at row pt
                         const bool cf = (d != pdir && tbit(nb, (pdir + 2) & 3)) || done;
                         const bool other = ag != h;
+                        if (FL_V_ACC) {
+                            const unsigned m_in = (in_cur ? 1u : 0u) | (in_pre ? 2u : 0u) | (in_post ? 4u : 0u);   // rows of the window the entry covers
+                            acc |= (other ? m_in : 0u) | (cf ? m_in << 3 : 0u);
+                        } else
                         acc |= (in_cur && other ? 1u : 0u) | (in_pre && other ? 2u : 0u) | (in_post && other ? 4u : 0u) |
                                (in_cur && cf ? 8u : 0u) | (in_pre && cf ? 16u : 0u) | (in_post && cf ? 32u : 0u);
                     };
                     uint32_t idx = s0;
                     for (; idx < s1; idx++) {                                    // long-lived entries come first
                         const uint32_t en = ent_at(idx);
-                        if (!((en >> 19) & 1u)) break;
-                        const int t0 = (int)((en >> 10) & 511);
+                        if (!entry_long_lived(en)) break;
+                        const int t0 = entry_t0(en);
                         if (t0 > post) break;                                    // ordered by t0: none of the rest has started yet
                         candidate(en, t0);
                     }
@@ -1312,11 +1341,11 @@ k_observe(FlBatch b, ObsLayout lay, float *__restrict__ out_attr, float *__restr
                     uint32_t lo = idx, hi = s1;
                     while (lo < hi) {
                         const uint32_t mid = (lo + hi) >> 1;
-                        if (entry_sort_key(ent_at(mid)) < key_lo) lo = mid + 1; else hi = mid;
+                        if (ent_at(mid) < (key_lo << 22)) lo = mid + 1; else hi = mid;
                     }
                     for (idx = lo; idx < s1; idx++) {
                         const uint32_t en = ent_at(idx);
-                        const int t0 = (int)((en >> 10) & 511);
+                        const int t0 = entry_t0(en);
                         if (t0 > post) break;
                         candidate(en, t0);
                     }

@@ -36,6 +36,7 @@ PLANS = [
     {"parts": 0, "nt": 128, "group": 7}, {"parts": 0, "nt": 128, "group": 4}, {"parts": 0, "nt": 128, "group": 7, "entcap": 0},
     {"parts": 0, "nt": 128, "group": 5, "segcap": 3, "sortsmall": 1}, {"parts": 0, "group": 3, "nt": 256}, {"parts": 0, "group": 7, "nt": 64},
     {"parts": 0, "nt": 128, "group": 6, "tables": 0}, {"parts": 0, "group": 2, "nt": 256},
+    {"sortsmall": 40}, {"sortsmall": 40, "parts": 2, "entcap": 0}, {"parts": 0, "nt": 160}, {"parts": 0, "nt": 192, "entcap": 0},
 ]
 
 
