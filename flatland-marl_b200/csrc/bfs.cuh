@@ -34,6 +34,9 @@ __global__ void __launch_bounds__(1024) k_bfs(FlBatch b, const int32_t *__restri
                         if (!tbit(nb, m)) continue;
                         const int rr = r + d_row(m), cc = c + d_col(m);
                         if (rr < 0 || cc < 0 || rr >= H || cc >= W) continue;
+                        // (compute-sanitizer racecheck flags this line: a thread may read a neighbour's distance while its
+                        // owner sets it to `level`.  Either value it can see — infinity before, `level` after — differs from
+                        // level - 1, so the comparison has one outcome; 16-bit aligned stores are not torn.)
                         if (dd[(rr * W + cc) * 4 + m] == level - 1) { dd[cell * 4 + o] = (uint16_t)level; changed = 1; break; }
                     }
                 }

@@ -32,11 +32,13 @@
 #include "observe.cuh"
 #include "bfs.cuh"
 #include "wire.cuh"
+#include "expand_pool.h"
 
 #include <chrono>
 #include <condition_variable>
 #include <cstdio>
 #include <functional>
+#include <memory>
 #include <thread>
 
 namespace {
@@ -511,84 +513,25 @@ cudaEvent_t chunk_event(int k) {
     }
     return pool[dev][k];
 }
+// extra compute streams of the host-buffer step (one set per device): the kernels of successive environment ranges run on
+// alternating streams, so that a range's latency-bound kernels overlap the next range's instead of queueing behind them
+cudaStream_t lane_stream(int k) {
+    static std::mutex mu;
+    static std::vector<std::vector<cudaStream_t>> pool;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    std::lock_guard<std::mutex> lk(mu);
+    if ((int)pool.size() <= dev) pool.resize(dev + 1);
+    while ((int)pool[dev].size() <= k) {
+        cudaStream_t s;
+        cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking);
+        pool[dev].push_back(s);
+    }
+    return pool[dev][k];
+}
 }  // namespace
 
 namespace {
-// Host threads that expand the compact wire format (wire.cuh) into the caller's tensors: persistent, woken per job, the
-// calling thread works along.  One pool per process; fl_host_threads sets its size before first use.
-class ExpandPool {
-  public:
-    void set_threads(int n) {
-        std::lock_guard<std::mutex> lk(mu_);
-        if (th_.empty()) want_ = n < 1 ? 1 : (n > 64 ? 64 : n);
-    }
-    int threads() {
-        std::lock_guard<std::mutex> lk(mu_);
-        return want_ ? want_ : default_threads();
-    }
-    void parallel_for(int n, const std::function<void(int)> &fn) {
-        if (n <= 0) return;
-        {
-            std::unique_lock<std::mutex> lk(mu_);
-            if (th_.empty()) start_locked();
-            fn_ = &fn; n_ = n; next_.store(0); left_.store(n); gen_++;
-        }
-        cv_.notify_all();
-        work();
-        std::unique_lock<std::mutex> lk(mu_);
-        done_cv_.wait(lk, [&] { return left_.load() == 0 && busy_ == 0; });
-        fn_ = nullptr;
-    }
-    ~ExpandPool() {
-        { std::lock_guard<std::mutex> lk(mu_); stop_ = true; }
-        cv_.notify_all();
-        for (auto &t : th_) t.join();
-    }
-
-  private:
-    static int default_threads() {
-        unsigned hc = std::thread::hardware_concurrency();
-        int n = hc ? (int)hc : 4;
-        if (const char *s = getenv("LOCAL_WORLD_SIZE")) { const int w = atoi(s); if (w > 1) n = n / w > 2 ? n / w : 2; }
-        return n > 32 ? 32 : n;
-    }
-    void start_locked() {
-        if (!want_) want_ = default_threads();
-        for (int k = 1; k < want_; k++) th_.emplace_back([this] { loop(); });
-    }
-    void work() {
-        const std::function<void(int)> *fn = fn_;
-        for (;;) {
-            const int k = next_.fetch_add(1);
-            if (k >= n_) break;
-            (*fn)(k);
-            left_.fetch_sub(1);
-        }
-    }
-    void loop() {
-        uint64_t seen = 0;
-        std::unique_lock<std::mutex> lk(mu_);
-        for (;;) {
-            cv_.wait(lk, [&] { return stop_ || gen_ != seen; });
-            if (stop_) return;
-            seen = gen_;
-            busy_++;
-            lk.unlock();
-            work();
-            lk.lock();
-            busy_--;
-            if (left_.load() == 0 && busy_ == 0) done_cv_.notify_all();
-        }
-    }
-    std::mutex mu_;
-    std::condition_variable cv_, done_cv_;
-    std::vector<std::thread> th_;
-    const std::function<void(int)> *fn_ = nullptr;
-    std::atomic<int> next_{0}, left_{0};
-    int n_ = 0, want_ = 0, busy_ = 0;
-    uint64_t gen_ = 0;
-    bool stop_ = false;
-};
 ExpandPool g_pool;
 }  // namespace
 
@@ -625,6 +568,16 @@ int fl_step_observe_host_compact(const FlBatch *b, const uint8_t *h_actions, uin
     double t_wait = 0.0, t_expand = 0.0;
     if ((err = cudaMemcpyAsync(d_actions, h_actions, (size_t)b->E * N, cudaMemcpyHostToDevice, st)) != cudaSuccess) return (int)err;
     if ((err = cudaMemsetAsync(d_cursor, 0, sizeof(uint32_t) * (size_t)n_chunks, st)) != cudaSuccess) return (int)err;
+    // compute lanes: range c runs on lane c % n_lanes (lane 0 = the caller's stream).  A range of 128 environments is one
+    // latency-bound wave of CTAs (0.2 ms whatever its size); two lanes keep the device ahead of the host's expansion
+    static const int lanes_env = getenv("FL_WIRE_LANES") ? atoi(getenv("FL_WIRE_LANES")) : 2;
+    const int n_lanes = copy_stream && n_chunks >= 2 ? (lanes_env < 1 ? 1 : lanes_env > 4 ? 4 : lanes_env) : 1;
+    if (n_lanes > 1) {
+        cudaEvent_t ev0 = chunk_event(160);
+        if ((err = cudaEventRecord(ev0, st)) != cudaSuccess) return (int)err;
+        for (int l = 1; l < n_lanes; l++)
+            if ((err = cudaStreamWaitEvent(lane_stream(l - 1), ev0, 0)) != cudaSuccess) return (int)err;
+    }
     std::vector<size_t> chunk_word0((size_t)n_chunks);
     for (int c = 0; c < n_chunks; c++) {
         const int64_t e0 = b->E * c / n_chunks, e1 = b->E * (c + 1) / n_chunks, n = e1 - e0;
@@ -632,15 +585,16 @@ int fl_step_observe_host_compact(const FlBatch *b, const uint8_t *h_actions, uin
         chunk_word0[c] = ((a0 * WIRE_MAX_WORDS + (size_t)e0 + 7) & ~(size_t)7) + 16 * (size_t)c;   // worst-case prefix, 32-byte aligned: regions never overlap
         FlBatch sub;
         if (int rc = fl_batch_slice(b, e0, n, &sub)) return rc;
-        if (int rc = fl_step(&sub, d_actions + a0, d_out->rewards + a0, d_out->dones + (size_t)e0 * (N + 1), flags, stream)) return rc;
+        cudaStream_t ls = c % n_lanes == 0 ? st : lane_stream(c % n_lanes - 1);
+        if (int rc = fl_step(&sub, d_actions + a0, d_out->rewards + a0, d_out->dones + (size_t)e0 * (N + 1), flags, (void *)ls)) return rc;
         if (int rc = fl_observe(&sub, d_out->agent_attr + a0 * FL_ATTR_F, d_out->forest + a0 * FL_MAX_NODES * FL_NODE_F,
                                 d_out->adjacency + a0 * (FL_MAX_NODES - 1) * 3, d_out->node_order + a0 * FL_MAX_NODES,
                                 d_out->edge_order + a0 * (FL_MAX_NODES - 1), d_out->valid_actions + a0 * 5,
-                                d_out->dist_target + a0, stream))
+                                d_out->dist_target + a0, (void *)ls))
             return rc;
-        if (cs != st) {
+        if (cs != ls) {
             cudaEvent_t ev = chunk_event(c);
-            if ((err = cudaEventRecord(ev, st)) != cudaSuccess) return (int)err;
+            if ((err = cudaEventRecord(ev, ls)) != cudaSuccess) return (int)err;
             if ((err = cudaStreamWaitEvent(cs, ev, 0)) != cudaSuccess) return (int)err;
         }
         WireSrc src{d_out->agent_attr + a0 * FL_ATTR_F, d_out->forest + a0 * FL_MAX_NODES * FL_NODE_F, d_out->dist_target + a0,

@@ -1349,9 +1349,32 @@ k_observe(FlBatch b, ObsLayout lay, float *__restrict__ out_attr, float *__restr
                         if (t0 > post) break;
                         candidate(en, t0);
                     }
-                    f_conf = (acc & 1u) ? (acc & 8u) : (acc & 2u) ? (acc & 16u) : (acc & 4u) ? (acc & 32u) : false;
+                    // treeobs.cpp:379-465: the first of the rows cur, pre, post that holds another agent decides, and it decides
+                    // "conflict" when an entry of that row crosses the observer's direction (or belongs to a DONE agent):
+                    // (acc & 1) ? (acc & 8) : (acc & 2) ? (acc & 16) : (acc & 4) ? (acc & 32) : false, as a 64-entry bit table
+#ifndef FL_V_CONF
+#define FL_V_CONF 1
+#endif
+                    f_conf = FL_V_CONF ? (bool)((0xfe54ba10ee44aa00ull >> acc) & 1ull)
+                                       : (bool)((acc & 1u) ? (acc & 8u) : (acc & 2u) ? (acc & 16u) : (acc & 4u) ? (acc & 32u) : 0u);
                 }
-                for (unsigned mm = __ballot_sync(0xFFFFFFFFu, f_conf); mm; mm &= mm - 1) {   // conflicts are rare: to the owner by shuffle
+                if (FL_V_CONF) {
+                    // A node keeps the FIRST conflict of its walk.  The queue holds cells in flat-list order (node after node,
+                    // walk step after walk step), so the lowest conflicting lane of a node has it: those lanes leave the step in
+                    // a 32-word table indexed by node rank (the room of the queue slots just read), the owners pick it up.
+                    const unsigned cm = __ballot_sync(0xFFFFFFFFu, f_conf);
+                    if (cm) {                                                        // warp-uniform
+                        const unsigned myr = (q.x >> 16) & 31u;
+                        const unsigned peers = __match_any_sync(0xFFFFFFFFu, f_conf ? myr : 32u + (unsigned)lane);
+                        const unsigned rmask = __reduce_or_sync(0xFFFFFFFFu, f_conf ? 1u << myr : 0u);
+                        uint32_t *kc = reinterpret_cast<uint32_t *>(sq);
+                        if (f_conf && __ffs(peers) - 1 == lane) kc[myr] = q.y & 0xFFFFu;
+                        __syncwarp();
+                        if (real && ((rmask >> my_rank) & 1u)) k_conf = min(k_conf, (int)kc[my_rank]);
+                        __syncwarp();
+                    }
+                } else
+                for (unsigned mm = __ballot_sync(0xFFFFFFFFu, f_conf); mm; mm &= mm - 1) {   // to the owner by shuffle
                     const int s = __ffs(mm) - 1;
                     const unsigned qx = __shfl_sync(0xFFFFFFFFu, q.x, s), qk = __shfl_sync(0xFFFFFFFFu, q.y, s);
                     if (real && my_rank == (int)((qx >> 16) & 31u)) k_conf = min(k_conf, (int)(qk & 0xFFFFu));

@@ -168,6 +168,8 @@ k_step(FlBatch b, const uint8_t *__restrict__ actions, int32_t *__restrict__ rew
         if (nxt_id == cur_id || sw || loser) s_blk[rep_cur] = 1;
     }
     __syncthreads();
+    // (racecheck warns about the loop below: s_blk flags only ever go 0 -> 1 and the loop runs to the fixpoint, so reading a
+    // flag while another thread sets it only decides in which round the reader follows)
     while (true) {                                 // propagate along chains until nothing changes
         int changed = 0;
         if (act && nxt_id != cur_id && rep_nxt >= 0 && !s_blk[rep_cur] && s_blk[rep_nxt]) { s_blk[rep_cur] = 1; changed = 1; }

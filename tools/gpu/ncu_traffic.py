@@ -3,6 +3,7 @@ one lock-step step, per (config, batch size) — what bench.py reports as roofli
 usage: python tools/gpu/ncu_traffic.py TAG Test_03:1024 Test_02:8192 ...   (reads gpurun_out/ncu_<cfg>_<TAG>_raw.csv)
 A split launch (k_observe<..., 1> index kernel + k_observe<..., 2> tree kernel) contributes one launch of each."""
 import csv
+import re
 import json
 import os
 import sys
@@ -42,12 +43,13 @@ def main():
             name = r[col["Kernel Name"]]
             if "k_observe" not in name:
                 continue
-            targs = name.split("<")[-1].split(">")[0].replace(" ", "").split(",")
+            m = re.search(r"k_observe<([^>]*)>", name)
+            targs = m.group(1).replace(" ", "").split(",") if m else []
             mode = MODE.get(targs[2] if len(targs) > 2 else "0", "fused")
             rd = to_bytes(r[col["dram__bytes_read.sum"]], units[col["dram__bytes_read.sum"]])
             wr = to_bytes(r[col["dram__bytes_write.sum"]], units[col["dram__bytes_write.sum"]])
             per_kernel[mode] = {"read": rd, "write": wr, "ncu_us": float(r[col["gpu__time_duration.sum"]].replace(",", "")),
-                                "kernel": name.split("(")[0].replace("void ", "").replace("<unnamed>::", "")}   # last launch of a kind wins
+                                "kernel": "k_observe<%s>" % ", ".join(targs)}   # last launch of a kind wins
         if not per_kernel:
             print("no k_observe launch in", src)
             continue
