@@ -21,7 +21,8 @@ _PTR = ["grid", "slot_rc", "dist", "max_steps", "init_rc", "tgt_rc", "init_dir",
         "rc", "old_rc", "dir", "old_dir", "state", "ctr", "mal", "saved", "sig_mal", "deadlocked", "done", "nmal",
         "arrival",
         "elapsed", "sched_pos", "done_all", "status", "stats",
-        "entries", "segs", "obs_ws"]
+        "entries", "segs", "obs_ws", "tree_cache"]
+TREE_CACHE_WORDS = 160
 
 
 class FlBatch(C.Structure):

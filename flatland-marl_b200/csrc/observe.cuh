@@ -39,6 +39,7 @@ struct ObsLayout {   // byte offsets into dynamic shared memory (host: make_obs_
     int bar, part, cmp, ag, dl, ci, ks, bm, sq, seg_cap, sort_small, kcls, grid, ridx, ent, ent_cap, total;
     int srec, wrec, whoff, whits, wlist, sdist;   // static walk tables (walks.cuh)
     int sq_words;                                 // uint32 words of the sq region (seg_cap may be lowered by a test override)
+    int tree_cache;                               // FlBatch.tree_cache is in use (the "treecache" knob turns it off)
     int exp;                                      // experiment switches (fl_observe_override "exp"; tuning only, none in use)
     int flat_walk;                                // path segments walked by warps as flat lists: bit 0 counting pass, bit 1 scatter pass
     int parts;                                    // split launch: CTAs per environment of the tree kernel (0 = fused kernel)
@@ -1117,93 +1118,124 @@ k_observe(FlBatch b, ObsLayout lay, float *__restrict__ out_attr, float *__restr
         const uint16_t *sd = sdist + (size_t)slot * SS;
         const float tpc_f = (float)(1.0 / (double)A.speed[h]);                          // treeobs.cpp:304
         const int n = lane;
-        // ---- structure: node n in lane n; one round per tree level (treeobs.cpp:171-256 FIFO, 583-608 children) ----
-        unsigned sid = 0xFFFFu, wx = 0, kunus = 0xFFFFu, c01 = 0xFFFFFFFFu, c2 = 0xFFFFu;
-        int tot0 = 0, kend = 0, kind = 0, parent = 0, ad = 0, level = 0, cb = 1;          // cb: index of the node's first child
-        // onp: the node's walk is part of the observer's own predicted path (its cell at distance tot is path element tot),
-        // gnx: the state the own path continues in after the node's walk (0xFFFF: it does not)
-        bool onp = false;
-        unsigned gnx = 0xFFFFu;
-        const uint32_t *gt = gtab + (size_t)slot * SS;
-        if (n >= 1 && n <= 3) {                                                           // roots (treeobs.cpp:171-221)
-            const int vr = (int)(short)(A.vrc[h] & 0xFFFF), vc = (int)(A.vrc[h] >> 16), dir = (int)(ainfo & 3);
-            const int nb = (int)((A.rec_b[h] >> 20) & 15u);
-            int orientation = dir;
-            if (__popc(nb) == 1) orientation = first_dir(nb);
-            ad = n - 2;
-            const int bd = (orientation + ad) & 3;
-            sid = (tbit(nb, bd) ? child_state(ridx, H, W, vr, vc, bd) : 0xFFFFFFFFu) & 0xFFFFu;
-            tot0 = 1; level = 1; cb = FL_MAX_NODES;
-            const unsigned s0 = A.sid0[h];
-            if (sid != 0xFFFFu && s0 != 0xFFFFu && sd[s0] != FL_DIST_INF) {
-                const uint32_t g0 = gt[s0];                                               // how the own path leaves the root cell
-                onp = ((g0 >> 16) & 0x3FFFu) ? true : sid == (g0 & 0xFFFFu);             // along the walk (one child) or into the greedy child
-            }
-        }
-        int count = 4, ls = 1, le = 4, cur = 1;
-        bool bad = false;
-        while (true) {
-            const bool real_l = n >= ls && n < le && sid != 0xFFFFu;
-            const unsigned lmask = __ballot_sync(0xFFFFFFFFu, real_l);
-            if (!lmask) break;
-            if (real_l) {
-                const uint4 w = wrec[sid];
-                const int L = (int)(w.y & 0xFFFFu), skind = (int)((w.y >> 16) & 15u), nh = (int)((w.y >> 20) & 255u);
-                kend = L;
-                bool hit = false;
-                if (nh) {                                                    // the observer's own target ends the walk early
-                    const uint32_t ho = whoff[sid];
-                    for (int q = 0; q < nh; q++) {
-                        const uint32_t hv = whits[ho + q];
-                        if ((hv >> 16) == slot) { kend = (int)(hv & 0xFFFFu); hit = true; break; }
-                    }
+        // ---- structure: node n in lane n (treeobs.cpp:171-256 FIFO, 583-608 children) ----
+        // Which walk each node stands for, where it ends, parents and evaluation orders follow from the static walk tables and
+        // the agent's rail state (cell, direction) alone, and most agents stand where they stood a step ago (95 % of the
+        // agent-steps of the benchmark's random-action episodes, fewer under a policy that keeps trains moving): the structure
+        // is kept per agent in FlBatch.tree_cache under that state as key — five coalesced loads instead of three
+        // ballot/shuffle rounds over the walk records.  Everything that depends on other trains (stages 1 and 2) is computed
+        // every step.
+        unsigned sid = 0xFFFFu, wx = 0, kunus = 0xFFFFu, dv_end = 0;
+        int tot0 = 0, kend = 0, kind = 0, parent = 0, ad = 0, count = 4, order = -2, porder = -2;
+        bool onp = false, exists = false, real = false;
+        uint32_t *tc = lay.tree_cache ? b.tree_cache + ((size_t)e * N + h) * FL_TREE_CACHE_WORDS : nullptr;
+        const uint32_t tkey = 0x80000000u | A.sid0[h];
+        bool cached = false;
+        uint32_t cw0 = 0;
+        if (tc) { cw0 = tc[lane]; cached = __shfl_sync(0xFFFFFFFFu, cw0, 31) == tkey; }
+        if (cached) {                                                                     // warp-uniform
+            const uint32_t cw1 = tc[32 + lane], cw2 = tc[64 + lane], cw3 = tc[96 + lane], cw4 = tc[128 + lane];
+            sid = cw0 & 0xFFFFu; kend = (int)(cw0 >> 16); wx = cw1; tot0 = (int)cw2;
+            kunus = cw3 & 0xFFFFu; dv_end = cw3 >> 16;
+            kind = (int)(cw4 & 7u); parent = (int)((cw4 >> 3) & 31u); ad = (int)((cw4 >> 8) & 3u) - 1; onp = (cw4 >> 10) & 1u;
+            exists = (cw4 >> 11) & 1u; order = (int)((cw4 >> 12) & 63u) - 2; porder = (int)((cw4 >> 18) & 63u) - 2;
+            count = (int)((cw4 >> 24) & 63u);
+            if (n == 31) { sid = 0xFFFFu; exists = false; }
+            real = n >= 1 && exists && sid != 0xFFFFu;
+        } else {
+            unsigned c01 = 0xFFFFFFFFu, c2 = 0xFFFFu;
+            int level = 0, cb = 1;                                                            // cb: index of the node's first child
+            // onp: the node's walk is part of the observer's own predicted path (its cell at distance tot is path element tot),
+            // gnx: the state the own path continues in after the node's walk (0xFFFF: it does not)
+            unsigned gnx = 0xFFFFu;
+            const uint32_t *gt = gtab + (size_t)slot * SS;
+            if (n >= 1 && n <= 3) {                                                           // roots (treeobs.cpp:171-221)
+                const int vr = (int)(short)(A.vrc[h] & 0xFFFF), vc = (int)(A.vrc[h] >> 16), dir = (int)(ainfo & 3);
+                const int nb = (int)((A.rec_b[h] >> 20) & 15u);
+                int orientation = dir;
+                if (__popc(nb) == 1) orientation = first_dir(nb);
+                ad = n - 2;
+                const int bd = (orientation + ad) & 3;
+                sid = (tbit(nb, bd) ? child_state(ridx, H, W, vr, vc, bd) : 0xFFFFFFFFu) & 0xFFFFu;
+                tot0 = 1; level = 1; cb = FL_MAX_NODES;
+                const unsigned s0 = A.sid0[h];
+                if (sid != 0xFFFFu && s0 != 0xFFFFu && sd[s0] != FL_DIST_INF) {
+                    const uint32_t g0 = gt[s0];                                               // how the own path leaves the root cell
+                    onp = ((g0 >> 16) & 0x3FFFu) ? true : sid == (g0 & 0xFFFFu);             // along the walk (one child) or into the greedy child
                 }
-                kind = hit ? 4 : (skind == WK_BAD ? 3 : skind);
-                if (!hit && skind == WK_BAD) bad = true;                     // treeobs.cpp:527-535 throws
-                wx = w.x; kunus = w.w >> 16; c01 = w.z; c2 = w.w & 0xFFFFu;
-                cb = le + 3 * __popc(lmask & ((1u << n) - 1u));
-                if (onp && !hit) gnx = gt[sid] & 0xFFFFu;
             }
-            if (le >= FL_MAX_NODES) break;
-            const int nle = min(FL_MAX_NODES, le + 3 * __popc(lmask));
-            const bool pull = n >= le && n < nle;
-            const int rt = pull ? (n - le) / 3 : 0, j = pull ? (n - le) - 3 * rt : 0;
-            if (real_l) cmp_s[__popc(lmask & ((1u << n) - 1u))] = (uint8_t)n;     // r-th real node of the level
-            __syncwarp();
-            const int p = pull ? (int)cmp_s[rt] : 0;
-            __syncwarp();
-            const unsigned pz = __shfl_sync(0xFFFFFFFFu, c01, p), pw = __shfl_sync(0xFFFFFFFFu, c2, p);
-            const int pk = __shfl_sync(0xFFFFFFFFu, kind, p), ptot = __shfl_sync(0xFFFFFFFFu, tot0 + kend + 1, p);
-            const unsigned pg = __shfl_sync(0xFFFFFFFFu, gnx, p);
-            if (pull) {
-                unsigned cs = j == 0 ? (pz & 0xFFFFu) : j == 1 ? (pz >> 16) : pw;
-                if (pk > 2) cs = 0xFFFFu;
-                sid = cs; tot0 = ptot; parent = p; ad = j - 1; level = cur + 1; cb = FL_MAX_NODES;
-                onp = cs != 0xFFFFu && cs == pg; gnx = 0xFFFFu;
+            int ls = 1, le = 4, cur = 1;
+            count = 4;
+            bool bad = false;
+            while (true) {
+                const bool real_l = n >= ls && n < le && sid != 0xFFFFu;
+                const unsigned lmask = __ballot_sync(0xFFFFFFFFu, real_l);
+                if (!lmask) break;
+                if (real_l) {
+                    const uint4 w = wrec[sid];
+                    const int L = (int)(w.y & 0xFFFFu), skind = (int)((w.y >> 16) & 15u), nh = (int)((w.y >> 20) & 255u);
+                    kend = L;
+                    bool hit = false;
+                    if (nh) {                                                    // the observer's own target ends the walk early
+                        const uint32_t ho = whoff[sid];
+                        for (int q = 0; q < nh; q++) {
+                            const uint32_t hv = whits[ho + q];
+                            if ((hv >> 16) == slot) { kend = (int)(hv & 0xFFFFu); hit = true; break; }
+                        }
+                    }
+                    kind = hit ? 4 : (skind == WK_BAD ? 3 : skind);
+                    if (!hit && skind == WK_BAD) bad = true;                     // treeobs.cpp:527-535 throws
+                    wx = w.x; kunus = w.w >> 16; c01 = w.z; c2 = w.w & 0xFFFFu;
+                    cb = le + 3 * __popc(lmask & ((1u << n) - 1u));
+                    if (onp && !hit) gnx = gt[sid] & 0xFFFFu;
+                }
+                if (le >= FL_MAX_NODES) break;
+                const int nle = min(FL_MAX_NODES, le + 3 * __popc(lmask));
+                const bool pull = n >= le && n < nle;
+                const int rt = pull ? (n - le) / 3 : 0, j = pull ? (n - le) - 3 * rt : 0;
+                if (real_l) cmp_s[__popc(lmask & ((1u << n) - 1u))] = (uint8_t)n;     // r-th real node of the level
+                __syncwarp();
+                const int p = pull ? (int)cmp_s[rt] : 0;
+                __syncwarp();
+                const unsigned pz = __shfl_sync(0xFFFFFFFFu, c01, p), pw = __shfl_sync(0xFFFFFFFFu, c2, p);
+                const int pk = __shfl_sync(0xFFFFFFFFu, kind, p), ptot = __shfl_sync(0xFFFFFFFFu, tot0 + kend + 1, p);
+                const unsigned pg = __shfl_sync(0xFFFFFFFFu, gnx, p);
+                if (pull) {
+                    unsigned cs = j == 0 ? (pz & 0xFFFFu) : j == 1 ? (pz >> 16) : pw;
+                    if (pk > 2) cs = 0xFFFFu;
+                    sid = cs; tot0 = ptot; parent = p; ad = j - 1; level = cur + 1; cb = FL_MAX_NODES;
+                    onp = cs != 0xFFFFu && cs == pg; gnx = 0xFFFFu;
+                }
+                ls = le; le = nle; count = nle; cur++;
             }
-            ls = le; le = nle; count = nle; cur++;
+            if (bad) { if (G > 1) atomicOr(&b.status[e], FL_ST_BAD_CELL); else s_misc[3] = 1; }
+            exists = n < count;
+            real = n >= 1 && exists && sid != 0xFFFFu;
+            // evaluation orders (tool.h:468-524): node_order = height above the leaves, bottom level first
+            order = exists ? 0 : -2;
+            for (int lev = cur; lev >= 0; lev--) {
+                const int c0 = min(cb, 31);
+                const int o0 = __shfl_sync(0xFFFFFFFFu, order, c0), o1 = __shfl_sync(0xFFFFFFFFu, order, min(cb + 1, 31)),
+                          o2 = __shfl_sync(0xFFFFFFFFu, order, min(cb + 2, 31));
+                if (level == lev && (n == 0 || real) && cb < count) {
+                    int m = o0;
+                    if (cb + 1 < count) m = max(m, o1);
+                    if (cb + 2 < count) m = max(m, o2);
+                    order = m + 1;
+                }
+            }
+            porder = __shfl_sync(0xFFFFFFFFu, order, parent);
+            if (real && kind != 4) dv_end = sd[wlist[wx + kend] & 0xFFFFu];
+            if (tc && !bad) {                                                             // (a bad cell keeps raising its status bit)
+                tc[lane] = n == 31 ? tkey : (sid & 0xFFFFu) | ((uint32_t)kend << 16);
+                tc[32 + lane] = wx; tc[64 + lane] = (uint32_t)tot0;
+                tc[96 + lane] = (kunus & 0xFFFFu) | (dv_end << 16);
+                tc[128 + lane] = (uint32_t)kind | ((uint32_t)parent << 3) | ((uint32_t)(ad + 1) << 8) | ((uint32_t)onp << 10) |
+                                 ((uint32_t)exists << 11) | ((uint32_t)(order + 2) << 12) | ((uint32_t)(porder + 2) << 18) |
+                                 ((uint32_t)count << 24);
+            }
         }
-        if (bad) { if (G > 1) atomicOr(&b.status[e], FL_ST_BAD_CELL); else s_misc[3] = 1; }
-        const bool exists = n < count;
-        const bool real = n >= 1 && exists && sid != 0xFFFFu;
-        // evaluation orders (tool.h:468-524): node_order = height above the leaves, bottom level first
-        int order = exists ? 0 : -2;
-        for (int lev = cur; lev >= 0; lev--) {
-            const int c0 = min(cb, 31);
-            const int o0 = __shfl_sync(0xFFFFFFFFu, order, c0), o1 = __shfl_sync(0xFFFFFFFFu, order, min(cb + 1, 31)),
-                      o2 = __shfl_sync(0xFFFFFFFFu, order, min(cb + 2, 31));
-            if (level == lev && (n == 0 || real) && cb < count) {
-                int m = o0;
-                if (cb + 1 < count) m = max(m, o1);
-                if (cb + 2 < count) m = max(m, o2);
-                order = m + 1;
-            }
-        }
-        const int porder = __shfl_sync(0xFFFFFFFFu, order, parent);
         // ---- features: the flat list of the cells of all walks of the agent, 32 cells at a time ----
-        // the distance to the target from the state the walk ends on: loaded now, used when the node is written
-        unsigned dv_end = 0;
-        if (real && kind != 4) dv_end = sd[wlist[wx + kend] & 0xFFFFu];
         const unsigned len = real ? (unsigned)kend + 1u : 0u;
         unsigned total;
         const unsigned off = warp_excl_scan(len, lane, total);

@@ -69,6 +69,8 @@ __global__ void k_reset(FlBatch b, const uint8_t *__restrict__ mask, uint32_t fl
     const int e = blockIdx.x;
     if (mask && !mask[e]) return;
     reset_env(b, e, !(flags & FL_RESET_KEEP_SCHEDULE), (flags & FL_RESET_KEEP_ARRIVAL) != 0);
+    if (b.tree_cache)                               // a reset may follow an upload: drop the cached tree structures
+        for (int i = threadIdx.x; i < (int)b.N; i += blockDim.x) b.tree_cache[((size_t)e * b.N + i) * FL_TREE_CACHE_WORDS + 31] = 0u;
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -115,6 +115,9 @@ __global__ void __launch_bounds__(NT) k_walks(FlBatch b, const int32_t *__restri
     uint16_t *ridx = b.ridx + (size_t)e * b.ridx_stride;
     int32_t *tot = b.walk_total + (size_t)e * 4;
 
+    // new tables: every cached tree structure of the environment is stale (observe.cuh; lane 31's first word is the key)
+    if (FILL && b.tree_cache)
+        for (int i = tid; i < (int)b.N; i += NT) b.tree_cache[((size_t)e * b.N + i) * FL_TREE_CACHE_WORDS + 31] = 0u;
     for (int k = tid; k < (HW + 31) / 32; k += NT) s_tbits[k] = 0;
     __syncthreads();
     for (int s = tid; s < (int)b.n_slots; s += NT) {

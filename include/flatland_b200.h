@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define FL_ABI_VERSION 3
+#define FL_ABI_VERSION 4
 
 /* fixed by the reference (solution/impl_config.py:4-21, flatland_cutils/src/tool.h:67-93) */
 #define FL_MAX_NODES 31     /* num_tree_obs_nodes = 1 + 3*10 */
@@ -149,7 +149,13 @@ typedef struct FlBatch {
     uint32_t *obs_ws;     /* [E][ws_stride] split launch of fl_observe (k_observe as two kernels, see csrc/observe.cuh): the
                                        prediction index of an environment between the index kernel and the tree kernel.
                                        NULL = fl_observe always runs the fused kernel */
+    uint32_t *tree_cache; /* [E][N][FL_TREE_CACHE_WORDS] the structure of every agent's branch tree (which walk each of the 31
+                                       nodes stands for, where it ends, parents, evaluation orders) as fl_observe left it,
+                                       keyed by the agent's rail state: the structure is a function of the static walk
+                                       tables and the agent's (cell, direction) alone, and most agents stand where they stood
+                                       a step ago.  Invalidated by fl_walk_tables / fl_reset.  NULL = recomputed every step */
 } FlBatch;
+#define FL_TREE_CACHE_WORDS 160 /* 5 words per lane of the agent's warp; lane 31 (no node) holds the key */
 
 int fl_abi_version(void);
 size_t fl_batch_sizeof(void);

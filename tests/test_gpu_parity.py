@@ -37,6 +37,8 @@ PLANS = [
     {"parts": 0, "nt": 128, "group": 5, "segcap": 3, "sortsmall": 1}, {"parts": 0, "group": 3, "nt": 256}, {"parts": 0, "group": 7, "nt": 64},
     {"parts": 0, "nt": 128, "group": 6, "tables": 0}, {"parts": 0, "group": 2, "nt": 256},
     {"sortsmall": 40}, {"sortsmall": 40, "parts": 2, "entcap": 0}, {"parts": 0, "nt": 160}, {"parts": 0, "nt": 192, "entcap": 0},
+    # tree structures recomputed every step instead of taken from FlBatch.tree_cache (the default, which every other plan runs)
+    {"treecache": 0}, {"treecache": 0, "parts": 2}, {"treecache": 0, "parts": 0, "nt": 128, "group": 7},
 ]
 
 
