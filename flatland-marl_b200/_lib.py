@@ -15,13 +15,13 @@ RESET_KEEP_SCHEDULE, RESET_KEEP_ARRIVAL = 1, 2
 # field order of struct FlBatch (include/flatland_b200.h)
 _FIELDS = [("E", "i"), ("N", "i"), ("H", "i"), ("W", "i"), ("n_slots", "i"), ("S", "i"), ("ent_cap", "i"), ("grid_stride", "i"),
            ("dist_stride", "i"), ("debug_clocks", "p"), ("ridx_stride", "i"), ("state_stride", "i"), ("wlist_stride", "i"),
-           ("whits_stride", "i"), ("seg_stride", "i"), ("ws_stride", "i")]
+           ("whits_stride", "i"), ("seg_stride", "i"), ("pc_stride", "i"), ("ws_stride", "i")]
 _PTR = ["grid", "slot_rc", "dist", "max_steps", "init_rc", "tgt_rc", "init_dir", "max_count", "slot", "speed",
         "earliest", "latest", "sched", "ridx", "srec", "wrec", "whoff", "wlist", "whits", "kcls", "sdist", "gtab", "walk_total",
         "rc", "old_rc", "dir", "old_dir", "state", "ctr", "mal", "saved", "sig_mal", "deadlocked", "done", "nmal",
         "arrival",
         "elapsed", "sched_pos", "done_all", "status", "stats",
-        "entries", "segs", "obs_ws", "tree_cache"]
+        "entries", "segs", "obs_ws", "tree_cache", "path_cache"]
 TREE_CACHE_WORDS = 160
 
 

@@ -99,10 +99,10 @@ int align_up(int v, int a) { return (v + a - 1) / a * a; }
 
 // Plan overrides (fl_observe_override; tuning and tests only).  -1 = default.  Seeded once from FL_OBS_<KEY> environment
 // variables when the library is loaded; the launch path reads these atomics, never the environment.
-enum ObsKnob : int { KNOB_NT = 0, KNOB_CTAS, KNOB_TABLES, KNOB_SEGCAP, KNOB_ENTCAP, KNOB_SORTSMALL, KNOB_PARTS, KNOB_BMGLOBAL, KNOB_TREENT, KNOB_FLATWALK, KNOB_GROUP, KNOB_EXP, KNOB_TREECACHE, KNOB_COUNT };
-const char *const kKnobNames[KNOB_COUNT] = {"nt", "ctas", "tables", "segcap", "entcap", "sortsmall", "parts", "bmglobal", "treent", "flatwalk", "group", "exp", "treecache"};
+enum ObsKnob : int { KNOB_NT = 0, KNOB_CTAS, KNOB_TABLES, KNOB_SEGCAP, KNOB_ENTCAP, KNOB_SORTSMALL, KNOB_PARTS, KNOB_BMGLOBAL, KNOB_TREENT, KNOB_FLATWALK, KNOB_GROUP, KNOB_EXP, KNOB_TREECACHE, KNOB_PATHCACHE, KNOB_COUNT };
+const char *const kKnobNames[KNOB_COUNT] = {"nt", "ctas", "tables", "segcap", "entcap", "sortsmall", "parts", "bmglobal", "treent", "flatwalk", "group", "exp", "treecache", "pathcache"};
 const char *const kKnobEnv[KNOB_COUNT] = {"FL_OBS_NT", "FL_OBS_CTAS", "FL_OBS_TABLES", "FL_OBS_SEGCAP", "FL_OBS_ENTCAP", "FL_OBS_SORTSMALL", "FL_OBS_PARTS",
-                                          "FL_OBS_BMGLOBAL", "FL_OBS_TREENT", "FL_OBS_FLATWALK", "FL_OBS_GROUP", "FL_OBS_EXP", "FL_OBS_TREECACHE"};
+                                          "FL_OBS_BMGLOBAL", "FL_OBS_TREENT", "FL_OBS_FLATWALK", "FL_OBS_GROUP", "FL_OBS_EXP", "FL_OBS_TREECACHE", "FL_OBS_PATHCACHE"};
 std::atomic<int> g_knob[KNOB_COUNT];
 struct KnobInit {
     KnobInit() {
@@ -152,7 +152,8 @@ ObsLayout make_obs_layout(const FlBatch *b, int nt, int mode, int parts, int *ct
     L.sq_words = L.seg_cap * 2;
     L.flat_walk = knob(KNOB_FLATWALK) >= 0 ? knob(KNOB_FLATWALK) : 3;
     L.exp = knob(KNOB_EXP) >= 0 ? knob(KNOB_EXP) : 0;
-    L.tree_cache = b->tree_cache && knob(KNOB_TREECACHE) != 0;  // "treecache" 0: recompute every tree's structure every step
+    L.tree_cache = b->tree_cache && knob(KNOB_TREECACHE) != 0;
+    L.path_cache = b->path_cache && b->pc_stride >= 2 && knob(KNOB_PATHCACHE) != 0;   // "pathcache" 0: every predicted path walked every step  // "treecache" 0: recompute every tree's structure every step
     int seg_cap_use = L.seg_cap;                                // "segcap" / "entcap" overrides (tests): smaller capacities in
     if (knob(KNOB_SEGCAP) >= 0 && knob(KNOB_SEGCAP) < seg_cap_use) seg_cap_use = knob(KNOB_SEGCAP);                            // the same room,
     L.sq = take((long long)L.seg_cap * 8);                      // per-warp queues of the full conflict checks / segment pool
@@ -493,7 +494,7 @@ int fl_batch_slice(const FlBatch *b, int64_t e0, int64_t n, FlBatch *out) {
     FL_ADV(rc, N * 2) FL_ADV(old_rc, N * 2) FL_ADV(dir, N) FL_ADV(old_dir, N) FL_ADV(state, N) FL_ADV(ctr, N) FL_ADV(mal, N)
     FL_ADV(saved, N) FL_ADV(sig_mal, N) FL_ADV(deadlocked, N) FL_ADV(done, N) FL_ADV(nmal, N) FL_ADV(arrival, N)
     FL_ADV(elapsed, 1) FL_ADV(sched_pos, 1) FL_ADV(done_all, 1) FL_ADV(status, 1)
-    FL_ADV(stats, 4) FL_ADV(entries, b->ent_cap) FL_ADV(segs, b->seg_stride) FL_ADV(debug_clocks, 32) FL_ADV(obs_ws, b->ws_stride) FL_ADV(tree_cache, b->N * FL_TREE_CACHE_WORDS)
+    FL_ADV(stats, 4) FL_ADV(entries, b->ent_cap) FL_ADV(segs, b->seg_stride) FL_ADV(debug_clocks, 32) FL_ADV(obs_ws, b->ws_stride) FL_ADV(tree_cache, b->N * FL_TREE_CACHE_WORDS) FL_ADV(path_cache, b->N * b->pc_stride)
 #undef FL_ADV
     return FL_OK;
 }

@@ -39,6 +39,7 @@ struct ObsLayout {   // byte offsets into dynamic shared memory (host: make_obs_
     int bar, part, cmp, ag, dl, ci, ks, bm, sq, seg_cap, sort_small, kcls, grid, ridx, ent, ent_cap, total;
     int srec, wrec, whoff, whits, wlist, sdist;   // static walk tables (walks.cuh)
     int sq_words;                                 // uint32 words of the sq region (seg_cap may be lowered by a test override)
+    int path_cache;                               // FlBatch.path_cache is in use (the "pathcache" knob turns it off)
     int tree_cache;                               // FlBatch.tree_cache is in use (the "treecache" knob turns it off)
     int exp;                                      // experiment switches (fl_observe_override "exp"; tuning only, none in use)
     int flat_walk;                                // path segments walked by warps as flat lists: bit 0 counting pass, bit 1 scatter pass
@@ -702,11 +703,25 @@ k_observe(FlBatch b, ObsLayout lay, float *__restrict__ out_attr, float *__restr
                                                                       // agent | first path index << 10 | direction after << 19 | last << 21
         uint2 *pool_g = reinterpret_cast<uint2 *>(b.segs) + (size_t)e * b.seg_stride;   // segments beyond the shared-memory pool
         const int seg_gcap = b.segs ? (int)b.seg_stride : 0;
+        // Path cache (FlBatch.path_cache): the elements of an agent's predicted path — rail key and index entry, rows counted
+        // from "now" — depend on the static tables and the agent's (cell, direction, rows per cell, done) alone.  An agent
+        // whose key matches what the cache holds takes its elements from there (two streaming passes, no walk); the others
+        // are walked as before and leave their elements behind for the next step.  pc_n[i]: elements of agent i, | 0x10000
+        // when they come from the cache (the room of A.initcell, which only the occupancy pass of phase 1 reads).
+        uint2 *const pcache = lay.path_cache ? reinterpret_cast<uint2 *>(b.path_cache) + (size_t)e * N * b.pc_stride : nullptr;
+        const int PC = (int)b.pc_stride;
+        int *const pc_n = A.initcell;
+        auto path_key = [&](int i) { const uint32_t inf = A.info[i]; return 0x80000000u | (((inf >> 5) & 1u) << 24) | ((inf >> 24) << 16) | (A.sid0[i] & 0xFFFFu); };
         for (int i = tid; i < N; i += NW) {
             const uint32_t info = A.info[i];
             const unsigned slot = (info >> 8) & 0xFFFFu;
             unsigned sid = A.sid0[i];
+            pc_n[i] = 0;
             if (sid == 0xFFFFu) continue;
+            if (pcache) {
+                const uint2 hdr = pcache[(size_t)i * PC];
+                if (hdr.x == path_key(i)) { pc_n[i] = (int)(hdr.y | 0x10000u); continue; }
+            }
             const int tpc = (int)(info >> 24);
             const uint32_t *gt = gtab + (size_t)slot * SS;
             unsigned dp = sid & 3u;
@@ -838,14 +853,25 @@ k_observe(FlBatch b, ObsLayout lay, float *__restrict__ out_attr, float *__restr
             }
         };
         auto count_emit = [&](unsigned rail, int, int, uint32_t) { atomicAdd(&ks[kcls ? (unsigned)kcls[rail] : rail], 1u); };
+        // the cached paths: a warp per agent, a lane per element
+        auto for_cached = [&](auto fn) {
+            if (!pcache) return;
+            for (int i = warp; i < N; i += NW / 32) {
+                const int pn = pc_n[i];
+                if (!(pn & 0x10000)) continue;
+                const uint2 *lst = pcache + (size_t)i * PC + 1;
+                for (int j = lane; j < (pn & 0xFFFF); j += 32) fn(lst[j]);
+            }
+        };
         // counting pass: entries per rail cell (or key class)
         if (pooled) { if (lay.flat_walk & 1) emit_pool_flat(false, count_emit); else for (int j = tid; j < n_seg; j += NW) emit_segment(j, count_emit); }
         else
             for (int i = tid; i < N; i += NW) {
                 const uint32_t info = A.info[i];
                 const unsigned slot = (info >> 8) & 0xFFFFu, s0 = A.sid0[i];
-                if (s0 != 0xFFFFu) predict_path(wrec, whoff, whits, wlist, sdist + (size_t)slot * SS, s0, slot, (int)(info >> 24), i, entry_extra((int)(info >> 24), (info >> 5) & 1u), count_emit);
+                if (s0 != 0xFFFFu && !(pc_n[i] & 0x10000)) predict_path(wrec, whoff, whits, wlist, sdist + (size_t)slot * SS, s0, slot, (int)(info >> 24), i, entry_extra((int)(info >> 24), (info >> 5) & 1u), count_emit);
             }
+        for_cached([&](uint2 el) { atomicAdd(&ks[el.x], 1u); });
         named_bar_sync(BAR_B, NW);
         OBS_TICK(2);
         // exclusive scan of ks[0..R] (R+1 values; the last becomes the total)
@@ -873,8 +899,7 @@ k_observe(FlBatch b, ObsLayout lay, float *__restrict__ out_attr, float *__restr
         if (tid == 0) s_misc[0] = n_ent;
         if (n_ent > lay.ent_cap) ent = b.entries + (size_t)e * b.ent_cap;   // does not fit in shared memory: global spill space
         // scatter pass.  ks[key] is advanced to the END of its bucket; bucket r is [ks[r-1], ks[r]) afterwards (ks[-1] = 0).
-        auto scatter_emit = [&](unsigned rail, int t0, int t1, uint32_t en) {
-            const unsigned key = kcls ? (unsigned)kcls[rail] : rail;
+        auto scatter_key = [&](unsigned key, int t0, int t1, uint32_t en) {
             ent[atomicAdd(&ks[key], 1u)] = en;
             const int sa = t0 >> 2, sb = t1 >> 2;             // time slots of 4 rows the entry overlaps
             for (int wd = sa >> 5; wd <= sb >> 5; wd++) {
@@ -885,14 +910,34 @@ k_observe(FlBatch b, ObsLayout lay, float *__restrict__ out_attr, float *__restr
                 if (twice) { if (bm_smem) atomicOr(&bm_s[key * 4 + wd].y, twice); else atomicOr(&w2->y, twice); }
             }
         };
+        auto scatter_emit = [&](unsigned rail, int t0, int t1, uint32_t en) {
+            const unsigned key = kcls ? (unsigned)kcls[rail] : rail;
+            scatter_key(key, t0, t1, en);
+            if (pcache) {                              // a walked path leaves its elements in the cache: element idx at slot 1 + idx
+                const int ag = (int)(en & 1023u), tpc = entry_tpc(en, A.info);
+                const int idx = t0 ? (t0 - 1) / tpc + 1 : 0;
+                if (idx + 1 < PC) pcache[(size_t)ag * PC + 1 + idx] = make_uint2(key, en);
+                atomicMax(&pc_n[ag], idx + 1);
+            }
+        };
         if (pooled) { if (lay.flat_walk & 2) emit_pool_flat(true, scatter_emit); else for (int j = tid; j < n_seg; j += NW) emit_segment(j, scatter_emit); }
         else
             for (int i = tid; i < N; i += NW) {
                 const uint32_t info = A.info[i];
                 const unsigned slot = (info >> 8) & 0xFFFFu, s0 = A.sid0[i];
-                if (s0 != 0xFFFFu) predict_path(wrec, whoff, whits, wlist, sdist + (size_t)slot * SS, s0, slot, (int)(info >> 24), i, entry_extra((int)(info >> 24), (info >> 5) & 1u), scatter_emit);
+                if (s0 != 0xFFFFu && !(pc_n[i] & 0x10000)) predict_path(wrec, whoff, whits, wlist, sdist + (size_t)slot * SS, s0, slot, (int)(info >> 24), i, entry_extra((int)(info >> 24), (info >> 5) & 1u), scatter_emit);
             }
+        for_cached([&](uint2 el) {
+            const uint32_t en = el.y;
+            const int t0 = entry_t0(en);
+            scatter_key(el.x, t0, entry_long_lived(en) ? NPRED - 1 : (t0 ? t0 + entry_tpc(en, A.info) - 1 : 0), en);
+        });
         named_bar_sync(BAR_B, NW);
+        if (pcache)                                    // headers of the paths walked in this step (too long for the cache: no key)
+            for (int i = tid; i < N; i += NW) {
+                const int pn = pc_n[i];
+                if (pn > 0 && !(pn & 0x10000)) pcache[(size_t)i * PC] = pn < PC ? make_uint2(path_key(i), (uint32_t)pn) : make_uint2(0u, 0u);
+            }
         OBS_TICK(4);
         // order every bucket: long-lived entries first, then by t0, so that the tree walk scans a time window only.
         // Entries in shared memory: buckets up to sort_small by one thread each (insertion sort: 32 buckets per warp at a

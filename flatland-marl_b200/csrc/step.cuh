@@ -71,6 +71,8 @@ __global__ void k_reset(FlBatch b, const uint8_t *__restrict__ mask, uint32_t fl
     reset_env(b, e, !(flags & FL_RESET_KEEP_SCHEDULE), (flags & FL_RESET_KEEP_ARRIVAL) != 0);
     if (b.tree_cache)                               // a reset may follow an upload: drop the cached tree structures
         for (int i = threadIdx.x; i < (int)b.N; i += blockDim.x) b.tree_cache[((size_t)e * b.N + i) * FL_TREE_CACHE_WORDS + 31] = 0u;
+    if (b.path_cache)
+        for (int i = threadIdx.x; i < (int)b.N; i += blockDim.x) b.path_cache[((size_t)e * b.N + i) * b.pc_stride] = 0ull;
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -118,6 +118,8 @@ __global__ void __launch_bounds__(NT) k_walks(FlBatch b, const int32_t *__restri
     // new tables: every cached tree structure of the environment is stale (observe.cuh; lane 31's first word is the key)
     if (FILL && b.tree_cache)
         for (int i = tid; i < (int)b.N; i += NT) b.tree_cache[((size_t)e * b.N + i) * FL_TREE_CACHE_WORDS + 31] = 0u;
+    if (FILL && b.path_cache)
+        for (int i = tid; i < (int)b.N; i += NT) b.path_cache[((size_t)e * b.N + i) * b.pc_stride] = 0ull;
     for (int k = tid; k < (HW + 31) / 32; k += NT) s_tbits[k] = 0;
     __syncthreads();
     for (int s = tid; s < (int)b.n_slots; s += NT) {

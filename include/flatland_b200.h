@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define FL_ABI_VERSION 4
+#define FL_ABI_VERSION 5
 
 /* fixed by the reference (solution/impl_config.py:4-21, flatland_cutils/src/tool.h:67-93) */
 #define FL_MAX_NODES 31     /* num_tree_obs_nodes = 1 + 3*10 */
@@ -80,6 +80,7 @@ typedef struct FlBatch {
     int64_t wlist_stride;  /* uint32 elements per env of wlist, multiple of 4, with 8 elements of slack at the end */
     int64_t whits_stride;  /* uint32 elements per env of whits, multiple of 4 */
     int64_t seg_stride;    /* uint64 elements per env of segs (0 = none) */
+    int64_t pc_stride;     /* uint2 elements per AGENT of path_cache: 1 header + the longest predicted path it can hold (0 = none) */
     int64_t ws_stride;     /* uint32 elements per env of obs_ws: >= fl_observe_ws_words(b), multiple of 4 (0 = none: fused kernel only) */
 
     /* ---- world, static after upload (RailEnv.reset generators stay reference Python) ---- */
@@ -154,6 +155,11 @@ typedef struct FlBatch {
                                        keyed by the agent's rail state: the structure is a function of the static walk
                                        tables and the agent's (cell, direction) alone, and most agents stand where they stood
                                        a step ago.  Invalidated by fl_walk_tables / fl_reset.  NULL = recomputed every step */
+    uint64_t *path_cache; /* [E][N][pc_stride] (key class of the rail cell, index entry) of every element of an agent's predicted
+                                       path as fl_observe last computed it, behind a header (key, elements): the predicted
+                                       path and its timing relative to "now" are a function of the static tables and the
+                                       agent's (cell, direction, speed, done) alone.  Invalidated like tree_cache.  NULL = the
+                                       paths are walked every step */
 } FlBatch;
 #define FL_TREE_CACHE_WORDS 160 /* 5 words per lane of the agent's warp; lane 31 (no node) holds the key */
 

@@ -57,7 +57,7 @@ def test_policy_library_exports_every_declared_symbol(lib):
 
 def test_struct_layout_and_version(lib):
     import flatland_marl_b200 as fb
-    assert lib.fl_abi_version() == 4
+    assert lib.fl_abi_version() == 5
     assert lib.fl_batch_sizeof() == C.sizeof(fb._lib.FlBatch)
     assert lib.fl_profile_num_kernels() >= 4
     assert lib.fl_error_string(0) == b"ok"

@@ -39,6 +39,8 @@ PLANS = [
     {"sortsmall": 40}, {"sortsmall": 40, "parts": 2, "entcap": 0}, {"parts": 0, "nt": 160}, {"parts": 0, "nt": 192, "entcap": 0},
     # tree structures recomputed every step instead of taken from FlBatch.tree_cache (the default, which every other plan runs)
     {"treecache": 0}, {"treecache": 0, "parts": 2}, {"treecache": 0, "parts": 0, "nt": 128, "group": 7},
+    # predicted paths walked every step instead of taken from FlBatch.path_cache; the cache under the other index plans
+    {"pathcache": 0}, {"pathcache": 0, "treecache": 0, "parts": 2}, {"pathcache": 1, "segcap": 0, "entcap": 0}, {"pathcache": 1, "flatwalk": 0, "parts": 0, "nt": 128, "group": 5},
 ]
 
 
