@@ -657,17 +657,12 @@ k_observe(FlBatch b, ObsLayout lay, float *__restrict__ out_attr, float *__restr
     }
     OBS_TICK(1);
 
-    // ---- phase 2 (lane 0 of the last warp): deadlocks; phase 3: predictions ----
-    // Split launch (index kernel): the last warp runs the serial deadlock lane WHILE the other warps build the prediction index
-    // (named barrier B) and joins them afterwards.  Fused kernel: all warps build the index, then the last warp runs the
-    // deadlock lane while the others already walk trees — a quarter more threads on the index (4 instead of 3 warps at the
-    // headline shape), and the serial lane still hides behind parallel work.
-#ifndef FL_DL_LATE
-#define FL_DL_LATE 0    // measured on one box: 0.429 ms with, 0.400 ms without (profiles/r02_n_ab.txt)
-#endif
-    constexpr bool DL_LATE = MODE == OBS_FUSED && FL_DL_LATE;
+    // ---- phase 2 (lane 0 of the last warp): deadlocks; phase 3 (the other warps, named barrier B): predictions ----
+    // The last warp runs the serial deadlock lane WHILE the other warps build the prediction index and joins the tree phase
+    // afterwards.  (Building the index with all warps and running the lane beside the tree phase instead was measured: 9 % more
+    // instructions, 7 % more time — profiles/r02_n_ab.txt.)
     const bool dl_warp = warp == NT / 32 - 1;
-    constexpr int NW = DL_LATE ? NT : NT - 32;     // threads walking predictions
+    constexpr int NW = NT - 32;                    // threads walking predictions
     auto run_deadlocks = [&]() {
         if (lane == 0) { update_deadlocks(D, N); if (dbg) dbg[8] = clock64(); }
         __syncwarp();
@@ -691,7 +686,7 @@ k_observe(FlBatch b, ObsLayout lay, float *__restrict__ out_attr, float *__restr
             }
         }
     };
-    if (dl_warp && !DL_LATE) {
+    if (dl_warp) {
         run_deadlocks();
         asm volatile("bar.sync %0, %1;" ::"r"(BAR_C), "r"(NT) : "memory");    // the prediction index is complete (the other warps only arrive)
         if (s_misc[0] > lay.ent_cap) ent = b.entries + (size_t)e * b.ent_cap;
@@ -1084,8 +1079,7 @@ k_observe(FlBatch b, ObsLayout lay, float *__restrict__ out_attr, float *__restr
                 for (int k = tid; k < n_ent; k += NW) ge[k] = ent_s[k];
             }
         }
-        if (!DL_LATE) asm volatile("bar.arrive %0, %1;" ::"r"(BAR_C), "r"(NT) : "memory");  // lets the deadlock warp go on when it is done
-        if (DL_LATE && dl_warp) run_deadlocks();
+        asm volatile("bar.arrive %0, %1;" ::"r"(BAR_C), "r"(NT) : "memory");  // lets the deadlock warp go on when it is done
     }
     OBS_TICK(3);
     if (dbg && tid == 0) dbg[10] = s_misc[0];
@@ -1150,13 +1144,8 @@ k_observe(FlBatch b, ObsLayout lay, float *__restrict__ out_attr, float *__restr
         const Scale sc{T_, __frcp_rn(T_), Nf, __frcp_rn(Nf)};
         // one generic load (address + LD) wherever the entries live; selecting between a typed shared-memory load and a global
         // one per access compiles to a branch with a reconvergence point around every load: 8 instructions instead of 2
-#ifndef FL_V_GENERIC
-#define FL_V_GENERIC 1
-#endif
-#ifndef FL_V_ACC
-#define FL_V_ACC 1
-#endif
-        auto ent_at = [&](uint32_t i) { return FL_V_GENERIC ? ent[i] : (spill ? ent[i] : ent_s[i]); };
+        // (-4.7 % of the kernel's instructions, profiles/r02_o_ab.txt)
+        auto ent_at = [&](uint32_t i) { return ent[i]; };
         const size_t ea = (size_t)e * N + h;
         const uint32_t ainfo = A.info[h];
         const unsigned slot = (ainfo >> 8) & 0xFFFFu;
@@ -1329,8 +1318,7 @@ k_observe(FlBatch b, ObsLayout lay, float *__restrict__ out_attr, float *__restr
                     if (pt < NPRED && tot < NPRED) {                                 // treeobs.cpp:379-465
                         const unsigned bk = kcls ? (unsigned)kcls[rail] : rail;    // the reference's position key c*W + r
                         const int sa = max(0, pt - 1) >> 2, sb = min(NPRED - 1, pt + 1) >> 2;
-                        const uint2 wa = FL_V_GENERIC ? bm[bk * 4 + (sa >> 5)] : (bm_smem ? bm_s[bk * 4 + (sa >> 5)] : bm[bk * 4 + (sa >> 5)]);
-                        const uint2 wb = FL_V_GENERIC ? bm[bk * 4 + (sb >> 5)] : (bm_smem ? bm_s[bk * 4 + (sb >> 5)] : bm[bk * 4 + (sb >> 5)]);
+                        const uint2 wa = bm[bk * 4 + (sa >> 5)], wb = bm[bk * 4 + (sb >> 5)];
                         // On the own path the observer's own entry (path element tot, rows t0o..t1o) is in the index too: a slot it
                         // covers needs a second entry to matter.  (t1o is a lower bound for the last element: errs towards checking.)
                         bool own_a = false, own_b = false;
@@ -1396,12 +1384,8 @@ k_observe(FlBatch b, ObsLayout lay, float *__restrict__ out_attr, float *__restr
                         const int pdir = pt < t0 ? dpv : (pt > t1 ? dn : dh);  // always the direction at row pt
                         const bool cf = (d != pdir && tbit(nb, (pdir + 2) & 3)) || done;
                         const bool other = ag != h;
-                        if (FL_V_ACC) {
-                            const unsigned m_in = (in_cur ? 1u : 0u) | (in_pre ? 2u : 0u) | (in_post ? 4u : 0u);   // rows of the window the entry covers
-                            acc |= (other ? m_in : 0u) | (cf ? m_in << 3 : 0u);
-                        } else
-                        acc |= (in_cur && other ? 1u : 0u) | (in_pre && other ? 2u : 0u) | (in_post && other ? 4u : 0u) |
-                               (in_cur && cf ? 8u : 0u) | (in_pre && cf ? 16u : 0u) | (in_post && cf ? 32u : 0u);
+                        const unsigned m_in = (in_cur ? 1u : 0u) | (in_pre ? 2u : 0u) | (in_post ? 4u : 0u);   // rows of the window the entry covers
+                        acc |= (other ? m_in : 0u) | (cf ? m_in << 3 : 0u);
                     };
                     uint32_t idx = s0;
                     for (; idx < s1; idx++) {                                    // long-lived entries come first
@@ -1429,13 +1413,9 @@ k_observe(FlBatch b, ObsLayout lay, float *__restrict__ out_attr, float *__restr
                     // treeobs.cpp:379-465: the first of the rows cur, pre, post that holds another agent decides, and it decides
                     // "conflict" when an entry of that row crosses the observer's direction (or belongs to a DONE agent):
                     // (acc & 1) ? (acc & 8) : (acc & 2) ? (acc & 16) : (acc & 4) ? (acc & 32) : false, as a 64-entry bit table
-#ifndef FL_V_CONF
-#define FL_V_CONF 1
-#endif
-                    f_conf = FL_V_CONF ? (bool)((0xfe54ba10ee44aa00ull >> acc) & 1ull)
-                                       : (bool)((acc & 1u) ? (acc & 8u) : (acc & 2u) ? (acc & 16u) : (acc & 4u) ? (acc & 32u) : 0u);
+                    f_conf = (bool)((0xfe54ba10ee44aa00ull >> acc) & 1ull);
                 }
-                if (FL_V_CONF) {
+                {
                     // A node keeps the FIRST conflict of its walk.  The queue holds cells in flat-list order (node after node,
                     // walk step after walk step), so the lowest conflicting lane of a node has it: those lanes leave the step in
                     // a 32-word table indexed by node rank (the room of the queue slots just read), the owners pick it up.
@@ -1450,11 +1430,6 @@ k_observe(FlBatch b, ObsLayout lay, float *__restrict__ out_attr, float *__restr
                         if (real && ((rmask >> my_rank) & 1u)) k_conf = min(k_conf, (int)kc[my_rank]);
                         __syncwarp();
                     }
-                } else
-                for (unsigned mm = __ballot_sync(0xFFFFFFFFu, f_conf); mm; mm &= mm - 1) {   // to the owner by shuffle
-                    const int s = __ffs(mm) - 1;
-                    const unsigned qx = __shfl_sync(0xFFFFFFFFu, q.x, s), qk = __shfl_sync(0xFFFFFFFFu, q.y, s);
-                    if (real && my_rank == (int)((qx >> 16) & 31u)) k_conf = min(k_conf, (int)(qk & 0xFFFFu));
                 }
                 // the rest of the queue moves to the front
                 uint2 mv = make_uint2(0u, 0u);
