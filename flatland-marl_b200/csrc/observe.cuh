@@ -1096,6 +1096,8 @@ k_observe(FlBatch b, ObsLayout lay, float *__restrict__ out_attr, float *__restr
     uint32_t *const ent_home = ent;
     const int tpc_max_home = tpc_max;
     uint2 *const sq_home = sq;
+    const float T_home = T_;
+    const Scale sc_home = sc;
     while (MODE != OBS_INDEX) {
         int h = 0, s_sel = sub;
         if (G == 1) {
@@ -1140,8 +1142,8 @@ k_observe(FlBatch b, ObsLayout lay, float *__restrict__ out_attr, float *__restr
         uint32_t *const ent = G > 1 ? (spill ? V.ent_g : V.ent_s) : ent_home;
         const int tpc_max = G > 1 ? ld_vol_i32(&V.misc[2]) : tpc_max_home;
         uint2 *const sq = sq_home;                  // the queue stays the warp's own
-        const float T_ = G > 1 ? (float)b.max_steps[e] : (float)b.max_steps[e_home];
-        const Scale sc{T_, __frcp_rn(T_), Nf, __frcp_rn(Nf)};
+        const float T_ = G > 1 ? (float)b.max_steps[e] : T_home;
+        const Scale sc = G > 1 ? Scale{T_, __frcp_rn(T_), Nf, __frcp_rn(Nf)} : sc_home;   // (two correctly rounded reciprocals: not per agent)
         // one generic load (address + LD) wherever the entries live; selecting between a typed shared-memory load and a global
         // one per access compiles to a branch with a reconvergence point around every load: 8 instructions instead of 2
         // (-4.7 % of the kernel's instructions, profiles/r02_o_ab.txt)
@@ -1150,7 +1152,6 @@ k_observe(FlBatch b, ObsLayout lay, float *__restrict__ out_attr, float *__restr
         const uint32_t ainfo = A.info[h];
         const unsigned slot = (ainfo >> 8) & 0xFFFFu;
         const uint16_t *sd = sdist + (size_t)slot * SS;
-        const float tpc_f = (float)(1.0 / (double)A.speed[h]);                          // treeobs.cpp:304
         const int n = lane;
         // ---- structure: node n in lane n (treeobs.cpp:171-256 FIFO, 583-608 children) ----
         // Which walk each node stands for, where it ends, parents and evaluation orders follow from the static walk tables and
@@ -1167,8 +1168,10 @@ k_observe(FlBatch b, ObsLayout lay, float *__restrict__ out_attr, float *__restr
         bool cached = false;
         uint32_t cw0 = 0;
         if (tc) { cw0 = tc[lane]; cached = __shfl_sync(0xFFFFFFFFu, cw0, 31) == tkey; }
+        float tpc_f;                                                                      // rows per cell as treeobs.cpp:304 has it
         if (cached) {                                                                     // warp-uniform
             const uint32_t cw1 = tc[32 + lane], cw2 = tc[64 + lane], cw3 = tc[96 + lane], cw4 = tc[128 + lane];
+            tpc_f = __uint_as_float(__shfl_sync(0xFFFFFFFFu, cw1, 31));                   // lane 31 holds no node: its second word keeps the quotient
             sid = cw0 & 0xFFFFu; kend = (int)(cw0 >> 16); wx = cw1; tot0 = (int)cw2;
             kunus = cw3 & 0xFFFFu; dv_end = cw3 >> 16;
             kind = (int)(cw4 & 7u); parent = (int)((cw4 >> 3) & 31u); ad = (int)((cw4 >> 8) & 3u) - 1; onp = (cw4 >> 10) & 1u;
@@ -1177,6 +1180,7 @@ k_observe(FlBatch b, ObsLayout lay, float *__restrict__ out_attr, float *__restr
             if (n == 31) { sid = 0xFFFFu; exists = false; }
             real = n >= 1 && exists && sid != 0xFFFFu;
         } else {
+            tpc_f = (float)(1.0 / (double)A.speed[h]);                                    // (a double-precision division: ~60 instructions)
             unsigned c01 = 0xFFFFFFFFu, c2 = 0xFFFFu;
             int level = 0, cb = 1;                                                            // cb: index of the node's first child
             // onp: the node's walk is part of the observer's own predicted path (its cell at distance tot is path element tot),
@@ -1262,7 +1266,7 @@ k_observe(FlBatch b, ObsLayout lay, float *__restrict__ out_attr, float *__restr
             if (real && kind != 4) dv_end = sd[wlist[wx + kend] & 0xFFFFu];
             if (tc && !bad) {                                                             // (a bad cell keeps raising its status bit)
                 tc[lane] = n == 31 ? tkey : (sid & 0xFFFFu) | ((uint32_t)kend << 16);
-                tc[32 + lane] = wx; tc[64 + lane] = (uint32_t)tot0;
+                tc[32 + lane] = n == 31 ? __float_as_uint(tpc_f) : wx; tc[64 + lane] = (uint32_t)tot0;
                 tc[96 + lane] = (kunus & 0xFFFFu) | (dv_end << 16);
                 tc[128 + lane] = (uint32_t)kind | ((uint32_t)parent << 3) | ((uint32_t)(ad + 1) << 8) | ((uint32_t)onp << 10) |
                                  ((uint32_t)exists << 11) | ((uint32_t)(order + 2) << 12) | ((uint32_t)(porder + 2) << 18) |
@@ -1446,8 +1450,9 @@ k_observe(FlBatch b, ObsLayout lay, float *__restrict__ out_attr, float *__restr
             if (n == 0) {
                 const float dtv = A.dt[h];
                 v0 = make_float4(0.f, 0.f, 0.f, 0.f);
-                v1 = make_float4(0.f, 0.f, dtv != INFINITY ? dtv / T_ : -1.0f, 0.f);
-                v2 = make_float4(0.f, (float)((A.rec_b[h] >> 16) & 1u) / Nf, A.speed[h], 0.f);
+                // (integer-valued operands: div_rn is the IEEE quotient, like every other node feature)
+                v1 = make_float4(0.f, 0.f, dtv != INFINITY ? div_rn(dtv, sc.T, sc.rT) : -1.0f, 0.f);
+                v2 = make_float4(0.f, div_rn((float)((A.rec_b[h] >> 16) & 1u), sc.N, sc.rN), A.speed[h], 0.f);
             } else if (real) {
                 const int tot = tot0 + kend;
                 const bool tb = kind == 4;

@@ -92,3 +92,52 @@ def test_chunked_host_step_equals_device_step():
                 np.testing.assert_array_equal(h[k].numpy(), ref.obs[k].cpu().numpy(), err_msg="%s chunks=%s step %d" % (k, c, t))
             np.testing.assert_array_equal(h["rewards"].numpy(), ref.rewards.cpu().numpy())
             np.testing.assert_array_equal(h["dones"].numpy(), ref.dones.cpu().numpy())
+
+
+@pytest.mark.parametrize("config,n_envs,n_steps", [("Test_03", 96, 260), ("Test_02", 256, 200), ("Test_08", 16, 320)])
+def test_caches_do_not_change_a_byte(config, n_envs, n_steps):
+    """FlBatch.tree_cache / path_cache keep per-agent intermediates of fl_observe under the agent's rail state as key.  Two
+    batches of the same worlds step the same random actions through whole episodes with in-place resets, one with both caches
+    on (the default), one with both off: every observation tensor, reward and done flag must be the same bytes at every step;
+    then the cached batch gets new worlds in some slots (the tables change under the caches) and a mid-episode state upload."""
+    import torch
+    import flatland_marl_b200 as fb
+    lib = fb._lib.lib()
+    worlds = _load(config, n_envs)
+    N = int(worlds[0]["N"])
+    on, off = fb.BatchedRailEnv(worlds, auto_reset=True, reserve=0.5, min_slots=12), fb.BatchedRailEnv(worlds, auto_reset=True, reserve=0.5, min_slots=12)
+
+    def both(fn):
+        out = []
+        for batch, flag in ((on, -1), (off, 0)):
+            for knob in (b"treecache", b"pathcache"):
+                assert lib.fl_observe_override(knob, flag) == 0
+            out.append(fn(batch))
+        return out
+
+    def same(what):
+        for k in on.obs:
+            assert torch.equal(on.obs[k], off.obs[k]), "%s: %s differs with the caches on" % (what, k)
+
+    try:
+        both(lambda b: b.reset())
+        same("reset")
+        rng = np.random.RandomState(11)
+        for t in range(n_steps):
+            # phases of mostly-forward and uniform random actions: trains depart, move, stop and wait
+            p_fwd = 0.8 if (t // 40) % 2 == 0 else 0.0
+            act = torch.from_numpy(np.where(rng.rand(n_envs, N) < p_fwd, 2, rng.randint(0, 5, (n_envs, N))).astype(np.uint8)).to(on.device)
+            (_, r1, d1), (_, r2, d2) = both(lambda b: b.step(act))
+            assert torch.equal(r1, r2) and torch.equal(d1, d2), "step %d rewards / dones" % (t + 1)
+            same("step %d" % (t + 1))
+            if t == n_steps // 2:
+                # new worlds in a few slots of both batches: the walk tables of those slots change under the caches
+                ids = list(range(0, n_envs, max(n_envs // 5, 1)))
+                new = _load(config, len(ids) + n_envs)[n_envs:]
+                both(lambda b: b.replace_worlds(ids, new))
+                both(lambda b: b.observe())
+                same("after replace_worlds")
+        assert int(on.t["status"].max()) & 4 == 0
+    finally:
+        for knob in (b"treecache", b"pathcache"):
+            lib.fl_observe_override(knob, -1)
