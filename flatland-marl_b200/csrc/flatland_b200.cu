@@ -99,10 +99,10 @@ int align_up(int v, int a) { return (v + a - 1) / a * a; }
 
 // Plan overrides (fl_observe_override; tuning and tests only).  -1 = default.  Seeded once from FL_OBS_<KEY> environment
 // variables when the library is loaded; the launch path reads these atomics, never the environment.
-enum ObsKnob : int { KNOB_NT = 0, KNOB_CTAS, KNOB_TABLES, KNOB_SEGCAP, KNOB_ENTCAP, KNOB_SORTSMALL, KNOB_PARTS, KNOB_BMGLOBAL, KNOB_TREENT, KNOB_FLATWALK, KNOB_GROUP, KNOB_EXP, KNOB_TREECACHE, KNOB_PATHCACHE, KNOB_COUNT };
-const char *const kKnobNames[KNOB_COUNT] = {"nt", "ctas", "tables", "segcap", "entcap", "sortsmall", "parts", "bmglobal", "treent", "flatwalk", "group", "exp", "treecache", "pathcache"};
+enum ObsKnob : int { KNOB_NT = 0, KNOB_CTAS, KNOB_TABLES, KNOB_SEGCAP, KNOB_ENTCAP, KNOB_SORTSMALL, KNOB_PARTS, KNOB_BMGLOBAL, KNOB_TREENT, KNOB_FLATWALK, KNOB_GROUP, KNOB_TREECACHE, KNOB_PATHCACHE, KNOB_COUNT };
+const char *const kKnobNames[KNOB_COUNT] = {"nt", "ctas", "tables", "segcap", "entcap", "sortsmall", "parts", "bmglobal", "treent", "flatwalk", "group", "treecache", "pathcache"};
 const char *const kKnobEnv[KNOB_COUNT] = {"FL_OBS_NT", "FL_OBS_CTAS", "FL_OBS_TABLES", "FL_OBS_SEGCAP", "FL_OBS_ENTCAP", "FL_OBS_SORTSMALL", "FL_OBS_PARTS",
-                                          "FL_OBS_BMGLOBAL", "FL_OBS_TREENT", "FL_OBS_FLATWALK", "FL_OBS_GROUP", "FL_OBS_EXP", "FL_OBS_TREECACHE", "FL_OBS_PATHCACHE"};
+                                          "FL_OBS_BMGLOBAL", "FL_OBS_TREENT", "FL_OBS_FLATWALK", "FL_OBS_GROUP", "FL_OBS_TREECACHE", "FL_OBS_PATHCACHE"};
 std::atomic<int> g_knob[KNOB_COUNT];
 struct KnobInit {
     KnobInit() {
@@ -151,7 +151,6 @@ ObsLayout make_obs_layout(const FlBatch *b, int nt, int mode, int parts, int *ct
     if (L.seg_cap < (nt / 32) * 64) L.seg_cap = (nt / 32) * 64;
     L.sq_words = L.seg_cap * 2;
     L.flat_walk = knob(KNOB_FLATWALK) >= 0 ? knob(KNOB_FLATWALK) : 3;
-    L.exp = knob(KNOB_EXP) >= 0 ? knob(KNOB_EXP) : 0;
     L.tree_cache = b->tree_cache && knob(KNOB_TREECACHE) != 0;
     L.path_cache = b->path_cache && b->pc_stride >= 2 && knob(KNOB_PATHCACHE) != 0;   // "pathcache" 0: every predicted path walked every step  // "treecache" 0: recompute every tree's structure every step
     int seg_cap_use = L.seg_cap;                                // "segcap" / "entcap" overrides (tests): smaller capacities in

@@ -41,7 +41,6 @@ struct ObsLayout {   // byte offsets into dynamic shared memory (host: make_obs_
     int sq_words;                                 // uint32 words of the sq region (seg_cap may be lowered by a test override)
     int path_cache;                               // FlBatch.path_cache is in use (the "pathcache" knob turns it off)
     int tree_cache;                               // FlBatch.tree_cache is in use (the "treecache" knob turns it off)
-    int exp;                                      // experiment switches (fl_observe_override "exp"; tuning only, none in use)
     int flat_walk;                                // path segments walked by warps as flat lists: bit 0 counting pass, bit 1 scatter pass
     int parts;                                    // split launch: CTAs per environment of the tree kernel (0 = fused kernel)
     int ws_ag, ws_idx, ws_ag_bytes, ws_idx_bytes; // split launch: byte offsets / sizes of the two blocks of FlBatch.obs_ws
