@@ -256,8 +256,9 @@ int obs_group(const FlBatch *b, int nt) {
     int g = v > 1 ? v : ctas;
     if (g > 7) g = 7;
     while (g > 1 && g * nt > 1024) g--;
+    // the instantiated shapes: 128 threads x 4..7, 256 x 2..3, 64 x 7 environments
     if (nt == 128) { if (g < 4) return 1; }
-    else if (nt == 256) { if (g < 2) return 1; }
+    else if (nt == 256) { if (g < 2) return 1; if (g > 3) g = 3; }
     else if (nt == 64) { if (g < 7) return 1; }
     else return 1;
     {   // the mandatory regions + typical entries must fit the group's per-environment budget
