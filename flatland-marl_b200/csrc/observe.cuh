@@ -854,7 +854,14 @@ k_observe(FlBatch b, ObsLayout lay, float *__restrict__ out_attr, float *__restr
                 const int pn = pc_n[i];
                 if (!(pn & 0x10000)) continue;
                 const uint2 *lst = pcache + (size_t)i * PC + 1;
-                for (int j = lane; j < (pn & 0xFFFF); j += 32) fn(lst[j]);
+                const int n_el = pn & 0xFFFF;
+                for (int j0 = lane; j0 < n_el; j0 += 128) {                  // four loads in flight per lane: the lists are in L2 / HBM
+                    uint2 el[4];
+#pragma unroll
+                    for (int u = 0; u < 4; u++) if (j0 + 32 * u < n_el) el[u] = lst[j0 + 32 * u];
+#pragma unroll
+                    for (int u = 0; u < 4; u++) if (j0 + 32 * u < n_el) fn(el[u]);
+                }
             }
         };
         // counting pass: entries per rail cell (or key class)
@@ -1034,6 +1041,8 @@ k_observe(FlBatch b, ObsLayout lay, float *__restrict__ out_attr, float *__restr
             }
         } else {
             OBS_TICK(9);
+            // (Packing consecutive small buckets into one 32-entry network per pass, a contiguous bucket range per warp, was
+            // measured: nothing at Test_08, the index kernel of Test_14 0.31 -> 0.42 ms — profiles/r02_w_packed_sort.txt.)
             // every non-empty bucket by a warp; the entries of the warp's next two buckets are in flight while the current
             // one is sorted (a bucket costs one L2 / DRAM round trip that nothing else hides at 32 warps per SM)
             auto fetch = [&](int key, int &s0, int &n, uint32_t &v) {
@@ -1134,8 +1143,8 @@ k_observe(FlBatch b, ObsLayout lay, float *__restrict__ out_attr, float *__restr
         const uint16_t *const ridx = V.ridx, *const sdist = V.sdist, *const kcls = V.kcls;
         const uint4 *const wrec = V.wrec;
         const uint32_t *const whoff = V.whoff, *const whits = V.whits, *const wlist = V.wlist, *const gtab = V.gtab;
-        uint32_t *const ci = V.ci, *const ks = V.ks, *const ent_s = V.ent_s;
-        uint2 *const bm = V.bm, *const bm_s = V.bm_s;
+        uint32_t *const ci = V.ci, *const ks = V.ks;
+        uint2 *const bm = V.bm;
         const ObsAgents A = V.A;
         const bool spill = G > 1 ? ld_vol_i32(&V.misc[0]) > lay.ent_cap : spill_home;
         uint32_t *const ent = G > 1 ? (spill ? V.ent_g : V.ent_s) : ent_home;
