@@ -1049,18 +1049,19 @@ k_observe(FlBatch b, ObsLayout lay, float *__restrict__ out_attr, float *__restr
                 n = 0; v = 0u; s0 = 0;
                 if (key < R) { s0 = (int)ks[key - 1]; n = (int)ks[key] - s0; if (n >= 2 && n <= 32 && lane < n) v = ent[s0 + lane]; }
             };
-            int s0a, na, s0b, nb;
-            uint32_t va, vb;
-            fetch(warp, s0a, na, va);
-            fetch(warp + NWARPS, s0b, nb, vb);
+            constexpr int PF = 2;                       // buckets in flight per warp (four measured: no change — profiles/r02_y_prefetch4.txt)
+            int s0q[PF], nq[PF];
+            uint32_t vq[PF];
+#pragma unroll
+            for (int u = 0; u < PF; u++) fetch(warp + u * NWARPS, s0q[u], nq[u], vq[u]);
             for (int key = warp; key < R; key += NWARPS) {
-                int s0x, nx;
-                uint32_t vx;
-                fetch(key + 2 * NWARPS, s0x, nx, vx);
+                const int s0a = s0q[0], na = nq[0];
+                const uint32_t va = vq[0];
+#pragma unroll
+                for (int u = 0; u + 1 < PF; u++) { s0q[u] = s0q[u + 1]; nq[u] = nq[u + 1]; vq[u] = vq[u + 1]; }
+                fetch(key + PF * NWARPS, s0q[PF - 1], nq[PF - 1], vq[PF - 1]);
                 if (na > 32) warp_sort_radix(key, s0a, na);
                 else if (na >= 2) warp_sort_regs(key, s0a, na, va);
-                s0a = s0b; na = nb; va = vb;
-                s0b = s0x; nb = nx; vb = vx;
             }
         }
         named_bar_sync(BAR_B, NW);
