@@ -99,10 +99,10 @@ int align_up(int v, int a) { return (v + a - 1) / a * a; }
 
 // Plan overrides (fl_observe_override; tuning and tests only).  -1 = default.  Seeded once from FL_OBS_<KEY> environment
 // variables when the library is loaded; the launch path reads these atomics, never the environment.
-enum ObsKnob : int { KNOB_NT = 0, KNOB_CTAS, KNOB_TABLES, KNOB_SEGCAP, KNOB_ENTCAP, KNOB_SORTSMALL, KNOB_PARTS, KNOB_BMGLOBAL, KNOB_TREENT, KNOB_FLATWALK, KNOB_GROUP, KNOB_TREECACHE, KNOB_PATHCACHE, KNOB_COUNT };
-const char *const kKnobNames[KNOB_COUNT] = {"nt", "ctas", "tables", "segcap", "entcap", "sortsmall", "parts", "bmglobal", "treent", "flatwalk", "group", "treecache", "pathcache"};
+enum ObsKnob : int { KNOB_NT = 0, KNOB_CTAS, KNOB_TABLES, KNOB_SEGCAP, KNOB_ENTCAP, KNOB_SORTSMALL, KNOB_PARTS, KNOB_BMGLOBAL, KNOB_TREENT, KNOB_FLATWALK, KNOB_GROUP, KNOB_TREECACHE, KNOB_PATHCACHE, KNOB_STEPMAP, KNOB_COUNT };
+const char *const kKnobNames[KNOB_COUNT] = {"nt", "ctas", "tables", "segcap", "entcap", "sortsmall", "parts", "bmglobal", "treent", "flatwalk", "group", "treecache", "pathcache", "stepmap"};
 const char *const kKnobEnv[KNOB_COUNT] = {"FL_OBS_NT", "FL_OBS_CTAS", "FL_OBS_TABLES", "FL_OBS_SEGCAP", "FL_OBS_ENTCAP", "FL_OBS_SORTSMALL", "FL_OBS_PARTS",
-                                          "FL_OBS_BMGLOBAL", "FL_OBS_TREENT", "FL_OBS_FLATWALK", "FL_OBS_GROUP", "FL_OBS_TREECACHE", "FL_OBS_PATHCACHE"};
+                                          "FL_OBS_BMGLOBAL", "FL_OBS_TREENT", "FL_OBS_FLATWALK", "FL_OBS_GROUP", "FL_OBS_TREECACHE", "FL_OBS_PATHCACHE", "FL_STEP_MAP"};
 std::atomic<int> g_knob[KNOB_COUNT];
 struct KnobInit {
     KnobInit() {
@@ -413,9 +413,21 @@ int fl_step(const FlBatch *b, const uint8_t *d_actions, int32_t *d_rewards, uint
     if (int rc = check_batch(b)) return rc;
     if (!d_actions || !d_rewards || !d_dones) return FL_ERR_BAD_ARG;
     const int nt = round_up((int)b->N, 32);
+    // MotionCheck through per-rail-cell tables from 32 agents on ("stepmap" knob: 0 never, 1 always); they need the rail index
+    // of fl_walk_tables and three words per rail cell of shared memory.  k_step at 425 agents: 44 -> 17 us; at 50 agents
+    // 17.2 -> 16.6 us (profiles/r02_aa_stepmap.txt)
+    int map_cells = 0;
+    const int want_map = knob(KNOB_STEPMAP);
+    if (want_map != 0 && (want_map > 0 || b->N >= 32) && b->ridx && b->walk_total && b->state_stride > 0) map_cells = (int)(b->state_stride / 4);
+    size_t smem = (4 * (size_t)b->N + 3 * (size_t)map_cells) * sizeof(int);
+    if (smem > (size_t)SMEM_MAX) { map_cells = 0; smem = 4 * (size_t)b->N * sizeof(int); }
+    if (smem > 48 * 1024) {
+        cudaError_t err = cudaFuncSetAttribute(k_step, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (err != cudaSuccess) return (int)err;
+    }
     {
         LaunchScope ls(K_STEP, (cudaStream_t)stream);
-        k_step<<<(unsigned)b->E, nt, 4 * b->N * sizeof(int), (cudaStream_t)stream>>>(*b, d_actions, d_rewards, d_dones, flags);
+        k_step<<<(unsigned)b->E, nt, smem, (cudaStream_t)stream>>>(*b, d_actions, d_rewards, d_dones, flags, map_cells);
     }
     return finish(cudaGetLastError());
 }

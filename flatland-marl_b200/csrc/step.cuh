@@ -78,14 +78,21 @@ __global__ void k_reset(FlBatch b, const uint8_t *__restrict__ mask, uint32_t fl
 // ---------------------------------------------------------------------------------------------
 // k_step: RailEnv.step (rail_env.py:501-632)
 // ---------------------------------------------------------------------------------------------
+// map_cells > 0: MotionCheck looks its neighbours up in per-rail-cell tables (O(N)) instead of comparing every pair of agents
+// (O(N^2): 40 us at 425 agents); map_cells = rail-cell capacity of the tables, which follow the four per-agent arrays.
 __global__ void __launch_bounds__(1024)
 k_step(FlBatch b, const uint8_t *__restrict__ actions, int32_t *__restrict__ rewards,
-       uint8_t *__restrict__ dones, uint32_t flags) {
+       uint8_t *__restrict__ dones, uint32_t flags, int map_cells) {
     const int e = blockIdx.x, N = (int)b.N, H = (int)b.H, W = (int)b.W, HW = H * W;
     const int i = threadIdx.x;
     const bool act = i < N;
     extern __shared__ int sm[];
     int *s_cur = sm, *s_nxt = sm + N, *s_rep = sm + 2 * N, *s_blk = sm + 3 * N;
+    int *m_rep = sm + 4 * N, *m_want = m_rep + map_cells, *m_out = m_want + map_cells;   // per rail cell, see MotionCheck below
+    const uint16_t *__restrict__ ridx = b.ridx + (size_t)e * b.ridx_stride;
+    const int R_env = map_cells > 0 ? (int)(b.walk_total[(size_t)e * 4] >> 2) : 0;       // 0: the rail index is not built
+    if (R_env > 0)
+        for (int k = i; k < R_env; k += blockDim.x) { m_rep[k] = 0; m_want[k] = 0x7fffffff; m_out[k] = 0; }
     const size_t ea = (size_t)e * N + (act ? i : 0);
     const uint16_t *__restrict__ g = b.grid + (size_t)e * b.grid_stride;
 
@@ -144,7 +151,20 @@ k_step(FlBatch b, const uint8_t *__restrict__ actions, int32_t *__restrict__ rew
         nxt_id = nr < 0 ? -1 - i : nr * W + nc;
         s_cur[i] = cur_id; s_nxt[i] = nxt_id; s_blk[i] = 0;
     }
-    __syncthreads();
+    // rail indices of the two cells (-1: private node); a cell outside the rail (an invalid world) sends the environment to
+    // the pairwise comparison, which needs no tables
+    int ri_cur = -1, ri_nxt = -1;
+    bool off_rail = false;
+    if (act && R_env > 0) {
+        if (r >= 0) { const unsigned v = ridx[r * W + c]; ri_cur = (int)v; off_rail |= v >= (unsigned)R_env; }
+        if (nr >= 0) {
+            const unsigned v = (nr < H && nc >= 0 && nc < W) ? (unsigned)ridx[nr * W + nc] : 0xFFFFu;
+            ri_nxt = (int)v; off_rail |= v >= (unsigned)R_env;
+        } else if (r >= 0) off_rail = true;        // a move off the top edge of the grid
+
+    }
+    const bool use_map = R_env > 0 && !__syncthreads_or(off_rail);           // (also orders the writes above)
+    if (!use_map) __syncthreads();
 
     // ---- MotionCheck (agent_chains.py:151-236) as a least fixpoint over CELL NODES:
     //        blocked(X) = some train on X stays | swaps | loses a contended cell | heads for a blocked node
@@ -153,6 +173,35 @@ k_step(FlBatch b, const uint8_t *__restrict__ actions, int32_t *__restrict__ rew
     //      the last one added, i.e. the highest handle (agent_chains.py:33) — its representative here.
     int rep_cur = i, rep_nxt = -1;
     bool sw = false;
+    if (use_map) {
+        // The same three facts from tables per rail cell.  m_rep[X]: highest handle standing on X (+1).  m_out[X]: bit m = a
+        // train on X wants to leave in direction m.  m_want[X]: lowest representative among the nodes that want to move onto X.
+        //   representative of my node / of my target: m_rep of the cell (an off-map train is its own node);
+        //   swap: a train on my target wants to leave it towards me, i.e. in the direction opposite to mine;
+        //   loser: somebody with a lower representative wants my target — trains of my own node share my representative and a
+        //   train that stays on the target does not "want" it, so the two exclusions of the pairwise test hold by construction.
+        if (act && ri_cur >= 0) atomicMax(&m_rep[ri_cur], i + 1);
+        __syncthreads();
+        if (act) {
+            if (ri_cur >= 0) rep_cur = m_rep[ri_cur] - 1;
+            if (nxt_id != cur_id) {
+                atomicMin(&m_want[ri_nxt], rep_cur);
+                if (ri_cur >= 0) atomicOr(&m_out[ri_cur], 1 << nd);
+            }
+            s_rep[i] = rep_cur;
+        }
+        __syncthreads();
+        if (act) {
+            rep_nxt = ri_nxt >= 0 ? m_rep[ri_nxt] - 1 : i;
+            bool loser = false;
+            if (nxt_id != cur_id) {
+                sw = ri_cur >= 0 && ((m_out[ri_nxt] >> (nd ^ 2)) & 1);
+                loser = m_want[ri_nxt] < rep_cur;
+            }
+            if (nxt_id == cur_id || sw || loser) s_blk[rep_cur] = 1;
+        }
+        __syncthreads();
+    } else {
     if (act) {
         for (int k = 0; k < N; k++) {              // shared-memory broadcasts, no bank conflicts
             const int ck = s_cur[k], nk = s_nxt[k];
@@ -172,6 +221,7 @@ k_step(FlBatch b, const uint8_t *__restrict__ actions, int32_t *__restrict__ rew
         if (nxt_id == cur_id || sw || loser) s_blk[rep_cur] = 1;
     }
     __syncthreads();
+    }
     // (racecheck warns about the loop below: s_blk flags only ever go 0 -> 1 and the loop runs to the fixpoint, so reading a
     // flag while another thread sets it only decides in which round the reader follows)
     while (true) {                                 // propagate along chains until nothing changes

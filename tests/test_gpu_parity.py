@@ -166,6 +166,22 @@ def test_cuda_matches_golden_and_oracle(golden, obs_plan, name, parts):
     assert_same(batch.dist_numpy(0)[: g["dist"].shape[0]], g["dist"], name + " reference distance map")
 
 
+@pytest.mark.parametrize("name", ["t02_l2_stacking", "t03_l2_stacking", "t03_l1_greedy", "t08_l0_greedy", "t00_l0_random"])
+def test_motion_check_through_rail_cell_tables(golden, obs_plan, name):
+    """k_step's MotionCheck looks neighbours up in per-rail-cell tables from 64 agents on; forced here ("stepmap" 1) on the
+    fixtures with stacked trains, contended cells, swaps and long chains, against the oracle and the reference's final state."""
+    obs_plan({"stepmap": 1})
+    g = golden(name)
+    n_steps = int(g["n_steps"])
+    rng = np.random.RandomState(321)
+    other = np.where(rng.rand(*g["actions"].shape) < 0.6, 2, rng.randint(0, 5, size=g["actions"].shape)).astype(np.uint8)
+    batch = run_against_oracle([g, g], [g["actions"], other], [g["sched"], g["sched"]], n_steps, check_every=4)
+    final = {k: g["tr_" + k][n_steps] for k in STATE_KEYS}
+    s = batch.state_numpy(0)
+    for k in STATE_KEYS:
+        assert_same(s[k], final[k], "%s final reference %s" % (name, k))
+
+
 def test_step_after_done_and_auto_reset(golden):
     import torch
     import flatland_marl_b200 as fb
