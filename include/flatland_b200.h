@@ -195,7 +195,8 @@ int fl_reset_ex(const FlBatch *b, const uint8_t *d_env_mask, uint32_t flags, voi
 /* Replaces RailEnv.step(action_dict) up to but excluding the observation
  * (flatland/envs/rail_env.py:501-632, step_utils/*, agent_chains.py MotionCheck).
  * d_actions [E][N] uint8 (FL_ACTION_ABSENT = key missing); d_rewards [E][N] int32;
- * d_dones [E][N+1] uint8, last column = "__all__". */
+ * d_dones [E][N+1] uint8, last column = "__all__".  From 32 agents on MotionCheck uses the rail index of fl_walk_tables
+ * (FlBatch.ridx, walk_total) when it is built; without it every pair of agents is compared, with the same result. */
 int fl_step(const FlBatch *b, const uint8_t *d_actions, int32_t *d_rewards, uint8_t *d_dones,
             uint32_t flags, void *stream);
 
@@ -218,8 +219,12 @@ int64_t fl_observe_ws_words(const FlBatch *b);
  * (CTAs per SM the plan is cut for), "tables" (bit mask of the static tables staged in shared memory), "segcap", "entcap"
  * (capacities of the shared-memory segment pool / entry array, to force the global spill paths), "sortsmall" (largest bucket
  * sorted by one thread), "parts" (CTAs per environment of the tree kernel; 0 = fused kernel), "treent" (threads per CTA of the
- * tree kernel), "bmglobal" (1: the tree kernel reads the time-slot filter from the workspace instead of shared memory).  The same knobs are read ONCE from the
- * environment variables FL_OBS_<KEY> when the library is loaded; fl_observe itself never calls getenv.
+ * tree kernel), "bmglobal" (1: the tree kernel reads the time-slot filter from the workspace instead of shared memory),
+ * "flatwalk" (bit 0 / 1: path segments walked by warps as flat lists in the counting / scatter pass), "group" (environments
+ * per CTA of the fused kernel, 1 = one CTA per environment), "treecache" / "pathcache" (0: FlBatch.tree_cache / path_cache
+ * are not used), and one knob of fl_step: "stepmap" (MotionCheck through per-rail-cell tables: 0 never, 1 always; default from
+ * 32 agents on).  The same knobs are read ONCE from the environment variables FL_OBS_<KEY> (FL_STEP_MAP for "stepmap") when the
+ * library is loaded; fl_observe itself never calls getenv.
  * Returns 0, or FL_ERR_BAD_ARG for an unknown key. */
 int fl_observe_override(const char *key, int value);
 
