@@ -14,7 +14,11 @@ POLICY_SRC = os.path.join(POLICY_DIR, "policy.cu")
 POLICY_HDR = os.path.join(ROOT, "include", "flatland_policy_b200.h")
 POLICY_LIB = os.path.join(POLICY_DIR, "libflatland_policy_b200.so")
 
-NVCC_FLAGS = ["--split-compile", "0", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+# (nvcc's --split-compile cuts the build from 3 min to 1, but its output differs from run to run — in size by tens of per
+# cent; the shipped libraries are built without it so that a rebuild from these sources gives the same bytes.  Development
+# builds may set FL_NVCC_SPLIT=1.)
+NVCC_FLAGS = (["--split-compile", "0"] if os.environ.get("FL_NVCC_SPLIT") == "1" else []) + \
+             ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "--expt-extended-lambda", "-Xcompiler", "-fPIC", "-shared"]
 
 
